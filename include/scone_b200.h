@@ -1,0 +1,173 @@
+/* scone_b200 -- C ABI of the B200 transport engine.
+ *
+ * SCONE (Fortran 2008) has no FFI today. The seam this library plugs into is the body of the
+ * `gen` loop of the physics packages: instead of calling transOp%transport / collOp%collide /
+ * tally%report* once per particle from inside an OpenMP loop, the package calls this library
+ * once per cycle through a thin iso_c_binding shim (INTEGRATION.md shows the shim).
+ *   PhysicsPackages/eigenPhysicsPackage_class.f90:203-307   (cycle body that is replaced)
+ *   TransportOperator/transportOperator_inter.f90:105-130    (transport)
+ *   CollisionOperator/CollisionProcessors/collisionProcessor_inter.f90:114-195 (collide)
+ *   Tallies/tallyAdmin_class.f90:466-794                     (report*, reportCycleEnd)
+ *   ParticleObjects/particleDungeon_class.f90:431-602        (normSize_Repr)
+ *
+ * Conventions: plain pointers and sizes only; all indices that cross the boundary are 1-based
+ * exactly as SCONE holds them (matIdx, uniIdx, surfIdx, localID, uniqueID, group G);
+ * reals are IEEE binary64, integers int32 unless stated; arrays are caller-owned and copied.
+ * Every function returns 0 on success, non-zero on error; sb_last_error() gives the text
+ * (the shim forwards it to fatalError, SharedModules/errors_mod.f90:32-69).
+ * One engine handle drives one GPU and is not re-entrant.
+ */
+#ifndef SCONE_B200_H
+#define SCONE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb_engine sb_engine;
+
+/* ---- special material codes: SharedModules/universalVariables.f90:43-47 ---- */
+#define SB_OUTSIDE_MAT 0
+#define SB_VOID_MAT    2147483647
+#define SB_UNDEF_MAT   2147483646
+#define SB_OVERLAP_MAT 2147483645
+
+/* ---- surfaces: Geometry/Surfaces/ ------------------------------------------------------
+ * par[8] per surface:
+ *   x/y/zPlane      : par[0] = a0
+ *   plane           : par[0..2] = unit normal, par[3] = offset
+ *   sphere          : par[0..2] = origin, par[3] = r, par[4] = r*r
+ *   x/y/zCylinder   : par[0..2] = origin, par[3] = r, par[4] = r*r
+ *   box             : par[0..2] = origin, par[3..5] = halfwidth
+ *   x/y/zSquareCyl. : par[0..2] = origin, par[3..5] = halfwidth (axis component unused)
+ *   par[6] = surface tolerance (surface_inter.f90 surf_tol)                                  */
+enum { SB_SURF_XPLANE = 1, SB_SURF_YPLANE = 2, SB_SURF_ZPLANE = 3, SB_SURF_PLANE = 4, SB_SURF_SPHERE = 5,
+       SB_SURF_XCYL = 6, SB_SURF_YCYL = 7, SB_SURF_ZCYL = 8, SB_SURF_BOX = 9,
+       SB_SURF_XSQCYL = 10, SB_SURF_YSQCYL = 11, SB_SURF_ZSQCYL = 12 };
+#define SB_SURF_NPAR 8
+
+/* ---- universes: Geometry/Universes/ ------------------------------------------------------
+ * dpar[32] per universe: [0..2] origin, [3..11] rotation matrix (row major, r' = R r),
+ *   lattice: [12..14] pitch, [15..17] corner, [18..20] a_bar, [21..23] outline halfwidth
+ * ipar[8] per universe: [0] rotated?, [1] global transform?,
+ *   root   : [2] border surfIdx
+ *   pin    : [2] number of annuli N, [3] offset into aux_d of { r_sq[N], tol[N] }
+ *   lattice: [2..4] sizeN, [5] outLocalID, [6] offset mode (0 none, 1 all cells, 2 per-cell map),
+ *            [7] offset into aux_i of the per-cell map (mode 2; outLocalID entries)
+ *   cell   : [2] number of cells, [3] offset into aux_i of the cellIdx list, [4] checkOverlap */
+enum { SB_UNI_ROOT = 1, SB_UNI_PIN = 2, SB_UNI_LAT = 3, SB_UNI_CELL = 4 };
+#define SB_UNI_NDPAR 32
+#define SB_UNI_NIPAR 8
+
+typedef struct sb_geom_flat {
+  int32_t n_surf;  const int32_t* surf_type;  const double* surf_par;      /* [n_surf][8]            */
+  int32_t n_cell;  const int32_t* cell_off;   const int32_t* cell_surf;    /* CSR, signed surfIdx     */
+  int32_t n_uni;   const int32_t* uni_type;   const int32_t* uni_ipar;  const double* uni_dpar;
+  int32_t n_aux_d; const double*  aux_d;
+  int32_t n_aux_i; const int32_t* aux_i;
+  int32_t n_graph; const int32_t* graph_idx;  const int32_t* graph_id;     /* geomGraph_class.f90:21-24 */
+  int32_t root_idx, border_idx;                                            /* csg_class.f90 rootIdx, borderIdx */
+  int32_t bc[6];                                                           /* (-x +x -y +y -z +z): 0 vacuum 1 reflective 2 periodic */
+} sb_geom_flat;
+
+/* ---- multigroup data: NuclearData/mgNeutronData/baseMgNeutron/ ---------------------------
+ * data  : [n_mat][n_g][6] = Fortran data(6,nG) of each material, rows TOTAL, IESCATTER, CAPTURE,
+ *         FISSION, NU_FISSION, KAPPA_FISSION (baseMgNeutronMaterial_class.f90:32-37)
+ * P0/prod/P1 : [n_mat][n_g][n_g] = Fortran P0(G_out,G_in) storage order (G_out fastest);
+ *         P1 already normalised as multiScatterP1MG does (P1/P0*3); NULL for P0 scattering
+ * chi   : [n_mat][n_g] ; fissile : [n_mat] ; majorant : [n_g] (initMajorant)                 */
+typedef struct sb_mg_flat {
+  int32_t n_mat, n_g;
+  const double* data; const double* P0; const double* prod; const double* P1; const double* chi;
+  const int32_t* fissile; const double* majorant; double collision_xs;
+} sb_mg_flat;
+
+/* ---- tallies: Tallies/TallyClerks/collisionClerk_class.f90, TallyMaps/, TallyResponses/ ---- */
+enum { SB_MAP_SPACE = 1, SB_MAP_MATERIAL = 2, SB_MAP_ENERGY = 3 };
+enum { SB_GRID_LIN = 1, SB_GRID_LOG = 2, SB_GRID_UNSTRUCT = 3 };
+typedef struct sb_map1d {
+  int32_t type, axis /*0 x,1 y,2 z*/, grid, n_bins;
+  double first, step;             /* grid%bins(1), grid%step (lin/log)                        */
+  const double* bounds;           /* n_bins+1 boundaries (unstruct) or NULL                   */
+  const int32_t* mat_bin;         /* materialMap: bin of matIdx m at [m-1], size n_mat; NULL  */
+  int32_t default_bin;            /* materialMap default (0 = not scored)                     */
+} sb_map1d;
+#define SB_MAX_MAPS 4
+#define SB_MAX_RESP 8
+typedef struct sb_clerk {
+  int32_t n_maps; sb_map1d maps[SB_MAX_MAPS];   /* multiMap order; 0 maps = single bin        */
+  int32_t n_resp; int32_t resp_mt[SB_MAX_RESP]; /* 0 = fluxResponse, else SCONE macro MT (-1..) */
+  int32_t handle_virtual;
+} sb_clerk;
+
+enum { SB_TRACK_DT = 0, SB_TRACK_ST = 1, SB_TRACK_HT = 2 };
+typedef struct sb_options {
+  int32_t tracking; double ht_cutoff; int32_t st_cache;
+  int32_t max_pop;          /* capacity of the device banks is 2*max_pop as eigenPP allocates dungeons */
+  int32_t threads_per_block, blocks_per_sm;   /* 0 = engine default                            */
+} sb_options;
+
+/* result of one cycle, all of it computed on the device */
+typedef struct sb_cycle_result {
+  int32_t n_start;            /* histories transported                                         */
+  int32_t n_sites;            /* fission sites banked before normalisation                     */
+  double  start_wgt, end_wgt; /* popWeight of this / next cycle dungeon (keffAnalogClerk)      */
+  double  imp_prod, imp_abs, scatter_prod, ana_leak;  /* keffImplicitClerk bins of the cycle   */
+  double  k_analog, k_implicit;                        /* per-cycle estimates                   */
+  double  k_cum, k_cum_std;   /* cumulative mean of this phase's attachment clerk = k_new      */
+  int64_t n_segments, n_collisions;
+  int32_t error;              /* device-side fatal condition (SB_ERR_*), 0 if none             */
+} sb_cycle_result;
+enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
+       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7 };
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+int  sb_create(sb_engine** h, int device);
+void sb_destroy(sb_engine* h);
+const char* sb_last_error(sb_engine* h);
+/* number of kernels of this library launched so far by this handle */
+int64_t sb_launch_count(sb_engine* h);
+
+/* ---- model load (replaces nothing at run time; consumes what csg%init / database%init built) */
+int sb_load_geometry(sb_engine* h, const sb_geom_flat* g);
+int sb_load_mg_data(sb_engine* h, const sb_mg_flat* d);
+/* phase: 0 inactive, 1 active. norm_clerk = 1-based clerk whose first bin normalises (0 = none) */
+int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n_clerks, int norm_clerk, double norm_val);
+int sb_set_options(sb_engine* h, const sb_options* o);
+
+/* ---- banks (particleDungeon) ---------------------------------------------------------------
+ * host SoA <-> device "this cycle" bank; r, dir are [n][3]                                   */
+int sb_bank_upload(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G);
+int sb_bank_download(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, int32_t* G);
+int sb_bank_size(sb_engine* h);
+/* fissionSource%generate on the device (ParticleObjects/Source/fissionSource_class.f90:149-271) */
+int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offset);
+
+/* ---- the cycle ------------------------------------------------------------------------------
+ * Transports every history of the current bank to its death (transport + collide + tallies +
+ * fission-site banking), closes the cycle's tallies (reduceBins, closeCycle with normalisation,
+ * k estimators) and leaves the brood-sorted next-cycle bank on the device.
+ * rng_state = state of the package RNG at cycle start (pRNG); history n of this engine uses
+ * rng_state skipped by 152917*(history_offset+n), eigenPhysicsPackage_class.f90:216-218.       */
+int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, sb_cycle_result* res);
+/* particleDungeon%normSize_Repr(totPop, pRNG) on the next-cycle bank, then swap banks.
+ * rng_state = pRNG state after the stride(totalPop+1) of the cycle.                            */
+int sb_resample(sb_engine* h, int tot_pop, uint64_t rng_state);
+
+/* ---- results (scoreMemory) ---------------------------------------------------------------- */
+int64_t sb_tally_size(sb_engine* h, int phase);
+int sb_tally_read(sb_engine* h, int phase, double* csum, double* csum2, int32_t* batch_n);
+int sb_tally_last_bins(sb_engine* h, int phase, double* bins);   /* BIN column of the last closed cycle, before normalisation */
+
+/* ---- batch queries used by the parity tests (same device functions as the cycle kernel) ---- */
+/* placeCoord / whatIsAt for n points; if dist != NULL teleport by dist[i] first (geometryStd teleport) */
+int sb_geom_query(sb_engine* h, int64_t n, double* r, double* dir, const double* dist, int32_t* mat, int32_t* unique_id);
+int sb_mg_query(sb_engine* h, int64_t n, const int32_t* mat, const int32_t* G, double* total, double* majorant);
+int sb_rng_query(int64_t n, const uint64_t* state, const int64_t* skip, uint64_t* out_state, double* out_real);
+int sb_math_query(int64_t n, const double* x, double* log_x, double* sin_x, double* cos_x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

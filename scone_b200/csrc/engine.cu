@@ -1,0 +1,1204 @@
+// scone_b200 engine: CUDA kernels for sm_100a + the C ABI of include/scone_b200.h.
+//
+// Design (DESIGN.md has the long form):
+//  * k_histories  - persistent event loop. One lane owns one history at a time and keeps its state in
+//                   registers; every loop iteration is one event round (tentative-flight, then collision
+//                   for the lanes whose flight ended in a real collision); a lane whose history died is
+//                   refilled from a warp-private chunk of the bank (warp-level compaction by ballot), chunks
+//                   are claimed with one global atomic. Tables (geometry graph + MG data) are staged once
+//                   per CTA into shared memory with a bulk async copy (TMA, cp.async.bulk) when they fit.
+//  * fission bank - sites are appended with one atomic per warp per round (warp scan of the counts), keyed
+//                   (broodID, seq); k_scan* + k_sort_sites place them in the reference's stable brood order.
+//  * tallies      - per-history k-eff scores are written per history and reduced in a fixed tree
+//                   (bitwise reproducible); map tallies use f64 L2 atomics (red.global.add.f64).
+//  * resampling   - normSize_Repr: per-site LCG numbers by skip-ahead, exact k-th smallest by a two-level
+//                   radix select, keep/duplicate flags, scan, scatter.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sb_device.cuh"
+
+using namespace sbd;
+
+// ------------------------------------------------------------------------------------------------
+// device data structures
+// ------------------------------------------------------------------------------------------------
+struct Bank {            // particleDungeon as structure of arrays
+  double *rx, *ry, *rz, *ux, *uy, *uz, *w;
+  int *G, *brood, *seq;
+};
+
+struct CycleDev {        // small device-resident record of the running cycle
+  int nStart, nSites, nextHistory, error;
+  int selBin, selRank, nCand, nNew;
+  unsigned long long thrState;
+  double thrReal;
+  double startWgt, endWgt, impProd, impAbs, scatProd, anaLeak, kAnalog, kImplicit, normFactor;
+  long long nSeg, nColl;
+  // cumulative k of the attachment clerks: [phase] CSUM, CSUM2, batches
+  double kCsum[2], kCsum2[2]; int kBatches[2];
+  double kCum, kCumStd;
+};
+
+struct CycleArgs {
+  Model M; const char* blob; int useSmem;
+  int n; Bank in; Bank out; int cap;
+  int *nsites; double *hProd, *hAbs, *hLeak, *hScat; int *hSeg, *hColl;
+  double* bins; int phase;
+  uint64_t rng0; int histOffset; double k_eff;
+  CycleDev* cd; int chunk;
+};
+
+#define CUDA_OK(call)                                                                         \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// bulk async copy global -> shared (TMA 1-D) with an mbarrier; falls back to a plain loop if the
+// size is not a multiple of 16 (the blob is padded so it always is)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stageBlob(char* smem, const char* gsrc, int bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
+    // one bulk copy per <= 64 KiB piece keeps each request small
+    int off = 0;
+    while (off < bytes) {
+      int piece = min(bytes - off, 32768);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + off), "l"(gsrc + off), "r"(piece), "r"(barAddr) : "memory");
+      off += piece;
+    }
+  }
+  {
+    unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(barAddr) : "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scoring of one collision (virtual or real) for the active-cycle tallies
+//   tallyAdmin%reportInColl -> collisionClerk%reportInColl (collisionClerk_class.f90:192-244)
+//                           -> keffImplicitClerk%reportInColl (keffImplicitClerk_class.f90:180-236)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scoreInColl(const CycleArgs& a, const Tables& T, const char* base, const double r[3], int mat, int G,
+                                            double w, double trackXS, bool virt, double& sProd, double& sAbs) {
+  // in void macroResponse returns 0 and keffImplicitClerk returns early; fluxResponse still scores
+  const bool isVoid = (mat == SB_VOID_MAT);
+  const double* x = isVoid ? T.xs : mgRow(a.M, T, mat, G);
+  const bool fissile = isVoid ? false : (T.fissile[mat - 1] != 0);
+  const double flux = w / trackXS;
+  const int nC = a.M.nClerk[a.phase];
+  const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
+  for (int c = 0; c < nC; ++c) {
+    const DClerk& k = cl[c];
+    if (!k.handleVirtual && virt) continue;
+    int bin = clerkBin(k, base, r, mat);
+    if (bin == 0) continue;
+    if (isVoid && !k.handleVirtual) continue;
+    double f = k.handleVirtual ? flux : w / (x[XS_TOTAL] + 0.0);
+    int addr = k.addr + k.nResp * (bin - 1) - 1;      // 0-based slot of response 1
+    for (int i = 0; i < k.nResp; ++i) {
+      double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : mgResponse(x, fissile, k.respMT[i]));
+      double s = resp * f;
+      if (s != 0.0) atomicAdd(a.bins + addr + i, s);
+    }
+  }
+  if (a.phase == 1 && !isVoid) {
+    double nuf = fissile ? x[XS_NUFISSION] : 0.0, fis = fissile ? x[XS_FISSION] : 0.0;
+    sProd += nuf * flux;
+    sAbs += (x[XS_CAPTURE] + fis) * flux;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The history kernel (delta tracking + neutronMGstd collisions)
+//   eigenPhysicsPackage_class.f90:213-252   history loop
+//   transportOperatorDT_class.f90:47-130    deltaTracking
+//   collisionProcessor_inter.f90:114-195 + neutronMGstd_class.f90:85-297   collide
+// ------------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) char g_smem[];
+
+__global__ void __launch_bounds__(256, 2) k_histories(const CycleArgs a) {
+  __shared__ __align__(8) uint64_t s_bar;
+  const char* base = a.blob;
+  if (a.useSmem) { stageBlob(g_smem, a.blob, a.M.blobBytes, &s_bar); base = g_smem; }
+  const Tables T = bind(a.M, base);
+  const Model& M = a.M;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned ltMask = (1u << lane) - 1u;
+
+  // warp-private chunk of bank indices [cnext, cend)
+  int cnext = 0, cend = 0; bool exhausted = false;
+
+  // history state (registers)
+  bool alive = false;
+  int hi = -1;
+  double r[3], u[3], w = 0.0, w0 = 0.0; uint64_t rng = 0; int G = 0, mat = 0, uid = 0;
+  double trackXS = 1.0, majorant_inv = 1.0;
+  int nSite = 0, nSeg = 0, nColl = 0;
+  double sProd = 0.0, sAbs = 0.0, sLeak = 0.0, sScat = 0.0;
+  bool needMaj = true;
+
+  for (;;) {
+    // ---------------- refill dead lanes from the warp's chunk --------------------------------
+    unsigned need = __ballot_sync(FULL, !alive);
+    if (need) {
+      if (cnext >= cend && !exhausted) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(&a.cd->nextHistory, a.chunk);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= a.n) { exhausted = true; cnext = cend = 0; }
+        else { cnext = b; cend = min(b + a.chunk, a.n); }
+      }
+      int my = cnext + __popc(need & ltMask);
+      if (!alive && my < cend) {
+        hi = my;
+        r[0] = a.in.rx[hi]; r[1] = a.in.ry[hi]; r[2] = a.in.rz[hi];
+        u[0] = a.in.ux[hi]; u[1] = a.in.uy[hi]; u[2] = a.in.uz[hi];
+        w = a.in.w[hi]; w0 = w; G = a.in.G[hi];
+        rng = rng_skip(a.rng0, RNG_STRIDE * (int64_t)(a.histOffset + hi + 1));
+        if (!geomPlace(M, T, r, u, mat, uid)) atomicMax(&a.cd->error, SB_ERR_NEST);
+        nSite = 0; nSeg = 0; nColl = 0; sProd = 0.0; sAbs = 0.0; sLeak = 0.0; sScat = 0.0;
+        needMaj = true;
+        alive = true;
+      }
+      cnext = min(cend, cnext + __popc(need));
+      if (exhausted && !__any_sync(FULL, alive)) break;
+    }
+
+    // ---------------- event: tentative flight (delta tracking) --------------------------------
+    bool realColl = false;
+    bool died = false;
+    if (alive) {
+      if (needMaj) { trackXS = mgMajorant(M, T, G); majorant_inv = 1.0 / trackXS; needMaj = false; }
+      double distance = -sbm::log(rng_get(rng)) * majorant_inv;
+      geomTeleport(M, T, r, u, distance, mat, uid);
+      ++nSeg;
+      if (mat == SB_OUTSIDE_MAT) { sLeak += w; died = true; }
+      else if (mat == SB_VOID_MAT) scoreInColl(a, T, base, r, mat, G, w, trackXS, true, sProd, sAbs);
+      else if (mat == SB_UNDEF_MAT) { atomicMax(&a.cd->error, SB_ERR_UNDEF_MAT); died = true; }
+      else if (mat == SB_OVERLAP_MAT) { atomicMax(&a.cd->error, SB_ERR_OVERLAP_MAT); died = true; }
+      else {
+        double sigmaT = mgRow(M, T, mat, G)[XS_TOTAL] + 0.0;
+        if (rng_get(rng) < sigmaT * majorant_inv) realColl = true;
+        else scoreInColl(a, T, base, r, mat, G, w, trackXS, true, sProd, sAbs);
+      }
+    }
+
+    // ---------------- event: collision, part 1 (channel + number of fission sites) --------------
+    int MT = 0, nNew = 0;
+    const double* x = nullptr;
+    if (realColl) {
+      x = mgRow(M, T, mat, G);
+      const bool fissile = T.fissile[mat - 1] != 0;
+      double rAlpha = rng_get(rng);                       // alpha-absorption test always draws (probAlpha = 0)
+      (void)rAlpha;
+      double rr = rng_get(rng);
+      {                                                   // neutronMacroXSs%invert (neutronXsPackages_class.f90:211-250)
+        int C = 1;
+        double xs = x[XS_TOTAL] * rr - 0.0;
+        if (xs > 0.0) C += 1;
+        xs = xs - x[XS_IESCATTER];
+        if (xs > 0.0) C += 1;
+        xs = xs - x[XS_CAPTURE];
+        if (xs > 0.0) C += 1;
+        MT = C;                                           // 1 elastic, 2 inelastic, 3 capture, 4 fission
+      }
+      scoreInColl(a, T, base, r, mat, G, w, trackXS, false, sProd, sAbs);
+      ++nColl;
+      if (fissile) {                                      // neutronMGstd implicit (:131-199)
+        double rand1 = rng_get(rng);
+        nNew = (int)(fabs((w * x[XS_NUFISSION]) / (w0 * x[XS_TOTAL] * a.k_eff)) + rand1);
+        if (nNew < 0) nNew = 0;
+      }
+    }
+
+    // ---------------- warp-aggregated allocation of fission-bank slots -------------------------
+    int slot = 0;
+    unsigned spawn = __ballot_sync(FULL, nNew > 0);
+    if (spawn) {
+      int inc = nNew;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+      int total = __shfl_sync(FULL, inc, 31);
+      int b = 0;
+      if (lane == 0) b = atomicAdd(&a.cd->nSites, total);
+      b = __shfl_sync(FULL, b, 0);
+      slot = b + inc - nNew;
+      if (b + total > a.cap) { atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW); nNew = -nNew; }
+    }
+
+    // ---------------- collision, part 2 (sites, then the sampled channel) ----------------------
+    if (realColl) {
+      const int nDraw = nNew < 0 ? -nNew : nNew;
+      const double wSite = fsign(w0, w);
+      for (int i = 0; i < nDraw; ++i) {
+        double mu, phi;
+        int Gout = mgFissionSample(M, T, mat, mu, phi, rng);
+        if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = 1; }
+        double d[3] = {u[0], u[1], u[2]};
+        rotateVector(d, mu, phi);
+        if (nNew > 0) {
+          int s = slot + i;
+          a.out.rx[s] = r[0]; a.out.ry[s] = r[1]; a.out.rz[s] = r[2];
+          a.out.ux[s] = d[0]; a.out.uy[s] = d[1]; a.out.uz[s] = d[2];
+          a.out.w[s] = wSite; a.out.G[s] = Gout; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
+        }
+      }
+      nSite += nDraw;
+      if (MT == 2) {                                      // inelastic (:221-252), multiScatterMG%sampleOut
+        const double* P0 = T.P0 + ((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG;
+        double rem = rng_get(rng) * x[XS_IESCATTER];
+        int Gout = 0;
+        for (int g = 1; g <= M.nG; ++g) { rem = rem - P0[g - 1]; if (rem < 0.0) { Gout = g; break; } }
+        if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = G; }
+        double mu;
+        if (M.isP1) mu = sampleLegendreP1(T.P1[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)], rng);
+        else mu = 2.0 * rng_get(rng) - 1.0;
+        double phi = TWO_PI * rng_get(rng);
+        double w_mul = T.prod[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)];
+        double wPre = w;
+        G = Gout; needMaj = true;
+        w = w * w_mul;
+        rotateVector(u, mu, phi);
+        double sc = fmax(w - wPre, 0.0);                   // keffImplicitClerk%reportOutColl
+        if (sc > 0.0) sScat += sc;
+      } else if (MT == 3 || MT == 4) {
+        died = true;                                       // capture / fission: history ends (ABS_FATE)
+      }
+      // MT == 1 (elastic) cannot be selected for MG data (elasticScatter = 0): "Do nothing"
+    }
+
+    if (died) {
+      a.nsites[hi] = nSite;
+      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
+      a.hSeg[hi] = nSeg; a.hColl[hi] = nColl;
+      alive = false;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of int32 (3 kernels) -- used for brood offsets and resampling compaction
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8;                  // per thread
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ int blockExclusiveScan(int v, int* sWarp, int& blockTotal) {
+  const unsigned FULL = 0xffffffffu;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) sWarp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int ws = (lane < (int)(blockDim.x >> 5)) ? sWarp[lane] : 0;
+    int winc = ws;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, winc, d); if (lane >= d) winc += t; }
+    sWarp[lane] = winc - ws;                   // exclusive warp offsets
+    if (lane == 31) sWarp[32] = winc;
+  }
+  __syncthreads();
+  int res = sWarp[wid] + inc - v;
+  blockTotal = sWarp[32];
+  __syncthreads();
+  return res;
+}
+
+// nPtr: device pointer to the element count (so no host sync is needed); nMax bounds the grid
+__global__ void k_scan_reduce(const int* in, const int* nPtr, int* tileSums) {
+  __shared__ int sWarp[33];
+  int n = *nPtr;
+  int tile = blockIdx.x;
+  if ((long long)tile * SCAN_TILE >= n) { return; }
+  int sum = 0;
+  int b = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) if (b + i < n) sum += in[b + i];
+  int tot; blockExclusiveScan(sum, sWarp, tot);
+  if (threadIdx.x == 0) tileSums[tile] = tot;
+}
+__global__ void k_scan_tiles(int* tileSums, const int* nPtr, int* totalOut) {
+  __shared__ int sWarp[33];
+  __shared__ int carry;
+  int n = *nPtr;
+  int nTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b = 0; b < nTiles; b += blockDim.x) {
+    int i = b + threadIdx.x;
+    int v = (i < nTiles) ? tileSums[i] : 0;
+    int tot; int ex = blockExclusiveScan(v, sWarp, tot);
+    int c = carry;
+    if (i < nTiles) tileSums[i] = c + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && totalOut) *totalOut = carry;
+}
+__global__ void k_scan_apply(const int* in, const int* nPtr, const int* tileSums, int* out) {
+  __shared__ int sWarp[33];
+  int n = *nPtr;
+  int tile = blockIdx.x;
+  if ((long long)tile * SCAN_TILE >= n) return;
+  int b = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS]; int sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (b + i < n) ? in[b + i] : 0; sum += v[i]; }
+  int tot; int ex = blockExclusiveScan(sum, sWarp, tot) + tileSums[tile];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { if (b + i < n) out[b + i] = ex; ex += v[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fission bank ordering: particleDungeon%sortByBroodID (particleDungeon_class.f90:923-981) is a
+// stable counting sort by broodID; with the per-history site counts known, the destination of site
+// (brood, seq) is offset[brood] + seq.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sort_sites(Bank src, Bank dst, const int* offsets, const CycleDev* cd, int cap) {
+  int n = min(cd->nSites, cap);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    int b = src.brood[s];
+    int d = offsets[b] + src.seq[s];
+    dst.rx[d] = src.rx[s]; dst.ry[d] = src.ry[s]; dst.rz[d] = src.rz[s];
+    dst.ux[d] = src.ux[s]; dst.uy[d] = src.uy[s]; dst.uz[d] = src.uz[s];
+    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.brood[d] = b; dst.seq[d] = src.seq[s];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic reduction of the per-history scores (fixed tiling, fixed tree)
+// ------------------------------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 592;      // 4 per SM on 148 SMs; the tiling is a constant of the algorithm
+constexpr int RED_THREADS = 256;
+struct RedOut { double prod, abs, leak, scat, wgt; long long seg, coll; };
+
+__device__ __forceinline__ double warpSum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ long long warpSumLL(long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ void blockReduce7(double v[5], long long c[2], RedOut* out) {
+  __shared__ double sd[5][RED_THREADS / 32];
+  __shared__ long long sc[2][RED_THREADS / 32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { double s = warpSum(v[k]); if (lane == 0) sd[k][wid] = s; }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { long long s = warpSumLL(c[k]); if (lane == 0) sc[k][wid] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    RedOut o = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < RED_THREADS / 32; ++i) {
+      o.prod += sd[0][i]; o.abs += sd[1][i]; o.leak += sd[2][i]; o.scat += sd[3][i]; o.wgt += sd[4][i];
+      o.seg += sc[0][i]; o.coll += sc[1][i];
+    }
+    *out = o;
+  }
+}
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(const CycleArgs a, RedOut* partial) {
+  // contiguous slice per block, strided by thread inside the slice: fixed order for fixed n
+  int n = a.n;
+  int per = (n + RED_BLOCKS - 1) / RED_BLOCKS;
+  int b0 = blockIdx.x * per, b1 = min(n, b0 + per);
+  double v[5] = {0, 0, 0, 0, 0}; long long c[2] = {0, 0};
+  for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) {
+    v[0] += a.hProd[i]; v[1] += a.hAbs[i]; v[2] += a.hLeak[i]; v[3] += a.hScat[i]; v[4] += a.in.w[i];
+    c[0] += a.hSeg[i]; c[1] += a.hColl[i];
+  }
+  blockReduce7(v, c, partial + blockIdx.x);
+}
+// sum of weights of the (sorted) next-cycle bank: popWeight for keffAnalogClerk%reportCycleEnd
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_wgt(const double* w, const CycleDev* cd, int cap, double* partial) {
+  __shared__ double sd[RED_THREADS / 32];
+  int n = min(cd->nSites, cap);
+  int per = (n + RED_BLOCKS - 1) / RED_BLOCKS;
+  int b0 = blockIdx.x * per, b1 = min(n, b0 + per);
+  double v = 0.0;
+  for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) v += w[i];
+  v = warpSum(v);
+  if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < RED_THREADS / 32; ++i) s += sd[i]; partial[blockIdx.x] = s; }
+}
+
+// tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
+//   keffAnalogClerk%closeCycle (keffAnalogClerk_class.f90:156-176), keffImplicitClerk%closeCycle (:292-312)
+__global__ void k_close_cycle_head(const RedOut* partial, const double* wPartial, CycleDev* cd, int phase, double kNorm,
+                                   const double* bins, int normAddr, double normVal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  RedOut o = {0, 0, 0, 0, 0, 0, 0}; double endW = 0.0;
+  for (int i = 0; i < RED_BLOCKS; ++i) {
+    o.prod += partial[i].prod; o.abs += partial[i].abs; o.leak += partial[i].leak; o.scat += partial[i].scat; o.wgt += partial[i].wgt;
+    o.seg += partial[i].seg; o.coll += partial[i].coll; endW += wPartial[i];
+  }
+  cd->startWgt = o.wgt; cd->endWgt = endW;
+  cd->impProd = o.prod; cd->impAbs = o.abs; cd->anaLeak = o.leak; cd->scatProd = o.scat;
+  cd->nSeg = o.seg; cd->nColl = o.coll;
+  cd->kAnalog = endW / o.wgt * kNorm;
+  cd->kImplicit = o.prod / (o.abs + o.leak - o.scat);
+  double k = (phase == 0) ? cd->kAnalog : cd->kImplicit;
+  cd->kCsum[phase] = cd->kCsum[phase] + k;
+  cd->kCsum2[phase] = cd->kCsum2[phase] + k * k;
+  cd->kBatches[phase] += 1;
+  int N = cd->kBatches[phase];                              // scoreMemory%getResult (scoreMemory_class.f90:537-573)
+  double mean = cd->kCsum[phase] / N;
+  double inv_N = 1.0 / N, inv_Nm1 = (N != 1) ? 1.0 / (N - 1) : 1.0;
+  double sd = cd->kCsum2[phase] * inv_N * inv_Nm1 - mean * mean * inv_Nm1;
+  cd->kCum = mean; cd->kCumStd = sqrt(sd);
+  double nf = 1.0;
+  if (normAddr > 0) {
+    double sc = bins[normAddr - 1];
+    if (sc == 0.0) { atomicMax(&cd->error, SB_ERR_NORM); sc = 1.0; }
+    nf = normVal / sc;
+  }
+  cd->normFactor = nf;
+}
+// scoreMemory%closeCycle (scoreMemory_class.f90:309-342)
+__global__ void k_close_cycle_bins(double* bins, double* lastBins, double* csum, double* csum2, int nBins, const CycleDev* cd) {
+  double nf = cd->normFactor;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nBins; i += gridDim.x * blockDim.x) {
+    double b = bins[i];
+    double res = b * nf;
+    lastBins[i] = b;
+    bins[i] = 0.0;
+    csum[i] = csum[i] + res;
+    csum2[i] = csum2[i] + res * res;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// normSize_Repr (particleDungeon_class.f90:431-602) on the device, single rank
+// ------------------------------------------------------------------------------------------------
+constexpr int RN_CHUNK = 16;
+// rn_j = j-th number of the LCG stream started at `state0` (j = 1..n), stored as the integer state
+__global__ void k_rn_generate(unsigned long long* rn, const CycleDev* cd, int cap, uint64_t state0) {
+  int n = min(cd->nSites, cap);
+  int nChunks = (n + RN_CHUNK - 1) / RN_CHUNK;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nChunks; c += gridDim.x * blockDim.x) {
+    int j0 = c * RN_CHUNK;
+    uint64_t s = rng_skip(state0, (int64_t)j0);
+    for (int j = j0; j < min(n, j0 + RN_CHUNK); ++j) { s = (RNG_G * s) & RNG_MASK; s = (s + 1ULL) & RNG_MASK; rn[j] = s; }
+  }
+}
+constexpr int SEL_BITS = 16;
+constexpr int SEL_BINS = 1 << SEL_BITS;
+constexpr int SEL_CAND_CAP = 1 << 18;
+__global__ void k_sel_hist(const unsigned long long* rn, const CycleDev* cd, int cap, int* hist) {
+  int n = min(cd->nSites, cap);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    atomicAdd(&hist[(int)(rn[j] >> (63 - SEL_BITS))], 1);
+}
+// heapSize-th smallest (1-based rank k): find the 16-bit bin holding it
+__global__ void k_sel_find_bin(const int* hist, CycleDev* cd, int cap, int totPop) {
+  __shared__ int sWarp[33];
+  __shared__ int carry;
+  int totSites = min(cd->nSites, cap);
+  int excess = totSites - totPop;
+  int k = (excess < 0) ? (int)(((long long)(-excess)) % totSites) : excess;     // heapSize
+  if (threadIdx.x == 0) { carry = 0; cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; }
+  __syncthreads();
+  if (k == 0) return;
+  for (int b = 0; b < SEL_BINS; b += blockDim.x) {
+    int i = b + threadIdx.x;
+    int v = hist[i];
+    int tot; int ex = blockExclusiveScan(v, sWarp, tot);
+    int c = carry;
+    int before = c + ex;
+    if (before < k && before + v >= k) { cd->selBin = i; cd->selRank = k - before; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+}
+__global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, int cap, unsigned long long* cand) {
+  int n = min(cd->nSites, cap);
+  int bin = cd->selBin;
+  if (bin < 0) return;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    unsigned long long s = rn[j];
+    if ((int)(s >> (63 - SEL_BITS)) == bin) {
+      int p = atomicAdd(&cd->nCand, 1);
+      if (p < SEL_CAND_CAP) cand[p] = s;
+    }
+  }
+}
+// threshold = selRank-th smallest of the candidates (states are distinct within the LCG period)
+__global__ void k_sel_threshold(const unsigned long long* cand, CycleDev* cd) {
+  int m = cd->nCand;
+  if (cd->selBin < 0) { if (threadIdx.x == 0) { cd->thrState = 0; cd->thrReal = 1.0; } return; }
+  if (m > SEL_CAND_CAP) { if (threadIdx.x == 0) atomicMax(&cd->error, SB_ERR_NORM); return; }
+  int want = cd->selRank - 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    unsigned long long v = cand[i];
+    int less = 0;
+    for (int j = 0; j < m; ++j) less += (cand[j] < v) ? 1 : 0;
+    if (less == want) { cd->thrState = v; cd->thrReal = (double)(long long)v * (1.0 / 9223372036854775808.0); }
+  }
+}
+// keep (excess > 0: rn > threshold) or duplicate (excess < 0: rn <= threshold) flags
+__global__ void k_norm_flags(const unsigned long long* rn, const CycleDev* cd, int cap, int totPop, int* flag) {
+  int n = min(cd->nSites, cap);
+  int excess = n - totPop;
+  int nDup = (excess < 0) ? (int)(((long long)(-excess)) % n) : 0;
+  double thr = cd->thrReal;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double x = (double)(long long)rn[j] * (1.0 / 9223372036854775808.0);
+    int f;
+    if (excess > 0) f = (x > thr) ? 1 : 0;
+    else if (excess < 0) f = (nDup != 0 && x <= thr) ? 1 : 0;
+    else f = 1;
+    flag[j] = f;
+  }
+}
+// scatter into the new bank. src is brood-sorted; offs = exclusive scan of flags; hOff/hCnt = per-history
+// offsets/counts of src (brood segments).
+__global__ void k_norm_scatter(Bank src, Bank dst, const int* flag, const int* offs, const int* hOff, const int* hCnt,
+                               const CycleDev* cd, int cap, int totPop, int dstCap, CycleDev* cdw) {
+  int n = min(cd->nSites, cap);
+  int excess = n - totPop;
+  int nCopies = (excess < 0) ? (-excess) / n : 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    int d0 = -1, stride = 0, reps = 0, dDup = -1;
+    if (excess > 0) { if (flag[j]) { d0 = offs[j]; reps = 1; } }
+    else if (excess == 0) { d0 = j; reps = 1; }
+    else {
+      int b = src.brood[j];
+      int sb = hOff[b], nb = hCnt[b];
+      int Dsb = offs[sb];
+      int start = (nCopies + 1) * sb + Dsb;
+      d0 = start + (j - sb); stride = nb; reps = nCopies + 1;
+      if (flag[j]) dDup = start + (nCopies + 1) * nb + (offs[j] - Dsb);
+    }
+    for (int m = 0; m <= reps; ++m) {
+      int d = (m < reps) ? d0 + m * stride : dDup;
+      if (d < 0) continue;
+      if (d >= dstCap) { atomicMax(&cdw->error, SB_ERR_BANK_OVERFLOW); continue; }
+      dst.rx[d] = src.rx[j]; dst.ry[d] = src.ry[j]; dst.rz[d] = src.rz[j];
+      dst.ux[d] = src.ux[j]; dst.uy[d] = src.uy[j]; dst.uz[d] = src.uz[j];
+      dst.w[d] = src.w[j]; dst.G[d] = src.G[j]; dst.brood[d] = src.brood[j]; dst.seq[d] = 0;
+    }
+  }
+}
+__global__ void k_norm_count(const int* flag, const int* offs, const CycleDev* cd, int cap, int totPop, CycleDev* cdw) {
+  int n = min(cd->nSites, cap);
+  if (n <= 0) { cdw->nNew = 0; return; }
+  int excess = n - totPop;
+  int selected = offs[n - 1] + flag[n - 1];
+  int nCopies = (excess < 0) ? (-excess) / n : 0;
+  int nNew = (excess > 0) ? selected : (excess == 0 ? n : n * (nCopies + 1) + selected);
+  cdw->nNew = nNew;
+  if (nNew != totPop) atomicMax(&cdw->error, SB_ERR_NORM);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fissionSource (ParticleObjects/Source/fissionSource_class.f90:149-271, source_inter.f90:98-118)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_source(const Model M, const char* blob, Bank out, int n, uint64_t rng0, int offset,
+                         double b0, double b1, double b2, double t0, double t1, double t2, CycleDev* cd) {
+  const Tables T = bind(M, blob);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint64_t rng = rng_skip(rng0, RNG_STRIDE * (int64_t)(offset + i + 1));
+    const double bottom[3] = {b0, b1, b2}, top[3] = {t0, t1, t2};
+    bool ok = false;
+    for (int att = 0; att < 10000 && !ok; ++att) {
+      double r3[3]; r3[0] = rng_get(rng); r3[1] = rng_get(rng); r3[2] = rng_get(rng);
+      double r[3], u[3] = {1.0, 0.0, 0.0};
+      for (int k = 0; k < 3; ++k) r[k] = (top[k] - bottom[k]) * r3[k] + bottom[k];
+      int mat, uid;
+      geomPlace(M, T, r, u, mat, uid);
+      if (mat == SB_VOID_MAT || mat == SB_OUTSIDE_MAT) continue;
+      if (mat == SB_UNDEF_MAT) { atomicMax(&cd->error, SB_ERR_UNDEF_MAT); break; }
+      if (mat == SB_OVERLAP_MAT) { atomicMax(&cd->error, SB_ERR_OVERLAP_MAT); break; }
+      if (!T.fissile[mat - 1]) continue;
+      double mu, phi;
+      int Gout = mgFissionSample(M, T, mat, mu, phi, rng);
+      if (Gout == 0) { atomicMax(&cd->error, SB_ERR_SAMPLING); Gout = 1; }
+      double d[3] = {1.0, 0.0, 0.0};
+      rotateVector(d, mu, phi);
+      out.rx[i] = r[0]; out.ry[i] = r[1]; out.rz[i] = r[2];
+      out.ux[i] = d[0]; out.uy[i] = d[1]; out.uz[i] = d[2];
+      out.w[i] = 1.0; out.G[i] = Gout; out.brood[i] = 0; out.seq[i] = 0;
+      ok = true;
+    }
+    if (!ok) atomicMax(&cd->error, SB_ERR_SOURCE);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch query kernels (parity tests)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_geom_query(const Model M, const char* blob, long long n, double* r, double* dir, const double* dist, int* mat, int* uid) {
+  const Tables T = bind(M, blob);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double rr[3] = {r[3 * i], r[3 * i + 1], r[3 * i + 2]}, uu[3] = {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+    int m, q;
+    if (dist) geomTeleport(M, T, rr, uu, dist[i], m, q);
+    else geomPlace(M, T, rr, uu, m, q);
+    for (int k = 0; k < 3; ++k) { r[3 * i + k] = rr[k]; dir[3 * i + k] = uu[k]; }
+    mat[i] = m; uid[i] = q;
+  }
+}
+__global__ void k_mg_query(const Model M, const char* blob, long long n, const int* mat, const int* G, double* total, double* maj) {
+  const Tables T = bind(M, blob);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    total[i] = mgRow(M, T, mat[i], G[i])[XS_TOTAL] + 0.0;
+    maj[i] = mgMajorant(M, T, G[i]);
+  }
+}
+__global__ void k_rng_query(long long n, const unsigned long long* st, const long long* skip, unsigned long long* outS, double* outR) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint64_t s = rng_skip(st[i], skip[i]);
+    double x = rng_get(s);
+    outS[i] = s; outR[i] = x;
+  }
+}
+__global__ void k_math_query(long long n, const double* x, double* lg, double* sn, double* cs) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    lg[i] = sbm::log(x[i]);
+    double s, c; sbm::sincos(x[i], &s, &c); sn[i] = s; cs[i] = c;
+  }
+}
+__global__ void k_cycle_begin(CycleDev* cd, int* nCur, int n) {
+  cd->nStart = n; cd->nSites = 0; cd->nextHistory = 0; cd->error = 0;
+  cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; cd->nNew = 0;
+  *nCur = n;
+}
+__global__ void k_zero_int(int* p, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0; }
+
+// ================================================================================================
+// host side: engine handle + C ABI
+// ================================================================================================
+struct sb_engine {
+  int device = 0, numSM = 148;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // model
+  bool haveGeom = false, haveData = false;
+  sb_geom_flat g{}; std::vector<int> gi_surfType, gi_cellOff, gi_cellSurf, gi_uniType, gi_uniIpar, gi_auxI, gi_gidx, gi_gid;
+  std::vector<double> gd_surfPar, gd_uniDpar, gd_auxD;
+  int nMat = 0, nG = 0, isP1 = 0; double collisionXS = 0.0;
+  std::vector<double> xs, P0, prod, P1, chi, majorant; std::vector<int> fissile;
+  std::vector<DClerk> clerks[2]; std::vector<std::vector<char>> clerkAux[2]; int nBins[2] = {0, 0}; int normAddr[2] = {0, 0}; double normVal[2] = {1.0, 1.0};
+  std::vector<sb_clerk> clerkDefs[2]; std::vector<std::vector<double>> mapBounds[2]; std::vector<std::vector<int>> mapMat[2];
+  Model M{}; char* dBlob = nullptr; bool blobDirty = true; int useSmem = 0;
+  sb_options opt{SB_TRACK_DT, 0.9, 1, 0, 0, 0};
+  // banks
+  int cap = 0; Bank bank[3]{}; int cur = 0;          // bank[cur] = this cycle; others: raw sites, sorted/next
+  int nCur = 0;
+  int *dNsites = nullptr, *dOffsets = nullptr, *dTile = nullptr, *dFlag = nullptr, *dFlagOff = nullptr, *dHist = nullptr, *dHSeg = nullptr, *dHColl = nullptr;
+  double *dHProd = nullptr, *dHAbs = nullptr, *dHLeak = nullptr, *dHScat = nullptr;
+  unsigned long long *dRn = nullptr, *dCand = nullptr;
+  RedOut* dPartial = nullptr; double* dWPartial = nullptr;
+  CycleDev* dCd = nullptr; CycleDev* hCd = nullptr; int* dNcur = nullptr;
+  double *dBins[2] = {nullptr, nullptr}, *dLast[2] = {nullptr, nullptr}, *dCsum[2] = {nullptr, nullptr}, *dCsum2[2] = {nullptr, nullptr};
+  int batchN[2] = {0, 0};
+  double bounds[6] = {0, 0, 0, 0, 0, 0};
+  double kNormNext = 1.0;   // nextCycle%k_eff of the dungeon that will receive the sites (keffAnalogClerk k_norm)
+  bool sortedReady = false;
+};
+
+static std::string g_globalErr;
+
+static int allocBank(sb_engine* h, Bank& b, int cap) {
+  CUDA_OK(cudaMalloc(&b.rx, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.ry, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.rz, sizeof(double) * cap));
+  CUDA_OK(cudaMalloc(&b.ux, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.uy, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.uz, sizeof(double) * cap));
+  CUDA_OK(cudaMalloc(&b.w, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.G, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&b.brood, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&b.seq, sizeof(int) * cap));
+  return 0;
+}
+static void freeBank(Bank& b) {
+  cudaFree(b.rx); cudaFree(b.ry); cudaFree(b.rz); cudaFree(b.ux); cudaFree(b.uy); cudaFree(b.uz); cudaFree(b.w); cudaFree(b.G); cudaFree(b.brood); cudaFree(b.seq);
+  b = Bank{};
+}
+
+static int ensureCapacity(sb_engine* h, int maxPop) {
+  int cap = 2 * maxPop;                      // eigenPhysicsPackage_class.f90:355-356 dungeons of 2*pop
+  if (cap <= h->cap) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  for (int i = 0; i < 3; ++i) { freeBank(h->bank[i]); if (allocBank(h, h->bank[i], cap)) return -1; }
+  cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
+  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
+  CUDA_OK(cudaMalloc(&h->dNsites, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dOffsets, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&h->dTile, sizeof(int) * (cap / SCAN_TILE + 2)));
+  CUDA_OK(cudaMalloc(&h->dFlag, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dFlagOff, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&h->dHSeg, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dHColl, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&h->dHProd, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHAbs, sizeof(double) * cap));
+  CUDA_OK(cudaMalloc(&h->dHLeak, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHScat, sizeof(double) * cap));
+  CUDA_OK(cudaMalloc(&h->dRn, sizeof(unsigned long long) * cap));
+  h->cap = cap; h->cur = 0; h->nCur = 0;
+  return 0;
+}
+
+template <typename T>
+static int put(std::vector<char>& blob, const std::vector<T>& v) {
+  while (blob.size() % 16) blob.push_back(0);
+  int off = (int)blob.size();
+  const char* p = (const char*)v.data();
+  blob.insert(blob.end(), p, p + sizeof(T) * v.size());
+  return off;
+}
+
+// (re)build the device table blob from the loaded model
+static int buildBlob(sb_engine* h) {
+  if (!h->blobDirty) return 0;
+  if (!h->haveGeom || !h->haveData) { h->err = "geometry and nuclear data must be loaded first"; return -1; }
+  Model& M = h->M;
+  std::vector<char> blob;
+  M.nSurf = h->g.n_surf; M.nCell = h->g.n_cell; M.nUni = h->g.n_uni; M.nGraph = h->g.n_graph;
+  M.rootIdx = h->g.root_idx; M.borderIdx = h->g.border_idx;
+  for (int i = 0; i < 6; ++i) M.bc[i] = h->g.bc[i];
+  M.oSurfType = put(blob, h->gi_surfType); M.oSurfPar = put(blob, h->gd_surfPar);
+  M.oCellOff = put(blob, h->gi_cellOff); M.oCellSurf = put(blob, h->gi_cellSurf);
+  M.oUniType = put(blob, h->gi_uniType); M.oUniIpar = put(blob, h->gi_uniIpar); M.oUniDpar = put(blob, h->gd_uniDpar);
+  M.oAuxD = put(blob, h->gd_auxD); M.oAuxI = put(blob, h->gi_auxI);
+  std::vector<int> graph(2 * (size_t)h->g.n_graph);
+  for (int i = 0; i < h->g.n_graph; ++i) { graph[2 * i] = h->gi_gidx[i]; graph[2 * i + 1] = h->gi_gid[i]; }
+  M.oGraph = put(blob, graph);
+  M.nMat = h->nMat; M.nG = h->nG; M.isP1 = h->isP1; M.collisionXS = h->collisionXS;
+  M.oXs = put(blob, h->xs); M.oP0 = put(blob, h->P0); M.oProd = put(blob, h->prod);
+  M.oP1 = h->isP1 ? put(blob, h->P1) : M.oP0;
+  M.oChi = put(blob, h->chi); M.oFissile = put(blob, h->fissile); M.oMajorant = put(blob, h->majorant);
+  for (int ph = 0; ph < 2; ++ph) {
+    // per-map auxiliary tables first, then the clerk records that point at them
+    std::vector<DClerk> cl = h->clerks[ph];
+    for (size_t c = 0; c < cl.size(); ++c)
+      for (int m = 0; m < cl[c].nMaps; ++m) {
+        size_t key = c * SB_MAX_MAPS + m;
+        if (cl[c].mapType[m] == SB_MAP_MATERIAL) cl[c].mapOff[m] = put(blob, h->mapMat[ph][key]);
+        else if (cl[c].mapGrid[m] == SB_GRID_UNSTRUCT) cl[c].mapOff[m] = put(blob, h->mapBounds[ph][key]);
+        else cl[c].mapOff[m] = 0;
+      }
+    M.nClerk[ph] = (int)cl.size(); M.nBins[ph] = h->nBins[ph];
+    M.oClerk[ph] = put(blob, cl);
+  }
+  while (blob.size() % 16) blob.push_back(0);
+  M.blobBytes = (int)blob.size();
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaFree(h->dBlob);
+  CUDA_OK(cudaMalloc(&h->dBlob, blob.size()));
+  CUDA_OK(cudaMemcpy(h->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  // shared-memory staging if the blob fits beside the static shared memory (227 KB per CTA on sm_100)
+  h->useSmem = (M.blobBytes <= 96 * 1024) ? 1 : 0;
+  if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(k_histories, cudaFuncAttributeMaxDynamicSharedMemorySize, M.blobBytes));
+  for (int ph = 0; ph < 2; ++ph) {
+    cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]);
+    size_t nb = (size_t)std::max(1, h->nBins[ph]);
+    CUDA_OK(cudaMalloc(&h->dBins[ph], sizeof(double) * nb)); CUDA_OK(cudaMalloc(&h->dLast[ph], sizeof(double) * nb));
+    CUDA_OK(cudaMalloc(&h->dCsum[ph], sizeof(double) * nb)); CUDA_OK(cudaMalloc(&h->dCsum2[ph], sizeof(double) * nb));
+    CUDA_OK(cudaMemset(h->dBins[ph], 0, sizeof(double) * nb)); CUDA_OK(cudaMemset(h->dLast[ph], 0, sizeof(double) * nb));
+    CUDA_OK(cudaMemset(h->dCsum[ph], 0, sizeof(double) * nb)); CUDA_OK(cudaMemset(h->dCsum2[ph], 0, sizeof(double) * nb));
+    h->batchN[ph] = 0;
+  }
+  h->blobDirty = false;
+  return 0;
+}
+
+static int gridFor(sb_engine* h, long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)h->numSM * 8;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+
+extern "C" {
+
+int sb_create(sb_engine** out, int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_globalErr = "scone_b200: no CUDA device available (the engine has no CPU fallback)"; return -1; }
+  if (device < 0 || device >= ndev) { g_globalErr = "scone_b200: invalid device ordinal"; return -1; }
+  sb_engine* h = new sb_engine();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { g_globalErr = "cudaSetDevice failed"; delete h; return -1; }
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, device);
+  h->numSM = p.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { g_globalErr = "cudaStreamCreate failed"; delete h; return -1; }
+  cudaMalloc(&h->dCd, sizeof(CycleDev)); cudaMemset(h->dCd, 0, sizeof(CycleDev));
+  cudaMallocHost(&h->hCd, sizeof(CycleDev));
+  cudaMalloc(&h->dPartial, sizeof(RedOut) * RED_BLOCKS); cudaMalloc(&h->dWPartial, sizeof(double) * RED_BLOCKS);
+  cudaMalloc(&h->dHist, sizeof(int) * SEL_BINS); cudaMalloc(&h->dCand, sizeof(unsigned long long) * SEL_CAND_CAP);
+  cudaMalloc(&h->dNcur, sizeof(int));
+  *out = h;
+  return 0;
+}
+
+void sb_destroy(sb_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 3; ++i) freeBank(h->bank[i]);
+  cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
+  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
+  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dWPartial); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
+  for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* sb_last_error(sb_engine* h) { return h ? h->err.c_str() : g_globalErr.c_str(); }
+int64_t sb_launch_count(sb_engine* h) { return h->launches; }
+
+int sb_load_geometry(sb_engine* h, const sb_geom_flat* g) {
+  if (g->n_uni < 1 || g->n_graph < 1 || g->root_idx < 1 || g->root_idx > g->n_uni) { h->err = "sb_load_geometry: invalid sizes"; return -1; }
+  h->g = *g;
+  h->gi_surfType.assign(g->surf_type, g->surf_type + g->n_surf);
+  h->gd_surfPar.assign(g->surf_par, g->surf_par + (size_t)g->n_surf * SB_SURF_NPAR);
+  h->gi_cellOff.assign(1, 0);
+  if (g->n_cell > 0) { h->gi_cellOff.assign(g->cell_off, g->cell_off + g->n_cell + 1); h->gi_cellSurf.assign(g->cell_surf, g->cell_surf + g->cell_off[g->n_cell]); }
+  else h->gi_cellSurf.clear();
+  h->gi_uniType.assign(g->uni_type, g->uni_type + g->n_uni);
+  h->gi_uniIpar.assign(g->uni_ipar, g->uni_ipar + (size_t)g->n_uni * SB_UNI_NIPAR);
+  h->gd_uniDpar.assign(g->uni_dpar, g->uni_dpar + (size_t)g->n_uni * SB_UNI_NDPAR);
+  h->gd_auxD.assign(g->aux_d, g->aux_d + g->n_aux_d); h->gi_auxI.assign(g->aux_i, g->aux_i + g->n_aux_i);
+  if (h->gd_auxD.empty()) h->gd_auxD.push_back(0.0);
+  if (h->gi_auxI.empty()) h->gi_auxI.push_back(0);
+  if (h->gi_cellSurf.empty()) h->gi_cellSurf.push_back(0);
+  h->gi_gidx.assign(g->graph_idx, g->graph_idx + g->n_graph); h->gi_gid.assign(g->graph_id, g->graph_id + g->n_graph);
+  if (g->border_idx < 1 || g->border_idx > g->n_surf) { h->err = "sb_load_geometry: invalid border surface index"; return -1; }
+  // geometry % bounds() (geometryStd_class.f90:188-206) of the border surface, for the fission source
+  {
+    int t = g->surf_type[g->border_idx - 1]; const double* p = g->surf_par + (size_t)(g->border_idx - 1) * SB_SURF_NPAR;
+    double lo[3] = {-INF, -INF, -INF}, hi[3] = {INF, INF, INF};
+    if (t == SB_SURF_BOX) for (int a = 0; a < 3; ++a) { lo[a] = p[a] - p[3 + a]; hi[a] = p[a] + p[3 + a]; }
+    else if (t >= SB_SURF_XSQCYL) { int ax = t - SB_SURF_XSQCYL; for (int a = 0; a < 3; ++a) if (a != ax) { lo[a] = p[a] - p[3 + a]; hi[a] = p[a] + p[3 + a]; } }
+    else if (t == SB_SURF_SPHERE) for (int a = 0; a < 3; ++a) { lo[a] = p[a] - p[3]; hi[a] = p[a] + p[3]; }
+    else if (t >= SB_SURF_XCYL && t <= SB_SURF_ZCYL) { int ax = t - SB_SURF_XCYL; for (int a = 0; a < 3; ++a) if (a != ax) { lo[a] = p[a] - p[3]; hi[a] = p[a] + p[3]; } }
+    else if (t >= SB_SURF_XPLANE && t <= SB_SURF_ZPLANE) { lo[t - SB_SURF_XPLANE] = p[0]; hi[t - SB_SURF_XPLANE] = p[0]; }
+    for (int a = 0; a < 3; ++a) { if (lo[a] <= -INF && hi[a] >= INF) { lo[a] = 0.0; hi[a] = 0.0; } h->bounds[a] = lo[a]; h->bounds[a + 3] = hi[a]; }
+  }
+  h->haveGeom = true; h->blobDirty = true;
+  return 0;
+}
+
+int sb_load_mg_data(sb_engine* h, const sb_mg_flat* d) {
+  if (d->n_mat < 1 || d->n_g < 1) { h->err = "sb_load_mg_data: invalid sizes"; return -1; }
+  size_t nm = d->n_mat, ng = d->n_g;
+  h->nMat = d->n_mat; h->nG = d->n_g; h->isP1 = d->P1 ? 1 : 0; h->collisionXS = d->collision_xs;
+  h->xs.assign(d->data, d->data + nm * ng * 6);
+  h->P0.assign(d->P0, d->P0 + nm * ng * ng); h->prod.assign(d->prod, d->prod + nm * ng * ng);
+  if (d->P1) h->P1.assign(d->P1, d->P1 + nm * ng * ng); else h->P1.clear();
+  h->chi.assign(d->chi, d->chi + nm * ng);
+  h->fissile.assign(d->fissile, d->fissile + nm);
+  h->majorant.assign(d->majorant, d->majorant + ng);
+  h->haveData = true; h->blobDirty = true;
+  return 0;
+}
+
+int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, int normClerk, double normVal) {
+  if (phase < 0 || phase > 1) { h->err = "sb_define_tallies: phase must be 0 or 1"; return -1; }
+  h->clerks[phase].clear(); h->mapBounds[phase].clear(); h->mapMat[phase].clear();
+  h->mapBounds[phase].resize((size_t)std::max(1, n) * SB_MAX_MAPS); h->mapMat[phase].resize((size_t)std::max(1, n) * SB_MAX_MAPS);
+  int memLoc = 1;
+  h->normAddr[phase] = 0; h->normVal[phase] = normVal;
+  for (int c = 0; c < n; ++c) {
+    const sb_clerk& s = clerks[c];
+    if (s.n_maps < 0 || s.n_maps > SB_MAX_MAPS || s.n_resp < 1 || s.n_resp > SB_MAX_RESP) { h->err = "sb_define_tallies: invalid clerk"; return -1; }
+    DClerk d; memset(&d, 0, sizeof(d));
+    d.addr = memLoc; d.nMaps = s.n_maps; d.nResp = s.n_resp; d.handleVirtual = s.handle_virtual;
+    int mul = 1;
+    for (int m = 0; m < s.n_maps; ++m) {
+      const sb_map1d& mp = s.maps[m];
+      d.mapType[m] = mp.type; d.mapAxis[m] = mp.axis; d.mapGrid[m] = mp.grid; d.mapN[m] = mp.n_bins; d.mapMul[m] = mul;
+      d.mapFirst[m] = mp.first; d.mapStep[m] = mp.step; d.mapDef[m] = mp.default_bin;
+      size_t key = (size_t)c * SB_MAX_MAPS + m;
+      if (mp.type == SB_MAP_MATERIAL) {
+        if (!mp.mat_bin) { h->err = "sb_define_tallies: materialMap without mat_bin"; return -1; }
+        h->mapMat[phase][key].assign(mp.mat_bin, mp.mat_bin + h->nMat);
+        d.mapGrid[m] = h->nMat;
+      } else if (mp.grid == SB_GRID_UNSTRUCT) {
+        if (!mp.bounds) { h->err = "sb_define_tallies: unstructured grid without bounds"; return -1; }
+        h->mapBounds[phase][key].assign(mp.bounds, mp.bounds + mp.n_bins + 1);
+      }
+      mul *= mp.n_bins;
+    }
+    for (int i = 0; i < s.n_resp; ++i) d.respMT[i] = s.resp_mt[i];
+    if (normClerk == c + 1) h->normAddr[phase] = memLoc;
+    memLoc += s.n_resp * mul;
+    h->clerks[phase].push_back(d);
+  }
+  h->nBins[phase] = memLoc - 1;
+  h->blobDirty = true;
+  return 0;
+}
+
+int sb_set_options(sb_engine* h, const sb_options* o) {
+  if (o->tracking != SB_TRACK_DT) { h->err = "sb_set_options: only delta tracking (transportOperatorDT) is implemented on the device in this round"; return -1; }
+  h->opt = *o;
+  if (o->max_pop > 0) return ensureCapacity(h, o->max_pop);
+  return 0;
+}
+
+int sb_bank_size(sb_engine* h) { return h->nCur; }
+
+int sb_bank_upload(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G) {
+  if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  std::vector<double> t((size_t)n);
+  Bank& b = h->bank[h->cur];
+  double* dst[6] = {b.rx, b.ry, b.rz, b.ux, b.uy, b.uz};
+  for (int k = 0; k < 6; ++k) {
+    const double* src = k < 3 ? r : dir; int c = k % 3;
+    for (int i = 0; i < n; ++i) t[i] = src[3 * (size_t)i + c];
+    CUDA_OK(cudaMemcpyAsync(dst[k], t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  CUDA_OK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(b.G, G, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->nCur = n;
+  return 0;
+}
+
+int sb_bank_download(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, int32_t* G) {
+  CUDA_OK(cudaSetDevice(h->device));
+  int m = h->nCur;
+  *n = m;
+  if (m > cap) { h->err = "sb_bank_download: buffer too small"; return -1; }
+  std::vector<double> t((size_t)std::max(1, m));
+  Bank& b = h->bank[h->cur];
+  double* src[6] = {b.rx, b.ry, b.rz, b.ux, b.uy, b.uz};
+  for (int k = 0; k < 6; ++k) {
+    CUDA_OK(cudaMemcpyAsync(t.data(), src[k], sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    double* dst = k < 3 ? r : dir; int c = k % 3;
+    for (int i = 0; i < m; ++i) dst[3 * (size_t)i + c] = t[i];
+  }
+  CUDA_OK(cudaMemcpyAsync(w, b.w, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaMemcpyAsync(G, b.G, sizeof(int) * m, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int checkDeviceError(sb_engine* h, int code) {
+  if (code == 0) return 0;
+  const char* msg = "unknown device error";
+  switch (code) {
+    case SB_ERR_BANK_OVERFLOW: msg = "Run out of space for particles (particleDungeon detain): fission bank overflow"; break;
+    case SB_ERR_UNDEF_MAT: msg = "Particle is in undefined material"; break;
+    case SB_ERR_OVERLAP_MAT: msg = "Particle is in overlapping cells"; break;
+    case SB_ERR_SAMPLING: msg = "Sampling failed (scatter XS / chi normalisation or random number above 1)"; break;
+    case SB_ERR_NEST: msg = "Failed to find material cell (nesting exceeded)"; break;
+    case SB_ERR_SOURCE: msg = "fissionSource: failed to find a fissile material in 10000 attempts"; break;
+    case SB_ERR_NORM: msg = "Normalisation failed!"; break;
+  }
+  h->err = msg;
+  return -1;
+}
+
+int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offset) {
+  if (buildBlob(h)) return -1;
+  if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemsetAsync(h->dCd, 0, sizeof(CycleDev), h->stream));
+  const double* b = h->bounds;
+  k_source<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, h->bank[h->cur], n, rng_state, history_offset, b[0], b[1], b[2], b[3], b[4], b[5], h->dCd);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  h->nCur = n;
+  return checkDeviceError(h, h->hCd->error);
+}
+
+int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, sb_cycle_result* res) {
+  if (phase < 0 || phase > 1) { h->err = "sb_run_cycle: phase must be 0 or 1"; return -1; }
+  if (buildBlob(h)) return -1;
+  if (h->nCur <= 0) { h->err = "sb_run_cycle: empty bank"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int n = h->nCur;
+  Bank& in = h->bank[h->cur]; Bank& raw = h->bank[(h->cur + 1) % 3]; Bank& sorted = h->bank[(h->cur + 2) % 3];
+
+  // reset the running-cycle record (the cumulative k sums stay)
+  k_cycle_begin<<<1, 1, 0, st>>>(h->dCd, h->dNcur, n);
+  h->launches++;
+
+  CycleArgs a;
+  a.M = h->M; a.blob = h->dBlob; a.useSmem = h->useSmem;
+  a.n = n; a.in = in; a.out = raw; a.cap = h->cap;
+  a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat; a.hSeg = h->dHSeg; a.hColl = h->dHColl;
+  a.bins = h->dBins[phase]; a.phase = phase;
+  a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
+  const int threads = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 256;
+  const int bps = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 2;
+  int blocks = h->numSM * bps;
+  int needBlocks = (n + threads - 1) / threads;
+  if (needBlocks < blocks) blocks = needBlocks;
+  long long warps = (long long)blocks * (threads / 32);
+  int chunk = (int)(n / (4 * warps)); if (chunk < 1) chunk = 1; if (chunk > 128) chunk = 128;
+  a.chunk = chunk;
+  k_histories<<<blocks, threads, h->useSmem ? h->M.blobBytes : 0, st>>>(a);
+  h->launches++;
+
+  // brood offsets = exclusive scan of per-history site counts ; stable brood order
+  int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dNsites, h->dNcur, h->dTile);
+  k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, h->dNcur, nullptr);
+  k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dNsites, h->dNcur, h->dTile, h->dOffsets);
+  k_sort_sites<<<gridFor(h, 2LL * n, 256), 256, 0, st>>>(raw, sorted, h->dOffsets, h->dCd, h->cap);
+  // deterministic reductions and cycle close
+  k_reduce_hist<<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, h->dPartial);
+  k_reduce_wgt<<<RED_BLOCKS, RED_THREADS, 0, st>>>(sorted.w, h->dCd, h->cap, h->dWPartial);
+  k_close_cycle_head<<<1, 32, 0, st>>>(h->dPartial, h->dWPartial, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase]);
+  int nb = std::max(1, h->nBins[phase]);
+  k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
+  h->launches += 8;
+  h->batchN[phase] += 1;
+  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  const CycleDev& c = *h->hCd;
+  if (res) {
+    res->n_start = n; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
+    res->imp_prod = c.impProd; res->imp_abs = c.impAbs; res->scatter_prod = c.scatProd; res->ana_leak = c.anaLeak;
+    res->k_analog = c.kAnalog; res->k_implicit = c.kImplicit; res->k_cum = c.kCum; res->k_cum_std = c.kCumStd;
+    res->n_segments = c.nSeg; res->n_collisions = c.nColl; res->error = c.error;
+  }
+  h->sortedReady = true;
+  return checkDeviceError(h, c.error);
+}
+
+int sb_resample(sb_engine* h, int totPop, uint64_t rng_state) {
+  if (!h->sortedReady) { h->err = "sb_resample: no cycle has been run"; return -1; }
+  if (2 * totPop > h->cap) { h->err = "sb_resample: target population exceeds the bank capacity"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  Bank& sorted = h->bank[(h->cur + 2) % 3]; Bank& dst = h->bank[(h->cur + 1) % 3];
+  const int nSites = h->hCd->nSites;
+  if (nSites <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
+  int g = gridFor(h, nSites, 256);
+  k_rn_generate<<<gridFor(h, (nSites + RN_CHUNK - 1) / RN_CHUNK, 128), 128, 0, st>>>(h->dRn, h->dCd, h->cap, rng_state);
+  k_zero_int<<<gridFor(h, SEL_BINS, 256), 256, 0, st>>>(h->dHist, SEL_BINS);
+  k_sel_hist<<<g, 256, 0, st>>>(h->dRn, h->dCd, h->cap, h->dHist);
+  k_sel_find_bin<<<1, 1024, 0, st>>>(h->dHist, h->dCd, h->cap, totPop);
+  k_sel_collect<<<g, 256, 0, st>>>(h->dRn, h->dCd, h->cap, h->dCand);
+  k_sel_threshold<<<1, 1024, 0, st>>>(h->dCand, h->dCd);
+  k_norm_flags<<<g, 256, 0, st>>>(h->dRn, h->dCd, h->cap, totPop, h->dFlag);
+  int tiles = (nSites + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dCd->nSites, h->dTile);
+  k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, &h->dCd->nSites, nullptr);
+  k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dCd->nSites, h->dTile, h->dFlagOff);
+  k_norm_scatter<<<g, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dCd, h->cap, totPop, h->cap, h->dCd);
+  k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dCd, h->cap, totPop, h->dCd);
+  h->launches += 12;
+  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  if (checkDeviceError(h, h->hCd->error)) return -1;
+  h->cur = (h->cur + 1) % 3;
+  h->nCur = h->hCd->nNew;
+  h->kNormNext = h->hCd->kCum;      // self%nextCycle%k_eff = k_new (eigenPhysicsPackage_class.f90:306)
+  h->sortedReady = false;
+  return 0;
+}
+
+int64_t sb_tally_size(sb_engine* h, int phase) { return (phase < 0 || phase > 1) ? -1 : h->nBins[phase]; }
+int sb_tally_read(sb_engine* h, int phase, double* csum, double* csum2, int32_t* batch_n) {
+  if (phase < 0 || phase > 1) { h->err = "phase must be 0 or 1"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->nBins[phase] > 0 && h->dCsum[phase]) {
+    CUDA_OK(cudaMemcpy(csum, h->dCsum[phase], sizeof(double) * h->nBins[phase], cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(csum2, h->dCsum2[phase], sizeof(double) * h->nBins[phase], cudaMemcpyDeviceToHost));
+  }
+  *batch_n = h->batchN[phase];
+  return 0;
+}
+int sb_tally_last_bins(sb_engine* h, int phase, double* bins) {
+  if (phase < 0 || phase > 1) { h->err = "phase must be 0 or 1"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->nBins[phase] > 0 && h->dLast[phase]) CUDA_OK(cudaMemcpy(bins, h->dLast[phase], sizeof(double) * h->nBins[phase], cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- batch queries -------------------------------------------------------------------------------
+int sb_geom_query(sb_engine* h, int64_t n, double* r, double* dir, const double* dist, int32_t* mat, int32_t* uid) {
+  if (!h->haveData) {                        // geometry-only use: give the blob a dummy 1-group material table
+    sb_mg_flat d{}; double z6[6] = {1, 0, 1, 0, 0, 0}, one = 1.0, zero = 0.0; int f = 0;
+    d.n_mat = 1; d.n_g = 1; d.data = z6; d.P0 = &zero; d.prod = &one; d.P1 = nullptr; d.chi = &zero; d.fissile = &f; d.majorant = &one; d.collision_xs = 0.0;
+    if (sb_load_mg_data(h, &d)) return -1;
+  }
+  if (buildBlob(h)) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  double *dr, *du, *dd = nullptr; int *dm, *dq;
+  CUDA_OK(cudaMalloc(&dr, sizeof(double) * 3 * n)); CUDA_OK(cudaMalloc(&du, sizeof(double) * 3 * n));
+  CUDA_OK(cudaMalloc(&dm, sizeof(int) * n)); CUDA_OK(cudaMalloc(&dq, sizeof(int) * n));
+  CUDA_OK(cudaMemcpy(dr, r, sizeof(double) * 3 * n, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(du, dir, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+  if (dist) { CUDA_OK(cudaMalloc(&dd, sizeof(double) * n)); CUDA_OK(cudaMemcpy(dd, dist, sizeof(double) * n, cudaMemcpyHostToDevice)); }
+  k_geom_query<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, n, dr, du, dd, dm, dq);
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(r, dr, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(dir, du, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(mat, dm, sizeof(int) * n, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(uid, dq, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dr); cudaFree(du); cudaFree(dm); cudaFree(dq); cudaFree(dd);
+  return 0;
+}
+
+int sb_mg_query(sb_engine* h, int64_t n, const int32_t* mat, const int32_t* G, double* total, double* majorant) {
+  if (buildBlob(h)) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  int *dm, *dg; double *dt, *dj;
+  CUDA_OK(cudaMalloc(&dm, sizeof(int) * n)); CUDA_OK(cudaMalloc(&dg, sizeof(int) * n));
+  CUDA_OK(cudaMalloc(&dt, sizeof(double) * n)); CUDA_OK(cudaMalloc(&dj, sizeof(double) * n));
+  CUDA_OK(cudaMemcpy(dm, mat, sizeof(int) * n, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(dg, G, sizeof(int) * n, cudaMemcpyHostToDevice));
+  k_mg_query<<<gridFor(h, n, 256), 256, 0, h->stream>>>(h->M, h->dBlob, n, dm, dg, dt, dj);
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(total, dt, sizeof(double) * n, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(majorant, dj, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dm); cudaFree(dg); cudaFree(dt); cudaFree(dj);
+  return 0;
+}
+
+int sb_rng_query(int64_t n, const uint64_t* state, const int64_t* skip, uint64_t* out_state, double* out_real) {
+  unsigned long long *ds, *dout; long long* dk; double* dr;
+  if (cudaMalloc(&ds, 8 * n) != cudaSuccess) { g_globalErr = "sb_rng_query: no CUDA device / allocation failed"; return -1; }
+  cudaMalloc(&dk, 8 * n); cudaMalloc(&dout, 8 * n); cudaMalloc(&dr, 8 * n);
+  cudaMemcpy(ds, state, 8 * n, cudaMemcpyHostToDevice); cudaMemcpy(dk, skip, 8 * n, cudaMemcpyHostToDevice);
+  k_rng_query<<<(int)std::min<long long>((n + 255) / 256, 1184), 256>>>(n, ds, dk, dout, dr);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(out_state, dout, 8 * n, cudaMemcpyDeviceToHost); cudaMemcpy(out_real, dr, 8 * n, cudaMemcpyDeviceToHost);
+  cudaFree(ds); cudaFree(dk); cudaFree(dout); cudaFree(dr);
+  if (e != cudaSuccess) { g_globalErr = cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
+int sb_math_query(int64_t n, const double* x, double* lg, double* sn, double* cs) {
+  double *dx, *dl, *dsn, *dcs;
+  if (cudaMalloc(&dx, 8 * n) != cudaSuccess) { g_globalErr = "sb_math_query: no CUDA device / allocation failed"; return -1; }
+  cudaMalloc(&dl, 8 * n); cudaMalloc(&dsn, 8 * n); cudaMalloc(&dcs, 8 * n);
+  cudaMemcpy(dx, x, 8 * n, cudaMemcpyHostToDevice);
+  k_math_query<<<(int)std::min<long long>((n + 255) / 256, 1184), 256>>>(n, dx, dl, dsn, dcs);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(lg, dl, 8 * n, cudaMemcpyDeviceToHost); cudaMemcpy(sn, dsn, 8 * n, cudaMemcpyDeviceToHost); cudaMemcpy(cs, dcs, 8 * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dl); cudaFree(dsn); cudaFree(dcs);
+  if (e != cudaSuccess) { g_globalErr = cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
+}  // extern "C"

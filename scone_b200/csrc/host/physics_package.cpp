@@ -1,0 +1,249 @@
+// Host-side mirror of SCONE's eigenPhysicsPackage, driving the engine through the C ABI only.
+//   PhysicsPackages/eigenPhysicsPackage_class.f90:135-159  run
+//   PhysicsPackages/eigenPhysicsPackage_class.f90:164-343  cycles
+//   PhysicsPackages/eigenPhysicsPackage_class.f90:348-366  generateInitialState
+//   PhysicsPackages/eigenPhysicsPackage_class.f90:417-645  init
+// The Fortran package would keep this control flow and call sb_* through iso_c_binding
+// (INTEGRATION.md); there is no Fortran compiler in the build image, so the same sequence of
+// calls is written here in C++ and exported with a small C API (sbh_*) for bench.py / tests.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/scone_b200.h"
+#include "../sb_rng.h"
+#include "model.hpp"
+
+namespace {
+
+struct eigenPhysicsPackage {
+  // settings
+  int pop = 0, totalPop = 0, N_inactive = 0, N_active = 0;
+  double keff_0 = 1.0;
+  uint64_t pRNG = 0;
+  int rankOffset = 0;                      // getOffset(totalPop) of this rank (mpi_func.f90:133-159)
+  sb::FlatGeometry geom; sb::FlatMgData data; sb::TallyDefs tallies[2];
+  sb_engine* eng = nullptr;
+  std::string err;
+  // results
+  std::vector<double> cycleK; sb_cycle_result last{};
+  long long nSegActive = 0, nSegInactive = 0, nHist = 0;
+  double timeTransport = 0.0;
+  // host copy of the bank for the end-to-end (host buffer) mode
+  std::vector<double> hr, hdir, hw; std::vector<int32_t> hG; int hN = 0;
+  std::vector<double> hBins;
+
+  static std::string dirName(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? "." : p.substr(0, k); }
+
+  void stride(int64_t n) { pRNG = sbd::rng_skip(pRNG, sbd::RNG_STRIDE * n); }
+
+  int fail(const std::string& m) { err = m; return -1; }
+  int engFail() { err = sb_last_error(eng); return -1; }
+
+  int init(const std::string& deckPath, const char* overrides, int device, int rank, int nRanks) {
+    try {
+      sb::Dict dict = sb::Dict::fromFile(deckPath);
+      if (overrides && *overrides) {
+        sb::Dict ov = sb::Dict::fromString(overrides);
+        auto dk = ov.keys("dict");
+        for (auto& k : ov.keys("all")) {
+          if (std::find(dk.begin(), dk.end(), k) != dk.end()) dict.setDict(k, ov.getDict(k));
+          else dict.setScalar(k, ov.getWord(k));
+        }
+      }
+      if (dict.getWord("type") != "eigenPhysicsPackage") return fail("only eigenPhysicsPackage decks are driven by this host");
+      totalPop = dict.getInt("pop");
+      // getWorkshare / getOffset (mpi_func.f90:133-159): contiguous shares, remainder to the low ranks
+      { int base = totalPop / nRanks, rem = totalPop % nRanks; pop = base + (rank < rem ? 1 : 0); rankOffset = rank * base + std::min(rank, rem); }
+      N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active");
+      std::string nucData = dict.getWord("XSdata"), energy = dict.getWord("dataType");
+      if (energy != "mg") return fail("dataType must be 'mg' (the CE path is not on the device yet)");
+      if (!dict.isPresent("seed")) return fail("an explicit `seed` is required for a reproducible run");
+      pRNG = (uint64_t)(int64_t)dict.getInt("seed");
+      keff_0 = dict.getReal("keff_0", 1.0);
+      const sb::Dict& nd = dict.getDict("nuclearData");
+      sb::MatMap mats = sb::materialMenu(nd);
+      geom = sb::buildGeometry(dict.getDict("geometry"), mats);
+      data = sb::buildMgData(nd, nucData, dirName(deckPath), geom.activeMats());
+      const sb::Dict& co = dict.getDict("collisionOperator");
+      if (!co.isPresent("neutronMG") || co.getDict("neutronMG").getWord("type") != "neutronMGstd") return fail("collisionOperator: neutronMGstd is required");
+      sb_options opt{}; opt.max_pop = pop; opt.ht_cutoff = 0.9; opt.st_cache = 1;
+      const sb::Dict& to = dict.getDict("transportOperator");
+      std::string tt = to.getWord("type");
+      if (tt == "transportOperatorDT") opt.tracking = SB_TRACK_DT;
+      else if (tt == "transportOperatorST") opt.tracking = SB_TRACK_ST;
+      else if (tt == "transportOperatorHT") { opt.tracking = SB_TRACK_HT; opt.ht_cutoff = to.getReal("cutoff", 0.9); }
+      else return fail("Unrecognised type of transportOperator: " + tt);
+      tallies[0] = sb::buildTallies(dict.getDict("inactiveTally"), mats, data.nMat);
+      tallies[1] = sb::buildTallies(dict.getDict("activeTally"), mats, data.nMat);
+      if (dict.isPresent("source")) return fail("only the default fissionSource is supported");
+
+      if (device < 0) return 0;     // host model only (CPU-side tests of the flattening); no engine, no transport
+      if (sb_create(&eng, device)) return fail(sb_last_error(nullptr));
+      sb_geom_flat gv = geom.view(); if (sb_load_geometry(eng, &gv)) return engFail();
+      sb_mg_flat dv = data.view(); if (sb_load_mg_data(eng, &dv)) return engFail();
+      for (int ph = 0; ph < 2; ++ph)
+        if (sb_define_tallies(eng, ph, tallies[ph].clerks.data(), (int)tallies[ph].clerks.size(), tallies[ph].normClerk, tallies[ph].normVal)) return engFail();
+      if (sb_set_options(eng, &opt)) return engFail();
+    } catch (const std::exception& e) { return fail(e.what()); }
+    return 0;
+  }
+
+  // run(): pRNG%stride(getOffset(totalPop)) then generateInitialState
+  int generateInitialState() {
+    if (!eng) return fail("no engine: this handle was created without a device");
+    stride(rankOffset);
+    if (sb_source_generate(eng, pop, pRNG, 0)) return engFail();
+    stride(totalPop);
+    return 0;
+  }
+
+  // one pass of the cycle body (eigenPhysicsPackage_class.f90:203-307) with the bank resident on the device
+  int cycle(int active, double& k_new) {
+    if (!eng) return fail("no engine: this handle was created without a device");
+    auto t0 = std::chrono::steady_clock::now();
+    if (sb_run_cycle(eng, pRNG, 0, k_new, active, &last)) return engFail();
+    stride(totalPop + 1);
+    if (sb_resample(eng, pop, pRNG)) return engFail();
+    stride(1);
+    k_new = last.k_cum;
+    keff_0 = k_new;
+    cycleK.push_back(k_new);
+    (active ? nSegActive : nSegInactive) += last.n_segments;
+    nHist += last.n_start;
+    timeTransport += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+  }
+
+  // the same cycle with the dungeons kept in HOST memory, as a shim that leaves thisCycle/nextCycle in
+  // Fortran arrays would do: upload bank, run, resample, download bank, read the cycle's bins
+  int cycleHostBuffers(int active, double& k_new) {
+    if (!eng) return fail("no engine: this handle was created without a device");
+    if (hN == 0) { if (downloadBank()) return -1; }
+    if (sb_bank_upload(eng, hN, hr.data(), hdir.data(), hw.data(), hG.data())) return engFail();
+    if (sb_run_cycle(eng, pRNG, 0, k_new, active, &last)) return engFail();
+    stride(totalPop + 1);
+    if (sb_resample(eng, pop, pRNG)) return engFail();
+    stride(1);
+    if (downloadBank()) return -1;
+    int64_t nb = sb_tally_size(eng, active);
+    hBins.resize((size_t)std::max<int64_t>(1, nb));
+    if (nb > 0 && sb_tally_last_bins(eng, active, hBins.data())) return engFail();
+    k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
+    (active ? nSegActive : nSegInactive) += last.n_segments;
+    nHist += last.n_start;
+    return 0;
+  }
+  int downloadBank() {
+    int cap = 2 * pop;
+    hr.resize(3 * (size_t)cap); hdir.resize(3 * (size_t)cap); hw.resize(cap); hG.resize(cap);
+    if (sb_bank_download(eng, cap, &hN, hr.data(), hdir.data(), hw.data(), hG.data())) return engFail();
+    return 0;
+  }
+
+  int cycles(int active, int N) {
+    double k_new = keff_0;
+    for (int i = 0; i < N; ++i) if (cycle(active, k_new)) return -1;
+    return 0;
+  }
+  int run() {
+    if (generateInitialState()) return -1;
+    if (cycles(0, N_inactive)) return -1;
+    return cycles(1, N_active);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+static std::string g_sbhErr;
+const char* sbh_last_error(void* p) { return p ? ((eigenPhysicsPackage*)p)->err.c_str() : g_sbhErr.c_str(); }
+
+void* sbh_eigen_create(const char* deckPath, const char* overrides, int device, int rank, int nRanks) {
+  auto* p = new eigenPhysicsPackage();
+  if (p->init(deckPath, overrides, device, rank, nRanks < 1 ? 1 : nRanks)) { g_sbhErr = p->err; if (p->eng) sb_destroy(p->eng); delete p; return nullptr; }
+  return p;
+}
+void sbh_eigen_destroy(void* pv) { auto* p = (eigenPhysicsPackage*)pv; if (!p) return; if (p->eng) sb_destroy(p->eng); delete p; }
+sb_engine* sbh_engine(void* pv) { return ((eigenPhysicsPackage*)pv)->eng; }
+int sbh_eigen_info(void* pv, int* pop, int* nInactive, int* nActive, int* nG, int* nMat, int* nGraph, int* uniqueCells) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  *pop = p->pop; *nInactive = p->N_inactive; *nActive = p->N_active; *nG = p->data.nG; *nMat = p->data.nMat;
+  *nGraph = (int)p->geom.graphIdx.size(); *uniqueCells = p->geom.uniqueCells;
+  return 0;
+}
+uint64_t sbh_eigen_rng_state(void* pv) { return ((eigenPhysicsPackage*)pv)->pRNG; }
+void sbh_eigen_set_rng_state(void* pv, uint64_t s) { ((eigenPhysicsPackage*)pv)->pRNG = s; }
+double sbh_eigen_keff0(void* pv) { return ((eigenPhysicsPackage*)pv)->keff_0; }
+int sbh_eigen_generate_initial_state(void* pv) { return ((eigenPhysicsPackage*)pv)->generateInitialState(); }
+int sbh_eigen_cycle(void* pv, int active, double* k, sb_cycle_result* res) {
+  auto* p = (eigenPhysicsPackage*)pv; int rc = p->cycle(active, *k); if (res) *res = p->last; return rc;
+}
+int sbh_eigen_cycle_host_buffers(void* pv, int active, double* k, sb_cycle_result* res) {
+  auto* p = (eigenPhysicsPackage*)pv; int rc = p->cycleHostBuffers(active, *k); if (res) *res = p->last; return rc;
+}
+int sbh_eigen_cycles(void* pv, int active, int N) { return ((eigenPhysicsPackage*)pv)->cycles(active, N); }
+int sbh_eigen_run(void* pv) { return ((eigenPhysicsPackage*)pv)->run(); }
+int sbh_eigen_stats(void* pv, long long* segInactive, long long* segActive, long long* hist, double* tTransport) {
+  auto* p = (eigenPhysicsPackage*)pv; *segInactive = p->nSegInactive; *segActive = p->nSegActive; *hist = p->nHist; *tTransport = p->timeTransport; return 0;
+}
+// bytes moved per host-buffer cycle: bank up (pop sites) + bank down (pop sites) + bins
+int sbh_eigen_host_bytes(void* pv, int active, long long* h2d, long long* d2h) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  long long site = 3 * 8 + 3 * 8 + 8 + 4;
+  *h2d = site * p->pop; *d2h = site * p->pop + 8 * (long long)sb_tally_size(p->eng, active) + (long long)sizeof(sb_cycle_result);
+  return 0;
+}
+
+// ---- flat model access for the tests (what the engine was given) ---------------------------------
+int sbh_model_graph(void* pv, int* idx, int* id) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  for (size_t i = 0; i < p->geom.graphIdx.size(); ++i) { idx[i] = p->geom.graphIdx[i]; id[i] = p->geom.graphId[i]; }
+  return 0;
+}
+int sbh_model_xs(void* pv, double* data /*[nMat][nG][6]*/, double* majorant) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  std::memcpy(data, p->data.data.data(), sizeof(double) * p->data.data.size());
+  std::memcpy(majorant, p->data.majorant.data(), sizeof(double) * p->data.majorant.size());
+  return 0;
+}
+
+// geometry-only handle for geometry parity tests: dictionary text (deck or geometry-level) -> engine
+void* sbh_geom_create(const char* text, int isPath, int device) {
+  try {
+    sb::Dict d = isPath ? sb::Dict::fromFile(text) : sb::Dict::fromString(text);
+    sb::MatMap mats = sb::materialMenu(d.getDict("nuclearData"));
+    const sb::Dict& gd = d.isPresent("geometry") ? d.getDict("geometry") : d;
+    auto* p = new eigenPhysicsPackage();
+    p->geom = sb::buildGeometry(gd, mats);
+    if (device >= 0) {
+      if (sb_create(&p->eng, device)) { g_sbhErr = sb_last_error(nullptr); delete p; return nullptr; }
+      sb_geom_flat gv = p->geom.view();
+      if (sb_load_geometry(p->eng, &gv)) { g_sbhErr = sb_last_error(p->eng); sb_destroy(p->eng); delete p; return nullptr; }
+    }
+    return p;
+  } catch (const std::exception& e) { g_sbhErr = e.what(); return nullptr; }
+}
+int sbh_geom_info(void* pv, int* nSurf, int* nCell, int* nUni, int* nGraph, int* uniqueCells, int* rootIdx, int* borderIdx, int* nesting) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  *nSurf = (int)p->geom.surfType.size(); *nCell = (int)p->geom.cellOff.size() - 1; *nUni = (int)p->geom.uniType.size();
+  *nGraph = (int)p->geom.graphIdx.size(); *uniqueCells = p->geom.uniqueCells; *rootIdx = p->geom.rootIdx; *borderIdx = p->geom.borderIdx; *nesting = p->geom.nesting;
+  return 0;
+}
+int sbh_geom_uni_fill(void* pv, int uniIdx, int* out, int cap) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  auto& f = p->geom.fills.at(uniIdx - 1);
+  for (size_t i = 0; i < f.size() && (int)i < cap; ++i) out[i] = f[i];
+  return (int)f.size();
+}
+int sbh_geom_active_mats(void* pv, int* out, int cap) {
+  auto a = ((eigenPhysicsPackage*)pv)->geom.activeMats();
+  for (size_t i = 0; i < a.size() && (int)i < cap; ++i) out[i] = a[i];
+  return (int)a.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""GPU parity, end to end: the CUDA cycle (transport + collisions + tallies + fission bank + resampling)
+against the CPU oracle on identical inputs and seeds.
+
+With the oracle in its "sbmath" mode both sides use the same deterministic log/sin/cos, every history
+draws the reference's random stream, and the comparison is EXACT: the fission bank after every cycle is
+bit-identical (positions, directions, groups, order), site counts are equal, and k-eff / tally bins agree
+to summation-order rounding (1e-12 relative).  At full BASELINE size the check is statistical (3 sigma)
+plus size-independent invariants."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scone_b200
+from tests import oracle_lib as ol
+from tests.gpu_util import DECK
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_bank(orc, e):
+    n = orc.orc_eigen_bank_size(e)
+    r = np.zeros((n, 3)); d = np.zeros((n, 3)); w = np.zeros(n); G = np.zeros(n, np.int32); b = np.zeros(n, np.int32)
+    orc.orc_eigen_bank(e, ol.dp(r), ol.dp(d), ol.dp(w), ol.ip(G), ol.ip(b))
+    return r, d, w, G
+
+
+@pytest.mark.parametrize("deck,pop,ninact,nact", [("inf", 4000, 3, 3), ("slab", 4000, 3, 3), ("c5g7", 20000, 3, 3), ("c5g7_3d", 10000, 2, 2)])
+def test_cycles_bit_exact_against_oracle(orc, deck, pop, ninact, nact):
+    ov = "pop %d; inactive %d; active %d; seed 12345;" % (pop, ninact, nact)
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(DECK[deck].encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(DECK[deck], ov, device=0)
+        assert orc.orc_eigen_init_source(e) == 0, ol.err(orc)
+        pp.generateInitialState()
+        assert pp.rng_state == orc.orc_eigen_rng_state(e)
+        for a, b in zip(pp.bank(), oracle_bank(orc, e)):
+            assert np.array_equal(a, b)                    # initial source: bit-identical
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(ninact + nact):
+            active = cyc >= ninact
+            res = pp.cycle(active)
+            k_o = orc.orc_eigen_cycle(e, 1 if active else 0, k_o)
+            assert not np.isnan(k_o), ol.err(orc)
+            assert pp.rng_state == orc.orc_eigen_rng_state(e)
+            gb = pp.bank(); ob = oracle_bank(orc, e)
+            assert len(gb[2]) == len(ob[2]) == pop
+            for a, b in zip(gb, ob):
+                assert np.array_equal(a, b), "fission bank differs after cycle %d" % cyc
+            assert pp.k == pytest.approx(k_o, rel=1e-12)
+        # tallies of the active phase (CSUM, CSUM2 of every bin)
+        n = orc.orc_eigen_tally_size(e, 1)
+        cs, cs2, nb = pp.tally(True)
+        assert len(cs) == n
+        if n:
+            ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+            orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+            assert nb == b.value == nact
+            np.testing.assert_allclose(cs, ocs, rtol=1e-11, atol=1e-300)
+            np.testing.assert_allclose(cs2, ocs2, rtol=1e-11, atol=1e-300)
+            assert cs.sum() > 0
+        # segment counts are integers: equal
+        seg, coll, hist = C.c_long(), C.c_long(), C.c_long()
+        orc.orc_eigen_stats(e, C.byref(seg), C.byref(coll), C.byref(hist))
+        st = pp.stats()
+        assert st["seg_inactive"] + st["seg_active"] == seg.value
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
+
+
+def test_host_buffer_cycle_equals_device_resident_cycle():
+    ov = "pop 20000; inactive 2; active 2; seed 777;"
+    a = scone_b200.EigenPhysicsPackage(DECK["c5g7"], ov, device=0)
+    b = scone_b200.EigenPhysicsPackage(DECK["c5g7"], ov, device=0)
+    a.generateInitialState(); b.generateInitialState()
+    for cyc in range(4):
+        a.cycle(cyc >= 2); b.cycle(cyc >= 2, host_buffers=True)
+        assert a.k == b.k
+        for x, y in zip(a.bank(), b.bank()):
+            assert np.array_equal(x, y)
+    a.close(); b.close()
+
+
+def test_k_inf_analytic():
+    """InputFiles/SCONE_Inf: k-inf of the 2-group URR set is 1.631452 (eigenvalue of the 2x2 balance)."""
+    pp = scone_b200.EigenPhysicsPackage(DECK["inf"], "pop 100000; inactive 20; active 60; seed 99;", device=0)
+    pp.generateInitialState()
+    pp.cycles(False, 20)
+    res = pp.cycles(True, 60)
+    assert abs(pp.k - 1.631452) < 4 * res.k_cum_std + 2e-5
+    pp.close()
+
+
+def test_full_size_c5g7_invariants_and_statistics(orc):
+    """BASELINE configs[0] size (1e5 histories per cycle): invariants + 3-sigma agreement with the oracle (libm mode)."""
+    pop = 100000
+    ov = "pop %d; inactive 15; active 15; seed 2026;" % pop
+    pp = scone_b200.EigenPhysicsPackage(DECK["c5g7"], ov, device=0)
+    pp.generateInitialState()
+    pp.cycles(False, 15)
+    ks = []
+    for _ in range(15):
+        res = pp.cycle(True)
+        ks.append(res.k_implicit)
+        assert res.n_start == pop
+        assert 0.5 * pop < res.n_sites < 2 * pop
+    r, d, w, G = pp.bank()
+    assert len(w) == pop and np.all(w == 1.0)
+    assert np.all((G >= 1) & (G <= 7))
+    np.testing.assert_allclose((d * d).sum(1), 1.0, rtol=1e-12)
+    mat, uid, _, _ = pp.geom_query(r, d)
+    assert np.all(np.isin(mat, [1, 2, 3, 4, 5]))          # every source site sits in a fissile material
+    k_gpu, s_gpu = pp.k, res.k_cum_std
+    # oracle with a smaller population (CPU time), independent seed, glibc math
+    e = orc.orc_eigen_load(DECK["c5g7"].encode(), b"pop 20000; inactive 15; active 30; seed 4242;")
+    assert orc.orc_eigen_run(e) == 0, ol.err(orc)
+    cs = np.zeros(5); cs2 = np.zeros(5); b = C.c_int()
+    orc.orc_eigen_tally(e, 3, ol.dp(cs), ol.dp(cs2), C.byref(b))
+    n = b.value
+    k_o = cs[4] / n
+    s_o = np.sqrt(max(cs2[4] / n / (n - 1) - k_o * k_o / (n - 1), 0.0))
+    assert abs(k_gpu - k_o) < 3.0 * np.sqrt(s_gpu ** 2 + s_o ** 2)
+    assert abs(k_gpu - 1.18655) < 0.004               # NEA C5G7 2-D reference (external)
+    cs_t, _, nb = pp.tally(True)
+    assert nb == 15 and cs_t.min() >= 0 and cs_t.sum() > 0
+    orc.orc_eigen_free(e); pp.close()
