@@ -1,0 +1,291 @@
+#!/usr/bin/env python3
+"""bench.py -- active-cycle throughput of the SCONE hot path on B200 (and of the CPU reference arm).
+
+Metric (BASELINE.json): active-cycle neutrons/s (and segments/s) on the C5G7 MOX 2-D 7-group eigenvalue
+problem, delta tracking, 1e5 neutrons per cycle per GPU.  A "step" is one active cycle: every history of the
+current fission bank is transported to its death (XS lookup, delta-tracking flights, collisions, tallies,
+fission-site banking), the cycle's tallies are closed and the next bank is normalised (normSize_Repr).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pop P] [--deck c5g7|c5g7_3d|inf|slab]
+
+value : whole-job neutrons/s with the bank resident in HBM (CUDA-event time, max over ranks)
+e2e   : the same through the host-buffer path of the C ABI (bank uploaded from pinned host memory and the
+        next bank + tally bins read back every step; wall clock, max over ranks)
+--impl reference : the CPU restatement of SCONE's own OpenMP history loop (oracle/, the reference itself is
+        Fortran and cannot be compiled in this image) on all host threads, same deck / pop / metric.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DECKS = {"c5g7": "decks/c5g7/c5g7_2d", "c5g7_3d": "decks/c5g7/c5g7_3d_rodded", "inf": "decks/urr/inf", "slab": "decks/urr/slab"}
+WORKLOAD = {"c5g7": "C5G7 MOX 2D 7-group eigenvalue, delta tracking (InputFiles/Benchmarks/Multigroup/C5G7 as decks/c5g7/c5g7_2d)",
+            "c5g7_3d": "C5G7 3D rodded-A 7-group eigenvalue with 34x34x9 flux+fission mesh, delta tracking",
+            "inf": "SCONE_Inf URRa-2-1-IN 2-group infinite medium", "slab": "SCONE_Slab URRa-2-1-SL 2-group slab (P1)"}
+ALG_BYTES_PER_SEGMENT = 124      # particle SoA read+write per flight segment
+ALG_BYTES_PER_SCORE = 16         # f64 read-modify-write per tally score
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_rate(deck, pop, n_inactive, seconds, threads):
+    """CPU arm: oracle (C++ restatement of SCONE's OpenMP loop) active-cycle neutrons/s on `threads` threads."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from tests import oracle_lib as ol
+    orc = ol.load()
+    ov = "pop %d; inactive %d; active 1000000; seed 20261017;" % (pop, n_inactive)
+    e = orc.orc_eigen_load(os.path.join(ROOT, deck).encode(), ov.encode())
+    if not e:
+        raise RuntimeError(ol.err(orc))
+    orc.orc_eigen_init_source(e)
+    k = orc.orc_eigen_keff0(e)
+    for _ in range(n_inactive):
+        k = orc.orc_eigen_cycle(e, 0, k)
+    seg0, c0, h0 = C.c_long(), C.c_long(), C.c_long()
+    orc.orc_eigen_stats(e, C.byref(seg0), C.byref(c0), C.byref(h0))
+    t0 = time.perf_counter(); n = 0
+    while True:
+        k = orc.orc_eigen_cycle(e, 1, k); n += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    seg1, c1, h1 = C.c_long(), C.c_long(), C.c_long()
+    orc.orc_eigen_stats(e, C.byref(seg1), C.byref(c1), C.byref(h1))
+    orc.orc_eigen_free(e)
+    return dict(nps=pop * n / dt, sps=(seg1.value - seg0.value) / dt, cycles=n, seconds=dt, k=k)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from tests import oracle_lib as ol
+    orc = ol.load()
+    deck = DECKS[args.deck]
+    pop = args.pop
+    ov = "pop %d; inactive %d; active 1000000; seed 20261017;" % (pop, args.inactive)
+    e = orc.orc_eigen_load(os.path.join(ROOT, deck).encode(), ov.encode())
+    if not e:
+        raise RuntimeError(ol.err(orc))
+    orc.orc_eigen_init_source(e)
+    k = orc.orc_eigen_keff0(e)
+    for _ in range(args.inactive):
+        k = orc.orc_eigen_cycle(e, 0, k)
+    for _ in range(args.warmup):
+        k = orc.orc_eigen_cycle(e, 1, k)
+    s0, c0, h0 = C.c_long(), C.c_long(), C.c_long()
+    orc.orc_eigen_stats(e, C.byref(s0), C.byref(c0), C.byref(h0))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        k = orc.orc_eigen_cycle(e, 1, k)
+    dt = time.perf_counter() - t0
+    s1, c1, h1 = C.c_long(), C.c_long(), C.c_long()
+    orc.orc_eigen_stats(e, C.byref(s1), C.byref(c1), C.byref(h1))
+    val = pop * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "active-cycle neutrons/s", "value": val, "unit": "neutrons/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": "DT",
+                   "note": "CPU reference arm: one step = one active cycle of pop histories on the host cores"},
+        "segments_per_s": (s1.value - s0.value) / dt, "keff": k,
+        "cpu_baseline": {"value": val, "unit": "neutrons/s", "cores": threads, "kind": "port",
+                         "sample": "%d active cycles of %d histories (oracle: C++/OpenMP restatement of SCONE's history loop; "
+                                   "SCONE itself is Fortran and no Fortran compiler exists in the image)" % (args.steps, pop)},
+        "e2e": {"value": val, "unit": "neutrons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own")
+    ap.add_argument("--deck", default="c5g7", choices=sorted(DECKS))
+    ap.add_argument("--pop", type=int, default=100000, help="histories per cycle PER GPU (weak scaling)")
+    ap.add_argument("--inactive", type=int, default=10, help="untimed inactive cycles before the active phase")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import scone_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    deck = os.path.join(ROOT, DECKS[args.deck])
+    pop = args.pop
+    total_pop = pop * world
+    ov = "pop %d; inactive %d; active %d; seed 20261017;" % (total_pop, args.inactive, args.warmup + 2 * args.steps + 4)
+    pp = scone_b200.EigenPhysicsPackage(deck, ov, device=local, rank=rank, n_ranks=world)
+    L = pp.L
+    eng = pp.engine
+    pp.generateInitialState()
+    pp.cycles(False, args.inactive)
+    for _ in range(max(3, args.warmup)):
+        pp.cycle(True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    flush = not args.no_l2_flush
+    FLUSH_BYTES = 256 << 20
+    # ---- device-resident arm: K active cycles, CUDA events on the engine stream --------------------------
+    sampler = ClockSampler(local); sampler.start()
+    L.sb_profile_enable(eng, 1)
+    launches0 = pp.launch_count()
+    barrier()
+    ms_total = 0.0; seg = 0; scores = 0; nsites = 0
+    ms = C.c_double()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush:
+            L.sb_flush_l2(eng, FLUSH_BYTES)
+        L.sb_timer_begin(eng)
+        res = pp.cycle(True)
+        L.sb_timer_end(eng, C.byref(ms))
+        ms_total += ms.value; seg += res.n_segments; scores += res.n_scores; nsites += res.n_sites
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = pp.launch_count() - launches0 - (args.steps if flush else 0) * 0
+    msk, nl, segp, scp = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+    L.sb_profile_read(eng, C.byref(msk), C.byref(nl), C.byref(segp), C.byref(scp))
+    L.sb_profile_enable(eng, 0)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    ms_max = maxreduce(ms_total)
+    value = total_pop * args.steps / (ms_max * 1e-3)
+    seg_all = sumreduce(float(seg))
+    k_dev, k_std = pp.k, res.k_cum_std
+
+    # ---- end-to-end arm: bank in pinned HOST memory, copied in and out every step ------------------------
+    pp.cycle(True, host_buffers=True)          # warm the host buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pp.cycle(True, host_buffers=True)
+    barrier()
+    t_e2e = maxreduce(time.perf_counter() - t0)
+    h2d, d2h = pp.host_bytes(True)
+    e2e_val = total_pop * args.steps / t_e2e
+
+    # ---- roofline of the dominant kernel (k_histories) -----------------------------------------------------
+    peak, peak_src = measured_peak()
+    alg_bytes = (ALG_BYTES_PER_SEGMENT * segp.value + ALG_BYTES_PER_SCORE * scp.value) / max(1, nl.value)
+    k_ms = msk.value / max(1, nl.value)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_histories_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "k_histories", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,
+                "note": "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)"}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            r = oracle_rate(DECKS[args.deck], pop, 3, args.cpu_seconds, threads)
+            cpu = {"value": r["nps"], "unit": "neutrons/s", "cores": threads, "kind": "port", "segments_per_s": r["sps"],
+                   "sample": "%d active cycles of %d histories in %.1f s (oracle: C++/OpenMP restatement of SCONE's history loop; "
+                             "SCONE is Fortran and cannot be compiled in this image)" % (r["cycles"], pop, r["seconds"])}
+        line = {
+            "metric": "active-cycle neutrons/s", "value": value, "unit": "neutrons/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD[args.deck], "deck": DECKS[args.deck], "pop_per_cycle_per_gpu": pop, "pop_per_cycle_total": total_pop,
+                       "tracking": "DT", "inactive_cycles_before": args.inactive,
+                       "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
+                       "parallelism": "bank sharded by history index over %d GPU(s)" % world},
+            "segments_per_s": seg_all / (ms_max * 1e-3), "segments_per_history": seg / max(1, pop * args.steps),
+            "keff": k_dev, "keff_std": k_std, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "e2e": {"value": e2e_val, "unit": "neutrons/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "clocks": sampler.summary(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    pp.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

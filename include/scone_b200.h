@@ -19,6 +19,7 @@
  */
 #ifndef SCONE_B200_H
 #define SCONE_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -116,7 +117,7 @@ typedef struct sb_cycle_result {
   double  imp_prod, imp_abs, scatter_prod, ana_leak;  /* keffImplicitClerk bins of the cycle   */
   double  k_analog, k_implicit;                        /* per-cycle estimates                   */
   double  k_cum, k_cum_std;   /* cumulative mean of this phase's attachment clerk = k_new      */
-  int64_t n_segments, n_collisions;
+  int64_t n_segments, n_collisions, n_scores;   /* flights, real collisions, tally scores (f64 accumulations) */
   int32_t error;              /* device-side fatal condition (SB_ERR_*), 0 if none             */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
@@ -159,6 +160,18 @@ int sb_resample(sb_engine* h, int tot_pop, uint64_t rng_state);
 int64_t sb_tally_size(sb_engine* h, int phase);
 int sb_tally_read(sb_engine* h, int phase, double* csum, double* csum2, int32_t* batch_n);
 int sb_tally_last_bins(sb_engine* h, int phase, double* bins);   /* BIN column of the last closed cycle, before normalisation */
+
+/* ---- measurement ------------------------------------------------------------------------------
+ * sb_timer_*: CUDA events on the engine's stream around whatever is issued in between.
+ * sb_profile_*: per-launch CUDA-event time of the history kernel, accumulated over cycles.          */
+int sb_timer_begin(sb_engine* h);
+int sb_timer_end(sb_engine* h, double* ms);
+int sb_profile_enable(sb_engine* h, int on);
+int sb_profile_read(sb_engine* h, double* ms_histories, int64_t* n_launches, int64_t* n_segments, int64_t* n_scores);
+int sb_flush_l2(sb_engine* h, size_t bytes);
+/* page-locked host memory for the banks the caller keeps (so that uploads/downloads are true async DMA) */
+void* sb_pinned_alloc(size_t bytes);
+void  sb_pinned_free(void* p);
 
 /* ---- batch queries used by the parity tests (same device functions as the cycle kernel) ---- */
 /* placeCoord / whatIsAt for n points; if dist != NULL teleport by dist[i] first (geometryStd teleport) */

@@ -39,7 +39,7 @@ struct CycleDev {        // small device-resident record of the running cycle
   unsigned long long thrState;
   double thrReal;
   double startWgt, endWgt, impProd, impAbs, scatProd, anaLeak, kAnalog, kImplicit, normFactor;
-  long long nSeg, nColl;
+  long long nSeg, nColl, nScore;
   // cumulative k of the attachment clerks: [phase] CSUM, CSUM2, batches
   double kCsum[2], kCsum2[2]; int kBatches[2];
   double kCum, kCumStd;
@@ -48,7 +48,7 @@ struct CycleDev {        // small device-resident record of the running cycle
 struct CycleArgs {
   Model M; const char* blob; int useSmem;
   int n; Bank in; Bank out; int cap;
-  int *nsites; double *hProd, *hAbs, *hLeak, *hScat; int *hSeg, *hColl;
+  int *nsites; double *hProd, *hAbs, *hLeak, *hScat; int *hSeg, *hColl, *hScore;
   double* bins; int phase;
   uint64_t rng0; int histOffset; double k_eff;
   CycleDev* cd; int chunk;
@@ -92,12 +92,12 @@ __device__ __forceinline__ void stageBlob(char* smem, const char* gsrc, int byte
 }
 
 // ------------------------------------------------------------------------------------------------
-// scoring of one collision (virtual or real) for the active-cycle tallies
+// scoring of one collision (virtual or real) for the cycle's tallies
 //   tallyAdmin%reportInColl -> collisionClerk%reportInColl (collisionClerk_class.f90:192-244)
 //                           -> keffImplicitClerk%reportInColl (keffImplicitClerk_class.f90:180-236)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void scoreInColl(const CycleArgs& a, const Tables& T, const char* base, const double r[3], int mat, int G,
-                                            double w, double trackXS, bool virt, double& sProd, double& sAbs) {
+                                            double w, double trackXS, bool virt, double& sProd, double& sAbs, int& nScore) {
   // in void macroResponse returns 0 and keffImplicitClerk returns early; fluxResponse still scores
   const bool isVoid = (mat == SB_VOID_MAT);
   const double* x = isVoid ? T.xs : mgRow(a.M, T, mat, G);
@@ -107,22 +107,22 @@ __device__ __forceinline__ void scoreInColl(const CycleArgs& a, const Tables& T,
   const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
   for (int c = 0; c < nC; ++c) {
     const DClerk& k = cl[c];
-    if (!k.handleVirtual && virt) continue;
+    if (!k.handleVirtual && (virt || isVoid)) continue;
     int bin = clerkBin(k, base, r, mat);
     if (bin == 0) continue;
-    if (isVoid && !k.handleVirtual) continue;
     double f = k.handleVirtual ? flux : w / (x[XS_TOTAL] + 0.0);
     int addr = k.addr + k.nResp * (bin - 1) - 1;      // 0-based slot of response 1
     for (int i = 0; i < k.nResp; ++i) {
       double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : mgResponse(x, fissile, k.respMT[i]));
       double s = resp * f;
-      if (s != 0.0) atomicAdd(a.bins + addr + i, s);
+      if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
     }
   }
   if (a.phase == 1 && !isVoid) {
     double nuf = fissile ? x[XS_NUFISSION] : 0.0, fis = fissile ? x[XS_FISSION] : 0.0;
     sProd += nuf * flux;
     sAbs += (x[XS_CAPTURE] + fis) * flux;
+    nScore += 2;
   }
 }
 
@@ -131,6 +131,12 @@ __device__ __forceinline__ void scoreInColl(const CycleArgs& a, const Tables& T,
 //   eigenPhysicsPackage_class.f90:213-252   history loop
 //   transportOperatorDT_class.f90:47-130    deltaTracking
 //   collisionProcessor_inter.f90:114-195 + neutronMGstd_class.f90:85-297   collide
+//
+// One loop iteration is one event round for the warp. Every piece of physics has exactly one call site
+// (flight, cell search, scoring, direction rotation) so that the loop body stays inside the instruction
+// cache; rare paths (boundary transformations, general CSG cells) are out of line.
+// Lane states: ST_FLIGHT (sample a distance and move), ST_REPLACE (position changed by a boundary
+// transformation: search again without moving).
 // ------------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) char g_smem[];
 
@@ -143,21 +149,20 @@ __global__ void __launch_bounds__(256, 2) k_histories(const CycleArgs a) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
+  const int borderS = M.borderIdx - 1;
 
-  // warp-private chunk of bank indices [cnext, cend)
-  int cnext = 0, cend = 0; bool exhausted = false;
+  int cnext = 0, cend = 0; bool exhausted = false;       // warp-private chunk of bank indices [cnext, cend)
 
-  // history state (registers)
-  bool alive = false;
+  bool alive = false, replace = false;
   int hi = -1;
-  double r[3], u[3], w = 0.0, w0 = 0.0; uint64_t rng = 0; int G = 0, mat = 0, uid = 0;
+  double r[3], u[3], w = 0.0, w0 = 0.0; uint64_t rng = 0; int G = 1, mat = 0, uid = 0;
   double trackXS = 1.0, majorant_inv = 1.0;
-  int nSite = 0, nSeg = 0, nColl = 0;
+  int nSite = 0, nSeg = 0, nColl = 0, nScore = 0;
   double sProd = 0.0, sAbs = 0.0, sLeak = 0.0, sScat = 0.0;
-  bool needMaj = true;
+  r[0] = r[1] = r[2] = 0.0; u[0] = 1.0; u[1] = u[2] = 0.0;
 
   for (;;) {
-    // ---------------- refill dead lanes from the warp's chunk --------------------------------
+    // ---------------- refill dead lanes from the warp's chunk (warp-level compaction) ---------------
     unsigned need = __ballot_sync(FULL, !alive);
     if (need) {
       if (cnext >= cend && !exhausted) {
@@ -174,42 +179,51 @@ __global__ void __launch_bounds__(256, 2) k_histories(const CycleArgs a) {
         u[0] = a.in.ux[hi]; u[1] = a.in.uy[hi]; u[2] = a.in.uz[hi];
         w = a.in.w[hi]; w0 = w; G = a.in.G[hi];
         rng = rng_skip(a.rng0, RNG_STRIDE * (int64_t)(a.histOffset + hi + 1));
-        if (!geomPlace(M, T, r, u, mat, uid)) atomicMax(&a.cd->error, SB_ERR_NEST);
-        nSite = 0; nSeg = 0; nColl = 0; sProd = 0.0; sAbs = 0.0; sLeak = 0.0; sScat = 0.0;
-        needMaj = true;
+        // geom%placeCoord of the source site is not needed by delta tracking: the first thing the flight
+        // does is teleport + placeCoord (transportOperatorDT_class.f90:57-75)
+        trackXS = mgMajorant(M, T, G); majorant_inv = 1.0 / trackXS;
+        nSite = 0; nSeg = 0; nColl = 0; nScore = 0; sProd = 0.0; sAbs = 0.0; sLeak = 0.0; sScat = 0.0;
+        replace = false;
         alive = true;
       }
       cnext = min(cend, cnext + __popc(need));
       if (exhausted && !__any_sync(FULL, alive)) break;
     }
 
-    // ---------------- event: tentative flight (delta tracking) --------------------------------
-    bool realColl = false;
-    bool died = false;
+    // ---------------- event: tentative flight = move + cell search ------------------------------------
+    bool realColl = false, died = false;
     if (alive) {
-      if (needMaj) { trackXS = mgMajorant(M, T, G); majorant_inv = 1.0 / trackXS; needMaj = false; }
-      double distance = -sbm::log(rng_get(rng)) * majorant_inv;
-      geomTeleport(M, T, r, u, distance, mat, uid);
-      ++nSeg;
-      if (mat == SB_OUTSIDE_MAT) { sLeak += w; died = true; }
-      else if (mat == SB_VOID_MAT) scoreInColl(a, T, base, r, mat, G, w, trackXS, true, sProd, sAbs);
-      else if (mat == SB_UNDEF_MAT) { atomicMax(&a.cd->error, SB_ERR_UNDEF_MAT); died = true; }
-      else if (mat == SB_OVERLAP_MAT) { atomicMax(&a.cd->error, SB_ERR_OVERLAP_MAT); died = true; }
-      else {
-        double sigmaT = mgRow(M, T, mat, G)[XS_TOTAL] + 0.0;
-        if (rng_get(rng) < sigmaT * majorant_inv) realColl = true;
-        else scoreInColl(a, T, base, r, mat, G, w, trackXS, true, sProd, sAbs);
+      if (!replace) {
+        double distance = -sbm::log(rng_get(rng)) * majorant_inv;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = r[i] + distance * u[i];
+        ++nSeg;
+      }
+      if (!geomPlace(M, T, r, u, mat, uid)) atomicMax(&a.cd->error, SB_ERR_NEST);
+      if (mat == SB_OUTSIDE_MAT) {
+        if (!replace && T.surfType[borderS] >= SB_SURF_BOX) {      // geometryStd%teleport: transformBC, then place again
+          surfTransformBCCold(T.surfType[borderS], T.surfPar + borderS * SB_SURF_NPAR, M.bc, r, u);
+          replace = true;
+        } else { sLeak += w; died = true; replace = false; }        // LEAK_FATE
+      } else {
+        replace = false;
+        if (mat >= SB_OVERLAP_MAT && mat != SB_VOID_MAT) { atomicMax(&a.cd->error, mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
+        else {
+          bool virt = true;
+          if (mat != SB_VOID_MAT) {
+            double sigmaT = mgRow(M, T, mat, G)[XS_TOTAL] + 0.0;
+            if (rng_get(rng) < sigmaT * majorant_inv) { realColl = true; virt = false; }
+          }
+          scoreInColl(a, T, base, r, mat, G, w, trackXS, virt, sProd, sAbs, nScore);
+        }
       }
     }
 
-    // ---------------- event: collision, part 1 (channel + number of fission sites) --------------
+    // ---------------- event: collision, part 1 (channel + number of fission sites) --------------------
     int MT = 0, nNew = 0;
-    const double* x = nullptr;
     if (realColl) {
-      x = mgRow(M, T, mat, G);
-      const bool fissile = T.fissile[mat - 1] != 0;
-      double rAlpha = rng_get(rng);                       // alpha-absorption test always draws (probAlpha = 0)
-      (void)rAlpha;
+      const double* x = mgRow(M, T, mat, G);
+      (void)rng_get(rng);                                 // alpha-absorption test always draws (probAlpha = 0)
       double rr = rng_get(rng);
       {                                                   // neutronMacroXSs%invert (neutronXsPackages_class.f90:211-250)
         int C = 1;
@@ -221,17 +235,16 @@ __global__ void __launch_bounds__(256, 2) k_histories(const CycleArgs a) {
         if (xs > 0.0) C += 1;
         MT = C;                                           // 1 elastic, 2 inelastic, 3 capture, 4 fission
       }
-      scoreInColl(a, T, base, r, mat, G, w, trackXS, false, sProd, sAbs);
       ++nColl;
-      if (fissile) {                                      // neutronMGstd implicit (:131-199)
+      if (T.fissile[mat - 1] != 0) {                      // neutronMGstd implicit (:131-199)
         double rand1 = rng_get(rng);
         nNew = (int)(fabs((w * x[XS_NUFISSION]) / (w0 * x[XS_TOTAL] * a.k_eff)) + rand1);
         if (nNew < 0) nNew = 0;
       }
     }
 
-    // ---------------- warp-aggregated allocation of fission-bank slots -------------------------
-    int slot = 0;
+    // ---------------- warp-aggregated allocation of fission-bank slots --------------------------------
+    int slot = -1;
     unsigned spawn = __ballot_sync(FULL, nNew > 0);
     if (spawn) {
       int inc = nNew;
@@ -242,54 +255,56 @@ __global__ void __launch_bounds__(256, 2) k_histories(const CycleArgs a) {
       if (lane == 0) b = atomicAdd(&a.cd->nSites, total);
       b = __shfl_sync(FULL, b, 0);
       slot = b + inc - nNew;
-      if (b + total > a.cap) { atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW); nNew = -nNew; }
+      if (b + total > a.cap) { atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW); slot = -1; }
     }
 
-    // ---------------- collision, part 2 (sites, then the sampled channel) ----------------------
+    // ---------------- collision, part 2: fission sites, then the scattered neutron --------------------
+    // one loop, one rotateVector: iterations 0..nNew-1 emit sites (fissionMG%sampleOut: mu, phi, then chi),
+    // the last iteration is the scattering itself (multiScatterMG%sampleOut: G_out, then mu, phi)
     if (realColl) {
-      const int nDraw = nNew < 0 ? -nNew : nNew;
       const double wSite = fsign(w0, w);
-      for (int i = 0; i < nDraw; ++i) {
-        double mu, phi;
-        int Gout = mgFissionSample(M, T, mat, mu, phi, rng);
-        if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = 1; }
+      const int nIter = nNew + (MT == 2 ? 1 : 0);
+      for (int i = 0; i < nIter; ++i) {
+        const bool isScat = (i == nNew);
+        const double* cdf = isScat ? T.P0 + ((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG : T.chi + (size_t)(mat - 1) * M.nG;
+        double mu = 0.0, phi = 0.0, rem;
+        if (isScat) rem = rng_get(rng) * mgRow(M, T, mat, G)[XS_IESCATTER];
+        else { mu = 2.0 * rng_get(rng) - 1.0; phi = TWO_PI * rng_get(rng); rem = rng_get(rng); }
+        int Gout = 0;
+        for (int g = 1; g <= M.nG; ++g) { rem = rem - cdf[g - 1]; if (rem < 0.0) { Gout = g; break; } }
+        if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = G; }
+        if (isScat) {
+          if (M.isP1) mu = sampleLegendreP1(T.P1[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)], rng);
+          else mu = 2.0 * rng_get(rng) - 1.0;
+          phi = TWO_PI * rng_get(rng);
+        }
         double d[3] = {u[0], u[1], u[2]};
         rotateVector(d, mu, phi);
-        if (nNew > 0) {
+        if (isScat) {                                       // neutronMGstd inelastic (:221-252)
+          double w_mul = T.prod[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)];
+          double wPre = w;
+          G = Gout;
+          trackXS = mgMajorant(M, T, G); majorant_inv = 1.0 / trackXS;
+          w = w * w_mul;
+          u[0] = d[0]; u[1] = d[1]; u[2] = d[2];
+          double sc = fmax(w - wPre, 0.0);                   // keffImplicitClerk%reportOutColl
+          if (sc > 0.0) sScat += sc;
+        } else if (slot >= 0) {
           int s = slot + i;
           a.out.rx[s] = r[0]; a.out.ry[s] = r[1]; a.out.rz[s] = r[2];
           a.out.ux[s] = d[0]; a.out.uy[s] = d[1]; a.out.uz[s] = d[2];
           a.out.w[s] = wSite; a.out.G[s] = Gout; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
         }
       }
-      nSite += nDraw;
-      if (MT == 2) {                                      // inelastic (:221-252), multiScatterMG%sampleOut
-        const double* P0 = T.P0 + ((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG;
-        double rem = rng_get(rng) * x[XS_IESCATTER];
-        int Gout = 0;
-        for (int g = 1; g <= M.nG; ++g) { rem = rem - P0[g - 1]; if (rem < 0.0) { Gout = g; break; } }
-        if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = G; }
-        double mu;
-        if (M.isP1) mu = sampleLegendreP1(T.P1[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)], rng);
-        else mu = 2.0 * rng_get(rng) - 1.0;
-        double phi = TWO_PI * rng_get(rng);
-        double w_mul = T.prod[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)];
-        double wPre = w;
-        G = Gout; needMaj = true;
-        w = w * w_mul;
-        rotateVector(u, mu, phi);
-        double sc = fmax(w - wPre, 0.0);                   // keffImplicitClerk%reportOutColl
-        if (sc > 0.0) sScat += sc;
-      } else if (MT == 3 || MT == 4) {
-        died = true;                                       // capture / fission: history ends (ABS_FATE)
-      }
+      nSite += nNew;
+      if (MT == 3 || MT == 4) died = true;                   // capture / fission: history ends (ABS_FATE)
       // MT == 1 (elastic) cannot be selected for MG data (elasticScatter = 0): "Do nothing"
     }
 
     if (died) {
       a.nsites[hi] = nSite;
       a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
-      a.hSeg[hi] = nSeg; a.hColl[hi] = nColl;
+      a.hSeg[hi] = nSeg; a.hColl[hi] = nColl; a.hScore[hi] = nScore;
       alive = false;
     }
   }
@@ -392,7 +407,7 @@ __global__ void k_sort_sites(Bank src, Bank dst, const int* offsets, const Cycle
 // ------------------------------------------------------------------------------------------------
 constexpr int RED_BLOCKS = 592;      // 4 per SM on 148 SMs; the tiling is a constant of the algorithm
 constexpr int RED_THREADS = 256;
-struct RedOut { double prod, abs, leak, scat, wgt; long long seg, coll; };
+struct RedOut { double prod, abs, leak, scat, wgt; long long seg, coll, score; };
 
 __device__ __forceinline__ double warpSum(double v) {
 #pragma unroll
@@ -404,20 +419,20 @@ __device__ __forceinline__ long long warpSumLL(long long v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
   return v;
 }
-__device__ __forceinline__ void blockReduce7(double v[5], long long c[2], RedOut* out) {
+__device__ __forceinline__ void blockReduce7(double v[5], long long c[3], RedOut* out) {
   __shared__ double sd[5][RED_THREADS / 32];
-  __shared__ long long sc[2][RED_THREADS / 32];
+  __shared__ long long sc[3][RED_THREADS / 32];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { double s = warpSum(v[k]); if (lane == 0) sd[k][wid] = s; }
 #pragma unroll
-  for (int k = 0; k < 2; ++k) { long long s = warpSumLL(c[k]); if (lane == 0) sc[k][wid] = s; }
+  for (int k = 0; k < 3; ++k) { long long s = warpSumLL(c[k]); if (lane == 0) sc[k][wid] = s; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    RedOut o = {0, 0, 0, 0, 0, 0, 0};
+    RedOut o = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < RED_THREADS / 32; ++i) {
       o.prod += sd[0][i]; o.abs += sd[1][i]; o.leak += sd[2][i]; o.scat += sd[3][i]; o.wgt += sd[4][i];
-      o.seg += sc[0][i]; o.coll += sc[1][i];
+      o.seg += sc[0][i]; o.coll += sc[1][i]; o.score += sc[2][i];
     }
     *out = o;
   }
@@ -427,10 +442,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(const CycleArgs a, 
   int n = a.n;
   int per = (n + RED_BLOCKS - 1) / RED_BLOCKS;
   int b0 = blockIdx.x * per, b1 = min(n, b0 + per);
-  double v[5] = {0, 0, 0, 0, 0}; long long c[2] = {0, 0};
+  double v[5] = {0, 0, 0, 0, 0}; long long c[3] = {0, 0, 0};
   for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) {
     v[0] += a.hProd[i]; v[1] += a.hAbs[i]; v[2] += a.hLeak[i]; v[3] += a.hScat[i]; v[4] += a.in.w[i];
-    c[0] += a.hSeg[i]; c[1] += a.hColl[i];
+    c[0] += a.hSeg[i]; c[1] += a.hColl[i]; c[2] += a.hScore[i];
   }
   blockReduce7(v, c, partial + blockIdx.x);
 }
@@ -453,14 +468,14 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_wgt(const double* w, con
 __global__ void k_close_cycle_head(const RedOut* partial, const double* wPartial, CycleDev* cd, int phase, double kNorm,
                                    const double* bins, int normAddr, double normVal) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  RedOut o = {0, 0, 0, 0, 0, 0, 0}; double endW = 0.0;
+  RedOut o = {0, 0, 0, 0, 0, 0, 0, 0}; double endW = 0.0;
   for (int i = 0; i < RED_BLOCKS; ++i) {
     o.prod += partial[i].prod; o.abs += partial[i].abs; o.leak += partial[i].leak; o.scat += partial[i].scat; o.wgt += partial[i].wgt;
-    o.seg += partial[i].seg; o.coll += partial[i].coll; endW += wPartial[i];
+    o.seg += partial[i].seg; o.coll += partial[i].coll; o.score += partial[i].score; endW += wPartial[i];
   }
   cd->startWgt = o.wgt; cd->endWgt = endW;
   cd->impProd = o.prod; cd->impAbs = o.abs; cd->anaLeak = o.leak; cd->scatProd = o.scat;
-  cd->nSeg = o.seg; cd->nColl = o.coll;
+  cd->nSeg = o.seg; cd->nColl = o.coll; cd->nScore = o.score;
   cd->kAnalog = endW / o.wgt * kNorm;
   cd->kImplicit = o.prod / (o.abs + o.leak - o.scat);
   double k = (phase == 0) ? cd->kAnalog : cd->kImplicit;
@@ -690,6 +705,20 @@ __global__ void k_cycle_begin(CycleDev* cd, int* nCur, int n) {
   cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; cd->nNew = 0;
   *nCur = n;
 }
+// particleState arrays cross the boundary as r(3,n), dir(3,n) (Fortran order); banks are SoA on the device
+__global__ void k_bank_unpack(const double* r, const double* d, Bank b, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    b.rx[i] = r[3 * (size_t)i]; b.ry[i] = r[3 * (size_t)i + 1]; b.rz[i] = r[3 * (size_t)i + 2];
+    b.ux[i] = d[3 * (size_t)i]; b.uy[i] = d[3 * (size_t)i + 1]; b.uz[i] = d[3 * (size_t)i + 2];
+    b.brood[i] = 0; b.seq[i] = 0;
+  }
+}
+__global__ void k_bank_pack(Bank b, double* r, double* d, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    r[3 * (size_t)i] = b.rx[i]; r[3 * (size_t)i + 1] = b.ry[i]; r[3 * (size_t)i + 2] = b.rz[i];
+    d[3 * (size_t)i] = b.ux[i]; d[3 * (size_t)i + 1] = b.uy[i]; d[3 * (size_t)i + 2] = b.uz[i];
+  }
+}
 __global__ void k_zero_int(int* p, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0; }
 
 // ================================================================================================
@@ -713,7 +742,7 @@ struct sb_engine {
   // banks
   int cap = 0; Bank bank[3]{}; int cur = 0;          // bank[cur] = this cycle; others: raw sites, sorted/next
   int nCur = 0;
-  int *dNsites = nullptr, *dOffsets = nullptr, *dTile = nullptr, *dFlag = nullptr, *dFlagOff = nullptr, *dHist = nullptr, *dHSeg = nullptr, *dHColl = nullptr;
+  int *dNsites = nullptr, *dOffsets = nullptr, *dTile = nullptr, *dFlag = nullptr, *dFlagOff = nullptr, *dHist = nullptr, *dHSeg = nullptr, *dHColl = nullptr, *dHScore = nullptr;
   double *dHProd = nullptr, *dHAbs = nullptr, *dHLeak = nullptr, *dHScat = nullptr;
   unsigned long long *dRn = nullptr, *dCand = nullptr;
   RedOut* dPartial = nullptr; double* dWPartial = nullptr;
@@ -723,6 +752,10 @@ struct sb_engine {
   double bounds[6] = {0, 0, 0, 0, 0, 0};
   double kNormNext = 1.0;   // nextCycle%k_eff of the dungeon that will receive the sites (keffAnalogClerk k_norm)
   bool sortedReady = false;
+  // measurement
+  bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
+  double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
+  double* dStage = nullptr; size_t stageBytes = 0;
 };
 
 static std::string g_globalErr;
@@ -745,11 +778,11 @@ static int ensureCapacity(sb_engine* h, int maxPop) {
   CUDA_OK(cudaSetDevice(h->device));
   for (int i = 0; i < 3; ++i) { freeBank(h->bank[i]); if (allocBank(h, h->bank[i], cap)) return -1; }
   cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
-  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
+  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHScore); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   CUDA_OK(cudaMalloc(&h->dNsites, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dOffsets, sizeof(int) * cap));
   CUDA_OK(cudaMalloc(&h->dTile, sizeof(int) * (cap / SCAN_TILE + 2)));
   CUDA_OK(cudaMalloc(&h->dFlag, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dFlagOff, sizeof(int) * cap));
-  CUDA_OK(cudaMalloc(&h->dHSeg, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dHColl, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&h->dHSeg, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dHColl, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dHScore, sizeof(int) * cap));
   CUDA_OK(cudaMalloc(&h->dHProd, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHAbs, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&h->dHLeak, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHScat, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&h->dRn, sizeof(unsigned long long) * cap));
@@ -846,6 +879,7 @@ int sb_create(sb_engine** out, int device) {
   cudaMalloc(&h->dPartial, sizeof(RedOut) * RED_BLOCKS); cudaMalloc(&h->dWPartial, sizeof(double) * RED_BLOCKS);
   cudaMalloc(&h->dHist, sizeof(int) * SEL_BINS); cudaMalloc(&h->dCand, sizeof(unsigned long long) * SEL_CAND_CAP);
   cudaMalloc(&h->dNcur, sizeof(int));
+  cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
   *out = h;
   return 0;
 }
@@ -855,9 +889,10 @@ void sb_destroy(sb_engine* h) {
   cudaSetDevice(h->device);
   for (int i = 0; i < 3; ++i) freeBank(h->bank[i]);
   cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
-  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
+  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHScore); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dWPartial); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
+  cudaFree(h->dStage);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -957,21 +992,27 @@ int sb_set_options(sb_engine* h, const sb_options* o) {
 
 int sb_bank_size(sb_engine* h) { return h->nCur; }
 
+static int ensureStage(sb_engine* h, size_t bytes) {
+  if (bytes <= h->stageBytes) return 0;
+  cudaFree(h->dStage);
+  CUDA_OK(cudaMalloc(&h->dStage, bytes));
+  h->stageBytes = bytes;
+  return 0;
+}
+
 int sb_bank_upload(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G) {
   if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
   CUDA_OK(cudaSetDevice(h->device));
-  std::vector<double> t((size_t)n);
+  if (ensureStage(h, sizeof(double) * 6 * (size_t)h->cap)) return -1;
   Bank& b = h->bank[h->cur];
-  double* dst[6] = {b.rx, b.ry, b.rz, b.ux, b.uy, b.uz};
-  for (int k = 0; k < 6; ++k) {
-    const double* src = k < 3 ? r : dir; int c = k % 3;
-    for (int i = 0; i < n; ++i) t[i] = src[3 * (size_t)i + c];
-    CUDA_OK(cudaMemcpyAsync(dst[k], t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-    CUDA_OK(cudaStreamSynchronize(h->stream));
-  }
-  CUDA_OK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  CUDA_OK(cudaMemcpyAsync(b.G, G, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaStream_t st = h->stream;
+  CUDA_OK(cudaMemcpyAsync(h->dStage, r, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(h->dStage + 3 * (size_t)h->cap, dir, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(b.G, G, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  k_bank_unpack<<<gridFor(h, n, 256), 256, 0, st>>>(h->dStage, h->dStage + 3 * (size_t)h->cap, b, n);
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(st));
   h->nCur = n;
   return 0;
 }
@@ -981,18 +1022,17 @@ int sb_bank_download(sb_engine* h, int cap, int* n, double* r, double* dir, doub
   int m = h->nCur;
   *n = m;
   if (m > cap) { h->err = "sb_bank_download: buffer too small"; return -1; }
-  std::vector<double> t((size_t)std::max(1, m));
+  if (m == 0) return 0;
+  if (ensureStage(h, sizeof(double) * 6 * (size_t)h->cap)) return -1;
   Bank& b = h->bank[h->cur];
-  double* src[6] = {b.rx, b.ry, b.rz, b.ux, b.uy, b.uz};
-  for (int k = 0; k < 6; ++k) {
-    CUDA_OK(cudaMemcpyAsync(t.data(), src[k], sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(cudaStreamSynchronize(h->stream));
-    double* dst = k < 3 ? r : dir; int c = k % 3;
-    for (int i = 0; i < m; ++i) dst[3 * (size_t)i + c] = t[i];
-  }
-  CUDA_OK(cudaMemcpyAsync(w, b.w, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaMemcpyAsync(G, b.G, sizeof(int) * m, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaStream_t st = h->stream;
+  k_bank_pack<<<gridFor(h, m, 256), 256, 0, st>>>(b, h->dStage, h->dStage + 3 * (size_t)h->cap, m);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(r, h->dStage, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(dir, h->dStage + 3 * (size_t)h->cap, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(w, b.w, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(G, b.G, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1043,7 +1083,7 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   CycleArgs a;
   a.M = h->M; a.blob = h->dBlob; a.useSmem = h->useSmem;
   a.n = n; a.in = in; a.out = raw; a.cap = h->cap;
-  a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat; a.hSeg = h->dHSeg; a.hColl = h->dHColl;
+  a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat; a.hSeg = h->dHSeg; a.hColl = h->dHColl; a.hScore = h->dHScore;
   a.bins = h->dBins[phase]; a.phase = phase;
   a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
   const int threads = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 256;
@@ -1054,7 +1094,9 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   long long warps = (long long)blocks * (threads / 32);
   int chunk = (int)(n / (4 * warps)); if (chunk < 1) chunk = 1; if (chunk > 128) chunk = 128;
   a.chunk = chunk;
+  if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
   k_histories<<<blocks, threads, h->useSmem ? h->M.blobBytes : 0, st>>>(a);
+  if (h->profiling) CUDA_OK(cudaEventRecord(h->evK1, st));
   h->launches++;
 
   // brood offsets = exclusive scan of per-history site counts ; stable brood order
@@ -1075,11 +1117,15 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
   const CycleDev& c = *h->hCd;
+  if (h->profiling) {
+    float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, h->evK0, h->evK1));
+    h->msHistories += ms; h->nHistLaunches++; h->segProfiled += c.nSeg; h->scoreProfiled += c.nScore;
+  }
   if (res) {
     res->n_start = n; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
     res->imp_prod = c.impProd; res->imp_abs = c.impAbs; res->scatter_prod = c.scatProd; res->ana_leak = c.anaLeak;
     res->k_analog = c.kAnalog; res->k_implicit = c.kImplicit; res->k_cum = c.kCum; res->k_cum_std = c.kCumStd;
-    res->n_segments = c.nSeg; res->n_collisions = c.nColl; res->error = c.error;
+    res->n_segments = c.nSeg; res->n_collisions = c.nColl; res->n_scores = c.nScore; res->error = c.error;
   }
   h->sortedReady = true;
   return checkDeviceError(h, c.error);
@@ -1134,6 +1180,27 @@ int sb_tally_last_bins(sb_engine* h, int phase, double* bins) {
   if (phase < 0 || phase > 1) { h->err = "phase must be 0 or 1"; return -1; }
   CUDA_OK(cudaSetDevice(h->device));
   if (h->nBins[phase] > 0 && h->dLast[phase]) CUDA_OK(cudaMemcpy(bins, h->dLast[phase], sizeof(double) * h->nBins[phase], cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- measurement -----------------------------------------------------------------------------------
+int sb_profile_enable(sb_engine* h, int on) { h->profiling = on != 0; h->msHistories = 0.0; h->nHistLaunches = 0; h->segProfiled = 0; h->scoreProfiled = 0; return 0; }
+int sb_profile_read(sb_engine* h, double* ms_histories, int64_t* n_launches, int64_t* n_segments, int64_t* n_scores) {
+  *ms_histories = h->msHistories; *n_launches = h->nHistLaunches; *n_segments = h->segProfiled; *n_scores = h->scoreProfiled; return 0;
+}
+int sb_timer_begin(sb_engine* h) { CUDA_OK(cudaSetDevice(h->device)); CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaEventRecord(h->evT0, h->stream)); return 0; }
+int sb_timer_end(sb_engine* h, double* ms) {
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaEventRecord(h->evT1, h->stream)); CUDA_OK(cudaEventSynchronize(h->evT1));
+  float f = 0.f; CUDA_OK(cudaEventElapsedTime(&f, h->evT0, h->evT1)); *ms = f; return 0;
+}
+void* sb_pinned_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
+void sb_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+// writes `bytes` of device memory (> L2) so that the next timed step starts with a cold L2
+int sb_flush_l2(sb_engine* h, size_t bytes) {
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ensureStage(h, bytes)) return -1;
+  CUDA_OK(cudaMemsetAsync(h->dStage, 0, bytes, h->stream));
   return 0;
 }
 

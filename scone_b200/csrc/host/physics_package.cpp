@@ -33,7 +33,7 @@ struct eigenPhysicsPackage {
   long long nSegActive = 0, nSegInactive = 0, nHist = 0;
   double timeTransport = 0.0;
   // host copy of the bank for the end-to-end (host buffer) mode
-  std::vector<double> hr, hdir, hw; std::vector<int32_t> hG; int hN = 0;
+  double *hr = nullptr, *hdir = nullptr, *hw = nullptr; int32_t* hG = nullptr; int hN = 0, hCap = 0;   // page-locked
   std::vector<double> hBins;
 
   static std::string dirName(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? "." : p.substr(0, k); }
@@ -123,7 +123,7 @@ struct eigenPhysicsPackage {
   int cycleHostBuffers(int active, double& k_new) {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (hN == 0) { if (downloadBank()) return -1; }
-    if (sb_bank_upload(eng, hN, hr.data(), hdir.data(), hw.data(), hG.data())) return engFail();
+    if (sb_bank_upload(eng, hN, hr, hdir, hw, hG)) return engFail();
     if (sb_run_cycle(eng, pRNG, 0, k_new, active, &last)) return engFail();
     stride(totalPop + 1);
     if (sb_resample(eng, pop, pRNG)) return engFail();
@@ -139,8 +139,14 @@ struct eigenPhysicsPackage {
   }
   int downloadBank() {
     int cap = 2 * pop;
-    hr.resize(3 * (size_t)cap); hdir.resize(3 * (size_t)cap); hw.resize(cap); hG.resize(cap);
-    if (sb_bank_download(eng, cap, &hN, hr.data(), hdir.data(), hw.data(), hG.data())) return engFail();
+    if (cap > hCap) {
+      sb_pinned_free(hr); sb_pinned_free(hdir); sb_pinned_free(hw); sb_pinned_free(hG);
+      hr = (double*)sb_pinned_alloc(sizeof(double) * 3 * (size_t)cap); hdir = (double*)sb_pinned_alloc(sizeof(double) * 3 * (size_t)cap);
+      hw = (double*)sb_pinned_alloc(sizeof(double) * (size_t)cap); hG = (int32_t*)sb_pinned_alloc(sizeof(int32_t) * (size_t)cap);
+      if (!hr || !hdir || !hw || !hG) return fail("pinned host allocation failed");
+      hCap = cap;
+    }
+    if (sb_bank_download(eng, cap, &hN, hr, hdir, hw, hG)) return engFail();
     return 0;
   }
 
@@ -168,7 +174,12 @@ void* sbh_eigen_create(const char* deckPath, const char* overrides, int device, 
   if (p->init(deckPath, overrides, device, rank, nRanks < 1 ? 1 : nRanks)) { g_sbhErr = p->err; if (p->eng) sb_destroy(p->eng); delete p; return nullptr; }
   return p;
 }
-void sbh_eigen_destroy(void* pv) { auto* p = (eigenPhysicsPackage*)pv; if (!p) return; if (p->eng) sb_destroy(p->eng); delete p; }
+void sbh_eigen_destroy(void* pv) {
+  auto* p = (eigenPhysicsPackage*)pv; if (!p) return;
+  sb_pinned_free(p->hr); sb_pinned_free(p->hdir); sb_pinned_free(p->hw); sb_pinned_free(p->hG);
+  if (p->eng) sb_destroy(p->eng);
+  delete p;
+}
 sb_engine* sbh_engine(void* pv) { return ((eigenPhysicsPackage*)pv)->eng; }
 int sbh_eigen_info(void* pv, int* pop, int* nInactive, int* nActive, int* nG, int* nMat, int* nGraph, int* uniqueCells) {
   auto* p = (eigenPhysicsPackage*)pv;

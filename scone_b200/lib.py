@@ -20,7 +20,7 @@ class CycleResult(C.Structure):
                 ("start_wgt", C.c_double), ("end_wgt", C.c_double),
                 ("imp_prod", C.c_double), ("imp_abs", C.c_double), ("scatter_prod", C.c_double), ("ana_leak", C.c_double),
                 ("k_analog", C.c_double), ("k_implicit", C.c_double), ("k_cum", C.c_double), ("k_cum_std", C.c_double),
-                ("n_segments", C.c_int64), ("n_collisions", C.c_int64), ("error", C.c_int32)]
+                ("n_segments", C.c_int64), ("n_collisions", C.c_int64), ("n_scores", C.c_int64), ("error", C.c_int32)]
 
 
 def load_library():
@@ -47,6 +47,10 @@ def load_library():
         "sb_resample": (i32, [vp, i32, u64]),
         "sb_tally_size": (i64, [vp, i32]), "sb_tally_read": (i32, [vp, i32, dp, dp, ip]), "sb_tally_last_bins": (i32, [vp, i32, dp]),
         "sb_geom_query": (i32, [vp, i64, dp, dp, dp, ip, ip]), "sb_mg_query": (i32, [vp, i64, ip, ip, dp, dp]),
+        "sb_timer_begin": (i32, [vp]), "sb_timer_end": (i32, [vp, dp]),
+        "sb_profile_enable": (i32, [vp, i32]),
+        "sb_profile_read": (i32, [vp, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "sb_flush_l2": (i32, [vp, C.c_size_t]), "sb_pinned_alloc": (vp, [C.c_size_t]), "sb_pinned_free": (None, [vp]),
         "sb_rng_query": (i32, [i64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), dp]),
         "sb_math_query": (i32, [i64, dp, dp, dp, dp]),
         # host driver (scone_b200/csrc/host/physics_package.cpp)
