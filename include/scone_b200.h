@@ -119,6 +119,7 @@ typedef struct sb_cycle_result {
   double  k_cum, k_cum_std;   /* cumulative mean of this phase's attachment clerk = k_new      */
   int64_t n_segments, n_collisions, n_scores;   /* flights, real collisions, tally scores (f64 accumulations) */
   int32_t error;              /* device-side fatal condition (SB_ERR_*), 0 if none             */
+  int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
        SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7 };

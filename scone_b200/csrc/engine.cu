@@ -17,298 +17,19 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "sb_device.cuh"
+#include "sb_hist.cuh"
 
 using namespace sbd;
-
-// ------------------------------------------------------------------------------------------------
-// device data structures
-// ------------------------------------------------------------------------------------------------
-struct Bank {            // particleDungeon as structure of arrays
-  double *rx, *ry, *rz, *ux, *uy, *uz, *w;
-  int *G, *brood, *seq;
-};
-
-struct CycleDev {        // small device-resident record of the running cycle
-  int nStart, nSites, nextHistory, error;
-  int selBin, selRank, nCand, nNew;
-  unsigned long long thrState;
-  double thrReal;
-  double startWgt, endWgt, impProd, impAbs, scatProd, anaLeak, kAnalog, kImplicit, normFactor;
-  long long nSeg, nColl, nScore;
-  // cumulative k of the attachment clerks: [phase] CSUM, CSUM2, batches
-  double kCsum[2], kCsum2[2]; int kBatches[2];
-  double kCum, kCumStd;
-};
-
-struct CycleArgs {
-  Model M; const char* blob; int useSmem;
-  int n; Bank in; Bank out; int cap;
-  int *nsites; double *hProd, *hAbs, *hLeak, *hScat; int *hSeg, *hColl, *hScore;
-  double* bins; int phase;
-  uint64_t rng0; int histOffset; double k_eff;
-  CycleDev* cd; int chunk;
-};
+using sbh::Bank; using sbh::CycleDev; using sbh::HistArgs; using sbh::HotLayout; using sbh::HUni;
 
 #define CUDA_OK(call)                                                                         \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// bulk async copy global -> shared (TMA 1-D) with an mbarrier; falls back to a plain loop if the
-// size is not a multiple of 16 (the blob is padded so it always is)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stageBlob(char* smem, const char* gsrc, int bytes, uint64_t* bar) {
-  if (threadIdx.x == 0) {
-    unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
-    // one bulk copy per <= 64 KiB piece keeps each request small
-    int off = 0;
-    while (off < bytes) {
-      int piece = min(bytes - off, 32768);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst + off), "l"(gsrc + off), "r"(piece), "r"(barAddr) : "memory");
-      off += piece;
-    }
-  }
-  {
-    unsigned barAddr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned done = 0;
-    while (!done) {
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(done) : "r"(barAddr) : "memory");
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// scoring of one collision (virtual or real) for the cycle's tallies
-//   tallyAdmin%reportInColl -> collisionClerk%reportInColl (collisionClerk_class.f90:192-244)
-//                           -> keffImplicitClerk%reportInColl (keffImplicitClerk_class.f90:180-236)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void scoreInColl(const CycleArgs& a, const Tables& T, const char* base, const double r[3], int mat, int G,
-                                            double w, double trackXS, bool virt, double& sProd, double& sAbs, int& nScore) {
-  // in void macroResponse returns 0 and keffImplicitClerk returns early; fluxResponse still scores
-  const bool isVoid = (mat == SB_VOID_MAT);
-  const double* x = isVoid ? T.xs : mgRow(a.M, T, mat, G);
-  const bool fissile = isVoid ? false : (T.fissile[mat - 1] != 0);
-  const double flux = w / trackXS;
-  const int nC = a.M.nClerk[a.phase];
-  const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
-  for (int c = 0; c < nC; ++c) {
-    const DClerk& k = cl[c];
-    if (!k.handleVirtual && (virt || isVoid)) continue;
-    int bin = clerkBin(k, base, r, mat);
-    if (bin == 0) continue;
-    double f = k.handleVirtual ? flux : w / (x[XS_TOTAL] + 0.0);
-    int addr = k.addr + k.nResp * (bin - 1) - 1;      // 0-based slot of response 1
-    for (int i = 0; i < k.nResp; ++i) {
-      double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : mgResponse(x, fissile, k.respMT[i]));
-      double s = resp * f;
-      if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
-    }
-  }
-  if (a.phase == 1 && !isVoid) {
-    double nuf = fissile ? x[XS_NUFISSION] : 0.0, fis = fissile ? x[XS_FISSION] : 0.0;
-    sProd += nuf * flux;
-    sAbs += (x[XS_CAPTURE] + fis) * flux;
-    nScore += 2;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The history kernel (delta tracking + neutronMGstd collisions)
-//   eigenPhysicsPackage_class.f90:213-252   history loop
-//   transportOperatorDT_class.f90:47-130    deltaTracking
-//   collisionProcessor_inter.f90:114-195 + neutronMGstd_class.f90:85-297   collide
-//
-// One loop iteration is one event round for the warp. Every piece of physics has exactly one call site
-// (flight, cell search, scoring, direction rotation) so that the loop body stays inside the instruction
-// cache; rare paths (boundary transformations, general CSG cells) are out of line.
-// Lane states: ST_FLIGHT (sample a distance and move), ST_REPLACE (position changed by a boundary
-// transformation: search again without moving).
-// ------------------------------------------------------------------------------------------------
-extern __shared__ __align__(16) char g_smem[];
-
-__global__ void __launch_bounds__(256, 2) k_histories(const CycleArgs a) {
-  __shared__ __align__(8) uint64_t s_bar;
-  const char* base = a.blob;
-  if (a.useSmem) { stageBlob(g_smem, a.blob, a.M.blobBytes, &s_bar); base = g_smem; }
-  const Tables T = bind(a.M, base);
-  const Model& M = a.M;
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned ltMask = (1u << lane) - 1u;
-  const int borderS = M.borderIdx - 1;
-
-  int cnext = 0, cend = 0; bool exhausted = false;       // warp-private chunk of bank indices [cnext, cend)
-
-  bool alive = false, replace = false;
-  int hi = -1;
-  double r[3], u[3], w = 0.0, w0 = 0.0; uint64_t rng = 0; int G = 1, mat = 0, uid = 0;
-  double trackXS = 1.0, majorant_inv = 1.0;
-  int nSite = 0, nSeg = 0, nColl = 0, nScore = 0;
-  double sProd = 0.0, sAbs = 0.0, sLeak = 0.0, sScat = 0.0;
-  r[0] = r[1] = r[2] = 0.0; u[0] = 1.0; u[1] = u[2] = 0.0;
-
-  for (;;) {
-    // ---------------- refill dead lanes from the warp's chunk (warp-level compaction) ---------------
-    unsigned need = __ballot_sync(FULL, !alive);
-    if (need) {
-      if (cnext >= cend && !exhausted) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(&a.cd->nextHistory, a.chunk);
-        b = __shfl_sync(FULL, b, 0);
-        if (b >= a.n) { exhausted = true; cnext = cend = 0; }
-        else { cnext = b; cend = min(b + a.chunk, a.n); }
-      }
-      int my = cnext + __popc(need & ltMask);
-      if (!alive && my < cend) {
-        hi = my;
-        r[0] = a.in.rx[hi]; r[1] = a.in.ry[hi]; r[2] = a.in.rz[hi];
-        u[0] = a.in.ux[hi]; u[1] = a.in.uy[hi]; u[2] = a.in.uz[hi];
-        w = a.in.w[hi]; w0 = w; G = a.in.G[hi];
-        rng = rng_skip(a.rng0, RNG_STRIDE * (int64_t)(a.histOffset + hi + 1));
-        // geom%placeCoord of the source site is not needed by delta tracking: the first thing the flight
-        // does is teleport + placeCoord (transportOperatorDT_class.f90:57-75)
-        trackXS = mgMajorant(M, T, G); majorant_inv = 1.0 / trackXS;
-        nSite = 0; nSeg = 0; nColl = 0; nScore = 0; sProd = 0.0; sAbs = 0.0; sLeak = 0.0; sScat = 0.0;
-        replace = false;
-        alive = true;
-      }
-      cnext = min(cend, cnext + __popc(need));
-      if (exhausted && !__any_sync(FULL, alive)) break;
-    }
-
-    // ---------------- event: tentative flight = move + cell search ------------------------------------
-    bool realColl = false, died = false;
-    if (alive) {
-      if (!replace) {
-        double distance = -sbm::log(rng_get(rng)) * majorant_inv;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = r[i] + distance * u[i];
-        ++nSeg;
-      }
-      if (!geomPlace(M, T, r, u, mat, uid)) atomicMax(&a.cd->error, SB_ERR_NEST);
-      if (mat == SB_OUTSIDE_MAT) {
-        if (!replace && T.surfType[borderS] >= SB_SURF_BOX) {      // geometryStd%teleport: transformBC, then place again
-          surfTransformBCCold(T.surfType[borderS], T.surfPar + borderS * SB_SURF_NPAR, M.bc, r, u);
-          replace = true;
-        } else { sLeak += w; died = true; replace = false; }        // LEAK_FATE
-      } else {
-        replace = false;
-        if (mat >= SB_OVERLAP_MAT && mat != SB_VOID_MAT) { atomicMax(&a.cd->error, mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
-        else {
-          bool virt = true;
-          if (mat != SB_VOID_MAT) {
-            double sigmaT = mgRow(M, T, mat, G)[XS_TOTAL] + 0.0;
-            if (rng_get(rng) < sigmaT * majorant_inv) { realColl = true; virt = false; }
-          }
-          scoreInColl(a, T, base, r, mat, G, w, trackXS, virt, sProd, sAbs, nScore);
-        }
-      }
-    }
-
-    // ---------------- event: collision, part 1 (channel + number of fission sites) --------------------
-    int MT = 0, nNew = 0;
-    if (realColl) {
-      const double* x = mgRow(M, T, mat, G);
-      (void)rng_get(rng);                                 // alpha-absorption test always draws (probAlpha = 0)
-      double rr = rng_get(rng);
-      {                                                   // neutronMacroXSs%invert (neutronXsPackages_class.f90:211-250)
-        int C = 1;
-        double xs = x[XS_TOTAL] * rr - 0.0;
-        if (xs > 0.0) C += 1;
-        xs = xs - x[XS_IESCATTER];
-        if (xs > 0.0) C += 1;
-        xs = xs - x[XS_CAPTURE];
-        if (xs > 0.0) C += 1;
-        MT = C;                                           // 1 elastic, 2 inelastic, 3 capture, 4 fission
-      }
-      ++nColl;
-      if (T.fissile[mat - 1] != 0) {                      // neutronMGstd implicit (:131-199)
-        double rand1 = rng_get(rng);
-        nNew = (int)(fabs((w * x[XS_NUFISSION]) / (w0 * x[XS_TOTAL] * a.k_eff)) + rand1);
-        if (nNew < 0) nNew = 0;
-      }
-    }
-
-    // ---------------- warp-aggregated allocation of fission-bank slots --------------------------------
-    int slot = -1;
-    unsigned spawn = __ballot_sync(FULL, nNew > 0);
-    if (spawn) {
-      int inc = nNew;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-      int total = __shfl_sync(FULL, inc, 31);
-      int b = 0;
-      if (lane == 0) b = atomicAdd(&a.cd->nSites, total);
-      b = __shfl_sync(FULL, b, 0);
-      slot = b + inc - nNew;
-      if (b + total > a.cap) { atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW); slot = -1; }
-    }
-
-    // ---------------- collision, part 2: fission sites, then the scattered neutron --------------------
-    // one loop, one rotateVector: iterations 0..nNew-1 emit sites (fissionMG%sampleOut: mu, phi, then chi),
-    // the last iteration is the scattering itself (multiScatterMG%sampleOut: G_out, then mu, phi)
-    if (realColl) {
-      const double wSite = fsign(w0, w);
-      const int nIter = nNew + (MT == 2 ? 1 : 0);
-      for (int i = 0; i < nIter; ++i) {
-        const bool isScat = (i == nNew);
-        const double* cdf = isScat ? T.P0 + ((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG : T.chi + (size_t)(mat - 1) * M.nG;
-        double mu = 0.0, phi = 0.0, rem;
-        if (isScat) rem = rng_get(rng) * mgRow(M, T, mat, G)[XS_IESCATTER];
-        else { mu = 2.0 * rng_get(rng) - 1.0; phi = TWO_PI * rng_get(rng); rem = rng_get(rng); }
-        int Gout = 0;
-        for (int g = 1; g <= M.nG; ++g) { rem = rem - cdf[g - 1]; if (rem < 0.0) { Gout = g; break; } }
-        if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = G; }
-        if (isScat) {
-          if (M.isP1) mu = sampleLegendreP1(T.P1[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)], rng);
-          else mu = 2.0 * rng_get(rng) - 1.0;
-          phi = TWO_PI * rng_get(rng);
-        }
-        double d[3] = {u[0], u[1], u[2]};
-        rotateVector(d, mu, phi);
-        if (isScat) {                                       // neutronMGstd inelastic (:221-252)
-          double w_mul = T.prod[((size_t)(mat - 1) * M.nG + (G - 1)) * M.nG + (Gout - 1)];
-          double wPre = w;
-          G = Gout;
-          trackXS = mgMajorant(M, T, G); majorant_inv = 1.0 / trackXS;
-          w = w * w_mul;
-          u[0] = d[0]; u[1] = d[1]; u[2] = d[2];
-          double sc = fmax(w - wPre, 0.0);                   // keffImplicitClerk%reportOutColl
-          if (sc > 0.0) sScat += sc;
-        } else if (slot >= 0) {
-          int s = slot + i;
-          a.out.rx[s] = r[0]; a.out.ry[s] = r[1]; a.out.rz[s] = r[2];
-          a.out.ux[s] = d[0]; a.out.uy[s] = d[1]; a.out.uz[s] = d[2];
-          a.out.w[s] = wSite; a.out.G[s] = Gout; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
-        }
-      }
-      nSite += nNew;
-      if (MT == 3 || MT == 4) died = true;                   // capture / fission: history ends (ABS_FATE)
-      // MT == 1 (elastic) cannot be selected for MG data (elasticScatter = 0): "Do nothing"
-    }
-
-    if (died) {
-      a.nsites[hi] = nSite;
-      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
-      a.hSeg[hi] = nSeg; a.hColl[hi] = nColl; a.hScore[hi] = nScore;
-      alive = false;
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // exclusive scan of int32 (3 kernels) -- used for brood offsets and resampling compaction
@@ -403,81 +124,67 @@ __global__ void k_sort_sites(Bank src, Bank dst, const int* offsets, const Cycle
 }
 
 // ------------------------------------------------------------------------------------------------
-// deterministic reduction of the per-history scores (fixed tiling, fixed tree)
+// deterministic reduction of the per-history scores (fixed tiling, fixed tree): the result depends on
+// n only, never on the execution order of the history kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int RED_BLOCKS = 592;      // 4 per SM on 148 SMs; the tiling is a constant of the algorithm
 constexpr int RED_THREADS = 256;
-struct RedOut { double prod, abs, leak, scat, wgt; long long seg, coll, score; };
+struct RedOut { double prod, abs, leak, scat, wgt, endw; };
 
 __device__ __forceinline__ double warpSum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
   return v;
 }
-__device__ __forceinline__ long long warpSumLL(long long v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-  return v;
-}
-__device__ __forceinline__ void blockReduce7(double v[5], long long c[3], RedOut* out) {
-  __shared__ double sd[5][RED_THREADS / 32];
-  __shared__ long long sc[3][RED_THREADS / 32];
+// blocks [0, RED_BLOCKS): per-history scores + start weights of this cycle's bank;
+// the same blocks also sum the weights of the (sorted) next-cycle bank: popWeight for keffAnalogClerk%reportCycleEnd
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(int n, const double* hProd, const double* hAbs, const double* hLeak, const double* hScat,
+                                                             const double* wIn, const double* wSites, const CycleDev* cd, int cap, RedOut* partial) {
+  __shared__ double sd[6][RED_THREADS / 32];
+  // contiguous slice per block, strided by thread inside the slice: fixed order for fixed n
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  {
+    int per = (n + RED_BLOCKS - 1) / RED_BLOCKS;
+    int b0 = blockIdx.x * per, b1 = min(n, b0 + per);
+    for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) { v[0] += hProd[i]; v[1] += hAbs[i]; v[2] += hLeak[i]; v[3] += hScat[i]; v[4] += wIn[i]; }
+  }
+  {
+    int m = min(cd->nSites, cap);
+    int per = (m + RED_BLOCKS - 1) / RED_BLOCKS;
+    int b0 = blockIdx.x * per, b1 = min(m, b0 + per);
+    for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) v[5] += wSites[i];
+  }
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) { double s = warpSum(v[k]); if (lane == 0) sd[k][wid] = s; }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { long long s = warpSumLL(c[k]); if (lane == 0) sc[k][wid] = s; }
+  for (int k = 0; k < 6; ++k) { double s = warpSum(v[k]); if (lane == 0) sd[k][wid] = s; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    RedOut o = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < RED_THREADS / 32; ++i) {
-      o.prod += sd[0][i]; o.abs += sd[1][i]; o.leak += sd[2][i]; o.scat += sd[3][i]; o.wgt += sd[4][i];
-      o.seg += sc[0][i]; o.coll += sc[1][i]; o.score += sc[2][i];
-    }
-    *out = o;
+  if (threadIdx.x < 6) {
+    double s = 0.0;
+    for (int i = 0; i < RED_THREADS / 32; ++i) s += sd[threadIdx.x][i];
+    ((double*)(partial + blockIdx.x))[threadIdx.x] = s;
   }
-}
-__global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(const CycleArgs a, RedOut* partial) {
-  // contiguous slice per block, strided by thread inside the slice: fixed order for fixed n
-  int n = a.n;
-  int per = (n + RED_BLOCKS - 1) / RED_BLOCKS;
-  int b0 = blockIdx.x * per, b1 = min(n, b0 + per);
-  double v[5] = {0, 0, 0, 0, 0}; long long c[3] = {0, 0, 0};
-  for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) {
-    v[0] += a.hProd[i]; v[1] += a.hAbs[i]; v[2] += a.hLeak[i]; v[3] += a.hScat[i]; v[4] += a.in.w[i];
-    c[0] += a.hSeg[i]; c[1] += a.hColl[i]; c[2] += a.hScore[i];
-  }
-  blockReduce7(v, c, partial + blockIdx.x);
-}
-// sum of weights of the (sorted) next-cycle bank: popWeight for keffAnalogClerk%reportCycleEnd
-__global__ void __launch_bounds__(RED_THREADS) k_reduce_wgt(const double* w, const CycleDev* cd, int cap, double* partial) {
-  __shared__ double sd[RED_THREADS / 32];
-  int n = min(cd->nSites, cap);
-  int per = (n + RED_BLOCKS - 1) / RED_BLOCKS;
-  int b0 = blockIdx.x * per, b1 = min(n, b0 + per);
-  double v = 0.0;
-  for (int i = b0 + threadIdx.x; i < b1; i += RED_THREADS) v += w[i];
-  v = warpSum(v);
-  if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < RED_THREADS / 32; ++i) s += sd[i]; partial[blockIdx.x] = s; }
 }
 
 // tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
 //   keffAnalogClerk%closeCycle (keffAnalogClerk_class.f90:156-176), keffImplicitClerk%closeCycle (:292-312)
-__global__ void k_close_cycle_head(const RedOut* partial, const double* wPartial, CycleDev* cd, int phase, double kNorm,
+// one warp: lane l sums partials l, l+32, ... in order, then a fixed shuffle tree
+__global__ void k_close_cycle_head(const RedOut* partial, CycleDev* cd, int phase, double kNorm,
                                    const double* bins, int normAddr, double normVal) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  RedOut o = {0, 0, 0, 0, 0, 0, 0, 0}; double endW = 0.0;
-  for (int i = 0; i < RED_BLOCKS; ++i) {
-    o.prod += partial[i].prod; o.abs += partial[i].abs; o.leak += partial[i].leak; o.scat += partial[i].scat; o.wgt += partial[i].wgt;
-    o.seg += partial[i].seg; o.coll += partial[i].coll; o.score += partial[i].score; endW += wPartial[i];
+  const int lane = threadIdx.x;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = lane; i < RED_BLOCKS; i += 32) {
+    const double* p = (const double*)(partial + i);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] += p[k];
   }
-  cd->startWgt = o.wgt; cd->endWgt = endW;
-  cd->impProd = o.prod; cd->impAbs = o.abs; cd->anaLeak = o.leak; cd->scatProd = o.scat;
-  cd->nSeg = o.seg; cd->nColl = o.coll; cd->nScore = o.score;
-  cd->kAnalog = endW / o.wgt * kNorm;
-  cd->kImplicit = o.prod / (o.abs + o.leak - o.scat);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = warpSum(v[k]);
+  if (lane != 0) return;
+  const double prod = v[0], abs_ = v[1], leak = v[2], scat = v[3], wgt = v[4], endW = v[5];
+  cd->startWgt = wgt; cd->endWgt = endW;
+  cd->impProd = prod; cd->impAbs = abs_; cd->anaLeak = leak; cd->scatProd = scat;
+  cd->kAnalog = endW / wgt * kNorm;
+  cd->kImplicit = prod / (abs_ + leak - scat);
   double k = (phase == 0) ? cd->kAnalog : cd->kImplicit;
   cd->kCsum[phase] = cd->kCsum[phase] + k;
   cd->kCsum2[phase] = cd->kCsum2[phase] + k * k;
@@ -530,26 +237,27 @@ __global__ void k_sel_hist(const unsigned long long* rn, const CycleDev* cd, int
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     atomicAdd(&hist[(int)(rn[j] >> (63 - SEL_BITS))], 1);
 }
-// heapSize-th smallest (1-based rank k): find the 16-bit bin holding it
+// heapSize-th smallest (1-based rank k): find the 16-bit bin holding it.
+// 1024 threads: each sums its 64 consecutive bins, one block scan, the owner of the rank walks its bins
 __global__ void k_sel_find_bin(const int* hist, CycleDev* cd, int cap, int totPop) {
   __shared__ int sWarp[33];
-  __shared__ int carry;
   int totSites = min(cd->nSites, cap);
   int excess = totSites - totPop;
-  int k = (excess < 0) ? (int)(((long long)(-excess)) % totSites) : excess;     // heapSize
-  if (threadIdx.x == 0) { carry = 0; cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; }
+  int k = (totSites <= 0) ? 0 : ((excess < 0) ? (int)(((long long)(-excess)) % totSites) : excess);     // heapSize
+  if (threadIdx.x == 0) { cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; }
   __syncthreads();
   if (k == 0) return;
-  for (int b = 0; b < SEL_BINS; b += blockDim.x) {
-    int i = b + threadIdx.x;
-    int v = hist[i];
-    int tot; int ex = blockExclusiveScan(v, sWarp, tot);
-    int c = carry;
-    int before = c + ex;
-    if (before < k && before + v >= k) { cd->selBin = i; cd->selRank = k - before; }
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + tot;
-    __syncthreads();
+  constexpr int PER = SEL_BINS / 1024;
+  const int* my = hist + threadIdx.x * PER;
+  int sum = 0;
+  for (int i = 0; i < PER; ++i) sum += my[i];
+  int tot; int before = blockExclusiveScan(sum, sWarp, tot);
+  if (before < k && before + sum >= k) {
+    for (int i = 0; i < PER; ++i) {
+      int v = my[i];
+      if (before < k && before + v >= k) { cd->selBin = threadIdx.x * PER + i; cd->selRank = k - before; break; }
+      before += v;
+    }
   }
 }
 __global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, int cap, unsigned long long* cand) {
@@ -703,6 +411,7 @@ __global__ void k_math_query(long long n, const double* x, double* lg, double* s
 __global__ void k_cycle_begin(CycleDev* cd, int* nCur, int n) {
   cd->nStart = n; cd->nSites = 0; cd->nextHistory = 0; cd->error = 0;
   cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; cd->nNew = 0;
+  cd->nSeg = 0ULL; cd->nColl = 0ULL; cd->nScore = 0ULL; cd->maxSeg = 256;
   *nCur = n;
 }
 // particleState arrays cross the boundary as r(3,n), dir(3,n) (Fortran order); banks are SoA on the device
@@ -742,16 +451,18 @@ struct sb_engine {
   // banks
   int cap = 0; Bank bank[3]{}; int cur = 0;          // bank[cur] = this cycle; others: raw sites, sorted/next
   int nCur = 0;
-  int *dNsites = nullptr, *dOffsets = nullptr, *dTile = nullptr, *dFlag = nullptr, *dFlagOff = nullptr, *dHist = nullptr, *dHSeg = nullptr, *dHColl = nullptr, *dHScore = nullptr;
+  int *dNsites = nullptr, *dOffsets = nullptr, *dTile = nullptr, *dFlag = nullptr, *dFlagOff = nullptr, *dHist = nullptr;
   double *dHProd = nullptr, *dHAbs = nullptr, *dHLeak = nullptr, *dHScat = nullptr;
   unsigned long long *dRn = nullptr, *dCand = nullptr;
-  RedOut* dPartial = nullptr; double* dWPartial = nullptr;
+  RedOut* dPartial = nullptr;
+  char* dHot = nullptr; HotLayout hot{}; ulonglong2* dSeedTab = nullptr;
   CycleDev* dCd = nullptr; CycleDev* hCd = nullptr; int* dNcur = nullptr;
   double *dBins[2] = {nullptr, nullptr}, *dLast[2] = {nullptr, nullptr}, *dCsum[2] = {nullptr, nullptr}, *dCsum2[2] = {nullptr, nullptr};
   int batchN[2] = {0, 0};
   double bounds[6] = {0, 0, 0, 0, 0, 0};
   double kNormNext = 1.0;   // nextCycle%k_eff of the dungeon that will receive the sites (keffAnalogClerk k_norm)
   bool sortedReady = false;
+  int refillMin = 1;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
   double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
@@ -778,11 +489,10 @@ static int ensureCapacity(sb_engine* h, int maxPop) {
   CUDA_OK(cudaSetDevice(h->device));
   for (int i = 0; i < 3; ++i) { freeBank(h->bank[i]); if (allocBank(h, h->bank[i], cap)) return -1; }
   cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
-  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHScore); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
+  cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   CUDA_OK(cudaMalloc(&h->dNsites, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dOffsets, sizeof(int) * cap));
   CUDA_OK(cudaMalloc(&h->dTile, sizeof(int) * (cap / SCAN_TILE + 2)));
   CUDA_OK(cudaMalloc(&h->dFlag, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dFlagOff, sizeof(int) * cap));
-  CUDA_OK(cudaMalloc(&h->dHSeg, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dHColl, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&h->dHScore, sizeof(int) * cap));
   CUDA_OK(cudaMalloc(&h->dHProd, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHAbs, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&h->dHLeak, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHScat, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&h->dRn, sizeof(unsigned long long) * cap));
@@ -799,12 +509,14 @@ static int put(std::vector<char>& blob, const std::vector<T>& v) {
   return off;
 }
 
-// (re)build the device table blob from the loaded model
+// (re)build the device tables from the loaded model:
+//   generic blob = [Model header][tables]  (global memory; query kernels, source kernel, cold paths)
+//   hot blob     = compact records of sb_hist.cuh (staged into shared memory by the history kernel)
 static int buildBlob(sb_engine* h) {
   if (!h->blobDirty) return 0;
   if (!h->haveGeom || !h->haveData) { h->err = "geometry and nuclear data must be loaded first"; return -1; }
   Model& M = h->M;
-  std::vector<char> blob;
+  std::vector<char> blob(sizeof(Model), 0);
   M.nSurf = h->g.n_surf; M.nCell = h->g.n_cell; M.nUni = h->g.n_uni; M.nGraph = h->g.n_graph;
   M.rootIdx = h->g.root_idx; M.borderIdx = h->g.border_idx;
   for (int i = 0; i < 6; ++i) M.bc[i] = h->g.bc[i];
@@ -819,28 +531,81 @@ static int buildBlob(sb_engine* h) {
   M.oXs = put(blob, h->xs); M.oP0 = put(blob, h->P0); M.oProd = put(blob, h->prod);
   M.oP1 = h->isP1 ? put(blob, h->P1) : M.oP0;
   M.oChi = put(blob, h->chi); M.oFissile = put(blob, h->fissile); M.oMajorant = put(blob, h->majorant);
-  for (int ph = 0; ph < 2; ++ph) {
-    // per-map auxiliary tables first, then the clerk records that point at them
-    std::vector<DClerk> cl = h->clerks[ph];
-    for (size_t c = 0; c < cl.size(); ++c)
-      for (int m = 0; m < cl[c].nMaps; ++m) {
-        size_t key = c * SB_MAX_MAPS + m;
-        if (cl[c].mapType[m] == SB_MAP_MATERIAL) cl[c].mapOff[m] = put(blob, h->mapMat[ph][key]);
-        else if (cl[c].mapGrid[m] == SB_GRID_UNSTRUCT) cl[c].mapOff[m] = put(blob, h->mapBounds[ph][key]);
-        else cl[c].mapOff[m] = 0;
-      }
-    M.nClerk[ph] = (int)cl.size(); M.nBins[ph] = h->nBins[ph];
-    M.oClerk[ph] = put(blob, cl);
-  }
+  for (int ph = 0; ph < 2; ++ph) { M.nClerk[ph] = (int)h->clerks[ph].size(); M.nBins[ph] = h->nBins[ph]; M.oClerk[ph] = 0; }
   while (blob.size() % 16) blob.push_back(0);
   M.blobBytes = (int)blob.size();
+  memcpy(blob.data(), &M, sizeof(Model));
   CUDA_OK(cudaSetDevice(h->device));
   cudaFree(h->dBlob);
   CUDA_OK(cudaMalloc(&h->dBlob, blob.size()));
   CUDA_OK(cudaMemcpy(h->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-  // shared-memory staging if the blob fits beside the static shared memory (227 KB per CTA on sm_100)
-  h->useSmem = (M.blobBytes <= 96 * 1024) ? 1 : 0;
-  if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(k_histories, cudaFuncAttributeMaxDynamicSharedMemorySize, M.blobBytes));
+
+  // ---- hot blob ----------------------------------------------------------------------------------
+  {
+    HotLayout& L = h->hot; L = HotLayout{};
+    std::vector<char> hb;
+    std::vector<HUni> unis((size_t)h->g.n_uni);
+    for (int ui = 0; ui < h->g.n_uni; ++ui) {
+      HUni& U = unis[ui]; memset(&U, 0, sizeof(U));
+      const int* ip = &h->gi_uniIpar[(size_t)ui * SB_UNI_NIPAR]; const double* dp = &h->gd_uniDpar[(size_t)ui * SB_UNI_NDPAR];
+      const int t = h->gi_uniType[ui];
+      if (ip[0]) U.flags |= sbh::HF_ROT;
+      if (ip[1]) U.flags |= sbh::HF_GLOBAL;
+      for (int i = 0; i < 3; ++i) U.org[i] = dp[i];
+      if (dp[0] == 0.0 && dp[1] == 0.0 && dp[2] == 0.0) U.flags |= sbh::HF_ORG0;
+      U.type = sbh::HU_COLD;
+      if (t == SB_UNI_LAT) {
+        U.type = sbh::HU_LAT;
+        for (int i = 0; i < 3; ++i) { U.pitch[i] = dp[12 + i]; U.corner[i] = dp[15 + i]; U.abar[i] = dp[18 + i]; U.inv[i] = 1.0 / dp[12 + i]; U.hp[i] = 0.5 * dp[12 + i]; }
+        U.n0 = ip[2]; U.n1 = ip[3]; U.n2 = ip[4]; U.outID = ip[5]; U.aux = ip[7];
+        if (ip[6] == 1) U.flags |= sbh::HF_OFFALL; else if (ip[6] == 2) U.flags |= sbh::HF_OFFMAP;
+        if (ip[4] == 1 && dp[14] >= 2.0 * INF && dp[17] == -INF) U.flags |= sbh::HF_LAT2D;
+      } else if (t == SB_UNI_PIN) {
+        U.type = sbh::HU_PIN; U.n0 = ip[2]; U.aux = ip[3];
+      } else if (t == SB_UNI_ROOT) {
+        int sidx = ip[2] - 1;
+        if (h->gi_surfType[sidx] == SB_SURF_BOX) {
+          const double* p = &h->gd_surfPar[(size_t)sidx * SB_SURF_NPAR];
+          U.type = sbh::HU_ROOTBOX;
+          for (int i = 0; i < 3; ++i) { U.corner[i] = p[i]; U.pitch[i] = p[3 + i]; }
+          U.abar[0] = p[6];
+        }
+      }
+    }
+    L.oUni = put(hb, unis); L.oGraph = put(hb, graph); L.oAuxD = put(hb, h->gd_auxD); L.oAuxI = put(hb, h->gi_auxI);
+    L.oXs = put(hb, h->xs); L.oP0 = put(hb, h->P0); L.oProd = put(hb, h->prod); L.oP1 = h->isP1 ? put(hb, h->P1) : L.oP0;
+    L.oChi = put(hb, h->chi); L.oFissile = put(hb, h->fissile);
+    std::vector<double> majT(h->nG), majInv(h->nG);
+    for (int g = 0; g < h->nG; ++g) { majT[g] = std::fmax(h->majorant[g] + 0.0, h->collisionXS); majInv[g] = 1.0 / majT[g]; }   // getTrackingXS(MAJORANT_XS)
+    L.oMajT = put(hb, majT); L.oMajInv = put(hb, majInv);
+    for (int ph = 0; ph < 2; ++ph) {
+      // per-map auxiliary tables first, then the clerk records that point at them
+      std::vector<DClerk> cl = h->clerks[ph];
+      for (size_t c = 0; c < cl.size(); ++c)
+        for (int m = 0; m < cl[c].nMaps; ++m) {
+          size_t key = c * SB_MAX_MAPS + m;
+          if (cl[c].mapType[m] == SB_MAP_MATERIAL) cl[c].mapOff[m] = put(hb, h->mapMat[ph][key]);
+          else if (cl[c].mapGrid[m] == SB_GRID_UNSTRUCT) cl[c].mapOff[m] = put(hb, h->mapBounds[ph][key]);
+          else cl[c].mapOff[m] = 0;
+        }
+      L.nClerk[ph] = (int)cl.size();
+      if (cl.empty()) cl.push_back(DClerk{});
+      L.oClerk[ph] = put(hb, cl);
+    }
+    while (hb.size() % 16) hb.push_back(0);
+    L.bytes = (int)hb.size();
+    L.nG = h->nG; L.nMat = h->nMat; L.isP1 = h->isP1; L.rootIdx = h->g.root_idx; L.borderS = h->g.border_idx - 1;
+    L.borderIsBox = h->gi_surfType[h->g.border_idx - 1] >= SB_SURF_BOX ? 1 : 0;
+    cudaFree(h->dHot);
+    CUDA_OK(cudaMalloc(&h->dHot, hb.size()));
+    CUDA_OK(cudaMemcpy(h->dHot, hb.data(), hb.size(), cudaMemcpyHostToDevice));
+    // shared-memory staging when two CTAs per SM fit beside each other (227 KB per SM on sm_100)
+    h->useSmem = (L.bytes <= 72 * 1024) ? 1 : 0;
+    if (h->useSmem) {
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+    }
+  }
   for (int ph = 0; ph < 2; ++ph) {
     cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]);
     size_t nb = (size_t)std::max(1, h->nBins[ph]);
@@ -876,9 +641,23 @@ int sb_create(sb_engine** out, int device) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { g_globalErr = "cudaStreamCreate failed"; delete h; return -1; }
   cudaMalloc(&h->dCd, sizeof(CycleDev)); cudaMemset(h->dCd, 0, sizeof(CycleDev));
   cudaMallocHost(&h->hCd, sizeof(CycleDev));
-  cudaMalloc(&h->dPartial, sizeof(RedOut) * RED_BLOCKS); cudaMalloc(&h->dWPartial, sizeof(double) * RED_BLOCKS);
+  cudaMalloc(&h->dPartial, sizeof(RedOut) * RED_BLOCKS);
+  {                                        // LCG jump table for per-history seeding: maps for stride*i*1024^level
+    std::vector<ulonglong2> tab(3 * 1024);
+    for (int lvl = 0; lvl < 3; ++lvl)
+      for (int i = 0; i < 1024; ++i) {
+        int64_t k = RNG_STRIDE * ((int64_t)i << (10 * lvl));
+        uint64_t c = rng_skip(0ULL, k);                       // f^k(0) = C_k
+        uint64_t g = (rng_skip(1ULL, k) - c) & RNG_MASK;     // f^k(1) - C_k = G_k
+        tab[lvl * 1024 + i] = make_ulonglong2(g, c);
+      }
+    cudaMalloc(&h->dSeedTab, sizeof(ulonglong2) * tab.size());
+    cudaMemcpy(h->dSeedTab, tab.data(), sizeof(ulonglong2) * tab.size(), cudaMemcpyHostToDevice);
+  }
   cudaMalloc(&h->dHist, sizeof(int) * SEL_BINS); cudaMalloc(&h->dCand, sizeof(unsigned long long) * SEL_CAND_CAP);
   cudaMalloc(&h->dNcur, sizeof(int));
+  if (const char* e = getenv("SB_REFILL_MIN")) h->refillMin = std::max(1, atoi(e));     // tuning knobs (measurement only)
+  if (const char* e = getenv("SB_BLOCKS_PER_SM")) h->opt.blocks_per_sm = atoi(e);
   cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
   *out = h;
   return 0;
@@ -889,8 +668,8 @@ void sb_destroy(sb_engine* h) {
   cudaSetDevice(h->device);
   for (int i = 0; i < 3; ++i) freeBank(h->bank[i]);
   cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
-  cudaFree(h->dHSeg); cudaFree(h->dHColl); cudaFree(h->dHScore); cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
-  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dWPartial); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
+  cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
+  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
   cudaFree(h->dStage);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -961,7 +740,7 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
     for (int m = 0; m < s.n_maps; ++m) {
       const sb_map1d& mp = s.maps[m];
       d.mapType[m] = mp.type; d.mapAxis[m] = mp.axis; d.mapGrid[m] = mp.grid; d.mapN[m] = mp.n_bins; d.mapMul[m] = mul;
-      d.mapFirst[m] = mp.first; d.mapStep[m] = mp.step; d.mapDef[m] = mp.default_bin;
+      d.mapFirst[m] = mp.first; d.mapStep[m] = mp.step; d.mapInv[m] = (mp.step != 0.0) ? 1.0 / mp.step : 0.0; d.mapDef[m] = mp.default_bin;
       size_t key = (size_t)c * SB_MAX_MAPS + m;
       if (mp.type == SB_MAP_MATERIAL) {
         if (!mp.mat_bin) { h->err = "sb_define_tallies: materialMap without mat_bin"; return -1; }
@@ -985,7 +764,7 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
 
 int sb_set_options(sb_engine* h, const sb_options* o) {
   if (o->tracking != SB_TRACK_DT) { h->err = "sb_set_options: only delta tracking (transportOperatorDT) is implemented on the device in this round"; return -1; }
-  h->opt = *o;
+  { int keep = h->opt.blocks_per_sm; h->opt = *o; if (h->opt.blocks_per_sm <= 0) h->opt.blocks_per_sm = keep; }
   if (o->max_pop > 0) return ensureCapacity(h, o->max_pop);
   return 0;
 }
@@ -1080,22 +859,23 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   k_cycle_begin<<<1, 1, 0, st>>>(h->dCd, h->dNcur, n);
   h->launches++;
 
-  CycleArgs a;
-  a.M = h->M; a.blob = h->dBlob; a.useSmem = h->useSmem;
+  HistArgs a{};
+  a.L = h->hot; a.L.oClerk[0] = h->hot.oClerk[phase]; a.L.nClerk[0] = h->hot.nClerk[phase];
+  a.hot = h->dHot; a.blob = h->dBlob; a.seedTab = h->dSeedTab;
   a.n = n; a.in = in; a.out = raw; a.cap = h->cap;
-  a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat; a.hSeg = h->dHSeg; a.hColl = h->dHColl; a.hScore = h->dHScore;
+  a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat;
   a.bins = h->dBins[phase]; a.phase = phase;
   a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
-  const int threads = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 256;
+  a.refillMin = h->refillMin;
+  const int threads = 256;
   const int bps = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 2;
   int blocks = h->numSM * bps;
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
-  long long warps = (long long)blocks * (threads / 32);
-  int chunk = (int)(n / (4 * warps)); if (chunk < 1) chunk = 1; if (chunk > 128) chunk = 128;
-  a.chunk = chunk;
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
-  k_histories<<<blocks, threads, h->useSmem ? h->M.blobBytes : 0, st>>>(a);
+  if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, threads, h->hot.bytes, st>>>(a);
+  else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, threads, h->hot.bytes, st>>>(a);
+  else sbh::k_histories<false, 2><<<blocks, threads, 0, st>>>(a);
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK1, st));
   h->launches++;
 
@@ -1106,12 +886,11 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dNsites, h->dNcur, h->dTile, h->dOffsets);
   k_sort_sites<<<gridFor(h, 2LL * n, 256), 256, 0, st>>>(raw, sorted, h->dOffsets, h->dCd, h->cap);
   // deterministic reductions and cycle close
-  k_reduce_hist<<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, h->dPartial);
-  k_reduce_wgt<<<RED_BLOCKS, RED_THREADS, 0, st>>>(sorted.w, h->dCd, h->cap, h->dWPartial);
-  k_close_cycle_head<<<1, 32, 0, st>>>(h->dPartial, h->dWPartial, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase]);
+  k_reduce_hist<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, h->dHProd, h->dHAbs, h->dHLeak, h->dHScat, in.w, sorted.w, h->dCd, h->cap, h->dPartial);
+  k_close_cycle_head<<<1, 32, 0, st>>>(h->dPartial, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase]);
   int nb = std::max(1, h->nBins[phase]);
   k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
-  h->launches += 8;
+  h->launches += 7;
   h->batchN[phase] += 1;
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -1119,13 +898,13 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   const CycleDev& c = *h->hCd;
   if (h->profiling) {
     float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, h->evK0, h->evK1));
-    h->msHistories += ms; h->nHistLaunches++; h->segProfiled += c.nSeg; h->scoreProfiled += c.nScore;
+    h->msHistories += ms; h->nHistLaunches++; h->segProfiled += (long long)c.nSeg; h->scoreProfiled += (long long)c.nScore;
   }
   if (res) {
     res->n_start = n; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
     res->imp_prod = c.impProd; res->imp_abs = c.impAbs; res->scatter_prod = c.scatProd; res->ana_leak = c.anaLeak;
     res->k_analog = c.kAnalog; res->k_implicit = c.kImplicit; res->k_cum = c.kCum; res->k_cum_std = c.kCumStd;
-    res->n_segments = c.nSeg; res->n_collisions = c.nColl; res->n_scores = c.nScore; res->error = c.error;
+    res->n_segments = (int64_t)c.nSeg; res->n_collisions = (int64_t)c.nColl; res->n_scores = (int64_t)c.nScore; res->error = c.error; res->max_history_segments = c.maxSeg;
   }
   h->sortedReady = true;
   return checkDeviceError(h, c.error);
