@@ -172,12 +172,13 @@ def main():
     total_pop = pop * world
     ov = "pop %d; inactive %d; active %d; seed 20261017;" % (total_pop, args.inactive, args.warmup + 2 * args.steps + 4)
     pp = scone_b200.EigenPhysicsPackage(deck, ov, device=local, rank=rank, n_ranks=world)
+    comm = scone_b200.distributed.TorchComm(device=torch.device("cuda", local)) if world > 1 else None
     L = pp.L
     eng = pp.engine
     pp.generateInitialState()
-    pp.cycles(False, args.inactive)
+    pp.cycles(False, args.inactive, comm=comm)
     for _ in range(max(3, args.warmup)):
-        pp.cycle(True)
+        pp.cycle(True, comm=comm)
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,7 +214,7 @@ def main():
         if flush:
             L.sb_flush_l2(eng, FLUSH_BYTES)
         L.sb_timer_begin(eng)
-        res = pp.cycle(True)
+        res = pp.cycle(True, comm=comm)
         L.sb_timer_end(eng, C.byref(ms))
         ms_total += ms.value; seg += res.n_segments; scores += res.n_scores; nsites += res.n_sites
     barrier()
@@ -227,13 +228,14 @@ def main():
     value = total_pop * args.steps / (ms_max * 1e-3)
     seg_all = sumreduce(float(seg))
     k_dev, k_std = pp.k, res.k_cum_std
+    max_seg = int(maxreduce(float(res.max_history_segments)))
 
     # ---- end-to-end arm: bank in pinned HOST memory, copied in and out every step ------------------------
-    pp.cycle(True, host_buffers=True)          # warm the host buffers
+    pp.cycle(True, host_buffers=True, comm=comm)          # warm the host buffers
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pp.cycle(True, host_buffers=True)
+        pp.cycle(True, host_buffers=True, comm=comm)
     barrier()
     t_e2e = maxreduce(time.perf_counter() - t0)
     h2d, d2h = pp.host_bytes(True)
@@ -270,7 +272,9 @@ def main():
             "config": {"workload": WORKLOAD[args.deck], "deck": DECKS[args.deck], "pop_per_cycle_per_gpu": pop, "pop_per_cycle_total": total_pop,
                        "tracking": "DT", "inactive_cycles_before": args.inactive,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
-                       "parallelism": "bank sharded by history index over %d GPU(s)" % world},
+                       "parallelism": "bank sharded by history index over %d GPU(s)%s" % (
+                           world, "; per cycle: all-reduce of 6 f64 k-eff sums, 2 all-gathers of one int, neighbour send/recv of boundary sites (NCCL)" if world > 1 else "")},
+            "longest_history_segments": max_seg,
             "segments_per_s": seg_all / (ms_max * 1e-3), "segments_per_history": seg / max(1, pop * args.steps),
             "keff": k_dev, "keff_std": k_std, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_val, "unit": "neutrons/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,

@@ -157,6 +157,28 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
  * rng_state = pRNG state after the stride(totalPop+1) of the cycle.                            */
 int sb_resample(sb_engine* h, int tot_pop, uint64_t rng_state);
 
+/* ---- the cycle split for several ranks (one engine = one GPU = one rank) ---------------------
+ * Ranks own contiguous shares of the bank (getWorkshare/getOffset, SharedModules/mpi_func.f90:133-159) and
+ * exchange once per cycle what SCONE exchanges over MPI; the transport between ranks (NCCL, CUDA-aware MPI,
+ * peer copies) is the caller's, the engine only exposes device buffers:
+ *   sb_cycle_begin : transport + brood order; writes this rank's 6 score sums {implicit production, implicit
+ *                    absorption, analog leakage, scatter production, start weight, end weight} to dev_sums
+ *                    (device pointer, 6 doubles) -> caller all-reduces them (scoreMemory%reduceBins with
+ *                    mpiSync, scoreMemory_class.f90:404-431; mpi_bcast of k, eigenPhysicsPackage_class.f90:302)
+ *   sb_cycle_end   : k estimators and closeCycle from the reduced sums (identical on every rank)
+ *   sb_resample_ranked : normSize_Repr with the bank sizes of all ranks (replaces mpi_gather + 3 mpi_bcast,
+ *                    particleDungeon_class.f90:464,516-518: the threshold is recomputed on every rank from
+ *                    master_rng_state = state of the MASTER's pRNG); returns the new local size
+ *   sb_bank_export / sb_bank_splice : loadBalancing (particleDungeon_class.f90:607-698): pack k sites of the
+ *                    front / back of the bank into device buffers of sb_site_buffer_bytes(k) bytes; then rebuild
+ *                    the bank as [add_front] + bank[drop_front : n - drop_back] + [add_back]                */
+int sb_cycle_begin(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, double* dev_sums, int32_t* n_sites);
+int sb_cycle_end(sb_engine* h, const double* dev_sums, sb_cycle_result* res);
+int sb_resample_ranked(sb_engine* h, int tot_pop, uint64_t master_rng_state, int n_ranks, int rank, const int32_t* pop_sizes, int32_t* new_local_pop);
+size_t sb_site_buffer_bytes(int k);
+int sb_bank_export(sb_engine* h, int k_front, void* dev_buf_front, int k_back, void* dev_buf_back);
+int sb_bank_splice(sb_engine* h, int drop_front, int drop_back, int add_front, const void* dev_buf_front, int add_back, const void* dev_buf_back);
+
 /* ---- results (scoreMemory) ---------------------------------------------------------------- */
 int64_t sb_tally_size(sb_engine* h, int phase);
 int sb_tally_read(sb_engine* h, int phase, double* csum, double* csum2, int32_t* batch_n);

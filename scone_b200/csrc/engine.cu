@@ -74,7 +74,7 @@ __global__ void k_scan_reduce(const int* in, const int* nPtr, int* tileSums) {
   int tot; blockExclusiveScan(sum, sWarp, tot);
   if (threadIdx.x == 0) tileSums[tile] = tot;
 }
-__global__ void k_scan_tiles(int* tileSums, const int* nPtr, int* totalOut) {
+__global__ void __launch_bounds__(1024) k_scan_tiles(int* tileSums, const int* nPtr, int* totalOut) {
   __shared__ int sWarp[33];
   __shared__ int carry;
   int n = *nPtr;
@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(int n, const double
   }
 }
 
-// tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
-//   keffAnalogClerk%closeCycle (keffAnalogClerk_class.f90:156-176), keffImplicitClerk%closeCycle (:292-312)
-// one warp: lane l sums partials l, l+32, ... in order, then a fixed shuffle tree
-__global__ void k_close_cycle_head(const RedOut* partial, CycleDev* cd, int phase, double kNorm,
-                                   const double* bins, int normAddr, double normVal) {
+// one warp: lane l sums partials l, l+32, ... in order, then a fixed shuffle tree -> ksum[6] =
+// { implicit production, implicit absorption, analog leakage, scatter production, start weight, end weight }
+// (the bins of keffImplicitClerk / keffAnalogClerk that are reduced across ranks every cycle: mpiSync = 1,
+//  eigenPhysicsPackage_class.f90:605-640, scoreMemory_class.f90:404-431)
+__global__ void k_sum_partials(const RedOut* partial, double* ksum) {
   const int lane = threadIdx.x;
   double v[6] = {0, 0, 0, 0, 0, 0};
   for (int i = lane; i < RED_BLOCKS; i += 32) {
@@ -179,8 +179,17 @@ __global__ void k_close_cycle_head(const RedOut* partial, CycleDev* cd, int phas
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) v[k] = warpSum(v[k]);
-  if (lane != 0) return;
-  const double prod = v[0], abs_ = v[1], leak = v[2], scat = v[3], wgt = v[4], endW = v[5];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ksum[k] = v[k];
+  }
+}
+// tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
+//   keffAnalogClerk%closeCycle (keffAnalogClerk_class.f90:156-176), keffImplicitClerk%closeCycle (:292-312)
+__global__ void k_close_cycle_head(const double* ksum, CycleDev* cd, int phase, double kNorm,
+                                   const double* bins, int normAddr, double normVal) {
+  if (threadIdx.x != 0) return;
+  const double prod = ksum[0], abs_ = ksum[1], leak = ksum[2], scat = ksum[3], wgt = ksum[4], endW = ksum[5];
   cd->startWgt = wgt; cd->endWgt = endW;
   cd->impProd = prod; cd->impAbs = abs_; cd->anaLeak = leak; cd->scatProd = scat;
   cd->kAnalog = endW / wgt * kNorm;
@@ -216,12 +225,23 @@ __global__ void k_close_cycle_bins(double* bins, double* lastBins, double* csum,
 }
 
 // ------------------------------------------------------------------------------------------------
-// normSize_Repr (particleDungeon_class.f90:431-602) on the device, single rank
+// normSize_Repr (particleDungeon_class.f90:431-602) on the device.
+// The random numbers that decide the fate of the sites are one sequential LCG stream over the
+// concatenation of all ranks' banks (rank r starts where rank r-1 ended, :497-511); every rank generates
+// the whole stream itself (a pure function of the master RNG state and the sizes) and finds the same
+// threshold, then applies it to its own slice [offLocal, offLocal + nLocal).
 // ------------------------------------------------------------------------------------------------
+struct NormDev { int nGlobal, offLocal, nLocal, totPop, check, pad; };
+__global__ void k_norm_setup(NormDev* nd, const CycleDev* cd, int cap, int totPop, int nGlobal, int offLocal, int check) {
+  int nLocal = min(cd->nSites, cap);
+  nd->nLocal = nLocal; nd->totPop = totPop; nd->check = check;
+  nd->nGlobal = (nGlobal < 0) ? nLocal : nGlobal;
+  nd->offLocal = (nGlobal < 0) ? 0 : offLocal;
+}
 constexpr int RN_CHUNK = 16;
 // rn_j = j-th number of the LCG stream started at `state0` (j = 1..n), stored as the integer state
-__global__ void k_rn_generate(unsigned long long* rn, const CycleDev* cd, int cap, uint64_t state0) {
-  int n = min(cd->nSites, cap);
+__global__ void k_rn_generate(unsigned long long* rn, const NormDev* nd, uint64_t state0) {
+  int n = nd->nGlobal;
   int nChunks = (n + RN_CHUNK - 1) / RN_CHUNK;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nChunks; c += gridDim.x * blockDim.x) {
     int j0 = c * RN_CHUNK;
@@ -232,36 +252,38 @@ __global__ void k_rn_generate(unsigned long long* rn, const CycleDev* cd, int ca
 constexpr int SEL_BITS = 16;
 constexpr int SEL_BINS = 1 << SEL_BITS;
 constexpr int SEL_CAND_CAP = 1 << 18;
-__global__ void k_sel_hist(const unsigned long long* rn, const CycleDev* cd, int cap, int* hist) {
-  int n = min(cd->nSites, cap);
+__global__ void k_sel_hist(const unsigned long long* rn, const NormDev* nd, int* hist) {
+  int n = nd->nGlobal;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     atomicAdd(&hist[(int)(rn[j] >> (63 - SEL_BITS))], 1);
 }
 // heapSize-th smallest (1-based rank k): find the 16-bit bin holding it.
 // 1024 threads: each sums its 64 consecutive bins, one block scan, the owner of the rank walks its bins
-__global__ void k_sel_find_bin(const int* hist, CycleDev* cd, int cap, int totPop) {
+__global__ void __launch_bounds__(1024) k_sel_find_bin(const int* hist, CycleDev* cd, const NormDev* nd) {
   __shared__ int sWarp[33];
-  int totSites = min(cd->nSites, cap);
-  int excess = totSites - totPop;
+  int totSites = nd->nGlobal;
+  int excess = totSites - nd->totPop;
   int k = (totSites <= 0) ? 0 : ((excess < 0) ? (int)(((long long)(-excess)) % totSites) : excess);     // heapSize
   if (threadIdx.x == 0) { cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; }
   __syncthreads();
   if (k == 0) return;
   constexpr int PER = SEL_BINS / 1024;
-  const int* my = hist + threadIdx.x * PER;
+  const int4* my = (const int4*)(hist + threadIdx.x * PER);
   int sum = 0;
-  for (int i = 0; i < PER; ++i) sum += my[i];
+#pragma unroll 4
+  for (int i = 0; i < PER / 4; ++i) { int4 v = my[i]; sum += (v.x + v.y) + (v.z + v.w); }
   int tot; int before = blockExclusiveScan(sum, sWarp, tot);
   if (before < k && before + sum >= k) {
+    const int* mine = hist + threadIdx.x * PER;
     for (int i = 0; i < PER; ++i) {
-      int v = my[i];
+      int v = mine[i];
       if (before < k && before + v >= k) { cd->selBin = threadIdx.x * PER + i; cd->selRank = k - before; break; }
       before += v;
     }
   }
 }
-__global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, int cap, unsigned long long* cand) {
-  int n = min(cd->nSites, cap);
+__global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, const NormDev* nd, unsigned long long* cand) {
+  int n = nd->nGlobal;
   int bin = cd->selBin;
   if (bin < 0) return;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -273,7 +295,7 @@ __global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, int ca
   }
 }
 // threshold = selRank-th smallest of the candidates (states are distinct within the LCG period)
-__global__ void k_sel_threshold(const unsigned long long* cand, CycleDev* cd) {
+__global__ void __launch_bounds__(1024) k_sel_threshold(const unsigned long long* cand, CycleDev* cd) {
   int m = cd->nCand;
   if (cd->selBin < 0) { if (threadIdx.x == 0) { cd->thrState = 0; cd->thrReal = 1.0; } return; }
   if (m > SEL_CAND_CAP) { if (threadIdx.x == 0) atomicMax(&cd->error, SB_ERR_NORM); return; }
@@ -285,14 +307,15 @@ __global__ void k_sel_threshold(const unsigned long long* cand, CycleDev* cd) {
     if (less == want) { cd->thrState = v; cd->thrReal = (double)(long long)v * (1.0 / 9223372036854775808.0); }
   }
 }
-// keep (excess > 0: rn > threshold) or duplicate (excess < 0: rn <= threshold) flags
-__global__ void k_norm_flags(const unsigned long long* rn, const CycleDev* cd, int cap, int totPop, int* flag) {
-  int n = min(cd->nSites, cap);
-  int excess = n - totPop;
-  int nDup = (excess < 0) ? (int)(((long long)(-excess)) % n) : 0;
+// keep (excess > 0: rn > threshold) or duplicate (excess < 0: rn <= threshold) flags of the local slice
+__global__ void k_norm_flags(const unsigned long long* rn, const CycleDev* cd, const NormDev* nd, int* flag) {
+  int n = nd->nLocal;
+  int excess = nd->nGlobal - nd->totPop;
+  int nDup = (excess < 0) ? (int)(((long long)(-excess)) % nd->nGlobal) : 0;
   double thr = cd->thrReal;
+  const unsigned long long* mine = rn + nd->offLocal;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    double x = (double)(long long)rn[j] * (1.0 / 9223372036854775808.0);
+    double x = (double)(long long)mine[j] * (1.0 / 9223372036854775808.0);
     int f;
     if (excess > 0) f = (x > thr) ? 1 : 0;
     else if (excess < 0) f = (nDup != 0 && x <= thr) ? 1 : 0;
@@ -301,12 +324,13 @@ __global__ void k_norm_flags(const unsigned long long* rn, const CycleDev* cd, i
   }
 }
 // scatter into the new bank. src is brood-sorted; offs = exclusive scan of flags; hOff/hCnt = per-history
-// offsets/counts of src (brood segments).
+// offsets/counts of src (brood segments). For excess < 0 the result is already in the order that the second
+// sortByBroodID of the reference produces (:571-574): per brood, copies first, duplicates after.
 __global__ void k_norm_scatter(Bank src, Bank dst, const int* flag, const int* offs, const int* hOff, const int* hCnt,
-                               const CycleDev* cd, int cap, int totPop, int dstCap, CycleDev* cdw) {
-  int n = min(cd->nSites, cap);
-  int excess = n - totPop;
-  int nCopies = (excess < 0) ? (-excess) / n : 0;
+                               const NormDev* nd, int dstCap, CycleDev* cdw) {
+  int n = nd->nLocal;
+  int excess = nd->nGlobal - nd->totPop;
+  int nCopies = (excess < 0) ? (-excess) / nd->nGlobal : 0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     int d0 = -1, stride = 0, reps = 0, dDup = -1;
     if (excess > 0) { if (flag[j]) { d0 = offs[j]; reps = 1; } }
@@ -329,15 +353,44 @@ __global__ void k_norm_scatter(Bank src, Bank dst, const int* flag, const int* o
     }
   }
 }
-__global__ void k_norm_count(const int* flag, const int* offs, const CycleDev* cd, int cap, int totPop, CycleDev* cdw) {
-  int n = min(cd->nSites, cap);
+__global__ void k_norm_count(const int* flag, const int* offs, const NormDev* nd, CycleDev* cdw) {
+  int n = nd->nLocal;
   if (n <= 0) { cdw->nNew = 0; return; }
-  int excess = n - totPop;
+  int excess = nd->nGlobal - nd->totPop;
   int selected = offs[n - 1] + flag[n - 1];
-  int nCopies = (excess < 0) ? (-excess) / n : 0;
+  int nCopies = (excess < 0) ? (-excess) / nd->nGlobal : 0;
   int nNew = (excess > 0) ? selected : (excess == 0 ? n : n * (nCopies + 1) + selected);
   cdw->nNew = nNew;
-  if (nNew != totPop) atomicMax(&cdw->error, SB_ERR_NORM);
+  if (nd->check && nNew != nd->totPop) atomicMax(&cdw->error, SB_ERR_NORM);      // "Normalisation failed!" (:596)
+}
+
+// loadBalancing (particleDungeon_class.f90:607-698): pack sites of the ends of the bank / rebuild the bank as
+// [received from below] + kept middle + [received from above]. Packed site layout: 7 f64 arrays of k, then k i32 (G)
+__global__ void k_bank_pack_range(Bank b, int first, int k, double* buf) {
+  int* g = (int*)(buf + 7 * (size_t)k);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    int s = first + i;
+    buf[i] = b.rx[s]; buf[k + i] = b.ry[s]; buf[2 * (size_t)k + i] = b.rz[s];
+    buf[3 * (size_t)k + i] = b.ux[s]; buf[4 * (size_t)k + i] = b.uy[s]; buf[5 * (size_t)k + i] = b.uz[s];
+    buf[6 * (size_t)k + i] = b.w[s]; g[i] = b.G[s];
+  }
+}
+__global__ void k_bank_unpack_range(Bank b, int first, int k, const double* buf) {
+  const int* g = (const int*)(buf + 7 * (size_t)k);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    int s = first + i;
+    b.rx[s] = buf[i]; b.ry[s] = buf[k + i]; b.rz[s] = buf[2 * (size_t)k + i];
+    b.ux[s] = buf[3 * (size_t)k + i]; b.uy[s] = buf[4 * (size_t)k + i]; b.uz[s] = buf[5 * (size_t)k + i];
+    b.w[s] = buf[6 * (size_t)k + i]; b.G[s] = g[i]; b.brood[s] = 0; b.seq[s] = 0;
+  }
+}
+__global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfirst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    int s = first + i, d = dfirst + i;
+    dst.rx[d] = src.rx[s]; dst.ry[d] = src.ry[s]; dst.rz[d] = src.rz[s];
+    dst.ux[d] = src.ux[s]; dst.uy[d] = src.uy[s]; dst.uz[d] = src.uz[s];
+    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.brood[d] = 0; dst.seq[d] = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,7 +514,8 @@ struct sb_engine {
   int batchN[2] = {0, 0};
   double bounds[6] = {0, 0, 0, 0, 0, 0};
   double kNormNext = 1.0;   // nextCycle%k_eff of the dungeon that will receive the sites (keffAnalogClerk k_norm)
-  bool sortedReady = false;
+  bool sortedReady = false; int phaseOpen = -1; double kCumLast = 1.0;
+  double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -655,7 +709,7 @@ int sb_create(sb_engine** out, int device) {
     cudaMemcpy(h->dSeedTab, tab.data(), sizeof(ulonglong2) * tab.size(), cudaMemcpyHostToDevice);
   }
   cudaMalloc(&h->dHist, sizeof(int) * SEL_BINS); cudaMalloc(&h->dCand, sizeof(unsigned long long) * SEL_CAND_CAP);
-  cudaMalloc(&h->dNcur, sizeof(int));
+  cudaMalloc(&h->dNcur, sizeof(int)); cudaMalloc(&h->dKsum, 8 * sizeof(double)); cudaMalloc(&h->dNd, sizeof(NormDev));
   if (const char* e = getenv("SB_REFILL_MIN")) h->refillMin = std::max(1, atoi(e));     // tuning knobs (measurement only)
   if (const char* e = getenv("SB_BLOCKS_PER_SM")) h->opt.blocks_per_sm = atoi(e);
   cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
@@ -669,7 +723,7 @@ void sb_destroy(sb_engine* h) {
   for (int i = 0; i < 3; ++i) freeBank(h->bank[i]);
   cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
-  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
+  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
   cudaFree(h->dStage);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -846,7 +900,8 @@ int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offs
   return checkDeviceError(h, h->hCd->error);
 }
 
-int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, sb_cycle_result* res) {
+// transport of the whole bank + brood ordering + per-rank score sums (no cycle close yet)
+static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase) {
   if (phase < 0 || phase > 1) { h->err = "sb_run_cycle: phase must be 0 or 1"; return -1; }
   if (buildBlob(h)) return -1;
   if (h->nCur <= 0) { h->err = "sb_run_cycle: empty bank"; return -1; }
@@ -885,12 +940,24 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
   k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, h->dNcur, nullptr);
   k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dNsites, h->dNcur, h->dTile, h->dOffsets);
   k_sort_sites<<<gridFor(h, 2LL * n, 256), 256, 0, st>>>(raw, sorted, h->dOffsets, h->dCd, h->cap);
-  // deterministic reductions and cycle close
+  // deterministic reductions of this rank's scores
   k_reduce_hist<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, h->dHProd, h->dHAbs, h->dHLeak, h->dHScat, in.w, sorted.w, h->dCd, h->cap, h->dPartial);
-  k_close_cycle_head<<<1, 32, 0, st>>>(h->dPartial, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase]);
+  k_sum_partials<<<1, 32, 0, st>>>(h->dPartial, h->dKsum);
+  h->launches += 6;
+  h->phaseOpen = phase;
+  return 0;
+}
+
+// cycle close from (possibly rank-reduced) score sums: k estimators, normalisation, scoreMemory%closeCycle
+static int cycleClose(sb_engine* h, const double* dKsum, sb_cycle_result* res) {
+  const int phase = h->phaseOpen;
+  if (phase < 0) { h->err = "sb_cycle_end: no cycle is open"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  k_close_cycle_head<<<1, 32, 0, st>>>(dKsum, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase]);
   int nb = std::max(1, h->nBins[phase]);
   k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
-  h->launches += 7;
+  h->launches += 2;
   h->batchN[phase] += 1;
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -901,46 +968,117 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
     h->msHistories += ms; h->nHistLaunches++; h->segProfiled += (long long)c.nSeg; h->scoreProfiled += (long long)c.nScore;
   }
   if (res) {
-    res->n_start = n; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
+    res->n_start = c.nStart; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
     res->imp_prod = c.impProd; res->imp_abs = c.impAbs; res->scatter_prod = c.scatProd; res->ana_leak = c.anaLeak;
     res->k_analog = c.kAnalog; res->k_implicit = c.kImplicit; res->k_cum = c.kCum; res->k_cum_std = c.kCumStd;
     res->n_segments = (int64_t)c.nSeg; res->n_collisions = (int64_t)c.nColl; res->n_scores = (int64_t)c.nScore; res->error = c.error; res->max_history_segments = c.maxSeg;
   }
-  h->sortedReady = true;
+  h->sortedReady = true; h->phaseOpen = -1;
+  h->kCumLast = c.kCum;
   return checkDeviceError(h, c.error);
 }
 
-int sb_resample(sb_engine* h, int totPop, uint64_t rng_state) {
+int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, sb_cycle_result* res) {
+  if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
+  return cycleClose(h, h->dKsum, res);
+}
+
+int sb_cycle_begin(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, double* dev_sums, int32_t* n_sites) {
+  if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
+  if (dev_sums) CUDA_OK(cudaMemcpyAsync(dev_sums, h->dKsum, 6 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  if (n_sites) *n_sites = std::min(h->hCd->nSites, h->cap);
+  return checkDeviceError(h, h->hCd->error);
+}
+int sb_cycle_end(sb_engine* h, const double* dev_sums, sb_cycle_result* res) {
+  return cycleClose(h, dev_sums ? dev_sums : h->dKsum, res);
+}
+
+static int resampleImpl(sb_engine* h, int totPop, uint64_t rng_state, int nGlobal, int offLocal, int check, int32_t* newLocal) {
   if (!h->sortedReady) { h->err = "sb_resample: no cycle has been run"; return -1; }
-  if (2 * totPop > h->cap) { h->err = "sb_resample: target population exceeds the bank capacity"; return -1; }
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   Bank& sorted = h->bank[(h->cur + 2) % 3]; Bank& dst = h->bank[(h->cur + 1) % 3];
-  const int nSites = h->hCd->nSites;
-  if (nSites <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
-  int g = gridFor(h, nSites, 256);
-  k_rn_generate<<<gridFor(h, (nSites + RN_CHUNK - 1) / RN_CHUNK, 128), 128, 0, st>>>(h->dRn, h->dCd, h->cap, rng_state);
+  const int nSites = std::min(h->hCd->nSites, h->cap);
+  const int nG = nGlobal < 0 ? nSites : nGlobal;
+  if (nG <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
+  unsigned long long* rn = h->dRn;
+  if (nGlobal >= 0) {                                  // the stream over all ranks' banks
+    if ((size_t)nG > h->rnGlobalCap) { cudaFree(h->dRnGlobal); h->rnGlobalCap = (size_t)nG + nG / 4 + 1024; CUDA_OK(cudaMalloc(&h->dRnGlobal, sizeof(unsigned long long) * h->rnGlobalCap)); }
+    rn = h->dRnGlobal;
+  }
+  k_norm_setup<<<1, 1, 0, st>>>(h->dNd, h->dCd, h->cap, totPop, nGlobal, offLocal, check);
+  int g = gridFor(h, nG, 256), gl = gridFor(h, std::max(1, nSites), 256);
+  k_rn_generate<<<gridFor(h, (nG + RN_CHUNK - 1) / RN_CHUNK, 128), 128, 0, st>>>(rn, h->dNd, rng_state);
   k_zero_int<<<gridFor(h, SEL_BINS, 256), 256, 0, st>>>(h->dHist, SEL_BINS);
-  k_sel_hist<<<g, 256, 0, st>>>(h->dRn, h->dCd, h->cap, h->dHist);
-  k_sel_find_bin<<<1, 1024, 0, st>>>(h->dHist, h->dCd, h->cap, totPop);
-  k_sel_collect<<<g, 256, 0, st>>>(h->dRn, h->dCd, h->cap, h->dCand);
+  k_sel_hist<<<g, 256, 0, st>>>(rn, h->dNd, h->dHist);
+  k_sel_find_bin<<<1, 1024, 0, st>>>(h->dHist, h->dCd, h->dNd);
+  k_sel_collect<<<g, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dCand);
   k_sel_threshold<<<1, 1024, 0, st>>>(h->dCand, h->dCd);
-  k_norm_flags<<<g, 256, 0, st>>>(h->dRn, h->dCd, h->cap, totPop, h->dFlag);
-  int tiles = (nSites + SCAN_TILE - 1) / SCAN_TILE;
-  k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dCd->nSites, h->dTile);
-  k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, &h->dCd->nSites, nullptr);
-  k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dCd->nSites, h->dTile, h->dFlagOff);
-  k_norm_scatter<<<g, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dCd, h->cap, totPop, h->cap, h->dCd);
-  k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dCd, h->cap, totPop, h->dCd);
-  h->launches += 12;
+  k_norm_flags<<<gl, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dFlag);
+  int tiles = (std::max(1, nSites) + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile);
+  k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, &h->dNd->nLocal, nullptr);
+  k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile, h->dFlagOff);
+  k_norm_scatter<<<gl, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
+  k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dNd, h->dCd);
+  h->launches += 13;
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
   if (checkDeviceError(h, h->hCd->error)) return -1;
   h->cur = (h->cur + 1) % 3;
   h->nCur = h->hCd->nNew;
-  h->kNormNext = h->hCd->kCum;      // self%nextCycle%k_eff = k_new (eigenPhysicsPackage_class.f90:306)
+  if (newLocal) *newLocal = h->nCur;
+  h->kNormNext = h->kCumLast;       // self%nextCycle%k_eff = k_new (eigenPhysicsPackage_class.f90:306)
   h->sortedReady = false;
+  return 0;
+}
+
+int sb_resample(sb_engine* h, int totPop, uint64_t rng_state) {
+  if (2 * totPop > h->cap) { h->err = "sb_resample: target population exceeds the bank capacity"; return -1; }
+  return resampleImpl(h, totPop, rng_state, -1, 0, 1, nullptr);
+}
+
+int sb_resample_ranked(sb_engine* h, int tot_pop, uint64_t master_rng_state, int n_ranks, int rank, const int32_t* pop_sizes, int32_t* new_local_pop) {
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !pop_sizes) { h->err = "sb_resample_ranked: invalid rank arguments"; return -1; }
+  long long tot = 0, off = 0;
+  for (int i = 0; i < n_ranks; ++i) { if (i < rank) off += pop_sizes[i]; tot += pop_sizes[i]; }
+  if (tot > 2000000000LL) { h->err = "sb_resample_ranked: more than 2^31 sites"; return -1; }
+  if (pop_sizes[rank] != std::min(h->hCd->nSites, h->cap)) { h->err = "sb_resample_ranked: pop_sizes[rank] is not this rank's bank size"; return -1; }
+  return resampleImpl(h, tot_pop, master_rng_state, (int)tot, (int)off, 0, new_local_pop);
+}
+
+// loadBalancing (particleDungeon_class.f90:607-698): sites leave from / arrive at the two ends of the bank
+size_t sb_site_buffer_bytes(int k) { return (size_t)k * (7 * sizeof(double) + sizeof(int32_t)) + 8; }
+int sb_bank_export(sb_engine* h, int k_front, void* dev_buf_front, int k_back, void* dev_buf_back) {
+  CUDA_OK(cudaSetDevice(h->device));
+  if (k_front < 0 || k_back < 0 || k_front + k_back > h->nCur) { h->err = "sb_bank_export: more sites requested than the bank holds"; return -1; }
+  Bank& b = h->bank[h->cur];
+  if (k_front > 0) { k_bank_pack_range<<<gridFor(h, k_front, 256), 256, 0, h->stream>>>(b, 0, k_front, (double*)dev_buf_front); h->launches++; }
+  if (k_back > 0) { k_bank_pack_range<<<gridFor(h, k_back, 256), 256, 0, h->stream>>>(b, h->nCur - k_back, k_back, (double*)dev_buf_back); h->launches++; }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int sb_bank_splice(sb_engine* h, int drop_front, int drop_back, int add_front, const void* dev_buf_front, int add_back, const void* dev_buf_back) {
+  CUDA_OK(cudaSetDevice(h->device));
+  int keep = h->nCur - drop_front - drop_back;
+  if (drop_front < 0 || drop_back < 0 || add_front < 0 || add_back < 0 || keep < 0) { h->err = "sb_bank_splice: invalid counts"; return -1; }
+  int nNew = add_front + keep + add_back;
+  if (nNew > h->cap) { h->err = "Run out of space for particles (loadBalancing)"; return -1; }
+  if (drop_front == 0 && drop_back == 0 && add_front == 0 && add_back == 0) return 0;
+  Bank& src = h->bank[h->cur]; Bank& dst = h->bank[(h->cur + 1) % 3];
+  cudaStream_t st = h->stream;
+  if (add_front > 0) { k_bank_unpack_range<<<gridFor(h, add_front, 256), 256, 0, st>>>(dst, 0, add_front, (const double*)dev_buf_front); h->launches++; }
+  if (keep > 0) { k_bank_copy_range<<<gridFor(h, keep, 256), 256, 0, st>>>(src, drop_front, keep, dst, add_front); h->launches++; }
+  if (add_back > 0) { k_bank_unpack_range<<<gridFor(h, add_back, 256), 256, 0, st>>>(dst, add_front + keep, add_back, (const double*)dev_buf_back); h->launches++; }
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  h->cur = (h->cur + 1) % 3;
+  h->nCur = nNew;
   return 0;
 }
 

@@ -6,6 +6,7 @@
 // The Fortran package would keep this control flow and call sb_* through iso_c_binding
 // (INTEGRATION.md); there is no Fortran compiler in the build image, so the same sequence of
 // calls is written here in C++ and exported with a small C API (sbh_*) for bench.py / tests.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -23,7 +24,8 @@ struct eigenPhysicsPackage {
   // settings
   int pop = 0, totalPop = 0, N_inactive = 0, N_active = 0;
   double keff_0 = 1.0;
-  uint64_t pRNG = 0;
+  uint64_t pRNG = 0, masterRNG = 0;      // masterRNG: the pRNG of rank 0 (normSize_Repr draws from the master's stream)
+  int rank = 0, nRanks = 1;
   int rankOffset = 0;                      // getOffset(totalPop) of this rank (mpi_func.f90:133-159)
   sb::FlatGeometry geom; sb::FlatMgData data; sb::TallyDefs tallies[2];
   sb_engine* eng = nullptr;
@@ -38,12 +40,13 @@ struct eigenPhysicsPackage {
 
   static std::string dirName(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? "." : p.substr(0, k); }
 
-  void stride(int64_t n) { pRNG = sbd::rng_skip(pRNG, sbd::RNG_STRIDE * n); }
+  void stride(int64_t n) { pRNG = sbd::rng_skip(pRNG, sbd::RNG_STRIDE * n); masterRNG = sbd::rng_skip(masterRNG, sbd::RNG_STRIDE * n); }
 
   int fail(const std::string& m) { err = m; return -1; }
   int engFail() { err = sb_last_error(eng); return -1; }
 
-  int init(const std::string& deckPath, const char* overrides, int device, int rank, int nRanks) {
+  int init(const std::string& deckPath, const char* overrides, int device, int rank_, int nRanks_) {
+    rank = rank_; nRanks = nRanks_;
     try {
       sb::Dict dict = sb::Dict::fromFile(deckPath);
       if (overrides && *overrides) {
@@ -56,13 +59,14 @@ struct eigenPhysicsPackage {
       }
       if (dict.getWord("type") != "eigenPhysicsPackage") return fail("only eigenPhysicsPackage decks are driven by this host");
       totalPop = dict.getInt("pop");
-      // getWorkshare / getOffset (mpi_func.f90:133-159): contiguous shares, remainder to the low ranks
-      { int base = totalPop / nRanks, rem = totalPop % nRanks; pop = base + (rank < rem ? 1 : 0); rankOffset = rank * base + std::min(rank, rem); }
+      // getWorkshare / getOffset (mpi_func.f90:133-159): contiguous shares, the remainder goes to the high ranks
+      pop = (totalPop + rank) / nRanks;
+      rankOffset = totalPop / nRanks * rank + std::max(0, totalPop % nRanks + rank - nRanks);
       N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active");
       std::string nucData = dict.getWord("XSdata"), energy = dict.getWord("dataType");
       if (energy != "mg") return fail("dataType must be 'mg' (the CE path is not on the device yet)");
       if (!dict.isPresent("seed")) return fail("an explicit `seed` is required for a reproducible run");
-      pRNG = (uint64_t)(int64_t)dict.getInt("seed");
+      pRNG = (uint64_t)(int64_t)dict.getInt("seed"); masterRNG = pRNG;
       keff_0 = dict.getReal("keff_0", 1.0);
       const sb::Dict& nd = dict.getDict("nuclearData");
       sb::MatMap mats = sb::materialMenu(nd);
@@ -95,7 +99,7 @@ struct eigenPhysicsPackage {
   // run(): pRNG%stride(getOffset(totalPop)) then generateInitialState
   int generateInitialState() {
     if (!eng) return fail("no engine: this handle was created without a device");
-    stride(rankOffset);
+    pRNG = sbd::rng_skip(pRNG, sbd::RNG_STRIDE * (int64_t)rankOffset);      // self%pRNG%stride(getOffset(totalPop)), :142
     if (sb_source_generate(eng, pop, pRNG, 0)) return engFail();
     stride(totalPop);
     return 0;
@@ -115,6 +119,29 @@ struct eigenPhysicsPackage {
     (active ? nSegActive : nSegInactive) += last.n_segments;
     nHist += last.n_start;
     timeTransport += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+  }
+
+  // ---- the cycle in three steps for several ranks; the caller moves the data between ranks ----
+  // 1. transport; this rank's k-eff score sums land in dev_sums (device, 6 doubles) for the all-reduce
+  int cycleBegin(int active, double k_new, double* devSums, int32_t* nSites) {
+    if (!eng) return fail("no engine: this handle was created without a device");
+    if (sb_cycle_begin(eng, pRNG, 0, k_new, active, devSums, nSites)) return engFail();
+    return 0;
+  }
+  // 2. cycle close from the reduced sums; pRNG%stride(totalPop + 1)
+  int cycleEnd(int active, const double* devSums) {
+    if (sb_cycle_end(eng, devSums, &last)) return engFail();
+    stride(totalPop + 1);
+    (active ? nSegActive : nSegInactive) += last.n_segments;
+    nHist += last.n_start;
+    return 0;
+  }
+  // 3. normSize_Repr over all ranks' banks (sizes gathered by the caller); pRNG%stride(1); k_new
+  int resampleRanked(const int32_t* popSizes, int32_t* newLocal, double& k_new) {
+    if (sb_resample_ranked(eng, totalPop, masterRNG, nRanks, rank, popSizes, newLocal)) return engFail();
+    stride(1);
+    k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
     return 0;
   }
 
@@ -138,7 +165,7 @@ struct eigenPhysicsPackage {
     return 0;
   }
   int downloadBank() {
-    int cap = 2 * pop;
+    int cap = 2 * pop + 1024;
     if (cap > hCap) {
       sb_pinned_free(hr); sb_pinned_free(hdir); sb_pinned_free(hw); sb_pinned_free(hG);
       hr = (double*)sb_pinned_alloc(sizeof(double) * 3 * (size_t)cap); hdir = (double*)sb_pinned_alloc(sizeof(double) * 3 * (size_t)cap);
@@ -187,6 +214,7 @@ int sbh_eigen_info(void* pv, int* pop, int* nInactive, int* nActive, int* nG, in
   *nGraph = (int)p->geom.graphIdx.size(); *uniqueCells = p->geom.uniqueCells;
   return 0;
 }
+int sbh_eigen_total_pop(void* pv) { return ((eigenPhysicsPackage*)pv)->totalPop; }
 uint64_t sbh_eigen_rng_state(void* pv) { return ((eigenPhysicsPackage*)pv)->pRNG; }
 void sbh_eigen_set_rng_state(void* pv, uint64_t s) { ((eigenPhysicsPackage*)pv)->pRNG = s; }
 double sbh_eigen_keff0(void* pv) { return ((eigenPhysicsPackage*)pv)->keff_0; }
@@ -196,6 +224,43 @@ int sbh_eigen_cycle(void* pv, int active, double* k, sb_cycle_result* res) {
 }
 int sbh_eigen_cycle_host_buffers(void* pv, int active, double* k, sb_cycle_result* res) {
   auto* p = (eigenPhysicsPackage*)pv; int rc = p->cycleHostBuffers(active, *k); if (res) *res = p->last; return rc;
+}
+int sbh_eigen_cycle_begin(void* pv, int active, double k, double* devSums, int32_t* nSites) { return ((eigenPhysicsPackage*)pv)->cycleBegin(active, k, devSums, nSites); }
+int sbh_eigen_cycle_end(void* pv, int active, const double* devSums, sb_cycle_result* res) {
+  auto* p = (eigenPhysicsPackage*)pv; int rc = p->cycleEnd(active, devSums); if (res) *res = p->last; return rc;
+}
+int sbh_eigen_resample_ranked(void* pv, const int32_t* popSizes, int32_t* newLocal, double* k) {
+  return ((eigenPhysicsPackage*)pv)->resampleRanked(popSizes, newLocal, *k);
+}
+// mpi_func.f90:133-159 getWorkshare / getOffset
+int sbh_workshare(int totPop, int nRanks, int rank, int* share, int* offset) {
+  *share = (totPop + rank) / nRanks;
+  *offset = totPop / nRanks * rank + std::max(0, totPop % nRanks + rank - nRanks);
+  return 0;
+}
+// loadBalancing (particleDungeon_class.f90:607-698): numbers of sites this rank sends to / receives from its neighbours.
+// out = { send to rank+1 (from the end), receive from rank+1 (to the end), send to rank-1 (from the beginning),
+//         receive from rank-1 (to the beginning) }
+int sbh_balance_plan(int totPop, int nRanks, int rank, const int32_t* popSizes, int32_t* out) {
+  long long off1 = 0, off2 = 0;
+  for (int i = 0; i < rank; ++i) off1 += popSizes[i];
+  off2 = off1 + popSizes[rank];
+  int share, t1, t2;
+  sbh_workshare(totPop, nRanks, rank, &share, &t1);
+  if (rank + 1 == nRanks) t2 = totPop; else sbh_workshare(totPop, nRanks, rank + 1, &share, &t2);
+  long long excessEnd = off2 - t2, excessBeg = off1 - t1;
+  out[0] = excessEnd > 0 ? (int)excessEnd : 0; out[1] = excessEnd < 0 ? (int)(-excessEnd) : 0;
+  out[2] = excessBeg < 0 ? (int)(-excessBeg) : 0; out[3] = excessBeg > 0 ? (int)excessBeg : 0;
+  if (out[0] + out[2] > popSizes[rank]) return -1;          // nearest-neighbour balancing cannot fix this distribution
+  return 0;
+}
+// bank <-> page-locked host arrays (the end-to-end mode of a caller that keeps the dungeons in host memory)
+int sbh_eigen_download_bank(void* pv) { return ((eigenPhysicsPackage*)pv)->downloadBank(); }
+int sbh_eigen_upload_bank(void* pv) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  if (p->hN == 0 && p->downloadBank()) return -1;
+  if (sb_bank_upload(p->eng, p->hN, p->hr, p->hdir, p->hw, p->hG)) return p->engFail();
+  return 0;
 }
 int sbh_eigen_cycles(void* pv, int active, int N) { return ((eigenPhysicsPackage*)pv)->cycles(active, N); }
 int sbh_eigen_run(void* pv) { return ((eigenPhysicsPackage*)pv)->run(); }

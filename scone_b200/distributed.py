@@ -1,0 +1,162 @@
+"""Several ranks, one engine (GPU) each: the per-cycle exchanges SCONE does over MPI, on torch.distributed.
+
+  particleDungeon%normSize_Repr / loadBalancing   ParticleObjects/particleDungeon_class.f90:431-698
+  scoreMemory%reduceBins (mpiSync clerks)          Tallies/scoreMemory_class.f90:404-431
+  k_eff broadcast                                  PhysicsPackages/eigenPhysicsPackage_class.f90:302
+  getWorkshare / getOffset                         SharedModules/mpi_func.f90:133-159
+
+Per cycle: all-reduce of the 6 k-eff score sums, all-gather of the fission-bank sizes (twice, one int each),
+and send/recv of the few sites that cross the boundaries between neighbouring ranks. The resampling threshold
+is recomputed on every rank (a pure function of the sizes and the master RNG state): no gather + 3 broadcasts.
+With the nccl backend the buffers are device memory and move over NVLink; with gloo (CPU tests, or several
+ranks sharing one GPU) they are staged through host memory.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .lib import CycleResult, EngineError, load_library
+
+
+def workshare(tot_pop, n_ranks, rank):
+    """(share, offset) of `rank` -- mpi_func.f90:133-159."""
+    L = load_library()
+    s, o = C.c_int32(), C.c_int32()
+    L.sbh_workshare(tot_pop, n_ranks, rank, C.byref(s), C.byref(o))
+    return s.value, o.value
+
+
+def balance_plan(tot_pop, n_ranks, rank, pop_sizes):
+    """loadBalancing counts of `rank`: (send_up, recv_up, send_down, recv_down).
+    up = rank + 1 (sites leave from / arrive at the END of the bank), down = rank - 1 (the BEGINNING)."""
+    L = load_library()
+    sizes = np.ascontiguousarray(pop_sizes, np.int32)
+    out = np.zeros(4, np.int32)
+    rc = L.sbh_balance_plan(tot_pop, n_ranks, rank, sizes.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise EngineError("loadBalancing: rank %d would have to send more sites than it holds (sizes %s)" % (rank, list(pop_sizes)))
+    return tuple(int(x) for x in out)
+
+
+SITE_BYTES = 7 * 8 + 4
+
+
+def site_buffer_bytes(k):
+    return k * SITE_BYTES + 8
+
+
+class TorchComm:
+    """The three exchanges on a torch.distributed process group."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        self.device = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        self.on_device = self.backend == "nccl"
+        self.sums = torch.zeros(6, dtype=torch.float64, device=self.device)      # filled by the engine
+        self._stage = torch.zeros(6, dtype=torch.float64)
+        self._sizes = torch.zeros(self.size, dtype=torch.int32, device=self.device if self.on_device else "cpu")
+        self._one = torch.zeros(1, dtype=torch.int32, device=self.device if self.on_device else "cpu")
+        self._bufs = {}
+
+    def sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
+
+    def all_reduce_sums(self):
+        """In-place sum over ranks of self.sums (device)."""
+        if self.on_device:
+            self.dist.all_reduce(self.sums, group=self.group)
+            self.sync()
+        else:
+            self._stage.copy_(self.sums)
+            self.dist.all_reduce(self._stage, group=self.group)
+            self.sums.copy_(self._stage)
+            self.sync()
+
+    def all_gather_int(self, v):
+        self._one[0] = int(v)
+        self.dist.all_gather_into_tensor(self._sizes, self._one, group=self.group) if self.on_device else \
+            self.dist.all_gather(list(self._sizes.split(1)), self._one, group=self.group)
+        return [int(x) for x in self._sizes.cpu().tolist()]
+
+    def buffer(self, key, nbytes):
+        b = self._bufs.get(key)
+        if b is None or b.numel() < nbytes:
+            b = self.torch.empty(max(nbytes, 1 << 16), dtype=self.torch.uint8, device=self.device)
+            self._bufs[key] = b
+        return b
+
+    def exchange(self, sends, recvs):
+        """sends / recvs: lists of (peer, device uint8 tensor view of exact length). Nearest neighbours only."""
+        dist = self.dist
+        if self.on_device:
+            ops = [dist.P2POp(dist.isend, t, p, group=self.group) for p, t in sends] + [dist.P2POp(dist.irecv, t, p, group=self.group) for p, t in recvs]
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+                self.sync()
+        else:
+            reqs, staged = [], []
+            for p, t in sends:
+                reqs.append(dist.isend(t.cpu(), p, group=self.group))
+            for p, t in recvs:
+                c = self.torch.empty(t.numel(), dtype=self.torch.uint8)
+                staged.append((t, c))
+                reqs.append(dist.irecv(c, p, group=self.group))
+            for r in reqs:
+                r.wait()
+            for t, c in staged:
+                t.copy_(c)
+            self.sync()
+
+
+def cycle(pp, active, comm):
+    """One cycle of `pp` (EigenPhysicsPackage created with rank / n_ranks) in step with the other ranks.
+    eigenPhysicsPackage_class.f90:203-307 with MPI defined."""
+    L = pp.L
+    n_sites = C.c_int32()
+    if L.sbh_eigen_cycle_begin(pp.h, 1 if active else 0, pp.k, comm.sums.data_ptr(), C.byref(n_sites)) != 0:
+        raise EngineError(pp._err())
+    comm.all_reduce_sums()
+    res = CycleResult()
+    if L.sbh_eigen_cycle_end(pp.h, 1 if active else 0, comm.sums.data_ptr(), C.byref(res)) != 0:
+        raise EngineError(pp._err())
+    sizes = np.asarray(comm.all_gather_int(n_sites.value), np.int32)
+    new_local, k = C.c_int32(), C.c_double(pp.k)
+    if L.sbh_eigen_resample_ranked(pp.h, sizes.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(new_local), C.byref(k)) != 0:
+        raise EngineError(pp._err())
+    pp.k = k.value
+    sizes2 = comm.all_gather_int(new_local.value)
+    if sum(sizes2) != pp.total_pop:
+        raise EngineError("Normalisation failed!")
+    if comm.size > 1:
+        load_balance(pp, comm, sizes2)
+    return res
+
+
+def load_balance(pp, comm, sizes):
+    """particleDungeon%loadBalancing on the device banks."""
+    L, eng = pp.L, pp.engine
+    send_up, recv_up, send_down, recv_down = balance_plan(pp.total_pop, comm.size, comm.rank, sizes)
+    if not (send_up or recv_up or send_down or recv_down):
+        return
+    view = lambda key, k: comm.buffer(key, site_buffer_bytes(k))[:site_buffer_bytes(k)]
+    su, sd, ru, rd = view("su", send_up), view("sd", send_down), view("ru", recv_up), view("rd", recv_down)
+    if L.sb_bank_export(eng, send_down, sd.data_ptr(), send_up, su.data_ptr()) != 0:
+        raise EngineError(pp._eng_err())
+    sends, recvs = [], []
+    if send_up:
+        sends.append((comm.rank + 1, su))
+    if send_down:
+        sends.append((comm.rank - 1, sd))
+    if recv_up:
+        recvs.append((comm.rank + 1, ru))
+    if recv_down:
+        recvs.append((comm.rank - 1, rd))
+    comm.exchange(sends, recvs)
+    if L.sb_bank_splice(eng, send_down, send_up, recv_down, rd.data_ptr(), recv_up, ru.data_ptr()) != 0:
+        raise EngineError(pp._eng_err())

@@ -93,6 +93,8 @@ class EigenPhysicsPackage(_Base):
         v = [C.c_int32() for _ in range(7)]
         self.L.sbh_eigen_info(self.h, *[C.byref(x) for x in v])
         self.pop, self.n_inactive, self.n_active, self.n_groups, self.n_mat, self.n_graph, self.unique_cells = [x.value for x in v]
+        self.total_pop = int(self.L.sbh_eigen_total_pop(self.h))
+        self.rank, self.n_ranks = rank, n_ranks
         self.k = self.L.sbh_eigen_keff0(self.h)
 
     # -- reference-named procedures ----------------------------------------------------------
@@ -100,8 +102,22 @@ class EigenPhysicsPackage(_Base):
         if self.L.sbh_eigen_generate_initial_state(self.h) != 0:
             raise EngineError(self._err())
 
-    def cycle(self, active, host_buffers=False):
-        """One cycle; returns the CycleResult. self.k is k_new afterwards."""
+    def cycle(self, active, host_buffers=False, comm=None):
+        """One cycle; returns the CycleResult. self.k is k_new afterwards.
+        comm: a scone_b200.distributed.TorchComm when the bank is shared between ranks."""
+        if comm is not None:
+            from . import distributed
+            if host_buffers:                    # dungeons kept in (pinned) host memory: upload, cycle, download
+                if self.L.sbh_eigen_upload_bank(self.h) != 0:
+                    raise EngineError(self._err())
+            res = distributed.cycle(self, active, comm)
+            if host_buffers:
+                if self.L.sbh_eigen_download_bank(self.h) != 0:
+                    raise EngineError(self._err())
+                self.last_bins(active)
+            return res
+        if self.n_ranks > 1:
+            raise EngineError("this package owns a share of the bank (n_ranks > 1): pass comm= to cycle()")
         k = C.c_double(self.k)
         res = CycleResult()
         fn = self.L.sbh_eigen_cycle_host_buffers if host_buffers else self.L.sbh_eigen_cycle
@@ -110,10 +126,10 @@ class EigenPhysicsPackage(_Base):
         self.k = k.value
         return res
 
-    def cycles(self, active, n):
+    def cycles(self, active, n, comm=None):
         out = None
         for _ in range(n):
-            out = self.cycle(active)
+            out = self.cycle(active, comm=comm)
         return out
 
     def run(self):
@@ -131,7 +147,7 @@ class EigenPhysicsPackage(_Base):
         self.L.sbh_eigen_set_rng_state(self.h, s)
 
     def bank(self):
-        cap = 2 * self.pop
+        cap = 2 * self.pop + 1024
         n = C.c_int32()
         r = np.zeros((cap, 3)); d = np.zeros((cap, 3)); w = np.zeros(cap); G = np.zeros(cap, np.int32)
         if self.L.sb_bank_download(self.engine, cap, C.byref(n), _dp(r), _dp(d), _dp(w), _ip(G)) != 0:
