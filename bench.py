@@ -70,12 +70,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def oracle_rate(deck, pop, n_inactive, seconds, threads):
+def oracle_rate(deck, pop, n_inactive, seconds, threads, tracking="DT"):
     """CPU arm: oracle (C++ restatement of SCONE's OpenMP loop) active-cycle neutrons/s on `threads` threads."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from tests import oracle_lib as ol
     orc = ol.load()
-    ov = "pop %d; inactive %d; active 1000000; seed 20261017;" % (pop, n_inactive)
+    ov = "pop %d; inactive %d; active 1000000; seed 20261017; transportOperator { type transportOperator%s; }" % (pop, n_inactive, tracking)
     e = orc.orc_eigen_load(os.path.join(ROOT, deck).encode(), ov.encode())
     if not e:
         raise RuntimeError(ol.err(orc))
@@ -106,7 +106,7 @@ def run_reference(args, rank, world):
     orc = ol.load()
     deck = DECKS[args.deck]
     pop = args.pop
-    ov = "pop %d; inactive %d; active 1000000; seed 20261017;" % (pop, args.inactive)
+    ov = "pop %d; inactive %d; active 1000000; seed 20261017; transportOperator { type transportOperator%s; }" % (pop, args.inactive, args.tracking)
     e = orc.orc_eigen_load(os.path.join(ROOT, deck).encode(), ov.encode())
     if not e:
         raise RuntimeError(ol.err(orc))
@@ -129,7 +129,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "active-cycle neutrons/s", "value": val, "unit": "neutrons/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": "DT",
+        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking,
                    "note": "CPU reference arm: one step = one active cycle of pop histories on the host cores"},
         "segments_per_s": (s1.value - s0.value) / dt, "keff": k,
         "cpu_baseline": {"value": val, "unit": "neutrons/s", "cores": threads, "kind": "port",
@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--deck", default="c5g7", choices=sorted(DECKS))
     ap.add_argument("--pop", type=int, default=100000, help="histories per cycle PER GPU (weak scaling)")
     ap.add_argument("--inactive", type=int, default=10, help="untimed inactive cycles before the active phase")
+    ap.add_argument("--tracking", default="DT", choices=["DT", "ST", "HT"], help="transportOperator (the shipped C5G7 deck uses HT, BASELINE configs[0] names delta tracking)")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -170,7 +171,8 @@ def main():
     deck = os.path.join(ROOT, DECKS[args.deck])
     pop = args.pop
     total_pop = pop * world
-    ov = "pop %d; inactive %d; active %d; seed 20261017;" % (total_pop, args.inactive, args.warmup + 2 * args.steps + 4)
+    ov = "pop %d; inactive %d; active %d; seed 20261017; transportOperator { type transportOperator%s; }" % (
+        total_pop, args.inactive, args.warmup + 2 * args.steps + 4, args.tracking)
     pp = scone_b200.EigenPhysicsPackage(deck, ov, device=local, rank=rank, n_ranks=world)
     comm = scone_b200.distributed.TorchComm(device=torch.device("cuda", local)) if world > 1 else None
     L = pp.L
@@ -261,7 +263,7 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            r = oracle_rate(DECKS[args.deck], pop, 3, args.cpu_seconds, threads)
+            r = oracle_rate(DECKS[args.deck], pop, 3, args.cpu_seconds, threads, args.tracking)
             cpu = {"value": r["nps"], "unit": "neutrons/s", "cores": threads, "kind": "port", "segments_per_s": r["sps"],
                    "sample": "%d active cycles of %d histories in %.1f s (oracle: C++/OpenMP restatement of SCONE's history loop; "
                              "SCONE is Fortran and cannot be compiled in this image)" % (r["cycles"], pop, r["seconds"])}
@@ -270,7 +272,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD[args.deck], "deck": DECKS[args.deck], "pop_per_cycle_per_gpu": pop, "pop_per_cycle_total": total_pop,
-                       "tracking": "DT", "inactive_cycles_before": args.inactive,
+                       "tracking": args.tracking, "inactive_cycles_before": args.inactive,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
                        "parallelism": "bank sharded by history index over %d GPU(s)%s" % (
                            world, "; per cycle: all-reduce of 6 f64 k-eff sums, 2 all-gathers of one int, neighbour send/recv of boundary sites (NCCL)" if world > 1 else "")},

@@ -24,6 +24,7 @@
 
 #include "sb_device.cuh"
 #include "sb_hist.cuh"
+#include "sb_track.cuh"
 
 using namespace sbd;
 using sbh::Bank; using sbh::CycleDev; using sbh::HistArgs; using sbh::HotLayout; using sbh::HUni;
@@ -499,7 +500,7 @@ struct sb_engine {
   std::vector<double> xs, P0, prod, P1, chi, majorant; std::vector<int> fissile;
   std::vector<DClerk> clerks[2]; std::vector<std::vector<char>> clerkAux[2]; int nBins[2] = {0, 0}; int normAddr[2] = {0, 0}; double normVal[2] = {1.0, 1.0};
   std::vector<sb_clerk> clerkDefs[2]; std::vector<std::vector<double>> mapBounds[2]; std::vector<std::vector<int>> mapMat[2];
-  Model M{}; char* dBlob = nullptr; bool blobDirty = true; int useSmem = 0;
+  Model M{}; char* dBlob = nullptr; bool blobDirty = true; int useSmem = 0, trackSmem = 0;
   sb_options opt{SB_TRACK_DT, 0.9, 1, 0, 0, 0};
   // banks
   int cap = 0; Bank bank[3]{}; int cur = 0;          // bank[cur] = this cycle; others: raw sites, sorted/next
@@ -585,7 +586,20 @@ static int buildBlob(sb_engine* h) {
   M.oXs = put(blob, h->xs); M.oP0 = put(blob, h->P0); M.oProd = put(blob, h->prod);
   M.oP1 = h->isP1 ? put(blob, h->P1) : M.oP0;
   M.oChi = put(blob, h->chi); M.oFissile = put(blob, h->fissile); M.oMajorant = put(blob, h->majorant);
-  for (int ph = 0; ph < 2; ++ph) { M.nClerk[ph] = (int)h->clerks[ph].size(); M.nBins[ph] = h->nBins[ph]; M.oClerk[ph] = 0; }
+  for (int ph = 0; ph < 2; ++ph) {
+    // per-map auxiliary tables first, then the clerk records that point at them
+    std::vector<DClerk> cl = h->clerks[ph];
+    for (size_t c = 0; c < cl.size(); ++c)
+      for (int m = 0; m < cl[c].nMaps; ++m) {
+        size_t key = c * SB_MAX_MAPS + m;
+        if (cl[c].mapType[m] == SB_MAP_MATERIAL) cl[c].mapOff[m] = put(blob, h->mapMat[ph][key]);
+        else if (cl[c].mapGrid[m] == SB_GRID_UNSTRUCT) cl[c].mapOff[m] = put(blob, h->mapBounds[ph][key]);
+        else cl[c].mapOff[m] = 0;
+      }
+    M.nClerk[ph] = (int)cl.size(); M.nBins[ph] = h->nBins[ph];
+    if (cl.empty()) cl.push_back(DClerk{});
+    M.oClerk[ph] = put(blob, cl);
+  }
   while (blob.size() % 16) blob.push_back(0);
   M.blobBytes = (int)blob.size();
   memcpy(blob.data(), &M, sizeof(Model));
@@ -593,6 +607,8 @@ static int buildBlob(sb_engine* h) {
   cudaFree(h->dBlob);
   CUDA_OK(cudaMalloc(&h->dBlob, blob.size()));
   CUDA_OK(cudaMemcpy(h->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  h->trackSmem = (M.blobBytes <= 50 * 1024) ? 1 : 0;           // 4 CTAs of 128 threads per SM
+  if (h->trackSmem) CUDA_OK(cudaFuncSetAttribute(sbt::k_histories_track, cudaFuncAttributeMaxDynamicSharedMemorySize, M.blobBytes));
 
   // ---- hot blob ----------------------------------------------------------------------------------
   {
@@ -817,7 +833,7 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
 }
 
 int sb_set_options(sb_engine* h, const sb_options* o) {
-  if (o->tracking != SB_TRACK_DT) { h->err = "sb_set_options: only delta tracking (transportOperatorDT) is implemented on the device in this round"; return -1; }
+  if (o->tracking != SB_TRACK_DT && o->tracking != SB_TRACK_ST && o->tracking != SB_TRACK_HT) { h->err = "sb_set_options: unknown tracking"; return -1; }
   { int keep = h->opt.blocks_per_sm; h->opt = *o; if (h->opt.blocks_per_sm <= 0) h->opt.blocks_per_sm = keep; }
   if (o->max_pop > 0) return ensureCapacity(h, o->max_pop);
   return 0;
@@ -928,6 +944,16 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
+  if (h->opt.tracking != SB_TRACK_DT) {                       // surface / hybrid tracking: coordList-carrying kernel
+    sbt::TrackArgs t{};
+    t.M = h->M; t.blob = h->dBlob; t.useSmem = h->trackSmem; t.seedTab = h->dSeedTab;
+    t.n = n; t.in = in; t.out = raw; t.cap = h->cap;
+    t.nsites = h->dNsites; t.hProd = h->dHProd; t.hAbs = h->dHAbs; t.hLeak = h->dHLeak; t.hScat = h->dHScat;
+    t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
+    t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
+    int tb = std::min(h->numSM * 4, (n + 127) / 128);
+    sbt::k_histories_track<<<tb, 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
+  } else
   if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, threads, h->hot.bytes, st>>>(a);
   else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, threads, h->hot.bytes, st>>>(a);
   else sbh::k_histories<false, 2><<<blocks, threads, 0, st>>>(a);

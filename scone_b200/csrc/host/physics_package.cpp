@@ -78,8 +78,8 @@ struct eigenPhysicsPackage {
       const sb::Dict& to = dict.getDict("transportOperator");
       std::string tt = to.getWord("type");
       if (tt == "transportOperatorDT") opt.tracking = SB_TRACK_DT;
-      else if (tt == "transportOperatorST") opt.tracking = SB_TRACK_ST;
-      else if (tt == "transportOperatorHT") { opt.tracking = SB_TRACK_HT; opt.ht_cutoff = to.getReal("cutoff", 0.9); }
+      else if (tt == "transportOperatorST") { opt.tracking = SB_TRACK_ST; opt.st_cache = to.getBool("cache", true) ? 1 : 0; }
+      else if (tt == "transportOperatorHT") { opt.tracking = SB_TRACK_HT; opt.ht_cutoff = to.getReal("cutoff", 0.9); opt.st_cache = to.getBool("cache", true) ? 1 : 0; }
       else return fail("Unrecognised type of transportOperator: " + tt);
       tallies[0] = sb::buildTallies(dict.getDict("inactiveTally"), mats, data.nMat);
       tallies[1] = sb::buildTallies(dict.getDict("activeTally"), mats, data.nMat);

@@ -25,9 +25,19 @@ def oracle_bank(orc, e):
     return r, d, w, G
 
 
-@pytest.mark.parametrize("deck,pop,ninact,nact", [("inf", 4000, 3, 3), ("slab", 4000, 3, 3), ("c5g7", 20000, 3, 3), ("c5g7_3d", 10000, 2, 2)])
-def test_cycles_bit_exact_against_oracle(orc, deck, pop, ninact, nact):
-    ov = "pop %d; inactive %d; active %d; seed 12345;" % (pop, ninact, nact)
+ST = " transportOperator { type transportOperatorST; }"
+ST_NOCACHE = " transportOperator { type transportOperatorST; cache 0; }"
+HT = " transportOperator { type transportOperatorHT; cutoff 0.9; }"
+HT_HALF = " transportOperator { type transportOperatorHT; cutoff 0.5; cache 0; }"
+
+
+@pytest.mark.parametrize("deck,pop,ninact,nact,tracking", [
+    ("inf", 4000, 3, 3, ""), ("slab", 4000, 3, 3, ""), ("c5g7", 20000, 3, 3, ""), ("c5g7_3d", 10000, 2, 2, ""),
+    # surface tracking (transportOperatorST) and hybrid tracking (transportOperatorHT): coordList, distance cache, crossings, explicit BCs
+    ("c5g7", 8000, 2, 2, ST), ("c5g7", 8000, 2, 2, HT), ("c5g7", 6000, 2, 1, ST_NOCACHE), ("c5g7", 6000, 2, 1, HT_HALF),
+    ("slab", 4000, 2, 2, ST), ("inf", 4000, 2, 2, ST), ("c5g7_3d", 5000, 2, 1, HT), ("c5g7_3d", 4000, 1, 1, ST)])
+def test_cycles_bit_exact_against_oracle(orc, deck, pop, ninact, nact, tracking):
+    ov = "pop %d; inactive %d; active %d; seed 12345;%s" % (pop, ninact, nact, tracking)
     orc.orc_set_math_mode(1)
     try:
         e = orc.orc_eigen_load(DECK[deck].encode(), ov.encode())
