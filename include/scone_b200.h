@@ -84,6 +84,17 @@ typedef struct sb_mg_flat {
   const int32_t* fissile; const double* majorant; double collision_xs;
 } sb_mg_flat;
 
+/* ---- continuous-energy data: NuclearData/ceNeutronData/aceDatabase/ ---------------------------
+ * What aceNeutronDatabase holds after init (aceNeutronDatabase_class.f90:873-1163): per nuclide the energy grid
+ * eGrid(N) and mainData(rows, N) (rows = 4 non-fissile / 8 fissile: TOTAL, ESCATTER, IESCATTER, CAPTURE, FISSION,
+ * NU_FISSION, KAPPA, PROMPT_NU_FISSION; aceNeutronNuclide_class.f90:44-54), Fortran storage order (rows of one
+ * energy point contiguous); per material the nuclide indices (1-based) and atomic densities in composition order
+ * (ceNeutronMaterial_class.f90). grid / data are the concatenations over nuclides.                             */
+typedef struct sb_ce_flat {
+  int32_t n_nuc; const int32_t* grid_size; const int32_t* rows; const double* grid; const double* data;
+  int32_t n_mat; const int32_t* mat_off /*[n_mat+1]*/; const int32_t* mat_nuc; const double* mat_dens;
+} sb_ce_flat;
+
 /* ---- tallies: Tallies/TallyClerks/collisionClerk_class.f90, TallyMaps/, TallyResponses/ ---- */
 enum { SB_MAP_SPACE = 1, SB_MAP_MATERIAL = 2, SB_MAP_ENERGY = 3 };
 enum { SB_GRID_LIN = 1, SB_GRID_LOG = 2, SB_GRID_UNSTRUCT = 3 };
@@ -195,6 +206,23 @@ int sb_flush_l2(sb_engine* h, size_t bytes);
 /* page-locked host memory for the banks the caller keeps (so that uploads/downloads are true async DMA) */
 void* sb_pinned_alloc(size_t bytes);
 void  sb_pinned_free(void* p);
+
+/* ---- continuous-energy cross-section lookup (the XS-lookup event kernel) -----------------------
+ * sb_load_ce_data builds the unionised grid + majorant (initMajorant, aceNeutronDatabase_class.f90:1330-1621) and the
+ * per-nuclide index table on the device. sb_ce_lookup: for n particles (E [MeV], matIdx 1-based) any of
+ *   total    [n]    Sigma_t of the material (updateTotalMatXS / getTrackMatXS, :402-443,509-571)
+ *   macro    [n][8] full neutronMacroXSs set (updateMacroXSs, :579-644), order as mainData rows
+ *   majorant [n]    unionised majorant at E (updateMajorantXS, :346-394)
+ * NULL outputs are skipped. Host pointers: copied in and out (the end-to-end path); *_device: device pointers, no copies.
+ * sb_ce_nuclide_index: the index aceNeutronNuclide%search returns for nuclide nuc_idx (parity: bit-exact).        */
+int sb_load_ce_data(sb_engine* h, const sb_ce_flat* d);
+int sb_ce_union_size(sb_engine* h);
+int sb_ce_union(sb_engine* h, double* grid, double* majorant);
+int sb_ce_lookup(sb_engine* h, int64_t n, const double* E, const int32_t* mat, double* total, double* macro, double* majorant);
+int sb_ce_lookup_device(sb_engine* h, int64_t n, const double* dE, const int32_t* dMat, double* dTotal, double* dMacro, double* dMajorant);
+int sb_ce_nuclide_index(sb_engine* h, int nuc_idx, int64_t n, const double* E, int32_t* idx);
+/* CUDA-event time of the last sb_ce_lookup_device launch, in ms */
+int sb_ce_last_kernel_ms(sb_engine* h, double* ms);
 
 /* ---- batch queries used by the parity tests (same device functions as the cycle kernel) ---- */
 /* placeCoord / whatIsAt for n points; if dist != NULL teleport by dist[i] first (geometryStd teleport) */

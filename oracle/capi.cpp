@@ -411,6 +411,77 @@ int orc_eigen_stats(void* ev, long* seg, long* coll, long* hist) {
 
 }  // extern "C"
 
+
+// ---------------------------------------------------------------------------------------------------------
+// continuous-energy data (oracle/cedata.hpp)
+// ---------------------------------------------------------------------------------------------------------
+#include "cedata.hpp"
+#define CE_TRY try {
+#define CE_CATCH(ret) } catch (const std::exception& ex) { g_err = ex.what(); return ret; }
+extern "C" {
+void* orc_ce_nuclide_from_ace(const char* path, int lineNum) {
+  CE_TRY
+  orc_ce::AceCard ace; ace.readFromFile(path, lineNum);
+  auto* n = new orc_ce::Nuclide(); n->init(ace, true);
+  return n;
+  CE_CATCH(nullptr)
+}
+void* orc_ce_nuclide_from_arrays(int n, int rows, const double* grid, const double* data) {
+  auto* nuc = new orc_ce::Nuclide(); nuc->fromArrays(n, rows, grid, data); return nuc;
+}
+void orc_ce_nuclide_free(void* h) { delete (orc_ce::Nuclide*)h; }
+int orc_ce_nuclide_info(void* h, int* n, int* rows, double* mass, double* kT) {
+  auto* x = (orc_ce::Nuclide*)h; *n = x->N(); *rows = x->rows; *mass = x->mass; *kT = x->kT; return 0;
+}
+int orc_ce_nuclide_data(void* h, double* grid, double* data) {
+  auto* x = (orc_ce::Nuclide*)h;
+  std::copy(x->eGrid.begin(), x->eGrid.end(), grid); std::copy(x->main.begin(), x->main.end(), data); return 0;
+}
+int orc_ce_nuclide_search(void* h, double E, int* idx, double* f) { CE_TRY ((orc_ce::Nuclide*)h)->search(*idx, *f, E); return 0; CE_CATCH(-1) }
+int orc_ce_nuclide_micro(void* h, double E, double* out8) {
+  CE_TRY auto* x = (orc_ce::Nuclide*)h; int idx; double f; x->search(idx, f, E); x->microXSs(out8, idx, f); return 0; CE_CATCH(-1)
+}
+double orc_ce_nuclide_total(void* h, double E) {
+  CE_TRY auto* x = (orc_ce::Nuclide*)h; int idx; double f; x->search(idx, f, E); return x->totalXS(idx, f); CE_CATCH(std::nan(""))
+}
+int orc_ce_nuclide_nubar(void* h, double E, double* total, double* prompt, double* delayed) {
+  CE_TRY auto* x = (orc_ce::Nuclide*)h; *total = x->release(E); *prompt = x->releasePrompt(E); *delayed = x->releaseDelayed(E); return 0; CE_CATCH(-1)
+}
+void* orc_ce_db_new() { return new orc_ce::Database(); }
+void orc_ce_db_free(void* h) { delete (orc_ce::Database*)h; }
+int orc_ce_db_add_nuclide(void* h, void* nuc) { auto* d = (orc_ce::Database*)h; d->nuclides.push_back(*(orc_ce::Nuclide*)nuc); return (int)d->nuclides.size(); }
+int orc_ce_db_add_material(void* h, int n, const int* nucIdx, const double* dens) {
+  auto* d = (orc_ce::Database*)h; orc_ce::Material m; m.nuclides.assign(nucIdx, nucIdx + n); m.dens.assign(dens, dens + n); d->materials.push_back(m); return (int)d->materials.size();
+}
+int orc_ce_db_finalise(void* h) { CE_TRY auto* d = (orc_ce::Database*)h; d->finalise(); d->initMajorant(); return (int)d->eGridUnion.size(); CE_CATCH(-1) }
+int orc_ce_db_union(void* h, double* grid, double* maj) {
+  auto* d = (orc_ce::Database*)h; std::copy(d->eGridUnion.begin(), d->eGridUnion.end(), grid); std::copy(d->majorant.begin(), d->majorant.end(), maj); return 0;
+}
+// batch lookups (the CPU side of the parity tests and of bench.py's cpu_baseline for the lookup kernel); OpenMP over particles
+int orc_ce_db_total_n(void* h, long n, const double* E, const int* mat, double* out) {
+  CE_TRY auto* d = (orc_ce::Database*)h;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) out[i] = d->totalMatXS(E[i], mat[i]);
+  return 0; CE_CATCH(-1)
+}
+int orc_ce_db_macro_n(void* h, long n, const double* E, const int* mat, double* out8) {
+  CE_TRY auto* d = (orc_ce::Database*)h;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) d->macroXSs(out8 + 8 * i, E[i], mat[i]);
+  return 0; CE_CATCH(-1)
+}
+int orc_ce_db_majorant_n(void* h, long n, const double* E, double* out) {
+  CE_TRY auto* d = (orc_ce::Database*)h;
+  for (long i = 0; i < n; ++i) out[i] = d->majorantXS(E[i]);
+  return 0; CE_CATCH(-1)
+}
+int orc_ce_db_index_n(void* h, int nucIdx, long n, const double* E, int* idx) {
+  auto* d = (orc_ce::Database*)h; const auto& g = d->nuclides.at(nucIdx - 1).eGrid;
+  for (long i = 0; i < n; ++i) idx[i] = orc_ce::binarySearch(g, E[i]);
+  return 0;
+}
+}  // extern "C"
+
 #ifdef ORC_MAIN
 // scone_oracle <deck> [--omp N] [--pop P] [--inactive I] [--active A] [--seed S] [--tracking DT|ST|HT] [--math libm|sb]
 int main(int argc, char** argv) {

@@ -25,6 +25,7 @@
 #include "sb_device.cuh"
 #include "sb_hist.cuh"
 #include "sb_track.cuh"
+#include "sb_ce.cuh"
 
 using namespace sbd;
 using sbh::Bank; using sbh::CycleDev; using sbh::HistArgs; using sbh::HotLayout; using sbh::HUni;
@@ -522,6 +523,7 @@ struct sb_engine {
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
   double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
   double* dStage = nullptr; size_t stageBytes = 0;
+  sbce::CeHost ce; int* dCeErr = nullptr; cudaEvent_t evC0 = nullptr, evC1 = nullptr; float ceLastMs = 0.f;
 };
 
 static std::string g_globalErr;
@@ -741,7 +743,7 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
-  cudaFree(h->dStage);
+  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1144,6 +1146,77 @@ int sb_flush_l2(sb_engine* h, size_t bytes) {
   CUDA_OK(cudaSetDevice(h->device));
   if (ensureStage(h, bytes)) return -1;
   CUDA_OK(cudaMemsetAsync(h->dStage, 0, bytes, h->stream));
+  return 0;
+}
+
+// ---- continuous-energy lookup ----------------------------------------------------------------------
+static int ceLaunch(sb_engine* h, int64_t n, const double* dE, const int* dMat, double* dT, double* dM, double* dJ, int* dIdx, int probeNuc) {
+  if (!h->ce.loaded) { h->err = "continuous-energy data has not been loaded (sb_load_ce_data)"; return -1; }
+  if (!h->dCeErr) { CUDA_OK(cudaMalloc(&h->dCeErr, sizeof(int))); CUDA_OK(cudaEventCreate(&h->evC0)); CUDA_OK(cudaEventCreate(&h->evC1)); }
+  CUDA_OK(cudaMemsetAsync(h->dCeErr, 0, sizeof(int), h->stream));
+  int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 8);
+  if (blocks < 1) blocks = 1;
+  CUDA_OK(cudaEventRecord(h->evC0, h->stream));
+  sbce::k_ce_lookup<<<blocks, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, dM, dJ, dIdx, probeNuc, h->dCeErr);
+  CUDA_OK(cudaEventRecord(h->evC1, h->stream));
+  h->launches++;
+  int e = 0;
+  CUDA_OK(cudaMemcpyAsync(&e, h->dCeErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventElapsedTime(&h->ceLastMs, h->evC0, h->evC1));
+  if (e == 1) { h->err = "Failed to find energy in the nuclide energy grids (energy outside the bounds of the data)"; return -1; }
+  if (e == 2) { h->err = "Invalid material index in continuous-energy lookup"; return -1; }
+  return 0;
+}
+int sb_load_ce_data(sb_engine* h, const sb_ce_flat* d) {
+  CUDA_OK(cudaSetDevice(h->device));
+  h->err.clear();
+  if (sbce::ceBuild(h->ce, d, h->err)) return -1;
+  sbce::k_ce_majorant<<<std::max(1, std::min((h->ce.dev.nUnion + 127) / 128, h->numSM * 8)), 128, 0, h->stream>>>(h->ce.dev, (double*)h->ce.dev.uMaj);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(h->ce.uMaj.data(), h->ce.dev.uMaj, sizeof(double) * h->ce.uMaj.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int sb_ce_union_size(sb_engine* h) { return h->ce.loaded ? h->ce.dev.nUnion : 0; }
+int sb_ce_union(sb_engine* h, double* grid, double* majorant) {
+  if (!h->ce.loaded) { h->err = "continuous-energy data has not been loaded"; return -1; }
+  std::copy(h->ce.uGrid.begin(), h->ce.uGrid.end(), grid); std::copy(h->ce.uMaj.begin(), h->ce.uMaj.end(), majorant);
+  return 0;
+}
+int sb_ce_lookup_device(sb_engine* h, int64_t n, const double* dE, const int32_t* dMat, double* dTotal, double* dMacro, double* dMajorant) {
+  CUDA_OK(cudaSetDevice(h->device));
+  return ceLaunch(h, n, dE, dMat, dTotal, dMacro, dMajorant, nullptr, 0);
+}
+int sb_ce_last_kernel_ms(sb_engine* h, double* ms) { *ms = h->ceLastMs; return 0; }
+int sb_ce_lookup(sb_engine* h, int64_t n, const double* E, const int32_t* mat, double* total, double* macro, double* majorant) {
+  CUDA_OK(cudaSetDevice(h->device));
+  if (n <= 0) return 0;
+  // staging: E | mat | total | macro | majorant
+  size_t need = sizeof(double) * (size_t)n * (1 + 1 + 1 + 8 + 1);
+  if (ensureStage(h, need)) return -1;
+  double* dE = h->dStage; int* dMat = (int*)(dE + n); double* dT = dE + 2 * n; double* dM = dE + 3 * n; double* dJ = dE + 11 * n;
+  cudaStream_t st = h->stream;
+  CUDA_OK(cudaMemcpyAsync(dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  if (mat) CUDA_OK(cudaMemcpyAsync(dMat, mat, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  if ((total || macro) && !mat) { h->err = "sb_ce_lookup: material indices are required for total / macro"; return -1; }
+  if (ceLaunch(h, n, dE, dMat, total ? dT : nullptr, macro ? dM : nullptr, majorant ? dJ : nullptr, nullptr, 0)) return -1;
+  if (total) CUDA_OK(cudaMemcpyAsync(total, dT, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (macro) CUDA_OK(cudaMemcpyAsync(macro, dM, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
+  if (majorant) CUDA_OK(cudaMemcpyAsync(majorant, dJ, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+int sb_ce_nuclide_index(sb_engine* h, int nuc_idx, int64_t n, const double* E, int32_t* idx) {
+  CUDA_OK(cudaSetDevice(h->device));
+  if (!h->ce.loaded || nuc_idx < 1 || nuc_idx > h->ce.nNuc) { h->err = "sb_ce_nuclide_index: invalid nuclide index"; return -1; }
+  if (ensureStage(h, sizeof(double) * 2 * (size_t)n)) return -1;
+  double* dE = h->dStage; int* dI = (int*)(dE + n);
+  CUDA_OK(cudaMemcpyAsync(dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  if (ceLaunch(h, n, dE, nullptr, nullptr, nullptr, nullptr, dI, nuc_idx)) return -1;
+  CUDA_OK(cudaMemcpy(idx, dI, sizeof(int) * n, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -1,0 +1,236 @@
+// Continuous-energy cross-section lookup on the device (the XS-lookup event kernel of the CE path).
+//
+//   aceNeutronNuclide%search / totalXS / microXSs   aceDatabase/aceNeutronNuclide_class.f90:342-453
+//   aceNeutronDatabase%updateTotalMatXS / updateMacroXSs / updateMajorantXS / initMajorant
+//                                                   aceDatabase/aceNeutronDatabase_class.f90:346-394,509-644,1330-1621
+//   binarySearch                                    SharedModules/genericProcedures.f90:132-166
+//
+// The reference does one binary search per nuclide per lookup (~12 dependent loads for a 3667-point grid).
+// Here the searches are replaced by ONE search on the unionised grid of all nuclides plus a table
+// idxTab[union interval][nuclide] that holds, for every nuclide, the index binarySearch would return for any energy
+// inside that union interval (no nuclide grid point lies strictly inside a union interval, so the index is exact;
+// tests compare it bit for bit).  The union search itself is hashed on the IEEE bits of E (exponent + 9 mantissa
+// bits: monotone in E, no log), then walks at most the few points of one bucket.
+// Interpolation and summation are the reference's, in the reference's order (nuclides in material order), so the
+// macroscopic cross sections are bit-identical to the CPU restatement, not just within 1e-12.
+//
+// Layout: nuclide grids concatenated (f64); main data as the reference holds it, mainData(rows, N) with the rows of
+// one energy point contiguous (rows = 4 or 8), so the two points an interpolation needs are one contiguous
+// 64 B / 128 B segment; idxTab row-major by union interval (one coalesced row per lookup); materials in CSR.
+// Algorithmic bytes per lookup: total only: 36 B per nuclide + 20 B; full macro set:
+// 4 + 16 + 2*8*rows B per nuclide + 12 + 64 B.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/scone_b200.h"
+
+namespace sbce {
+
+constexpr int HASH_MBITS = 9;                     // mantissa bits in the bucket key
+
+struct CeDev {                                    // device pointers + sizes, passed by value
+  int nNuc, nMat, nUnion, nBuckets;
+  long long keyMin;
+  const double* grid; const double* data; const long long* gridOff; const long long* dataOff; const int* rows; const int* gridSize;
+  const int* matOff; const int* matNuc; const double* matDens;
+  const double* uGrid; const double* uMaj; const int* idxTab; const int* bucketStart;
+  double eMin, eMax;
+};
+
+__host__ __device__ inline long long hashKey(double E) {
+  long long b;
+#if defined(__CUDA_ARCH__)
+  b = __double_as_longlong(E);
+#else
+  memcpy(&b, &E, 8);
+#endif
+  return b >> (52 - HASH_MBITS);
+}
+
+// number of union points <= E (1 .. nUnion); 0 if E is outside [eMin, eMax].  Row (count - 1) of idxTab holds the
+// nuclide indices; min(count, nUnion - 1) is the floor index on the union grid itself (binarySearch returns N-1 at the top edge)
+__device__ __forceinline__ int unionSearch(const CeDev& c, double E) {
+  if (!(E >= c.eMin) || !(E <= c.eMax)) return 0;
+  long long b = hashKey(E) - c.keyMin;
+  b = b < 0 ? 0 : (b >= c.nBuckets ? c.nBuckets - 1 : b);
+  int u = __ldg(c.bucketStart + b);
+  const int hi = __ldg(c.bucketStart + b + 1);
+  while (u < hi && __ldg(c.uGrid + u) <= E) ++u;            // u = number of union points <= E
+  return u < 1 ? 1 : u;
+}
+
+// Sigma_t(material m, E) with E in union interval u: updateTotalMatXS (aceNeutronDatabase_class.f90:509-571)
+__device__ __forceinline__ double matTotal(const CeDev& c, int u, double e, int m) {
+  const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
+  const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
+  double tot = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const int nuc = __ldg(c.matNuc + k) - 1;
+    const int idx = __ldg(row + nuc);
+    const double* g = c.grid + __ldg(c.gridOff + nuc) + (idx - 1);
+    const double E_low = __ldg(g), E_top = __ldg(g + 1);
+    const double f = (e - E_low) / (E_top - E_low);
+    const int rows = __ldg(c.rows + nuc);
+    const double* d = c.data + __ldg(c.dataOff + nuc) + (size_t)(idx - 1) * rows;
+    tot = tot + __ldg(c.matDens + k) * (__ldg(d + rows) * f + (1.0 - f) * __ldg(d));
+  }
+  return tot * 1.0;
+}
+// initMajorant (:1545-1617): majorant(i) = max over materials of Sigma_t(E_i), nudged up by 1e-6
+__global__ void k_ce_majorant(const CeDev c, double* uMaj) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.nUnion; j += gridDim.x * blockDim.x) {
+    const double e = c.uGrid[j];
+    const int u = j + 1;
+    double maj = 0.0;
+    for (int m = 1; m <= c.nMat; ++m) maj = fmax(maj, matTotal(c, u, e, m));
+    uMaj[j] = maj * (1.0 + 1.0e-06);
+  }
+}
+
+// total / macro set (8 values) / majorant / per-nuclide index of nuclide `probeNuc`, whichever output pointers are given
+__global__ void __launch_bounds__(256) k_ce_lookup(const CeDev c, long long n, const double* __restrict__ E, const int* __restrict__ mat,
+                                                   double* __restrict__ total, double* __restrict__ macro, double* __restrict__ maj,
+                                                   int* __restrict__ probeIdx, int probeNuc, int* __restrict__ err) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double e = E[i];
+    const int u = unionSearch(c, e);
+    if (u == 0) { atomicMax(err, 1); continue; }               // "Failed to find energy"
+    if (maj) {                                                 // updateMajorantXS
+      const int uu = u > c.nUnion - 1 ? c.nUnion - 1 : u;
+      const double E_low = __ldg(c.uGrid + uu - 1), E_top = __ldg(c.uGrid + uu);
+      const double f = (e - E_low) / (E_top - E_low);
+      maj[i] = __ldg(c.uMaj + uu) * f + (1.0 - f) * __ldg(c.uMaj + uu - 1);
+    }
+    if (probeIdx) probeIdx[i] = __ldg(c.idxTab + (size_t)(u - 1) * c.nNuc + (probeNuc - 1));
+    if (!total && !macro) continue;
+    const int m = mat[i];
+    if (m < 1 || m > c.nMat) { atomicMax(err, 2); continue; }
+    const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
+    const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
+    double tot = 0.0;
+    double xs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = k0; k < k1; ++k) {
+      const int nuc = __ldg(c.matNuc + k) - 1;
+      const double dens = __ldg(c.matDens + k);
+      const int idx = __ldg(row + nuc);                        // what binarySearch(eGrid, E) returns for this nuclide
+      const double* g = c.grid + __ldg(c.gridOff + nuc) + (idx - 1);
+      const double E_low = __ldg(g), E_top = __ldg(g + 1);
+      const double f = (e - E_low) / (E_top - E_low);          // nuclide%search
+      const int rows = __ldg(c.rows + nuc);
+      const double* d = c.data + __ldg(c.dataOff + nuc) + (size_t)(idx - 1) * rows;
+      if (macro) {
+        if (rows == 8) {
+          const double2* p = (const double2*)d;                // 128 B: two energy points x 8 rows
+          double2 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3), b0 = __ldg(p + 4), b1 = __ldg(p + 5), b2 = __ldg(p + 6), b3 = __ldg(p + 7);
+          const double lo[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y}, hi8[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+#pragma unroll
+          for (int r = 0; r < 8; ++r) xs[r] = xs[r] + dens * (hi8[r] * f + (1.0 - f) * lo[r]);
+        } else {
+          const double2* p = (const double2*)d;                // 64 B: two energy points x 4 rows
+          double2 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+          const double lo[4] = {a0.x, a0.y, a1.x, a1.y}, hi4[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) xs[r] = xs[r] + dens * (hi4[r] * f + (1.0 - f) * lo[r]);
+#pragma unroll
+          for (int r = 4; r < 8; ++r) xs[r] = xs[r] + dens * 0.0;
+        }
+      }
+      if (total) tot = tot + dens * (__ldg(d + rows) * f + (1.0 - f) * __ldg(d));      // nuclide%totalXS
+    }
+    if (total) total[i] = tot * 1.0;
+    if (macro) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) macro[8 * i + r] = xs[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: build the union grid, the index table, the hash buckets; the majorant is filled by the kernel itself
+// ---------------------------------------------------------------------------------------------------------
+struct CeHost {
+  bool loaded = false;
+  CeDev dev{};
+  std::vector<void*> allocs;
+  std::vector<double> uGrid, uMaj;
+  int nNuc = 0, nMat = 0;
+  long long algBytesTotal(int nNucInMat) const { return 36LL * nNucInMat + 20; }
+};
+
+template <typename T>
+static T* ceUpload(CeHost& H, const std::vector<T>& v, std::string& err) {
+  T* p = nullptr;
+  size_t bytes = std::max<size_t>(sizeof(T) * v.size(), 16);
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { err = "cudaMalloc failed (CE tables)"; return nullptr; }
+  if (!v.empty() && cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy failed (CE tables)"; return nullptr; }
+  H.allocs.push_back(p);
+  return p;
+}
+static void ceFree(CeHost& H) { for (void* p : H.allocs) cudaFree(p); H.allocs.clear(); H.loaded = false; }
+
+static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err) {
+  ceFree(H);
+  if (f->n_nuc < 1 || f->n_mat < 1) { err = "sb_load_ce_data: invalid sizes"; return -1; }
+  const int nNuc = f->n_nuc, nMat = f->n_mat;
+  std::vector<long long> gridOff(nNuc), dataOff(nNuc); std::vector<int> rows(nNuc), gsize(nNuc);
+  long long go = 0, dofs = 0;
+  for (int n = 0; n < nNuc; ++n) {
+    if (f->grid_size[n] < 2 || (f->rows[n] != 4 && f->rows[n] != 8)) { err = "sb_load_ce_data: nuclide grid must have >= 2 points and 4 or 8 rows"; return -1; }
+    gridOff[n] = go; dataOff[n] = dofs; rows[n] = f->rows[n]; gsize[n] = f->grid_size[n];
+    go += f->grid_size[n]; dofs += (long long)f->grid_size[n] * f->rows[n];
+    dofs = (dofs + 3) & ~3LL;                                         // keep every nuclide's data 32-byte aligned for the vector loads
+  }
+  std::vector<double> grid(go), data(dofs, 0.0);
+  { long long gs = 0, ds = 0;
+    for (int n = 0; n < nNuc; ++n) {
+      std::copy(f->grid + gs, f->grid + gs + gsize[n], grid.begin() + gridOff[n]);
+      std::copy(f->data + ds, f->data + ds + (long long)gsize[n] * rows[n], data.begin() + dataOff[n]);
+      for (int i = 1; i < gsize[n]; ++i) if (grid[gridOff[n] + i] < grid[gridOff[n] + i - 1]) { err = "sb_load_ce_data: energy grid is not sorted"; return -1; }
+      gs += gsize[n]; ds += (long long)gsize[n] * rows[n];
+    } }
+  std::vector<int> matOff(f->mat_off, f->mat_off + nMat + 1), matNuc(f->mat_nuc, f->mat_nuc + f->mat_off[nMat]);
+  std::vector<double> matDens(f->mat_dens, f->mat_dens + f->mat_off[nMat]);
+  for (int v : matNuc) if (v < 1 || v > nNuc) { err = "sb_load_ce_data: material refers to an unknown nuclide"; return -1; }
+  // energy bounds of the database (aceNeutronDatabase_class.f90:1044-1051) and the unionised grid (initMajorant)
+  double eMin = grid[gridOff[0]], eMax = grid[gridOff[0] + gsize[0] - 1];
+  for (int n = 0; n < nNuc; ++n) { eMin = std::max(eMin, grid[gridOff[n]]); eMax = std::min(eMax, grid[gridOff[n] + gsize[n] - 1]); }
+  std::vector<char> used(nNuc, 0); for (int v : matNuc) used[v - 1] = 1;
+  std::vector<double> u;
+  for (int n = 0; n < nNuc; ++n) if (used[n]) for (int i = 0; i < gsize[n]; ++i) { double e = grid[gridOff[n] + i]; if (!(e < eMin || e > eMax)) u.push_back(e); }
+  std::sort(u.begin(), u.end()); u.erase(std::unique(u.begin(), u.end()), u.end());
+  const int nU = (int)u.size();
+  if (nU < 2) { err = "sb_load_ce_data: unionised grid has fewer than 2 points"; return -1; }
+  // idxTab[j][n] = min(N_n - 1, #{ i : grid_n(i) <= U_j }) : the value of binarySearch for any E in [U_j, U_{j+1})
+  // (last row: E == U_last exactly)
+  std::vector<int> idxTab((size_t)nU * nNuc, 1);
+  for (int n = 0; n < nNuc; ++n) {
+    const double* g = &grid[gridOff[n]]; int N = gsize[n], p = 0;
+    for (int j = 0; j < nU; ++j) {
+      while (p < N && g[p] <= u[j]) ++p;
+      idxTab[(size_t)j * nNuc + n] = std::max(1, std::min(N - 1, p));
+    }
+  }
+  // hash buckets on the IEEE bits
+  const long long keyMin = hashKey(u.front()), keyMax = hashKey(u.back());
+  const int nB = (int)(keyMax - keyMin + 1);
+  std::vector<int> bucketStart(nB + 1, 0);
+  { int p = 0; for (int b = 0; b <= nB; ++b) { while (p < nU && hashKey(u[p]) - keyMin < b) ++p; bucketStart[b] = p; } }
+  CeDev& d = H.dev;
+  d.nNuc = nNuc; d.nMat = nMat; d.nUnion = nU; d.nBuckets = nB; d.keyMin = keyMin; d.eMin = u.front(); d.eMax = u.back();
+  H.uGrid = u; H.uMaj.assign(nU, 0.0);
+  d.grid = ceUpload(H, grid, err); d.data = ceUpload(H, data, err); d.gridOff = ceUpload(H, gridOff, err); d.dataOff = ceUpload(H, dataOff, err);
+  d.rows = ceUpload(H, rows, err); d.gridSize = ceUpload(H, gsize, err);
+  d.matOff = ceUpload(H, matOff, err); d.matNuc = ceUpload(H, matNuc, err); d.matDens = ceUpload(H, matDens, err);
+  d.uGrid = ceUpload(H, u, err); d.uMaj = ceUpload(H, H.uMaj, err); d.idxTab = ceUpload(H, idxTab, err); d.bucketStart = ceUpload(H, bucketStart, err);
+  if (!err.empty()) return -1;
+  H.nNuc = nNuc; H.nMat = nMat; H.loaded = true;
+  return 0;
+}
+
+}  // namespace sbce

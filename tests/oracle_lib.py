@@ -18,7 +18,7 @@ c_ip = C.POINTER(C.c_int)
 
 
 def build():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("capi.cpp", "physics.hpp", "geom.hpp", "mgdata.hpp", "rng.hpp")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("capi.cpp", "cedata.hpp", "physics.hpp", "geom.hpp", "mgdata.hpp", "rng.hpp")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "all"])
@@ -114,6 +114,18 @@ def load():
         "orc_eigen_tally": (i32, [vp, i32, c_dp, c_dp, c_ip]),
         "orc_eigen_stats": (i32, [vp, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     }
+    sig.update({
+        "orc_ce_nuclide_from_ace": (vp, [C.c_char_p, i32]), "orc_ce_nuclide_from_arrays": (vp, [i32, i32, c_dp, c_dp]),
+        "orc_ce_nuclide_free": (None, [vp]), "orc_ce_nuclide_info": (i32, [vp, c_ip, c_ip, c_dp, c_dp]),
+        "orc_ce_nuclide_data": (i32, [vp, c_dp, c_dp]), "orc_ce_nuclide_search": (i32, [vp, dbl, c_ip, c_dp]),
+        "orc_ce_nuclide_micro": (i32, [vp, dbl, c_dp]), "orc_ce_nuclide_total": (dbl, [vp, dbl]),
+        "orc_ce_nuclide_nubar": (i32, [vp, dbl, c_dp, c_dp, c_dp]),
+        "orc_ce_db_new": (vp, []), "orc_ce_db_free": (None, [vp]), "orc_ce_db_add_nuclide": (i32, [vp, vp]),
+        "orc_ce_db_add_material": (i32, [vp, i32, c_ip, c_dp]), "orc_ce_db_finalise": (i32, [vp]),
+        "orc_ce_db_union": (i32, [vp, c_dp, c_dp]), "orc_ce_db_total_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]),
+        "orc_ce_db_macro_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]), "orc_ce_db_majorant_n": (i32, [vp, C.c_long, c_dp, c_dp]),
+        "orc_ce_db_index_n": (i32, [vp, i32, C.c_long, c_dp, c_ip]),
+    })
     for name, (res, args) in sig.items():
         f = getattr(L, name)
         f.restype = res
