@@ -60,7 +60,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
@@ -95,6 +95,71 @@ def oracle_rate(deck, pop, n_inactive, seconds, threads, tracking="DT"):
     orc.orc_eigen_stats(e, C.byref(seg1), C.byref(c1), C.byref(h1))
     orc.orc_eigen_free(e)
     return dict(nps=pop * n / dt, sps=(seg1.value - seg0.value) / dt, cycles=n, seconds=dt, k=k)
+
+
+def ce_nuclides_and_material(n_nuc=20):
+    """BASELINE configs[4]-style stress: ~20 nuclides per fuel material built from the golden nuclide tables."""
+    import numpy as np
+    from scone_b200.ce import synthetic_nuclides
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ce_nuclides.npz"))
+    base = [(g["grid_" + n], g["data_" + n]) for n in ("1001", "92233", "52126", "91231", "91232")]
+    nuclides = synthetic_nuclides(base, n_nuc, seed=7)
+    rng = np.random.default_rng(1)
+    material = [(k + 1, float(rng.uniform(1e-5, 5e-2))) for k in range(n_nuc)]
+    return nuclides, material
+
+
+def ce_lookup_bench(device, n_lookups, cpu_seconds, with_cpu):
+    """The CE XS-lookup kernel on its own: Sigma_t of a 20-nuclide material for n_lookups particles of random energy
+    (unsorted = worst case for the gathers). Returns the roofline object of that kernel."""
+    import numpy as np
+    import torch
+    from scone_b200.ce import CeDatabase
+    nuclides, material = ce_nuclides_and_material(20)
+    eng = CeDatabase(nuclides, [material], device=device)
+    rng = np.random.default_rng(3)
+    E_h = np.exp(rng.uniform(np.log(1e-11), np.log(20.0), n_lookups))
+    E = torch.from_numpy(E_h).to("cuda:%d" % device)
+    mat = torch.ones(n_lookups, dtype=torch.int32, device=E.device)
+    tot = torch.zeros(n_lookups, dtype=torch.float64, device=E.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=E.device)
+    ms = []
+    for it in range(8):
+        flush.zero_(); torch.cuda.synchronize()
+        ms.append(eng.lookup_device(E.data_ptr(), mat.data_ptr(), tot.data_ptr(), 0, 0, n=n_lookups))
+    k_ms = sum(ms[3:]) / len(ms[3:])
+    alg = (36 * len(material) + 20) * n_lookups                      # SURVEY.md section 8(d): 36 B per nuclide + 20 B per lookup
+    # end to end through the host-buffer call (pinned memory not required by the ABI; numpy arrays here)
+    t0 = time.perf_counter(); eng.lookup(E_h, np.ones(n_lookups, np.int32), total=True); t_e2e = time.perf_counter() - t0
+    peak, peak_src = measured_peak()
+    out = {"kernel": "k_ce_lookup", "workload": "Sigma_t of a 20-nuclide material, %d lookups, random (unsorted) energies in [1e-11, 20] MeV, "
+                     "tables: 20 nuclides from the reference's 5 bundled ACE nuclides by seeded energy shifts" % n_lookups,
+           "bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+           "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg,
+           "lookups_per_s": n_lookups / (k_ms * 1e-3), "e2e_lookups_per_s_host_buffers": n_lookups / t_e2e,
+           "l2": "flushed before every timed launch (256 MiB memset); the 4.5 MB of tables are re-read from HBM/L2 by the gathers",
+           "parity": "grid indices and cross sections bit-identical to the CPU restatement (tests/test_gpu_ce.py)"}
+    try:
+        out["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_ce_lookup_dram_bytes_per_launch")
+    except Exception:
+        pass
+    if with_cpu:
+        from tests import ce_util
+        from tests import oracle_lib as ol
+        orc = ol.load()
+        db, _ = ce_util.oracle_db(orc, nuclides, [material])
+        m = min(n_lookups, 2_000_000)
+        Ec = np.ascontiguousarray(E_h[:m]); mc = np.ones(m, np.int32); oc = np.zeros(m)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < cpu_seconds:
+            orc.orc_ce_db_total_n(db, m, ol.dp(Ec), ol.ip(mc), ol.dp(oc)); reps += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m * reps / dt, "unit": "lookups/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "%d x %d lookups in %.1f s (oracle: binary search per nuclide as aceNeutronNuclide%%search, OpenMP over particles)" % (reps, m, dt)}
+        assert np.array_equal(oc, tot[:m].cpu().numpy()), "CE lookup differs from the oracle"
+        orc.orc_ce_db_free(db)
+    eng.close()
+    return out
 
 
 def run_reference(args, rank, world):
@@ -153,6 +218,9 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the large-population and CE-lookup measurements")
+    ap.add_argument("--large-pop", type=int, default=1000000)
+    ap.add_argument("--ce-lookups", type=int, default=10000000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -173,6 +241,7 @@ def main():
     total_pop = pop * world
     ov = "pop %d; inactive %d; active %d; seed 20261017; transportOperator { type transportOperator%s; }" % (
         total_pop, args.inactive, args.warmup + 2 * args.steps + 4, args.tracking)
+    sampler = ClockSampler(local); sampler.start()
     pp = scone_b200.EigenPhysicsPackage(deck, ov, device=local, rank=rank, n_ranks=world)
     comm = scone_b200.distributed.TorchComm(device=torch.device("cuda", local)) if world > 1 else None
     L = pp.L
@@ -205,7 +274,6 @@ def main():
     flush = not args.no_l2_flush
     FLUSH_BYTES = 256 << 20
     # ---- device-resident arm: K active cycles, CUDA events on the engine stream --------------------------
-    sampler = ClockSampler(local); sampler.start()
     L.sb_profile_enable(eng, 1)
     launches0 = pp.launch_count()
     barrier()
@@ -225,7 +293,6 @@ def main():
     msk, nl, segp, scp = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
     L.sb_profile_read(eng, C.byref(msk), C.byref(nl), C.byref(segp), C.byref(scp))
     L.sb_profile_enable(eng, 0)
-    sampler.stop_flag = True; sampler.join(timeout=2)
     ms_max = maxreduce(ms_total)
     value = total_pop * args.steps / (ms_max * 1e-3)
     seg_all = sumreduce(float(seg))
@@ -242,6 +309,7 @@ def main():
     t_e2e = maxreduce(time.perf_counter() - t0)
     h2d, d2h = pp.host_bytes(True)
     e2e_val = total_pop * args.steps / t_e2e
+    sampler.stop_flag = True; sampler.join(timeout=2)
 
     # ---- roofline of the dominant kernel (k_histories) -----------------------------------------------------
     peak, peak_src = measured_peak()
@@ -257,6 +325,28 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,
                 "note": "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)"}
+
+    # ---- extras (N = 1 only): the same deck at a GPU-sized population, and the CE XS-lookup kernel ----------------
+    large = None; ce = None
+    if world == 1 and not args.no_extras:
+        pp.close()
+        ov2 = "pop %d; inactive 6; active 100; seed 20261017; transportOperator { type transportOperator%s; }" % (args.large_pop, args.tracking)
+        pl = scone_b200.EigenPhysicsPackage(deck, ov2, device=local)
+        pl.generateInitialState(); pl.cycles(False, 6)
+        for _ in range(3):
+            pl.cycle(True)
+        tms = 0.0; segl = 0; nst = 8
+        for _ in range(nst):
+            L.sb_flush_l2(pl.engine, FLUSH_BYTES); L.sb_timer_begin(pl.engine)
+            rl = pl.cycle(True)
+            L.sb_timer_end(pl.engine, C.byref(ms)); tms += ms.value; segl += rl.n_segments
+        large = {"pop_per_cycle": args.large_pop, "value": args.large_pop * nst / (tms * 1e-3), "unit": "neutrons/s", "ms_per_step": tms / nst,
+                 "segments_per_s": segl / (tms * 1e-3), "keff": pl.k, "steps": nst,
+                 "note": "same deck and engine at a population that fills the GPU (BASELINE configs[3] runs 1.25e6 histories per GPU); "
+                         "at 1e5 histories per cycle the kernel time is the critical path of the longest history"}
+        pl.close()
+        ce = ce_lookup_bench(local, args.ce_lookups, min(args.cpu_seconds, 6.0), not args.no_cpu_baseline)
+        pp = None
 
     line = None
     if rank == 0:
@@ -285,7 +375,12 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    pp.close()
+        if large is not None:
+            line["large_population"] = large
+        if ce is not None:
+            line["roofline_ce_lookup"] = ce
+    if pp is not None:
+        pp.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
