@@ -661,6 +661,28 @@ static int buildBlob(sb_engine* h) {
           else cl[c].mapOff[m] = 0;
         }
       L.nClerk[ph] = (int)cl.size();
+      // can any clerk of this phase score a non-zero value in (mat, G)?  (response values are functions of the XS row only)
+      std::vector<unsigned char> mask((size_t)h->nMat * h->nG + 16, 0);
+      for (int m = 0; m <= h->nMat; ++m)
+        for (int g = 0; g < (m < h->nMat ? h->nG : 1); ++g) {
+          bool any = false;
+          for (const DClerk& k : cl)
+            for (int i = 0; i < k.nResp; ++i) {
+              if (k.respMT[i] == 0) any = true;
+              else if (m < h->nMat) {
+                const double* x = &h->xs[((size_t)m * h->nG + g) * 6]; const bool fis = h->fissile[m] != 0;
+                double r = 0.0;
+                switch (k.respMT[i]) {                       // neutronMacroXSs%get (neutronXsPackages_class.f90:143-190)
+                  case -1: r = x[0]; break; case -2: r = x[2]; break; case -22: r = x[1] + (fis ? x[3] : 0.0) + x[2]; break;
+                  case -4: case -20: r = x[1]; break; case -6: r = fis ? x[3] : 0.0; break; case -7: case -9: r = fis ? x[4] : 0.0; break;
+                  case -80: r = fis ? x[5] : 0.0; break; case -21: r = (fis ? x[3] : 0.0) + x[2]; break; default: r = 0.0;
+                }
+                if (r != 0.0) any = true;
+              }
+            }
+          mask[m < h->nMat ? (size_t)m * h->nG + g : (size_t)h->nMat * h->nG] = any ? 1 : 0;
+        }
+      L.oScoreMask[ph] = put(hb, mask);
       if (cl.empty()) cl.push_back(DClerk{});
       L.oClerk[ph] = put(hb, cl);
     }
@@ -933,7 +955,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   h->launches++;
 
   HistArgs a{};
-  a.L = h->hot; a.L.oClerk[0] = h->hot.oClerk[phase]; a.L.nClerk[0] = h->hot.nClerk[phase];
+  a.L = h->hot; a.L.oClerk[0] = h->hot.oClerk[phase]; a.L.nClerk[0] = h->hot.nClerk[phase]; a.L.oScoreMask[0] = h->hot.oScoreMask[phase];
   a.hot = h->dHot; a.blob = h->dBlob; a.seedTab = h->dSeedTab;
   a.n = n; a.in = in; a.out = raw; a.cap = h->cap;
   a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat;
@@ -946,7 +968,22 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
-  if (h->opt.tracking != SB_TRACK_DT) {                       // surface / hybrid tracking: coordList-carrying kernel
+  bool useTrack = h->opt.tracking != SB_TRACK_DT;
+  if (h->opt.tracking == SB_TRACK_HT && !getenv("SB_FORCE_TRACK_KERNEL")) {
+    // transportOperatorHT picks delta tracking when Sigma_t / Sigma_maj > 1 - cutoff (transportOperatorHT_class.f90:63-78). If that
+    // holds for every (material, group) of the model -- and nothing is void -- the selector is a constant and the flights
+    // are exactly deltaTracking's: run the delta-tracking kernel.
+    bool always = true;
+    for (int i = 0; i < h->g.n_graph; ++i) if (h->gi_gidx[i] == SB_VOID_MAT) always = false;
+    for (int m = 0; m < h->nMat && always; ++m)
+      for (int g = 0; g < h->nG; ++g) {
+        double majorant_inv = 1.0 / std::fmax(h->majorant[g] + 0.0, h->collisionXS);
+        double ratio = (h->xs[((size_t)m * h->nG + g) * 6] + 0.0) * majorant_inv;
+        if (!(ratio > (1.0 - h->opt.ht_cutoff))) { always = false; break; }
+      }
+    if (always) useTrack = false;
+  }
+  if (useTrack) {                                             // surface / hybrid tracking: coordList-carrying kernel
     sbt::TrackArgs t{};
     t.M = h->M; t.blob = h->dBlob; t.useSmem = h->trackSmem; t.seedTab = h->dSeedTab;
     t.n = n; t.in = in; t.out = raw; t.cap = h->cap;

@@ -41,6 +41,7 @@ struct HotLayout {
   int bytes;
   int oUni, oGraph, oAuxD, oAuxI, oXs, oP0, oProd, oP1, oChi, oFissile, oMajT, oMajInv;
   int oClerk[2], nClerk[2];
+  int oScoreMask[2];                     // per phase: [nMat*nG + 1] bytes, 1 if any clerk can score a non-zero in (mat, G); last = void
   int nG, nMat, isP1, rootIdx, borderS, borderIsBox;
 };
 
@@ -79,10 +80,10 @@ struct HistArgs {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double rngGet(uint64_t& s) {
   s = (RNG_G * s + 1ULL) & RNG_MASK;
-  double hi = __hiloint2double(0x45300000, (int)(s >> 32));              // 2^84 + hi*2^32
-  double lo = __hiloint2double(0x43300000, (int)(s & 0xffffffffu));      // 2^52 + lo
-  double x = (hi - 19342813118337666422669312.0) + lo;                   // hi - (2^84 + 2^52), exact; + lo rounds once
-  return x * (1.0 / 9223372036854775808.0);
+  // the same with every term scaled by 2^-63 (exact): (2^21 + hi*2^-31) - (2^21 + 2^-11) + (2^-11 + lo*2^-63)
+  double hi = __hiloint2double(0x41400000, (int)(s >> 32));
+  double lo = __hiloint2double(0x3f400000, (int)(s & 0xffffffffu));
+  return (hi - 2097152.00048828125) + lo;                                // exact difference; the sum rounds once = RN(s) * 2^-63
 }
 __device__ __forceinline__ uint64_t rngSeed(const ulonglong2* tab, uint64_t s, unsigned n) {
 #pragma unroll
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
   const double* const majInvT = (const double*)(hb + a.L.oMajInv);
   const DClerk* const clerks = (const DClerk*)(hb + a.L.oClerk[0]);     // phase offset applied by the host (oClerk[0] = this launch)
   const int nClerk = a.L.nClerk[0];
+  const unsigned char* const scoreMask = (const unsigned char*)(hb + a.L.oScoreMask[0]);
   const int nG = a.L.nG;
   const bool active = a.phase == 1;
 
@@ -326,8 +328,10 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
           if (rngGet(rng) < sigmaT * majInv) { realColl = true; virt = false; }
         }
         // ---- tallyAdmin%reportInColl: collisionClerks, then keffImplicitClerk (active cycles) ----
+        // (skipped when no clerk of this phase can score a non-zero value in this material and group)
+        const int nC = scoreMask[isVoid ? a.L.nMat * nG : (mat - 1) * nG + (G - 1)] ? nClerk : 0;
 #pragma unroll 1
-        for (int c = 0; c < nClerk; ++c) {
+        for (int c = 0; c < nC; ++c) {
           const DClerk& k = clerks[c];
           if (!k.handleVirtual && (virt || isVoid)) continue;
           const double f = k.handleVirtual ? flux : w / (x[XS_TOTAL] + 0.0);
