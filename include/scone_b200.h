@@ -168,13 +168,20 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
  * rng_state = pRNG state after the stride(totalPop+1) of the cycle.                            */
 int sb_resample(sb_engine* h, int tot_pop, uint64_t rng_state);
 
+/* sb_run_cycle followed by sb_resample with ONE host synchronisation (single rank): nothing the host decides lies between
+ * reportCycleEnd and normSize_Repr (eigenPhysicsPackage_class.f90:254-275) except the deterministic stride of pRNG.
+ * rng_state_resample = pRNG state after stride(totalPop + 1).                                                    */
+int sb_run_cycle_resample(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop,
+                          uint64_t rng_state_resample, sb_cycle_result* res);
+
 /* ---- the cycle split for several ranks (one engine = one GPU = one rank) ---------------------
  * Ranks own contiguous shares of the bank (getWorkshare/getOffset, SharedModules/mpi_func.f90:133-159) and
  * exchange once per cycle what SCONE exchanges over MPI; the transport between ranks (NCCL, CUDA-aware MPI,
  * peer copies) is the caller's, the engine only exposes device buffers:
  *   sb_cycle_begin : transport + brood order; writes this rank's 6 score sums {implicit production, implicit
- *                    absorption, analog leakage, scatter production, start weight, end weight} to dev_sums
- *                    (device pointer, 6 doubles) -> caller all-reduces them (scoreMemory%reduceBins with
+ *                    absorption, analog leakage, scatter production, start weight, end weight}, its fission-bank size
+ *                    (as a double) and a zero to dev_sums (device pointer, 8 doubles) -> caller all-reduces the sums /
+ *                    all-gathers the 8 doubles (scoreMemory%reduceBins with
  *                    mpiSync, scoreMemory_class.f90:404-431; mpi_bcast of k, eigenPhysicsPackage_class.f90:302)
  *   sb_cycle_end   : k estimators and closeCycle from the reduced sums (identical on every rank)
  *   sb_resample_ranked : normSize_Repr with the bank sizes of all ranks (replaces mpi_gather + 3 mpi_bcast,
@@ -185,6 +192,10 @@ int sb_resample(sb_engine* h, int tot_pop, uint64_t rng_state);
  *                    the bank as [add_front] + bank[drop_front : n - drop_back] + [add_back]                */
 int sb_cycle_begin(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, double* dev_sums, int32_t* n_sites);
 int sb_cycle_end(sb_engine* h, const double* dev_sums, sb_cycle_result* res);
+/* sb_cycle_end + sb_resample_ranked with one synchronisation; host_sums = the 6 reduced sums in HOST memory; new_sizes[n_ranks] =
+ * bank size of every rank after normalisation (each rank computes all of them: no second all-gather)                */
+int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_pop, uint64_t master_rng_state, int n_ranks, int rank,
+                                 const int32_t* pop_sizes, int32_t* new_sizes, sb_cycle_result* res);
 int sb_resample_ranked(sb_engine* h, int tot_pop, uint64_t master_rng_state, int n_ranks, int rank, const int32_t* pop_sizes, int32_t* new_local_pop);
 size_t sb_site_buffer_bytes(int k);
 int sb_bank_export(sb_engine* h, int k_front, void* dev_buf_front, int k_back, void* dev_buf_back);

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(int n, const double
 // { implicit production, implicit absorption, analog leakage, scatter production, start weight, end weight }
 // (the bins of keffImplicitClerk / keffAnalogClerk that are reduced across ranks every cycle: mpiSync = 1,
 //  eigenPhysicsPackage_class.f90:605-640, scoreMemory_class.f90:404-431)
-__global__ void k_sum_partials(const RedOut* partial, double* ksum) {
+__global__ void k_sum_partials(const RedOut* partial, double* ksum, const CycleDev* cd, int cap) {
   const int lane = threadIdx.x;
   double v[6] = {0, 0, 0, 0, 0, 0};
   for (int i = lane; i < RED_BLOCKS; i += 32) {
@@ -184,6 +184,7 @@ __global__ void k_sum_partials(const RedOut* partial, double* ksum) {
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) ksum[k] = v[k];
+    ksum[6] = (double)min(cd->nSites, cap); ksum[7] = 0.0;      // the bank size rides along with the sums (one all-gather per cycle)
   }
 }
 // tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
@@ -366,6 +367,29 @@ __global__ void k_norm_count(const int* flag, const int* offs, const NormDev* nd
   if (nd->check && nNew != nd->totPop) atomicMax(&cdw->error, SB_ERR_NORM);      // "Normalisation failed!" (:596)
 }
 
+// number of flagged sites (kept for excess > 0, duplicated for excess < 0) in every rank's slice of the global stream:
+// every rank can then compute every rank's new bank size itself (replaces the mpi_allgather of :593)
+struct RankOffs { int n; int off[65]; };
+__global__ void k_norm_rank_counts(const unsigned long long* rn, const CycleDev* cd, const NormDev* nd, const RankOffs ro, int* counts) {
+  __shared__ int sc[64];
+  if (threadIdx.x < 64) sc[threadIdx.x] = 0;
+  __syncthreads();
+  const int n = nd->nGlobal;
+  const int excess = n - nd->totPop;
+  const int nDup = (excess < 0) ? (int)(((long long)(-excess)) % n) : 0;
+  const double thr = cd->thrReal;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double x = (double)(long long)rn[j] * (1.0 / 9223372036854775808.0);
+    int f;
+    if (excess > 0) f = (x > thr) ? 1 : 0;
+    else if (excess < 0) f = (nDup != 0 && x <= thr) ? 1 : 0;
+    else f = 1;
+    if (f) { int r = 0; while (r + 1 < ro.n && j >= ro.off[r + 1]) ++r; atomicAdd(&sc[r], 1); }
+  }
+  __syncthreads();
+  if (threadIdx.x < ro.n && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
+}
+
 // loadBalancing (particleDungeon_class.f90:607-698): pack sites of the ends of the bank / rebuild the bank as
 // [received from below] + kept middle + [received from above]. Packed site layout: 7 f64 arrays of k, then k i32 (G)
 __global__ void k_bank_pack_range(Bank b, int first, int k, double* buf) {
@@ -517,6 +541,7 @@ struct sb_engine {
   double bounds[6] = {0, 0, 0, 0, 0, 0};
   double kNormNext = 1.0;   // nextCycle%k_eff of the dungeon that will receive the sites (keffAnalogClerk k_norm)
   bool sortedReady = false; int phaseOpen = -1; double kCumLast = 1.0;
+  int* dRankCounts = nullptr; int* hRankCounts = nullptr;
   double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
   // measurement
@@ -763,7 +788,7 @@ void sb_destroy(sb_engine* h) {
   for (int i = 0; i < 3; ++i) freeBank(h->bank[i]);
   cudaFree(h->dNsites); cudaFree(h->dOffsets); cudaFree(h->dTile); cudaFree(h->dFlag); cudaFree(h->dFlagOff);
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
-  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
+  cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
   cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1007,14 +1032,14 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   k_sort_sites<<<gridFor(h, 2LL * n, 256), 256, 0, st>>>(raw, sorted, h->dOffsets, h->dCd, h->cap);
   // deterministic reductions of this rank's scores
   k_reduce_hist<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, h->dHProd, h->dHAbs, h->dHLeak, h->dHScat, in.w, sorted.w, h->dCd, h->cap, h->dPartial);
-  k_sum_partials<<<1, 32, 0, st>>>(h->dPartial, h->dKsum);
+  k_sum_partials<<<1, 32, 0, st>>>(h->dPartial, h->dKsum, h->dCd, h->cap);
   h->launches += 6;
   h->phaseOpen = phase;
   return 0;
 }
 
 // cycle close from (possibly rank-reduced) score sums: k estimators, normalisation, scoreMemory%closeCycle
-static int cycleClose(sb_engine* h, const double* dKsum, sb_cycle_result* res) {
+static int cycleCloseEnqueue(sb_engine* h, const double* dKsum) {
   const int phase = h->phaseOpen;
   if (phase < 0) { h->err = "sb_cycle_end: no cycle is open"; return -1; }
   CUDA_OK(cudaSetDevice(h->device));
@@ -1024,6 +1049,11 @@ static int cycleClose(sb_engine* h, const double* dKsum, sb_cycle_result* res) {
   k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
   h->launches += 2;
   h->batchN[phase] += 1;
+  return 0;
+}
+// read the cycle record back (one synchronisation) and fill the result
+static int cycleFinish(sb_engine* h, sb_cycle_result* res) {
+  cudaStream_t st = h->stream;
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
@@ -1042,6 +1072,10 @@ static int cycleClose(sb_engine* h, const double* dKsum, sb_cycle_result* res) {
   h->kCumLast = c.kCum;
   return checkDeviceError(h, c.error);
 }
+static int cycleClose(sb_engine* h, const double* dKsum, sb_cycle_result* res) {
+  if (cycleCloseEnqueue(h, dKsum)) return -1;
+  return cycleFinish(h, res);
+}
 
 int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, sb_cycle_result* res) {
   if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
@@ -1050,7 +1084,7 @@ int sb_run_cycle(sb_engine* h, uint64_t rng_state, int history_offset, double k_
 
 int sb_cycle_begin(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, double* dev_sums, int32_t* n_sites) {
   if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
-  if (dev_sums) CUDA_OK(cudaMemcpyAsync(dev_sums, h->dKsum, 6 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (dev_sums) CUDA_OK(cudaMemcpyAsync(dev_sums, h->dKsum, 8 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
@@ -1061,12 +1095,13 @@ int sb_cycle_end(sb_engine* h, const double* dev_sums, sb_cycle_result* res) {
   return cycleClose(h, dev_sums ? dev_sums : h->dKsum, res);
 }
 
-static int resampleImpl(sb_engine* h, int totPop, uint64_t rng_state, int nGlobal, int offLocal, int check, int32_t* newLocal) {
-  if (!h->sortedReady) { h->err = "sb_resample: no cycle has been run"; return -1; }
+// normSize_Repr kernels. nSitesHost: the bank size if the host knows it, -1 if the cycle record has not been read back
+// yet (fused cycle): launch sizes then come from the bank capacity, the kernels read the true size on the device.
+static int resampleEnqueue(sb_engine* h, int totPop, uint64_t rng_state, int nGlobal, int offLocal, int check, int nSitesHost) {
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   Bank& sorted = h->bank[(h->cur + 2) % 3]; Bank& dst = h->bank[(h->cur + 1) % 3];
-  const int nSites = std::min(h->hCd->nSites, h->cap);
+  const int nSites = nSitesHost >= 0 ? nSitesHost : h->cap;
   const int nG = nGlobal < 0 ? nSites : nGlobal;
   if (nG <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
   unsigned long long* rn = h->dRn;
@@ -1090,9 +1125,14 @@ static int resampleImpl(sb_engine* h, int totPop, uint64_t rng_state, int nGloba
   k_norm_scatter<<<gl, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
   k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dNd, h->dCd);
   h->launches += 13;
-  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int resampleFinish(sb_engine* h, int32_t* newLocal, bool readBack) {
+  if (readBack) {
+    CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+  }
   if (checkDeviceError(h, h->hCd->error)) return -1;
   h->cur = (h->cur + 1) % 3;
   h->nCur = h->hCd->nNew;
@@ -1100,6 +1140,23 @@ static int resampleImpl(sb_engine* h, int totPop, uint64_t rng_state, int nGloba
   h->kNormNext = h->kCumLast;       // self%nextCycle%k_eff = k_new (eigenPhysicsPackage_class.f90:306)
   h->sortedReady = false;
   return 0;
+}
+static int resampleImpl(sb_engine* h, int totPop, uint64_t rng_state, int nGlobal, int offLocal, int check, int32_t* newLocal) {
+  if (!h->sortedReady) { h->err = "sb_resample: no cycle has been run"; return -1; }
+  if (resampleEnqueue(h, totPop, rng_state, nGlobal, offLocal, check, std::min(h->hCd->nSites, h->cap))) return -1;
+  return resampleFinish(h, newLocal, true);
+}
+
+// the whole cycle with one host synchronisation: transport, cycle close, normSize_Repr (single rank).
+// rng_state_resample = pRNG state after the stride(totalPop + 1) that follows the history loop.
+int sb_run_cycle_resample(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop, uint64_t rng_state_resample, sb_cycle_result* res) {
+  if (2 * tot_pop > h->cap && h->cap > 0) { h->err = "sb_resample: target population exceeds the bank capacity"; return -1; }
+  if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
+  if (cycleCloseEnqueue(h, h->dKsum)) return -1;
+  if (resampleEnqueue(h, tot_pop, rng_state_resample, -1, 0, 1, -1)) return -1;
+  if (cycleFinish(h, res)) return -1;                      // one synchronisation; the record now holds nNew as well
+  if (h->hCd->nSites <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
+  return resampleFinish(h, nullptr, false);
 }
 
 int sb_resample(sb_engine* h, int totPop, uint64_t rng_state) {
@@ -1114,6 +1171,36 @@ int sb_resample_ranked(sb_engine* h, int tot_pop, uint64_t master_rng_state, int
   if (tot > 2000000000LL) { h->err = "sb_resample_ranked: more than 2^31 sites"; return -1; }
   if (pop_sizes[rank] != std::min(h->hCd->nSites, h->cap)) { h->err = "sb_resample_ranked: pop_sizes[rank] is not this rank's bank size"; return -1; }
   return resampleImpl(h, tot_pop, master_rng_state, (int)tot, (int)off, 0, new_local_pop);
+}
+
+// sb_cycle_end + sb_resample_ranked with one synchronisation. host_sums: the 6 score sums reduced over ranks (host memory);
+// new_sizes[n_ranks]: every rank's bank size after normSize_Repr (computed here, no second all-gather needed)
+int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_pop, uint64_t master_rng_state, int n_ranks, int rank,
+                                 const int32_t* pop_sizes, int32_t* new_sizes, sb_cycle_result* res) {
+  if (n_ranks < 1 || n_ranks > 64 || rank < 0 || rank >= n_ranks || !pop_sizes) { h->err = "sb_cycle_end_resample_ranked: invalid rank arguments (at most 64 ranks)"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  long long tot = 0, off = 0; RankOffs ro{}; ro.n = n_ranks;
+  for (int i = 0; i < n_ranks; ++i) { ro.off[i] = (int)tot; if (i < rank) off += pop_sizes[i]; tot += pop_sizes[i]; }
+  ro.off[n_ranks] = (int)tot;
+  if (tot > 2000000000LL || tot <= 0) { h->err = "sb_cycle_end_resample_ranked: invalid total number of sites"; return -1; }
+  if (!h->dRankCounts) { CUDA_OK(cudaMalloc(&h->dRankCounts, 64 * sizeof(int))); CUDA_OK(cudaMallocHost(&h->hRankCounts, 64 * sizeof(int))); }
+  cudaStream_t st = h->stream;
+  CUDA_OK(cudaMemcpyAsync(h->dKsum, host_sums, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (cycleCloseEnqueue(h, h->dKsum)) return -1;
+  if (resampleEnqueue(h, tot_pop, master_rng_state, (int)tot, (int)off, 0, pop_sizes[rank])) return -1;
+  CUDA_OK(cudaMemsetAsync(h->dRankCounts, 0, 64 * sizeof(int), st));
+  k_norm_rank_counts<<<gridFor(h, tot, 256), 256, 0, st>>>(h->dRnGlobal, h->dCd, h->dNd, ro, h->dRankCounts);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(h->hRankCounts, h->dRankCounts, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (cycleFinish(h, res)) return -1;
+  if (pop_sizes[rank] != std::min(h->hCd->nSites, h->cap)) { h->err = "sb_cycle_end_resample_ranked: pop_sizes[rank] is not this rank's bank size"; return -1; }
+  if (resampleFinish(h, nullptr, false)) return -1;
+  const long long excess = tot - tot_pop;
+  const long long nCopies = excess < 0 ? (-excess) / tot : 0;
+  for (int i = 0; i < n_ranks; ++i)
+    new_sizes[i] = excess > 0 ? h->hRankCounts[i] : (excess == 0 ? pop_sizes[i] : (int)(pop_sizes[i] * (nCopies + 1) + h->hRankCounts[i]));
+  if (new_sizes[rank] != h->nCur) { h->err = "sb_cycle_end_resample_ranked: inconsistent bank size after normalisation"; return -1; }
+  return 0;
 }
 
 // loadBalancing (particleDungeon_class.f90:607-698): sites leave from / arrive at the two ends of the bank

@@ -109,9 +109,10 @@ struct eigenPhysicsPackage {
   int cycle(int active, double& k_new) {
     if (!eng) return fail("no engine: this handle was created without a device");
     auto t0 = std::chrono::steady_clock::now();
-    if (sb_run_cycle(eng, pRNG, 0, k_new, active, &last)) return engFail();
+    if (nRanks > 1) return fail("this package owns a share of the bank: use the cycleBegin / cycleEnd / resampleRanked steps");
+    const uint64_t rng0 = pRNG;
     stride(totalPop + 1);
-    if (sb_resample(eng, pop, pRNG)) return engFail();
+    if (sb_run_cycle_resample(eng, rng0, 0, k_new, active, pop, pRNG, &last)) return engFail();      // one synchronisation per cycle
     stride(1);
     k_new = last.k_cum;
     keff_0 = k_new;
@@ -145,15 +146,26 @@ struct eigenPhysicsPackage {
     return 0;
   }
 
+  // steps 2 + 3 with one synchronisation (host-side reduced sums, every rank's new size computed locally)
+  int cycleEndResampleRanked(int active, const double* hostSums, const int32_t* popSizes, int32_t* newSizes, double& k_new) {
+    stride(totalPop + 1);
+    if (sb_cycle_end_resample_ranked(eng, hostSums, totalPop, masterRNG, nRanks, rank, popSizes, newSizes, &last)) return engFail();
+    stride(1);
+    (active ? nSegActive : nSegInactive) += last.n_segments;
+    nHist += last.n_start;
+    k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
+    return 0;
+  }
+
   // the same cycle with the dungeons kept in HOST memory, as a shim that leaves thisCycle/nextCycle in
   // Fortran arrays would do: upload bank, run, resample, download bank, read the cycle's bins
   int cycleHostBuffers(int active, double& k_new) {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (hN == 0) { if (downloadBank()) return -1; }
     if (sb_bank_upload(eng, hN, hr, hdir, hw, hG)) return engFail();
-    if (sb_run_cycle(eng, pRNG, 0, k_new, active, &last)) return engFail();
+    const uint64_t rng0 = pRNG;
     stride(totalPop + 1);
-    if (sb_resample(eng, pop, pRNG)) return engFail();
+    if (sb_run_cycle_resample(eng, rng0, 0, k_new, active, pop, pRNG, &last)) return engFail();
     stride(1);
     if (downloadBank()) return -1;
     int64_t nb = sb_tally_size(eng, active);
@@ -231,6 +243,9 @@ int sbh_eigen_cycle_end(void* pv, int active, const double* devSums, sb_cycle_re
 }
 int sbh_eigen_resample_ranked(void* pv, const int32_t* popSizes, int32_t* newLocal, double* k) {
   return ((eigenPhysicsPackage*)pv)->resampleRanked(popSizes, newLocal, *k);
+}
+int sbh_eigen_cycle_end_resample_ranked(void* pv, int active, const double* hostSums, const int32_t* popSizes, int32_t* newSizes, double* k, sb_cycle_result* res) {
+  auto* p = (eigenPhysicsPackage*)pv; int rc = p->cycleEndResampleRanked(active, hostSums, popSizes, newSizes, *k); if (res) *res = p->last; return rc;
 }
 // mpi_func.f90:133-159 getWorkshare / getOffset
 int sbh_workshare(int totPop, int nRanks, int rank, int* share, int* offset) {

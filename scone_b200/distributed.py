@@ -5,9 +5,10 @@
   k_eff broadcast                                  PhysicsPackages/eigenPhysicsPackage_class.f90:302
   getWorkshare / getOffset                         SharedModules/mpi_func.f90:133-159
 
-Per cycle: all-reduce of the 6 k-eff score sums, all-gather of the fission-bank sizes (twice, one int each),
-and send/recv of the few sites that cross the boundaries between neighbouring ranks. The resampling threshold
-is recomputed on every rank (a pure function of the sizes and the master RNG state): no gather + 3 broadcasts.
+Per cycle: ONE all-gather of 8 doubles per rank (the 6 k-eff score sums and the fission-bank size) and the send/recv of
+the few sites that cross the boundaries between neighbouring ranks. The resampling threshold and every rank's bank
+size after normalisation are recomputed on every rank (pure functions of the sizes and the master RNG state): no
+gather + 3 broadcasts + 2 all-gathers as in the MPI code.
 With the nccl backend the buffers are device memory and move over NVLink; with gloo (CPU tests, or several
 ranks sharing one GPU) they are staged through host memory.
 """
@@ -56,8 +57,9 @@ class TorchComm:
         self.backend = dist.get_backend(group)
         self.device = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
         self.on_device = self.backend == "nccl"
-        self.sums = torch.zeros(6, dtype=torch.float64, device=self.device)      # filled by the engine
-        self._stage = torch.zeros(6, dtype=torch.float64)
+        self.sums = torch.zeros(8, dtype=torch.float64, device=self.device)      # filled by the engine: 6 score sums, bank size, 0
+        self._stage = torch.zeros(8, dtype=torch.float64)
+        self._gath = torch.zeros(8 * self.size, dtype=torch.float64, device=self.device if self.on_device else "cpu")
         self._sizes = torch.zeros(self.size, dtype=torch.int32, device=self.device if self.on_device else "cpu")
         self._one = torch.zeros(1, dtype=torch.int32, device=self.device if self.on_device else "cpu")
         self._bufs = {}
@@ -76,6 +78,15 @@ class TorchComm:
             self.dist.all_reduce(self._stage, group=self.group)
             self.sums.copy_(self._stage)
             self.sync()
+
+    def all_gather_sums(self):
+        """All-gather of self.sums (8 doubles per rank) -> numpy [size][8] on the host."""
+        if self.on_device:
+            self.dist.all_gather_into_tensor(self._gath, self.sums, group=self.group)
+            return self._gath.cpu().numpy().reshape(self.size, 8).copy()
+        self._stage.copy_(self.sums)
+        self.dist.all_gather(list(self._gath.split(8)), self._stage, group=self.group)
+        return self._gath.numpy().reshape(self.size, 8).copy()
 
     def all_gather_int(self, v):
         self._one[0] = int(v)
@@ -121,16 +132,21 @@ def cycle(pp, active, comm):
     n_sites = C.c_int32()
     if L.sbh_eigen_cycle_begin(pp.h, 1 if active else 0, pp.k, comm.sums.data_ptr(), C.byref(n_sites)) != 0:
         raise EngineError(pp._err())
-    comm.all_reduce_sums()
-    res = CycleResult()
-    if L.sbh_eigen_cycle_end(pp.h, 1 if active else 0, comm.sums.data_ptr(), C.byref(res)) != 0:
-        raise EngineError(pp._err())
-    sizes = np.asarray(comm.all_gather_int(n_sites.value), np.int32)
-    new_local, k = C.c_int32(), C.c_double(pp.k)
-    if L.sbh_eigen_resample_ranked(pp.h, sizes.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(new_local), C.byref(k)) != 0:
+    # ONE collective per cycle: every rank gets every rank's 6 score sums and bank size, and adds the sums in rank order
+    # (same bits on every rank, independent of the collective's internal order)
+    g = comm.all_gather_sums()
+    sums = np.zeros(6)
+    for r in range(comm.size):
+        sums = sums + g[r, :6]
+    sizes = np.ascontiguousarray(g[:, 6].astype(np.int32))
+    new_sizes = np.zeros(comm.size, np.int32)
+    res, k = CycleResult(), C.c_double(pp.k)
+    if L.sbh_eigen_cycle_end_resample_ranked(pp.h, 1 if active else 0, sums.ctypes.data_as(C.POINTER(C.c_double)),
+                                             sizes.ctypes.data_as(C.POINTER(C.c_int32)), new_sizes.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             C.byref(k), C.byref(res)) != 0:
         raise EngineError(pp._err())
     pp.k = k.value
-    sizes2 = comm.all_gather_int(new_local.value)
+    sizes2 = [int(x) for x in new_sizes]
     if sum(sizes2) != pp.total_pop:
         raise EngineError("Normalisation failed!")
     if comm.size > 1:

@@ -45,7 +45,9 @@ def load_library():
         "sb_bank_size": (i32, [vp]), "sb_source_generate": (i32, [vp, i32, u64, i32]),
         "sb_run_cycle": (i32, [vp, u64, i32, dbl, i32, C.POINTER(CycleResult)]),
         "sb_resample": (i32, [vp, i32, u64]),
+        "sb_run_cycle_resample": (i32, [vp, u64, i32, dbl, i32, i32, u64, C.POINTER(CycleResult)]),
         "sb_cycle_begin": (i32, [vp, u64, i32, dbl, i32, vp, ip]), "sb_cycle_end": (i32, [vp, vp, C.POINTER(CycleResult)]),
+        "sb_cycle_end_resample_ranked": (i32, [vp, dp, i32, u64, i32, i32, ip, ip, C.POINTER(CycleResult)]),
         "sb_resample_ranked": (i32, [vp, i32, u64, i32, i32, ip, ip]), "sb_site_buffer_bytes": (C.c_size_t, [i32]),
         "sb_bank_export": (i32, [vp, i32, vp, i32, vp]), "sb_bank_splice": (i32, [vp, i32, i32, i32, vp, i32, vp]),
         "sb_tally_size": (i64, [vp, i32]), "sb_tally_read": (i32, [vp, i32, dp, dp, ip]), "sb_tally_last_bins": (i32, [vp, i32, dp]),
@@ -70,6 +72,7 @@ def load_library():
         "sbh_eigen_cycle_host_buffers": (i32, [vp, i32, dp, C.POINTER(CycleResult)]),
         "sbh_eigen_cycle_begin": (i32, [vp, i32, dbl, vp, ip]), "sbh_eigen_cycle_end": (i32, [vp, i32, vp, C.POINTER(CycleResult)]),
         "sbh_eigen_resample_ranked": (i32, [vp, ip, ip, dp]),
+        "sbh_eigen_cycle_end_resample_ranked": (i32, [vp, i32, dp, ip, ip, dp, C.POINTER(CycleResult)]),
         "sbh_workshare": (i32, [i32, i32, i32, ip, ip]), "sbh_balance_plan": (i32, [i32, i32, i32, ip, ip]),
         "sbh_eigen_download_bank": (i32, [vp]), "sbh_eigen_upload_bank": (i32, [vp]),
         "sbh_eigen_cycles": (i32, [vp, i32, i32]), "sbh_eigen_run": (i32, [vp]),

@@ -72,8 +72,11 @@ sizes = target + d
 start = int(sizes[:rank].sum())
 bank = np.arange(start, start + sizes[rank], dtype=np.int64)          # global site numbers stand in for sites
 # the three exchanges
-comm.sums.copy_(torch.arange(6, dtype=torch.float64) * (rank + 1)); comm.all_reduce_sums()
-assert torch.allclose(comm.sums, torch.arange(6, dtype=torch.float64) * sum(range(1, ws + 1)))
+comm.sums.copy_(torch.arange(8, dtype=torch.float64) * (rank + 1)); comm.all_reduce_sums()
+assert torch.allclose(comm.sums, torch.arange(8, dtype=torch.float64) * sum(range(1, ws + 1)))
+comm.sums.copy_(torch.arange(8, dtype=torch.float64) + 10 * rank)
+g = comm.all_gather_sums()
+assert g.shape == (ws, 8) and all(np.array_equal(g[r], np.arange(8) + 10.0 * r) for r in range(ws))
 got = comm.all_gather_int(int(sizes[rank])); assert got == [int(x) for x in sizes]
 su, ru, sd, rd = D.balance_plan(tot, ws, rank, sizes)
 as_u8 = lambda a: torch.from_numpy(a.view(np.uint8).copy())
