@@ -40,6 +40,7 @@ struct CeDev {                                    // device pointers + sizes, pa
   const double* grid; const double* data; const long long* gridOff; const long long* dataOff; const int* rows; const int* gridSize;
   const int* matOff; const int* matNuc; const double* matDens;
   const double* uGrid; const double* uMaj; const int* idxTab; const int* bucketStart;
+  const double* pairTot; const long long* pairOff;      // per nuclide and grid interval: { E_low, E_top, total_low, total_top }, 32-byte aligned
   double eMin, eMax;
 };
 
@@ -65,6 +66,10 @@ __device__ __forceinline__ int unionSearch(const CeDev& c, double E) {
   return u < 1 ? 1 : u;
 }
 
+// one 32-byte sector per nuclide: 256-bit load (LDG.E.256) of { E_low, E_top, total_low, total_top }
+__device__ __forceinline__ void ldPair(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 // Sigma_t(material m, E) with E in union interval u: updateTotalMatXS (aceNeutronDatabase_class.f90:509-571)
 __device__ __forceinline__ double matTotal(const CeDev& c, int u, double e, int m) {
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
@@ -72,13 +77,11 @@ __device__ __forceinline__ double matTotal(const CeDev& c, int u, double e, int 
   double tot = 0.0;
   for (int k = k0; k < k1; ++k) {
     const int nuc = __ldg(c.matNuc + k) - 1;
-    const int idx = __ldg(row + nuc);
-    const double* g = c.grid + __ldg(c.gridOff + nuc) + (idx - 1);
-    const double E_low = __ldg(g), E_top = __ldg(g + 1);
-    const double f = (e - E_low) / (E_top - E_low);
-    const int rows = __ldg(c.rows + nuc);
-    const double* d = c.data + __ldg(c.dataOff + nuc) + (size_t)(idx - 1) * rows;
-    tot = tot + __ldg(c.matDens + k) * (__ldg(d + rows) * f + (1.0 - f) * __ldg(d));
+    const int idx = __ldg(row + nuc);                          // what binarySearch(eGrid, E) returns for this nuclide
+    double E_low, E_top, s_low, s_top;
+    ldPair(c.pairTot + 4 * (__ldg(c.pairOff + nuc) + (idx - 1)), E_low, E_top, s_low, s_top);
+    const double f = (e - E_low) / (E_top - E_low);            // nuclide%search
+    tot = tot + __ldg(c.matDens + k) * (s_top * f + (1.0 - f) * s_low);      // nuclide%totalXS
   }
   return tot * 1.0;
 }
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(256) k_ce_lookup(const CeDev c, long long n, c
     if (!total && !macro) continue;
     const int m = mat[i];
     if (m < 1 || m > c.nMat) { atomicMax(err, 2); continue; }
+    if (!macro) { total[i] = matTotal(c, u, e, m); continue; }
     const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
     const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
     double tot = 0.0;
@@ -216,6 +220,16 @@ static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err) {
       idxTab[(size_t)j * nNuc + n] = std::max(1, std::min(N - 1, p));
     }
   }
+  // pair table of the total cross section: one 32-byte record per nuclide grid interval
+  std::vector<long long> pairOff(nNuc); long long po = 0;
+  for (int n = 0; n < nNuc; ++n) { pairOff[n] = po; po += gsize[n] - 1; }
+  std::vector<double> pairTot((size_t)po * 4);
+  for (int n = 0; n < nNuc; ++n)
+    for (int i = 0; i + 1 < gsize[n]; ++i) {
+      double* q = &pairTot[(size_t)(pairOff[n] + i) * 4];
+      q[0] = grid[gridOff[n] + i]; q[1] = grid[gridOff[n] + i + 1];
+      q[2] = data[dataOff[n] + (size_t)i * rows[n]]; q[3] = data[dataOff[n] + (size_t)(i + 1) * rows[n]];
+    }
   // hash buckets on the IEEE bits
   const long long keyMin = hashKey(u.front()), keyMax = hashKey(u.back());
   const int nB = (int)(keyMax - keyMin + 1);
@@ -227,6 +241,7 @@ static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err) {
   d.grid = ceUpload(H, grid, err); d.data = ceUpload(H, data, err); d.gridOff = ceUpload(H, gridOff, err); d.dataOff = ceUpload(H, dataOff, err);
   d.rows = ceUpload(H, rows, err); d.gridSize = ceUpload(H, gsize, err);
   d.matOff = ceUpload(H, matOff, err); d.matNuc = ceUpload(H, matNuc, err); d.matDens = ceUpload(H, matDens, err);
+  d.pairTot = ceUpload(H, pairTot, err); d.pairOff = ceUpload(H, pairOff, err);
   d.uGrid = ceUpload(H, u, err); d.uMaj = ceUpload(H, H.uMaj, err); d.idxTab = ceUpload(H, idxTab, err); d.bucketStart = ceUpload(H, bucketStart, err);
   if (!err.empty()) return -1;
   H.nNuc = nNuc; H.nMat = nMat; H.loaded = true;
