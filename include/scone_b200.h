@@ -95,6 +95,30 @@ typedef struct sb_ce_flat {
   int32_t n_mat; const int32_t* mat_off /*[n_mat+1]*/; const int32_t* mat_nuc; const double* mat_dens;
 } sb_ce_flat;
 
+/* ---- continuous-energy transport model ------------------------------------------------------------------------------
+ * One ACE card per nuclide, exactly the arrays aceCard holds after readFromFile (NuclearData/DataDecks/ACE/aceCard_class.f90:
+ * 96-98 NXS(16), JXS(32), XSS(:); :69-71 ZAID, AW, TZ): the engine builds from them what aceNeutronNuclide%init builds
+ * (aceNeutronNuclide_class.f90:737-948: main data, reaction list) and samples the reaction laws from XSS in place.
+ * Materials as ceNeutronMaterial holds them (nuclide indices 1-based in composition order, atomic densities) plus the material
+ * temperature [K] of materialMenu.  active_mats = the materials nuclearDatabase%activate receives (present in the geometry):
+ * the unionised majorant covers those (aceNeutronDatabase_class.f90:1330-1621).
+ * Settings: collision_xs = 1/avgDist, energy_per_fission = H235 (aceNeutronDatabase init); min/max_energy, thresh_energy,
+ * thresh_mass = neutronCEstd minEnergy/maxEnergy/energyThreshold/massThreshold (neutronCEstd_class.f90:110-150);
+ * source_energy = fissionSource E (fissionSource_class.f90:128).
+ * Not supported (refused with an error): S(a,b), URR tables, TMS, DBRC, correlated laws, 32-bin angular pdfs.          */
+typedef struct sb_ace_card {
+  const char* zaid; double aw, tz;
+  const int32_t* nxs /*[16]*/; const int32_t* jxs /*[32]*/; const double* xss; int64_t n_xss;
+} sb_ace_card;
+typedef struct sb_ce_model {
+  int32_t n_nuc; const sb_ace_card* cards;
+  int32_t n_mat; const int32_t* mat_off /*[n_mat+1]*/; const int32_t* mat_nuc; const double* mat_dens; const double* mat_temp /*[n_mat]*/;
+  int32_t n_active; const int32_t* active_mats;
+  double collision_xs, energy_per_fission;
+  double min_energy, max_energy, thresh_energy, thresh_mass;
+  double source_energy;
+} sb_ce_model;
+
 /* ---- tallies: Tallies/TallyClerks/collisionClerk_class.f90, TallyMaps/, TallyResponses/ ---- */
 enum { SB_MAP_SPACE = 1, SB_MAP_MATERIAL = 2, SB_MAP_ENERGY = 3 };
 enum { SB_GRID_LIN = 1, SB_GRID_LOG = 2, SB_GRID_UNSTRUCT = 3 };
@@ -133,7 +157,8 @@ typedef struct sb_cycle_result {
   int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
-       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7 };
+       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7,
+       SB_ERR_CE_ENERGY = 8 /* energy outside the bounds of the CE data */, SB_ERR_CE_DATA = 9 /* failed search / rejection loop in the reaction data */ };
 
 /* ---- life cycle -------------------------------------------------------------------------- */
 int  sb_create(sb_engine** h, int device);
@@ -145,6 +170,11 @@ int64_t sb_launch_count(sb_engine* h);
 /* ---- model load (replaces nothing at run time; consumes what csg%init / database%init built) */
 int sb_load_geometry(sb_engine* h, const sb_geom_flat* g);
 int sb_load_mg_data(sb_engine* h, const sb_mg_flat* d);
+/* continuous-energy transport data (instead of sb_load_mg_data); load the geometry first */
+int sb_load_ce_model(sb_engine* h, const sb_ce_model* m);
+/* what the engine built from the cards, for parity tests: grid size / rows of nuclide nuc_idx, then the arrays */
+int sb_ce_nuclide_info(sb_engine* h, int nuc_idx, int32_t* grid_size, int32_t* rows, int32_t* n_mt);
+int sb_ce_nuclide_data(sb_engine* h, int nuc_idx, double* grid, double* main_data, int32_t* mt_list);
 /* phase: 0 inactive, 1 active. norm_clerk = 1-based clerk whose first bin normalises (0 = none) */
 int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n_clerks, int norm_clerk, double norm_val);
 int sb_set_options(sb_engine* h, const sb_options* o);
@@ -154,6 +184,9 @@ int sb_set_options(sb_engine* h, const sb_options* o);
 int sb_bank_upload(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G);
 int sb_bank_download(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, int32_t* G);
 int sb_bank_size(sb_engine* h);
+/* continuous-energy banks carry E [MeV] instead of G */
+int sb_bank_upload_ce(sb_engine* h, int n, const double* r, const double* dir, const double* w, const double* E);
+int sb_bank_download_ce(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, double* E);
 /* fissionSource%generate on the device (ParticleObjects/Source/fissionSource_class.f90:149-271) */
 int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offset);
 

@@ -13,6 +13,7 @@
 #include <string>
 
 #include "physics.hpp"
+#include "cephysics.hpp"
 
 using namespace orc;
 
@@ -347,8 +348,8 @@ void* orc_eigen_load(const char* deckPath, const char* overrides) {
   ORC_TRY
   Dict d = Dict::fromFile(deckPath);
   applyOverrides(d, overrides);
-  auto* e = new EigenPP();
-  e->init(d, dirName(deckPath));
+  EigenPP* e = (d.getWord("dataType") == "ce") ? (EigenPP*)new CeEigenPP() : new EigenPP();
+  try { e->init(d, dirName(deckPath)); } catch (...) { delete e; throw; }
   return e;
   ORC_CATCH(nullptr)
 }
@@ -376,6 +377,12 @@ int orc_eigen_bank(void* ev, double* r, double* dir, double* w, int* G, int* bro
     for (int k = 0; k < 3; ++k) { r[3 * i + k] = p.r[k]; dir[3 * i + k] = p.dir[k]; }
     w[i] = p.wgt; G[i] = p.G; brood[i] = p.broodID;
   }
+  return e->thisCycle->pop;
+}
+// energies of the bank (continuous-energy runs)
+int orc_eigen_bank_E(void* ev, double* E) {
+  auto* e = (EigenPP*)ev;
+  for (int i = 0; i < e->thisCycle->pop; ++i) E[i] = e->thisCycle->prisoners[i].E;
   return e->thisCycle->pop;
 }
 int orc_eigen_set_bank(void* ev, int n, const double* r, const double* dir, const double* w, const int* G) {
@@ -447,6 +454,39 @@ double orc_ce_nuclide_total(void* h, double E) {
 int orc_ce_nuclide_nubar(void* h, double E, double* total, double* prompt, double* delayed) {
   CE_TRY auto* x = (orc_ce::Nuclide*)h; *total = x->release(E); *prompt = x->releasePrompt(E); *delayed = x->releaseDelayed(E); return 0; CE_CATCH(-1)
 }
+// ---- pins of the CE reaction restatement (tests/test_oracle_cereact.py) -------------------------------------------
+double orc_tabpdf_sample(int n, const double* x, const double* pdf, const double* cdf, int flag, double r) {
+  CE_TRY orc_ce::TabularPdf t; t.initCdf(std::vector<double>(x, x + n), std::vector<double>(pdf, pdf + n), std::vector<double>(cdf, cdf + n), flag); return t.sample(r); CE_CATCH(std::nan(""))
+}
+double orc_endftable_at(int n, const double* x, const double* y, int nr, const int* bounds, const int* inter, double v) {
+  CE_TRY orc_ce::EndfTable t; t.x.assign(x, x + n); t.y.assign(y, y + n);
+  if (nr > 0) { t.bounds.assign(bounds, bounds + nr); t.inter.assign(inter, inter + nr); }
+  return t.at(v); CE_CATCH(std::nan(""))
+}
+void* orc_ce_nuclide_from_acebin(const char* path) {
+  CE_TRY orc_ce::AceCard ace; orc::readAceBin(ace, path); auto* n = new orc_ce::Nuclide(); n->init(ace, true); return n; CE_CATCH(nullptr)
+}
+int orc_ce_nuclide_mt_list(void* h, int* MTs, int* firstIdx) {
+  auto* x = (orc_ce::Nuclide*)h;
+  for (int i = 0; i < x->nMTinelastic; ++i) { MTs[i] = x->mtData[i].MT; firstIdx[i] = x->mtData[i].firstIdx; }
+  return x->nMTinelastic;
+}
+// sampleOut of one reaction of the nuclide from a given RNG state: kind 0 elastic, 1 inelastic MT record `which` (0-based), 2 fission.
+// out = { mu, phi, E_out, lambda }, returns the number of random numbers drawn (< 0 on error)
+long orc_ce_nuclide_sample(void* h, int kind, int which, double E_in, uint64_t state, double* out) {
+  CE_TRY auto* x = (orc_ce::Nuclide*)h; orc::RNG r; r.init((int64_t)state);
+  double mu = 0, phi = 0, E = 0, lam = orc_ce::HUGE_LAMBDA;
+  if (kind == 0) x->elastic.sampleOut(mu, phi, E, E_in, r);
+  else if (kind == 1) x->mtData.at(which).kin.sampleOut(mu, phi, E, E_in, r);
+  else x->fission.sampleOut(mu, phi, E, E_in, r, lam);
+  out[0] = mu; out[1] = phi; out[2] = E; out[3] = lam;
+  return (long)r.count; CE_CATCH(-1)
+}
+int orc_ce_nuclide_invert_inelastic(void* h, double E, uint64_t state) {
+  CE_TRY auto* x = (orc_ce::Nuclide*)h; orc::RNG r; r.init((int64_t)state); return x->invertInelastic(E, r); CE_CATCH(-1)
+}
+double orc_ce_nuclide_mt_release(void* h, int which, double E) { CE_TRY return ((orc_ce::Nuclide*)h)->mtData.at(which).kin.release(E); CE_CATCH(std::nan("")) }
+int orc_ce_nuclide_mt_cm(void* h, int which) { return ((orc_ce::Nuclide*)h)->mtData.at(which).kin.cmFrame ? 1 : 0; }
 void* orc_ce_db_new() { return new orc_ce::Database(); }
 void orc_ce_db_free(void* h) { delete (orc_ce::Database*)h; }
 int orc_ce_db_add_nuclide(void* h, void* nuc) { auto* d = (orc_ce::Database*)h; d->nuclides.push_back(*(orc_ce::Nuclide*)nuc); return (int)d->nuclides.size(); }

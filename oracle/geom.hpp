@@ -483,6 +483,13 @@ struct CoordList {
     for (int i = 0; i < n; ++i)
       for (int k = 0; k < 3; ++k) lvl[i].r[k] = lvl[i].r[k] + d * lvl[i].dir[k];
   }
+  void point(const Vec3& d) {                                       // assignDirection, coord_class.f90:453-472
+    lvl[0].dir = d;
+    for (int i = 1; i < nesting; ++i) {
+      if (lvl[i].isRotated) lvl[i].dir = matvec(lvl[i].rotMat, lvl[i - 1].dir);
+      else lvl[i].dir = lvl[i - 1].dir;
+    }
+  }
   void rotate(double mu, double phi) {                              // coord_class.f90:386-408
     lvl[0].dir = rotateVector(lvl[0].dir, mu, phi);
     for (int i = 1; i < nesting; ++i) {

@@ -15,24 +15,17 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
 
-#include "../scone_b200/csrc/sb_math.h"
 #include "geom.hpp"
+#include "mathmode.hpp"
 #include "mgdata.hpp"
 #include "rng.hpp"
 
 namespace orc {
-
-enum MathMode { MATH_LIBM = 0, MATH_SB = 1 };
-inline int& mathMode() { static int m = MATH_LIBM; return m; }
-inline double mlog(double x) { return mathMode() == MATH_SB ? sbm::log(x) : std::log(x); }
-inline void msincos(double x, double& s, double& c) {
-  if (mathMode() == MATH_SB) sbm::sincos(x, &s, &c);
-  else { s = std::sin(x); c = std::cos(x); }
-}
 
 // SharedModules/genericProcedures.f90:1047-1084
 inline Vec3 rotateVector(const Vec3& dir, double mu, double phi) {
@@ -319,7 +312,7 @@ struct Grid {
   int search(double value) const {
     int idx = 0;
     if (type == LIN) idx = (int)std::floor((value - bins[0]) / step) + 1;
-    else if (type == LOGAR) idx = (int)std::floor(std::log(value / bins[0]) / step) + 1;
+    else if (type == LOGAR) idx = (int)std::floor(mlog(value / bins[0]) / step) + 1;
     else if (type == UNSTRUCT) idx = binarySearch(bins, value);
     if (idx < 1 || idx >= (int)bins.size()) idx = -1;   // valueOutsideArray
     return idx;
@@ -408,6 +401,30 @@ inline std::unique_ptr<TallyMap> newTallyMap(const Dict& d, const std::map<std::
   throw FatalError("new_tallyMap", "Unrecognised / unsupported type of tallyMap in oracle: " + t);
 }
 
+// what the clerks ask of the nuclear database for the particle at hand (nuclearDatabase_inter.f90:38-53: getTotalMatXS,
+// getMaterial -> getMacroXSs); implemented over the MG database here and over the CE database in cephysics.hpp
+struct XsView {
+  virtual ~XsView() = default;
+  virtual int nMat() const = 0;
+  virtual double totalMatXS(const Particle& p, int matIdx) const = 0;
+  virtual void macroXSs(MacroXSs& x, const Particle& p, int matIdx) const = 0;
+  // tracking interface (getTrackMatXS / getMajorantXS; collisionXS = 1/avgDist of the database)
+  virtual double trackMatXS(const Particle& p, int matIdx) const = 0;
+  virtual double majorantXS(const Particle& p) const = 0;
+  virtual double collisionXS() const = 0;
+  virtual bool isFissileMat(int matIdx) const = 0;
+};
+struct MgXsView : XsView {
+  const MgDatabase* db = nullptr;
+  int nMat() const override { return (int)db->mats.size(); }
+  double totalMatXS(const Particle& p, int matIdx) const override { return db->getTotalMatXS(p.G, matIdx); }
+  void macroXSs(MacroXSs& x, const Particle& p, int matIdx) const override { db->mats.at(matIdx - 1).getMacroXSs(x, p.G); }
+  double trackMatXS(const Particle& p, int matIdx) const override { return db->getTrackMatXS(p.G, matIdx); }
+  double majorantXS(const Particle& p) const override { return db->getMajorantXS(p.G); }
+  double collisionXS() const override { return db->collisionXS; }
+  bool isFissileMat(int matIdx) const override { return db->mats.at(matIdx - 1).fissile; }
+};
+
 // Tallies/TallyResponses: fluxResponse (=1) and macroResponse (macroResponse_class.f90:70-172)
 struct Response {
   bool isFlux = true; int MT = 0;
@@ -430,11 +447,12 @@ struct Response {
       }
     } else MT = mt;
   }
-  double get(const MgDatabase& db, int matIdx, int G) const {
+  double get(const XsView& db, const Particle& p) const {
     if (isFlux) return 1.0;
+    int matIdx = p.matIdx();
     if (matIdx == VOID_MAT) return 0.0;
-    if (matIdx < 1 || matIdx > (int)db.mats.size()) return 0.0;
-    MacroXSs x; db.mats[matIdx - 1].getMacroXSs(x, G);
+    if (matIdx < 1 || matIdx > db.nMat()) return 0.0;
+    MacroXSs x; db.macroXSs(x, p, matIdx);
     return x.get(MT);
   }
 };
@@ -494,7 +512,7 @@ struct TallyAdmin {
 
   // trackingXS: the value last stored in the tracking cache by the transport operator
   // (baseMgNeutronDatabase_class.f90:119-133)
-  void reportInColl(const Particle& p, const MgDatabase& db, double trackingXS, bool virt) {
+  void reportInColl(const Particle& p, const XsView& db, double trackingXS, bool virt) {
     if (atch) atch->reportInColl(p, db, trackingXS, virt);
     for (auto& c : clerks) {
       if (c.kind == Clerk::COLLISION) {                             // collisionClerk_class.f90:192-244
@@ -502,14 +520,14 @@ struct TallyAdmin {
         ParticleState s = p.state();
         int binIdx = c.map ? c.map->map(s) : 1;
         if (binIdx == 0) continue;
-        double flux = c.handleVirtual ? p.w / trackingXS : p.w / db.getTotalMatXS(p.G, p.matIdx());
+        double flux = c.handleVirtual ? p.w / trackingXS : p.w / db.totalMatXS(p, p.matIdx());
         long a = c.addr + (long)c.response.size() * (binIdx - 1) - 1;
-        for (size_t i = 1; i <= c.response.size(); ++i) mem.score(c.response[i - 1].get(db, p.matIdx(), p.G) * flux, a + (long)i);
+        for (size_t i = 1; i <= c.response.size(); ++i) mem.score(c.response[i - 1].get(db, p) * flux, a + (long)i);
       } else if (c.kind == Clerk::KEFF_IMPLICIT) {                  // keffImplicitClerk_class.f90:180-236
         if (!c.handleVirtual && virt) continue;
         if (p.matIdx() == VOID_MAT) continue;
-        double flux = c.handleVirtual ? p.w / trackingXS : p.w / db.getTotalMatXS(p.G, p.matIdx());
-        MacroXSs x; db.mats.at(p.matIdx() - 1).getMacroXSs(x, p.G);
+        double flux = c.handleVirtual ? p.w / trackingXS : p.w / db.totalMatXS(p, p.matIdx());
+        MacroXSs x; db.macroXSs(x, p, p.matIdx());
         double s1 = x.nuFission * flux, s2 = (x.capture + x.fission) * flux;
         mem.score(s1, c.addr + 0);   // IMP_PROD
         mem.score(s2, c.addr + 1);   // IMP_ABS
@@ -520,7 +538,10 @@ struct TallyAdmin {
     if (atch) atch->reportOutColl(p, MT);
     for (auto& c : clerks) if (c.kind == Clerk::KEFF_IMPLICIT) {
       double score = 0.0;
-      if (MT == macroAllScatter || MT == macroIEscatter) score = std::max(p.w - p.preCollision.wgt, 0.0);
+      if (MT == 16 || MT == 11 || MT == 24 || MT == 30 || MT == 41 || (MT >= 875 && MT <= 891)) score = 1.0 * p.preCollision.wgt;   // N_2N, N_2Nd, N_2Na, N_2N2a, N_2Np, N_2Nl(1):N_2Ncont
+      else if (MT == 17 || MT == 25 || MT == 42) score = 2.0 * p.preCollision.wgt;                                                   // N_3N, N_3Na, N_3Np
+      else if (MT == 37) score = 3.0 * p.preCollision.wgt;                                                                           // N_4N
+      else if (MT == macroAllScatter || MT == macroIEscatter) score = std::max(p.w - p.preCollision.wgt, 0.0);
       if (score > 0.0) mem.score(score, c.addr + 2);   // SCATTER_PROD
     }
   }
@@ -570,10 +591,12 @@ struct TallyAdmin {
 // Source  (ParticleObjects/Source/fissionSource_class.f90:149-271, source_inter.f90:98-118)
 // ===========================================================================
 struct FissionSource {
-  const GeometryStd* geom = nullptr; const MgDatabase* db = nullptr;
-  double bottom[3], top[3]; int G = 1, attempts = 10000;
-  void init(const GeometryStd* g, const MgDatabase* d) {
-    geom = g; db = d;
+  const GeometryStd* geom = nullptr; const MgDatabase* db = nullptr; const XsView* xs = nullptr;
+  double bottom[3], top[3]; int G = 1, attempts = 10000; double E = 1.0E-6;
+  // continuous-energy branch of sampleParticle (fissionSource_class.f90:211-235): set by the CE driver
+  std::function<void(ParticleState&, int, RNG&)> sampleCE;
+  void init(const GeometryStd* g, const MgDatabase* d, const XsView* v) {
+    geom = g; db = d; xs = v;
     double b[6]; g->bounds(b);
     for (int i = 0; i < 3; ++i) { bottom[i] = b[i]; top[i] = b[i + 3]; }
   }
@@ -592,9 +615,10 @@ struct FissionSource {
       if (matIdx == VOID_MAT || matIdx == OUTSIDE_MAT) continue;
       if (matIdx == UNDEF_MAT) throw FatalError("sampleParticle (fissionSource)", "Particle position was sampled in an undefined material");
       if (matIdx == OVERLAP_MAT) throw FatalError("sampleParticle (fissionSource)", "Particle position was sampled in an overlapping cell region");
-      const MgMaterial& mat = db->mats.at(matIdx - 1);
-      if (!mat.fissile) continue;
+      if (!xs->isFissileMat(matIdx)) continue;
       p.matIdx = matIdx; p.uniqueID = uniqueID; p.wgt = 1.0; p.time = 0.0; p.r = r;
+      if (sampleCE) { sampleCE(p, matIdx, rand); return p; }
+      const MgMaterial& mat = db->mats.at(matIdx - 1);
       double mu, phi; int G_out;
       mat.fissionSampleOut(mu, phi, G_out, rand);
       p.G = G_out; p.isMG = true;
@@ -626,7 +650,8 @@ struct EigenPP {
   int tracking = TRACK_DT; double htCutoff = 0.9; bool stCache = true;
   RNG pRNG;
   GeometryStd geom;
-  MgDatabase db;
+  MgDatabase db; MgXsView view; const XsView* xs = &view;
+  virtual ~EigenPP() = default;
   TallyAdmin inactiveTally, activeTally, inactiveAtch, activeAtch;
   FissionSource source;
   Dungeon dungeonA, dungeonB; Dungeon* thisCycle = &dungeonA; Dungeon* nextCycle = &dungeonB;
@@ -634,7 +659,7 @@ struct EigenPP {
   long nSegments = 0, nCollisions = 0, nHistories = 0;
   std::vector<double> cycleK;            // k_new after each cycle (both phases)
 
-  void init(const Dict& dict, const std::string& baseDir) {
+  virtual void init(const Dict& dict, const std::string& baseDir) {
     pop = dict.getInt("pop");
     N_inactive = dict.getInt("inactive");
     N_active = dict.getInt("active");
@@ -649,6 +674,7 @@ struct EigenPP {
     geom.init(dict.getDict("geometry"), mats);
     db.init(nd, nucData, baseDir);
     db.activate(geom.activeMats());
+    view.db = &db;
     const Dict& co = dict.getDict("collisionOperator");
     if (!co.isPresent("neutronMG") || co.getDict("neutronMG").getWord("type") != "neutronMGstd")
       throw FatalError("collisionOperator init", "oracle supports neutronMGstd only");
@@ -661,7 +687,7 @@ struct EigenPP {
     inactiveTally.init(dict.getDict("inactiveTally"), mats);
     activeTally.init(dict.getDict("activeTally"), mats);
     if (dict.isPresent("source")) throw FatalError("init (eigenPhysicsPackage)", "oracle supports the default fissionSource only");
-    source.init(&geom, &db);
+    source.init(&geom, &db, xs);
     inactiveAtch.init(Dict::fromString("keff { type keffAnalogClerk; } display (keff); mpiSync 1;"), mats);
     activeAtch.init(Dict::fromString("keff { type keffImplicitClerk; } display (keff); mpiSync 1;"), mats);
     inactiveTally.atch = &inactiveAtch;
@@ -673,7 +699,7 @@ struct EigenPP {
   // trackXS (out) = content of the tracking cache for the tallies.
   // -------------------------------------------------------------------------
   void deltaTracking(Particle& p, TallyAdmin& tally, double& trackXS, long& seg) const {   // transportOperatorDT_class.f90:47-130
-    trackXS = std::max(db.getMajorantXS(p.G), db.collisionXS);
+    trackXS = std::max(xs->majorantXS(p), xs->collisionXS());
     double majorant_inv = 1.0 / trackXS;
     for (;;) {
       double distance = -mlog(p.pRNG->get()) * majorant_inv;
@@ -682,12 +708,12 @@ struct EigenPP {
       ++seg;
       int m = p.matIdx();
       if (m == OUTSIDE_MAT) { p.fate = LEAK_FATE; p.isDead = true; break; }
-      if (m == VOID_MAT) { tally.reportInColl(p, db, trackXS, true); continue; }
+      if (m == VOID_MAT) { tally.reportInColl(p, *xs, trackXS, true); continue; }
       if (m == UNDEF_MAT) throw FatalError("deltaTracking", "Particle is in undefined material");
       if (m == OVERLAP_MAT) throw FatalError("deltaTracking", "Particle is in overlapping cells");
-      double sigmaT = db.getTrackMatXS(p.G, m);
+      double sigmaT = xs->trackMatXS(p, m);
       if (p.pRNG->get() < sigmaT * majorant_inv) break;
-      tally.reportInColl(p, db, trackXS, true);
+      tally.reportInColl(p, *xs, trackXS, true);
     }
   }
   void surfaceTracking(Particle& p, TallyAdmin& tally, double& trackXS, long& seg) const {  // transportOperatorHT_class.f90:156-258 (== ST_class.f90:48-166)
@@ -695,14 +721,14 @@ struct EigenPP {
     DistCache cache;
     for (;;) {
       int m = p.matIdx();
-      double sigmaTrack = (m == VOID_MAT) ? db.collisionXS : std::max(db.getTrackMatXS(p.G, m), db.collisionXS);
+      double sigmaTrack = (m == VOID_MAT) ? xs->collisionXS() : std::max(xs->trackMatXS(p, m), xs->collisionXS());
       trackXS = sigmaTrack;
       double dist, invSigmaTrack, sigmaT;
       if (sigmaTrack < tol) { dist = INF; invSigmaTrack = INF; sigmaT = 0.0; }
       else {
         invSigmaTrack = 1.0 / sigmaTrack;
         dist = -mlog(p.pRNG->get()) * invSigmaTrack;
-        sigmaT = db.getTrackMatXS(p.G, m);
+        sigmaT = xs->trackMatXS(p, m);
         if (dist != dist) throw FatalError("surfaceTracking", "Distance is NaN");
       }
       p.prePath = p.state();
@@ -718,7 +744,7 @@ struct EigenPP {
       if (p.isDead) break;
       if (event == COLL_EV) {
         if (p.pRNG->get() < sigmaT * invSigmaTrack) break;
-        tally.reportInColl(p, db, trackXS, true);
+        tally.reportInColl(p, *xs, trackXS, true);
       }
     }
   }
@@ -727,8 +753,8 @@ struct EigenPP {
     if (tracking == TRACK_DT) deltaTracking(p, tally, trackXS, seg);
     else if (tracking == TRACK_ST) surfaceTracking(p, tally, trackXS, seg);
     else {                                                          // transportOperatorHT_class.f90:49-81
-      double majorant_inv = 1.0 / std::max(db.getMajorantXS(p.G), db.collisionXS);
-      double sigmaT = (p.matIdx() == VOID_MAT) ? 0.0 : db.getTrackMatXS(p.G, p.matIdx());
+      double majorant_inv = 1.0 / std::max(xs->majorantXS(p), xs->collisionXS());
+      double sigmaT = (p.matIdx() == VOID_MAT) ? 0.0 : xs->trackMatXS(p, p.matIdx());
       double ratio = sigmaT * majorant_inv;
       if (ratio > (1.0 - htCutoff)) deltaTracking(p, tally, trackXS, seg);
       else surfaceTracking(p, tally, trackXS, seg);
@@ -737,7 +763,7 @@ struct EigenPP {
   }
 
   // collisionProcessor_inter.f90:114-195 with the neutronMGstd hooks (neutronMGstd_class.f90:85-297)
-  void collide(Particle& p, TallyAdmin& tally, double trackXS, Dungeon& next) const {
+  virtual void collide(Particle& p, TallyAdmin& tally, double trackXS, Dungeon& next) const {
     int matIdx = p.matIdx();
     // sampleCollision: alpha-absorption test always draws (alpha = 0 => never taken)
     double denom = db.getTrackMatXS(p.G, matIdx);
@@ -750,7 +776,7 @@ struct EigenPP {
       double r = p.pRNG->get();
       MT = x.invert(r);
     }
-    tally.reportInColl(p, db, trackXS, false);
+    tally.reportInColl(p, view, trackXS, false);
     p.preCollision = p.state();
     // implicit
     if (mat.fissile) {

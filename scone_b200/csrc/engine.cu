@@ -26,6 +26,7 @@
 #include "sb_hist.cuh"
 #include "sb_track.cuh"
 #include "sb_ce.cuh"
+#include "sb_cehist.cuh"
 
 using namespace sbd;
 using sbh::Bank; using sbh::CycleDev; using sbh::HistArgs; using sbh::HotLayout; using sbh::HUni;
@@ -121,7 +122,7 @@ __global__ void k_sort_sites(Bank src, Bank dst, const int* offsets, const Cycle
     int d = offsets[b] + src.seq[s];
     dst.rx[d] = src.rx[s]; dst.ry[d] = src.ry[s]; dst.rz[d] = src.rz[s];
     dst.ux[d] = src.ux[s]; dst.uy[d] = src.uy[s]; dst.uz[d] = src.uz[s];
-    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.brood[d] = b; dst.seq[d] = src.seq[s];
+    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.E[d] = src.E[s]; dst.brood[d] = b; dst.seq[d] = src.seq[s];
   }
 }
 
@@ -352,7 +353,7 @@ __global__ void k_norm_scatter(Bank src, Bank dst, const int* flag, const int* o
       if (d >= dstCap) { atomicMax(&cdw->error, SB_ERR_BANK_OVERFLOW); continue; }
       dst.rx[d] = src.rx[j]; dst.ry[d] = src.ry[j]; dst.rz[d] = src.rz[j];
       dst.ux[d] = src.ux[j]; dst.uy[d] = src.uy[j]; dst.uz[d] = src.uz[j];
-      dst.w[d] = src.w[j]; dst.G[d] = src.G[j]; dst.brood[d] = src.brood[j]; dst.seq[d] = 0;
+      dst.w[d] = src.w[j]; dst.G[d] = src.G[j]; dst.E[d] = src.E[j]; dst.brood[d] = src.brood[j]; dst.seq[d] = 0;
     }
   }
 }
@@ -393,21 +394,21 @@ __global__ void k_norm_rank_counts(const unsigned long long* rn, const CycleDev*
 // loadBalancing (particleDungeon_class.f90:607-698): pack sites of the ends of the bank / rebuild the bank as
 // [received from below] + kept middle + [received from above]. Packed site layout: 7 f64 arrays of k, then k i32 (G)
 __global__ void k_bank_pack_range(Bank b, int first, int k, double* buf) {
-  int* g = (int*)(buf + 7 * (size_t)k);
+  int* g = (int*)(buf + 8 * (size_t)k);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
     int s = first + i;
     buf[i] = b.rx[s]; buf[k + i] = b.ry[s]; buf[2 * (size_t)k + i] = b.rz[s];
     buf[3 * (size_t)k + i] = b.ux[s]; buf[4 * (size_t)k + i] = b.uy[s]; buf[5 * (size_t)k + i] = b.uz[s];
-    buf[6 * (size_t)k + i] = b.w[s]; g[i] = b.G[s];
+    buf[6 * (size_t)k + i] = b.w[s]; buf[7 * (size_t)k + i] = b.E[s]; g[i] = b.G[s];
   }
 }
 __global__ void k_bank_unpack_range(Bank b, int first, int k, const double* buf) {
-  const int* g = (const int*)(buf + 7 * (size_t)k);
+  const int* g = (const int*)(buf + 8 * (size_t)k);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
     int s = first + i;
     b.rx[s] = buf[i]; b.ry[s] = buf[k + i]; b.rz[s] = buf[2 * (size_t)k + i];
     b.ux[s] = buf[3 * (size_t)k + i]; b.uy[s] = buf[4 * (size_t)k + i]; b.uz[s] = buf[5 * (size_t)k + i];
-    b.w[s] = buf[6 * (size_t)k + i]; b.G[s] = g[i]; b.brood[s] = 0; b.seq[s] = 0;
+    b.w[s] = buf[6 * (size_t)k + i]; b.E[s] = buf[7 * (size_t)k + i]; b.G[s] = g[i]; b.brood[s] = 0; b.seq[s] = 0;
   }
 }
 __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfirst) {
@@ -415,7 +416,7 @@ __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfir
     int s = first + i, d = dfirst + i;
     dst.rx[d] = src.rx[s]; dst.ry[d] = src.ry[s]; dst.rz[d] = src.rz[s];
     dst.ux[d] = src.ux[s]; dst.uy[d] = src.uy[s]; dst.uz[d] = src.uz[s];
-    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.brood[d] = 0; dst.seq[d] = 0;
+    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.E[d] = src.E[s]; dst.brood[d] = 0; dst.seq[d] = 0;
   }
 }
 
@@ -446,7 +447,7 @@ __global__ void k_source(const Model M, const char* blob, Bank out, int n, uint6
       rotateVector(d, mu, phi);
       out.rx[i] = r[0]; out.ry[i] = r[1]; out.rz[i] = r[2];
       out.ux[i] = d[0]; out.uy[i] = d[1]; out.uz[i] = d[2];
-      out.w[i] = 1.0; out.G[i] = Gout; out.brood[i] = 0; out.seq[i] = 0;
+      out.w[i] = 1.0; out.G[i] = Gout; out.E[i] = 0.0; out.brood[i] = 0; out.seq[i] = 0;
       ok = true;
     }
     if (!ok) atomicMax(&cd->error, SB_ERR_SOURCE);
@@ -548,6 +549,8 @@ struct sb_engine {
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
   double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
   double* dStage = nullptr; size_t stageBytes = 0;
+  // continuous-energy transport model (sb_load_ce_model)
+  bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
   sbce::CeHost ce; int* dCeErr = nullptr; cudaEvent_t evC0 = nullptr, evC1 = nullptr; float ceLastMs = 0.f;
 };
 
@@ -557,11 +560,12 @@ static int allocBank(sb_engine* h, Bank& b, int cap) {
   CUDA_OK(cudaMalloc(&b.rx, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.ry, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.rz, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&b.ux, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.uy, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.uz, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&b.w, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&b.G, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&b.E, sizeof(double) * cap)); CUDA_OK(cudaMemset(b.E, 0, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&b.brood, sizeof(int) * cap)); CUDA_OK(cudaMalloc(&b.seq, sizeof(int) * cap));
   return 0;
 }
 static void freeBank(Bank& b) {
-  cudaFree(b.rx); cudaFree(b.ry); cudaFree(b.rz); cudaFree(b.ux); cudaFree(b.uy); cudaFree(b.uz); cudaFree(b.w); cudaFree(b.G); cudaFree(b.brood); cudaFree(b.seq);
+  cudaFree(b.rx); cudaFree(b.ry); cudaFree(b.rz); cudaFree(b.ux); cudaFree(b.uy); cudaFree(b.uz); cudaFree(b.w); cudaFree(b.G); cudaFree(b.E); cudaFree(b.brood); cudaFree(b.seq);
   b = Bank{};
 }
 
@@ -745,6 +749,14 @@ static int gridFor(sb_engine* h, long long n, int threads) {
   return (int)(b < cap ? b : cap);
 }
 
+template <typename T>
+static T* ceModelUpload(sb_engine* h, const std::vector<T>& v) {
+  T* p = nullptr;
+  if (cudaMalloc(&p, std::max<size_t>(sizeof(T) * v.size(), 16)) != cudaSuccess) { h->err = "cudaMalloc failed (CE model)"; return nullptr; }
+  if (!v.empty() && cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "cudaMemcpy failed (CE model)"; return nullptr; }
+  h->ceAllocs.push_back(p);
+  return p;
+}
 extern "C" {
 
 int sb_create(sb_engine** out, int device) {
@@ -945,6 +957,8 @@ static int checkDeviceError(sb_engine* h, int code) {
     case SB_ERR_NEST: msg = "Failed to find material cell (nesting exceeded)"; break;
     case SB_ERR_SOURCE: msg = "fissionSource: failed to find a fissile material in 10000 attempts"; break;
     case SB_ERR_NORM: msg = "Normalisation failed!"; break;
+    case SB_ERR_CE_ENERGY: msg = "Failed to find energy in the nuclide energy grids (particle energy outside the bounds of the CE data)"; break;
+    case SB_ERR_CE_DATA: msg = "Continuous-energy reaction data: a table search or a rejection loop failed"; break;
   }
   h->err = msg;
   return -1;
@@ -956,7 +970,8 @@ int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offs
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaMemsetAsync(h->dCd, 0, sizeof(CycleDev), h->stream));
   const double* b = h->bounds;
-  k_source<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, h->bank[h->cur], n, rng_state, history_offset, b[0], b[1], b[2], b[3], b[4], b[5], h->dCd);
+  if (h->ceMode) sbc::k_source_ce<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, h->ceModel, h->bank[h->cur], n, rng_state, history_offset, b[0], b[1], b[2], b[3], b[4], b[5], h->dCd);
+  else k_source<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, h->bank[h->cur], n, rng_state, history_offset, b[0], b[1], b[2], b[3], b[4], b[5], h->dCd);
   h->launches++;
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -994,7 +1009,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   if (needBlocks < blocks) blocks = needBlocks;
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
   bool useTrack = h->opt.tracking != SB_TRACK_DT;
-  if (h->opt.tracking == SB_TRACK_HT && !getenv("SB_FORCE_TRACK_KERNEL")) {
+  if (!h->ceMode && h->opt.tracking == SB_TRACK_HT && !getenv("SB_FORCE_TRACK_KERNEL")) {
     // transportOperatorHT picks delta tracking when Sigma_t / Sigma_maj > 1 - cutoff (transportOperatorHT_class.f90:63-78). If that
     // holds for every (material, group) of the model -- and nothing is void -- the selector is a constant and the flights
     // are exactly deltaTracking's: run the delta-tracking kernel.
@@ -1008,6 +1023,18 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
       }
     if (always) useTrack = false;
   }
+  if (h->ceMode) {                                            // continuous energy: sb_cehist.cuh
+    sbc::CeArgs t{};
+    t.M = h->M; t.blob = h->dBlob; t.ce = h->ceModel; t.seedTab = h->dSeedTab;
+    t.n = n; t.in = in; t.out = raw; t.cap = h->cap;
+    t.nsites = h->dNsites; t.hProd = h->dHProd; t.hAbs = h->dHAbs; t.hLeak = h->dHLeak; t.hScat = h->dHScat;
+    t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
+    t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
+    t.needMacro = 0;
+    for (const DClerk& k : h->clerks[phase]) for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1;
+    int tb = std::min(h->numSM * 4, (n + 127) / 128);
+    sbc::k_histories_ce<<<tb, 128, 0, st>>>(t);
+  } else
   if (useTrack) {                                             // surface / hybrid tracking: coordList-carrying kernel
     sbt::TrackArgs t{};
     t.M = h->M; t.blob = h->dBlob; t.useSmem = h->trackSmem; t.seedTab = h->dSeedTab;
@@ -1204,7 +1231,7 @@ int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_
 }
 
 // loadBalancing (particleDungeon_class.f90:607-698): sites leave from / arrive at the two ends of the bank
-size_t sb_site_buffer_bytes(int k) { return (size_t)k * (7 * sizeof(double) + sizeof(int32_t)) + 8; }
+size_t sb_site_buffer_bytes(int k) { return (size_t)k * (8 * sizeof(double) + sizeof(int32_t)) + 8; }
 int sb_bank_export(sb_engine* h, int k_front, void* dev_buf_front, int k_back, void* dev_buf_back) {
   CUDA_OK(cudaSetDevice(h->device));
   if (k_front < 0 || k_back < 0 || k_front + k_back > h->nCur) { h->err = "sb_bank_export: more sites requested than the bank holds"; return -1; }
@@ -1302,6 +1329,100 @@ int sb_load_ce_data(sb_engine* h, const sb_ce_flat* d) {
   CUDA_OK(cudaMemcpyAsync(h->ce.uMaj.data(), h->ce.dev.uMaj, sizeof(double) * h->ce.uMaj.size(), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// aceNeutronDatabase%init + activate for the eigenvalue driver (aceNeutronDatabase_class.f90:873-1163,1292-1328)
+int sb_load_ce_model(sb_engine* h, const sb_ce_model* m) {
+  CUDA_OK(cudaSetDevice(h->device));
+  h->err.clear();
+  if (!m || m->n_nuc < 1 || m->n_mat < 1 || !m->cards) { h->err = "sb_load_ce_model: invalid sizes"; return -1; }
+  for (void* p : h->ceAllocs) cudaFree(p);
+  h->ceAllocs.clear(); h->ceCards.assign(m->n_nuc, sbk::CardOut());
+  try {
+    for (int n = 0; n < m->n_nuc; ++n) sbk::ceProcessCard(m->cards[n], m->energy_per_fission, h->ceCards[n]);
+  } catch (const std::exception& e) { h->err = e.what(); return -1; }
+  // concatenated grids / main data for the lookup structures, concatenated tape + directory for the reactions
+  std::vector<int> gsize(m->n_nuc), rows(m->n_nuc); std::vector<double> grid, data, tape; std::vector<sbk::CeNucRec> recs(m->n_nuc); std::vector<sbk::CeMtRec> mts;
+  for (int n = 0; n < m->n_nuc; ++n) {
+    sbk::CardOut& c = h->ceCards[n];
+    gsize[n] = (int)c.grid.size(); rows[n] = c.rec.rows;
+    grid.insert(grid.end(), c.grid.begin(), c.grid.end()); data.insert(data.end(), c.main.begin(), c.main.end());
+    c.rec.base = (int)tape.size() - 1; c.rec.mtFirst = (int)mts.size();
+    tape.insert(tape.end(), c.tape.begin(), c.tape.end());
+    mts.insert(mts.end(), c.mt.begin(), c.mt.end());
+    recs[n] = c.rec;
+  }
+  sb_ce_flat f{}; f.n_nuc = m->n_nuc; f.grid_size = gsize.data(); f.rows = rows.data(); f.grid = grid.data(); f.data = data.data();
+  f.n_mat = m->n_mat; f.mat_off = m->mat_off; f.mat_nuc = m->mat_nuc; f.mat_dens = m->mat_dens;
+  std::vector<int> active(m->active_mats, m->active_mats + std::max(0, m->n_active));
+  if (active.empty()) { h->err = "sb_load_ce_model: no active material"; return -1; }
+  if (sbce::ceBuild(h->ce, &f, h->err, &active)) return -1;
+  sbce::k_ce_majorant<<<std::max(1, std::min((h->ce.dev.nUnion + 127) / 128, h->numSM * 8)), 128, 0, h->stream>>>(h->ce.dev, (double*)h->ce.dev.uMaj);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(h->ce.uMaj.data(), h->ce.dev.uMaj, sizeof(double) * h->ce.uMaj.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  sbc::CeModelDev& D = h->ceModel;
+  D.xs = h->ce.dev;
+  D.tape = ceModelUpload(h, tape); D.nuc = ceModelUpload(h, recs); D.mt = ceModelUpload(h, mts);
+  if (!D.tape || !D.nuc || !D.mt) return -1;
+  D.minE = m->min_energy; D.maxE = m->max_energy; D.threshE = m->thresh_energy; D.threshA = m->thresh_mass; D.sourceE = m->source_energy;
+  D.eLo = h->ce.dev.eMin; D.eHi = h->ce.dev.eMax;
+  if (!(D.minE >= 0.0) || !(D.maxE >= 0.0) || D.minE >= D.maxE || D.threshE < 0 || D.threshA < 0) { h->err = "sb_load_ce_model: invalid neutronCEstd settings (minEnergy / maxEnergy / thresholds)"; return -1; }
+  // the generic model blob carries the material count, fissile flags and collisionXS; no multigroup tables
+  h->nMat = m->n_mat; h->nG = 0; h->isP1 = 0; h->collisionXS = m->collision_xs;
+  h->xs.clear(); h->P0.clear(); h->prod.clear(); h->P1.clear(); h->chi.clear(); h->majorant.clear();
+  h->fissile.assign(m->n_mat, 0);
+  for (int i = 0; i < m->n_mat; ++i) for (int k = m->mat_off[i]; k < m->mat_off[i + 1]; ++k) if (recs[m->mat_nuc[k] - 1].fissile) h->fissile[i] = 1;
+  h->haveData = true; h->ceMode = true; h->blobDirty = true;
+  return 0;
+}
+int sb_ce_nuclide_info(sb_engine* h, int nuc_idx, int32_t* grid_size, int32_t* rows, int32_t* n_mt) {
+  if (nuc_idx < 1 || nuc_idx > (int)h->ceCards.size()) { h->err = "sb_ce_nuclide_info: invalid nuclide index"; return -1; }
+  const sbk::CardOut& c = h->ceCards[nuc_idx - 1];
+  *grid_size = (int)c.grid.size(); *rows = c.rec.rows; *n_mt = c.rec.nMT;
+  return 0;
+}
+int sb_ce_nuclide_data(sb_engine* h, int nuc_idx, double* grid, double* main_data, int32_t* mt_list) {
+  if (nuc_idx < 1 || nuc_idx > (int)h->ceCards.size()) { h->err = "sb_ce_nuclide_data: invalid nuclide index"; return -1; }
+  const sbk::CardOut& c = h->ceCards[nuc_idx - 1];
+  std::copy(c.grid.begin(), c.grid.end(), grid); std::copy(c.main.begin(), c.main.end(), main_data);
+  for (size_t i = 0; i < c.mt.size(); ++i) mt_list[i] = c.mt[i].MT;
+  return 0;
+}
+int sb_bank_upload_ce(sb_engine* h, int n, const double* r, const double* dir, const double* w, const double* E) {
+  if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ensureStage(h, sizeof(double) * 6 * (size_t)h->cap)) return -1;
+  Bank& b = h->bank[h->cur];
+  cudaStream_t st = h->stream;
+  CUDA_OK(cudaMemcpyAsync(h->dStage, r, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(h->dStage + 3 * (size_t)h->cap, dir, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(b.E, E, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(b.G, 0, sizeof(int) * n, st));
+  k_bank_unpack<<<gridFor(h, n, 256), 256, 0, st>>>(h->dStage, h->dStage + 3 * (size_t)h->cap, b, n);
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(st));
+  h->nCur = n;
+  return 0;
+}
+int sb_bank_download_ce(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, double* E) {
+  CUDA_OK(cudaSetDevice(h->device));
+  int m = h->nCur;
+  *n = m;
+  if (m > cap) { h->err = "sb_bank_download: buffer too small"; return -1; }
+  if (m == 0) return 0;
+  if (ensureStage(h, sizeof(double) * 6 * (size_t)h->cap)) return -1;
+  Bank& b = h->bank[h->cur];
+  cudaStream_t st = h->stream;
+  k_bank_pack<<<gridFor(h, m, 256), 256, 0, st>>>(b, h->dStage, h->dStage + 3 * (size_t)h->cap, m);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(r, h->dStage, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(dir, h->dStage + 3 * (size_t)h->cap, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(w, b.w, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(E, b.E, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
 int sb_ce_union_size(sb_engine* h) { return h->ce.loaded ? h->ce.dev.nUnion : 0; }

@@ -17,6 +17,8 @@
 #include "../../../include/scone_b200.h"
 #include "../sb_rng.h"
 #include "model.hpp"
+#include "ce_model.hpp"
+#include "../sb_cekin.cuh"
 
 namespace {
 
@@ -27,7 +29,7 @@ struct eigenPhysicsPackage {
   uint64_t pRNG = 0, masterRNG = 0;      // masterRNG: the pRNG of rank 0 (normSize_Repr draws from the master's stream)
   int rank = 0, nRanks = 1;
   int rankOffset = 0;                      // getOffset(totalPop) of this rank (mpi_func.f90:133-159)
-  sb::FlatGeometry geom; sb::FlatMgData data; sb::TallyDefs tallies[2];
+  sb::FlatGeometry geom; sb::FlatMgData data; sb::FlatCeData ceData; bool isCE = false; sb::TallyDefs tallies[2];
   sb_engine* eng = nullptr;
   std::string err;
   // results
@@ -35,7 +37,7 @@ struct eigenPhysicsPackage {
   long long nSegActive = 0, nSegInactive = 0, nHist = 0;
   double timeTransport = 0.0;
   // host copy of the bank for the end-to-end (host buffer) mode
-  double *hr = nullptr, *hdir = nullptr, *hw = nullptr; int32_t* hG = nullptr; int hN = 0, hCap = 0;   // page-locked
+  double *hr = nullptr, *hdir = nullptr, *hw = nullptr, *hE = nullptr; int32_t* hG = nullptr; int hN = 0, hCap = 0;   // page-locked
   std::vector<double> hBins;
 
   static std::string dirName(const std::string& p) { size_t k = p.rfind('/'); return k == std::string::npos ? "." : p.substr(0, k); }
@@ -64,16 +66,23 @@ struct eigenPhysicsPackage {
       rankOffset = totalPop / nRanks * rank + std::max(0, totalPop % nRanks + rank - nRanks);
       N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active");
       std::string nucData = dict.getWord("XSdata"), energy = dict.getWord("dataType");
-      if (energy != "mg") return fail("dataType must be 'mg' (the CE path is not on the device yet)");
+      if (energy != "mg" && energy != "ce") return fail("dataType must be 'mg' or 'ce'");
+      isCE = (energy == "ce");
       if (!dict.isPresent("seed")) return fail("an explicit `seed` is required for a reproducible run");
       pRNG = (uint64_t)(int64_t)dict.getInt("seed"); masterRNG = pRNG;
       keff_0 = dict.getReal("keff_0", 1.0);
       const sb::Dict& nd = dict.getDict("nuclearData");
       sb::MatMap mats = sb::materialMenu(nd);
       geom = sb::buildGeometry(dict.getDict("geometry"), mats);
-      data = sb::buildMgData(nd, nucData, dirName(deckPath), geom.activeMats());
       const sb::Dict& co = dict.getDict("collisionOperator");
-      if (!co.isPresent("neutronMG") || co.getDict("neutronMG").getWord("type") != "neutronMGstd") return fail("collisionOperator: neutronMGstd is required");
+      if (isCE) {
+        if (!co.isPresent("neutronCE")) return fail("collisionOperator: neutronCE { type neutronCEstd; } is required for dataType ce");
+        ceData = sb::buildCeData(nd, nucData, dirName(deckPath), geom.activeMats(), co);
+        data.nMat = ceData.nMat; data.nG = 0;
+      } else {
+        data = sb::buildMgData(nd, nucData, dirName(deckPath), geom.activeMats());
+        if (!co.isPresent("neutronMG") || co.getDict("neutronMG").getWord("type") != "neutronMGstd") return fail("collisionOperator: neutronMGstd is required");
+      }
       sb_options opt{}; opt.max_pop = pop; opt.ht_cutoff = 0.9; opt.st_cache = 1;
       const sb::Dict& to = dict.getDict("transportOperator");
       std::string tt = to.getWord("type");
@@ -88,7 +97,8 @@ struct eigenPhysicsPackage {
       if (device < 0) return 0;     // host model only (CPU-side tests of the flattening); no engine, no transport
       if (sb_create(&eng, device)) return fail(sb_last_error(nullptr));
       sb_geom_flat gv = geom.view(); if (sb_load_geometry(eng, &gv)) return engFail();
-      sb_mg_flat dv = data.view(); if (sb_load_mg_data(eng, &dv)) return engFail();
+      if (isCE) { sb_ce_model cv = ceData.view(); if (sb_load_ce_model(eng, &cv)) return engFail(); }
+      else { sb_mg_flat dv = data.view(); if (sb_load_mg_data(eng, &dv)) return engFail(); }
       for (int ph = 0; ph < 2; ++ph)
         if (sb_define_tallies(eng, ph, tallies[ph].clerks.data(), (int)tallies[ph].clerks.size(), tallies[ph].normClerk, tallies[ph].normVal)) return engFail();
       if (sb_set_options(eng, &opt)) return engFail();
@@ -162,7 +172,7 @@ struct eigenPhysicsPackage {
   int cycleHostBuffers(int active, double& k_new) {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (hN == 0) { if (downloadBank()) return -1; }
-    if (sb_bank_upload(eng, hN, hr, hdir, hw, hG)) return engFail();
+    if (isCE ? sb_bank_upload_ce(eng, hN, hr, hdir, hw, hE) : sb_bank_upload(eng, hN, hr, hdir, hw, hG)) return engFail();
     const uint64_t rng0 = pRNG;
     stride(totalPop + 1);
     if (sb_run_cycle_resample(eng, rng0, 0, k_new, active, pop, pRNG, &last)) return engFail();
@@ -179,13 +189,14 @@ struct eigenPhysicsPackage {
   int downloadBank() {
     int cap = 2 * pop + 1024;
     if (cap > hCap) {
-      sb_pinned_free(hr); sb_pinned_free(hdir); sb_pinned_free(hw); sb_pinned_free(hG);
+      sb_pinned_free(hr); sb_pinned_free(hdir); sb_pinned_free(hw); sb_pinned_free(hG); sb_pinned_free(hE);
       hr = (double*)sb_pinned_alloc(sizeof(double) * 3 * (size_t)cap); hdir = (double*)sb_pinned_alloc(sizeof(double) * 3 * (size_t)cap);
       hw = (double*)sb_pinned_alloc(sizeof(double) * (size_t)cap); hG = (int32_t*)sb_pinned_alloc(sizeof(int32_t) * (size_t)cap);
-      if (!hr || !hdir || !hw || !hG) return fail("pinned host allocation failed");
+      hE = (double*)sb_pinned_alloc(sizeof(double) * (size_t)cap);
+      if (!hr || !hdir || !hw || !hG || !hE) return fail("pinned host allocation failed");
       hCap = cap;
     }
-    if (sb_bank_download(eng, cap, &hN, hr, hdir, hw, hG)) return engFail();
+    if (isCE ? sb_bank_download_ce(eng, cap, &hN, hr, hdir, hw, hE) : sb_bank_download(eng, cap, &hN, hr, hdir, hw, hG)) return engFail();
     return 0;
   }
 
@@ -215,7 +226,7 @@ void* sbh_eigen_create(const char* deckPath, const char* overrides, int device, 
 }
 void sbh_eigen_destroy(void* pv) {
   auto* p = (eigenPhysicsPackage*)pv; if (!p) return;
-  sb_pinned_free(p->hr); sb_pinned_free(p->hdir); sb_pinned_free(p->hw); sb_pinned_free(p->hG);
+  sb_pinned_free(p->hr); sb_pinned_free(p->hdir); sb_pinned_free(p->hw); sb_pinned_free(p->hG); sb_pinned_free(p->hE);
   if (p->eng) sb_destroy(p->eng);
   delete p;
 }
@@ -274,9 +285,32 @@ int sbh_eigen_download_bank(void* pv) { return ((eigenPhysicsPackage*)pv)->downl
 int sbh_eigen_upload_bank(void* pv) {
   auto* p = (eigenPhysicsPackage*)pv;
   if (p->hN == 0 && p->downloadBank()) return -1;
-  if (sb_bank_upload(p->eng, p->hN, p->hr, p->hdir, p->hw, p->hG)) return p->engFail();
+  if (p->isCE ? sb_bank_upload_ce(p->eng, p->hN, p->hr, p->hdir, p->hw, p->hE) : sb_bank_upload(p->eng, p->hN, p->hr, p->hdir, p->hw, p->hG)) return p->engFail();
   return 0;
 }
+// the page-locked host copy of the bank (after sbh_eigen_download_bank): n, then pointers to r(3,n), dir(3,n), w(n), G(n), E(n)
+int sbh_eigen_host_bank(void* pv, int* n, double** r, double** dir, double** w, int32_t** G, double** E) {
+  auto* p = (eigenPhysicsPackage*)pv; *n = p->hN; *r = p->hr; *dir = p->hdir; *w = p->hw; *G = p->hG; *E = p->hE; return 0;
+}
+// continuous-energy decks: what the engine builds from card `nuc` (1-based) of the deck, computed on the host (no device needed):
+// sizes first (grid == NULL), then eGrid(N), mainData(rows, N) and the MT numbers in invertInelastic order
+int sbh_ce_card_process(void* pv, int nuc, int* gridSize, int* rows, int* nMT, double* grid, double* mainData, int* mtList, double* awr_kT) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  if (!p->isCE || nuc < 1 || nuc > (int)p->ceData.cards.size()) { p->err = "sbh_ce_card_process: not a continuous-energy deck or invalid nuclide index"; return -1; }
+  try {
+    sbk::CardOut out; sb_ace_card c = p->ceData.cards[nuc - 1].view();
+    sbk::ceProcessCard(c, p->ceData.energyPerFission, out);
+    *gridSize = (int)out.grid.size(); *rows = out.rec.rows; *nMT = out.rec.nMT;
+    if (grid) {
+      std::copy(out.grid.begin(), out.grid.end(), grid); std::copy(out.main.begin(), out.main.end(), mainData);
+      for (size_t i = 0; i < out.mt.size(); ++i) mtList[i] = out.mt[i].MT;
+      awr_kT[0] = out.rec.awr; awr_kT[1] = out.rec.kT;
+    }
+  } catch (const std::exception& e) { p->err = e.what(); return -1; }
+  return 0;
+}
+int sbh_ce_info(void* pv, int* nNuc, int* nMat) { auto* p = (eigenPhysicsPackage*)pv; *nNuc = (int)p->ceData.cards.size(); *nMat = p->ceData.nMat; return 0; }
+int sbh_eigen_is_ce(void* pv) { return ((eigenPhysicsPackage*)pv)->isCE ? 1 : 0; }
 int sbh_eigen_cycles(void* pv, int active, int N) { return ((eigenPhysicsPackage*)pv)->cycles(active, N); }
 int sbh_eigen_run(void* pv) { return ((eigenPhysicsPackage*)pv)->run(); }
 int sbh_eigen_stats(void* pv, long long* segInactive, long long* segActive, long long* hist, double* tTransport) {
@@ -285,7 +319,7 @@ int sbh_eigen_stats(void* pv, long long* segInactive, long long* segActive, long
 // bytes moved per host-buffer cycle: bank up (pop sites) + bank down (pop sites) + bins
 int sbh_eigen_host_bytes(void* pv, int active, long long* h2d, long long* d2h) {
   auto* p = (eigenPhysicsPackage*)pv;
-  long long site = 3 * 8 + 3 * 8 + 8 + 4;
+  long long site = 3 * 8 + 3 * 8 + 8 + (p->isCE ? 8 : 4);
   *h2d = site * p->pop; *d2h = site * p->pop + 8 * (long long)sb_tally_size(p->eng, active) + (long long)sizeof(sb_cycle_result);
   return 0;
 }

@@ -41,6 +41,7 @@ struct CeDev {                                    // device pointers + sizes, pa
   const int* matOff; const int* matNuc; const double* matDens;
   const double* uGrid; const double* uMaj; const int* idxTab; const int* bucketStart;
   const double* pairTot; const long long* pairOff;      // per nuclide and grid interval: { E_low, E_top, total_low, total_top }, 32-byte aligned
+  const int* activeMat; int nActive;                    // materials the majorant covers (nuclearDatabase%activate: those present in the geometry)
   double eMin, eMax;
 };
 
@@ -91,7 +92,7 @@ __global__ void k_ce_majorant(const CeDev c, double* uMaj) {
     const double e = c.uGrid[j];
     const int u = j + 1;
     double maj = 0.0;
-    for (int m = 1; m <= c.nMat; ++m) maj = fmax(maj, matTotal(c, u, e, m));
+    for (int a = 0; a < c.nActive; ++a) maj = fmax(maj, matTotal(c, u, e, __ldg(c.activeMat + a)));
     uMaj[j] = maj * (1.0 + 1.0e-06);
   }
 }
@@ -178,7 +179,7 @@ static T* ceUpload(CeHost& H, const std::vector<T>& v, std::string& err) {
 }
 static void ceFree(CeHost& H) { for (void* p : H.allocs) cudaFree(p); H.allocs.clear(); H.loaded = false; }
 
-static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err) {
+static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err, const std::vector<int>* activeIn = nullptr) {
   ceFree(H);
   if (f->n_nuc < 1 || f->n_mat < 1) { err = "sb_load_ce_data: invalid sizes"; return -1; }
   const int nNuc = f->n_nuc, nMat = f->n_mat;
@@ -204,7 +205,10 @@ static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err) {
   // energy bounds of the database (aceNeutronDatabase_class.f90:1044-1051) and the unionised grid (initMajorant)
   double eMin = grid[gridOff[0]], eMax = grid[gridOff[0] + gsize[0] - 1];
   for (int n = 0; n < nNuc; ++n) { eMin = std::max(eMin, grid[gridOff[n]]); eMax = std::min(eMax, grid[gridOff[n] + gsize[n] - 1]); }
-  std::vector<char> used(nNuc, 0); for (int v : matNuc) used[v - 1] = 1;
+  std::vector<int> active;
+  if (activeIn) active = *activeIn; else for (int m = 1; m <= nMat; ++m) active.push_back(m);
+  for (int m : active) if (m < 1 || m > nMat) { err = "sb_load_ce: active material index out of range"; return -1; }
+  std::vector<char> used(nNuc, 0); for (int m : active) for (int k = matOff[m - 1]; k < matOff[m]; ++k) used[matNuc[k] - 1] = 1;
   std::vector<double> u;
   for (int n = 0; n < nNuc; ++n) if (used[n]) for (int i = 0; i < gsize[n]; ++i) { double e = grid[gridOff[n] + i]; if (!(e < eMin || e > eMax)) u.push_back(e); }
   std::sort(u.begin(), u.end()); u.erase(std::unique(u.begin(), u.end()), u.end());
@@ -242,6 +246,7 @@ static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err) {
   d.rows = ceUpload(H, rows, err); d.gridSize = ceUpload(H, gsize, err);
   d.matOff = ceUpload(H, matOff, err); d.matNuc = ceUpload(H, matNuc, err); d.matDens = ceUpload(H, matDens, err);
   d.pairTot = ceUpload(H, pairTot, err); d.pairOff = ceUpload(H, pairOff, err);
+  d.activeMat = ceUpload(H, active, err); d.nActive = (int)active.size();
   d.uGrid = ceUpload(H, u, err); d.uMaj = ceUpload(H, H.uMaj, err); d.idxTab = ceUpload(H, idxTab, err); d.bucketStart = ceUpload(H, bucketStart, err);
   if (!err.empty()) return -1;
   H.nNuc = nNuc; H.nMat = nMat; H.loaded = true;

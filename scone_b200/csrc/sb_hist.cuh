@@ -47,6 +47,7 @@ struct HotLayout {
 
 struct Bank {            // particleDungeon as structure of arrays
   double *rx, *ry, *rz, *ux, *uy, *uz, *w;
+  double* E;               // continuous-energy runs: particle energy [MeV] (MG runs carry G)
   int *G, *brood, *seq;
 };
 

@@ -39,7 +39,7 @@ def balance_plan(tot_pop, n_ranks, rank, pop_sizes):
     return tuple(int(x) for x in out)
 
 
-SITE_BYTES = 7 * 8 + 4
+SITE_BYTES = 8 * 8 + 4      # r, dir, w, E (f64) + G (i32), as sb_site_buffer_bytes
 
 
 def site_buffer_bytes(k):

@@ -42,6 +42,8 @@ def load_library():
         "sb_load_geometry": (i32, [vp, vp]), "sb_load_mg_data": (i32, [vp, vp]),
         "sb_define_tallies": (i32, [vp, i32, vp, i32, i32, dbl]), "sb_set_options": (i32, [vp, vp]),
         "sb_bank_upload": (i32, [vp, i32, dp, dp, dp, ip]), "sb_bank_download": (i32, [vp, i32, ip, dp, dp, dp, ip]),
+        "sb_bank_upload_ce": (i32, [vp, i32, dp, dp, dp, dp]), "sb_bank_download_ce": (i32, [vp, i32, ip, dp, dp, dp, dp]),
+        "sb_load_ce_model": (i32, [vp, vp]), "sb_ce_nuclide_info": (i32, [vp, i32, ip, ip, ip]), "sb_ce_nuclide_data": (i32, [vp, i32, dp, dp, ip]),
         "sb_bank_size": (i32, [vp]), "sb_source_generate": (i32, [vp, i32, u64, i32]),
         "sb_run_cycle": (i32, [vp, u64, i32, dbl, i32, C.POINTER(CycleResult)]),
         "sb_resample": (i32, [vp, i32, u64]),
@@ -75,6 +77,8 @@ def load_library():
         "sbh_eigen_cycle_end_resample_ranked": (i32, [vp, i32, dp, ip, ip, dp, C.POINTER(CycleResult)]),
         "sbh_workshare": (i32, [i32, i32, i32, ip, ip]), "sbh_balance_plan": (i32, [i32, i32, i32, ip, ip]),
         "sbh_eigen_download_bank": (i32, [vp]), "sbh_eigen_upload_bank": (i32, [vp]),
+        "sbh_eigen_is_ce": (i32, [vp]), "sbh_ce_info": (i32, [vp, ip, ip]),
+        "sbh_ce_card_process": (i32, [vp, i32, ip, ip, ip, dp, dp, ip, dp]),
         "sbh_eigen_cycles": (i32, [vp, i32, i32]), "sbh_eigen_run": (i32, [vp]),
         "sbh_eigen_stats": (i32, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp]),
         "sbh_eigen_host_bytes": (i32, [vp, i32, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

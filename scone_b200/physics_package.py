@@ -146,10 +146,22 @@ class EigenPhysicsPackage(_Base):
     def rng_state(self, s):
         self.L.sbh_eigen_set_rng_state(self.h, s)
 
+    @property
+    def is_ce(self):
+        return bool(self.L.sbh_eigen_is_ce(self.h))
+
     def bank(self):
+        """The current bank: (r, dir, w, G) for multigroup decks, (r, dir, w, E) for continuous-energy decks."""
         cap = 2 * self.pop + 1024
         n = C.c_int32()
-        r = np.zeros((cap, 3)); d = np.zeros((cap, 3)); w = np.zeros(cap); G = np.zeros(cap, np.int32)
+        r = np.zeros((cap, 3)); d = np.zeros((cap, 3)); w = np.zeros(cap)
+        if self.is_ce:
+            E = np.zeros(cap)
+            if self.L.sb_bank_download_ce(self.engine, cap, C.byref(n), _dp(r), _dp(d), _dp(w), _dp(E)) != 0:
+                raise EngineError(self._eng_err())
+            m = n.value
+            return r[:m], d[:m], w[:m], E[:m]
+        G = np.zeros(cap, np.int32)
         if self.L.sb_bank_download(self.engine, cap, C.byref(n), _dp(r), _dp(d), _dp(w), _ip(G)) != 0:
             raise EngineError(self._eng_err())
         m = n.value

@@ -18,7 +18,7 @@ c_ip = C.POINTER(C.c_int)
 
 
 def build():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("capi.cpp", "cedata.hpp", "physics.hpp", "geom.hpp", "mgdata.hpp", "rng.hpp")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("capi.cpp", "cedata.hpp", "ceace.hpp", "cereact.hpp", "cephysics.hpp", "mathmode.hpp", "physics.hpp", "geom.hpp", "mgdata.hpp", "rng.hpp")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "all"])
@@ -125,6 +125,13 @@ def load():
         "orc_ce_db_union": (i32, [vp, c_dp, c_dp]), "orc_ce_db_total_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]),
         "orc_ce_db_macro_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]), "orc_ce_db_majorant_n": (i32, [vp, C.c_long, c_dp, c_dp]),
         "orc_ce_db_index_n": (i32, [vp, i32, C.c_long, c_dp, c_ip]),
+        "orc_eigen_bank_E": (i32, [vp, c_dp]),
+        "orc_tabpdf_sample": (dbl, [i32, c_dp, c_dp, c_dp, i32, dbl]),
+        "orc_endftable_at": (dbl, [i32, c_dp, c_dp, i32, c_ip, c_ip, dbl]),
+        "orc_ce_nuclide_from_acebin": (vp, [C.c_char_p]), "orc_ce_nuclide_mt_list": (i32, [vp, c_ip, c_ip]),
+        "orc_ce_nuclide_sample": (C.c_long, [vp, i32, i32, dbl, u64, c_dp]),
+        "orc_ce_nuclide_invert_inelastic": (i32, [vp, dbl, u64]),
+        "orc_ce_nuclide_mt_release": (dbl, [vp, i32, dbl]), "orc_ce_nuclide_mt_cm": (i32, [vp, i32]),
     })
     for name, (res, args) in sig.items():
         f = getattr(L, name)

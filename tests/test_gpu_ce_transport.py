@@ -1,0 +1,125 @@
+"""GPU parity of the continuous-energy history kernel (scone_b200/csrc/sb_cehist.cuh + sb_cekin.cuh) against the CPU oracle
+(oracle/cephysics.hpp) on the authored CE pin cell: with both sides on the shared deterministic log/sin/cos every history
+draws the reference's random stream and the comparison is EXACT -- source sites, fission bank after every cycle (positions,
+directions, energies, order), segment counts -- and k-eff / tally bins agree to summation-order rounding.
+Delta, surface (cached and uncached) and hybrid tracking."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import scone_b200
+from tests import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECK = os.path.join(ROOT, "decks", "ce", "pincell")
+
+
+def oracle_bank(orc, e):
+    n = orc.orc_eigen_bank_size(e)
+    r = np.zeros((n, 3)); d = np.zeros((n, 3)); w = np.zeros(n); G = np.zeros(n, np.int32); b = np.zeros(n, np.int32); E = np.zeros(n)
+    orc.orc_eigen_bank(e, ol.dp(r), ol.dp(d), ol.dp(w), ol.ip(G), ol.ip(b))
+    orc.orc_eigen_bank_E(e, ol.dp(E))
+    return r, d, w, E
+
+
+@pytest.mark.parametrize("pop,ninact,nact,tracking", [
+    (3000, 2, 2, "transportOperator { type transportOperatorST; cache 1; }"),
+    (2000, 1, 1, "transportOperator { type transportOperatorST; cache 0; }"),
+    (3000, 2, 2, "transportOperator { type transportOperatorDT; }"),
+    (2000, 1, 2, "transportOperator { type transportOperatorHT; cutoff 0.9; }"),
+    (2000, 1, 1, "transportOperator { type transportOperatorHT; cutoff 0.3; }")])
+def test_ce_cycles_bit_exact_against_oracle(orc, pop, ninact, nact, tracking):
+    ov = "pop %d; inactive %d; active %d; seed 20261017; %s" % (pop, ninact, nact, tracking)
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(DECK.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(DECK, ov, device=0)
+        assert pp.is_ce
+        assert orc.orc_eigen_init_source(e) == 0, ol.err(orc)
+        pp.generateInitialState()
+        assert pp.rng_state == orc.orc_eigen_rng_state(e)
+        for a, b in zip(pp.bank(), oracle_bank(orc, e)):
+            assert np.array_equal(a, b)                    # fissionSource, CE branch: bit-identical sites and energies
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(ninact + nact):
+            active = cyc >= ninact
+            res = pp.cycle(active)
+            k_o = orc.orc_eigen_cycle(e, 1 if active else 0, k_o)
+            assert not np.isnan(k_o), ol.err(orc)
+            assert pp.rng_state == orc.orc_eigen_rng_state(e)
+            gb = pp.bank(); ob = oracle_bank(orc, e)
+            assert len(gb[2]) == len(ob[2]) == pop
+            for a, b, what in zip(gb, ob, ("r", "dir", "w", "E")):
+                assert np.array_equal(a, b), "fission bank (%s) differs after cycle %d" % (what, cyc)
+            assert pp.k == pytest.approx(k_o, rel=1e-11)
+        n = orc.orc_eigen_tally_size(e, 1)
+        cs, cs2, nb = pp.tally(True)
+        assert len(cs) == n == 1 + 600
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        assert nb == b.value == nact
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+        assert cs[0] > 0 and cs[1:].sum() > 0 and np.count_nonzero(cs[1:]) > 100     # energy x material flux spectrum is populated
+        seg, coll, hist = C.c_long(), C.c_long(), C.c_long()
+        orc.orc_eigen_stats(e, C.byref(seg), C.byref(coll), C.byref(hist))
+        st = pp.stats()
+        assert st["seg_inactive"] + st["seg_active"] == seg.value
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
+
+
+def test_ce_nuclides_on_engine_match_oracle(orc):
+    """What sb_load_ce_model built (energy grids, main data, MT order) is what the oracle builds from the same cards."""
+    pp = scone_b200.EigenPhysicsPackage(DECK, "pop 100;", device=0)
+    L = pp.L
+    ace = os.path.join(ROOT, "tests", "golden", "ace")
+    for i, name in enumerate(["92233JEF311", "52126JEF311", "91231JEF311", "91232JEF311", "1001JEF311"], start=1):
+        gs, rows, nmt = C.c_int32(), C.c_int32(), C.c_int32()
+        assert L.sb_ce_nuclide_info(pp.engine, i, C.byref(gs), C.byref(rows), C.byref(nmt)) == 0
+        g = np.zeros(gs.value); d = np.zeros(gs.value * rows.value); mt = np.zeros(max(1, nmt.value), np.int32)
+        assert L.sb_ce_nuclide_data(pp.engine, i, ol.dp(g), ol.dp(d), mt.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        h = orc.orc_ce_nuclide_from_acebin(os.path.join(ace, name + ".acebin").encode())
+        n, r, m, kT = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        orc.orc_ce_nuclide_info(h, C.byref(n), C.byref(r), C.byref(m), C.byref(kT))
+        og = np.zeros(n.value); od = np.zeros(n.value * r.value)
+        orc.orc_ce_nuclide_data(h, ol.dp(og), ol.dp(od))
+        assert np.array_equal(og, g) and np.array_equal(od, d)
+        orc.orc_ce_nuclide_free(h)
+    pp.close()
+
+
+def test_ce_host_buffer_cycle_equals_device_resident_cycle():
+    ov = "pop 4000; inactive 1; active 2; seed 5;"
+    a = scone_b200.EigenPhysicsPackage(DECK, ov, device=0)
+    b = scone_b200.EigenPhysicsPackage(DECK, ov, device=0)
+    a.generateInitialState(); b.generateInitialState()
+    for cyc in range(3):
+        a.cycle(cyc >= 1); b.cycle(cyc >= 1, host_buffers=True)
+        assert a.k == b.k
+        for x, y in zip(a.bank(), b.bank()):
+            assert np.array_equal(x, y)
+    a.close(); b.close()
+
+
+def test_ce_statistics_against_oracle_libm(orc):
+    """Larger population, independent seeds, glibc math in the oracle: k-eff within 3 combined sigma."""
+    pp = scone_b200.EigenPhysicsPackage(DECK, "pop 40000; inactive 10; active 20; seed 31;", device=0)
+    pp.generateInitialState(); pp.cycles(False, 10)
+    res = pp.cycles(True, 20)
+    r, d, w, E = pp.bank()
+    assert len(w) == 40000 and np.all(E > 0) and np.all(E <= 20.0)
+    np.testing.assert_allclose((d * d).sum(1), 1.0, rtol=1e-12)
+    e = orc.orc_eigen_load(DECK.encode(), b"pop 8000; inactive 10; active 30; seed 4242;")
+    assert orc.orc_eigen_run(e) == 0, ol.err(orc)
+    cs = np.zeros(5); cs2 = np.zeros(5); b = C.c_int()
+    orc.orc_eigen_tally(e, 3, ol.dp(cs), ol.dp(cs2), C.byref(b))
+    n = b.value; k_o = cs[4] / n
+    s_o = np.sqrt(max(cs2[4] / n / (n - 1) - k_o * k_o / (n - 1), 0.0))
+    assert abs(pp.k - k_o) < 3.0 * np.sqrt(res.k_cum_std ** 2 + s_o ** 2) + 1e-4
+    orc.orc_eigen_free(e); pp.close()
