@@ -26,10 +26,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DECKS = {"c5g7": "decks/c5g7/c5g7_2d", "c5g7_3d": "decks/c5g7/c5g7_3d_rodded", "inf": "decks/urr/inf", "slab": "decks/urr/slab"}
+DECKS = {"c5g7": "decks/c5g7/c5g7_2d", "c5g7_3d": "decks/c5g7/c5g7_3d_rodded", "inf": "decks/urr/inf", "slab": "decks/urr/slab",
+         "ce_pin": "decks/ce/pincell"}
 WORKLOAD = {"c5g7": "C5G7 MOX 2D 7-group eigenvalue, delta tracking (InputFiles/Benchmarks/Multigroup/C5G7 as decks/c5g7/c5g7_2d)",
             "c5g7_3d": "C5G7 3D rodded-A 7-group eigenvalue with 34x34x9 flux+fission mesh, delta tracking",
-            "inf": "SCONE_Inf URRa-2-1-IN 2-group infinite medium", "slab": "SCONE_Slab URRa-2-1-SL 2-group slab (P1)"}
+            "inf": "SCONE_Inf URRa-2-1-IN 2-group infinite medium", "slab": "SCONE_Slab URRa-2-1-SL 2-group slab (P1)",
+            "ce_pin": "continuous-energy U-233 / H-1 pin cell from the reference's bundled ACE nuclides (BASELINE configs[2] stand-in), 300-bin energy x material flux tally"}
 ALG_BYTES_PER_SEGMENT = 124      # particle SoA read+write per flight segment
 ALG_BYTES_PER_SCORE = 16         # f64 read-modify-write per tally score
 
@@ -70,12 +72,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def oracle_rate(deck, pop, n_inactive, seconds, threads, tracking="DT"):
+def tracking_override(tracking):
+    return "" if not tracking else " transportOperator { type transportOperator%s; }" % tracking
+
+
+def oracle_rate(deck, pop, n_inactive, seconds, threads, tracking=None):
     """CPU arm: oracle (C++ restatement of SCONE's OpenMP loop) active-cycle neutrons/s on `threads` threads."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from tests import oracle_lib as ol
     orc = ol.load()
-    ov = "pop %d; inactive %d; active 1000000; seed 20261017; transportOperator { type transportOperator%s; }" % (pop, n_inactive, tracking)
+    ov = "pop %d; inactive %d; active 1000000; seed 20261017;%s" % (pop, n_inactive, tracking_override(tracking))
     e = orc.orc_eigen_load(os.path.join(ROOT, deck).encode(), ov.encode())
     if not e:
         raise RuntimeError(ol.err(orc))
@@ -171,7 +177,7 @@ def run_reference(args, rank, world):
     orc = ol.load()
     deck = DECKS[args.deck]
     pop = args.pop
-    ov = "pop %d; inactive %d; active 1000000; seed 20261017; transportOperator { type transportOperator%s; }" % (pop, args.inactive, args.tracking)
+    ov = "pop %d; inactive %d; active 1000000; seed 20261017;%s" % (pop, args.inactive, tracking_override(args.tracking))
     e = orc.orc_eigen_load(os.path.join(ROOT, deck).encode(), ov.encode())
     if not e:
         raise RuntimeError(ol.err(orc))
@@ -194,7 +200,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "active-cycle neutrons/s", "value": val, "unit": "neutrons/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking,
+        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck == "ce_pin" else "DT"),
                    "note": "CPU reference arm: one step = one active cycle of pop histories on the host cores"},
         "segments_per_s": (s1.value - s0.value) / dt, "keff": k,
         "cpu_baseline": {"value": val, "unit": "neutrons/s", "cores": threads, "kind": "port",
@@ -214,7 +220,7 @@ def main():
     ap.add_argument("--deck", default="c5g7", choices=sorted(DECKS))
     ap.add_argument("--pop", type=int, default=100000, help="histories per cycle PER GPU (weak scaling)")
     ap.add_argument("--inactive", type=int, default=10, help="untimed inactive cycles before the active phase")
-    ap.add_argument("--tracking", default="DT", choices=["DT", "ST", "HT"], help="transportOperator (the shipped C5G7 deck uses HT, BASELINE configs[0] names delta tracking)")
+    ap.add_argument("--tracking", default=None, choices=["DT", "ST", "HT"], help="transportOperator; default: what the deck says (delta tracking for the MG decks as BASELINE configs[0] names it, surface tracking with cache for the CE pin cell)")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,8 +245,8 @@ def main():
     deck = os.path.join(ROOT, DECKS[args.deck])
     pop = args.pop
     total_pop = pop * world
-    ov = "pop %d; inactive %d; active %d; seed 20261017; transportOperator { type transportOperator%s; }" % (
-        total_pop, args.inactive, args.warmup + 2 * args.steps + 4, args.tracking)
+    ov = "pop %d; inactive %d; active %d; seed 20261017;%s" % (
+        total_pop, args.inactive, args.warmup + 2 * args.steps + 4, tracking_override(args.tracking))
     sampler = ClockSampler(local); sampler.start()
     pp = scone_b200.EigenPhysicsPackage(deck, ov, device=local, rank=rank, n_ranks=world)
     comm = scone_b200.distributed.TorchComm(device=torch.device("cuda", local)) if world > 1 else None
@@ -318,10 +324,11 @@ def main():
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_histories_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(("k_histories_ce" if args.deck == "ce_pin" else "k_histories") + "_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_histories", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    kname = "k_histories_ce" if args.deck == "ce_pin" else ("k_histories" if args.tracking in (None, "DT") else "k_histories_track")
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,
                 "note": "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)"}
@@ -330,7 +337,7 @@ def main():
     large = None; ce = None
     if world == 1 and not args.no_extras:
         pp.close()
-        ov2 = "pop %d; inactive 6; active 100; seed 20261017; transportOperator { type transportOperator%s; }" % (args.large_pop, args.tracking)
+        ov2 = "pop %d; inactive 6; active 100; seed 20261017;%s" % (args.large_pop, tracking_override(args.tracking))
         pl = scone_b200.EigenPhysicsPackage(deck, ov2, device=local)
         pl.generateInitialState(); pl.cycles(False, 6)
         for _ in range(3):
@@ -362,7 +369,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD[args.deck], "deck": DECKS[args.deck], "pop_per_cycle_per_gpu": pop, "pop_per_cycle_total": total_pop,
-                       "tracking": args.tracking, "inactive_cycles_before": args.inactive,
+                       "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck == "ce_pin" else "DT"), "inactive_cycles_before": args.inactive,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
                        "parallelism": "bank sharded by history index over %d GPU(s)%s" % (
                            world, "; per cycle: all-reduce of 6 f64 k-eff sums, 2 all-gathers of one int, neighbour send/recv of boundary sites (NCCL)" if world > 1 else "")},

@@ -1032,8 +1032,10 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
     t.needMacro = 0;
     for (const DClerk& k : h->clerks[phase]) for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1;
-    int tb = std::min(h->numSM * 4, (n + 127) / 128);
-    sbc::k_histories_ce<<<tb, 128, 0, st>>>(t);
+    const char* cfg = getenv("SB_CE_KERNEL");                  // experiment switch: "async" = 128-thread CTAs without phase barriers
+    if (cfg && !strcmp(cfg, "async")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, 0, st>>>(t);
+    else if (cfg && !strcmp(cfg, "sync256")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM * 2, (n + 255) / 256), 256, 0, st>>>(t);
+    else sbc::k_histories_ce<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, 0, st>>>(t);
   } else
   if (useTrack) {                                             // surface / hybrid tracking: coordList-carrying kernel
     sbt::TrackArgs t{};

@@ -63,7 +63,7 @@ __device__ inline void nucMicro(const NucPoint& p, double xs[8]) {              
 #pragma unroll
   for (int r = 0; r < 8; ++r) xs[r] = (r < p.rows) ? nucRow(p, r + 1) : 0.0;
 }
-__device__ inline void matMacro(const sbce::CeDev& c, int u, double e, int m, double xs[8]) {         // updateMacroXSs + neutronMacroXSs%add
+__device__ __noinline__ void matMacro(const sbce::CeDev& c, int u, double e, int m, double xs[8]) {         // updateMacroXSs + neutronMacroXSs%add
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
 #pragma unroll
   for (int r = 0; r < 8; ++r) xs[r] = 0.0;
@@ -110,7 +110,7 @@ __device__ inline int clerkBinCE(const DClerk& c, const char* blob, const double
       const int* mb = (const int*)(blob + c.mapOff[i]);
       b = (mat >= 1 && mat <= c.mapGrid[i]) ? mb[mat - 1] : c.mapDef[i];
     } else if (c.mapGrid[i] == SB_GRID_LOG) {                                                          // grid_class.f90:154-176, logarithmic
-      b = (int)floor(sbm::log(E / c.mapFirst[i]) / c.mapStep[i]) + 1;
+      b = (int)floor(sbk::kLog(E / c.mapFirst[i]) / c.mapStep[i]) + 1;
       if (b < 1 || b >= c.mapN[i] + 1) b = 0;
     } else b = gridSearch(c.mapGrid[i], c.mapFirst[i], c.mapStep[i], c.mapN[i], (const double*)(blob + c.mapOff[i]), E);
     if (b == 0) return 0;
@@ -119,7 +119,7 @@ __device__ inline int clerkBinCE(const DClerk& c, const char* blob, const double
   return idx;
 }
 // tallyAdmin%reportInColl for a CE particle
-__device__ inline void scoreInCollCE(const CeArgs& a, const char* base, const double r[3], int mat, double E, int u,
+__device__ __noinline__ void scoreInCollCE(const CeArgs& a, const char* base, const double r[3], int mat, double E, int u,
                                      double w, double trackXS, double sigmaTot, bool virt, double& sProd, double& sAbs, unsigned& nScore) {
   const bool isVoid = (mat == SB_VOID_MAT);
   const int nC = a.M.nClerk[a.phase];
@@ -148,6 +148,9 @@ __device__ inline void scoreInCollCE(const CeArgs& a, const char* base, const do
   }
 }
 
+__device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e, int m) { return sbce::matTotal(c, u, e, m); }
+__device__ __noinline__ void ceRotate(double d[3], double mu, double phi) { rotateVector(d, mu, phi); }
+
 // ---- scattering kernels (scatteringKernels_func.f90) ---------------------------------------------------------------------
 __device__ __forceinline__ void asymptoticScatter(double& E, double& mu, double A) {
   const double E_in = E, inv_Ap1 = 1.0 / (A + 1.0);
@@ -162,19 +165,19 @@ __device__ __forceinline__ void asymptoticInelasticScatter(double& E, double& mu
   if (mu > 1.0) mu = 1.0;
 }
 // targetVelocity_constXS: returns X (speed in units of sqrt(kT/A)) and mu of the target; the rejection loop is the reference's
-__device__ inline void sampleTargetVelocity(double Y, uint64_t& rng, double& X, double& mu) {
+__device__ __noinline__ void sampleTargetVelocity(double Y, uint64_t& rng, double& X, double& mu) {
   const double alpha = 2.0 / (Y * sbk::SQRT_PI + 2.0);
   for (;;) {
     const double r1 = rngGet(rng), r2 = rngGet(rng), r3 = rngGet(rng);
     if (r1 > alpha) {                                                                                  // sample_x2expx2
       const double q1 = rngGet(rng), q2 = rngGet(rng), q3 = rngGet(rng);
-      double s, c; sbm::sincos(0.5 * sbk::PI * q1, &s, &c);
+      double s, c; sbk::kSinCos(0.5 * sbk::PI * q1, &s, &c);
       const double beta = c * c;
-      const double gamma05 = -sbm::log(q2) * beta;
-      X = sqrt(-sbm::log(q3) + gamma05);
+      const double gamma05 = -sbk::kLog(q2) * beta;
+      X = sqrt(-sbk::kLog(q3) + gamma05);
     } else {                                                                                           // sample_x3expx2
       const double q1 = rngGet(rng), q2 = rngGet(rng);
-      X = sqrt(-sbm::log(q1) - sbm::log(q2));
+      X = sqrt(-sbk::kLog(q1) - sbk::kLog(q2));
     }
     mu = 2.0 * r2 - 1.0;
     const double rel_v = sqrt(Y * Y + X * X - 2.0 * X * Y * mu);
@@ -223,7 +226,7 @@ __global__ void k_source_ce(const Model M, const char* blob, const CeModelDev ce
       sbk::tapeSampleFission(tp, N, E, rng, mu, phi, E_out, &kerr);
       if (kerr) { atomicMax(&cd->error, SB_ERR_CE_DATA); break; }
       double d[3] = {1.0, 0.0, 0.0};
-      rotateVector(d, mu, phi);
+      ceRotate(d, mu, phi);
       if (E_out > ce.eHi) E_out = ce.eHi;
       out.rx[i] = r[0]; out.ry[i] = r[1]; out.rz[i] = r[2];
       out.ux[i] = d[0]; out.uy[i] = d[1]; out.uz[i] = d[2];
@@ -235,7 +238,12 @@ __global__ void k_source_ce(const Model M, const char* blob, const CeModelDev ce
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
+// SYNC: the warps of a CTA run the event phases (refill | flight | collision 1 | collision 2) in lockstep, separated by CTA
+// barriers.  The loop body is far larger than the instruction caches (L0 6 KB, L1.5 32 KB per SM); without the barriers
+// every warp is at a different place of it and the SM stalls on instruction fetch (ncu r01f: 85 % of the stall samples are
+// "no instruction", I-cache hit rate 43 %); in lockstep one fetch serves all the warps of the CTA.
+template <int THREADS, int BPS, bool SYNC>
+__global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
   const char* base = a.blob;
   const Tables T = bind(a.M, base);
   const Model& M = a.M;
@@ -280,7 +288,9 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
         }
         need = __ballot_sync(FULL, !alive);
       }
-      if (need == FULL && exhausted) break;
+      const bool warpDone = (need == FULL && exhausted);
+      if (SYNC) { if (__syncthreads_and(warpDone ? 1 : 0)) break; }
+      else if (warpDone) break;
     }
 
     // ---------------- event: one flight segment -------------------------------------------------------
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
         else if (a.tracking == SB_TRACK_ST) mode = 2;
         else {                                              // transportOperatorHT_class.f90:49-81
           double majorant_inv = 1.0 / majXS;
-          double sigmaT = (c.mat == SB_VOID_MAT) ? 0.0 : sbce::matTotal(X, u, E, c.mat) + 0.0;
+          double sigmaT = (c.mat == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, c.mat) + 0.0;
           double ratio = sigmaT * majorant_inv;
           mode = (ratio > (1.0 - a.htCutoff)) ? 1 : 2;
         }
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
       if (mode == 1) {                                      // deltaTracking, one tentative flight
         trackXS = majXS;
         double majorant_inv = 1.0 / trackXS;
-        double distance = -sbm::log(rngGet(rng)) * majorant_inv;
+        double distance = -sbk::kLog(rngGet(rng)) * majorant_inv;
         sbt::geomTeleportCoords(M, T, c, distance);
         ++nSeg; ++hSeg;
         if (c.mat == SB_OUTSIDE_MAT) { leak = w; died = true; }
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
           bool virt = true;
           sigTot = 0.0;
           if (c.mat != SB_VOID_MAT) {
-            sigTot = sbce::matTotal(X, u, E, c.mat);
+            sigTot = ceMatTotal(X, u, E, c.mat);
             if (rngGet(rng) < (sigTot + 0.0) * majorant_inv) { realColl = true; virt = false; }
           }
           if (virt) scoreInCollCE(a, base, c.r[0], c.mat, E, u, w, trackXS, sigTot, true, sProd, sAbs, nScore);
@@ -318,14 +328,14 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
       } else {                                              // surfaceTracking, one segment
         const double tol = 1.0E-12;
         int m = c.mat;
-        sigTot = (m == SB_VOID_MAT) ? 0.0 : sbce::matTotal(X, u, E, m);
+        sigTot = (m == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, m);
         double sigmaTrack = (m == SB_VOID_MAT) ? collisionXS : fmax(sigTot + 0.0, collisionXS);
         trackXS = sigmaTrack;
         double dist, invSigmaTrack, sigmaT;
         if (sigmaTrack < tol) { dist = INF; invSigmaTrack = INF; sigmaT = 0.0; }
         else {
           invSigmaTrack = 1.0 / sigmaTrack;
-          dist = -sbm::log(rngGet(rng)) * invSigmaTrack;
+          dist = -sbk::kLog(rngGet(rng)) * invSigmaTrack;
           sigmaT = sigTot + 0.0;
         }
         int event;
@@ -341,6 +351,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
       }
     }
 
+    if (SYNC) __syncthreads();
     // ---------------- event: collision, part 1: nuclide, channel, number of fission sites ---------------------
     int MT = 0, nNew = 0, nuc0 = 0;
     const int mat = c.mat;
@@ -400,6 +411,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
         if (b + total > a.cap) { atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW); slot = -1; }
       }
     }
+    if (SYNC) __syncthreads();
     // ---------------- collision, part 2: fission sites, then the channel ------------------------------------------
     if (realColl) {
       const CeNucRec& N = a.ce.nuc[nuc0];
@@ -410,7 +422,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
         double mu, phi, E_out;
         sbk::tapeSampleFission(tp, N, E, rng, mu, phi, E_out, &kerr);
         double d[3] = {c.u[0][0], c.u[0][1], c.u[0][2]};
-        rotateVector(d, mu, phi);
+        ceRotate(d, mu, phi);
         if (E_out > a.ce.maxE) E_out = a.ce.maxE;
         if (slot >= 0) {
           int s = slot + i;
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
           double E_out = E;
           asymptoticScatter(E_out, mu, A);
           double d[3] = {c.u[0][0], c.u[0][1], c.u[0][2]};
-          rotateVector(d, mu, phi);
+          ceRotate(d, mu, phi);
           sbt::coordsRotate(T, c, d);
           E = E_out;
         } else {                                            // scatterFromMoving (:482-588), constant-XS free gas
@@ -444,7 +456,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
           const double r1 = rngGet(rng);
           const double phit = 2.0 * sbk::PI * r1;
           double V_t[3] = {dir_pre[0], dir_pre[1], dir_pre[2]};
-          rotateVector(V_t, mut, phit);
+          ceRotate(V_t, mut, phit);
           const double sc = Xt * sqrt(kT / A);
           double V_cm[3];
 #pragma unroll
@@ -454,7 +466,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
           for (int k = 0; k < 3; ++k) V_n[k] = V_n[k] / U_n;
           double mu = sbk::tapeSampleMu(tp, N.elAng, N.andPos, E, rng, &kerr);
           double phi = rngGet(rng) * sbk::TWO_PI;
-          rotateVector(V_n, mu, phi);
+          ceRotate(V_n, mu, phi);
 #pragma unroll
           for (int k = 0; k < 3; ++k) { V_n[k] = V_n[k] * U_n; V_n[k] = V_n[k] + V_cm[k]; }
           U_n = sqrt(V_n[0] * V_n[0] + V_n[1] * V_n[1] + V_n[2] * V_n[2]);
@@ -490,10 +502,10 @@ __global__ void __launch_bounds__(128, 4) k_histories_ce(const CeArgs a) {
           E = E_out;
         } else E = E_o;                                     // scatterInLAB
         double d[3] = {c.u[0][0], c.u[0][1], c.u[0][2]};
-        rotateVector(d, mu, phi);
+        ceRotate(d, mu, phi);
         sbt::coordsRotate(T, c, d);
         double rel = (double)m.TY;
-        if (m.relPos) rel = sbk::tapeTableAt(tp, m.relPos, E, &kerr);
+        if (m.relPos) rel = sbk::tapeTableAtNI(tp, m.relPos, E, &kerr, nullptr);
         w = w * rel;                                        // p%w * reac%release(p%E), at the outgoing energy as the reference
       } else died = true;                                   // capture / fission
       if (E < a.ce.minE) died = true;                       // cutoffs

@@ -137,11 +137,16 @@ SBK_HD bool tapeNuHas(const Tape& T, int pos, double E) { return T.i(pos) == 1 ?
 #if defined(__CUDACC__)
 namespace sbk {
 
-// rng: the lane's LCG state, advanced through RNGF (sbh::rngGet)
+// rng: the lane's LCG state, advanced through sbh::rngGet.  log / sincos / the table functions are kept out of line: one
+// copy each in the kernel (instruction-cache footprint, see sb_track.cuh)
 #define SBK_RNG(rng) sbh::rngGet(rng)
+__device__ __noinline__ double kLog(double x) { return sbm::log(x); }
+__device__ __noinline__ void kSinCos(double x, double* s, double* c) { sbm::sincos(x, s, c); }
+__device__ __noinline__ double tapeTableAtNI(const Tape& T, int pos, double x, int* err, int* next) { return tapeTableAt(T, pos, x, err, next); }
+__device__ __noinline__ double tapeNuNI(const Tape& T, int pos, double E, int* err) { return tapeNu(T, pos, E, err); }
 
 // tabularPdf%sample with x at px, pdf at px+NP, cdf at px+2NP
-__device__ inline double tapePdfSample(const Tape& T, int px, int NP, int flag, double r, int* err) {
+__device__ __noinline__ double tapePdfSample(const Tape& T, int px, int NP, int flag, double r, int* err) {
   int idx = tapeSearch(T, px + 2 * NP, NP, r);
   if (idx <= 0) { *err = KERR_SEARCH; return T(px); }
   idx = min(idx, NP - 1);
@@ -153,7 +158,7 @@ __device__ inline double tapePdfSample(const Tape& T, int px, int NP, int flag, 
   return x0 + (sqrt(disc) - pi) / f;
 }
 // angleLawENDF%sample: angPos = 0 -> isotropic, else tabularAngle block
-__device__ inline double tapeSampleMu(const Tape& T, int angPos, int andPos, double E, uint64_t& rng, int* err) {
+__device__ __noinline__ double tapeSampleMu(const Tape& T, int angPos, int andPos, double E, uint64_t& rng, int* err) {
   if (angPos == 0) return 2.0 * SBK_RNG(rng) - 1.0;
   const int NE = T.i(angPos);
   int idx = tapeSearch(T, angPos + 1, NE, E);
@@ -170,7 +175,7 @@ __device__ inline double tapeSampleMu(const Tape& T, int angPos, int andPos, dou
   return tapePdfSample(T, q + 2, NP, flag, rr, err);                  // tabularMu
 }
 // one ENDF energy law with its data at position q (root = JXS(11) or JXS(27))
-__device__ inline double tapeSampleLaw(const Tape& T, int LAW, int q, int root, double E_in, uint64_t& rng, int* err) {
+__device__ __noinline__ double tapeSampleLaw(const Tape& T, int LAW, int q, int root, double E_in, uint64_t& rng, int* err) {
   if (LAW == 3) return T(q + 1) * (E_in - T(q));                     // levelScattering: LDAT2 * (E_in - LDAT1)
   if (LAW == 4) {                                                    // contTabularEnergy%sample
     const int NR = T.i(q);
@@ -210,22 +215,22 @@ __device__ inline double tapeSampleLaw(const Tape& T, int LAW, int q, int root, 
   }
   if (LAW == 7 || LAW == 9) {
     int next = 0;
-    const double Tn = tapeTableAt(T, q, E_in, err, &next);
+    const double Tn = tapeTableAtNI(T, q, E_in, err, &next);
     const double U = T(next);
     if (LAW == 7) {                                                  // maxwellSpectrum%sample + maxwellEnergyPdf sample_Johnk
       for (int it = 0; it < 1000; ++it) {
         const double r1 = SBK_RNG(rng), r2 = SBK_RNG(rng), r3 = SBK_RNG(rng);
-        double s, c; sbm::sincos(0.5 * PI * r1, &s, &c);
+        double s, c; kSinCos(0.5 * PI * r1, &s, &c);
         const double beta = c * c;
-        const double gamma05 = -sbm::log(r2) * beta;
-        const double E_out = (-sbm::log(r3) + gamma05) * Tn;
+        const double gamma05 = -kLog(r2) * beta;
+        const double E_out = (-kLog(r3) + gamma05) * Tn;
         if (E_out < E_in - U) return E_out;
       }
       *err = KERR_REJECT; return 0.0;
     }
     for (int it = 0; it < 100000; ++it) {                            // evaporationSpectrum%sample (unbounded loop in the reference)
       const double r1 = SBK_RNG(rng), r2 = SBK_RNG(rng);
-      const double E_out = -Tn * sbm::log(r1 * r2);
+      const double E_out = -Tn * kLog(r1 * r2);
       if (E_out <= E_in - U) return E_out;
     }
     *err = KERR_REJECT; return 0.0;
@@ -233,7 +238,7 @@ __device__ inline double tapeSampleLaw(const Tape& T, int LAW, int q, int root, 
   *err = KERR_LAW; return E_in;
 }
 // energyLawENDF%sample for the law chain that starts at lawPos (LNW, LAW, IDAT, NR, ..., NE, E(NE), P(NE))
-__device__ inline double tapeSampleEnergy(const Tape& T, int lawPos, int root, double E_in, uint64_t& rng, int* err) {
+__device__ __noinline__ double tapeSampleEnergy(const Tape& T, int lawPos, int root, double E_in, uint64_t& rng, int* err) {
   int LNW = T.i(lawPos);
   if (LNW == 0) return tapeSampleLaw(T, T.i(lawPos + 1), root + T.i(lawPos + 2) - 1, root, E_in, rng, err);
   double r = SBK_RNG(rng);                                           // multipleEnergyLaws%sample
@@ -245,7 +250,7 @@ __device__ inline double tapeSampleEnergy(const Tape& T, int lawPos, int root, d
     double E = E_in;
     E = fmax(E, T(pN + 1));
     E = fmin(E, T(pN + N));
-    const double prob = tapeTableAt(T, p + 3, E, err);
+    const double prob = tapeTableAtNI(T, p + 3, E, err, nullptr);
     if (r < prob) return tapeSampleLaw(T, LAW, root + IDAT - 1, root, E_in, rng, err);
     r = r - prob;
     if (LNW == 0) break;
@@ -254,14 +259,14 @@ __device__ inline double tapeSampleEnergy(const Tape& T, int lawPos, int root, d
   *err = KERR_LAW; return E_in;
 }
 // fissionCE%sampleOut (fissionCE_class.f90:187-235)
-__device__ inline void tapeSampleFission(const Tape& T, const CeNucRec& n, double E_in, uint64_t& rng, double& mu, double& phi, double& E_out, int* err) {
+__device__ __noinline__ void tapeSampleFission(const Tape& T, const CeNucRec& n, double E_in, uint64_t& rng, double& mu, double& phi, double& E_out, int* err) {
   mu = 2.0 * SBK_RNG(rng) - 1.0;
   phi = TWO_PI * SBK_RNG(rng);
   double p_del = 0.0;
   if (n.nPrec > 0) {
     double del = 0.0;
-    if (n.nuDelPos != 0 && tapeNuHas(T, n.nuDelPos, E_in)) del = tapeNu(T, n.nuDelPos, E_in, err);
-    p_del = del / tapeNu(T, n.nuTotPos, E_in, err);
+    if (n.nuDelPos != 0 && tapeNuHas(T, n.nuDelPos, E_in)) del = tapeNuNI(T, n.nuDelPos, E_in, err);
+    p_del = del / tapeNuNI(T, n.nuTotPos, E_in, err);
   }
   const double r1 = SBK_RNG(rng);
   if (r1 > p_del) { E_out = tapeSampleEnergy(T, n.fisLawPos, n.dlwPos, E_in, rng, err); return; }
@@ -269,7 +274,7 @@ __device__ inline void tapeSampleFission(const Tape& T, const CeNucRec& n, doubl
   int p = n.precPos, g = 1;
   for (; g <= n.nPrec; ++g) {                                        // precursor block: DEC, NR, [..], NE, E(NE), P(NE)
     int next = 0;
-    r2 = r2 - tapeTableAt(T, p + 1, E_in, err, &next);
+    r2 = r2 - tapeTableAtNI(T, p + 1, E_in, err, &next);
     if (r2 < 0.0) break;
     p = next;
   }

@@ -28,8 +28,14 @@ struct Coords {                       // coordList (coord_class.f90:33-115), wit
 };
 struct DistCache { int lvl; double dist[MAX_NEST]; int surf[MAX_NEST]; };
 
+// The geometry procedures below are called from several places of the event loop; they are kept out of line (one copy each)
+// so that the loop body stays within the instruction cache (the fully inlined CE kernel was 585 KB of SASS and stalled on
+// instruction fetch for most of its cycles).
+__device__ __noinline__ int uniFindCellNI(const Tables& T, int ui, const double r[3], const double u[3]) { return uniFindCell(T, ui, r, u); }
+__device__ __noinline__ double surfDistanceNI(int type, const double* p, const double r[3], const double u[3]) { return surfDistance(type, p, r, u); }
+
 // geometryStd%diveToMat from level `start` (1-based) ; levels below are (re)entered
-__device__ inline bool diveToMat(const Tables& T, Coords& c, int start) {
+__device__ __noinline__ bool diveToMat(const Tables& T, Coords& c, int start) {
   for (int i = start; i <= MAX_NEST; ++i) {
     int2 f = T.graph[c.root[i - 1] + c.local[i - 1] - 2];
     if (f.x >= 0) { c.mat = f.x; c.uid = f.y; return true; }
@@ -43,31 +49,31 @@ __device__ inline bool diveToMat(const Tables& T, Coords& c, int start) {
     c.nesting += 1;
     uniEnter(T, ui, rin, uin, c.r[i], c.u[i]);
     c.uni[i] = ui; c.root[i] = f.y;
-    c.local[i] = uniFindCell(T, ui, c.r[i], c.u[i]);
+    c.local[i] = uniFindCellNI(T, ui, c.r[i], c.u[i]);
   }
   c.mat = SB_UNDEF_MAT; c.uid = -3;
   return false;
 }
 // geometryStd%placeCoord: from level-1 position and direction
-__device__ inline bool placeCoord(const Model& M, const Tables& T, Coords& c) {
+__device__ __noinline__ bool placeCoord(const Model& M, const Tables& T, Coords& c) {
   c.nesting = 1; c.mat = SB_UNDEF_MAT; c.uid = -3;
   int ui = M.rootIdx - 1;
   double rin[3] = {c.r[0][0], c.r[0][1], c.r[0][2]}, uin[3] = {c.u[0][0], c.u[0][1], c.u[0][2]};
   uniEnter(T, ui, rin, uin, c.r[0], c.u[0]);
   c.uni[0] = ui; c.root[0] = 1;
-  c.local[0] = uniFindCell(T, ui, c.r[0], c.u[0]);
+  c.local[0] = uniFindCellNI(T, ui, c.r[0], c.u[0]);
   return diveToMat(T, c, 1);
 }
 
 // universe%distance at one level -> d, surface memento
-__device__ inline void uniDistance(const Tables& T, int ui, const double r[3], const double u[3], int localID, double& d, int& sIdx) {
+__device__ __noinline__ void uniDistance(const Tables& T, int ui, const double r[3], const double u[3], int localID, double& d, int& sIdx) {
   const int type = T.uniType[ui];
   const int* ip = T.uniIpar + ui * SB_UNI_NIPAR;
   const double* dp = T.uniDpar + ui * SB_UNI_NDPAR;
   if (type == SB_UNI_ROOT) {                                  // rootUniverse_class.f90:145-160
     int s = ip[2] - 1;
     sIdx = ip[2];
-    d = surfDistance(T.surfType[s], T.surfPar + s * SB_SURF_NPAR, r, u);
+    d = surfDistanceNI(T.surfType[s], T.surfPar + s * SB_SURF_NPAR, r, u);
   } else if (type == SB_UNI_PIN) {                            // pinUniverse_class.f90:175-214
     const int N = ip[2]; const double* r_sq = T.auxD + ip[3]; const double* tol = r_sq + N;
     const double rs = r[0] * r[0] + r[1] * r[1];
@@ -81,7 +87,7 @@ __device__ inline void uniDistance(const Tables& T, int ui, const double r[3], c
     if (localID == ip[5]) {
       double p[SB_SURF_NPAR] = {0.0, 0.0, 0.0, dp[21], dp[22], dp[23], SURF_TOL, 0.0};
       sIdx = LAT_OUTLINE_SURF;
-      d = surfDistance(SB_SURF_BOX, p, r, u);
+      d = surfDistanceNI(SB_SURF_BOX, p, r, u);
       return;
     }
     int ijk[3]; lat_get_ijk(ijk, localID, ip + 2);
@@ -107,7 +113,7 @@ __device__ inline void uniDistance(const Tables& T, int ui, const double r[3], c
     for (int k = T.cellOff[cidx]; k < T.cellOff[cidx + 1]; ++k) {
       int sidx = T.cellSurf[k];
       int s = (sidx < 0 ? -sidx : sidx) - 1;
-      double t = surfDistance(T.surfType[s], T.surfPar + s * SB_SURF_NPAR, r, u);
+      double t = surfDistanceNI(T.surfType[s], T.surfPar + s * SB_SURF_NPAR, r, u);
       if (t < d) { d = t; sIdx = s + 1; }
     }
   }
@@ -123,11 +129,11 @@ __device__ inline void uniCross(const Tables& T, int ui, double r[3], const doub
 #pragma unroll
     for (int k = 0; k < 3; ++k) r[k] = r[k] + u[k] * NUDGE;
   }
-  localID = uniFindCell(T, ui, r, u);
+  localID = uniFindCellNI(T, ui, r, u);
 }
 
 // geometryStd%move_noCache / move_withCache (no fields)
-__device__ inline void geomMove(const Model& M, const Tables& T, Coords& c, double& maxDist, int& event, DistCache* cache) {
+__device__ __noinline__ void geomMove(const Model& M, const Tables& T, Coords& c, double& maxDist, int& event, DistCache* cache) {
   double dist = INF; int surfIdx = 0, level = 0;
   for (int l = 1; l <= c.nesting; ++l) {                      // closestDist[_cache]
     double td; int ti;
@@ -169,7 +175,7 @@ __device__ inline void geomMove(const Model& M, const Tables& T, Coords& c, doub
   }
 }
 // geometryStd%teleport on a coordList
-__device__ inline void geomTeleportCoords(const Model& M, const Tables& T, Coords& c, double dist) {
+__device__ __noinline__ void geomTeleportCoords(const Model& M, const Tables& T, Coords& c, double dist) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) c.r[0][k] = c.r[0][k] + dist * c.u[0][k];
   placeCoord(M, T, c);
@@ -181,7 +187,7 @@ __device__ inline void geomTeleportCoords(const Model& M, const Tables& T, Coord
   }
 }
 // coordList%rotate (coord_class.f90:386-408)
-__device__ inline void coordsRotate(const Tables& T, Coords& c, const double d[3]) {
+__device__ __noinline__ void coordsRotate(const Tables& T, Coords& c, const double d[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) c.u[0][k] = d[k];
   for (int i = 1; i < c.nesting; ++i) {
