@@ -639,7 +639,10 @@ static int buildBlob(sb_engine* h) {
   CUDA_OK(cudaMalloc(&h->dBlob, blob.size()));
   CUDA_OK(cudaMemcpy(h->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   h->trackSmem = (M.blobBytes <= 50 * 1024) ? 1 : 0;           // 4 CTAs of 128 threads per SM
-  if (h->trackSmem) CUDA_OK(cudaFuncSetAttribute(sbt::k_histories_track, cudaFuncAttributeMaxDynamicSharedMemorySize, M.blobBytes));
+  if (h->trackSmem) {
+    CUDA_OK(cudaFuncSetAttribute(sbt::k_histories_track<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, M.blobBytes));
+    CUDA_OK(cudaFuncSetAttribute(sbt::k_histories_track<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, M.blobBytes));
+  }
 
   // ---- hot blob ----------------------------------------------------------------------------------
   {
@@ -1035,6 +1038,9 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     const char* cfg = getenv("SB_CE_KERNEL");                  // experiment switch: "async" = 128-thread CTAs without phase barriers
     if (cfg && !strcmp(cfg, "async")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync256")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM * 2, (n + 255) / 256), 256, 0, st>>>(t);
+    else if (cfg && !strcmp(cfg, "sync256x1")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM, (n + 255) / 256), 256, 0, st>>>(t);
+    else if (cfg && !strcmp(cfg, "sync128x1")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM, (n + 127) / 128), 128, 0, st>>>(t);
+    else if (cfg && !strcmp(cfg, "sync64x1")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM, (n + 63) / 64), 64, 0, st>>>(t);
     else sbc::k_histories_ce<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, 0, st>>>(t);
   } else
   if (useTrack) {                                             // surface / hybrid tracking: coordList-carrying kernel
@@ -1044,8 +1050,9 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.nsites = h->dNsites; t.hProd = h->dHProd; t.hAbs = h->dHAbs; t.hLeak = h->dHLeak; t.hScat = h->dHScat;
     t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
     t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
-    int tb = std::min(h->numSM * 4, (n + 127) / 128);
-    sbt::k_histories_track<<<tb, 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
+    const char* cfg = getenv("SB_TRACK_KERNEL");               // experiment switch: "async" = 128-thread CTAs without phase barriers
+    if (cfg && !strcmp(cfg, "async")) sbt::k_histories_track<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
+    else sbt::k_histories_track<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
   } else
   if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, threads, h->hot.bytes, st>>>(a);
   else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, threads, h->hot.bytes, st>>>(a);

@@ -44,6 +44,10 @@ struct CeArgs {
   int tracking; double htCutoff; int stCache;
 };
 
+// what the out-of-line device functions need, kept once per CTA in shared memory: a reference to kernel parameters would make
+// every thread copy them to its stack (params live in the constant bank and have no address)
+struct CeCtx { Model M; Tables T; CeModelDev ce; double* bins; int phase, needMacro; };
+
 // ---- cross sections at (E, union interval u) ---------------------------------------------------------------------------
 struct NucPoint { int idx; double f; const double* d; int rows; };
 __device__ __forceinline__ NucPoint nucPoint(const sbce::CeDev& c, int u, double e, int nuc0) {      // nuclide%search through the index table
@@ -67,6 +71,7 @@ __device__ __noinline__ void matMacro(const sbce::CeDev& c, int u, double e, int
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
 #pragma unroll
   for (int r = 0; r < 8; ++r) xs[r] = 0.0;
+#pragma unroll 1
   for (int k = k0; k < k1; ++k) {
     const NucPoint p = nucPoint(c, u, e, __ldg(c.matNuc + k) - 1);
     const double dens = __ldg(c.matDens + k) * 1.0;
@@ -119,7 +124,7 @@ __device__ inline int clerkBinCE(const DClerk& c, const char* blob, const double
   return idx;
 }
 // tallyAdmin%reportInColl for a CE particle
-__device__ __noinline__ void scoreInCollCE(const CeArgs& a, const char* base, const double r[3], int mat, double E, int u,
+__device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, const double r[3], int mat, double E, int u,
                                      double w, double trackXS, double sigmaTot, bool virt, double& sProd, double& sAbs, unsigned& nScore) {
   const bool isVoid = (mat == SB_VOID_MAT);
   const int nC = a.M.nClerk[a.phase];
@@ -148,7 +153,22 @@ __device__ __noinline__ void scoreInCollCE(const CeArgs& a, const char* base, co
   }
 }
 
-__device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e, int m) { return sbce::matTotal(c, u, e, m); }
+// sbce::matTotal with the loop kept rolled (code size; the lookup kernel keeps the unrolled one)
+__device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e, int m) {
+  const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
+  const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
+  double tot = 0.0;
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    const int nuc = __ldg(c.matNuc + k) - 1;
+    const int idx = __ldg(row + nuc);
+    double E_low, E_top, s_low, s_top;
+    sbce::ldPair(c.pairTot + 4 * (__ldg(c.pairOff + nuc) + (idx - 1)), E_low, E_top, s_low, s_top);
+    const double f = (e - E_low) / (E_top - E_low);
+    tot = tot + __ldg(c.matDens + k) * (s_top * f + (1.0 - f) * s_low);
+  }
+  return tot * 1.0;
+}
 __device__ __noinline__ void ceRotate(double d[3], double mu, double phi) { rotateVector(d, mu, phi); }
 
 // ---- scattering kernels (scatteringKernels_func.f90) ---------------------------------------------------------------------
@@ -245,9 +265,13 @@ __global__ void k_source_ce(const Model M, const char* blob, const CeModelDev ce
 template <int THREADS, int BPS, bool SYNC>
 __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
   const char* base = a.blob;
-  const Tables T = bind(a.M, base);
-  const Model& M = a.M;
-  const sbce::CeDev& X = a.ce.xs;
+  __shared__ CeCtx s_ctx;
+  if (threadIdx.x == 0) { s_ctx.M = a.M; s_ctx.T = bind(a.M, base); s_ctx.ce = a.ce; s_ctx.bins = a.bins; s_ctx.phase = a.phase; s_ctx.needMacro = a.needMacro; }
+  __syncthreads();
+  const CeCtx& ctx = s_ctx;
+  const Tables& T = s_ctx.T;
+  const Model& M = s_ctx.M;
+  const sbce::CeDev& X = s_ctx.ce.xs;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
@@ -294,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
     }
 
     // ---------------- event: one flight segment -------------------------------------------------------
-    bool realColl = false, died = false;
+    bool realColl = false, died = false, scoreVirt = false;
     double leak = 0.0;
     if (alive) {
       if (mode == 0) {                                      // transportOperator%transport begins
@@ -323,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
             sigTot = ceMatTotal(X, u, E, c.mat);
             if (rngGet(rng) < (sigTot + 0.0) * majorant_inv) { realColl = true; virt = false; }
           }
-          if (virt) scoreInCollCE(a, base, c.r[0], c.mat, E, u, w, trackXS, sigTot, true, sProd, sAbs, nScore);
+          scoreVirt = virt;
         }
       } else {                                              // surfaceTracking, one segment
         const double tol = 1.0E-12;
@@ -346,10 +370,13 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         else if (m >= SB_OVERLAP_MAT && m != SB_VOID_MAT) { atomicMax(&a.cd->error, m == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
         else if (event == sbt::COLL_EV) {
           if (rngGet(rng) < sigmaT * invSigmaTrack) realColl = true;
-          else scoreInCollCE(a, base, c.r[0], m, E, u, w, trackXS, sigTot, true, sProd, sAbs, nScore);
+          else scoreVirt = true;
         }
       }
     }
+    if (SYNC) __syncthreads();
+    // ---------------- tallyAdmin%reportInColl of the virtual collisions ------------------------------------
+    if (scoreVirt) scoreInCollCE(ctx, base, c.r[0], c.mat, E, u, w, trackXS, sigTot, true, sProd, sAbs, nScore);
 
     if (SYNC) __syncthreads();
     // ---------------- event: collision, part 1: nuclide, channel, number of fission sites ---------------------
@@ -362,6 +389,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
       double rem = (sigTot * 1.0) * rngGet(rng);
       const int k0 = __ldg(X.matOff + mat - 1), k1 = __ldg(X.matOff + mat);
       nuc0 = -1;
+#pragma unroll 1
       for (int k = k0; k < k1; ++k) {
         const int nn = __ldg(X.matNuc + k) - 1;
         const int idx = __ldg(X.idxTab + (size_t)(u - 1) * X.nNuc + nn);
@@ -387,9 +415,12 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         MT = C;                                             // 1 elastic, 2 inelastic, 3 capture (N_disap), 4 fission
       }
       ++nColl;
+    }
+    if (SYNC) __syncthreads();
+    if (realColl) {
       // tallyAdmin%reportInColl(p, virtual = .false.) comes after sampleCollision (collisionProcessor_inter.f90:131)
-      scoreInCollCE(a, base, c.r[0], mat, E, u, w, trackXS, sigTot, false, sProd, sAbs, nScore);
-      if (a.ce.nuc[nuc0].fissile) {                         // neutronCEstd implicit (:217-300)
+      scoreInCollCE(ctx, base, c.r[0], mat, E, u, w, trackXS, sigTot, false, sProd, sAbs, nScore);
+      if (ctx.ce.nuc[nuc0].fissile) {                         // neutronCEstd implicit (:217-300)
         double rand1 = rngGet(rng);
         nNew = (int)(fabs((w * mic[5]) / (w0 * mic[0] * a.k_eff)) + rand1);
         if (nNew < 0) nNew = 0;
@@ -414,16 +445,17 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
     if (SYNC) __syncthreads();
     // ---------------- collision, part 2: fission sites, then the channel ------------------------------------------
     if (realColl) {
-      const CeNucRec& N = a.ce.nuc[nuc0];
-      const Tape tp{a.ce.tape, N.base};
+      const CeNucRec& N = ctx.ce.nuc[nuc0];
+      const Tape tp{ctx.ce.tape, N.base};
       int kerr = 0;
       const double wSite = fsign(w0, w);
+#pragma unroll 1
       for (int i = 0; i < nNew; ++i) {
         double mu, phi, E_out;
         sbk::tapeSampleFission(tp, N, E, rng, mu, phi, E_out, &kerr);
         double d[3] = {c.u[0][0], c.u[0][1], c.u[0][2]};
         ceRotate(d, mu, phi);
-        if (E_out > a.ce.maxE) E_out = a.ce.maxE;
+        if (E_out > ctx.ce.maxE) E_out = ctx.ce.maxE;
         if (slot >= 0) {
           int s = slot + i;
           a.out.rx[s] = c.r[0][0]; a.out.ry[s] = c.r[0][1]; a.out.rz[s] = c.r[0][2];
@@ -431,12 +463,19 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
           a.out.w[s] = wSite * 1.0; a.out.G[s] = 0; a.out.E[s] = E_out; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
         }
       }
+      if (kerr) atomicMax(&a.cd->error, SB_ERR_CE_DATA);
       nSite += nNew;
+    }
+    if (SYNC) __syncthreads();
+    if (realColl) {
+      const CeNucRec& N = ctx.ce.nuc[nuc0];
+      const Tape tp{ctx.ce.tape, N.base};
+      int kerr = 0;
       const double wPre = w;
       int MTout = 0;
       if (MT == 1) {                                        // elastic (:330-375)
         const double A = N.awr, kT = N.kT;
-        const bool isFixed = (E > kT * a.ce.threshE) && (A > a.ce.threshA);
+        const bool isFixed = (E > kT * ctx.ce.threshE) && (A > ctx.ce.threshA);
         if (isFixed) {                                      // scatterFromFixed
           double mu = sbk::tapeSampleMu(tp, N.elAng, N.andPos, E, rng, &kerr);
           double phi = rngGet(rng) * sbk::TWO_PI;
@@ -480,8 +519,9 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         double XS = nucRow(p, 3);
         XS = XS * rngGet(rng);
         int which = -1;
+#pragma unroll 1
         for (int i = 0; i < N.nMT; ++i) {
-          const CeMtRec& m = a.ce.mt[N.mtFirst + i];
+          const CeMtRec& m = ctx.ce.mt[N.mtFirst + i];
           const int idxT = p.idx - m.firstIdx + 1;
           if (idxT < 1) continue;
           const double topXS = tp(m.xsPos + idxT), bottomXS = tp(m.xsPos + idxT - 1);
@@ -489,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
           if (XS <= 0.0) { which = i; break; }
         }
         if (which < 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); which = 0; }
-        const CeMtRec& m = a.ce.mt[N.mtFirst + which];
+        const CeMtRec& m = ctx.ce.mt[N.mtFirst + which];
         MTout = m.MT;
         // neutronScatter%sampleOut
         double mu = sbk::tapeSampleMu(tp, m.angPos, N.andPos, E, rng, &kerr);
@@ -508,7 +548,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         if (m.relPos) rel = sbk::tapeTableAtNI(tp, m.relPos, E, &kerr, nullptr);
         w = w * rel;                                        // p%w * reac%release(p%E), at the outgoing energy as the reference
       } else died = true;                                   // capture / fission
-      if (E < a.ce.minE) died = true;                       // cutoffs
+      if (E < ctx.ce.minE) died = true;                       // cutoffs
       if (kerr) atomicMax(&a.cd->error, SB_ERR_CE_DATA);
       // keffImplicitClerk%reportOutColl: (n,xn) multiplicities by MT (keffImplicitClerk_class.f90:245-270)
       if (a.phase == 1 && MT == 2) {

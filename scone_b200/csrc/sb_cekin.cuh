@@ -81,6 +81,9 @@ struct Tape {
 SBK_HD int tapeSearch(const Tape& T, int p0, int N, double v) {
   if (N < 1 || v < T(p0) || v > T(p0 + N - 1)) return -1;
   int bottom = 1, top = N;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
   for (int it = 0; it < 70; ++it) {
     int idx = (top + bottom) / 2;
     if (bottom == idx) return idx;

@@ -246,12 +246,18 @@ __device__ inline void scoreInColl(const TrackArgs& a, const Tables& T, const ch
 
 extern __shared__ __align__(16) char g_trackSmem[];
 
-__global__ void __launch_bounds__(128, 4) k_histories_track(const TrackArgs a) {
+// SYNC: the warps of a CTA run the event phases in lockstep (CTA barriers between them): the loop body is larger than the
+// instruction caches, and in lockstep one instruction fetch serves every warp of the CTA (measured on the CE kernel: 2.3x).
+template <int THREADS, int BPS, bool SYNC>
+__global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ Model s_M; __shared__ Tables s_T;      // shared, not parameters: the out-of-line geometry functions take them by reference
   const char* base = a.blob;
   if (a.useSmem) { sbh::stageHot(g_trackSmem, a.blob, a.M.blobBytes, &s_bar); base = g_trackSmem; }
-  const Tables T = bind(a.M, base);
-  const Model& M = a.M;
+  if (threadIdx.x == 0) { s_M = a.M; s_T = bind(a.M, base); }
+  __syncthreads();
+  const Tables& T = s_T;
+  const Model& M = s_M;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
@@ -289,7 +295,9 @@ __global__ void __launch_bounds__(128, 4) k_histories_track(const TrackArgs a) {
         }
         need = __ballot_sync(FULL, !alive);
       }
-      if (need == FULL && exhausted) break;
+      const bool warpDone = (need == FULL && exhausted);
+      if (SYNC) { if (__syncthreads_and(warpDone ? 1 : 0)) break; }
+      else if (warpDone) break;
     }
 
     // ---------------- event: one flight segment -------------------------------------------------------
@@ -348,6 +356,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_track(const TrackArgs a) {
       }
     }
 
+    if (SYNC) __syncthreads();
     // ---------------- event: collision, part 1 --------------------------------------------------------
     int MT = 0, nNew = 0;
     const int mat = c.mat;
@@ -388,6 +397,7 @@ __global__ void __launch_bounds__(128, 4) k_histories_track(const TrackArgs a) {
         if (b + total > a.cap) { atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW); slot = -1; }
       }
     }
+    if (SYNC) __syncthreads();
     // ---------------- collision, part 2 ---------------------------------------------------------------
     if (realColl) {
       const double wSite = fsign(w0, w);
