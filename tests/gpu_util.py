@@ -8,6 +8,7 @@ DECK = {
     "c5g7_3d": os.path.join(ROOT, "decks", "c5g7", "c5g7_3d_rodded"),
     "inf": os.path.join(ROOT, "decks", "urr", "inf"),
     "slab": os.path.join(ROOT, "decks", "urr", "slab"),
+    "ce_pin": os.path.join(ROOT, "decks", "ce", "pincell"),
 }
 
 

@@ -31,7 +31,7 @@ def run_ranks(ws, backend, deck, ov, ninact, nact, out):
         assert p.returncode == 0 and ("ok %d" % r) in o, o[-3000:]
 
 
-@pytest.mark.parametrize("deck,pop,ws", [("c5g7", 20001, 2), ("c5g7", 9000, 3), ("slab", 6000, 2)])
+@pytest.mark.parametrize("deck,pop,ws", [("c5g7", 20001, 2), ("c5g7", 9000, 3), ("slab", 6000, 2), ("ce_pin", 3001, 2)])
 def test_ranked_run_reproduces_single_rank_histories(tmp_path, deck, pop, ws):
     ninact, nact = 3, 2
     ov = "pop %d; inactive %d; active %d; seed 31337;" % (pop, ninact, nact)
@@ -47,7 +47,7 @@ def test_ranked_run_reproduces_single_rank_histories(tmp_path, deck, pop, ws):
         sizes = [len(p["w"]) for p in parts]
         assert sizes == [scone_b200.distributed.workshare(pop, ws, r)[0] for r in range(ws)]      # load balancing restored the shares
         r1, d1, w1, G1 = pp.bank()
-        for key, ref in (("r", r1), ("d", d1), ("w", w1), ("G", G1)):
+        for key, ref in (("r", r1), ("d", d1), ("w", w1), ("G", G1)):      # 4th array: G (multigroup) or E (continuous energy)
             assert np.array_equal(np.concatenate([p[key] for p in parts]), ref), "bank differs after cycle %d (%s)" % (c, key)
         for f in fin:
             assert f["k"][c] == pytest.approx(pp.k, rel=1e-12)          # same k on every rank (sums differ in rounding only)
