@@ -27,10 +27,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DECKS = {"c5g7": "decks/c5g7/c5g7_2d", "c5g7_3d": "decks/c5g7/c5g7_3d_rodded", "inf": "decks/urr/inf", "slab": "decks/urr/slab",
-         "ce_pin": "decks/ce/pincell"}
+         "ce_pin": "decks/ce/pincell", "ce_asm": "decks/ce/assembly17"}
 WORKLOAD = {"c5g7": "C5G7 MOX 2D 7-group eigenvalue, delta tracking (InputFiles/Benchmarks/Multigroup/C5G7 as decks/c5g7/c5g7_2d)",
             "c5g7_3d": "C5G7 3D rodded-A 7-group eigenvalue with 34x34x9 flux+fission mesh, delta tracking",
             "inf": "SCONE_Inf URRa-2-1-IN 2-group infinite medium", "slab": "SCONE_Slab URRa-2-1-SL 2-group slab (P1)",
+            "ce_asm": "synthetic continuous-energy 17x17 assembly, 20 nuclides per fuel material (5 bundled ACE nuclides + 15 energy-shifted clones), delta tracking, k-eff only (BASELINE configs[4] at a single-GPU population)",
             "ce_pin": "continuous-energy U-233 / H-1 pin cell from the reference's bundled ACE nuclides (BASELINE configs[2] stand-in), 300-bin energy x material flux tally"}
 ALG_BYTES_PER_SEGMENT = 124      # particle SoA read+write per flight segment
 ALG_BYTES_PER_SCORE = 16         # f64 read-modify-write per tally score
@@ -324,10 +325,10 @@ def main():
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(("k_histories_ce" if args.deck == "ce_pin" else "k_histories") + "_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(("k_histories_ce" if args.deck.startswith("ce_") else "k_histories") + "_dram_bytes_per_launch")
     except Exception:
         pass
-    kname = "k_histories_ce" if args.deck == "ce_pin" else ("k_histories" if args.tracking in (None, "DT") else "k_histories_track")
+    kname = "k_histories_ce" if args.deck.startswith("ce_") else ("k_histories" if args.tracking in (None, "DT") else "k_histories_track")
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,

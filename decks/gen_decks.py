@@ -410,6 +410,112 @@ nuclearData {
            bc="1 1 1 1 1 1" if inf else "0 0 1 1 1 1", hw="10.0" if inf else "9.4959", pn="P0" if inf else "P1")
 
 
+
+# ---------------------------------------------------------------------------------------
+# Continuous-energy decks (authored from the nuclides bundled with the reference; the cards travel as the binary fixtures
+# tests/golden/ace/*.acebin, see tests/golden/make_ace_fixtures.py)
+CE_BASE = [("1001", "1001JEF311"), ("92233", "92233JEF311"), ("52126", "52126JEF311"), ("91231", "91231JEF311"), ("91232", "91232JEF311")]
+
+
+def synth_ace_cards(outdir):
+    """BASELINE configs[4] (SURVEY.md section 8d cfg 5): ~20 nuclides per fuel material made from the five bundled cards by
+    seeded shifts of the ESZ energy grid (interior points scaled UP by up to 2 %, end points kept, order kept; every other
+    block untouched, so reaction thresholds stay covered by their law tables). Written to decks/ce/synth/ (not tracked)."""
+    import struct
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "..", "tests", "golden", "ace")
+    dst = os.path.join(outdir, "ce", "synth")
+    os.makedirs(dst, exist_ok=True)
+    rng = np.random.default_rng(20261017)
+    lib = ["! synthetic ACE library: the five bundled cards + 15 energy-shifted clones (decks/gen_decks.py)"]
+    for za, fn in CE_BASE:
+        raw = open(os.path.join(src, fn + ".acebin"), "rb").read()
+        lib.append("%s.03c; 1; ../../../tests/golden/ace/%s.acebin;" % (za, fn))
+        head = raw[:8 + 16 + 16]
+        nxs = np.frombuffer(raw, np.int32, 16, 40).copy(); jxs = np.frombuffer(raw, np.int32, 32, 104).copy()
+        n = struct.unpack_from("<q", raw, 232)[0]
+        xss = np.frombuffer(raw, np.float64, n, 240).copy()
+        for k in (10, 11, 12):
+            x = xss.copy()
+            nes, p0 = int(nxs[2]), int(jxs[0]) - 1
+            g = x[p0:p0 + nes].copy()
+            s = 1.0 + rng.uniform(0.002, 0.02)
+            gi = g[1:-1] * s
+            ok = gi < g[-2]                                   # keep the top of the grid as it is
+            g2 = g.copy(); g2[1:-1] = np.where(ok, gi, g[1:-1])
+            g2 = np.maximum.accumulate(g2)
+            bad = np.where(np.diff(g2) <= 0)[0]
+            for i in bad:                                      # a shifted point must not land on its neighbour
+                if g[i + 1] > g[i]:
+                    g2[:] = g
+                    break
+            x[p0:p0 + nes] = g2
+            with open(os.path.join(dst, "%s_%d.acebin" % (za, k)), "wb") as f:
+                zaid = ("%s.%dc" % (za, k)).encode().ljust(16, b"\0")
+                f.write(raw[:8] + zaid + raw[24:40] + nxs.tobytes() + jxs.tobytes() + struct.pack("<q", n) + x.tobytes())
+            lib.append("%s.%dc; 1; %s_%d.acebin;" % (za, k, za, k))
+    with open(os.path.join(dst, "aceLib"), "w") as f:
+        f.write("\n".join(lib) + "\n")
+
+
+def ce_assembly17(pop=1000000, inactive=20, active=20, seed=20261017):
+    """Synthetic CE 17x17 assembly (BASELINE configs[4]): 264 fuel pins with 20 nuclides each + 25 water holes, reflective
+    boundaries, delta tracking, k-eff only."""
+    guide = {(2, 5), (2, 8), (2, 11), (3, 3), (3, 13), (5, 2), (5, 5), (5, 8), (5, 11), (5, 14), (8, 2), (8, 5), (8, 8), (8, 11), (8, 14),
+             (11, 2), (11, 5), (11, 8), (11, 11), (11, 14), (13, 3), (13, 13), (14, 5), (14, 8), (14, 11)}
+    rows = [[2 if (r, c) in guide else 1 for c in range(17)] for r in range(17)]
+    tags = ["03", "10", "11", "12"]
+    fuel = []
+    for za, tot in (("92233", 1.5e-4), ("52126", 2.2e-2), ("91231", 5.0e-5), ("91232", 2.0e-6), ("1001", 4.0e-6)):
+        for i, t in enumerate(tags):
+            fuel.append("%s.%s %.6E;" % (za, t, tot * (0.4, 0.3, 0.2, 0.1)[i]))
+    water = []
+    for za, tot in (("1001", 6.67e-2), ("52126", 1.0e-3)):
+        for i, t in enumerate(tags):
+            water.append("%s.%s %.6E;" % (za, t, tot * (0.4, 0.3, 0.2, 0.1)[i]))
+    return """// Synthetic continuous-energy 17x17 assembly (BASELINE configs[4] / SURVEY.md section 8d cfg 5): 20 nuclides per fuel
+// material = the five bundled nuclides + energy-shifted clones (decks/ce/synth, written by decks/gen_decks.py); unionised-grid stress.
+type eigenPhysicsPackage;
+pop      %(pop)d;
+active   %(active)d;
+inactive %(inactive)d;
+seed     %(seed)d;
+XSdata   ce;
+dataType ce;
+
+collisionOperator { neutronCE { type neutronCEstd; } }
+transportOperator { type transportOperatorDT; }
+
+inactiveTally { }
+activeTally { }
+
+geometry {
+  type geometryStd;
+  boundary (1 1 1 1 1 1);
+  graph { type shrunk; }
+  surfaces { bound { id 1; type box; origin (0.0 0.0 0.0); halfwidth (10.71 10.71 10.0); } }
+  cells { }
+  universes {
+    root { id 100; type rootUniverse; border 1; fill u<10>; }
+    pin  { id 1; type pinUniverse; radii (0.41 0.0); fills (fuel water); }
+    hole { id 2; type pinUniverse; radii (0.0); fills (water); }
+    lat  { id 10; type latUniverse; origin (0.0 0.0 0.0); pitch (1.26 1.26 0.0); shape (17 17 0); padMat water;
+      map (
+%(map)s ); }
+  }
+}
+
+nuclearData {
+  handles { ce { type aceNeutronDatabase; aceLibrary ./synth/aceLib; ures 0; majorant 1; } }
+  materials {
+    fuel  { temp 293; composition { %(fuel)s } }
+    water { temp 293; composition { %(water)s } }
+  }
+}
+""" % dict(pop=pop, inactive=inactive, active=active, seed=seed, map=fmt_map(rows), fuel=" ".join(fuel), water=" ".join(water))
+
+
 def write(outdir):
     def put(rel, text):
         p = os.path.join(outdir, rel)
@@ -425,6 +531,8 @@ def write(outdir):
     put("urr/xs/URRa_2_1.xs", "// Sood et al. URRa-2-1 two-group constants\n" + URR_2G)
     put("urr/inf", urr_deck("inf"))
     put("urr/slab", urr_deck("slab"))
+    synth_ace_cards(outdir)
+    put("ce/assembly17", ce_assembly17())
 
 
 if __name__ == "__main__":

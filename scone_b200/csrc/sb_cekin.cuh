@@ -231,7 +231,9 @@ __device__ __noinline__ double tapeSampleLaw(const Tape& T, int LAW, int q, int 
       }
       *err = KERR_REJECT; return 0.0;
     }
-    for (int it = 0; it < 100000; ++it) {                            // evaporationSpectrum%sample (unbounded loop in the reference)
+    // evaporationSpectrum%sample: an unbounded rejection loop in the reference; just above a threshold the acceptance
+    // probability ~ ((E_in - U) / T)^2 / 2 can be 1e-6 and below, so the bound is generous (a lane that reaches it flags an error)
+    for (long long it = 0; it < 2000000000LL; ++it) {
       const double r1 = SBK_RNG(rng), r2 = SBK_RNG(rng);
       const double E_out = -Tn * kLog(r1 * r2);
       if (E_out <= E_in - U) return E_out;

@@ -15,6 +15,11 @@ from tests import oracle_lib as ol
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DECK = os.path.join(ROOT, "decks", "ce", "pincell")
+ASM = os.path.join(ROOT, "decks", "ce", "assembly17")
+if not os.path.exists(os.path.join(ROOT, "decks", "ce", "synth", "aceLib")):        # written by __graft_entry__.build(); not tracked
+    import subprocess
+    import sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "decks", "gen_decks.py")])
 
 
 def oracle_bank(orc, e):
@@ -69,6 +74,31 @@ def test_ce_cycles_bit_exact_against_oracle(orc, pop, ninact, nact, tracking):
         orc.orc_eigen_stats(e, C.byref(seg), C.byref(coll), C.byref(hist))
         st = pp.stats()
         assert st["seg_inactive"] + st["seg_active"] == seg.value
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
+
+
+def test_ce_assembly_20_nuclides_bit_exact_against_oracle(orc):
+    """BASELINE configs[4] deck (17x17 lattice, 20 nuclides per fuel material, delta tracking) at a size the oracle finishes in seconds."""
+    ov = "pop 2500; inactive 1; active 2; seed 777;"
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(ASM.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(ASM, ov, device=0)
+        assert orc.orc_eigen_init_source(e) == 0, ol.err(orc)
+        pp.generateInitialState()
+        for a, b in zip(pp.bank(), oracle_bank(orc, e)):
+            assert np.array_equal(a, b)
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(3):
+            pp.cycle(cyc >= 1)
+            k_o = orc.orc_eigen_cycle(e, 1 if cyc >= 1 else 0, k_o)
+            assert not np.isnan(k_o), ol.err(orc)
+            for a, b, what in zip(pp.bank(), oracle_bank(orc, e), ("r", "dir", "w", "E")):
+                assert np.array_equal(a, b), "fission bank (%s) differs after cycle %d" % (what, cyc)
+            assert pp.k == pytest.approx(k_o, rel=1e-11)
         pp.close(); orc.orc_eigen_free(e)
     finally:
         orc.orc_set_math_mode(0)
