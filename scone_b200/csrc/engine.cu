@@ -27,6 +27,7 @@
 #include "sb_track.cuh"
 #include "sb_ce.cuh"
 #include "sb_cehist.cuh"
+#include "sb_ceevent.cuh"
 
 using namespace sbd;
 using sbh::Bank; using sbh::CycleDev; using sbh::HistArgs; using sbh::HotLayout; using sbh::HUni;
@@ -550,6 +551,7 @@ struct sb_engine {
   double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
   double* dStage = nullptr; size_t stageBytes = 0;
   // continuous-energy transport model (sb_load_ce_model)
+  char* dCeSlots = nullptr; size_t ceSlotCount = 0;
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
   sbce::CeHost ce; int* dCeErr = nullptr; cudaEvent_t evC0 = nullptr, evC1 = nullptr; float ceLastMs = 0.f;
 };
@@ -805,7 +807,8 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
-  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr);
+  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots);
+  for (void* p : h->ceAllocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1036,6 +1039,15 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.needMacro = 0;
     for (const DClerk& k : h->clerks[phase]) for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1;
     const char* cfg = getenv("SB_CE_KERNEL");                  // experiment switch: "async" = 128-thread CTAs without phase barriers
+    if (cfg && (!strcmp(cfg, "events") || !strcmp(cfg, "events1024"))) {   // event queues over slots in global memory (sb_ceevent.cuh)
+      const int slotsPerCta = !strcmp(cfg, "events") ? 512 : 1024;
+      const size_t need = (size_t)h->numSM * slotsPerCta;
+      if (need > h->ceSlotCount) { cudaFree(h->dCeSlots); h->dCeSlots = nullptr; CUDA_OK(cudaMalloc(&h->dCeSlots, sbc::CeSlots::bytes(need))); h->ceSlotCount = need; }
+      sbc::CeEventArgs ea{t, sbc::CeSlots{}};
+      ea.S.carve(h->dCeSlots, h->ceSlotCount);
+      if (slotsPerCta == 512) sbc::k_events_ce<512, 512><<<h->numSM, 512, 0, st>>>(ea);
+      else sbc::k_events_ce<512, 1024><<<h->numSM, 512, 0, st>>>(ea);
+    } else
     if (cfg && !strcmp(cfg, "async")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync256")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM * 2, (n + 255) / 256), 256, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync256x1")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM, (n + 255) / 256), 256, 0, st>>>(t);

@@ -21,12 +21,16 @@ using sbh::rngGet;
 constexpr int COLL_EV = 1, BOUNDARY_EV = 2, CROSS_EV = 3;
 constexpr int PIN_MOVING_IN = -1, PIN_MOVING_OUT = -2, LAT_OUTLINE_SURF = -7;
 
+#ifndef SB_COORD_NEST
+#define SB_COORD_NEST 12              // capacity of the coordList (hardcoded max nesting of the reference, universalVariables.f90 MAX_NEST... = 12 here)
+#endif
+constexpr int COORD_NEST = SB_COORD_NEST;
 struct Coords {                       // coordList (coord_class.f90:33-115), without the rotation matrices (read from the universe)
-  double r[MAX_NEST][3], u[MAX_NEST][3];
-  int uni[MAX_NEST], root[MAX_NEST], local[MAX_NEST];
+  double r[COORD_NEST][3], u[COORD_NEST][3];
+  int uni[COORD_NEST], root[COORD_NEST], local[COORD_NEST];
   int nesting, mat, uid;
 };
-struct DistCache { int lvl; double dist[MAX_NEST]; int surf[MAX_NEST]; };
+struct DistCache { int lvl; double dist[COORD_NEST]; int surf[COORD_NEST]; };
 
 // The geometry procedures below are called from several places of the event loop; they are kept out of line (one copy each)
 // so that the loop body stays within the instruction cache (the fully inlined CE kernel was 585 KB of SASS and stalled on
@@ -36,10 +40,10 @@ __device__ __noinline__ double surfDistanceNI(int type, const double* p, const d
 
 // geometryStd%diveToMat from level `start` (1-based) ; levels below are (re)entered
 __device__ __noinline__ bool diveToMat(const Tables& T, Coords& c, int start) {
-  for (int i = start; i <= MAX_NEST; ++i) {
+  for (int i = start; i <= COORD_NEST; ++i) {
     int2 f = T.graph[c.root[i - 1] + c.local[i - 1] - 2];
     if (f.x >= 0) { c.mat = f.x; c.uid = f.y; return true; }
-    if (i == MAX_NEST) break;
+    if (i == COORD_NEST) break;
     double off[3]; uniCellOffset(T, c.uni[i - 1], c.local[i - 1], off);
     int ui = -f.x - 1;
     bool glob = T.uniIpar[ui * SB_UNI_NIPAR + 1] != 0;

@@ -104,6 +104,31 @@ def test_ce_assembly_20_nuclides_bit_exact_against_oracle(orc):
         orc.orc_set_math_mode(0)
 
 
+def test_ce_event_queue_kernel_equals_lockstep_kernel(monkeypatch):
+    """The event-queue formulation (sb_ceevent.cuh: slots in global memory, per-phase queues, full warps) follows the same
+    histories as the lane-resident kernel: banks bit-identical, k equal to summation-order rounding."""
+    ov = "pop 6000; inactive 1; active 2; seed 11;"
+    monkeypatch.delenv("SB_CE_KERNEL", raising=False)
+    a = scone_b200.EigenPhysicsPackage(DECK, ov, device=0)
+    a.generateInitialState()
+    ra = []
+    for cyc in range(3):
+        a.cycle(cyc >= 1); ra.append((a.bank(), a.k))
+    ta = a.tally(True)[0]
+    a.close()
+    for cfg in ("events", "events1024"):
+        monkeypatch.setenv("SB_CE_KERNEL", cfg)
+        b = scone_b200.EigenPhysicsPackage(DECK, ov, device=0)
+        b.generateInitialState()
+        for cyc in range(3):
+            b.cycle(cyc >= 1)
+            for x, y in zip(b.bank(), ra[cyc][0]):
+                assert np.array_equal(x, y)
+            assert b.k == pytest.approx(ra[cyc][1], rel=1e-12)
+        np.testing.assert_allclose(b.tally(True)[0], ta, rtol=1e-10, atol=1e-300)
+        b.close()
+
+
 def test_ce_nuclides_on_engine_match_oracle(orc):
     """What sb_load_ce_model built (energy grids, main data, MT order) is what the oracle builds from the same cards."""
     pp = scone_b200.EigenPhysicsPackage(DECK, "pop 100;", device=0)
