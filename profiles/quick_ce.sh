@@ -1,5 +1,5 @@
-# quick A/B (not a benchmark of record): coordList capacity 4 instead of 12
-for cfg in sync512 events1024; do
+# quick A/B (not a benchmark of record): more warps per SM at fewer registers per thread
+for cfg in sync768 sync1024; do
 for deck in ce_pin; do
 for pop in 100000 1000000; do
 SB_CE_KERNEL=$cfg python bench.py --deck $deck --no-extras --no-cpu-baseline --steps 4 --warmup 3 --inactive 3 --pop $pop 2>&1 | python -c "
@@ -10,9 +10,3 @@ for l in sys.stdin:
     else: print(l.rstrip())
 "
 done; done; done
-SB_FORCE_TRACK_KERNEL=1 python bench.py --deck c5g7 --tracking ST --no-extras --no-cpu-baseline --steps 8 --warmup 3 --inactive 4 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('C5G7 ST: %.3e n/s  %.2f ms/step  seg/s %.3e' % (d['value'], d['ms_per_step'], d['segments_per_s']))
-"

@@ -1050,10 +1050,12 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     } else
     if (cfg && !strcmp(cfg, "async")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync256")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM * 2, (n + 255) / 256), 256, 0, st>>>(t);
+    else if (cfg && !strcmp(cfg, "sync768")) sbc::k_histories_ce<768, 1, true><<<std::min(h->numSM, (n + 767) / 768), 768, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync256x1")) sbc::k_histories_ce<256, 2, true><<<std::min(h->numSM, (n + 255) / 256), 256, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync128x1")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM, (n + 127) / 128), 128, 0, st>>>(t);
     else if (cfg && !strcmp(cfg, "sync64x1")) sbc::k_histories_ce<128, 4, false><<<std::min(h->numSM, (n + 63) / 64), 64, 0, st>>>(t);
-    else sbc::k_histories_ce<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, 0, st>>>(t);
+    else if ((cfg && !strcmp(cfg, "sync512")) || (!cfg && n < 400000)) sbc::k_histories_ce<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, 0, st>>>(t);
+    else sbc::k_histories_ce<1024, 1, true><<<std::min(h->numSM, (n + 1023) / 1024), 1024, 0, st>>>(t);   // large banks: 32 warps per SM at 64 registers hide more latency (120 -> 108 ms at 1e6)
   } else
   if (useTrack) {                                             // surface / hybrid tracking: coordList-carrying kernel
     sbt::TrackArgs t{};
