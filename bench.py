@@ -332,7 +332,8 @@ def main():
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,
-                "note": "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)"}
+                "note": ("lane-resident histories in CTA-lockstep phases: bound by instruction fetch, barrier wait and memory latency at 16-32 warps per SM, not by HBM (DESIGN.md section 4, profiles/README.md)"
+                         if kname != "k_histories" else "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)")}
 
     # ---- extras (N = 1 only): the same deck at a GPU-sized population, and the CE XS-lookup kernel ----------------
     large = None; ce = None
