@@ -516,6 +516,112 @@ nuclearData {
 """ % dict(pop=pop, inactive=inactive, active=active, seed=seed, map=fmt_map(rows), fuel=" ".join(fuel), water=" ".join(water))
 
 
+def fixed_mg(pop=100000, cycles=50, seed=20261017):
+    """Fixed-source multigroup problem (fixedSourcePhysicsPackage): isotropic group-1 point source in a UO2 sphere inside a water
+    box with vacuum boundaries (subcritical: fission neutrons are followed as secondaries of the same history)."""
+    return """// fixed-source multigroup: point source in a small UO2 sphere (C5G7 constants), vacuum box
+type fixedSourcePhysicsPackage;
+pop      %(pop)d;
+cycles   %(cycles)d;
+seed     %(seed)d;
+XSdata   mg;
+dataType mg;
+buffer   50;
+
+collisionOperator { neutronMG { type neutronMGstd; } }
+transportOperator { type transportOperatorDT; }
+
+source { type pointSource; r (0.1 0.2 0.3); particle neutron; G 1; }
+
+tally {
+  norm fiss; normVal 100;
+  fiss { type collisionClerk; response (fiss); fiss { type macroResponse; MT -6; } }
+  flux { type collisionClerk; map { type spaceMap; axis x; grid lin; min -5.0; max 5.0; N 20; } response (flux abs); flux { type fluxResponse; } abs { type macroResponse; MT -2; } }
+}
+
+geometry {
+  type geometryStd;
+  boundary (0 0 0 0 0 0);
+  graph { type shrunk; }
+  surfaces {
+    ball  { id 1; type sphere; origin (0.0 0.0 0.0); radius 3.0; }
+    bound { id 2; type box; origin (0.0 0.0 0.0); halfwidth (5.0 5.0 5.0); }
+  }
+  cells {
+    in  { id 1; type simpleCell; surfaces (-1); filltype mat; material UO2; }
+    out { id 2; type simpleCell; surfaces (1);  filltype mat; material water; }
+  }
+  universes {
+    root { id 1; type rootUniverse; border 2; fill u<2>; }
+    geom { id 2; type cellUniverse; cells (1 2); }
+  }
+}
+
+nuclearData {
+  handles { mg { type baseMgNeutronDatabase; PN P0; } }
+  materials {
+    UO2   { temp 300; xsFile ../c5g7/xs/UO2.xs; composition { } }
+    water { temp 300; xsFile ../c5g7/xs/moder.xs; composition { } }
+  }
+}
+""" % dict(pop=pop, cycles=cycles, seed=seed)
+
+
+def fixed_ce(pop=100000, cycles=20, seed=20261017):
+    """Fixed-source continuous-energy problem in the spirit of the reference's InputFiles/sphere_with_DT: 14.1 MeV point source in
+    a hollow fuel sphere (the bundled nuclides), vacuum boundary, surface tracking."""
+    return """// fixed-source continuous energy: 14.1 MeV point source in a fuel sphere (InputFiles/sphere_with_DT with the bundled nuclides)
+type fixedSourcePhysicsPackage;
+pop      %(pop)d;
+cycles   %(cycles)d;
+seed     %(seed)d;
+XSdata   ce;
+dataType ce;
+
+collisionOperator { neutronCE { type neutronCEstd; } }
+transportOperator { type transportOperatorST; }
+
+source { type pointSource; r (0.0 0.0 0.0); particle neutron; E 14.1; }
+
+tally {
+  fiss { type collisionClerk; response (fiss); fiss { type macroResponse; MT -6; } }
+  flux { type collisionClerk;
+         map { type multiMap; maps (ene mat);
+               ene { type energyMap; grid log; min 0.001; max 20.0; N 100; }
+               mat { type materialMap; materials (fuel water); } }
+         response (flux); flux { type fluxResponse; } }
+}
+
+geometry {
+  type geometryStd;
+  boundary (0 0 0 0 0 0);
+  graph { type shrunk; }
+  surfaces {
+    hollow { id 1; type sphere; origin (0.0 0.0 0.0); radius 0.5; }
+    fuel   { id 2; type sphere; origin (0.0 0.0 0.0); radius 4.0; }
+    bound  { id 3; type sphere; origin (0.0 0.0 0.0); radius 6.0; }
+  }
+  cells {
+    inside { id 1; type simpleCell; surfaces (-1);   filltype mat; material water; }
+    fuel   { id 2; type simpleCell; surfaces (1 -2); filltype mat; material fuel; }
+    refl   { id 3; type simpleCell; surfaces (2);    filltype mat; material water; }
+  }
+  universes {
+    root { id 1; type rootUniverse; border 3; fill u<2>; }
+    geom { id 2; type cellUniverse; cells (1 2 3); }
+  }
+}
+
+nuclearData {
+  handles { ce { type aceNeutronDatabase; aceLibrary ../../tests/golden/ace/aceLib; ures 0; majorant 1; } }
+  materials {
+    fuel  { temp 293; composition { 92233.03 1.0E-3; 52126.03 2.2E-2; 91231.03 5.0E-5; 91232.03 2.0E-6; } }
+    water { temp 293; composition { 1001.03 6.67E-2; 52126.03 1.0E-3; } }
+  }
+}
+""" % dict(pop=pop, cycles=cycles, seed=seed)
+
+
 def write(outdir):
     def put(rel, text):
         p = os.path.join(outdir, rel)
@@ -533,6 +639,8 @@ def write(outdir):
     put("urr/slab", urr_deck("slab"))
     synth_ace_cards(outdir)
     put("ce/assembly17", ce_assembly17())
+    put("fixed/mg_sphere", fixed_mg())
+    put("fixed/ce_sphere", fixed_ce())
 
 
 if __name__ == "__main__":

@@ -190,6 +190,22 @@ int sb_bank_download_ce(sb_engine* h, int cap, int* n, double* r, double* dir, d
 /* fissionSource%generate on the device (ParticleObjects/Source/fissionSource_class.f90:149-271) */
 int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offset);
 
+/* ---- fixed-source calculations: PhysicsPackages/fixedSourcePhysicsPackage_class.f90:149-289 ---------------------------------
+ * sb_set_fixed_source(on, buffer_size): particles banked by a collision (implicit fission sites) are not the next generation but
+ * secondaries of the SAME history: they go to the history's private buffer (`buffer`, default 50, :318) and are followed, last in
+ * first out, when the current particle dies, on the history's random stream (the bufferLoop, :198-246). Exceeding buffer_size is
+ * the reference's "Run out of space for particles" error. A cycle is then sb_source_point (or sb_bank_upload of any source the
+ * caller sampled) followed by sb_run_cycle with phase 1 and k_eff 1: transport + tallies + closeCycle; no normalisation of a bank.
+ * sb_source_point = pointSource%sampleParticle for n particles (ParticleObjects/Source/pointSource_class.f90:142-200,
+ * configSource_inter.f90:75-90): particle i uses rng_state skipped by 152917*(history_offset+i).                              */
+typedef struct sb_point_source {
+  double r[3], dir[3]; int32_t isotropic;          /* dir is used (already normalised) when isotropic == 0 */
+  int32_t is_mg; double E; int32_t G;               /* E [MeV] for continuous energy; G, or prob_g[n_prob] (normalised), for multigroup */
+  int32_t n_prob; const double* prob_g;
+} sb_point_source;
+int sb_set_fixed_source(sb_engine* h, int on, int buffer_size);
+int sb_source_point(sb_engine* h, int n, uint64_t rng_state, int history_offset, const sb_point_source* s);
+
 /* ---- the cycle ------------------------------------------------------------------------------
  * Transports every history of the current bank to its death (transport + collide + tallies +
  * fission-site banking), closes the cycle's tallies (reduceBins, closeCycle with normalisation,

@@ -367,6 +367,9 @@ int orc_eigen_init_source(void* ev) { ORC_TRY ((EigenPP*)ev)->generateInitialSta
 double orc_eigen_cycle(void* ev, int active, double k_in) {
   ORC_TRY return ((EigenPP*)ev)->cycle(active != 0, k_in); ORC_CATCH(std::nan(""))
 }
+// fixedSourcePhysicsPackage: one source batch (returns 0 / -1); pop, cycles via orc_eigen_info
+int orc_fixed_cycle(void* ev) { ORC_TRY ((EigenPP*)ev)->fixedCycle(); return 0; ORC_CATCH(-1) }
+int orc_eigen_is_fixed(void* ev) { return ((EigenPP*)ev)->fixedSource ? 1 : 0; }
 int orc_eigen_run(void* ev) { ORC_TRY ((EigenPP*)ev)->run(); return 0; ORC_CATCH(-1) }
 int orc_eigen_bank_size(void* ev) { return ((EigenPP*)ev)->thisCycle->pop; }
 // current source bank (thisCycle) as SoA

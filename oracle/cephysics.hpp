@@ -224,9 +224,7 @@ struct CeEigenPP : EigenPP {
   double minE = orc_ce::MINIMUM_ENERGY, maxE = orc_ce::MAXIMUM_ENERGY, threshE = 400.0, threshA = 1.0;
 
   void init(const Dict& dict, const std::string& baseDir) override {   // eigenPhysicsPackage_class.f90:417-645 with dataType ce
-    pop = dict.getInt("pop");
-    N_inactive = dict.getInt("inactive");
-    N_active = dict.getInt("active");
+    initCycles(dict);
     std::string nucData = dict.getWord("XSdata");
     if (dict.getWord("dataType") != "ce") throw FatalError("init (eigenPhysicsPackage)", "oracle CE driver: dataType must be 'ce'");
     if (!dict.isPresent("seed")) throw FatalError("init (eigenPhysicsPackage)", "oracle requires an explicit seed");
@@ -255,6 +253,12 @@ struct CeEigenPP : EigenPP {
     else if (tt == "transportOperatorST") { tracking = TRACK_ST; stCache = to.getBool("cache", true); }
     else if (tt == "transportOperatorHT") { tracking = TRACK_HT; htCutoff = to.getReal("cutoff", 0.9); stCache = to.getBool("cache", true); }
     else throw FatalError("new_transportOperator", "Unrecognised type of transportOperator: " + tt);
+    if (fixedSource) {
+      activeTally.init(dict.getDict("tally"), mats);
+      inactiveTally.init(Dict::fromString(""), mats);
+      initPointSource(dict.getDict("source"), 0);
+      return;
+    }
     inactiveTally.init(dict.getDict("inactiveTally"), mats);
     activeTally.init(dict.getDict("activeTally"), mats);
     if (dict.isPresent("source")) throw FatalError("init (eigenPhysicsPackage)", "oracle supports the default fissionSource only");

@@ -655,14 +655,75 @@ struct EigenPP {
   TallyAdmin inactiveTally, activeTally, inactiveAtch, activeAtch;
   FissionSource source;
   Dungeon dungeonA, dungeonB; Dungeon* thisCycle = &dungeonA; Dungeon* nextCycle = &dungeonB;
+  // fixedSourcePhysicsPackage (PhysicsPackages/fixedSourcePhysicsPackage_class.f90): cycles, private secondary buffer, pointSource
+  bool fixedSource = false; int N_cycles = 0, bufferSize = 50;
+  struct PointSource { Vec3 r, dir; bool isotropic = true, isMG = true; double E = 0.0; int G = 1; std::vector<double> probG; } psrc;
   // statistics the reference does not keep (for the segments/s metric)
   long nSegments = 0, nCollisions = 0, nHistories = 0;
   std::vector<double> cycleK;            // k_new after each cycle (both phases)
 
-  virtual void init(const Dict& dict, const std::string& baseDir) {
+  // the keys the two packages read differently (eigenPhysicsPackage_class.f90:417-470, fixedSourcePhysicsPackage_class.f90:296-330)
+  void initCycles(const Dict& dict) {
+    std::string t = dict.getWord("type", "eigenPhysicsPackage");
+    fixedSource = (t == "fixedSourcePhysicsPackage");
     pop = dict.getInt("pop");
-    N_inactive = dict.getInt("inactive");
-    N_active = dict.getInt("active");
+    if (fixedSource) { N_cycles = dict.getInt("cycles"); bufferSize = dict.getInt("buffer", 50); N_inactive = 0; N_active = N_cycles; }
+    else { N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active"); }
+  }
+  // pointSource%init (ParticleObjects/Source/pointSource_class.f90:60-140)
+  void initPointSource(const Dict& d, int nG) {
+    if (d.getWord("type") != "pointSource") throw FatalError("new_source", "oracle supports pointSource for fixed-source calculations");
+    if (d.getWord("particle", "neutron") != "neutron") throw FatalError("init (pointSource)", "oracle supports neutrons only");
+    auto rr = d.getRealArray("r");
+    if (rr.size() != 3) throw FatalError("init (pointSource)", "Source position must have three components");
+    for (int k = 0; k < 3; ++k) psrc.r[k] = rr[k];
+    int m, uid; geom.whatIsAt(m, uid, psrc.r);
+    if (m == OUTSIDE_MAT) throw FatalError("init (pointSource)", "Source has been placed outside geometry");
+    psrc.isotropic = !d.isPresent("dir");
+    if (!psrc.isotropic) {
+      auto dd = d.getRealArray("dir");
+      if (dd.size() != 3) throw FatalError("init (pointSource)", "Source direction must have three components");
+      double n = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+      for (int k = 0; k < 3; ++k) psrc.dir[k] = dd[k] / n;
+    }
+    bool isCE = d.isPresent("E"), isMGs = d.isPresent("G") || d.isPresent("probG");
+    if (isCE && isMGs) throw FatalError("init (pointSource)", "Source may be either continuous energy or MG, not both");
+    if (isCE) { psrc.E = d.getReal("E"); psrc.isMG = false; }
+    else if (isMGs) {
+      if (d.isPresent("probG") && d.isPresent("G")) throw FatalError("init (pointSource)", "Source may be either monoenergetic or a distribution, not both");
+      if (d.isPresent("probG")) {
+        psrc.probG = d.getRealArray("probG");
+        if ((int)psrc.probG.size() != nG) throw FatalError("init (pointSource)", "Source energy group distribution has the wrong number of groups");
+        double S = 0.0; for (double v : psrc.probG) S += v;
+        for (double& v : psrc.probG) v = v / S;
+      } else psrc.G = d.getInt("G");
+      psrc.isMG = true;
+    } else throw FatalError("init (pointSource)", "Must specify source energy, either Energy(E) or Group distribution (probG)");
+  }
+  // configSource%sampleParticle (configSource_inter.f90:75-90) with the pointSource procedures
+  ParticleState samplePoint(RNG& rand) const {
+    ParticleState p;
+    p.r = psrc.r;
+    if (psrc.isotropic) {
+      double mu = 2.0 * rand.get() - 1.0;
+      double phi = TWO_PI * rand.get();
+      Vec3 ex; ex[0] = 1.0;
+      p.dir = rotateVector(ex, mu, phi);
+    } else p.dir = psrc.dir;
+    if (psrc.isMG) {
+      if (!psrc.probG.empty()) {
+        double r = rand.get(); int g;
+        for (g = 1; g <= (int)psrc.probG.size(); ++g) { r = r - psrc.probG[g - 1]; if (r < 0.0) break; }
+        p.G = g;
+      } else p.G = psrc.G;
+      p.isMG = true;
+    } else { p.E = psrc.E; p.isMG = false; }
+    p.time = 0.0; p.wgt = 1.0;
+    return p;
+  }
+
+  virtual void init(const Dict& dict, const std::string& baseDir) {
+    initCycles(dict);
     std::string nucData = dict.getWord("XSdata");
     std::string energy = dict.getWord("dataType");
     if (energy != "mg") throw FatalError("init (eigenPhysicsPackage)", "oracle MG driver: dataType must be 'mg'");
@@ -684,6 +745,12 @@ struct EigenPP {
     else if (tt == "transportOperatorST") { tracking = TRACK_ST; stCache = to.getBool("cache", true); }
     else if (tt == "transportOperatorHT") { tracking = TRACK_HT; htCutoff = to.getReal("cutoff", 0.9); stCache = to.getBool("cache", true); }
     else throw FatalError("new_transportOperator", "Unrecognised type of transportOperator: " + tt);
+    if (fixedSource) {
+      activeTally.init(dict.getDict("tally"), mats);
+      inactiveTally.init(Dict::fromString(""), mats);
+      initPointSource(dict.getDict("source"), db.nG);
+      return;
+    }
     inactiveTally.init(dict.getDict("inactiveTally"), mats);
     activeTally.init(dict.getDict("activeTally"), mats);
     if (dict.isPresent("source")) throw FatalError("init (eigenPhysicsPackage)", "oracle supports the default fissionSource only");
@@ -693,6 +760,53 @@ struct EigenPP {
     inactiveTally.atch = &inactiveAtch;
     activeTally.atch = &activeAtch;
   }
+
+  // one source batch: fixedSourcePhysicsPackage_class.f90:149-289 (private buffer only, no common buffer)
+  void fixedCycle() {
+    TallyAdmin& tally = activeTally;
+    thisCycle = &dungeonA;
+    if ((int)dungeonA.prisoners.size() < pop) dungeonA.init(pop);
+    // source%generate (source_inter.f90:98-118)
+    dungeonA.setSize(pop);
+#pragma omp parallel for schedule(static)
+    for (int i = 1; i <= pop; ++i) { RNG pRand = pRNG; pRand.stride(i); dungeonA.prisoners[i - 1] = samplePoint(pRand); }
+    pRNG.stride(pop);
+    tally.reportCycleStart(*thisCycle);
+    long seg = 0, coll = 0;
+#pragma omp parallel reduction(+ : seg, coll)
+    {
+      Dungeon buffer; buffer.init(bufferSize);
+#pragma omp for schedule(dynamic)
+      for (int n = 1; n <= pop; ++n) {
+        RNG rng = pRNG; rng.stride(n);
+        Particle p; p.pRNG = &rng; p.k_eff = 1.0;
+        p.fromState(thisCycle->prisoners[n - 1]);
+        p.isDead = false;
+        for (;;) {                                                   // bufferLoop
+          geom.placeCoord(p.coords);
+          p.preHistory = p.state();
+          p.preCollision = p.state();
+          double trackXS = 0.0;
+          for (;;) {
+            transport(p, tally, trackXS, seg);
+            if (p.isDead) break;
+            collide(p, tally, trackXS, buffer);
+            ++coll;
+            if (p.isDead) break;
+          }
+          if (buffer.pop == 0) break;
+          ParticleState st = buffer.prisoners[buffer.pop - 1];       // release: the last one detained
+          buffer.pop -= 1;
+          p.fromState(st);
+          p.isDead = false;
+        }
+      }
+    }
+    nSegments += seg; nCollisions += coll; nHistories += pop;
+    pRNG.stride(pop);
+    tally.reportCycleEnd(*thisCycle);
+  }
+  void runFixed() { for (int i = 0; i < N_cycles; ++i) fixedCycle(); }
 
   // -------------------------------------------------------------------------
   // transport operators; return with p.isDead or at a real collision site.
@@ -878,6 +992,7 @@ struct EigenPP {
     for (int i = 0; i < N; ++i) k_new = cycle(active, k_new);
   }
   void run() {
+    if (fixedSource) { runFixed(); return; }
     generateInitialState();
     runCycles(false, N_inactive);
     runCycles(true, N_active);

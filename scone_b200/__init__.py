@@ -5,5 +5,5 @@ This package is the thin Python binding used by bench.py and the tests; there is
 creating an engine without the built library or without a CUDA device raises.
 """
 from .lib import load_library, library_path, EngineError  # noqa: F401
-from .physics_package import EigenPhysicsPackage, GeometryHandle, CycleResult  # noqa: F401
+from .physics_package import EigenPhysicsPackage, FixedSourcePhysicsPackage, GeometryHandle, CycleResult  # noqa: F401
 from . import distributed  # noqa: F401,E402

@@ -455,6 +455,30 @@ __global__ void k_source(const Model M, const char* blob, Bank out, int n, uint6
   }
 }
 
+// pointSource%sampleParticle (ParticleObjects/Source/pointSource_class.f90:142-200; configSource_inter.f90:75-90: type, position,
+// energy-angle, energy): particle i draws from rng0 skipped by stride*(offset + i + 1) as source%generate does (source_inter.f90:98-118)
+__global__ void k_source_point(Bank out, int n, uint64_t rng0, int offset, double r0, double r1, double r2, double u0, double u1, double u2,
+                               int isotropic, int isMG, double E, int G, int nProb, const double* probG) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint64_t rng = rng_skip(rng0, RNG_STRIDE * (int64_t)(offset + i + 1));
+    double d[3] = {u0, u1, u2};
+    if (isotropic) {
+      double mu = 2.0 * rng_get(rng) - 1.0;
+      double phi = TWO_PI * rng_get(rng);
+      d[0] = 1.0; d[1] = 0.0; d[2] = 0.0;
+      rotateVector(d, mu, phi);
+    }
+    int g = G;
+    if (isMG && nProb > 0) {
+      double r = rng_get(rng);
+      for (g = 1; g <= nProb; ++g) { r = r - probG[g - 1]; if (r < 0.0) break; }
+    }
+    out.rx[i] = r0; out.ry[i] = r1; out.rz[i] = r2;
+    out.ux[i] = d[0]; out.uy[i] = d[1]; out.uz[i] = d[2];
+    out.w[i] = 1.0; out.G[i] = isMG ? g : 0; out.E[i] = isMG ? 0.0 : E; out.brood[i] = 0; out.seq[i] = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // batch query kernels (parity tests)
 // ------------------------------------------------------------------------------------------------
@@ -552,6 +576,8 @@ struct sb_engine {
   double* dStage = nullptr; size_t stageBytes = 0;
   // continuous-energy transport model (sb_load_ce_model)
   char* dCeSlots = nullptr; size_t ceSlotCount = 0;
+  // fixed-source calculations: private secondary buffers of the lanes
+  bool fixedSource = false; int stkCap = 50; double* dStkD = nullptr; int* dStkG = nullptr; size_t stkLanes = 0; int stkAllocCap = 0;
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
   sbce::CeHost ce; int* dCeErr = nullptr; cudaEvent_t evC0 = nullptr, evC1 = nullptr; float ceLastMs = 0.f;
 };
@@ -807,7 +833,7 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
-  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots);
+  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG);
   for (void* p : h->ceAllocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -986,6 +1012,48 @@ int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offs
   return checkDeviceError(h, h->hCd->error);
 }
 
+int sb_set_fixed_source(sb_engine* h, int on, int buffer_size) {
+  if (on && buffer_size < 1) { h->err = "sb_set_fixed_source: buffer size must be +ve"; return -1; }
+  h->fixedSource = on != 0;
+  if (on) h->stkCap = buffer_size;
+  return 0;
+}
+int sb_source_point(sb_engine* h, int n, uint64_t rng_state, int history_offset, const sb_point_source* s) {
+  if (!s || n < 1) { h->err = "sb_source_point: invalid arguments"; return -1; }
+  if (buildBlob(h)) return -1;
+  if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->ceMode == (s->is_mg != 0)) { h->err = "sb_source_point: the source energy type (E / G) does not match the loaded nuclear data"; return -1; }
+  const double* dProb = nullptr;
+  if (s->is_mg && s->n_prob > 0) {
+    if (s->n_prob != h->nG) { h->err = "Source energy group distribution must have as many entries as there are groups"; return -1; }
+    if (ensureStage(h, sizeof(double) * 6 * (size_t)h->cap)) return -1;
+    CUDA_OK(cudaMemcpyAsync(h->dStage, s->prob_g, sizeof(double) * s->n_prob, cudaMemcpyHostToDevice, h->stream));
+    dProb = h->dStage;
+  } else if (s->is_mg && (s->G < 1 || s->G > h->nG)) { h->err = "sb_source_point: source group outside the group structure"; return -1; }
+  k_source_point<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->bank[h->cur], n, rng_state, history_offset, s->r[0], s->r[1], s->r[2], s->dir[0], s->dir[1], s->dir[2],
+                                                             s->isotropic, s->is_mg, s->E, s->G, s->is_mg ? s->n_prob : 0, dProb);
+  h->launches++;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  h->nCur = n;
+  return 0;
+}
+// lanes x buffer_size entries of { r, dir, w, E } + G
+static int ensureSecStack(sb_engine* h, size_t lanes, sbt::SecStack& out) {
+  out = sbt::SecStack{nullptr, nullptr, h->stkCap, 0};
+  if (!h->fixedSource) return 0;
+  if (lanes > h->stkLanes || h->stkCap > h->stkAllocCap) {
+    cudaFree(h->dStkD); cudaFree(h->dStkG); h->dStkD = nullptr; h->dStkG = nullptr;
+    size_t L = std::max(lanes, h->stkLanes); int cap = std::max(h->stkCap, h->stkAllocCap);
+    CUDA_OK(cudaMalloc(&h->dStkD, sizeof(double) * 8 * (size_t)cap * L));
+    CUDA_OK(cudaMalloc(&h->dStkG, sizeof(int) * (size_t)cap * L));
+    h->stkLanes = L; h->stkAllocCap = cap;
+  }
+  out.d = h->dStkD; out.G = h->dStkG; out.cap = h->stkCap; out.on = 1;
+  return 0;
+}
+
 // transport of the whole bank + brood ordering + per-rank score sums (no cycle close yet)
 static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase) {
   if (phase < 0 || phase > 1) { h->err = "sb_run_cycle: phase must be 0 or 1"; return -1; }
@@ -1014,8 +1082,8 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
-  bool useTrack = h->opt.tracking != SB_TRACK_DT;
-  if (!h->ceMode && h->opt.tracking == SB_TRACK_HT && !getenv("SB_FORCE_TRACK_KERNEL")) {
+  bool useTrack = h->opt.tracking != SB_TRACK_DT || h->fixedSource;      // the DT-only kernel has no secondary buffer
+  if (!h->ceMode && !h->fixedSource && h->opt.tracking == SB_TRACK_HT && !getenv("SB_FORCE_TRACK_KERNEL")) {
     // transportOperatorHT picks delta tracking when Sigma_t / Sigma_maj > 1 - cutoff (transportOperatorHT_class.f90:63-78). If that
     // holds for every (material, group) of the model -- and nothing is void -- the selector is a constant and the flights
     // are exactly deltaTracking's: run the delta-tracking kernel.
@@ -1039,6 +1107,11 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.needMacro = 0;
     for (const DClerk& k : h->clerks[phase]) for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1;
     const char* cfg = getenv("SB_CE_KERNEL");                  // experiment switch: "async" = 128-thread CTAs without phase barriers
+    if (h->fixedSource) {                                      // fixed source: private secondary buffers, lockstep kernel
+      cfg = nullptr;
+      const int threadsF = n < 400000 ? 512 : 1024;
+      if (ensureSecStack(h, (size_t)std::min(h->numSM, (n + threadsF - 1) / threadsF) * threadsF, t.stk)) return -1;
+    }
     if (cfg && (!strcmp(cfg, "events") || !strcmp(cfg, "events1024"))) {   // event queues over slots in global memory (sb_ceevent.cuh)
       const int slotsPerCta = !strcmp(cfg, "events") ? 512 : 1024;
       const size_t need = (size_t)h->numSM * slotsPerCta;
@@ -1065,6 +1138,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
     t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
     const char* cfg = getenv("SB_TRACK_KERNEL");               // experiment switch: "async" = 128-thread CTAs without phase barriers
+    if (h->fixedSource) { cfg = nullptr; if (ensureSecStack(h, (size_t)std::min(h->numSM, (n + 511) / 512) * 512, t.stk)) return -1; }
     if (cfg && !strcmp(cfg, "async")) sbt::k_histories_track<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
     else sbt::k_histories_track<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
   } else

@@ -30,6 +30,8 @@ struct eigenPhysicsPackage {
   int rank = 0, nRanks = 1;
   int rankOffset = 0;                      // getOffset(totalPop) of this rank (mpi_func.f90:133-159)
   sb::FlatGeometry geom; sb::FlatMgData data; sb::FlatCeData ceData; bool isCE = false; sb::TallyDefs tallies[2];
+  // fixedSourcePhysicsPackage (PhysicsPackages/fixedSourcePhysicsPackage_class.f90): cycles, buffer, pointSource
+  bool isFixed = false; int N_cycles = 0, bufferSize = 50; sb_point_source psrc{}; std::vector<double> probG;
   sb_engine* eng = nullptr;
   std::string err;
   // results
@@ -59,12 +61,15 @@ struct eigenPhysicsPackage {
           else dict.setScalar(k, ov.getWord(k));
         }
       }
-      if (dict.getWord("type") != "eigenPhysicsPackage") return fail("only eigenPhysicsPackage decks are driven by this host");
+      const std::string ppType = dict.getWord("type");
+      if (ppType != "eigenPhysicsPackage" && ppType != "fixedSourcePhysicsPackage") return fail("eigenPhysicsPackage and fixedSourcePhysicsPackage decks are driven by this host");
+      isFixed = (ppType == "fixedSourcePhysicsPackage");
       totalPop = dict.getInt("pop");
       // getWorkshare / getOffset (mpi_func.f90:133-159): contiguous shares, the remainder goes to the high ranks
       pop = (totalPop + rank) / nRanks;
       rankOffset = totalPop / nRanks * rank + std::max(0, totalPop % nRanks + rank - nRanks);
-      N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active");
+      if (isFixed) { N_cycles = dict.getInt("cycles"); bufferSize = dict.getInt("buffer", 50); N_inactive = 0; N_active = N_cycles; }
+      else { N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active"); }
       std::string nucData = dict.getWord("XSdata"), energy = dict.getWord("dataType");
       if (energy != "mg" && energy != "ce") return fail("dataType must be 'mg' or 'ce'");
       isCE = (energy == "ce");
@@ -90,9 +95,15 @@ struct eigenPhysicsPackage {
       else if (tt == "transportOperatorST") { opt.tracking = SB_TRACK_ST; opt.st_cache = to.getBool("cache", true) ? 1 : 0; }
       else if (tt == "transportOperatorHT") { opt.tracking = SB_TRACK_HT; opt.ht_cutoff = to.getReal("cutoff", 0.9); opt.st_cache = to.getBool("cache", true) ? 1 : 0; }
       else return fail("Unrecognised type of transportOperator: " + tt);
-      tallies[0] = sb::buildTallies(dict.getDict("inactiveTally"), mats, data.nMat);
-      tallies[1] = sb::buildTallies(dict.getDict("activeTally"), mats, data.nMat);
-      if (dict.isPresent("source")) return fail("only the default fissionSource is supported");
+      if (isFixed) {
+        tallies[0] = sb::buildTallies(sb::Dict::fromString(""), mats, data.nMat);
+        tallies[1] = sb::buildTallies(dict.getDict("tally"), mats, data.nMat);
+        if (int rc = initPointSource(dict.getDict("source"))) return rc;
+      } else {
+        tallies[0] = sb::buildTallies(dict.getDict("inactiveTally"), mats, data.nMat);
+        tallies[1] = sb::buildTallies(dict.getDict("activeTally"), mats, data.nMat);
+        if (dict.isPresent("source")) return fail("only the default fissionSource is supported in eigenvalue calculations");
+      }
 
       if (device < 0) return 0;     // host model only (CPU-side tests of the flattening); no engine, no transport
       if (sb_create(&eng, device)) return fail(sb_last_error(nullptr));
@@ -102,7 +113,52 @@ struct eigenPhysicsPackage {
       for (int ph = 0; ph < 2; ++ph)
         if (sb_define_tallies(eng, ph, tallies[ph].clerks.data(), (int)tallies[ph].clerks.size(), tallies[ph].normClerk, tallies[ph].normVal)) return engFail();
       if (sb_set_options(eng, &opt)) return engFail();
+      if (isFixed && sb_set_fixed_source(eng, 1, bufferSize)) return engFail();
     } catch (const std::exception& e) { return fail(e.what()); }
+    return 0;
+  }
+
+  // pointSource%init (ParticleObjects/Source/pointSource_class.f90:60-140); the OUTSIDE check of the position is the engine's
+  int initPointSource(const sb::Dict& d) {
+    if (d.getWord("type") != "pointSource") return fail("fixed-source calculations: only pointSource is supported");
+    if (d.getWord("particle", "neutron") != "neutron") return fail("init (pointSource): only neutrons are supported");
+    auto rr = d.getRealArray("r");
+    if (rr.size() != 3) return fail("init (pointSource): Source position must have three components");
+    for (int k = 0; k < 3; ++k) psrc.r[k] = rr[k];
+    psrc.isotropic = d.isPresent("dir") ? 0 : 1;
+    psrc.dir[0] = 1.0; psrc.dir[1] = 0.0; psrc.dir[2] = 0.0;
+    if (!psrc.isotropic) {
+      auto dd = d.getRealArray("dir");
+      if (dd.size() != 3) return fail("init (pointSource): Source direction must have three components");
+      double n = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+      for (int k = 0; k < 3; ++k) psrc.dir[k] = dd[k] / n;
+    }
+    const bool srcCE = d.isPresent("E"), srcMG = d.isPresent("G") || d.isPresent("probG");
+    if (srcCE && srcMG) return fail("init (pointSource): Source may be either continuous energy or MG, not both");
+    if (!srcCE && !srcMG) return fail("init (pointSource): Must specify source energy, either Energy(E) or Group distribution (probG)");
+    psrc.is_mg = srcMG ? 1 : 0; psrc.E = 0.0; psrc.G = 1; psrc.n_prob = 0; psrc.prob_g = nullptr;
+    if (srcCE) psrc.E = d.getReal("E");
+    else if (d.isPresent("probG")) {
+      if (d.isPresent("G")) return fail("init (pointSource): Source may be either monoenergetic or a distribution, not both");
+      probG = d.getRealArray("probG");
+      double S = 0.0; for (double v : probG) S += v;
+      for (double& v : probG) v = v / S;
+      psrc.n_prob = (int)probG.size(); psrc.prob_g = probG.data();
+    } else psrc.G = d.getInt("G");
+    if ((psrc.is_mg != 0) == isCE) return fail("init (pointSource): the source energy type does not match dataType");
+    return 0;
+  }
+
+  // one source batch (fixedSourcePhysicsPackage_class.f90:168-268): generate, stride, histories with their secondaries, stride, reportCycleEnd
+  int fixedCycle() {
+    if (!eng) return fail("no engine: this handle was created without a device");
+    if (!isFixed) return fail("not a fixedSourcePhysicsPackage deck");
+    if (nRanks > 1) return fail("fixed-source batches of several ranks: run one package per rank with its own share of pop");
+    if (sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
+    stride(totalPop);
+    if (sb_run_cycle(eng, pRNG, 0, 1.0, 1, &last)) return engFail();
+    stride(totalPop);
+    nSegActive += last.n_segments; nHist += last.n_start;
     return 0;
   }
 
@@ -310,6 +366,8 @@ int sbh_ce_card_process(void* pv, int nuc, int* gridSize, int* rows, int* nMT, d
   return 0;
 }
 int sbh_ce_info(void* pv, int* nNuc, int* nMat) { auto* p = (eigenPhysicsPackage*)pv; *nNuc = (int)p->ceData.cards.size(); *nMat = p->ceData.nMat; return 0; }
+int sbh_fixed_cycle(void* pv, sb_cycle_result* res) { auto* p = (eigenPhysicsPackage*)pv; int rc = p->fixedCycle(); if (res) *res = p->last; return rc; }
+int sbh_eigen_is_fixed(void* pv) { return ((eigenPhysicsPackage*)pv)->isFixed ? 1 : 0; }
 int sbh_eigen_is_ce(void* pv) { return ((eigenPhysicsPackage*)pv)->isCE ? 1 : 0; }
 int sbh_eigen_cycles(void* pv, int active, int N) { return ((eigenPhysicsPackage*)pv)->cycles(active, N); }
 int sbh_eigen_run(void* pv) { return ((eigenPhysicsPackage*)pv)->run(); }

@@ -42,6 +42,7 @@ struct CeArgs {
   uint64_t rng0; int histOffset; double k_eff;
   sbh::CycleDev* cd;
   int tracking; double htCutoff; int stCache;
+  sbt::SecStack stk;
 };
 
 // what the out-of-line device functions need, kept once per CTA in shared memory: a reference to kernel parameters would make
@@ -279,6 +280,8 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
 
   sbt::Coords c; sbt::DistCache cache; cache.lvl = 0;
   bool alive = false, exhausted = false;
+  const int gLane = blockIdx.x * blockDim.x + threadIdx.x, nLanes = gridDim.x * blockDim.x;
+  int nStk = 0;                                                 // fixed source: entries in this history's private buffer
   int hi = -1, nSite = 0, hSeg = 0, mode = 0, u = 1;            // mode: 0 = transport call begins, 1 = delta, 2 = surface; u = union interval of E
   double E = 1.0, w = 0.0, w0 = 0.0, trackXS = 1.0, majXS = 1.0, sigTot = 0.0;
   uint64_t rng = 0;
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
     // ---------------- warp-aggregated allocation of fission-bank slots --------------------------------
     int slot = -1;
     {
-      unsigned spawn = __ballot_sync(FULL, nNew > 0);
+      unsigned spawn = __ballot_sync(FULL, nNew > 0 && !a.stk.on);
       if (spawn) {
         int inc = nNew;
 #pragma unroll
@@ -456,7 +459,10 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         double d[3] = {c.u[0][0], c.u[0][1], c.u[0][2]};
         ceRotate(d, mu, phi);
         if (E_out > ctx.ce.maxE) E_out = ctx.ce.maxE;
-        if (slot >= 0) {
+        if (a.stk.on) {                                     // fixed source: a secondary of this history
+          if (nStk >= a.stk.cap) atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW);
+          else { a.stk.push(nStk, gLane, nLanes, c.r[0], d, wSite * 1.0, E_out, 0); ++nStk; }
+        } else if (slot >= 0) {
           int s = slot + i;
           a.out.rx[s] = c.r[0][0]; a.out.ry[s] = c.r[0][1]; a.out.rz[s] = c.r[0][2];
           a.out.ux[s] = d[0]; a.out.uy[s] = d[1]; a.out.uz[s] = d[2];
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         }
       }
       if (kerr) atomicMax(&a.cd->error, SB_ERR_CE_DATA);
-      nSite += nNew;
+      if (!a.stk.on) nSite += nNew;
     }
     if (SYNC) __syncthreads();
     if (realColl) {
@@ -564,6 +570,18 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         if (u == 0) { atomicMax(&a.cd->error, SB_ERR_CE_ENERGY); died = true; u = 1; }
         else majXS = fmax(majorantAt(X, u, E) + 0.0, collisionXS);
       }
+    }
+    if (died && nStk > 0) {                                  // bufferLoop: release the last particle detained and carry on
+      int Gdummy;
+      --nStk;
+      a.stk.pop(nStk, gLane, nLanes, c.r[0], c.u[0], w, E, Gdummy);
+      w0 = w;
+      if (!sbt::placeCoord(M, T, c)) atomicMax(&a.cd->error, SB_ERR_NEST);
+      mode = 0; cache.lvl = 0;
+      died = false;
+      u = sbce::unionSearch(X, E);
+      if (u == 0) { atomicMax(&a.cd->error, SB_ERR_CE_ENERGY); u = 1; died = true; }
+      else majXS = fmax(majorantAt(X, u, E) + 0.0, collisionXS);
     }
     if (died) {
       a.nsites[hi] = nSite;

@@ -207,6 +207,23 @@ __device__ __noinline__ void coordsRotate(const Tables& T, Coords& c, const doub
   }
 }
 
+// private buffer of a history in a fixed-source calculation (fixedSourcePhysicsPackage_class.f90:198-246): last in, first out.
+// Layout [field][entry][lane] so that the lanes of a warp touch consecutive words.
+struct SecStack {
+  double* d; int* G; int cap; int on;
+  __device__ __forceinline__ size_t at(int field, int entry, int lane, int nLanes) const { return ((size_t)field * cap + entry) * nLanes + lane; }
+  __device__ __forceinline__ void push(int entry, int lane, int nLanes, const double r[3], const double u[3], double w, double E, int g) const {
+    d[at(0, entry, lane, nLanes)] = r[0]; d[at(1, entry, lane, nLanes)] = r[1]; d[at(2, entry, lane, nLanes)] = r[2];
+    d[at(3, entry, lane, nLanes)] = u[0]; d[at(4, entry, lane, nLanes)] = u[1]; d[at(5, entry, lane, nLanes)] = u[2];
+    d[at(6, entry, lane, nLanes)] = w; d[at(7, entry, lane, nLanes)] = E; G[(size_t)entry * nLanes + lane] = g;
+  }
+  __device__ __forceinline__ void pop(int entry, int lane, int nLanes, double r[3], double u[3], double& w, double& E, int& g) const {
+    r[0] = d[at(0, entry, lane, nLanes)]; r[1] = d[at(1, entry, lane, nLanes)]; r[2] = d[at(2, entry, lane, nLanes)];
+    u[0] = d[at(3, entry, lane, nLanes)]; u[1] = d[at(4, entry, lane, nLanes)]; u[2] = d[at(5, entry, lane, nLanes)];
+    w = d[at(6, entry, lane, nLanes)]; E = d[at(7, entry, lane, nLanes)]; g = G[(size_t)entry * nLanes + lane];
+  }
+};
+
 struct TrackArgs {
   Model M; const char* blob; int useSmem;
   const ulonglong2* seedTab;
@@ -216,6 +233,7 @@ struct TrackArgs {
   uint64_t rng0; int histOffset; double k_eff;
   sbh::CycleDev* cd;
   int tracking; double htCutoff; int stCache;
+  SecStack stk;
 };
 
 // collisionClerk / keffImplicitClerk scoring of one collision (virtual or real), generic tables
@@ -269,6 +287,8 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
 
   Coords c; DistCache cache; cache.lvl = 0;
   bool alive = false, exhausted = false;
+  const int gLane = blockIdx.x * blockDim.x + threadIdx.x, nLanes = gridDim.x * blockDim.x;
+  int nStk = 0;                                                 // fixed source: entries in this history's private buffer
   int hi = -1, G = 1, nSite = 0, hSeg = 0, mode = 0;          // mode: 0 = transport call begins, 1 = delta, 2 = surface
   double w = 0.0, w0 = 0.0, trackXS = 1.0;
   uint64_t rng = 0;
@@ -310,6 +330,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
     if (alive) {
       if (mode == 0) {                                      // transportOperator%transport begins
         if (a.tracking == SB_TRACK_ST) mode = 2;
+        else if (a.tracking == SB_TRACK_DT) mode = 1;
         else {                                              // transportOperatorHT_class.f90:49-81
           double majorant_inv = 1.0 / mgMajorant(M, T, G);
           double sigmaT = (c.mat == SB_VOID_MAT) ? 0.0 : mgRow(M, T, c.mat, G)[XS_TOTAL] + 0.0;
@@ -388,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
     // ---------------- warp-aggregated allocation of fission-bank slots --------------------------------
     int slot = -1;
     {
-      unsigned spawn = __ballot_sync(FULL, nNew > 0);
+      unsigned spawn = __ballot_sync(FULL, nNew > 0 && !a.stk.on);
       if (spawn) {
         int inc = nNew;
 #pragma unroll
@@ -432,6 +453,9 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
           double sc = fmax(w - wPre, 0.0);
           if (sc > 0.0) sScat += sc;
           mode = 0;                                          // the next flight is a new transport call
+        } else if (a.stk.on) {                               // fixed source: a secondary of this history
+          if (nStk >= a.stk.cap) atomicMax(&a.cd->error, SB_ERR_BANK_OVERFLOW);
+          else { a.stk.push(nStk, gLane, nLanes, c.r[0], d, wSite, 0.0, Gout); ++nStk; }
         } else if (slot >= 0) {
           int s = slot + i;
           a.out.rx[s] = c.r[0][0]; a.out.ry[s] = c.r[0][1]; a.out.rz[s] = c.r[0][2];
@@ -439,9 +463,18 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
           a.out.w[s] = wSite; a.out.G[s] = Gout; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
         }
       }
-      nSite += nNew;
+      if (!a.stk.on) nSite += nNew;
       if (MT == 3 || MT == 4) died = true;
       if (MT == 1) mode = 0;
+    }
+    if (died && nStk > 0) {                                  // bufferLoop: release the last particle detained and carry on (:232-236)
+      double Edummy;
+      --nStk;
+      a.stk.pop(nStk, gLane, nLanes, c.r[0], c.u[0], w, Edummy, G);
+      w0 = w;
+      if (!placeCoord(M, T, c)) atomicMax(&a.cd->error, SB_ERR_NEST);
+      mode = 0; cache.lvl = 0;
+      died = false;
     }
     if (died) {
       a.nsites[hi] = nSite;

@@ -77,6 +77,17 @@ class GeometryHandle(_Base):
             self.h = None
 
 
+class FixedSourcePhysicsPackage:
+    """fixedSourcePhysicsPackage on the B200 engine: the same handle as EigenPhysicsPackage, created from a deck of that type."""
+
+    def __new__(cls, deck, overrides="", device=0):
+        pp = EigenPhysicsPackage(deck, overrides, device)
+        if not pp.is_fixed_source:
+            pp.close()
+            raise EngineError("%s is not a fixedSourcePhysicsPackage deck" % deck)
+        return pp
+
+
 class EigenPhysicsPackage(_Base):
     """eigenPhysicsPackage on the B200 engine.
 
@@ -136,6 +147,18 @@ class EigenPhysicsPackage(_Base):
         self.generateInitialState()
         self.cycles(False, self.n_inactive)
         return self.cycles(True, self.n_active)
+
+    # -- fixedSourcePhysicsPackage (decks of that type; n_active = cycles) -------------------------------
+    @property
+    def is_fixed_source(self):
+        return bool(self.L.sbh_eigen_is_fixed(self.h))
+
+    def fixed_cycle(self):
+        """One source batch: pointSource, histories with their secondaries, tallies closed. Returns the CycleResult."""
+        res = CycleResult()
+        if self.L.sbh_fixed_cycle(self.h, C.byref(res)) != 0:
+            raise EngineError(self._err())
+        return res
 
     # -- data access ------------------------------------------------------------------------------
     @property

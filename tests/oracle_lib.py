@@ -125,7 +125,7 @@ def load():
         "orc_ce_db_union": (i32, [vp, c_dp, c_dp]), "orc_ce_db_total_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]),
         "orc_ce_db_macro_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]), "orc_ce_db_majorant_n": (i32, [vp, C.c_long, c_dp, c_dp]),
         "orc_ce_db_index_n": (i32, [vp, i32, C.c_long, c_dp, c_ip]),
-        "orc_eigen_bank_E": (i32, [vp, c_dp]),
+        "orc_eigen_bank_E": (i32, [vp, c_dp]), "orc_fixed_cycle": (i32, [vp]), "orc_eigen_is_fixed": (i32, [vp]),
         "orc_tabpdf_sample": (dbl, [i32, c_dp, c_dp, c_dp, i32, dbl]),
         "orc_endftable_at": (dbl, [i32, c_dp, c_dp, i32, c_ip, c_ip, dbl]),
         "orc_ce_nuclide_from_acebin": (vp, [C.c_char_p]), "orc_ce_nuclide_mt_list": (i32, [vp, c_ip, c_ip]),

@@ -146,3 +146,31 @@ def test_host_card_processing_matches_oracle(orc):
         assert k == nmt.value and np.array_equal(omt[:k], mt[:k])
         orc.orc_ce_nuclide_free(h)
     pp.close()
+
+
+def test_fixed_source_oracle_and_host_model(orc):
+    """fixedSourcePhysicsPackage decks: the oracle runs source batches reproducibly; the product's host model parses the same decks."""
+    import scone_b200
+    for deck, nbins in (("mg_sphere", 1 + 40), ("ce_sphere", 1 + 200)):
+        path = os.path.join(ROOT, "decks", "fixed", deck)
+        out = []
+        for _ in range(2):
+            e = orc.orc_eigen_load(path.encode(), b"pop 1500; cycles 2; seed 3;")
+            assert e, ol.err(orc)
+            assert orc.orc_eigen_is_fixed(e) == 1
+            for _c in range(2):
+                assert orc.orc_fixed_cycle(e) == 0, ol.err(orc)
+            n = orc.orc_eigen_tally_size(e, 1)
+            assert n == nbins
+            cs = np.zeros(n); cs2 = np.zeros(n); b = C.c_int()
+            orc.orc_eigen_tally(e, 1, ol.dp(cs), ol.dp(cs2), C.byref(b))
+            seg, coll, hist = C.c_long(), C.c_long(), C.c_long()
+            orc.orc_eigen_stats(e, C.byref(seg), C.byref(coll), C.byref(hist))
+            out.append((cs, seg.value, coll.value))
+            assert b.value == 2 and hist.value == 3000 and cs.sum() > 0
+            orc.orc_eigen_free(e)
+        assert out[0][1:] == out[1][1:]
+        np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-12)
+        pp = scone_b200.EigenPhysicsPackage(path, "pop 100;", device=-1)
+        assert pp.is_fixed_source and pp.is_ce == (deck == "ce_sphere")
+        pp.close()
