@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
 
   for (;;) {
     if (threadIdx.x < Q_COUNT) Q.n[threadIdx.x] = 0;
+    const int exhaustedBefore = s_exhausted;          // read before the barrier: the refill phase below is the only writer
     __syncthreads();
     // ---------------- refill: dead slots claim histories ----------------------------------------------------------
     for (int pss = 0; pss < NPASS; ++pss) {
@@ -107,13 +108,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
       const bool inRange = si < SLOTS;
       const int g = g0 + si;
       bool alive = inRange && S.alive[g] != 0;
-      const bool want = inRange && !alive && s_exhausted == 0;
+      const bool want = inRange && !alive && exhaustedBefore == 0;
       const unsigned need = __ballot_sync(FULL, want);
       if (need) {
         int b = 0;
         if (lane == __ffs(need) - 1) b = atomicAdd(&a.cd->nextHistory, __popc(need));
         b = __shfl_sync(FULL, b, __ffs(need) - 1);
-        if (b + __popc(need) >= a.n) s_exhausted = 1;                // benign race: every writer writes 1
+        if (b + __popc(need) >= a.n) s_exhausted = 1;                // every writer writes 1; read again after the barrier
         const int my = b + __popc(need & ltMask);
         if (want && my < a.n) {
           CeSlotGeom& sg = S.g[g];
