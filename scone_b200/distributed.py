@@ -176,3 +176,19 @@ def load_balance(pp, comm, sizes):
     comm.exchange(sends, recvs)
     if L.sb_bank_splice(eng, send_down, send_up, recv_down, rd.data_ptr(), recv_up, ru.data_ptr()) != 0:
         raise EngineError(pp._eng_err())
+
+
+def collect_distributed(pp, comm, active=True):
+    """scoreMemory%collectDistributed (Tallies/scoreMemory_class.f90:443-467) at the end of a run whose ranks tallied independently:
+    the cumulative sums, the sums of squares and the batch counts are summed over ranks; the master (rank 0) holds the result and the
+    other ranks are left with a batch count of 0, as in the reference. Returns (csum, csum2, batch_n) as numpy arrays / int."""
+    torch = comm.torch
+    cs, cs2, nb = pp.tally(active)
+    dev = comm.device if comm.on_device else torch.device("cpu")
+    buf = torch.from_numpy(np.concatenate([cs, cs2, [float(nb)]])).to(dev)
+    comm.dist.all_reduce(buf, group=comm.group)              # sum; reduce-to-master semantics are applied below
+    out = buf.cpu().numpy()
+    n = len(cs)
+    if comm.rank == 0:
+        return out[:n].copy(), out[n:2 * n].copy(), int(round(out[2 * n]))
+    return cs, cs2, 0

@@ -26,6 +26,8 @@ for c in range(ninact + nact):
     np.savez(os.path.join(out, "bank_c%d_r%d.npz" % (c, rank)), r=r, d=d, w=w, G=G)
     ks.append(pp.k); segs.append(res.n_segments)
 cs, cs2, nb = pp.tally(True)
+ccs, ccs2, cnb = D.collect_distributed(pp, comm, True)          # tally%collectDistributed: the master holds the sums over ranks
+np.savez(os.path.join(out, "collected_r%d.npz" % rank), cs=ccs, cs2=ccs2, nb=cnb)
 np.savez(os.path.join(out, "final_r%d.npz" % rank), k=np.array(ks), seg=np.array(segs), cs=cs, cs2=cs2, nb=nb, rng=np.array([pp.rng_state], np.uint64))
 pp.close()
 dist.barrier()

@@ -55,6 +55,11 @@ def test_ranked_run_reproduces_single_rank_histories(tmp_path, deck, pop, ws):
     # user tallies: per-rank accumulation, summed at the end (scoreMemory%collectDistributed)
     cs, cs2, nb = pp.tally(True)
     assert sum(int(f["nb"]) for f in fin) == ws * nb           # batch counts are summed over ranks
+    # scoreMemory%collectDistributed: the master ends with the sums over ranks, the others with a batch count of 0
+    col = [np.load(os.path.join(tmp_path, "collected_r%d.npz" % r)) for r in range(ws)]
+    assert int(col[0]["nb"]) == ws * nb and all(int(c["nb"]) == 0 for c in col[1:])
+    np.testing.assert_allclose(col[0]["cs"], sum(f["cs"] for f in fin), rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(col[0]["cs2"], sum(f["cs2"] for f in fin), rtol=1e-13, atol=1e-300)
     if len(cs) and deck == "c5g7":
         # the un-normalised fission map is additive over ranks (a tally with `norm` is normalised per rank, as in SCONE)
         tot = sum(f["cs"] for f in fin)
