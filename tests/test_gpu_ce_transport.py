@@ -178,3 +178,25 @@ def test_ce_statistics_against_oracle_libm(orc):
     s_o = np.sqrt(max(cs2[4] / n / (n - 1) - k_o * k_o / (n - 1), 0.0))
     assert abs(pp.k - k_o) < 3.0 * np.sqrt(res.k_cum_std ** 2 + s_o ** 2) + 1e-4
     orc.orc_eigen_free(e); pp.close()
+
+
+@pytest.mark.parametrize("deck,pop", [(DECK, 1000000), (ASM, 1250000)])
+def test_ce_full_size_invariants(deck, pop):
+    """BASELINE configs[2] / configs[4] populations per GPU (1e6 pin cell; 1e8 / 8 GPUs = 1.25e7 is run at 1.25e6 here to keep the
+    test in seconds): size-independent properties of a cycle -- exact population after normalisation, unit weights, unit
+    directions, energies inside the data bounds, every site in the fuel, k-eff consistent between consecutive cycles."""
+    pp = scone_b200.EigenPhysicsPackage(deck, "pop %d; inactive 2; active 2; seed 99;" % pop, device=0)
+    pp.generateInitialState()
+    ks = []
+    for cyc in range(4):
+        res = pp.cycle(cyc >= 2)
+        assert res.n_start == pop and 0.5 * pop < res.n_sites < 2 * pop
+        ks.append(res.k_analog)
+    r, d, w, E = pp.bank()
+    assert len(w) == pop and np.all(w == 1.0)
+    np.testing.assert_allclose((d * d).sum(1), 1.0, rtol=1e-12)
+    assert E.min() >= 1.0e-11 and E.max() <= 20.0
+    mat, uid, _, _ = pp.geom_query(r, d)
+    assert np.all(mat == 1)                                    # material 1 = fuel: fission sites only
+    assert max(ks) - min(ks) < 0.02
+    pp.close()
