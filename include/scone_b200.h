@@ -131,10 +131,16 @@ typedef struct sb_map1d {
 } sb_map1d;
 #define SB_MAX_MAPS 4
 #define SB_MAX_RESP 8
+/* kind: collisionClerk (maps x responses), or one of the k-eff clerks as a USER clerk of a tally block (the engine always runs
+ * the attachment clerks of eigenPhysicsPackage itself): keffAnalogClerk = 3 bins { start weight, end weight, k }
+ * (keffAnalogClerk_class.f90:40-60,132-176), keffImplicitClerk = 5 bins { IMP_PROD, IMP_ABS, SCATTER_PROD, ANA_LEAK, K_EFF }
+ * (keffImplicitClerk_class.f90:60-75,292-312): the first bins pass through closeCycle (normalised), the k bin is accumulated as is */
+enum { SB_CLERK_COLLISION = 0, SB_CLERK_KEFF_ANALOG = 1, SB_CLERK_KEFF_IMPLICIT = 2 };
 typedef struct sb_clerk {
   int32_t n_maps; sb_map1d maps[SB_MAX_MAPS];   /* multiMap order; 0 maps = single bin        */
   int32_t n_resp; int32_t resp_mt[SB_MAX_RESP]; /* 0 = fluxResponse, else SCONE macro MT (-1..) */
   int32_t handle_virtual;
+  int32_t kind;                                 /* SB_CLERK_*; maps and responses are ignored for the k-eff clerks */
 } sb_clerk;
 
 enum { SB_TRACK_DT = 0, SB_TRACK_ST = 1, SB_TRACK_HT = 2 };

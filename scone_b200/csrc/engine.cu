@@ -189,12 +189,26 @@ __global__ void k_sum_partials(const RedOut* partial, double* ksum, const CycleD
     ksum[6] = (double)min(cd->nSites, cap); ksum[7] = 0.0;      // the bank size rides along with the sums (one all-gather per cycle)
   }
 }
+// k-eff clerks that a tally block names itself (next to the attachment clerks the engine always runs): kind and 1-based address
+struct UserKeff { int n; int kind[4]; int addr[4]; };
 // tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
 //   keffAnalogClerk%closeCycle (keffAnalogClerk_class.f90:156-176), keffImplicitClerk%closeCycle (:292-312)
 __global__ void k_close_cycle_head(const double* ksum, CycleDev* cd, int phase, double kNorm,
-                                   const double* bins, int normAddr, double normVal) {
+                                   double* bins, int normAddr, double normVal, UserKeff uk, double* csum, double* csum2) {
   if (threadIdx.x != 0) return;
   const double prod = ksum[0], abs_ = ksum[1], leak = ksum[2], scat = ksum[3], wgt = ksum[4], endW = ksum[5];
+  for (int i = 0; i < uk.n; ++i) {                          // user clerks: scores into BIN (closed with the other bins), k accumulated directly
+    const int a0 = uk.addr[i] - 1;
+    if (uk.kind[i] == SB_CLERK_KEFF_ANALOG) {               // keffAnalogClerk_class.f90:132-176
+      bins[a0] = wgt; bins[a0 + 1] = endW;
+      const double k = endW / wgt * kNorm;
+      csum[a0 + 2] = csum[a0 + 2] + k; csum2[a0 + 2] = csum2[a0 + 2] + k * k;
+    } else {                                                // keffImplicitClerk_class.f90:180-312
+      bins[a0] = prod; bins[a0 + 1] = abs_; bins[a0 + 2] = scat; bins[a0 + 3] = leak;
+      const double k = prod / (abs_ + leak - scat);
+      csum[a0 + 4] = csum[a0 + 4] + k; csum2[a0 + 4] = csum2[a0 + 4] + k * k;
+    }
+  }
   cd->startWgt = wgt; cd->endWgt = endW;
   cd->impProd = prod; cd->impAbs = abs_; cd->anaLeak = leak; cd->scatProd = scat;
   cd->kAnalog = endW / wgt * kNorm;
@@ -576,6 +590,7 @@ struct sb_engine {
   double* dStage = nullptr; size_t stageBytes = 0;
   // continuous-energy transport model (sb_load_ce_model)
   char* dCeSlots = nullptr; size_t ceSlotCount = 0;
+  UserKeff userKeff[2] = {};
   // fixed-source calculations: private secondary buffers of the lanes
   bool fixedSource = false; int stkCap = 50; double* dStkD = nullptr; int* dStkG = nullptr; size_t stkLanes = 0; int stkAllocCap = 0;
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
@@ -894,8 +909,20 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
   h->mapBounds[phase].resize((size_t)std::max(1, n) * SB_MAX_MAPS); h->mapMat[phase].resize((size_t)std::max(1, n) * SB_MAX_MAPS);
   int memLoc = 1;
   h->normAddr[phase] = 0; h->normVal[phase] = normVal;
+  h->userKeff[phase] = UserKeff{};
   for (int c = 0; c < n; ++c) {
     const sb_clerk& s = clerks[c];
+    if (s.kind == SB_CLERK_KEFF_ANALOG || s.kind == SB_CLERK_KEFF_IMPLICIT) {          // a clerk record without maps and responses keeps the order
+      UserKeff& uk = h->userKeff[phase];
+      if (uk.n >= 4) { h->err = "sb_define_tallies: at most 4 k-eff clerks per tally"; return -1; }
+      uk.kind[uk.n] = s.kind; uk.addr[uk.n] = memLoc; uk.n++;
+      DClerk d; memset(&d, 0, sizeof(d)); d.addr = memLoc; d.handleVirtual = 1;
+      if (normClerk == c + 1) h->normAddr[phase] = memLoc;
+      memLoc += (s.kind == SB_CLERK_KEFF_ANALOG) ? 3 : 5;
+      h->clerks[phase].push_back(d);
+      continue;
+    }
+    if (s.kind != SB_CLERK_COLLISION) { h->err = "sb_define_tallies: unknown clerk kind"; return -1; }
     if (s.n_maps < 0 || s.n_maps > SB_MAX_MAPS || s.n_resp < 1 || s.n_resp > SB_MAX_RESP) { h->err = "sb_define_tallies: invalid clerk"; return -1; }
     DClerk d; memset(&d, 0, sizeof(d));
     d.addr = memLoc; d.nMaps = s.n_maps; d.nResp = s.n_resp; d.handleVirtual = s.handle_virtual;
@@ -1074,6 +1101,9 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   a.n = n; a.in = in; a.out = raw; a.cap = h->cap;
   a.nsites = h->dNsites; a.hProd = h->dHProd; a.hAbs = h->dHAbs; a.hLeak = h->dHLeak; a.hScat = h->dHScat;
   a.bins = h->dBins[phase]; a.phase = phase;
+  int impScores = (phase == 1) ? 1 : 0;                          // the active attachment clerk is keffImplicitClerk; a user clerk may ask for the scores in any phase
+  for (int i = 0; i < h->userKeff[phase].n; ++i) if (h->userKeff[phase].kind[i] == SB_CLERK_KEFF_IMPLICIT) impScores = 1;
+  a.impScores = impScores;
   a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
   a.refillMin = h->refillMin;
   const int threads = 256;
@@ -1103,7 +1133,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.n = n; t.in = in; t.out = raw; t.cap = h->cap;
     t.nsites = h->dNsites; t.hProd = h->dHProd; t.hAbs = h->dHAbs; t.hLeak = h->dHLeak; t.hScat = h->dHScat;
     t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
-    t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
+    t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache; t.impScores = impScores;
     t.needMacro = 0;
     for (const DClerk& k : h->clerks[phase]) for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1;
     const char* cfg = getenv("SB_CE_KERNEL");                  // experiment switch: "async" = 128-thread CTAs without phase barriers
@@ -1136,7 +1166,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.n = n; t.in = in; t.out = raw; t.cap = h->cap;
     t.nsites = h->dNsites; t.hProd = h->dHProd; t.hAbs = h->dHAbs; t.hLeak = h->dHLeak; t.hScat = h->dHScat;
     t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
-    t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache;
+    t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache; t.impScores = impScores;
     const char* cfg = getenv("SB_TRACK_KERNEL");               // experiment switch: "async" = 128-thread CTAs without phase barriers
     if (h->fixedSource) { cfg = nullptr; if (ensureSecStack(h, (size_t)std::min(h->numSM, (n + 511) / 512) * 512, t.stk)) return -1; }
     if (cfg && !strcmp(cfg, "async")) sbt::k_histories_track<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
@@ -1168,7 +1198,8 @@ static int cycleCloseEnqueue(sb_engine* h, const double* dKsum) {
   if (phase < 0) { h->err = "sb_cycle_end: no cycle is open"; return -1; }
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  k_close_cycle_head<<<1, 32, 0, st>>>(dKsum, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase]);
+  k_close_cycle_head<<<1, 32, 0, st>>>(dKsum, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase],
+                                       h->userKeff[phase], h->dCsum[phase], h->dCsum2[phase]);
   int nb = std::max(1, h->nBins[phase]);
   k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
   h->launches += 2;

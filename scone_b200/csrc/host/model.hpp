@@ -500,6 +500,17 @@ inline TallyDefs buildTallies(const Dict& d, const MatMap& mats, int nMat) {
   for (auto& n : d.keys("dict")) {
     const Dict& cd = d.getDict(n);
     std::string t = cd.getWord("type");
+    if (t == "keffAnalogClerk" || t == "keffImplicitClerk") {      // k-eff clerks named by the deck itself: 3 / 5 bins, no maps, no responses
+      sb_clerk c{};
+      c.kind = (t == "keffAnalogClerk") ? SB_CLERK_KEFF_ANALOG : SB_CLERK_KEFF_IMPLICIT;
+      c.handle_virtual = 1;
+      if (t == "keffImplicitClerk" && !cd.getBool("handleVirtual", true)) throw FatalError("init (keffImplicitClerk)", "handleVirtual 0 is not supported by the device tallies");
+      const int w = (c.kind == SB_CLERK_KEFF_ANALOG) ? 3 : 5;
+      T.addr.push_back(memLoc); T.width.push_back(w);
+      memLoc += w;
+      T.clerks.push_back(c); T.names.push_back(n);
+      continue;
+    }
     if (t != "collisionClerk") throw FatalError("new_tallyClerk", "tallyClerk type not supported by the device tallies: " + t);
     if (cd.isPresent("filter")) throw FatalError("init (collisionClerk)", "tally filters are not supported by the device tallies");
     sb_clerk c{};

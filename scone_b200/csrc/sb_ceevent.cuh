@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
   __shared__ EventQueues<SLOTS> Q;
   __shared__ int s_exhausted;
   if (threadIdx.x == 0) {
-    s_ctx.M = a.M; s_ctx.T = bind(a.M, base); s_ctx.ce = a.ce; s_ctx.bins = a.bins; s_ctx.phase = a.phase; s_ctx.needMacro = a.needMacro;
+    s_ctx.M = a.M; s_ctx.T = bind(a.M, base); s_ctx.ce = a.ce; s_ctx.bins = a.bins; s_ctx.phase = a.phase; s_ctx.needMacro = a.needMacro; s_ctx.impScores = a.impScores;
     s_exhausted = 0;
   }
   const CeSlots& S = ea.S;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
         const CeSlotGeom& s = S.g[g];
         double sProd = S.sProd[g], sAbs = S.sAbs[g];
         scoreInCollCE(ctx, base, s.c.r[0], s.c.mat, S.E[g], S.u[g], S.w[g], S.trackXS[g], S.sigTot[g], true, sProd, sAbs, nScore);
-        if (a.phase == 1) { S.sProd[g] = sProd; S.sAbs[g] = sAbs; }
+        if (a.impScores) { S.sProd[g] = sProd; S.sAbs[g] = sAbs; }
       }
     }
     __syncthreads();
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
           ++nColl;
           double sProd = S.sProd[g], sAbs = S.sAbs[g];
           scoreInCollCE(ctx, base, s.c.r[0], mat, E, u, wgt, S.trackXS[g], sigTot, false, sProd, sAbs, nScore);
-          if (a.phase == 1) { S.sProd[g] = sProd; S.sAbs[g] = sAbs; }
+          if (a.impScores) { S.sProd[g] = sProd; S.sAbs[g] = sAbs; }
           const CeNucRec& N = ctx.ce.nuc[nuc0];
           if (N.fissile) {
             double rand1 = rngGet(rng);
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
           double rel = (double)m.TY;
           if (m.relPos) rel = sbk::tapeTableAtNI(tp, m.relPos, E, &kerr, nullptr);
           S.w[g] = wPre * rel;
-          if (a.phase == 1) {
+          if (a.impScores) {
             double score = 0.0;
             if (MTout == 16 || MTout == 11 || MTout == 24 || MTout == 30 || MTout == 41 || (MTout >= 875 && MTout <= 891)) score = 1.0 * wPre;
             else if (MTout == 17 || MTout == 25 || MTout == 42) score = 2.0 * wPre;

@@ -38,7 +38,7 @@ struct CeArgs {
   const ulonglong2* seedTab;
   int n; sbh::Bank in; sbh::Bank out; int cap;
   int* nsites; double *hProd, *hAbs, *hLeak, *hScat;
-  double* bins; int phase; int needMacro;
+  double* bins; int phase; int needMacro; int impScores;
   uint64_t rng0; int histOffset; double k_eff;
   sbh::CycleDev* cd;
   int tracking; double htCutoff; int stCache;
@@ -47,7 +47,7 @@ struct CeArgs {
 
 // what the out-of-line device functions need, kept once per CTA in shared memory: a reference to kernel parameters would make
 // every thread copy them to its stack (params live in the constant bank and have no address)
-struct CeCtx { Model M; Tables T; CeModelDev ce; double* bins; int phase, needMacro; };
+struct CeCtx { Model M; Tables T; CeModelDev ce; double* bins; int phase, needMacro, impScores; };
 
 // ---- cross sections at (E, union interval u) ---------------------------------------------------------------------------
 struct NucPoint { int idx; double f; const double* d; int rows; };
@@ -129,9 +129,9 @@ __device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, con
                                      double w, double trackXS, double sigmaTot, bool virt, double& sProd, double& sAbs, unsigned& nScore) {
   const bool isVoid = (mat == SB_VOID_MAT);
   const int nC = a.M.nClerk[a.phase];
-  if (nC == 0 && a.phase == 0) return;
+  if (nC == 0 && !a.impScores) return;
   double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (!isVoid && (a.needMacro || a.phase == 1)) matMacro(a.ce.xs, u, E, mat, x);
+  if (!isVoid && (a.needMacro || a.impScores)) matMacro(a.ce.xs, u, E, mat, x);
   const double flux = w / trackXS;
   const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
   for (int c = 0; c < nC; ++c) {
@@ -147,7 +147,7 @@ __device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, con
       if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
     }
   }
-  if (a.phase == 1 && !isVoid) {                                                                       // keffImplicitClerk%reportInColl
+  if (a.impScores && !isVoid) {                                                                        // keffImplicitClerk%reportInColl
     sProd += x[5] * flux;
     sAbs += (x[3] + x[4]) * flux;
     nScore += 2;
@@ -267,7 +267,7 @@ template <int THREADS, int BPS, bool SYNC>
 __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
   const char* base = a.blob;
   __shared__ CeCtx s_ctx;
-  if (threadIdx.x == 0) { s_ctx.M = a.M; s_ctx.T = bind(a.M, base); s_ctx.ce = a.ce; s_ctx.bins = a.bins; s_ctx.phase = a.phase; s_ctx.needMacro = a.needMacro; }
+  if (threadIdx.x == 0) { s_ctx.M = a.M; s_ctx.T = bind(a.M, base); s_ctx.ce = a.ce; s_ctx.bins = a.bins; s_ctx.phase = a.phase; s_ctx.needMacro = a.needMacro; s_ctx.impScores = a.impScores; }
   __syncthreads();
   const CeCtx& ctx = s_ctx;
   const Tables& T = s_ctx.T;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
   int hi = -1, nSite = 0, hSeg = 0, mode = 0, u = 1;            // mode: 0 = transport call begins, 1 = delta, 2 = surface; u = union interval of E
   double E = 1.0, w = 0.0, w0 = 0.0, trackXS = 1.0, majXS = 1.0, sigTot = 0.0;
   uint64_t rng = 0;
-  double sProd = 0.0, sAbs = 0.0, sScat = 0.0;
+  double sProd = 0.0, sAbs = 0.0, sScat = 0.0, sLeak = 0.0;     // sLeak: leaked weight of the history (with its secondaries in a fixed-source run)
   unsigned nSeg = 0, nColl = 0, nScore = 0;
   c.nesting = 1; c.mat = SB_UNDEF_MAT; c.uid = -3;
 
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
           w = a.in.w[hi]; w0 = w; E = a.in.E[hi];
           rng = sbh::rngSeed(a.seedTab, a.rng0, (unsigned)(a.histOffset + hi + 1));
           if (!sbt::placeCoord(M, T, c)) atomicMax(&a.cd->error, SB_ERR_NEST);
-          nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0; mode = 0;
+          nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0; sLeak = 0.0; mode = 0;
           alive = true;
           u = sbce::unionSearch(X, E);
           if (u == 0) { atomicMax(&a.cd->error, SB_ERR_CE_ENERGY); u = 1; }
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         double distance = -sbk::kLog(rngGet(rng)) * majorant_inv;
         sbt::geomTeleportCoords(M, T, c, distance);
         ++nSeg; ++hSeg;
-        if (c.mat == SB_OUTSIDE_MAT) { leak = w; died = true; }
+        if (c.mat == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
         else if (c.mat >= SB_OVERLAP_MAT && c.mat != SB_VOID_MAT) { atomicMax(&a.cd->error, c.mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
         else {
           bool virt = true;
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         sbt::geomMove(M, T, c, dist, event, a.stCache ? &cache : nullptr);
         ++nSeg; ++hSeg;
         m = c.mat;
-        if (m == SB_OUTSIDE_MAT) { leak = w; died = true; }
+        if (m == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
         else if (m >= SB_OVERLAP_MAT && m != SB_VOID_MAT) { atomicMax(&a.cd->error, m == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
         else if (event == sbt::COLL_EV) {
           if (rngGet(rng) < sigmaT * invSigmaTrack) realColl = true;
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
       if (E < ctx.ce.minE) died = true;                       // cutoffs
       if (kerr) atomicMax(&a.cd->error, SB_ERR_CE_DATA);
       // keffImplicitClerk%reportOutColl: (n,xn) multiplicities by MT (keffImplicitClerk_class.f90:245-270)
-      if (a.phase == 1 && MT == 2) {
+      if (a.impScores && MT == 2) {
         double score = 0.0;
         if (MTout == 16 || MTout == 11 || MTout == 24 || MTout == 30 || MTout == 41 || (MTout >= 875 && MTout <= 891)) score = 1.0 * wPre;
         else if (MTout == 17 || MTout == 25 || MTout == 42) score = 2.0 * wPre;
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
     }
     if (died) {
       a.nsites[hi] = nSite;
-      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = leak; a.hScat[hi] = sScat;
+      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
       if (hSeg > 256) atomicMax(&a.cd->maxSeg, hSeg);
       alive = false;
     }

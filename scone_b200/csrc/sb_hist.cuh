@@ -70,7 +70,7 @@ struct HistArgs {
   const ulonglong2* seedTab;             // [3][1024] affine maps of the LCG for stride*idx*1024^level
   int n; Bank in; Bank out; int cap;
   int* nsites; double *hProd, *hAbs, *hLeak, *hScat;
-  double* bins; int phase;
+  double* bins; int phase; int impScores;      // impScores: keffImplicitClerk scores wanted (active phase, or a user clerk)
   uint64_t rng0; int histOffset; double k_eff;
   CycleDev* cd; int refillMin;
 };
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
   const int nClerk = a.L.nClerk[0];
   const unsigned char* const scoreMask = (const unsigned char*)(hb + a.L.oScoreMask[0]);
   const int nG = a.L.nG;
-  const bool active = a.phase == 1;
+  const bool active = a.impScores != 0;
 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
   double r0 = 0.0, r1 = 0.0, r2 = 0.0, u0 = 1.0, u1 = 0.0, u2 = 0.0;
   double w = 0.0, w0 = 0.0, flux = 0.0, majInv = 1.0;
   uint64_t rng = 0;
-  double sProd = 0.0, sAbs = 0.0, sScat = 0.0;
+  double sProd = 0.0, sAbs = 0.0, sScat = 0.0, sLeak = 0.0;     // sLeak: leaked weight of the history (with its secondaries in a fixed-source run)
   unsigned nSeg = 0, nColl = 0, nScore = 0;        // per lane, over all its histories
 
   for (;;) {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
             // geom%placeCoord of the source site is not needed by delta tracking: the first thing the
             // flight does is teleport + placeCoord (transportOperatorDT_class.f90:57-75)
             majInv = majInvT[G - 1]; flux = w / majT[G - 1];
-            nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0;
+            nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0; sLeak = 0.0;
             alive = true;
             need &= ~(1u << lane);
           }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
         r0 = tr[0]; r1 = tr[1]; r2 = tr[2]; u0 = tu[0]; u1 = tu[1]; u2 = tu[2];
       }
       (void)uid;
-      if (mat == SB_OUTSIDE_MAT) { leak = w; died = true; }                     // LEAK_FATE
+      if (mat == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }                     // LEAK_FATE
       else if (mat >= SB_OVERLAP_MAT && mat != SB_VOID_MAT) {
         atomicMax(&a.cd->error, mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true;
       } else {
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
 
     if (died) {
       a.nsites[hi] = nSite;
-      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = leak; a.hScat[hi] = sScat;
+      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
       if (hSeg > 256) atomicMax(&a.cd->maxSeg, hSeg);
       alive = false;
     }

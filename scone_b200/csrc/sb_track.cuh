@@ -229,7 +229,7 @@ struct TrackArgs {
   const ulonglong2* seedTab;
   int n; sbh::Bank in; sbh::Bank out; int cap;
   int* nsites; double *hProd, *hAbs, *hLeak, *hScat;
-  double* bins; int phase;
+  double* bins; int phase; int impScores;
   uint64_t rng0; int histOffset; double k_eff;
   sbh::CycleDev* cd;
   int tracking; double htCutoff; int stCache;
@@ -258,7 +258,7 @@ __device__ inline void scoreInColl(const TrackArgs& a, const Tables& T, const ch
       if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
     }
   }
-  if (a.phase == 1 && !isVoid) {
+  if (a.impScores && !isVoid) {
     double nuf = fissile ? x[XS_NUFISSION] : 0.0, fis = fissile ? x[XS_FISSION] : 0.0;
     sProd += nuf * flux;
     sAbs += (x[XS_CAPTURE] + fis) * flux;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
   int hi = -1, G = 1, nSite = 0, hSeg = 0, mode = 0;          // mode: 0 = transport call begins, 1 = delta, 2 = surface
   double w = 0.0, w0 = 0.0, trackXS = 1.0;
   uint64_t rng = 0;
-  double sProd = 0.0, sAbs = 0.0, sScat = 0.0;
+  double sProd = 0.0, sAbs = 0.0, sScat = 0.0, sLeak = 0.0;     // sLeak: leaked weight of the history (with its secondaries in a fixed-source run)
   unsigned nSeg = 0, nColl = 0, nScore = 0;
   c.nesting = 1; c.mat = SB_UNDEF_MAT; c.uid = -3;
 
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
           w = a.in.w[hi]; w0 = w; G = a.in.G[hi];
           rng = sbh::rngSeed(a.seedTab, a.rng0, (unsigned)(a.histOffset + hi + 1));
           if (!placeCoord(M, T, c)) atomicMax(&a.cd->error, SB_ERR_NEST);       // geom%placeCoord (eigenPhysicsPackage_class.f90:224)
-          nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0; mode = 0;
+          nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0; sLeak = 0.0; mode = 0;
           alive = true;
         }
         need = __ballot_sync(FULL, !alive);
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
         double distance = -sbm::log(rngGet(rng)) * majorant_inv;
         geomTeleportCoords(M, T, c, distance);
         ++nSeg; ++hSeg;
-        if (c.mat == SB_OUTSIDE_MAT) { leak = w; died = true; }
+        if (c.mat == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
         else if (c.mat >= SB_OVERLAP_MAT && c.mat != SB_VOID_MAT) { atomicMax(&a.cd->error, c.mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
         else {
           bool virt = true;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
         geomMove(M, T, c, dist, event, a.stCache ? &cache : nullptr);
         ++nSeg; ++hSeg;
         m = c.mat;
-        if (m == SB_OUTSIDE_MAT) { leak = w; died = true; }
+        if (m == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
         else if (m >= SB_OVERLAP_MAT && m != SB_VOID_MAT) { atomicMax(&a.cd->error, m == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }
         else if (event == COLL_EV) {
           bool virt = true;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
     }
     if (died) {
       a.nsites[hi] = nSite;
-      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = leak; a.hScat[hi] = sScat;
+      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
       if (hSeg > 256) atomicMax(&a.cd->maxSeg, hSeg);
       alive = false;
     }

@@ -1,0 +1,72 @@
+"""k-eff clerks named by the deck itself (keffAnalogClerk / keffImplicitClerk inside inactiveTally / activeTally / tally, as most of
+the reference's input files have them) next to collision clerks: memory layout, normalisation and accumulated k against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import scone_b200
+from tests import oracle_lib as ol
+from tests.gpu_util import DECK
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TALLY = ("%s { norm fiss; normVal 100; k_ana { type keffAnalogClerk; } "
+         "fiss { type collisionClerk; response (fiss); fiss { type macroResponse; MT -6; } } k_imp { type keffImplicitClerk; } }")
+
+
+@pytest.mark.parametrize("deck,pop,extra", [
+    (DECK["c5g7"], 6000, ""), (DECK["ce_pin"], 2500, ""),
+    (DECK["slab"], 4000, " transportOperator { type transportOperatorST; }")])
+def test_user_keff_clerks_eigen(orc, deck, pop, extra):
+    ov = "pop %d; inactive 2; active 3; seed 21; %s %s%s" % (pop, TALLY % "inactiveTally", TALLY % "activeTally", extra)
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(deck.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(deck, ov, device=0)
+        orc.orc_eigen_init_source(e); pp.generateInitialState()
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(5):
+            pp.cycle(cyc >= 2)
+            k_o = orc.orc_eigen_cycle(e, 1 if cyc >= 2 else 0, k_o)
+            assert pp.k == pytest.approx(k_o, rel=1e-11)
+        for phase, nb_expected in ((0, 2), (1, 3)):
+            n = orc.orc_eigen_tally_size(e, phase)
+            assert n == 3 + 1 + 5
+            cs, cs2, nb = pp.tally(bool(phase))
+            ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+            orc.orc_eigen_tally(e, phase, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+            assert nb == b.value == nb_expected
+            np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+            np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+            assert cs[2] > 0 and cs[8] > 0 and cs[3] == pytest.approx(100.0 * nb)      # k bins filled, norm applied to the fission bin
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
+
+
+def test_user_keff_implicit_clerk_fixed_source(orc):
+    """InputFiles/sphere_with_DT has a keffImplicitClerk in its fixed-source tally: leakage of every secondary counts."""
+    deck = os.path.join(ROOT, "decks", "fixed", "ce_sphere")
+    ov = "pop 5000; cycles 3; seed 4; tally { k_eff { type keffImplicitClerk; } fiss { type collisionClerk; response (fiss); fiss { type macroResponse; MT -6; } } }"
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(deck.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.FixedSourcePhysicsPackage(deck, ov, device=0)
+        for _ in range(3):
+            assert orc.orc_fixed_cycle(e) == 0, ol.err(orc)
+            pp.fixed_cycle()
+        n = orc.orc_eigen_tally_size(e, 1)
+        assert n == 6
+        cs, cs2, nb = pp.tally(True)
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+        assert 0.0 < cs[4] / nb < 1.0 and cs[3] > 0          # subcritical k estimate, leakage scored
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
