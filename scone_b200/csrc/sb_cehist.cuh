@@ -24,6 +24,11 @@
 
 namespace sbc {
 using namespace sbd;
+#ifndef SB_CE_NUC_UNROLL
+#define SB_CE_NUC_UNROLL 1
+#endif
+constexpr int NUC_UNROLL = SB_CE_NUC_UNROLL;      // nuclide loops: rolled keeps the code small, unrolled overlaps the gathers of consecutive nuclides
+
 using sbh::rngGet;
 using sbk::CeMtRec; using sbk::CeNucRec; using sbk::Tape;
 
@@ -144,7 +149,7 @@ __device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, con
     for (int i = 0; i < k.nResp; ++i) {
       double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : ceResponse(x, k.respMT[i]));
       double s = resp * f;
-      if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
+      if (s != 0.0) { binAdd(a.bins + addr + i, s); ++nScore; }
     }
   }
   if (a.impScores && !isVoid) {                                                                        // keffImplicitClerk%reportInColl
@@ -159,7 +164,7 @@ __device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e,
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
   const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
   double tot = 0.0;
-#pragma unroll 1
+#pragma unroll NUC_UNROLL
   for (int k = k0; k < k1; ++k) {
     const int nuc = __ldg(c.matNuc + k) - 1;
     const int idx = __ldg(row + nuc);
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
       double rem = (sigTot * 1.0) * rngGet(rng);
       const int k0 = __ldg(X.matOff + mat - 1), k1 = __ldg(X.matOff + mat);
       nuc0 = -1;
-#pragma unroll 1
+#pragma unroll NUC_UNROLL
       for (int k = k0; k < k1; ++k) {
         const int nn = __ldg(X.matNuc + k) - 1;
         const int idx = __ldg(X.idxTab + (size_t)(u - 1) * X.nNuc + nn);

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
           for (int i = 0; i < k.nResp; ++i) {
             double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : mgResponse(x, fissile, k.respMT[i]));
             double s = resp * f;
-            if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
+            if (s != 0.0) { binAdd(a.bins + addr + i, s); ++nScore; }
           }
         }
         if (active && !isVoid) {

@@ -255,7 +255,7 @@ __device__ inline void scoreInColl(const TrackArgs& a, const Tables& T, const ch
     for (int i = 0; i < k.nResp; ++i) {
       double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : mgResponse(x, fissile, k.respMT[i]));
       double s = resp * f;
-      if (s != 0.0) { atomicAdd(a.bins + addr + i, s); ++nScore; }
+      if (s != 0.0) { binAdd(a.bins + addr + i, s); ++nScore; }
     }
   }
   if (a.impScores && !isVoid) {
