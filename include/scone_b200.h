@@ -135,7 +135,8 @@ typedef struct sb_map1d {
  * the attachment clerks of eigenPhysicsPackage itself): keffAnalogClerk = 3 bins { start weight, end weight, k }
  * (keffAnalogClerk_class.f90:40-60,132-176), keffImplicitClerk = 5 bins { IMP_PROD, IMP_ABS, SCATTER_PROD, ANA_LEAK, K_EFF }
  * (keffImplicitClerk_class.f90:60-75,292-312): the first bins pass through closeCycle (normalised), the k bin is accumulated as is */
-enum { SB_CLERK_COLLISION = 0, SB_CLERK_KEFF_ANALOG = 1, SB_CLERK_KEFF_IMPLICIT = 2 };
+enum { SB_CLERK_COLLISION = 0, SB_CLERK_KEFF_ANALOG = 1, SB_CLERK_KEFF_IMPLICIT = 2,
+       SB_CLERK_TRACK = 3 /* trackClerk (trackClerk_class.f90:185-232): maps on the pre-path state, score = response * w * path length; surface tracking only */ };
 typedef struct sb_clerk {
   int32_t n_maps; sb_map1d maps[SB_MAX_MAPS];   /* multiMap order; 0 maps = single bin        */
   int32_t n_resp; int32_t resp_mt[SB_MAX_RESP]; /* 0 = fluxResponse, else SCONE macro MT (-1..) */

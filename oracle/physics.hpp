@@ -447,9 +447,9 @@ struct Response {
       }
     } else MT = mt;
   }
-  double get(const XsView& db, const Particle& p) const {
+  double get(const XsView& db, const Particle& p, int matOverride = -1) const {      // matOverride: trackClerk scores in the pre-path material
     if (isFlux) return 1.0;
-    int matIdx = p.matIdx();
+    int matIdx = matOverride >= 0 ? matOverride : p.matIdx();
     if (matIdx == VOID_MAT) return 0.0;
     if (matIdx < 1 || matIdx > db.nMat()) return 0.0;
     MacroXSs x; db.macroXSs(x, p, matIdx);
@@ -458,7 +458,7 @@ struct Response {
 };
 
 struct Clerk {
-  enum Kind { COLLISION, KEFF_ANALOG, KEFF_IMPLICIT } kind = COLLISION;
+  enum Kind { COLLISION, KEFF_ANALOG, KEFF_IMPLICIT, TRACK } kind = COLLISION;
   std::string name;
   long addr = 1;
   // collisionClerk
@@ -490,6 +490,11 @@ struct TallyAdmin {
         if (cd.isPresent("map")) c.map = newTallyMap(cd.getDict("map"), mats);
         for (auto& rn : cd.getWordArray("response")) { Response r; r.init(cd.getDict(rn)); c.response.push_back(r); }
         c.handleVirtual = cd.getBool("handleVirtual", true);
+      } else if (t == "trackClerk") {                                 // trackClerk_class.f90:100-150 (same dictionary as collisionClerk, no handleVirtual)
+        c.kind = Clerk::TRACK;
+        if (cd.isPresent("filter")) throw FatalError("trackClerk init", "filters are not supported in oracle");
+        if (cd.isPresent("map")) c.map = newTallyMap(cd.getDict("map"), mats);
+        for (auto& rn : cd.getWordArray("response")) { Response r; r.init(cd.getDict(rn)); c.response.push_back(r); }
       } else if (t == "keffAnalogClerk") c.kind = Clerk::KEFF_ANALOG;
       else if (t == "keffImplicitClerk") { c.kind = Clerk::KEFF_IMPLICIT; c.handleVirtual = cd.getBool("handleVirtual", true); }
       else throw FatalError("new_tallyClerk", "Unsupported clerk in oracle: " + t);
@@ -532,6 +537,16 @@ struct TallyAdmin {
         mem.score(s1, c.addr + 0);   // IMP_PROD
         mem.score(s2, c.addr + 1);   // IMP_ABS
       }
+    }
+  }
+  void reportPath(const Particle& p, const XsView& db, double L) {   // tallyAdmin_class.f90:545-568 ; trackClerk_class.f90:185-232
+    if (atch) atch->reportPath(p, db, L);
+    for (auto& c : clerks) if (c.kind == Clerk::TRACK) {
+      const ParticleState& s = p.prePath;
+      int binIdx = c.map ? c.map->map(s) : 1;
+      if (binIdx == 0) continue;
+      long a = c.addr + (long)c.response.size() * (binIdx - 1) - 1;
+      for (size_t i = 1; i <= c.response.size(); ++i) mem.score(c.response[i - 1].get(db, p, s.matIdx) * p.w * L, a + (long)i);
     }
   }
   void reportOutColl(const Particle& p, int MT) {                   // keffImplicitClerk_class.f90:238-270
@@ -851,6 +866,7 @@ struct EigenPP {
       p.time = p.time + dist / 1.0;
       ++seg;
       if (event == COLL_EV) p.fate = NO_FATE;
+      tally.reportPath(p, *xs, dist);                                // transportOperatorST_class.f90:125
       m = p.matIdx();
       if (m == OUTSIDE_MAT) { p.isDead = true; p.fate = LEAK_FATE; }
       else if (m == UNDEF_MAT) throw FatalError("surfaceTracking", "Particle is in undefined material");

@@ -922,10 +922,10 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
       h->clerks[phase].push_back(d);
       continue;
     }
-    if (s.kind != SB_CLERK_COLLISION) { h->err = "sb_define_tallies: unknown clerk kind"; return -1; }
+    if (s.kind != SB_CLERK_COLLISION && s.kind != SB_CLERK_TRACK) { h->err = "sb_define_tallies: unknown clerk kind"; return -1; }
     if (s.n_maps < 0 || s.n_maps > SB_MAX_MAPS || s.n_resp < 1 || s.n_resp > SB_MAX_RESP) { h->err = "sb_define_tallies: invalid clerk"; return -1; }
     DClerk d; memset(&d, 0, sizeof(d));
-    d.addr = memLoc; d.nMaps = s.n_maps; d.nResp = s.n_resp; d.handleVirtual = s.handle_virtual;
+    d.addr = memLoc; d.nMaps = s.n_maps; d.nResp = s.n_resp; d.handleVirtual = s.handle_virtual; d.kind = s.kind;
     int mul = 1;
     for (int m = 0; m < s.n_maps; ++m) {
       const sb_map1d& mp = s.maps[m];
@@ -1113,6 +1113,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   if (needBlocks < blocks) blocks = needBlocks;
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
   bool useTrack = h->opt.tracking != SB_TRACK_DT || h->fixedSource;      // the DT-only kernel has no secondary buffer
+  // (trackClerks score along surface-tracking segments only: under delta tracking the reference makes no path reports either)
   if (!h->ceMode && !h->fixedSource && h->opt.tracking == SB_TRACK_HT && !getenv("SB_FORCE_TRACK_KERNEL")) {
     // transportOperatorHT picks delta tracking when Sigma_t / Sigma_maj > 1 - cutoff (transportOperatorHT_class.f90:63-78). If that
     // holds for every (material, group) of the model -- and nothing is void -- the selector is a constant and the flights
@@ -1135,13 +1136,14 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
     t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache; t.impScores = impScores;
     t.needMacro = 0;
-    for (const DClerk& k : h->clerks[phase]) for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1;
+    for (const DClerk& k : h->clerks[phase]) { for (int i = 0; i < k.nResp; ++i) if (k.respMT[i] != 0) t.needMacro = 1; if (k.kind == SB_CLERK_TRACK) t.nTrackClerks++; }
     const char* cfg = getenv("SB_CE_KERNEL");                  // experiment switch: "async" = 128-thread CTAs without phase barriers
     if (h->fixedSource) {                                      // fixed source: private secondary buffers, lockstep kernel
       cfg = nullptr;
       const int threadsF = n < 400000 ? 512 : 1024;
       if (ensureSecStack(h, (size_t)std::min(h->numSM, (n + threadsF - 1) / threadsF) * threadsF, t.stk)) return -1;
     }
+    if (t.nTrackClerks) cfg = nullptr;                             // path-length scores are made by the lane-resident kernel
     if (cfg && (!strcmp(cfg, "events") || !strcmp(cfg, "events1024"))) {   // event queues over slots in global memory (sb_ceevent.cuh)
       const int slotsPerCta = !strcmp(cfg, "events") ? 512 : 1024;
       const size_t need = (size_t)h->numSM * slotsPerCta;
@@ -1167,6 +1169,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     t.nsites = h->dNsites; t.hProd = h->dHProd; t.hAbs = h->dHAbs; t.hLeak = h->dHLeak; t.hScat = h->dHScat;
     t.bins = h->dBins[phase]; t.phase = phase; t.rng0 = rng_state; t.histOffset = history_offset; t.k_eff = k_eff; t.cd = h->dCd;
     t.tracking = h->opt.tracking; t.htCutoff = h->opt.ht_cutoff; t.stCache = h->opt.st_cache; t.impScores = impScores;
+    for (const DClerk& k : h->clerks[phase]) if (k.kind == SB_CLERK_TRACK) t.nTrackClerks++;
     const char* cfg = getenv("SB_TRACK_KERNEL");               // experiment switch: "async" = 128-thread CTAs without phase barriers
     if (h->fixedSource) { cfg = nullptr; if (ensureSecStack(h, (size_t)std::min(h->numSM, (n + 511) / 512) * 512, t.stk)) return -1; }
     if (cfg && !strcmp(cfg, "async")) sbt::k_histories_track<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);

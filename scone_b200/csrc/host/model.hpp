@@ -511,9 +511,10 @@ inline TallyDefs buildTallies(const Dict& d, const MatMap& mats, int nMat) {
       T.clerks.push_back(c); T.names.push_back(n);
       continue;
     }
-    if (t != "collisionClerk") throw FatalError("new_tallyClerk", "tallyClerk type not supported by the device tallies: " + t);
-    if (cd.isPresent("filter")) throw FatalError("init (collisionClerk)", "tally filters are not supported by the device tallies");
+    if (t != "collisionClerk" && t != "trackClerk") throw FatalError("new_tallyClerk", "tallyClerk type not supported by the device tallies: " + t);
+    if (cd.isPresent("filter")) throw FatalError("init (" + t + ")", "tally filters are not supported by the device tallies");
     sb_clerk c{};
+    c.kind = (t == "trackClerk") ? SB_CLERK_TRACK : SB_CLERK_COLLISION;
     if (cd.isPresent("map")) {
       const Dict& md = cd.getDict("map");
       if (md.getWord("type") == "multiMap") for (auto& mn : md.getWordArray("maps")) detail::addMap1D(T, c, md.getDict(mn), mats, nMat);

@@ -48,6 +48,7 @@ struct CeArgs {
   sbh::CycleDev* cd;
   int tracking; double htCutoff; int stCache;
   sbt::SecStack stk;
+  int nTrackClerks;
 };
 
 // what the out-of-line device functions need, kept once per CTA in shared memory: a reference to kernel parameters would make
@@ -141,6 +142,7 @@ __device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, con
   const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
   for (int c = 0; c < nC; ++c) {
     const DClerk& k = cl[c];
+    if (k.kind != SB_CLERK_COLLISION) continue;
     if (!k.handleVirtual && (virt || isVoid)) continue;
     int bin = clerkBinCE(k, base, r, mat, E);
     if (bin == 0) continue;
@@ -176,6 +178,27 @@ __device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e,
   return tot * 1.0;
 }
 __device__ __noinline__ void ceRotate(double d[3], double mu, double phi) { rotateVector(d, mu, phi); }
+
+// tallyAdmin%reportPath -> trackClerk%reportPath for a CE particle (pre-path position and material, current energy)
+__device__ __noinline__ void scorePathCE(const CeCtx& a, const char* base, const double rPre[3], int matPre, double E, int u, double w, double L, unsigned& nScore) {
+  const bool isVoid = (matPre == SB_VOID_MAT);
+  double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (!isVoid && a.needMacro) matMacro(a.ce.xs, u, E, matPre, x);
+  const int nC = a.M.nClerk[a.phase];
+  const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
+  for (int c = 0; c < nC; ++c) {
+    const DClerk& k = cl[c];
+    if (k.kind != SB_CLERK_TRACK) continue;
+    int bin = clerkBinCE(k, base, rPre, matPre, E);
+    if (bin == 0) continue;
+    int addr = k.addr + k.nResp * (bin - 1) - 1;
+    for (int i = 0; i < k.nResp; ++i) {
+      double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : ceResponse(x, k.respMT[i]));
+      double s = resp * w * L;
+      if (s != 0.0) { binAdd(a.bins + addr + i, s); ++nScore; }
+    }
+  }
+}
 
 // ---- scattering kernels (scatteringKernels_func.f90) ---------------------------------------------------------------------
 __device__ __forceinline__ void asymptoticScatter(double& E, double& mu, double A) {
@@ -371,8 +394,10 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
           sigmaT = sigTot + 0.0;
         }
         int event;
+        const double rPre[3] = {c.r[0][0], c.r[0][1], c.r[0][2]};      // p%savePrePath
         sbt::geomMove(M, T, c, dist, event, a.stCache ? &cache : nullptr);
         ++nSeg; ++hSeg;
+        if (a.nTrackClerks) scorePathCE(ctx, base, rPre, m, E, u, w, dist, nScore);      // tally%reportPath(p, dist)
         m = c.mat;
         if (m == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
         else if (m >= SB_OVERLAP_MAT && m != SB_VOID_MAT) { atomicMax(&a.cd->error, m == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }

@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
 #pragma unroll 1
         for (int c = 0; c < nC; ++c) {
           const DClerk& k = clerks[c];
+          if (k.kind != SB_CLERK_COLLISION) continue;
           if (!k.handleVirtual && (virt || isVoid)) continue;
           const double f = k.handleVirtual ? flux : w / (x[XS_TOTAL] + 0.0);
           bool any = false;

@@ -234,6 +234,7 @@ struct TrackArgs {
   sbh::CycleDev* cd;
   int tracking; double htCutoff; int stCache;
   SecStack stk;
+  int nTrackClerks;                       // trackClerks of this phase (path-length scores along surface-tracking segments)
 };
 
 // collisionClerk / keffImplicitClerk scoring of one collision (virtual or real), generic tables
@@ -247,6 +248,7 @@ __device__ inline void scoreInColl(const TrackArgs& a, const Tables& T, const ch
   const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
   for (int c = 0; c < nC; ++c) {
     const DClerk& k = cl[c];
+    if (k.kind != SB_CLERK_COLLISION) continue;
     if (!k.handleVirtual && (virt || isVoid)) continue;
     int bin = clerkBin(k, base, r, mat);
     if (bin == 0) continue;
@@ -263,6 +265,27 @@ __device__ inline void scoreInColl(const TrackArgs& a, const Tables& T, const ch
     sProd += nuf * flux;
     sAbs += (x[XS_CAPTURE] + fis) * flux;
     nScore += 2;
+  }
+}
+
+// tallyAdmin%reportPath -> trackClerk%reportPath (trackClerk_class.f90:185-232): bin from the pre-path state, response in the pre-path material
+__device__ __noinline__ void scorePath(const TrackArgs& a, const Tables& T, const char* base, const double rPre[3], int matPre, int G, double w, double L, unsigned& nScore) {
+  const bool isVoid = (matPre == SB_VOID_MAT);
+  const double* x = isVoid ? T.xs : mgRow(a.M, T, matPre, G);
+  const bool fissile = isVoid ? false : (T.fissile[matPre - 1] != 0);
+  const int nC = a.M.nClerk[a.phase];
+  const DClerk* cl = (const DClerk*)(base + a.M.oClerk[a.phase]);
+  for (int c = 0; c < nC; ++c) {
+    const DClerk& k = cl[c];
+    if (k.kind != SB_CLERK_TRACK) continue;
+    int bin = clerkBin(k, base, rPre, matPre);
+    if (bin == 0) continue;
+    int addr = k.addr + k.nResp * (bin - 1) - 1;
+    for (int i = 0; i < k.nResp; ++i) {
+      double resp = (k.respMT[i] == 0) ? 1.0 : (isVoid ? 0.0 : mgResponse(x, fissile, k.respMT[i]));
+      double s = resp * w * L;
+      if (s != 0.0) { binAdd(a.bins + addr + i, s); ++nScore; }
+    }
   }
 }
 
@@ -368,8 +391,10 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
           sigmaT = mgRow(M, T, m, G)[XS_TOTAL] + 0.0;
         }
         int event;
+        const double rPre[3] = {c.r[0][0], c.r[0][1], c.r[0][2]};      // p%savePrePath (transportOperatorST_class.f90:107)
         geomMove(M, T, c, dist, event, a.stCache ? &cache : nullptr);
         ++nSeg; ++hSeg;
+        if (a.nTrackClerks) scorePath(a, T, base, rPre, m, G, w, dist, nScore);      // tally%reportPath(p, dist), :125
         m = c.mat;
         if (m == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
         else if (m >= SB_OVERLAP_MAT && m != SB_VOID_MAT) { atomicMax(&a.cd->error, m == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true; }

@@ -70,3 +70,43 @@ def test_user_keff_implicit_clerk_fixed_source(orc):
         pp.close(); orc.orc_eigen_free(e)
     finally:
         orc.orc_set_math_mode(0)
+
+
+TRACK = ("activeTally { flxT { type trackClerk; map { type spaceMap; axis x; grid lin; min %g; max %g; N 12; } response (flux fis); flux { type fluxResponse; } fis { type macroResponse; MT -6; } } "
+         "flxC { type collisionClerk; map { type spaceMap; axis x; grid lin; min %g; max %g; N 12; } response (flux); flux { type fluxResponse; } } }")
+
+
+@pytest.mark.parametrize("deck,pop,lo,hi,tracking", [
+    (DECK["c5g7"], 5000, -32.13, 32.13, "transportOperator { type transportOperatorST; }"),
+    (DECK["c5g7"], 5000, -32.13, 32.13, "transportOperator { type transportOperatorHT; cutoff 0.6; }"),
+    (DECK["ce_pin"], 2500, -0.63, 0.63, "transportOperator { type transportOperatorST; cache 0; }"),
+    (DECK["slab"], 4000, -9.4959, 9.4959, "transportOperator { type transportOperatorDT; }")])
+def test_track_clerk_path_length_estimator(orc, deck, pop, lo, hi, tracking):
+    """trackClerk (path-length flux) next to a collisionClerk on the same mesh: every bin against the oracle; the two flux estimators
+    agree statistically; under delta tracking the track clerk stays empty, as in the reference (no path reports)."""
+    ov = "pop %d; inactive 1; active 3; seed 8; %s %s" % (pop, TRACK % (lo, hi, lo, hi), tracking)
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(deck.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(deck, ov, device=0)
+        orc.orc_eigen_init_source(e); pp.generateInitialState()
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(4):
+            pp.cycle(cyc >= 1)
+            k_o = orc.orc_eigen_cycle(e, 1 if cyc >= 1 else 0, k_o)
+        n = orc.orc_eigen_tally_size(e, 1)
+        assert n == 24 + 12
+        cs, cs2, nb = pp.tally(True)
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+        fluxT, fluxC = cs[0:24:2].sum(), cs[24:].sum()
+        if "DT" in tracking:
+            assert fluxT == 0.0 and fluxC > 0.0
+        else:
+            assert fluxT > 0.0 and (abs(fluxT / fluxC - 1.0) < 0.1 or "HT" in tracking)
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
