@@ -367,6 +367,17 @@ int orc_eigen_init_source(void* ev) { ORC_TRY ((EigenPP*)ev)->generateInitialSta
 double orc_eigen_cycle(void* ev, int active, double k_in) {
   ORC_TRY return ((EigenPP*)ev)->cycle(active != 0, k_in); ORC_CATCH(std::nan(""))
 }
+// ---- scoreMemory on its own (pins of Tallies/Tests/scoreMemory_test.f90) ----
+void* orc_mem_new(long n, int batch) { auto* m = new ScoreMemory(); m->init(n, batch); return m; }
+void orc_mem_free(void* m) { delete (ScoreMemory*)m; }
+int orc_mem_score(void* m, double v, long idx) { ORC_TRY ((ScoreMemory*)m)->score(v, idx); return 0; ORC_CATCH(-1) }
+int orc_mem_accumulate(void* m, double v, long idx) { ORC_TRY ((ScoreMemory*)m)->accumulate(v, idx); return 0; ORC_CATCH(-1) }
+int orc_mem_reduce(void* m) { ((ScoreMemory*)m)->reduceBins(); return 0; }
+int orc_mem_close_bin(void* m, double norm, long idx) { ORC_TRY ((ScoreMemory*)m)->closeBin(norm, idx); return 0; ORC_CATCH(-1) }
+int orc_mem_close_cycle(void* m, double norm) { ((ScoreMemory*)m)->closeCycle(norm); return 0; }
+int orc_mem_last_cycle(void* m) { return ((ScoreMemory*)m)->lastCycle() ? 1 : 0; }
+double orc_mem_get_score(void* m, long idx) { return ((ScoreMemory*)m)->getScore(idx); }
+int orc_mem_result(void* m, long idx, int samples, double* mean, double* std_) { ((ScoreMemory*)m)->getResult(*mean, *std_, idx, samples); return 0; }
 // fixedSourcePhysicsPackage: one source batch (returns 0 / -1); pop, cycles via orc_eigen_info
 int orc_fixed_cycle(void* ev) { ORC_TRY ((EigenPP*)ev)->fixedCycle(); return 0; ORC_CATCH(-1) }
 int orc_eigen_is_fixed(void* ev) { return ((EigenPP*)ev)->fixedSource ? 1 : 0; }

@@ -262,9 +262,16 @@ struct ScoreMemory {
       batchN += 1;
     }
   }
-  void getResult(double& mean, double& STD, long idx) const {       // :537-573
+  void closeBin(double normFactor, long idx) {                      // :344-362
+    if (idx < 0 || idx > N) throw FatalError("closeBin (scoreMemory)", "Index is outside bounds of memory");
+    double res = bin[idx - 1] * normFactor;
+    csum[idx - 1] = csum[idx - 1] + res;
+    csum2[idx - 1] = csum2[idx - 1] + res * res;
+    bin[idx - 1] = 0.0;
+  }
+  void getResult(double& mean, double& STD, long idx, int samples = -1) const {       // :537-573
     if (idx < 0 || idx > N) { mean = 0.0; STD = 0.0; return; }
-    int n = batchN;
+    int n = samples > 0 ? samples : batchN;
     mean = csum[idx - 1] / n;
     double inv_N = 1.0 / n, inv_Nm1 = (n != 1) ? 1.0 / (n - 1) : 1.0;
     STD = csum2[idx - 1] * inv_N * inv_Nm1 - mean * mean * inv_Nm1;

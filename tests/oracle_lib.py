@@ -125,6 +125,10 @@ def load():
         "orc_ce_db_union": (i32, [vp, c_dp, c_dp]), "orc_ce_db_total_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]),
         "orc_ce_db_macro_n": (i32, [vp, C.c_long, c_dp, c_ip, c_dp]), "orc_ce_db_majorant_n": (i32, [vp, C.c_long, c_dp, c_dp]),
         "orc_ce_db_index_n": (i32, [vp, i32, C.c_long, c_dp, c_ip]),
+        "orc_mem_new": (vp, [C.c_long, i32]), "orc_mem_free": (None, [vp]), "orc_mem_score": (i32, [vp, dbl, C.c_long]),
+        "orc_mem_accumulate": (i32, [vp, dbl, C.c_long]), "orc_mem_reduce": (i32, [vp]), "orc_mem_close_bin": (i32, [vp, dbl, C.c_long]),
+        "orc_mem_close_cycle": (i32, [vp, dbl]), "orc_mem_last_cycle": (i32, [vp]), "orc_mem_get_score": (dbl, [vp, C.c_long]),
+        "orc_mem_result": (i32, [vp, C.c_long, i32, c_dp, c_dp]),
         "orc_eigen_bank_E": (i32, [vp, c_dp]), "orc_fixed_cycle": (i32, [vp]), "orc_eigen_is_fixed": (i32, [vp]),
         "orc_tabpdf_sample": (dbl, [i32, c_dp, c_dp, c_dp, i32, dbl]),
         "orc_endftable_at": (dbl, [i32, c_dp, c_dp, i32, c_ip, c_ip, dbl]),
