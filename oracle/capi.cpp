@@ -378,6 +378,55 @@ int orc_mem_close_cycle(void* m, double norm) { ((ScoreMemory*)m)->closeCycle(no
 int orc_mem_last_cycle(void* m) { return ((ScoreMemory*)m)->lastCycle() ? 1 : 0; }
 double orc_mem_get_score(void* m, long idx) { return ((ScoreMemory*)m)->getScore(idx); }
 int orc_mem_result(void* m, long idx, int samples, double* mean, double* std_) { ((ScoreMemory*)m)->getResult(*mean, *std_, idx, samples); return 0; }
+// ---- k-eff clerks on their own (pins of Tallies/TallyClerks/Tests/keff{Implicit,Analog}Clerk_test.f90) ----
+// testNeutronDatabase (NuclearData/testNeutronData/testNeutronDatabase_class.f90): the same cross sections everywhere
+struct ConstXsView : XsView {
+  MacroXSs x;
+  int nMat() const override { return 1 << 30; }
+  double totalMatXS(const Particle&, int) const override { return x.total; }
+  void macroXSs(MacroXSs& o, const Particle&, int) const override { o = x; }
+  double trackMatXS(const Particle&, int) const override { return x.total; }
+  double majorantXS(const Particle&) const override { return x.total; }
+  double collisionXS() const override { return 0.0; }
+  bool isFissileMat(int) const override { return x.fission > 0.0; }
+};
+// keffImplicitClerk_test.f90 test1CycleBatch: two cycles of { collision at weight w_coll, (n,2n) with pre-collision weight w_pre, leak at w_leak }
+int orc_keff_implicit_sequence(double total, double capture, double fission, double nuFission, int n, const double* w_coll, const double* w_pre,
+                               const double* w_leak, double* k, double* std_) {
+  ORC_TRY
+  ConstXsView xs; xs.x.total = total; xs.x.capture = capture; xs.x.fission = fission; xs.x.nuFission = nuFission;
+  TallyAdmin t; std::map<std::string, int> mats;
+  t.init(Dict::fromString("k { type keffImplicitClerk; }"), mats);
+  Dungeon pit; pit.init(4);
+  for (int c = 0; c < n; ++c) {
+    Particle p; p.coords.matIdx = 1;
+    p.w = w_coll[c];
+    t.reportInColl(p, xs, total, false);
+    p.preCollision.wgt = w_pre[c];
+    t.reportOutColl(p, 16);                                           // N_2N
+    p.w = w_leak[c]; p.fate = LEAK_FATE;
+    t.reportHist(p);
+    t.reportCycleEnd(pit);
+  }
+  return t.getKeff(*k, *std_) ? 0 : -1;
+  ORC_CATCH(-1)
+}
+// keffAnalogClerk_test.f90 test1CycleBatch: cycles of { start population weight, end population weight, k_eff of the end dungeon }; closeCycle norm 0.8
+int orc_keff_analog_sequence(int n, const double* w_start, const double* w_end, const double* k_norm, double norm, double* k, double* std_) {
+  ORC_TRY
+  TallyAdmin t; std::map<std::string, int> mats;
+  t.init(Dict::fromString("k { type keffAnalogClerk; }"), mats);
+  (void)norm;
+  for (int c = 0; c < n; ++c) {
+    Dungeon a, b; a.init(1); b.init(1);
+    ParticleState s; s.wgt = w_start[c]; a.detain(s);
+    t.reportCycleStart(a);
+    s.wgt = w_end[c]; b.detain(s); b.k_eff = k_norm[c];
+    t.reportCycleEnd(b);
+  }
+  return t.getKeff(*k, *std_) ? 0 : -1;
+  ORC_CATCH(-1)
+}
 // fixedSourcePhysicsPackage: one source batch (returns 0 / -1); pop, cycles via orc_eigen_info
 int orc_fixed_cycle(void* ev) { ORC_TRY ((EigenPP*)ev)->fixedCycle(); return 0; ORC_CATCH(-1) }
 int orc_eigen_is_fixed(void* ev) { return ((EigenPP*)ev)->fixedSource ? 1 : 0; }

@@ -129,6 +129,8 @@ def load():
         "orc_mem_accumulate": (i32, [vp, dbl, C.c_long]), "orc_mem_reduce": (i32, [vp]), "orc_mem_close_bin": (i32, [vp, dbl, C.c_long]),
         "orc_mem_close_cycle": (i32, [vp, dbl]), "orc_mem_last_cycle": (i32, [vp]), "orc_mem_get_score": (dbl, [vp, C.c_long]),
         "orc_mem_result": (i32, [vp, C.c_long, i32, c_dp, c_dp]),
+        "orc_keff_implicit_sequence": (i32, [dbl, dbl, dbl, dbl, i32, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "orc_keff_analog_sequence": (i32, [i32, c_dp, c_dp, c_dp, dbl, c_dp, c_dp]),
         "orc_eigen_bank_E": (i32, [vp, c_dp]), "orc_fixed_cycle": (i32, [vp]), "orc_eigen_is_fixed": (i32, [vp]),
         "orc_tabpdf_sample": (dbl, [i32, c_dp, c_dp, c_dp, i32, dbl]),
         "orc_endftable_at": (dbl, [i32, c_dp, c_dp, i32, c_ip, c_ip, dbl]),

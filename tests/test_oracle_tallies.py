@@ -1,4 +1,5 @@
-"""CPU: the oracle's scoreMemory against the known answers of the reference's own test (Tallies/Tests/scoreMemory_test.f90)."""
+"""CPU: the oracle's scoreMemory and k-eff clerks against the known answers of the reference's own tests
+(Tallies/Tests/scoreMemory_test.f90, Tallies/TallyClerks/Tests/keffImplicitClerk_test.f90, keffAnalogClerk_test.f90)."""
 import ctypes as C
 
 import numpy as np
@@ -55,3 +56,21 @@ def test_score_memory_batches_and_get_score(orc):
     orc.orc_mem_reduce(m)
     assert orc.orc_mem_get_score(m, 1) == 3.0 and orc.orc_mem_get_score(m, 0) == 0.0 and orc.orc_mem_get_score(m, 2) == 0.0
     orc.orc_mem_free(m)
+
+
+def test_keff_implicit_clerk_known_answer(orc):
+    # keffImplicitClerk_test.f90:33-34 (total 1, capture 2, fission 1, nuFission 3), test1CycleBatch :45-88
+    a = lambda v: np.ascontiguousarray(v, np.float64)
+    wc, wp, wl = a([0.7, 0.6]), a([0.1, 0.1]), a([0.3, 0.3])
+    k, s = C.c_double(), C.c_double()
+    assert orc.orc_keff_implicit_sequence(1.0, 2.0, 1.0, 3.0, 2, ol.dp(wc), ol.dp(wp), ol.dp(wl), C.byref(k), C.byref(s)) == 0, ol.err(orc)
+    assert k.value == pytest.approx(0.906521739130435, abs=1e-9) and s.value == pytest.approx(0.006521739130435, abs=1e-9)
+
+
+def test_keff_analog_clerk_known_answer(orc):
+    # keffAnalogClerk_test.f90 test1CycleBatch: (1000 -> 1200, k 1.0), (1000 -> 900, k 1.2): k = 1.14 +- 0.06
+    a = lambda v: np.ascontiguousarray(v, np.float64)
+    ws, we, kn = a([1000.0, 1000.0]), a([1200.0, 900.0]), a([1.0, 1.2])
+    k, s = C.c_double(), C.c_double()
+    assert orc.orc_keff_analog_sequence(2, ol.dp(ws), ol.dp(we), ol.dp(kn), 0.8, C.byref(k), C.byref(s)) == 0, ol.err(orc)
+    assert k.value == pytest.approx(1.14, abs=1e-9) and s.value == pytest.approx(0.06, abs=1e-9)
