@@ -164,7 +164,7 @@ typedef struct sb_cycle_result {
   int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
-       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7,
+       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10,
        SB_ERR_CE_ENERGY = 8 /* energy outside the bounds of the CE data */, SB_ERR_CE_DATA = 9 /* failed search / rejection loop in the reaction data */ };
 
 /* ---- life cycle -------------------------------------------------------------------------- */
@@ -191,6 +191,9 @@ int sb_set_options(sb_engine* h, const sb_options* o);
 int sb_bank_upload(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G);
 int sb_bank_download(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, int32_t* G);
 int sb_bank_size(sb_engine* h);
+/* broodID of every site of the current bank (1-based index of the parent history in the cycle that made it; 0 for source and uploaded banks):
+ * the ninth column of particleDungeon%printToFile (particleDungeon_class.f90:1077-1112)                                        */
+int sb_bank_brood(sb_engine* h, int cap, int32_t* brood);
 /* continuous-energy banks carry E [MeV] instead of G */
 int sb_bank_upload_ce(sb_engine* h, int n, const double* r, const double* dir, const double* w, const double* E);
 int sb_bank_download_ce(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, double* E);
@@ -212,6 +215,12 @@ typedef struct sb_point_source {
 } sb_point_source;
 int sb_set_fixed_source(sb_engine* h, int on, int buffer_size);
 int sb_source_point(sb_engine* h, int n, uint64_t rng_state, int history_offset, const sb_point_source* s);
+/* fileSource (ParticleObjects/Source/fileSource_class.f90): rows[n_rows][10] are the records of a printToFile dump
+ * (r, dir, E, G, broodID, wgt; particleDungeon_class.f90:1077-1112), kept on the device by sb_set_file_source.
+ * sb_source_file = fileSource%sampleParticle for n particles (:151-196): row int(rand * n_rows) + 1, position checked
+ * against OUTSIDE / undefined regions, weight and E (or G) from the row.                                                      */
+int sb_set_file_source(sb_engine* h, int64_t n_rows, const double* rows, int is_mg);
+int sb_source_file(sb_engine* h, int n, uint64_t rng_state, int history_offset);
 
 /* ---- the cycle ------------------------------------------------------------------------------
  * Transports every history of the current bank to its death (transport + collide + tallies +

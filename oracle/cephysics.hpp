@@ -256,7 +256,7 @@ struct CeEigenPP : EigenPP {
     if (fixedSource) {
       activeTally.init(dict.getDict("tally"), mats);
       inactiveTally.init(Dict::fromString(""), mats);
-      initPointSource(dict.getDict("source"), 0);
+      initSource(dict.getDict("source"), 0);
       return;
     }
     inactiveTally.init(dict.getDict("inactiveTally"), mats);

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -140,6 +141,19 @@ struct Dungeon {
     for (auto& p : prisoners) p = ParticleState();
   }
   double popWeight() const { double s = 0.0; for (int i = 0; i < pop; ++i) s += prisoners[i].wgt; return s; }
+  // printToFile (particleDungeon_class.f90:1077-1112): r, dir, E, real(G), real(broodID), wgt per prisoner; stream binary or one text row.
+  // Fortran's list-directed text is compiler-formatted; here 17 significant digits, which reads back to the same doubles.
+  void printToFile(const std::string& name, bool writeBinary) const {
+    FILE* f = fopen((name + (writeBinary ? ".bin" : ".txt")).c_str(), writeBinary ? "wb" : "w");
+    if (!f) throw FatalError("printToFile", "cannot open " + name);
+    for (int i = 0; i < pop; ++i) {
+      const ParticleState& p = prisoners[i];
+      double row[10] = {p.r[0], p.r[1], p.r[2], p.dir[0], p.dir[1], p.dir[2], p.E, (double)p.G, (double)p.broodID, p.wgt};
+      if (writeBinary) fwrite(row, sizeof(double), 10, f);
+      else { for (int k = 0; k < 10; ++k) fprintf(f, "%s%.17g", k ? " " : "  ", row[k]); fprintf(f, "\n"); }
+    }
+    fclose(f);
+  }
 
   // :923-981, transcribed literally including the in-place cycle permutation
   void sortByBroodID(int k) {
@@ -680,6 +694,10 @@ struct EigenPP {
   // fixedSourcePhysicsPackage (PhysicsPackages/fixedSourcePhysicsPackage_class.f90): cycles, private secondary buffer, pointSource
   bool fixedSource = false; int N_cycles = 0, bufferSize = 50;
   struct PointSource { Vec3 r, dir; bool isotropic = true, isMG = true; double E = 0.0; int G = 1; std::vector<double> probG; } psrc;
+  // fileSource (ParticleObjects/Source/fileSource_class.f90): rows of a printToFile dump
+  struct FileSource { bool on = false, isMG = false; long N = 0; std::vector<double> rows; } fsrc;
+  // printSource / outputFile (eigenPhysicsPackage_class.f90:278-281,463,501-504)
+  int printSource = 0; std::string outputFile = "./output"; int cycleInPhase[2] = {0, 0};
   // statistics the reference does not keep (for the segments/s metric)
   long nSegments = 0, nCollisions = 0, nHistories = 0;
   std::vector<double> cycleK;            // k_new after each cycle (both phases)
@@ -691,10 +709,54 @@ struct EigenPP {
     pop = dict.getInt("pop");
     if (fixedSource) { N_cycles = dict.getInt("cycles"); bufferSize = dict.getInt("buffer", 50); N_inactive = 0; N_active = N_cycles; }
     else { N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active"); }
+    outputFile = dict.getWord("outputFile", "./output");
+    printSource = dict.getInt("printSource", 0);
+    if (printSource < 0 || printSource > 2) throw FatalError("init (eigenPhysicsPackage)", "printSource must be 0 (No printing), 1 (ASCII) or 2 (BINARY)");
+  }
+  // fileSource%init (fileSource_class.f90:46-144): every row of the file is kept; broodID (column 9) is ignored
+  void initFileSource(const Dict& d, bool dataIsMG) {
+    std::string energy = d.getWord("data", "ce");
+    if (energy != "ce" && energy != "mg") throw FatalError("init (fileSource)", "Invalid source data type specified: must be ce or mg");
+    fsrc.isMG = (energy == "mg");
+    if (!d.isPresent("path")) throw FatalError("init (fileSource)", "path must be specified in the dictionary for fileSource");
+    std::string path = d.getWord("path");
+    bool binary = d.getBool("binary", false);
+    FILE* f = fopen(path.c_str(), binary ? "rb" : "r");
+    if (!f) throw FatalError("init (fileSource)", "cannot open " + path);
+    double row[10];
+    for (;;) {
+      bool ok = true;
+      if (binary) ok = fread(row, sizeof(double), 10, f) == 10;
+      else for (int k = 0; k < 10 && ok; ++k) ok = fscanf(f, "%lf", &row[k]) == 1;
+      if (!ok) break;
+      fsrc.rows.insert(fsrc.rows.end(), row, row + 10);
+    }
+    fclose(f);
+    fsrc.N = (long)(fsrc.rows.size() / 10);
+    fsrc.on = true;
+    if (fsrc.isMG != dataIsMG) throw FatalError("init (fileSource)", "source data type inconsistent with nuclear database");
+  }
+  // fileSource%sampleParticle (:151-196)
+  ParticleState sampleFile(RNG& rand) const {
+    long idx = (long)(rand.get() * (double)fsrc.N) + 1;
+    if (idx > fsrc.N) throw FatalError("sampleParticle (fileSource)", "Requested neutron is not in the file source file");
+    const double* row = &fsrc.rows[10 * (size_t)(idx - 1)];
+    ParticleState p;
+    for (int k = 0; k < 3; ++k) { p.r[k] = row[k]; p.dir[k] = row[3 + k]; }
+    int m, uid; geom.whatIsAt(m, uid, p.r);
+    if (m == OUTSIDE_MAT || m == UNDEF_MAT) throw FatalError("sampleParticle (fileSource)", "Neutron sampled from file source is outside of geometry or in undefined region.");
+    p.time = 0.0; p.wgt = row[9];
+    if (fsrc.isMG) { p.G = (int)row[7]; p.isMG = true; } else { p.E = row[6]; p.isMG = false; }
+    return p;
+  }
+  ParticleState sampleSource(RNG& rand) const { return fsrc.on ? sampleFile(rand) : samplePoint(rand); }
+  void initSource(const Dict& d, int nG) {
+    if (d.getWord("type") == "fileSource") initFileSource(d, nG > 0);
+    else initPointSource(d, nG);
   }
   // pointSource%init (ParticleObjects/Source/pointSource_class.f90:60-140)
   void initPointSource(const Dict& d, int nG) {
-    if (d.getWord("type") != "pointSource") throw FatalError("new_source", "oracle supports pointSource for fixed-source calculations");
+    if (d.getWord("type") != "pointSource") throw FatalError("new_source", "oracle supports pointSource and fileSource for fixed-source calculations");
     if (d.getWord("particle", "neutron") != "neutron") throw FatalError("init (pointSource)", "oracle supports neutrons only");
     auto rr = d.getRealArray("r");
     if (rr.size() != 3) throw FatalError("init (pointSource)", "Source position must have three components");
@@ -770,7 +832,7 @@ struct EigenPP {
     if (fixedSource) {
       activeTally.init(dict.getDict("tally"), mats);
       inactiveTally.init(Dict::fromString(""), mats);
-      initPointSource(dict.getDict("source"), db.nG);
+      initSource(dict.getDict("source"), db.nG);
       return;
     }
     inactiveTally.init(dict.getDict("inactiveTally"), mats);
@@ -790,8 +852,17 @@ struct EigenPP {
     if ((int)dungeonA.prisoners.size() < pop) dungeonA.init(pop);
     // source%generate (source_inter.f90:98-118)
     dungeonA.setSize(pop);
+    std::string srcErr;                                              // an exception may not leave the parallel region
 #pragma omp parallel for schedule(static)
-    for (int i = 1; i <= pop; ++i) { RNG pRand = pRNG; pRand.stride(i); dungeonA.prisoners[i - 1] = samplePoint(pRand); }
+    for (int i = 1; i <= pop; ++i) {
+      RNG pRand = pRNG; pRand.stride(i);
+      try { dungeonA.prisoners[i - 1] = sampleSource(pRand); }
+      catch (const std::exception& ex) {
+#pragma omp critical
+        srcErr = ex.what();
+      }
+    }
+    if (!srcErr.empty()) throw FatalError("generate (source)", srcErr);
     pRNG.stride(pop);
     tally.reportCycleStart(*thisCycle);
     long seg = 0, coll = 0;
@@ -1000,6 +1071,9 @@ struct EigenPP {
     tally.reportCycleEnd(*nextCycle);
     nextCycle->normSize_Repr(pop, pRNG);
     pRNG.stride(1);
+    cycleInPhase[active ? 1 : 0] += 1;                               // the `i` of the cycles loop restarts with each phase
+    if (printSource != 0)
+      nextCycle->printToFile(outputFile + "_source" + std::to_string(cycleInPhase[active ? 1 : 0]) + "_rank0", printSource == 2);
     std::swap(thisCycle, nextCycle);
     double k, s;
     atchT.getKeff(k, s);

@@ -407,14 +407,14 @@ __global__ void k_norm_rank_counts(const unsigned long long* rn, const CycleDev*
 }
 
 // loadBalancing (particleDungeon_class.f90:607-698): pack sites of the ends of the bank / rebuild the bank as
-// [received from below] + kept middle + [received from above]. Packed site layout: 7 f64 arrays of k, then k i32 (G)
+// [received from below] + kept middle + [received from above]. Packed site layout: 8 f64 arrays of k, then k i32 (G), k i32 (broodID)
 __global__ void k_bank_pack_range(Bank b, int first, int k, double* buf) {
   int* g = (int*)(buf + 8 * (size_t)k);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
     int s = first + i;
     buf[i] = b.rx[s]; buf[k + i] = b.ry[s]; buf[2 * (size_t)k + i] = b.rz[s];
     buf[3 * (size_t)k + i] = b.ux[s]; buf[4 * (size_t)k + i] = b.uy[s]; buf[5 * (size_t)k + i] = b.uz[s];
-    buf[6 * (size_t)k + i] = b.w[s]; buf[7 * (size_t)k + i] = b.E[s]; g[i] = b.G[s];
+    buf[6 * (size_t)k + i] = b.w[s]; buf[7 * (size_t)k + i] = b.E[s]; g[i] = b.G[s]; g[k + i] = b.brood[s];
   }
 }
 __global__ void k_bank_unpack_range(Bank b, int first, int k, const double* buf) {
@@ -423,7 +423,7 @@ __global__ void k_bank_unpack_range(Bank b, int first, int k, const double* buf)
     int s = first + i;
     b.rx[s] = buf[i]; b.ry[s] = buf[k + i]; b.rz[s] = buf[2 * (size_t)k + i];
     b.ux[s] = buf[3 * (size_t)k + i]; b.uy[s] = buf[4 * (size_t)k + i]; b.uz[s] = buf[5 * (size_t)k + i];
-    b.w[s] = buf[6 * (size_t)k + i]; b.E[s] = buf[7 * (size_t)k + i]; b.G[s] = g[i]; b.brood[s] = 0; b.seq[s] = 0;
+    b.w[s] = buf[6 * (size_t)k + i]; b.E[s] = buf[7 * (size_t)k + i]; b.G[s] = g[i]; b.brood[s] = g[k + i]; b.seq[s] = 0;
   }
 }
 __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfirst) {
@@ -431,7 +431,7 @@ __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfir
     int s = first + i, d = dfirst + i;
     dst.rx[d] = src.rx[s]; dst.ry[d] = src.ry[s]; dst.rz[d] = src.rz[s];
     dst.ux[d] = src.ux[s]; dst.uy[d] = src.uy[s]; dst.uz[d] = src.uz[s];
-    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.E[d] = src.E[s]; dst.brood[d] = 0; dst.seq[d] = 0;
+    dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.E[d] = src.E[s]; dst.brood[d] = src.brood[s]; dst.seq[d] = 0;
   }
 }
 
@@ -490,6 +490,25 @@ __global__ void k_source_point(Bank out, int n, uint64_t rng0, int offset, doubl
     out.rx[i] = r0; out.ry[i] = r1; out.rz[i] = r2;
     out.ux[i] = d[0]; out.uy[i] = d[1]; out.uz[i] = d[2];
     out.w[i] = 1.0; out.G[i] = isMG ? g : 0; out.E[i] = isMG ? 0.0 : E; out.brood[i] = 0; out.seq[i] = 0;
+  }
+}
+
+// fileSource%sampleParticle (ParticleObjects/Source/fileSource_class.f90:151-196)
+__global__ void k_source_file(const Model M, const char* blob, Bank out, int n, uint64_t rng0, int offset, const double* rows, long long nRows, int isMG,
+                              CycleDev* cd) {
+  const Tables T = bind(M, blob);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint64_t rng = rng_skip(rng0, RNG_STRIDE * (int64_t)(offset + i + 1));
+    long long idx = (long long)(rng_get(rng) * (double)nRows);
+    if (idx >= nRows) { atomicMax(&cd->error, SB_ERR_FILE_SOURCE); idx = nRows - 1; }
+    const double* row = rows + 10 * idx;
+    double r[3] = {row[0], row[1], row[2]}, u[3] = {row[3], row[4], row[5]};
+    int mat, uid;
+    geomPlace(M, T, r, u, mat, uid);
+    if (mat == SB_OUTSIDE_MAT || mat == SB_UNDEF_MAT) atomicMax(&cd->error, SB_ERR_FILE_SOURCE);
+    out.rx[i] = row[0]; out.ry[i] = row[1]; out.rz[i] = row[2];
+    out.ux[i] = row[3]; out.uy[i] = row[4]; out.uz[i] = row[5];
+    out.w[i] = row[9]; out.G[i] = isMG ? (int)row[7] : 0; out.E[i] = isMG ? 0.0 : row[6]; out.brood[i] = 0; out.seq[i] = 0;
   }
 }
 
@@ -593,6 +612,8 @@ struct sb_engine {
   UserKeff userKeff[2] = {};
   // fixed-source calculations: private secondary buffers of the lanes
   bool fixedSource = false; int stkCap = 50; double* dStkD = nullptr; int* dStkG = nullptr; size_t stkLanes = 0; int stkAllocCap = 0;
+  bool broodValid = false;       // the current bank came out of a cycle (its sites have parents); false for source / uploaded banks
+  double* dFileSrc = nullptr; long long nFileSrc = 0; bool fileSrcMG = false;     // fileSource rows (printToFile records)
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
   sbce::CeHost ce; int* dCeErr = nullptr; cudaEvent_t evC0 = nullptr, evC1 = nullptr; float ceLastMs = 0.f;
 };
@@ -848,7 +869,7 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
-  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG);
+  cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG); cudaFree(h->dFileSrc);
   for (void* p : h->ceAllocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -960,6 +981,16 @@ int sb_set_options(sb_engine* h, const sb_options* o) {
 }
 
 int sb_bank_size(sb_engine* h) { return h->nCur; }
+int sb_bank_brood(sb_engine* h, int cap, int32_t* brood) {
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->nCur > cap) { h->err = "sb_bank_brood: buffer too small"; return -1; }
+  if (h->nCur == 0) return 0;
+  if (!h->broodValid) { for (int i = 0; i < h->nCur; ++i) brood[i] = 0; return 0; }
+  CUDA_OK(cudaMemcpyAsync(brood, h->bank[h->cur].brood, sizeof(int) * h->nCur, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->nCur; ++i) brood[i] += 1;      // the device numbers the histories of a cycle from 0, SCONE from 1
+  return 0;
+}
 
 static int ensureStage(sb_engine* h, size_t bytes) {
   if (bytes <= h->stageBytes) return 0;
@@ -982,7 +1013,7 @@ int sb_bank_upload(sb_engine* h, int n, const double* r, const double* dir, cons
   k_bank_unpack<<<gridFor(h, n, 256), 256, 0, st>>>(h->dStage, h->dStage + 3 * (size_t)h->cap, b, n);
   h->launches++;
   CUDA_OK(cudaStreamSynchronize(st));
-  h->nCur = n;
+  h->nCur = n; h->broodValid = false;
   return 0;
 }
 
@@ -1014,6 +1045,7 @@ static int checkDeviceError(sb_engine* h, int code) {
     case SB_ERR_OVERLAP_MAT: msg = "Particle is in overlapping cells"; break;
     case SB_ERR_SAMPLING: msg = "Sampling failed (scatter XS / chi normalisation or random number above 1)"; break;
     case SB_ERR_NEST: msg = "Failed to find material cell (nesting exceeded)"; break;
+    case SB_ERR_FILE_SOURCE: msg = "fileSource: neutron sampled from file source is outside of geometry or in undefined region"; break;
     case SB_ERR_SOURCE: msg = "fissionSource: failed to find a fissile material in 10000 attempts"; break;
     case SB_ERR_NORM: msg = "Normalisation failed!"; break;
     case SB_ERR_CE_ENERGY: msg = "Failed to find energy in the nuclide energy grids (particle energy outside the bounds of the CE data)"; break;
@@ -1035,7 +1067,7 @@ int sb_source_generate(sb_engine* h, int n, uint64_t rng_state, int history_offs
   CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
-  h->nCur = n;
+  h->nCur = n; h->broodValid = false;
   return checkDeviceError(h, h->hCd->error);
 }
 
@@ -1063,8 +1095,38 @@ int sb_source_point(sb_engine* h, int n, uint64_t rng_state, int history_offset,
   h->launches++;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
-  h->nCur = n;
+  h->nCur = n; h->broodValid = false;
   return 0;
+}
+int sb_set_file_source(sb_engine* h, int64_t n_rows, const double* rows, int is_mg) {
+  if (n_rows < 1 || !rows) { h->err = "sb_set_file_source: the source file holds no particles"; return -1; }
+  if (h->ceMode == (is_mg != 0)) { h->err = "sb_set_file_source: source data type inconsistent with nuclear database"; return -1; }
+  if (is_mg) for (int64_t i = 0; i < n_rows; ++i) {
+    int g = (int)rows[10 * i + 7];
+    if (g < 1 || g > h->nG) { h->err = "sb_set_file_source: a source particle has a group outside the group structure"; return -1; }
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaFree(h->dFileSrc); h->dFileSrc = nullptr;
+  CUDA_OK(cudaMalloc(&h->dFileSrc, sizeof(double) * 10 * (size_t)n_rows));
+  CUDA_OK(cudaMemcpy(h->dFileSrc, rows, sizeof(double) * 10 * (size_t)n_rows, cudaMemcpyHostToDevice));
+  h->nFileSrc = n_rows; h->fileSrcMG = is_mg != 0;
+  return 0;
+}
+int sb_source_file(sb_engine* h, int n, uint64_t rng_state, int history_offset) {
+  if (n < 1) { h->err = "sb_source_file: invalid arguments"; return -1; }
+  if (!h->dFileSrc) { h->err = "sb_source_file: no file source has been set"; return -1; }
+  if (buildBlob(h)) return -1;
+  if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemsetAsync(h->dCd, 0, sizeof(CycleDev), h->stream));
+  k_source_file<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, h->bank[h->cur], n, rng_state, history_offset, h->dFileSrc, h->nFileSrc,
+                                                            h->fileSrcMG ? 1 : 0, h->dCd);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  h->nCur = n; h->broodValid = false;
+  return checkDeviceError(h, h->hCd->error);
 }
 // lanes x buffer_size entries of { r, dir, w, E } + G
 static int ensureSecStack(sb_engine* h, size_t lanes, sbt::SecStack& out) {
@@ -1293,7 +1355,7 @@ static int resampleFinish(sb_engine* h, int32_t* newLocal, bool readBack) {
   }
   if (checkDeviceError(h, h->hCd->error)) return -1;
   h->cur = (h->cur + 1) % 3;
-  h->nCur = h->hCd->nNew;
+  h->nCur = h->hCd->nNew; h->broodValid = true;
   if (newLocal) *newLocal = h->nCur;
   h->kNormNext = h->kCumLast;       // self%nextCycle%k_eff = k_new (eigenPhysicsPackage_class.f90:306)
   h->sortedReady = false;
@@ -1362,7 +1424,7 @@ int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_
 }
 
 // loadBalancing (particleDungeon_class.f90:607-698): sites leave from / arrive at the two ends of the bank
-size_t sb_site_buffer_bytes(int k) { return (size_t)k * (8 * sizeof(double) + sizeof(int32_t)) + 8; }
+size_t sb_site_buffer_bytes(int k) { return (size_t)k * (8 * sizeof(double) + 2 * sizeof(int32_t)) + 8; }
 int sb_bank_export(sb_engine* h, int k_front, void* dev_buf_front, int k_back, void* dev_buf_back) {
   CUDA_OK(cudaSetDevice(h->device));
   if (k_front < 0 || k_back < 0 || k_front + k_back > h->nCur) { h->err = "sb_bank_export: more sites requested than the bank holds"; return -1; }
@@ -1535,7 +1597,7 @@ int sb_bank_upload_ce(sb_engine* h, int n, const double* r, const double* dir, c
   k_bank_unpack<<<gridFor(h, n, 256), 256, 0, st>>>(h->dStage, h->dStage + 3 * (size_t)h->cap, b, n);
   h->launches++;
   CUDA_OK(cudaStreamSynchronize(st));
-  h->nCur = n;
+  h->nCur = n; h->broodValid = false;
   return 0;
 }
 int sb_bank_download_ce(sb_engine* h, int cap, int* n, double* r, double* dir, double* w, double* E) {

@@ -32,6 +32,10 @@ struct eigenPhysicsPackage {
   sb::FlatGeometry geom; sb::FlatMgData data; sb::FlatCeData ceData; bool isCE = false; sb::TallyDefs tallies[2];
   // fixedSourcePhysicsPackage (PhysicsPackages/fixedSourcePhysicsPackage_class.f90): cycles, buffer, pointSource
   bool isFixed = false; int N_cycles = 0, bufferSize = 50; sb_point_source psrc{}; std::vector<double> probG;
+  // fileSource (ParticleObjects/Source/fileSource_class.f90): the rows of a printToFile dump
+  bool isFileSrc = false, fileSrcMG = false; std::vector<double> fileRows;
+  // printSource / outputFile (eigenPhysicsPackage_class.f90:278-281,463,501-504)
+  int printSource = 0; std::string outputFile = "./output"; int cycleInPhase[2] = {0, 0}, lastActive = 0; std::vector<int32_t> hBrood;
   sb_engine* eng = nullptr;
   std::string err;
   // results
@@ -70,6 +74,10 @@ struct eigenPhysicsPackage {
       rankOffset = totalPop / nRanks * rank + std::max(0, totalPop % nRanks + rank - nRanks);
       if (isFixed) { N_cycles = dict.getInt("cycles"); bufferSize = dict.getInt("buffer", 50); N_inactive = 0; N_active = N_cycles; }
       else { N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active"); }
+      outputFile = dict.getWord("outputFile", "./output");
+      printSource = dict.getInt("printSource", 0);
+      if (printSource < 0 || printSource > 2) return fail("printSource must be 0 (No printing), 1 (ASCII) or 2 (BINARY)");
+      if (printSource != 0 && isFixed) return fail("printSource is a keyword of the eigenvalue package");
       std::string nucData = dict.getWord("XSdata"), energy = dict.getWord("dataType");
       if (energy != "mg" && energy != "ce") return fail("dataType must be 'mg' or 'ce'");
       isCE = (energy == "ce");
@@ -98,7 +106,8 @@ struct eigenPhysicsPackage {
       if (isFixed) {
         tallies[0] = sb::buildTallies(sb::Dict::fromString(""), mats, data.nMat);
         tallies[1] = sb::buildTallies(dict.getDict("tally"), mats, data.nMat);
-        if (int rc = initPointSource(dict.getDict("source"))) return rc;
+        const sb::Dict& sd = dict.getDict("source");
+        if (int rc = (sd.getWord("type") == "fileSource") ? initFileSource(sd) : initPointSource(sd)) return rc;
       } else {
         tallies[0] = sb::buildTallies(dict.getDict("inactiveTally"), mats, data.nMat);
         tallies[1] = sb::buildTallies(dict.getDict("activeTally"), mats, data.nMat);
@@ -114,10 +123,60 @@ struct eigenPhysicsPackage {
         if (sb_define_tallies(eng, ph, tallies[ph].clerks.data(), (int)tallies[ph].clerks.size(), tallies[ph].normClerk, tallies[ph].normVal)) return engFail();
       if (sb_set_options(eng, &opt)) return engFail();
       if (isFixed && sb_set_fixed_source(eng, 1, bufferSize)) return engFail();
+      if (isFileSrc && sb_set_file_source(eng, (int64_t)(fileRows.size() / 10), fileRows.data(), fileSrcMG ? 1 : 0)) return engFail();
     } catch (const std::exception& e) { return fail(e.what()); }
     return 0;
   }
 
+  // fileSource%init (fileSource_class.f90:46-144): all rows are kept, broodID (column 9) is ignored by the sampling
+  int initFileSource(const sb::Dict& d) {
+    std::string energy = d.getWord("data", "ce");
+    if (energy != "ce" && energy != "mg") return fail("init (fileSource): Invalid source data type specified: must be ce or mg");
+    fileSrcMG = (energy == "mg");
+    if (fileSrcMG == isCE) return fail("init (fileSource): source data type inconsistent with nuclear database");
+    if (!d.isPresent("path")) return fail("init (fileSource): path must be specified in the dictionary for fileSource");
+    const std::string path = d.getWord("path");
+    const bool binary = d.getBool("binary", false);
+    FILE* f = fopen(path.c_str(), binary ? "rb" : "r");
+    if (!f) return fail("init (fileSource): cannot open the source file " + path);
+    double row[10];
+    for (;;) {
+      bool ok = true;
+      if (binary) ok = fread(row, sizeof(double), 10, f) == 10;
+      else for (int k = 0; k < 10 && ok; ++k) ok = fscanf(f, "%lf", &row[k]) == 1;
+      if (!ok) break;
+      fileRows.insert(fileRows.end(), row, row + 10);
+    }
+    fclose(f);
+    if (fileRows.empty()) return fail("init (fileSource): the source file holds no particles: " + path);
+    isFileSrc = true;
+    return 0;
+  }
+  // particleDungeon%printToFile (particleDungeon_class.f90:1077-1112) for the bank the cycle has just normalised: r, dir, E, real(G),
+  // real(broodID), wgt per site; stream binary (.bin) or one text row per site (.txt, 17 significant digits: reads back exactly)
+  // deferred = the caller still has to balance the banks of the ranks (loadBalancing is part of normSize_Repr): it prints afterwards
+  int printBank(int active, bool deferred = false) {
+    if (!deferred || nRanks == 1) cycleInPhase[active ? 1 : 0] += 1;      // the `i` of the cycles loop restarts with each phase
+    if (printSource == 0 || (deferred && nRanks > 1)) return 0;
+    if (downloadBank()) return -1;
+    hBrood.resize((size_t)std::max(1, hN));
+    if (sb_bank_brood(eng, (int)hBrood.size(), hBrood.data())) return engFail();
+    const bool bin = (printSource == 2);
+    const int i = cycleInPhase[active ? 1 : 0];
+    const std::string name = outputFile + "_source" + std::to_string(i) + "_rank" + std::to_string(rank) + (bin ? ".bin" : ".txt");
+    FILE* f = fopen(name.c_str(), bin ? "wb" : "w");
+    if (!f) return fail("printToFile: cannot open " + name);
+    std::vector<double> rows(10 * (size_t)hN);
+    for (int s = 0; s < hN; ++s) {
+      double* row = &rows[10 * (size_t)s];
+      for (int k = 0; k < 3; ++k) { row[k] = hr[3 * (size_t)s + k]; row[3 + k] = hdir[3 * (size_t)s + k]; }
+      row[6] = isCE ? hE[s] : 0.0; row[7] = isCE ? 0.0 : (double)hG[s]; row[8] = (double)hBrood[s]; row[9] = hw[s];
+    }
+    if (bin) fwrite(rows.data(), sizeof(double), rows.size(), f);
+    else for (int s = 0; s < hN; ++s) { for (int k = 0; k < 10; ++k) fprintf(f, "%s%.17g", k ? " " : "  ", rows[10 * (size_t)s + k]); fprintf(f, "\n"); }
+    fclose(f);
+    return 0;
+  }
   // pointSource%init (ParticleObjects/Source/pointSource_class.f90:60-140); the OUTSIDE check of the position is the engine's
   int initPointSource(const sb::Dict& d) {
     if (d.getWord("type") != "pointSource") return fail("fixed-source calculations: only pointSource is supported");
@@ -154,7 +213,7 @@ struct eigenPhysicsPackage {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (!isFixed) return fail("not a fixedSourcePhysicsPackage deck");
     if (nRanks > 1) return fail("fixed-source batches of several ranks: run one package per rank with its own share of pop");
-    if (sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
+    if (isFileSrc ? sb_source_file(eng, pop, pRNG, 0) : sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
     stride(totalPop);
     if (sb_run_cycle(eng, pRNG, 0, 1.0, 1, &last)) return engFail();
     stride(totalPop);
@@ -180,6 +239,7 @@ struct eigenPhysicsPackage {
     stride(totalPop + 1);
     if (sb_run_cycle_resample(eng, rng0, 0, k_new, active, pop, pRNG, &last)) return engFail();      // one synchronisation per cycle
     stride(1);
+    if (printBank(active)) return -1;
     k_new = last.k_cum;
     keff_0 = k_new;
     cycleK.push_back(k_new);
@@ -200,6 +260,7 @@ struct eigenPhysicsPackage {
   int cycleEnd(int active, const double* devSums) {
     if (sb_cycle_end(eng, devSums, &last)) return engFail();
     stride(totalPop + 1);
+    lastActive = active;
     (active ? nSegActive : nSegInactive) += last.n_segments;
     nHist += last.n_start;
     return 0;
@@ -208,6 +269,7 @@ struct eigenPhysicsPackage {
   int resampleRanked(const int32_t* popSizes, int32_t* newLocal, double& k_new) {
     if (sb_resample_ranked(eng, totalPop, masterRNG, nRanks, rank, popSizes, newLocal)) return engFail();
     stride(1);
+    if (printBank(lastActive, true)) return -1;
     k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
     return 0;
   }
@@ -217,6 +279,7 @@ struct eigenPhysicsPackage {
     stride(totalPop + 1);
     if (sb_cycle_end_resample_ranked(eng, hostSums, totalPop, masterRNG, nRanks, rank, popSizes, newSizes, &last)) return engFail();
     stride(1);
+    if (printBank(active, true)) return -1;
     (active ? nSegActive : nSegInactive) += last.n_segments;
     nHist += last.n_start;
     k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
@@ -233,6 +296,7 @@ struct eigenPhysicsPackage {
     stride(totalPop + 1);
     if (sb_run_cycle_resample(eng, rng0, 0, k_new, active, pop, pRNG, &last)) return engFail();
     stride(1);
+    if (printBank(active)) return -1;
     if (downloadBank()) return -1;
     int64_t nb = sb_tally_size(eng, active);
     hBins.resize((size_t)std::max<int64_t>(1, nb));
@@ -366,6 +430,9 @@ int sbh_ce_card_process(void* pv, int nuc, int* gridSize, int* rows, int* nMT, d
   return 0;
 }
 int sbh_ce_info(void* pv, int* nNuc, int* nMat) { auto* p = (eigenPhysicsPackage*)pv; *nNuc = (int)p->ceData.cards.size(); *nMat = p->ceData.nMat; return 0; }
+// several ranks: the source dump of this rank after the caller has balanced the banks
+int sbh_eigen_print_source(void* pv, int active) { return ((eigenPhysicsPackage*)pv)->printBank(active); }
+int sbh_eigen_print_source_mode(void* pv) { return ((eigenPhysicsPackage*)pv)->printSource; }
 int sbh_fixed_cycle(void* pv, sb_cycle_result* res) { auto* p = (eigenPhysicsPackage*)pv; int rc = p->fixedCycle(); if (res) *res = p->last; return rc; }
 int sbh_eigen_is_fixed(void* pv) { return ((eigenPhysicsPackage*)pv)->isFixed ? 1 : 0; }
 int sbh_eigen_is_ce(void* pv) { return ((eigenPhysicsPackage*)pv)->isCE ? 1 : 0; }

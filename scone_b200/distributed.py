@@ -39,7 +39,7 @@ def balance_plan(tot_pop, n_ranks, rank, pop_sizes):
     return tuple(int(x) for x in out)
 
 
-SITE_BYTES = 8 * 8 + 4      # r, dir, w, E (f64) + G (i32), as sb_site_buffer_bytes
+SITE_BYTES = 8 * 8 + 8      # r, dir, w, E (f64) + G, broodID (i32), as sb_site_buffer_bytes
 
 
 def site_buffer_bytes(k):
@@ -151,6 +151,9 @@ def cycle(pp, active, comm):
         raise EngineError("Normalisation failed!")
     if comm.size > 1:
         load_balance(pp, comm, sizes2)
+        # printSource: nextCycle%printToFile comes after normSize_Repr, whose last step is the balancing
+        if L.sbh_eigen_print_source(pp.h, 1 if active else 0) != 0:
+            raise EngineError(pp._err())
     return res
 
 

@@ -79,6 +79,8 @@ def load_library():
         "sbh_eigen_download_bank": (i32, [vp]), "sbh_eigen_upload_bank": (i32, [vp]),
         "sbh_eigen_is_ce": (i32, [vp]), "sbh_eigen_is_fixed": (i32, [vp]), "sbh_fixed_cycle": (i32, [vp, C.POINTER(CycleResult)]),
         "sb_set_fixed_source": (i32, [vp, i32, i32]), "sb_source_point": (i32, [vp, i32, u64, i32, vp]), "sbh_ce_info": (i32, [vp, ip, ip]),
+        "sb_bank_brood": (i32, [vp, i32, ip]), "sb_set_file_source": (i32, [vp, i64, dp, i32]), "sb_source_file": (i32, [vp, i32, u64, i32]),
+        "sbh_eigen_print_source": (i32, [vp, i32]), "sbh_eigen_print_source_mode": (i32, [vp]),
         "sbh_ce_card_process": (i32, [vp, i32, ip, ip, ip, dp, dp, ip, dp]),
         "sbh_eigen_cycles": (i32, [vp, i32, i32]), "sbh_eigen_run": (i32, [vp]),
         "sbh_eigen_stats": (i32, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp]),

@@ -65,3 +65,31 @@ def test_ranked_run_reproduces_single_rank_histories(tmp_path, deck, pop, ws):
         tot = sum(f["cs"] for f in fin)
         np.testing.assert_allclose(tot, cs, rtol=1e-10, atol=1e-300)
     pp.close()
+
+
+def test_ranked_source_dumps_concatenate_to_the_single_rank_dump(tmp_path):
+    """printSource with several ranks: every rank writes <outputFile>_source<i>_rank<r> AFTER the load balancing
+    (eigenPhysicsPackage_class.f90:275-281); the rank files in rank order hold the sites of the single-rank dump.  broodID is the
+    parent's index within its rank's share, carried through the exchange (MPI_PARTICLE_STATE holds it, mpi_func.f90:88-117)."""
+    pop, ws, ninact, nact = 7001, 2, 2, 1
+    base = "pop %d; inactive %d; active %d; seed 99; printSource 2; " % (pop, ninact, nact)
+    run_ranks(ws, "gloo", DECK["c5g7"], base + "outputFile %s;" % (tmp_path / "ranked"), ninact, nact, tmp_path)
+    pp = scone_b200.EigenPhysicsPackage(DECK["c5g7"], base + "outputFile %s;" % (tmp_path / "single"), device=0)
+    pp.generateInitialState()
+    for c in range(ninact + nact):
+        pp.cycle(c >= ninact)
+    pp.close()
+    shares = [scone_b200.distributed.workshare(pop, ws, r)[0] for r in range(ws)]
+    for i in (1, 2):
+        one = np.fromfile(str(tmp_path / ("single_source%d_rank0.bin" % i))).reshape(-1, 10)
+        parts = [np.fromfile(str(tmp_path / ("ranked_source%d_rank%d.bin" % (i, r)))).reshape(-1, 10) for r in range(ws)]
+        assert [len(p) for p in parts] == shares
+        cat = np.concatenate(parts)
+        cols = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+        assert np.array_equal(cat[:, cols], one[:, cols])
+        for r, p in enumerate(parts):
+            assert p[:, 8].min() >= 1 and p[:, 8].max() <= max(shares)
+        # rank 0 starts the global history numbering, so its own sites keep the brood IDs of the single-rank run
+        kept = min(len(parts[0]), len(one))
+        same = parts[0][:kept, 8] == one[:kept, 8]
+        assert same[: kept // 2].all()
