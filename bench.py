@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--pop", type=int, default=100000, help="histories per cycle PER GPU (weak scaling)")
     ap.add_argument("--inactive", type=int, default=10, help="untimed inactive cycles before the active phase")
     ap.add_argument("--tracking", default=None, choices=["DT", "ST", "HT"], help="transportOperator; default: what the deck says (delta tracking for the MG decks as BASELINE configs[0] names it, surface tracking with cache for the CE pin cell)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: per-cycle exchange between the ranks through peer memory (engine kernels storing into the other GPUs' HBM over NVLink) or through NCCL collectives")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,6 +254,12 @@ def main():
     comm = scone_b200.distributed.TorchComm(device=torch.device("cuda", local)) if world > 1 else None
     L = pp.L
     eng = pp.engine
+    exchange = ""
+    if world > 1:
+        peer = args.exchange == "peer" and scone_b200.distributed.enable_peer(pp, comm)
+        exchange = ("; per cycle: score sums, bank sizes and the load-balancing sites stored by the engines' kernels into the other GPUs' memory "
+                    "(CUDA IPC over NVLink), no collective, one host synchronisation") if peer else \
+                   "; per cycle: one all-gather of 7 f64 (score sums + bank size), neighbour send/recv of boundary sites (NCCL)"
     pp.generateInitialState()
     pp.cycles(False, args.inactive, comm=comm)
     for _ in range(max(3, args.warmup)):
@@ -374,7 +381,7 @@ def main():
                        "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck == "ce_pin" else "DT"), "inactive_cycles_before": args.inactive,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
                        "parallelism": "bank sharded by history index over %d GPU(s)%s" % (
-                           world, "; per cycle: all-reduce of 6 f64 k-eff sums, 2 all-gathers of one int, neighbour send/recv of boundary sites (NCCL)" if world > 1 else "")},
+                           world, exchange)},
             "longest_history_segments": max_seg,
             "segments_per_s": seg_all / (ms_max * 1e-3), "segments_per_history": seg / max(1, pop * args.steps),
             "keff": k_dev, "keff_std": k_std, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,

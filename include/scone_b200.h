@@ -164,7 +164,7 @@ typedef struct sb_cycle_result {
   int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
-       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10,
+       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10, SB_ERR_PEER_TIMEOUT = 11, SB_ERR_BALANCE = 12,
        SB_ERR_CE_ENERGY = 8 /* energy outside the bounds of the CE data */, SB_ERR_CE_DATA = 9 /* failed search / rejection loop in the reaction data */ };
 
 /* ---- life cycle -------------------------------------------------------------------------- */
@@ -263,6 +263,27 @@ int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_
                                  const int32_t* pop_sizes, int32_t* new_sizes, sb_cycle_result* res);
 int sb_resample_ranked(sb_engine* h, int tot_pop, uint64_t master_rng_state, int n_ranks, int rank, const int32_t* pop_sizes, int32_t* new_local_pop);
 size_t sb_site_buffer_bytes(int k);
+
+/* ---- the ranks of one node over peer memory (NVLink / NVSwitch) --------------------------------
+ * The same cycle with no host and no library collective in the loop: every rank owns a small mailbox + site staging buffers in
+ * its own HBM, exported with CUDA IPC; the other ranks' kernels store into it (score sums, bank sizes, the sites loadBalancing
+ * hands to the neighbours) and release a flag, the owner's kernels spin on their local flags.  Replaces, per cycle, the
+ * mpi_reduce / mpi_bcast of scoreMemory%reduceBins, the gathers and broadcasts of normSize_Repr (particleDungeon_class.f90:464,
+ * 516-518,593) and the mpi_send / mpi_recv of loadBalancing (:607-698).
+ *   sb_peer_create  after sb_set_options: allocates the region, returns its 64-byte cudaIpcMemHandle_t; stage_cap (sites) is the
+ *                   same on every rank and at least the largest sb_bank_capacity of the ranks
+ *   sb_peer_attach  handles of all ranks in rank order (the caller exchanges them once, e.g. MPI_Allgather); caps[r] = sb_peer_capacity
+ *                   (the stage_cap) of rank r (must be equal), may be NULL
+ *   sb_run_cycle_ranked_peer  = sb_cycle_begin + reduction + sb_cycle_end_resample_ranked + loadBalancing with ONE host
+ *                   synchronisation; final_sizes[n_ranks] = every rank's bank size afterwards.  All ranks must call it for the
+ *                   same cycles; a rank that does not show up within the timeout (default 20 s) gives SB_ERR_PEER_TIMEOUT.     */
+int sb_bank_capacity(sb_engine* h);
+int sb_peer_create(sb_engine* h, int n_ranks, int rank, int stage_cap, void* ipc_handle_64_bytes);
+int sb_peer_attach(sb_engine* h, const void* ipc_handles, const int32_t* caps);
+int sb_peer_capacity(sb_engine* h);
+int sb_peer_set_timeout(sb_engine* h, double seconds);
+int sb_run_cycle_ranked_peer(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop,
+                             uint64_t master_rng_state_resample, int32_t* final_sizes, sb_cycle_result* res);
 int sb_bank_export(sb_engine* h, int k_front, void* dev_buf_front, int k_back, void* dev_buf_back);
 int sb_bank_splice(sb_engine* h, int drop_front, int drop_back, int add_front, const void* dev_buf_front, int add_back, const void* dev_buf_back);
 

@@ -436,6 +436,196 @@ __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfir
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ranks of one node exchanging through peer memory (NVLink / NVSwitch; CUDA IPC between the processes), no host in the loop.
+// What SCONE moves over MPI per cycle is tiny: 6 score sums + the bank size of every rank (scoreMemory%reduceBins,
+// particleDungeon_class.f90:464,516-518,593) and the sites that loadBalancing hands to the neighbours (:607-698).  Every rank owns
+// one PeerBox in its own memory; the others WRITE into it (posted stores, then a release flag) and the owner spins on its local
+// flags - no rank ever reads remote memory.  Slots are double-buffered by cycle parity: the all-to-all of the sums is a barrier,
+// so a rank is never more than one cycle ahead of another and a slot is rewritten only after its reader has consumed it.
+// ------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX = 64;
+struct PeerBox {
+  double data[2][PEER_MAX][8];                   // [parity][source rank]: 6 score sums, bank size, 0
+  unsigned long long flagSums[2][PEER_MAX];      // cycle sequence number of the data above
+  unsigned long long flagSites[2][2];            // [parity][0 = from the rank below, 1 = from the rank above]
+  unsigned long long pad[4];
+};
+struct PeerPtrs { PeerBox* box[PEER_MAX]; char* stage[PEER_MAX]; };     // stage: 4 site buffers {below,above} x parity of every rank
+struct PeerPlan {            // what the host would have computed from the gathered sizes, left on the device
+  int n, rank, nGlobal, offLocal;
+  int popSizes[PEER_MAX], off[PEER_MAX + 1], newSizes[PEER_MAX], finalSizes[PEER_MAX];
+  int sendUp, recvUp, sendDown, recvDown, finalLocal, ok;
+};
+__device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void stReleaseSys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ bool spinUntil(const unsigned long long* flag, unsigned long long seq, unsigned long long timeoutNs) {
+  const unsigned long long t0 = globalTimerNs();
+  for (;;) {
+    if (ldAcquireSys(flag) >= seq) return true;
+    if (globalTimerNs() - t0 > timeoutNs) return false;
+    __nanosleep(200);
+  }
+}
+// all-to-all of { 6 sums, bank size } + the barrier it implies; sums added in rank order (same bits on every rank)
+__global__ void k_peer_post_wait(PeerPtrs P, int nRanks, int rank, unsigned long long seq, const double* own, double* total, PeerPlan* plan,
+                                 CycleDev* cd, int cap, unsigned long long timeoutNs) {
+  __shared__ int sOk[PEER_MAX];
+  const int par = (int)(seq & 1ULL), t = threadIdx.x;
+  if (t < nRanks) {
+    PeerBox* dst = P.box[t];
+    for (int k = 0; k < 8; ++k) dst->data[par][rank][k] = own[k];
+    __threadfence_system();
+    stReleaseSys(&dst->flagSums[par][rank], seq);
+    sOk[t] = spinUntil(&P.box[rank]->flagSums[par][t], seq, timeoutNs) ? 1 : 0;
+  }
+  __syncthreads();
+  if (t == 0) {
+    const PeerBox* me = P.box[rank];
+    bool ok = true;
+    for (int r = 0; r < nRanks; ++r) ok = ok && sOk[r];
+    double sum[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    long long tot = 0;
+    plan->n = nRanks; plan->rank = rank;
+    for (int r = 0; r < nRanks; ++r) {
+      const volatile double* d = me->data[par][r];
+      for (int k = 0; k < 6; ++k) sum[k] = sum[k] + (ok ? d[k] : (r == rank ? own[k] : 0.0));
+      int sz = ok ? (int)d[6] : (r == rank ? (int)own[6] : 0);
+      plan->popSizes[r] = sz; plan->off[r] = (int)tot; tot += sz;
+    }
+    plan->off[nRanks] = (int)tot;
+    if (!ok) atomicMax(&cd->error, SB_ERR_PEER_TIMEOUT);
+    if (tot > 2000000000LL || tot <= 0) { atomicMax(&cd->error, SB_ERR_NORM); tot = max(1, min(cd->nSites, cap)); }
+    plan->nGlobal = (int)tot; plan->offLocal = plan->off[rank]; plan->ok = ok ? 1 : 0;
+    for (int k = 0; k < 6; ++k) total[k] = sum[k];
+    total[6] = (double)tot; total[7] = 0.0;
+  }
+}
+__global__ void k_norm_setup_plan(NormDev* nd, const CycleDev* cd, int cap, int totPop, const PeerPlan* plan) {
+  nd->nLocal = min(cd->nSites, cap); nd->totPop = totPop; nd->check = 0;
+  nd->nGlobal = plan->nGlobal; nd->offLocal = plan->offLocal;
+}
+__global__ void k_norm_rank_counts_plan(const unsigned long long* rn, const CycleDev* cd, const NormDev* nd, const PeerPlan* plan, int* counts) {
+  __shared__ int sc[PEER_MAX]; __shared__ int so[PEER_MAX + 1];
+  const int nr = plan->n;
+  if (threadIdx.x < PEER_MAX) sc[threadIdx.x] = 0;
+  if (threadIdx.x <= nr) so[threadIdx.x] = plan->off[threadIdx.x];
+  __syncthreads();
+  const int n = nd->nGlobal;
+  const int excess = n - nd->totPop;
+  const int nDup = (excess < 0) ? (int)(((long long)(-excess)) % n) : 0;
+  const double thr = cd->thrReal;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double x = (double)(long long)rn[j] * (1.0 / 9223372036854775808.0);
+    int f;
+    if (excess > 0) f = (x > thr) ? 1 : 0;
+    else if (excess < 0) f = (nDup != 0 && x <= thr) ? 1 : 0;
+    else f = 1;
+    if (f) { int r = 0; while (r + 1 < nr && j >= so[r + 1]) ++r; atomicAdd(&sc[r], 1); }
+  }
+  __syncthreads();
+  if (threadIdx.x < nr && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
+}
+// every rank's size after normSize_Repr (what the mpi_allgather of :593 returns) and this rank's part of loadBalancing (:607-698)
+__global__ void k_peer_plan(PeerPlan* plan, const int* counts, const NormDev* nd, CycleDev* cd, int cap, int stageCap) {
+  const int nr = plan->n, rank = plan->rank, totPop = nd->totPop;
+  const long long tot = nd->nGlobal, excess = tot - totPop, nCopies = excess < 0 ? (-excess) / tot : 0;
+  long long off1 = 0, off2 = 0, sum = 0;
+  for (int i = 0; i < nr; ++i) {
+    int ns = excess > 0 ? counts[i] : (excess == 0 ? plan->popSizes[i] : (int)(plan->popSizes[i] * (nCopies + 1) + counts[i]));
+    plan->newSizes[i] = ns;
+    if (i < rank) off1 += ns;
+    sum += ns;
+  }
+  off2 = off1 + plan->newSizes[rank];
+  if (sum != totPop || plan->newSizes[rank] != cd->nNew) atomicMax(&cd->error, SB_ERR_NORM);
+  // getWorkshare / getOffset (mpi_func.f90:133-159)
+  auto offsetOf = [&](int r) { return (long long)(totPop / nr) * r + max(0, totPop % nr + r - nr); };
+  const long long t1 = offsetOf(rank), t2 = (rank + 1 == nr) ? totPop : offsetOf(rank + 1);
+  const long long eEnd = off2 - t2, eBeg = off1 - t1;
+  int sendUp = eEnd > 0 ? (int)eEnd : 0, recvUp = eEnd < 0 ? (int)(-eEnd) : 0;
+  int sendDown = eBeg < 0 ? (int)(-eBeg) : 0, recvDown = eBeg > 0 ? (int)eBeg : 0;
+  long long run = 0;
+  for (int i = 0; i < nr; ++i) {                 // every rank's size after the exchange with its two neighbours
+    long long a = run, b = run + plan->newSizes[i];
+    long long ta = offsetOf(i), tb = (i + 1 == nr) ? totPop : offsetOf(i + 1);
+    plan->finalSizes[i] = (int)(plan->newSizes[i] - max(0LL, b - tb) + max(0LL, tb - b) - max(0LL, ta - a) + max(0LL, a - ta));
+    if (max(0LL, b - tb) + max(0LL, ta - a) > plan->newSizes[i]) atomicMax(&cd->error, SB_ERR_BALANCE);     // nearest neighbours cannot fix this
+    run = b;
+  }
+  const int fin = plan->newSizes[rank] - sendUp - sendDown + recvUp + recvDown;
+  if (fin > cap || max(max(sendUp, sendDown), max(recvUp, recvDown)) > stageCap) { atomicMax(&cd->error, SB_ERR_BANK_OVERFLOW); sendUp = recvUp = sendDown = recvDown = 0; }
+  if (cd->error != 0) { sendUp = recvUp = sendDown = recvDown = 0; }
+  plan->sendUp = sendUp; plan->recvUp = recvUp; plan->sendDown = sendDown; plan->recvDown = recvDown;
+  plan->finalLocal = plan->newSizes[rank] - sendUp - sendDown + recvUp + recvDown;
+}
+// packed site layout of k sites with capacity `cap`: 8 f64 arrays of cap, then cap i32 (G), cap i32 (broodID)
+__device__ __forceinline__ void packSite(const Bank& b, int s, double* buf, int cap, int i) {
+  int* g = (int*)(buf + 8 * (size_t)cap);
+  buf[i] = b.rx[s]; buf[(size_t)cap + i] = b.ry[s]; buf[2 * (size_t)cap + i] = b.rz[s];
+  buf[3 * (size_t)cap + i] = b.ux[s]; buf[4 * (size_t)cap + i] = b.uy[s]; buf[5 * (size_t)cap + i] = b.uz[s];
+  buf[6 * (size_t)cap + i] = b.w[s]; buf[7 * (size_t)cap + i] = b.E[s]; g[i] = b.G[s]; g[cap + i] = b.brood[s];
+}
+__device__ __forceinline__ void unpackSite(Bank& b, int s, const double* buf, int cap, int i) {
+  const int* g = (const int*)(buf + 8 * (size_t)cap);
+  b.rx[s] = buf[i]; b.ry[s] = buf[(size_t)cap + i]; b.rz[s] = buf[2 * (size_t)cap + i];
+  b.ux[s] = buf[3 * (size_t)cap + i]; b.uy[s] = buf[4 * (size_t)cap + i]; b.uz[s] = buf[5 * (size_t)cap + i];
+  b.w[s] = buf[6 * (size_t)cap + i]; b.E[s] = buf[7 * (size_t)cap + i]; b.G[s] = g[i]; b.brood[s] = g[cap + i]; b.seq[s] = 0;
+}
+__host__ __device__ inline size_t peerStageBytes(int cap) { return ((size_t)cap * (8 * sizeof(double) + 2 * sizeof(int)) + 255) / 256 * 256; }
+// stage buffer of rank r: index 2*parity + (0 = sites arriving from below, 1 = from above)
+__device__ __forceinline__ double* peerStage(const PeerPtrs& P, int r, int par, int fromAbove, int cap) {
+  return (double*)(P.stage[r] + (size_t)(2 * par + fromAbove) * peerStageBytes(cap));
+}
+// the sites this rank gives away go straight into the neighbours' stage buffers (stores over NVLink)
+__global__ void k_peer_push(PeerPtrs P, const PeerPlan* plan, Bank src, int cap, int par) {
+  const int rank = plan->rank, nLocal = plan->newSizes[rank];
+  const int up = plan->sendUp, down = plan->sendDown;
+  double* bufUp = up > 0 ? peerStage(P, rank + 1, par, 0, cap) : nullptr;          // arrives "from below" at rank + 1
+  double* bufDown = down > 0 ? peerStage(P, rank - 1, par, 1, cap) : nullptr;      // arrives "from above" at rank - 1
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < up + down; i += gridDim.x * blockDim.x) {
+    if (i < up) packSite(src, nLocal - up + i, bufUp, cap, i);
+    else packSite(src, i - up, bufDown, cap, i - up);
+  }
+}
+__global__ void k_peer_flag_sites(PeerPtrs P, const PeerPlan* plan, unsigned long long seq) {
+  const int rank = plan->rank, par = (int)(seq & 1ULL);
+  __threadfence_system();
+  if (threadIdx.x == 0 && plan->sendUp > 0) stReleaseSys(&P.box[rank + 1]->flagSites[par][0], seq);
+  if (threadIdx.x == 1 && plan->sendDown > 0) stReleaseSys(&P.box[rank - 1]->flagSites[par][1], seq);
+}
+__global__ void k_peer_wait_sites(PeerPtrs P, const PeerPlan* plan, unsigned long long seq, CycleDev* cd, unsigned long long timeoutNs) {
+  const int rank = plan->rank, par = (int)(seq & 1ULL);
+  bool ok = true;
+  if (threadIdx.x == 0 && plan->recvDown > 0) ok = spinUntil(&P.box[rank]->flagSites[par][0], seq, timeoutNs);
+  if (threadIdx.x == 1 && plan->recvUp > 0) ok = spinUntil(&P.box[rank]->flagSites[par][1], seq, timeoutNs);
+  if (!ok) atomicMax(&cd->error, SB_ERR_PEER_TIMEOUT);
+}
+// the bank after loadBalancing: [received from below] + kept middle + [received from above]
+__global__ void k_peer_splice(PeerPtrs P, const PeerPlan* plan, Bank src, Bank dst, int cap, int par, const CycleDev* cd) {
+  const int rank = plan->rank;
+  const bool bad = cd->error != 0;
+  const int addF = bad ? 0 : plan->recvDown, addB = bad ? 0 : plan->recvUp, dropF = plan->sendDown, dropB = plan->sendUp;
+  const int keep = plan->newSizes[rank] - dropF - dropB;
+  const double* bufF = peerStage(P, rank, par, 0, cap);
+  const double* bufB = peerStage(P, rank, par, 1, cap);
+  const int n = addF + keep + addB;
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+    if (d < addF) unpackSite(dst, d, bufF, cap, d);
+    else if (d < addF + keep) {
+      int s = dropF + (d - addF);
+      dst.rx[d] = src.rx[s]; dst.ry[d] = src.ry[s]; dst.rz[d] = src.rz[s];
+      dst.ux[d] = src.ux[s]; dst.uy[d] = src.uy[s]; dst.uz[d] = src.uz[s];
+      dst.w[d] = src.w[s]; dst.G[d] = src.G[s]; dst.E[d] = src.E[s]; dst.brood[d] = src.brood[s]; dst.seq[d] = 0;
+    } else unpackSite(dst, d, bufB, cap, d - addF - keep);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fissionSource (ParticleObjects/Source/fissionSource_class.f90:149-271, source_inter.f90:98-118)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_source(const Model M, const char* blob, Bank out, int n, uint64_t rng0, int offset,
@@ -612,6 +802,9 @@ struct sb_engine {
   UserKeff userKeff[2] = {};
   // fixed-source calculations: private secondary buffers of the lanes
   bool fixedSource = false; int stkCap = 50; double* dStkD = nullptr; int* dStkG = nullptr; size_t stkLanes = 0; int stkAllocCap = 0;
+  // peer-memory exchange between the ranks of a node (sb_peer_*)
+  int peerRanks = 0, peerRank = 0, peerCap = 0; char* peerRegion = nullptr; PeerPtrs peerPtrs{}; void* peerOpened[PEER_MAX] = {};
+  PeerPlan* dPlan = nullptr; PeerPlan* hPlan = nullptr; double* dKsumTot = nullptr; unsigned long long peerSeq = 0; double peerTimeoutS = 20.0;
   bool broodValid = false;       // the current bank came out of a cycle (its sites have parents); false for source / uploaded banks
   double* dFileSrc = nullptr; long long nFileSrc = 0; bool fileSrcMG = false;     // fileSource rows (printToFile records)
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
@@ -870,6 +1063,8 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
   cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG); cudaFree(h->dFileSrc);
+  for (int r = 0; r < PEER_MAX; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerOpened[r]);
+  cudaFree(h->peerRegion); cudaFree(h->dPlan); cudaFreeHost(h->hPlan); cudaFree(h->dKsumTot);
   for (void* p : h->ceAllocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1045,6 +1240,8 @@ static int checkDeviceError(sb_engine* h, int code) {
     case SB_ERR_OVERLAP_MAT: msg = "Particle is in overlapping cells"; break;
     case SB_ERR_SAMPLING: msg = "Sampling failed (scatter XS / chi normalisation or random number above 1)"; break;
     case SB_ERR_NEST: msg = "Failed to find material cell (nesting exceeded)"; break;
+    case SB_ERR_PEER_TIMEOUT: msg = "peer exchange: a rank of the node did not post its cycle data in time"; break;
+    case SB_ERR_BALANCE: msg = "loadBalancing: nearest-neighbour exchange cannot restore the shares of this distribution"; break;
     case SB_ERR_FILE_SOURCE: msg = "fileSource: neutron sampled from file source is outside of geometry or in undefined region"; break;
     case SB_ERR_SOURCE: msg = "fissionSource: failed to find a fissile material in 10000 attempts"; break;
     case SB_ERR_NORM: msg = "Normalisation failed!"; break;
@@ -1420,6 +1617,110 @@ int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_
   for (int i = 0; i < n_ranks; ++i)
     new_sizes[i] = excess > 0 ? h->hRankCounts[i] : (excess == 0 ? pop_sizes[i] : (int)(pop_sizes[i] * (nCopies + 1) + h->hRankCounts[i]));
   if (new_sizes[rank] != h->nCur) { h->err = "sb_cycle_end_resample_ranked: inconsistent bank size after normalisation"; return -1; }
+  return 0;
+}
+
+// ---- ranks of one node over peer memory -------------------------------------------------------------------------------------
+static size_t peerRegionBytes(int cap) { return (sizeof(PeerBox) + 255) / 256 * 256 + 4 * peerStageBytes(cap); }
+int sb_bank_capacity(sb_engine* h) {
+  if (h->opt.max_pop < 1) { h->err = "sb_bank_capacity: set the options (max_pop) first"; return -1; }
+  if (ensureCapacity(h, h->opt.max_pop)) return -1;
+  return h->cap;
+}
+int sb_peer_create(sb_engine* h, int n_ranks, int rank, int stage_cap, void* ipc_handle) {
+  if (n_ranks < 1 || n_ranks > PEER_MAX || rank < 0 || rank >= n_ranks || !ipc_handle) { h->err = "sb_peer_create: invalid rank arguments (at most 64 ranks)"; return -1; }
+  if (h->peerRegion) { h->err = "sb_peer_create: the peer region of this engine exists already"; return -1; }
+  if (h->opt.max_pop < 1) { h->err = "sb_peer_create: set the options (max_pop) first"; return -1; }
+  if (ensureCapacity(h, h->opt.max_pop)) return -1;
+  if (stage_cap < h->cap) { h->err = "sb_peer_create: stage_cap must be at least the largest bank capacity of the ranks (sb_bank_capacity)"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  h->peerRanks = n_ranks; h->peerRank = rank; h->peerCap = stage_cap;
+  const size_t bytes = peerRegionBytes(stage_cap);
+  CUDA_OK(cudaMalloc(&h->peerRegion, bytes));
+  CUDA_OK(cudaMemset(h->peerRegion, 0, (sizeof(PeerBox) + 255) / 256 * 256));
+  CUDA_OK(cudaMalloc(&h->dPlan, sizeof(PeerPlan))); CUDA_OK(cudaMallocHost(&h->hPlan, sizeof(PeerPlan)));
+  CUDA_OK(cudaMalloc(&h->dKsumTot, 8 * sizeof(double)));
+  if (!h->dRankCounts) { CUDA_OK(cudaMalloc(&h->dRankCounts, 64 * sizeof(int))); CUDA_OK(cudaMallocHost(&h->hRankCounts, 64 * sizeof(int))); }
+  const size_t nG = (size_t)n_ranks * (size_t)stage_cap;                 // the stream over all ranks' banks, upper bound
+  if (nG > h->rnGlobalCap) { cudaFree(h->dRnGlobal); h->rnGlobalCap = nG; CUDA_OK(cudaMalloc(&h->dRnGlobal, sizeof(unsigned long long) * nG)); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CUDA_OK(cudaIpcGetMemHandle(&hd, h->peerRegion));
+  memcpy(ipc_handle, &hd, sizeof(hd));
+  CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+int sb_peer_attach(sb_engine* h, const void* ipc_handles, const int32_t* caps) {
+  if (!h->peerRegion) { h->err = "sb_peer_attach: sb_peer_create first"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t boxBytes = (sizeof(PeerBox) + 255) / 256 * 256;
+  for (int r = 0; r < h->peerRanks; ++r) {
+    if (caps && caps[r] != h->peerCap) { h->err = "sb_peer_attach: every rank must have created its region with the same stage_cap"; return -1; }
+    char* base = h->peerRegion;
+    if (r != h->peerRank) {
+      cudaIpcMemHandle_t hd; memcpy(&hd, (const char*)ipc_handles + 64 * (size_t)r, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { h->err = std::string("sb_peer_attach: cudaIpcOpenMemHandle failed for rank ") + std::to_string(r) + ": " + cudaGetErrorString(e); cudaGetLastError(); return -1; }
+      h->peerOpened[r] = ptr; base = (char*)ptr;
+    }
+    h->peerPtrs.box[r] = (PeerBox*)base; h->peerPtrs.stage[r] = base + boxBytes;
+  }
+  h->peerSeq = 0;
+  return 0;
+}
+int sb_peer_capacity(sb_engine* h) { return h->peerCap; }
+int sb_peer_set_timeout(sb_engine* h, double seconds) { if (!(seconds > 0.0)) { h->err = "sb_peer_set_timeout: must be +ve"; return -1; } h->peerTimeoutS = seconds; return 0; }
+
+// One cycle of one rank with the other ranks' data arriving through peer memory: transport, all-to-all of the score sums and bank
+// sizes, cycle close, normSize_Repr over the global stream, loadBalancing with the two neighbours - one host synchronisation.
+int sb_run_cycle_ranked_peer(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop, uint64_t master_rng_resample,
+                             int32_t* final_sizes, sb_cycle_result* res) {
+  if (!h->peerPtrs.box[h->peerRank]) { h->err = "sb_run_cycle_ranked_peer: sb_peer_attach first"; return -1; }
+  if (h->cap > h->peerCap) { h->err = "sb_run_cycle_ranked_peer: the bank capacity grew beyond the stage capacity of sb_peer_create"; return -1; }
+  if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
+  cudaStream_t st = h->stream;
+  const unsigned long long seq = ++h->peerSeq, tmo = (unsigned long long)(h->peerTimeoutS * 1.0e9);
+  const int par = (int)(seq & 1ULL), nr = h->peerRanks;
+  k_peer_post_wait<<<1, PEER_MAX, 0, st>>>(h->peerPtrs, nr, h->peerRank, seq, h->dKsum, h->dKsumTot, h->dPlan, h->dCd, h->cap, tmo);
+  if (cycleCloseEnqueue(h, h->dKsumTot)) return -1;
+  {  // normSize_Repr with the global sizes taken from the plan on the device (resampleEnqueue with host-known sizes otherwise)
+    Bank& sorted = h->bank[(h->cur + 2) % 3]; Bank& dst = h->bank[(h->cur + 1) % 3];
+    const long long nGmax = (long long)nr * h->peerCap; const int nSites = h->cap;
+    unsigned long long* rn = h->dRnGlobal;
+    k_norm_setup_plan<<<1, 1, 0, st>>>(h->dNd, h->dCd, h->cap, tot_pop, h->dPlan);
+    int g = gridFor(h, nGmax, 256), gl = gridFor(h, nSites, 256);
+    k_rn_generate<<<gridFor(h, (nGmax + RN_CHUNK - 1) / RN_CHUNK, 128), 128, 0, st>>>(rn, h->dNd, master_rng_resample);
+    k_zero_int<<<gridFor(h, SEL_BINS, 256), 256, 0, st>>>(h->dHist, SEL_BINS);
+    k_sel_hist<<<g, 256, 0, st>>>(rn, h->dNd, h->dHist);
+    k_sel_find_bin<<<1, 1024, 0, st>>>(h->dHist, h->dCd, h->dNd);
+    k_sel_collect<<<g, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dCand);
+    k_sel_threshold<<<1, 1024, 0, st>>>(h->dCand, h->dCd);
+    k_norm_flags<<<gl, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dFlag);
+    int tiles = (nSites + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile);
+    k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, &h->dNd->nLocal, nullptr);
+    k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile, h->dFlagOff);
+    k_norm_scatter<<<gl, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
+    k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dNd, h->dCd);
+    CUDA_OK(cudaMemsetAsync(h->dRankCounts, 0, 64 * sizeof(int), st));
+    k_norm_rank_counts_plan<<<g, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dPlan, h->dRankCounts);
+    k_peer_plan<<<1, 1, 0, st>>>(h->dPlan, h->dRankCounts, h->dNd, h->dCd, h->cap, h->peerCap);
+    // loadBalancing: push to the neighbours, flag, wait for what they push, rebuild
+    k_peer_push<<<gridFor(h, h->cap / 8 + 1, 256), 256, 0, st>>>(h->peerPtrs, h->dPlan, dst, h->peerCap, par);
+    k_peer_flag_sites<<<1, 32, 0, st>>>(h->peerPtrs, h->dPlan, seq);
+    k_peer_wait_sites<<<1, 32, 0, st>>>(h->peerPtrs, h->dPlan, seq, h->dCd, tmo);
+    k_peer_splice<<<gl, 256, 0, st>>>(h->peerPtrs, h->dPlan, dst, sorted, h->peerCap, par, h->dCd);
+    h->launches += 20;
+  }
+  CUDA_OK(cudaMemcpyAsync(h->hPlan, h->dPlan, sizeof(PeerPlan), cudaMemcpyDeviceToHost, st));
+  if (cycleFinish(h, res)) return -1;                      // the one synchronisation
+  if (h->hCd->nSites <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
+  h->cur = (h->cur + 2) % 3;
+  h->nCur = h->hPlan->finalLocal; h->broodValid = true;
+  h->kNormNext = h->kCumLast;
+  h->sortedReady = false;
+  if (final_sizes) for (int i = 0; i < nr; ++i) final_sizes[i] = h->hPlan->finalSizes[i];
   return 0;
 }
 

@@ -286,6 +286,19 @@ struct eigenPhysicsPackage {
     return 0;
   }
 
+  // the whole cycle of one rank with the other ranks reached through peer memory (sb_peer_*): no collective, one synchronisation
+  int cyclePeer(int active, int32_t* finalSizes, double& k_new) {
+    if (!eng) return fail("no engine: this handle was created without a device");
+    const uint64_t rng0 = pRNG;
+    stride(totalPop + 1);
+    if (sb_run_cycle_ranked_peer(eng, rng0, 0, k_new, active, totalPop, masterRNG, finalSizes, &last)) return engFail();
+    stride(1);
+    (active ? nSegActive : nSegInactive) += last.n_segments;
+    nHist += last.n_start;
+    k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
+    return printBank(active);
+  }
+
   // the same cycle with the dungeons kept in HOST memory, as a shim that leaves thisCycle/nextCycle in
   // Fortran arrays would do: upload bank, run, resample, download bank, read the cycle's bins
   int cycleHostBuffers(int active, double& k_new) {
@@ -430,6 +443,9 @@ int sbh_ce_card_process(void* pv, int nuc, int* gridSize, int* rows, int* nMT, d
   return 0;
 }
 int sbh_ce_info(void* pv, int* nNuc, int* nMat) { auto* p = (eigenPhysicsPackage*)pv; *nNuc = (int)p->ceData.cards.size(); *nMat = p->ceData.nMat; return 0; }
+int sbh_eigen_cycle_peer(void* pv, int active, double* k, int32_t* finalSizes, sb_cycle_result* res) {
+  auto* p = (eigenPhysicsPackage*)pv; int rc = p->cyclePeer(active, finalSizes, *k); if (res) *res = p->last; return rc;
+}
 // several ranks: the source dump of this rank after the caller has balanced the banks
 int sbh_eigen_print_source(void* pv, int active) { return ((eigenPhysicsPackage*)pv)->printBank(active); }
 int sbh_eigen_print_source_mode(void* pv) { return ((eigenPhysicsPackage*)pv)->printSource; }

@@ -63,6 +63,7 @@ class TorchComm:
         self._sizes = torch.zeros(self.size, dtype=torch.int32, device=self.device if self.on_device else "cpu")
         self._one = torch.zeros(1, dtype=torch.int32, device=self.device if self.on_device else "cpu")
         self._bufs = {}
+        self.peer = False          # set by enable_peer(): the engines exchange through peer memory, this object is not used per cycle
 
     def sync(self):
         if self.device.type == "cuda":
@@ -125,10 +126,61 @@ class TorchComm:
             self.sync()
 
 
+def enable_peer(pp, comm):
+    """Connect the engines of the ranks of one node through peer memory (include/scone_b200.h, sb_peer_*): every rank exports its
+    mailbox region with CUDA IPC, the handles go round once over the process group; afterwards a cycle needs no collective.
+    Returns True if every rank attached (False, with the NCCL / gloo exchange kept, if IPC is not available)."""
+    import torch
+    L, eng = pp.L, pp.engine
+    handle = C.create_string_buffer(64)
+    caps = [None] * comm.size
+    comm.dist.all_gather_object(caps, int(L.sb_bank_capacity(eng)), group=comm.group)
+    ok = min(caps) > 0 and L.sb_peer_create(eng, comm.size, comm.rank, max(caps), handle) == 0
+    why = "" if ok else pp._eng_err()
+    mine = (bytes(handle.raw), int(L.sb_peer_capacity(eng)) if ok else -1, socket_host())
+    everyone = [None] * comm.size
+    comm.dist.all_gather_object(everyone, mine, group=comm.group)
+    ok = ok and all(c == mine[1] and c > 0 for _, c, _ in everyone) and all(hn == mine[2] for _, _, hn in everyone)
+    if ok:
+        blob = b"".join(hd for hd, _, _ in everyone)
+        caps = np.array([c for _, c, _ in everyone], np.int32)
+        ok = L.sb_peer_attach(eng, blob, caps.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        why = "" if ok else pp._eng_err()
+    elif not why:
+        why = "ranks on different hosts or with different bank capacities: %r" % [(c, hn) for _, c, hn in everyone]
+    flags = [None] * comm.size
+    comm.dist.all_gather_object(flags, bool(ok), group=comm.group)
+    comm.peer = all(flags)
+    comm.peer_error = why
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    return comm.peer
+
+
+def socket_host():
+    import socket
+    return socket.gethostname()
+
+
+def cycle_peer(pp, active, comm):
+    """One cycle with the exchange done by the engines themselves over peer memory: one call, one synchronisation."""
+    L = pp.L
+    final = np.zeros(comm.size, np.int32)
+    res, k = CycleResult(), C.c_double(pp.k)
+    if L.sbh_eigen_cycle_peer(pp.h, 1 if active else 0, C.byref(k), final.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(res)) != 0:
+        raise EngineError(pp._err())
+    pp.k = k.value
+    if int(final.sum()) != pp.total_pop:
+        raise EngineError("Normalisation failed!")
+    return res
+
+
 def cycle(pp, active, comm):
     """One cycle of `pp` (EigenPhysicsPackage created with rank / n_ranks) in step with the other ranks.
     eigenPhysicsPackage_class.f90:203-307 with MPI defined."""
     L = pp.L
+    if getattr(comm, "peer", False):
+        return cycle_peer(pp, active, comm)
     n_sites = C.c_int32()
     if L.sbh_eigen_cycle_begin(pp.h, 1 if active else 0, pp.k, comm.sums.data_ptr(), C.byref(n_sites)) != 0:
         raise EngineError(pp._err())

@@ -81,6 +81,10 @@ def load_library():
         "sb_set_fixed_source": (i32, [vp, i32, i32]), "sb_source_point": (i32, [vp, i32, u64, i32, vp]), "sbh_ce_info": (i32, [vp, ip, ip]),
         "sb_bank_brood": (i32, [vp, i32, ip]), "sb_set_file_source": (i32, [vp, i64, dp, i32]), "sb_source_file": (i32, [vp, i32, u64, i32]),
         "sbh_eigen_print_source": (i32, [vp, i32]), "sbh_eigen_print_source_mode": (i32, [vp]),
+        "sb_peer_create": (i32, [vp, i32, i32, i32, vp]), "sb_bank_capacity": (i32, [vp]), "sb_peer_attach": (i32, [vp, vp, ip]), "sb_peer_capacity": (i32, [vp]),
+        "sb_peer_set_timeout": (i32, [vp, dbl]),
+        "sb_run_cycle_ranked_peer": (i32, [vp, u64, i32, dbl, i32, i32, u64, ip, C.POINTER(CycleResult)]),
+        "sbh_eigen_cycle_peer": (i32, [vp, i32, dp, ip, C.POINTER(CycleResult)]),
         "sbh_ce_card_process": (i32, [vp, i32, ip, ip, ip, dp, dp, ip, dp]),
         "sbh_eigen_cycles": (i32, [vp, i32, i32]), "sbh_eigen_run": (i32, [vp]),
         "sbh_eigen_stats": (i32, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp]),

@@ -1,5 +1,5 @@
 """Worker of tests/test_gpu_distributed.py: one rank of an eigenvalue run whose bank is shared between ranks.
-argv: root port rank world backend deck overrides ncycles_inactive ncycles_active outdir"""
+argv: root port rank world backend deck overrides ncycles_inactive ncycles_active outdir [peer]"""
 import os
 import sys
 
@@ -18,6 +18,8 @@ torch.cuda.set_device(dev)
 dist.init_process_group(backend, init_method="tcp://127.0.0.1:%s" % port, rank=rank, world_size=ws)
 comm = D.TorchComm(device=torch.device("cuda", dev))
 pp = scone_b200.EigenPhysicsPackage(deck, ov, device=dev, rank=rank, n_ranks=ws)
+if len(sys.argv) > 11 and sys.argv[11] == "peer":          # exchange through peer memory instead of the process group
+    assert D.enable_peer(pp, comm), "peer memory could not be attached: " + comm.peer_error
 pp.generateInitialState()
 ks, segs = [], []
 for c in range(ninact + nact):

@@ -21,10 +21,10 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def run_ranks(ws, backend, deck, ov, ninact, nact, out):
+def run_ranks(ws, backend, deck, ov, ninact, nact, out, extra=()):
     port = str(_free_port())
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), ROOT, port, str(r), str(ws), backend,
-                               deck, ov, str(ninact), str(nact), str(out)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                               deck, ov, str(ninact), str(nact), str(out), *extra], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(ws)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
@@ -93,3 +93,26 @@ def test_ranked_source_dumps_concatenate_to_the_single_rank_dump(tmp_path):
         kept = min(len(parts[0]), len(one))
         same = parts[0][:kept, 8] == one[:kept, 8]
         assert same[: kept // 2].all()
+
+
+@pytest.mark.parametrize("deck,pop,ws", [("c5g7", 20001, 2), ("c5g7", 9000, 3), ("ce_pin", 3001, 2)])
+def test_peer_memory_exchange_reproduces_single_rank_histories(tmp_path, deck, pop, ws):
+    """The ranks exchange score sums, bank sizes and the balanced sites by storing into each other's memory (CUDA IPC; NVLink on a
+    multi-GPU node) with no collective and one host synchronisation per cycle: same banks, bit for bit, as the single-rank run."""
+    ninact, nact = 3, 2
+    ov = "pop %d; inactive %d; active %d; seed 4242;" % (pop, ninact, nact)
+    run_ranks(ws, "gloo", DECK[deck], ov, ninact, nact, tmp_path, extra=("peer",))
+    pp = scone_b200.EigenPhysicsPackage(DECK[deck], ov, device=0)
+    pp.generateInitialState()
+    fin = [np.load(os.path.join(tmp_path, "final_r%d.npz" % r)) for r in range(ws)]
+    for c in range(ninact + nact):
+        res = pp.cycle(c >= ninact)
+        parts = [np.load(os.path.join(tmp_path, "bank_c%d_r%d.npz" % (c, r))) for r in range(ws)]
+        assert [len(p["w"]) for p in parts] == [scone_b200.distributed.workshare(pop, ws, r)[0] for r in range(ws)]
+        for key, ref in zip(("r", "d", "w", "G"), pp.bank()):
+            assert np.array_equal(np.concatenate([p[key] for p in parts]), ref), "bank differs after cycle %d (%s)" % (c, key)
+        for f in fin:
+            assert f["k"][c] == pytest.approx(pp.k, rel=1e-12)
+        assert sum(int(f["seg"][c]) for f in fin) == res.n_segments
+    assert len({int(f["rng"][0]) for f in fin}) == ws          # every rank keeps its own stream offset
+    pp.close()
