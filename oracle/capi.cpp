@@ -72,6 +72,33 @@ void orc_rotate_vector(const double* dir, double mu, double phi, double* out) {
   for (int k = 0; k < 3; ++k) out[k] = n[k];
 }
 int orc_grid_search_lin(double mini, double maxi, int N, double v) { Grid g; g.initEqual(mini, maxi, N, "lin"); return g.search(v); }
+// ---- tally maps (for the reference's map unit tests) -------------------------------------------
+void* orc_map_new(const char* text, const char* matList) {
+  ORC_TRY
+  std::map<std::string, int> mats;
+  { std::istringstream is(matList ? matList : ""); std::string n; int i; while (is >> n >> i) mats[n] = i; }
+  return newTallyMap(Dict::fromString(text), mats).release();
+  ORC_CATCH(nullptr)
+}
+void orc_map_free(void* m) { delete (TallyMap*)m; }
+int orc_map_bins(void* m) { return ((TallyMap*)m)->bins(); }
+int orc_map_map(void* m, const double* r, double E, int isMG, int G, int matIdx) {
+  ParticleState s; for (int k = 0; k < 3; ++k) s.r[k] = r[k];
+  s.E = E; s.isMG = isMG != 0; s.G = G; s.matIdx = matIdx;
+  return ((TallyMap*)m)->map(s);
+}
+// grid_class (SharedModules/grid_class.f90): kind 0 lin, 1 log, 2 unstruct (bins given); returns the number of bin boundaries,
+// fills idx[] = search(keys[]) and bounds[] = the boundaries
+int orc_grid(int kind, double mini, double maxi, int N, const double* binsIn, int nBinsIn, int nKeys, const double* keys, int* idx, double* bounds, int cap) {
+  ORC_TRY
+  Grid g;
+  if (kind == 2) g.initUnstruct(std::vector<double>(binsIn, binsIn + nBinsIn));
+  else g.initEqual(mini, maxi, N, kind == 0 ? "lin" : "log");
+  for (int i = 0; i < nKeys; ++i) idx[i] = g.search(keys[i]);
+  for (size_t i = 0; i < g.bins.size() && (int)i < cap; ++i) bounds[i] = g.bins[i];
+  return (int)g.bins.size();
+  ORC_CATCH(-1)
+}
 int orc_binary_search(const double* a, int n, double v) { std::vector<double> x(a, a + n); return Grid::binarySearch(x, v); }
 
 // ---- geometry ----------------------------------------------------------------
@@ -317,6 +344,20 @@ uint64_t orc_mg_sample_fission(void* dbv, int matIdx, uint64_t state, double* mu
   return r.seed;
 }
 
+// heapQueue (DataStructures/heapQueue_class.f90): push the sequence (conditional = only values below the current maximum once the
+// queue is non-empty, as normSize_Repr uses it); returns the maximum, *size = entries held
+double orc_heap_queue(int maxSize, int n, const double* seq, int conditional, int* size) {
+  ORC_TRY
+  HeapQueue hq; hq.init(maxSize);
+  for (int i = 0; i < n; ++i) {
+    if (conditional && hq.size > 0 && !(seq[i] < hq.maxValue())) continue;
+    hq.pushReplace(seq[i]);
+  }
+  *size = hq.size;
+  return hq.maxValue();
+  ORC_CATCH(std::nan(""))
+}
+
 // ---- dungeon -------------------------------------------------------------------
 // normSize_Repr on a bank described by its broodIDs; `tag` travels with each site so the
 // caller can see which sites survive and in which order. Returns new size (or -1).
@@ -409,6 +450,30 @@ int orc_keff_implicit_sequence(double total, double capture, double fission, dou
     t.reportCycleEnd(pit);
   }
   return t.getKeff(*k, *std_) ? 0 : -1;
+  ORC_CATCH(-1)
+}
+// collisionClerk_test.f90 testScoring / testScoringVirtual and trackClerk_test.f90 testScoring: a clerk of the given dictionary is fed
+// n events { material, weight, virtual flag (collision) or path length (track) } over the constant-XS database, then one cycle is closed
+// with norm 1; out[] = the means of the clerk's bins.  kind 0: reportInColl, kind 1: reportPath.
+int orc_clerk_sequence(const char* clerkText, const char* matList, double xsAll, double trackingXS, int kind, int n, const int* matIdx,
+                       const double* w, const double* aux, double* out, int cap) {
+  ORC_TRY
+  ConstXsView xs; xs.x.total = xsAll; xs.x.capture = xsAll; xs.x.fission = xsAll; xs.x.nuFission = xsAll; xs.x.elasticScatter = xsAll; xs.x.inelasticScatter = xsAll;
+  std::map<std::string, int> mats;
+  { std::istringstream is(matList ? matList : ""); std::string nm; int i; while (is >> nm >> i) mats[nm] = i; }
+  TallyAdmin t;
+  t.init(Dict::fromString(std::string("myClerk { ") + clerkText + " }"), mats);
+  for (int i = 0; i < n; ++i) {
+    Particle p; p.coords.matIdx = matIdx[i]; p.w = w[i]; p.E = 10.0; p.isMG = false;
+    p.preCollision = p.state(); p.prePath = p.state();
+    if (kind == 0) t.reportInColl(p, xs, trackingXS, aux[i] != 0.0);
+    else t.reportPath(p, xs, aux[i]);
+  }
+  Dungeon pit; pit.init(1);
+  t.reportCycleEnd(pit);
+  if (t.mem.N > cap) return -2;
+  for (long i = 0; i < t.mem.N; ++i) { double m, sd; t.mem.getResult(m, sd, i + 1, 1); out[i] = m; }
+  return (int)t.mem.N;
   ORC_CATCH(-1)
 }
 // keffAnalogClerk_test.f90 test1CycleBatch: cycles of { start population weight, end population weight, k_eff of the end dungeon }; closeCycle norm 0.8
@@ -529,6 +594,17 @@ double orc_endftable_at(int n, const double* x, const double* y, int nr, const i
 void* orc_ce_nuclide_from_acebin(const char* path) {
   CE_TRY orc_ce::AceCard ace; orc::readAceBin(ace, path); auto* n = new orc_ce::Nuclide(); n->init(ace, true); return n; CE_CATCH(nullptr)
 }
+// aceCard header and fission-data flags (DataDecks/Tests/aceCard_iTest.f90): out = { AW, TZ }, flags = { precursorGroups, isFissile,
+// hasNuPrompt, hasNuDelayed, hasNuTotal }, zaid[16]
+int orc_ace_card_info(const char* path, double* out, int* flags, char* zaid) {
+  CE_TRY orc_ce::AceCard ace; orc::readAceBin(ace, path);
+  out[0] = ace.AW; out[1] = ace.TZ;
+  flags[0] = ace.NXS[7]; flags[1] = ace.isFiss ? 1 : 0; flags[2] = ace.promptNUp != 0; flags[3] = ace.delayNUp != 0; flags[4] = ace.totalNUp != 0;
+  strncpy(zaid, ace.ZAID.c_str(), 15); zaid[15] = 0;
+  return 0; CE_CATCH(-1)
+}
+// elasticNeutronScatter of the nuclide: 1 if the angular law is isotropic (LOCB == 0), else 0
+int orc_ce_nuclide_elastic_isotropic(void* h) { return ((orc_ce::Nuclide*)h)->elastic.angle.kind == orc_ce::AngleLaw::ISOTROPIC ? 1 : 0; }
 int orc_ce_nuclide_mt_list(void* h, int* MTs, int* firstIdx) {
   auto* x = (orc_ce::Nuclide*)h;
   for (int i = 0; i < x->nMTinelastic; ++i) { MTs[i] = x->mtData[i].MT; firstIdx[i] = x->mtData[i].firstIdx; }

@@ -64,3 +64,52 @@ def test_flat_xs_equals_oracle(orc, deck):
     orc.orc_mg_free(db)
     orc.orc_eigen_free(e)
     assert (maj > 0).all()
+
+
+# --------------------------------------------------------------------------- geomGraph_test / uniFills_test
+# A geometry whose universe fill vectors are the ones Geometry/Tests/geomGraph_test.f90:16-46 builds by hand:
+#   idx 1 (id 3)    [-7, OUTSIDE]         idx 2 (id 7)    [-1001, -1001, -1003]     idx 3 (id 1001) [1, 4]
+#   idx 4 (id 1002) [1, 3]                idx 5 (id 1003) [1, 2]                     idx 6, 7 (ids 200, 201) [-1001, -200] (unused)
+GRAPH_GEOM = """
+boundary (0 0 0 0 0 0);
+graph { type %s; }
+surfaces { bound { id 1; type sphere; origin (0.0 0.0 0.0); radius 10.0; } }
+cells { }
+universes {
+  root { id 3; type rootUniverse; border 1; fill u<7>; }
+  u7    { id 7;    type pinUniverse; radii (1.0 2.0 0.0); fills (u<1001> u<1001> u<1003>); }
+  u1001 { id 1001; type pinUniverse; radii (0.5 0.0); fills (m1 m4); }
+  u1002 { id 1002; type pinUniverse; radii (0.5 0.0); fills (m1 m3); }
+  u1003 { id 1003; type pinUniverse; radii (0.5 0.0); fills (m1 m2); }
+  u200  { id 200;  type pinUniverse; radii (0.5 0.0); fills (u<1001> u<200>); }
+  u201  { id 201;  type pinUniverse; radii (0.5 0.0); fills (u<1001> u<200>); }
+}
+nuclearData { materials { m1 { temp 1; composition { } } m2 { temp 1; composition { } } m3 { temp 1; composition { } } m4 { temp 1; composition { } } } }
+"""
+
+
+@pytest.mark.parametrize("kind,idx_ref,id_ref,unique", [
+    ("shrunk", [-2, 0, -3, -3, -5, 1, 4, 1, 2], [3, 0, 6, 6, 8, 1, 2, 3, 4], 4),                       # geomGraph_test.f90 test_shrunk :60-66
+    ("extended", [-2, 0, -3, -3, -5, 1, 4, 1, 4, 1, 2], [3, 0, 6, 8, 10, 1, 2, 3, 4, 5, 6], 6)])      # test_extended :96-102
+def test_geom_graph_known_answers(orc, kind, idx_ref, id_ref, unique):
+    text = GRAPH_GEOM % kind
+    for g in (scone_b200.GeometryHandle(text, device=-1), ol.Geom(orc, text)):      # the product's host builder and the oracle's
+        idx, gid = g.graph()
+        assert idx.tolist() == idx_ref and gid.tolist() == id_ref
+        info = g.info()
+        assert info["uniqueCells"] == unique and info["nUni"] == 7 and info["rootIdx"] == 1
+        assert info["nesting"] == 3                                                  # uniFills_test.f90 test_nesting_count :118
+    g = scone_b200.GeometryHandle(text, device=-1)
+    assert g.uni_fill(1) == [-2, 0] and g.uni_fill(2) == [-3, -3, -5] and g.uni_fill(3) == [1, 4] and g.uni_fill(6) == [-3, -6]
+    assert g.active_mats() == [1, 2, 4]                                              # graph % usedMats, :65 / :101
+
+
+def test_geometry_structure_errors(orc):
+    # uniFills_test.f90 test_cycles :74-111 (a universe below itself), test_outside_search :125-131 (outside below the root)
+    cyc = GRAPH_GEOM.replace("fills (m1 m4)", "fills (m1 u<7>)") % "shrunk"
+    out = GRAPH_GEOM.replace("fills (m1 m2)", "fills (m1 outside)") % "shrunk"
+    for text, msg in ((cyc, "recursion"), (out, "outside fill")):
+        with pytest.raises(scone_b200.EngineError, match=msg):
+            scone_b200.GeometryHandle(text, device=-1)
+        with pytest.raises(RuntimeError, match=msg):
+            ol.Geom(orc, text)

@@ -174,3 +174,34 @@ def test_fixed_source_oracle_and_host_model(orc):
         pp = scone_b200.EigenPhysicsPackage(path, "pop 100;", device=-1)
         assert pp.is_fixed_source and pp.is_ce == (deck == "ce_sphere")
         pp.close()
+
+
+def test_ace_card_header_and_fission_flags(orc):
+    # NuclearData/DataDecks/Tests/aceCard_iTest.f90:26-57: Pa-231 (8 precursor groups, prompt + delayed + total nu-bar) and
+    # Pa-232 (no delayed data) of JEFF 3.1.1
+    ref = {"91231JEF311": (229.05, 2.5852e-08, "91231.03c", [8, 1, 1, 1, 1]),
+           "91232JEF311": (230.045, 2.5852e-08, "91232.03c", [0, 1, 1, 0, 1])}
+    for name, (aw, tz, zaid, flags) in ref.items():
+        out = np.zeros(2); fl = np.zeros(5, np.int32); z = C.create_string_buffer(16)
+        assert orc.orc_ace_card_info(os.path.join(ACE, name + ".acebin").encode(), ol.dp(out), ol.ip(fl), z) == 0, ol.err(orc)
+        assert out[0] == pytest.approx(aw, rel=1e-6) and out[1] == pytest.approx(tz, rel=1e-6)
+        assert z.value.decode().strip() == zaid
+        assert fl.tolist() == flags
+
+
+def test_elastic_scattering_of_te126_is_isotropic_in_cm(orc):
+    # NuclearData/Reactions/Tests/elasticScattering_iTest.f90:83-107 (LOCB == 0 card, Te-126): probOf = 1 / (4 pi) for every mu, i.e.
+    # mu is sampled as 2 r - 1 and E_out = E_in; :53-56 elastic scattering is in the CM frame with one neutron out
+    h = orc.orc_ce_nuclide_from_acebin(os.path.join(ACE, "52126JEF311.acebin").encode())
+    assert h, ol.err(orc)
+    assert orc.orc_ce_nuclide_elastic_isotropic(h) == 1
+    out = np.zeros(4)
+    state = 987654321
+    n = orc.orc_ce_nuclide_sample(h, 0, 0, 6.7, state, ol.dp(out))
+    assert n == 2                                                      # one number for mu, one for phi
+    r1 = orc.orc_rng_real(orc.orc_rng_next(state)); r2 = orc.orc_rng_real(orc.orc_rng_next(orc.orc_rng_next(state)))
+    assert out[0] == 2.0 * r1 - 1.0 and out[1] == r2 * (2.0 * np.pi) and out[2] == 6.7
+    orc.orc_ce_nuclide_free(h)
+    h = orc.orc_ce_nuclide_from_acebin(os.path.join(ACE, "92233JEF311.acebin").encode())      # a card with LOCB > 0: tabular mu
+    assert orc.orc_ce_nuclide_elastic_isotropic(h) == 0
+    orc.orc_ce_nuclide_free(h)

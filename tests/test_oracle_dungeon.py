@@ -71,3 +71,16 @@ def test_norm_size_up_with_copies(orc):
     seq = np.concatenate([np.arange(n), np.arange(n), dup])
     ref = seq[np.argsort(brood[seq], kind="stable")]
     np.testing.assert_array_equal(tag[:m], ref)
+
+
+def test_heap_queue_known_answers(orc):
+    # DataStructures/Tests/heapQueue_test.f90 testBelowMaximum :8-19, testAboveMaximum :21-33 (the bounded max-heap normSize_Repr
+    # uses to find the k-th smallest random number)
+    import ctypes as C
+    import numpy as np
+    from tests import oracle_lib as ol
+    n = C.c_int()
+    seq = np.array([2.0, 3.0, 1.0, 4.0, 5.0])
+    assert orc.orc_heap_queue(8, len(seq), ol.dp(seq), 0, C.byref(n)) == 5.0 and n.value == 5
+    seq = np.array([1000.0, 2.0, 3.0, 1.0, 1.4, 5.0])
+    assert orc.orc_heap_queue(3, len(seq), ol.dp(seq), 1, C.byref(n)) == 2.0 and n.value == 3

@@ -212,3 +212,68 @@ def test_pin_edge_cases(pin):
     assert e["localID"] == 1
     d, s = pin.distance(1, r, u)
     assert d == pytest.approx(0.0, abs=1e-3) and s == MOVING_OUT
+
+
+# --------------------------------------------------------------------------- cellUniverse_test
+CELL_ENV = """surfaces { surf1 { id 1; type sphere; origin (0.0 0.0 0.0); radius 2;} surf2 { id 2; type sphere; origin (4.0 0.0 0.0); radius 1;} }
+cells { cell1 {id 1; type simpleCell; surfaces (-1); filltype uni; universe 3;}
+        cell2 {id 2; type simpleCell; surfaces (1 2); filltype uni; universe 4;} }"""
+CELL_UNI = "id 1; type cellUniverse; origin (2.0 0.0 0.0); rotation (90.0 90.0 90.0); cells (1 2);"
+CELL2_ENV = """surfaces { surf1 { id 1; type sphere; origin (21.0 0.0 0.0); radius 4.5;} surf2 { id 2; type sphere; origin (0.0 0.0 0.0); radius 24.1;} }
+cells { cell1 {id 1; type simpleCell; surfaces (-1); filltype uni; universe 3;}
+        cell2 {id 2; type simpleCell; surfaces (1 -2); filltype uni; universe 4;}
+        cell3 {id 3; type simpleCell; surfaces (2); filltype uni; universe 5;} }"""
+CELL2_UNI = "id 2; type cellUniverse; origin (0.0 0.0 0.0); checkOverlap 1; cells (1 2 3);"
+VOID_MAT = 2147483647                   # universalVariables.f90: huge(shortInt)
+UNDEF_MAT, OVERLAP_MAT = VOID_MAT - 1, VOID_MAT - 2
+
+
+def test_cell_universe(orc):
+    # cellUniverse_test.f90:17-36 definitions (rotation maps x -> z, y -> -y, z -> x), :98-99 fill, test_enter :142-199,
+    # test_distance :204-246, test_cross :251-268, test_cellOffset :273-296
+    u = ol.Uni(orc, CELL_UNI, {}, 8, env=CELL_ENV)
+    assert u.fill() == [-3, -4, UNDEF_MAT, OVERLAP_MAT]
+    e = u.enter([0.0, 0.0, 3.0], [0, 0, 1])
+    np.testing.assert_allclose(e["r"], [1.0, 0.0, 0.0], atol=1e-7); np.testing.assert_allclose(e["dir"], [1, 0, 0], atol=1e-7)
+    assert (e["uniIdx"], e["localID"], e["cellIdx"]) == (8, 1, 1)
+    e = u.enter([2.0, 0.0, 1.0], [0, 1, 0])
+    np.testing.assert_allclose(e["r"], [-1.0, 0.0, 2.0], atol=1e-7); np.testing.assert_allclose(e["dir"], [0, -1, 0], atol=1e-7)
+    assert (e["uniIdx"], e["localID"], e["cellIdx"]) == (8, 2, 2)
+    e = u.enter([0.0, 0.0, 6.5], [1, 0, 0])                       # the undefined region
+    np.testing.assert_allclose(e["r"], [4.5, 0.0, 0.0], atol=1e-7); np.testing.assert_allclose(e["dir"], [0, 0, 1], atol=1e-7)
+    assert (e["uniIdx"], e["localID"], e["cellIdx"]) == (8, 3, 0)
+    d, s = u.distance(1, [-1.0, 0.0, 0.0], [1, 0, 0]); assert d == pytest.approx(3.0, rel=1e-7) and s == 1
+    d, s = u.distance(2, [7.0, 0.0, 0.0], [-1, 0, 0]); assert d == pytest.approx(2.0, rel=1e-7) and s == 2
+    d, s = u.distance(2, [7.0, 0.0, 0.0], [1, 0, 0]); assert d == INF and s == 0
+    assert u.cross(1, [0.0, 2.0, 0.0], [0, 1, 0], 1) == 2
+    np.testing.assert_array_equal(u.offset(1), [0, 0, 0]); np.testing.assert_array_equal(u.offset(2), [0, 0, 0])
+
+
+def test_cell_universe_overlap_check(orc):
+    # cellUniverse_test.f90:38-48 (checkOverlap 1), :99 fill, test_overlap :322-373
+    u = ol.Uni(orc, CELL2_UNI, {}, 9, env=CELL2_ENV)
+    assert u.fill() == [-3, -4, -5, UNDEF_MAT, OVERLAP_MAT]
+    e = u.enter([22.0, 0.0, 0.0], [1, 0, 0])
+    np.testing.assert_allclose(e["r"], [22.0, 0.0, 0.0], atol=1e-7)
+    assert (e["uniIdx"], e["localID"], e["cellIdx"]) == (9, 1, 1)
+    e = u.enter([0.0, 25.0, 0.0], [1, 0, 0]); assert (e["localID"], e["cellIdx"]) == (3, 3)
+    e = u.enter([24.2, 0.0, 0.0], [1, 0, 0]); assert (e["uniIdx"], e["localID"], e["cellIdx"]) == (9, 5, 0)      # inside cells 1 and 3
+
+
+# --------------------------------------------------------------------------- rootUniverse_test
+def test_root_universe(orc):
+    # rootUniverse_test.f90:16-21 (border = surface id 1, the second one defined), :52 fill, test_enter :83-110, test_distance :115-133,
+    # test_cross :138-152, test_cellOffset :157-176
+    env = "surfaces { surf1 { id 4; type sphere; origin (0.0 5.0 0.0); radius 0.5;} surf2 { id 1; type sphere; origin (0.0 0.0 0.0); radius 2;} }"
+    u = ol.Uni(orc, "id 1; type rootUniverse; border 1; fill u<17>;", {}, 8, env=env)
+    OUTSIDE_MAT = 0
+    assert u.fill() == [-17, OUTSIDE_MAT]
+    e = u.enter([1.0, -1.0, 1.0], [1, 0, 0])
+    np.testing.assert_allclose(e["r"], [1.0, -1.0, 1.0], atol=1e-7); np.testing.assert_allclose(e["dir"], [1, 0, 0], atol=1e-7)
+    assert (e["uniIdx"], e["cellIdx"], e["localID"]) == (8, 0, 1)
+    e = u.enter([2.0, -2.0, 1.0], [1, 0, 0])
+    assert (e["uniIdx"], e["cellIdx"], e["localID"]) == (8, 0, 2)
+    d, s = u.distance(1, [1.0, 0.0, 0.0], [1, 0, 0])
+    assert d == pytest.approx(1.0, rel=1e-7) and s == 2                  # index of surface id 1 on the shelf
+    assert u.cross(1, [2.0, 0.0, 0.0], [1, 0, 0], 2) == 2
+    np.testing.assert_array_equal(u.offset(1), [0, 0, 0]); np.testing.assert_array_equal(u.offset(2), [0, 0, 0])

@@ -63,3 +63,58 @@ def test_sampling_statistics(orc, tmp_path):
         cnt[g.value] += 1
     np.testing.assert_allclose(cnt[1:] / N, [0.8, 0.2, 0, 0], atol=4 * np.sqrt(0.25 / N))
     orc.orc_mg_free(db)
+
+
+def _one_material_deck(tmp_path, xs_text, pn):
+    (tmp_path / "mat").write_text(xs_text)
+    deck = tmp_path / "deck"
+    deck.write_text("nuclearData { handles { mg { type baseMgNeutronDatabase; PN %s; } } materials { m { temp 1; composition { } xsFile ./mat; } } }" % pn)
+    return str(deck)
+
+
+@pytest.mark.parametrize("pn", ["P0", "P1"])
+def test_multi_scatter_known_answers(orc, tmp_path, pn):
+    # reactionMG/Tests/multiScatterMG_test.f90:13-14,50-66 and multiScatterP1MG_test.f90:13-15,52-74:
+    # P0 = [1.3 0.7 0.3 4.0], scatteringMultiplicity = [1.1 1.05 1 1] (column-major (G_out, G_in)), P1 = [0.5 0.1 0 0]
+    xs = """numberOfGroups 2; capture (0.0 0.0);
+            P0 (1.3 0.7 0.3 4.0); scatteringMultiplicity (1.1 1.05 1.0 1.0); P1 (0.5 0.1 0.0 0.0);"""
+    db = orc.orc_mg_load(_one_material_deck(tmp_path, xs, pn).encode(), b"mg")
+    assert db, ol.err(orc)
+    x = np.zeros(8)
+    orc.orc_mg_macro(db, 1, 1, ol.dp(x)); assert x[2] == pytest.approx(2.0, abs=TOL)          # scatterXS(1)
+    orc.orc_mg_macro(db, 1, 2, ol.dp(x)); assert x[2] == pytest.approx(4.3, abs=TOL)          # scatterXS(2)
+    P0 = np.zeros(4); prod = np.zeros(4); P1 = np.zeros(4); chi = np.zeros(2); nu = np.zeros(2)
+    isP1 = orc.orc_mg_matrices(db, 1, ol.dp(P0), ol.dp(prod), ol.dp(P1), ol.dp(chi), ol.dp(nu))
+    P0 = P0.reshape(2, 2).T; prod = prod.reshape(2, 2).T; P1 = P1.reshape(2, 2).T          # [G_out - 1, G_in - 1]
+    # production(G_in, G_out): (1,1) = 1.1, (2,1) = 1, (1,2) = 1.05
+    assert prod[0, 0] == pytest.approx(1.1, abs=TOL) and prod[0, 1] == pytest.approx(1.0, abs=TOL) and prod[1, 0] == pytest.approx(1.05, abs=TOL)
+    # releasePrompt(1) = sum(P0 * prod) / scatterXS = 1.0825; release(2) = 1
+    assert (P0[:, 0] * prod[:, 0]).sum() / P0[:, 0].sum() == pytest.approx(1.0825, abs=TOL)
+    assert (P0[:, 1] * prod[:, 1]).sum() / P0[:, 1].sum() == pytest.approx(1.0, abs=TOL)
+    if pn == "P1":
+        assert isP1 == 1
+        # P1(G_out, G_in): (2,2) = 0, (1,2) = 0, (1,1) = 1.1538461538, (2,1) = 0.4285714287
+        assert P1[1, 1] == pytest.approx(0.0, abs=TOL) and P1[0, 1] == pytest.approx(0.0, abs=TOL)
+        assert P1[0, 0] == pytest.approx(1.1538461538, abs=TOL) and P1[1, 0] == pytest.approx(0.4285714287, abs=TOL)
+    orc.orc_mg_free(db)
+
+
+@pytest.mark.parametrize("kappa", [None, (200.0, 203.0, 201.0)])
+def test_fission_mg_known_answers(orc, tmp_path, kappa):
+    # reactionMG/Tests/fissionMG_test.f90:13-15,48-68: nu = [2.3 2.0 1.3], chi = [0.333333 0.333333 0.333334]; kappa defaults to 202.27 MeV
+    xs = """numberOfGroups 3; capture (0.0 0.0 0.0); fission (1.0 1.0 1.0); nu (2.3 2.0 1.3); chi (0.333333 0.333333 0.333334);
+            P0 (1 0 0 0 1 0 0 0 1); scatteringMultiplicity (1 1 1 1 1 1 1 1 1);"""
+    if kappa:
+        xs += " kappa (%s);" % " ".join(map(str, kappa))
+    db = orc.orc_mg_load(_one_material_deck(tmp_path, xs, "P0").encode(), b"mg")
+    assert db, ol.err(orc)
+    x = np.zeros(8)
+    for g, nu in ((2, 2.0), (3, 1.3)):                        # release(2), releasePrompt(3) through nuFission = nu * fission
+        orc.orc_mg_macro(db, 1, g, ol.dp(x))
+        assert x[5] == pytest.approx(nu, abs=TOL) and x[7] == 1.0
+    orc.orc_mg_macro(db, 1, 2, ol.dp(x))
+    assert x[6] == pytest.approx(203.0 if kappa else 202.27, abs=1e-5)       # getKappa
+    P0 = np.zeros(9); prod = np.zeros(9); P1 = np.zeros(9); chi = np.zeros(3); nu = np.zeros(3)
+    orc.orc_mg_matrices(db, 1, ol.dp(P0), ol.dp(prod), ol.dp(P1), ol.dp(chi), ol.dp(nu))
+    np.testing.assert_allclose(chi, [0.333333, 0.333333, 0.333334]); np.testing.assert_allclose(nu, [2.3, 2.0, 1.3])
+    orc.orc_mg_free(db)

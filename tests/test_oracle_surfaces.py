@@ -175,3 +175,69 @@ def test_general_plane(orc):
     assert s.distance([4.0, 0.0, 0.0], x) == INF and s.distance([4.0, 0.0, 0.0], -x) == pytest.approx(1.0, rel=1e-7)
     assert s.distance([-1.0, 0.0, 0.0], u2) == INF
     s.close()
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_square_cylinder(orc, axis):
+    # squareCylinder_test.f90:72-118 (origin: axis 2, p1 1, p2 2; halfwidths p1 2, p2 3), testBC :186-271, testHalfspace :277-328,
+    # testDistance :334-410, testEdgeCases :463-520
+    ax = axis
+    p1, p2 = [(1, 2), (0, 2), (0, 1)][axis]
+    origin = [2.0, 2.0, 2.0]; origin[p1] = 1.0; origin[p2] = 2.0
+    hw = [0.0, 0.0, 0.0]; hw[p1] = 2.0; hw[p2] = 3.0
+    s = Surf(orc, "type %sSquareCylinder; id 75; origin (%s); halfwidth (%s);" % ("xyz"[axis], " ".join(map(str, origin)), " ".join(map(str, hw))))
+
+    def v(a, b, c):                 # vector given as (axis, p1, p2) components
+        out = np.zeros(3); out[ax] = a; out[p1] = b; out[p2] = c
+        return out
+
+    bcs = [0] * 6
+    bcs[p1 * 2 + 1] = 1; bcs[p1 * 2] = 0; bcs[p2 * 2 + 1] = 2; bcs[p2 * 2] = 2          # BC(p*2) is the +ve face (1-based), BC(p*2-1) the -ve
+    r, u = s.bc(0, v(0, -1, 3), v(0, -1, 0), bcs)                                           # vacuum face
+    np.testing.assert_allclose(r, v(0, -1, 3), atol=1e-6); np.testing.assert_allclose(u, v(0, -1, 0), atol=1e-6)
+    r, u = s.bc(0, v(0, 3, 3), v(0, 1, 0), bcs)                                             # reflection
+    np.testing.assert_allclose(r, v(0, 3, 3), atol=1e-6); np.testing.assert_allclose(u, v(0, -1, 0), atol=1e-6)
+    r, u = s.bc(0, v(0, 2, 5), v(0, 0, 1), bcs)                                             # periodic
+    np.testing.assert_allclose(r, v(0, 2, -1), atol=1e-6); np.testing.assert_allclose(u, v(0, 0, 1), atol=1e-6)
+    r, u = s.bc(0, v(0, 3, -1), unit(v(0, 1, -1)), bcs)                                     # corner
+    np.testing.assert_allclose(r, v(0, 3, 5), atol=1e-6); np.testing.assert_allclose(u, unit(v(0, -1, -1)), atol=1e-6)
+    r, u = s.bc(1, v(0, 20, -13), unit(v(0, 1, -1)), bcs)                                   # transformBC
+    np.testing.assert_allclose(r, v(0, -14, 5), atol=1e-6); np.testing.assert_allclose(u, unit(v(0, -1, -1)), atol=1e-6)
+    r, u = s.bc(1, v(0, 3, -1), unit(v(0, 1, -1)), bcs)
+    np.testing.assert_allclose(r, v(0, 3, 5), atol=1e-6); np.testing.assert_allclose(u, unit(v(0, -1, -1)), atol=1e-6)
+
+    up2 = v(0, 0, 1)
+    assert not s.halfspace(v(0, 2, 0), up2) and not s.halfspace(v(0, -0.5, 2), up2)
+    assert s.halfspace(v(0, -1.5, 2), up2) and s.halfspace(v(0, 0.5, 5.2), up2)
+    r = v(0, -1, 3); u = v(0, -1, 0)
+    assert s.halfspace(r, u) and not s.halfspace(r, -u)
+    assert s.halfspace(r - 0.5 * SURF_TOL * u, u) and not s.halfspace(r - 1.0001 * SURF_TOL * u, u)
+    assert s.halfspace(r + 0.5 * SURF_TOL * u, up2) and not s.halfspace(r - 0.5 * SURF_TOL * u, up2)
+
+    r = v(0, -2, 0)
+    u = unit(v(1, 1, 0))
+    assert s.distance(r, u) == pytest.approx(SQRT2, rel=1e-7) and s.distance(r, -u) == INF
+    assert s.distance(r, unit(v(1, 1, 1))) == pytest.approx(SQRT3, rel=1e-7)
+    assert s.distance(r, unit(v(1, 1, -2))) == INF
+    assert s.distance(v(0, -1.3, 0.3), unit(v(0, 0.3, -1.3))) == INF                       # corner skim
+    assert s.distance(v(0, -1.3, 0.3), v(0, 0, 1)) == INF                                   # parallel
+    assert s.distance(v(0, -1, 0.5), v(0, 1, 0)) == pytest.approx(4.0, rel=1e-7)            # at the surface
+    assert s.distance(v(0, -1 - 0.5 * SURF_TOL, 0.5), v(0, 1, 0)) == pytest.approx(4.0 + 0.5 * SURF_TOL, rel=1e-7)
+    assert s.distance(v(0, -1 + 0.5 * SURF_TOL, 0.5), v(0, 1, 0)) == pytest.approx(4.0 - 0.5 * SURF_TOL, rel=1e-7)
+    assert s.distance(v(9, 1.15, 1), v(0, 0, 1)) == pytest.approx(4.0, rel=1e-7)
+    assert s.distance(v(9, 1.15, 1), v(0, 0, -1)) == pytest.approx(2.0, rel=1e-7)
+
+    eps = 5.0 * np.finfo(float).eps                        # a particle almost at a corner is outside or escapes with a short move
+    for r, u in ((v(0, -1 + eps, -1 + eps), unit(v(0, 2, -1))), (v(0, -1 + eps, -1 + eps), unit(v(0, -1, 2))),
+                 (v(0, -1 + eps, -1 + 2 * eps), unit(v(0, 2, -1))), (v(0, -1 + 2 * eps, -1 + eps), unit(v(0, -1, 2)))):
+        if not s.halfspace(r, u):
+            d = s.distance(r, u)
+            assert abs(d) < 1e-6 and s.halfspace(r + d * u, u)
+    s.close()
+
+
+def test_square_cylinder_regression_case(orc):
+    # squareCylinder_test.f90:529-546 test_problems: on the +y face moving inwards -> inside
+    s = Surf(orc, "type zSquareCylinder; id 7; origin (0.0 0.0 0.0); halfwidth (8.0 1.26 0.0);")
+    assert not s.halfspace([-7.63, 1.26, 0.0], [0.0, -1.0, 0.0])
+    s.close()

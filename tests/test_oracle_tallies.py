@@ -74,3 +74,148 @@ def test_keff_analog_clerk_known_answer(orc):
     k, s = C.c_double(), C.c_double()
     assert orc.orc_keff_analog_sequence(2, ol.dp(ws), ol.dp(we), ol.dp(kn), 0.8, C.byref(k), C.byref(s)) == 0, ol.err(orc)
     assert k.value == pytest.approx(1.14, abs=1e-9) and s.value == pytest.approx(0.06, abs=1e-9)
+
+
+# --------------------------------------------------------------------------- tally maps
+class Map:
+    def __init__(self, orc, text, mats=None):
+        self.orc = orc
+        ml = " ".join("%s %d" % kv for kv in (mats or {}).items())
+        self.h = orc.orc_map_new(text.encode(), ml.encode())
+        assert self.h, ol.err(orc)
+
+    def bins(self):
+        return self.orc.orc_map_bins(self.h)
+
+    def map(self, r=(0.0, 0.0, 0.0), E=1.0, mg=False, G=0, mat=0):
+        r = np.ascontiguousarray(r, np.float64)
+        return self.orc.orc_map_map(self.h, ol.dp(r), float(E), 1 if mg else 0, G, mat)
+
+
+def test_energy_map_known_answers(orc):
+    # Tallies/TallyMaps/Maps1D/Tests/energyMap_test.f90: testLinearGrid, testLogGrid, testUnstructGrid, testMGParticle, testBinNumber
+    lin = Map(orc, "type energyMap; grid lin; min 0.01; max 10.0; N 20;")
+    log = Map(orc, "type energyMap; grid log; min 1.0E-7; max 10.0; N 20;")
+    grid = [0.00000000001, 0.00000003, 0.000000058, 0.00000014, 0.00000028, 0.00000035, 0.000000625, 0.000000972, 0.00000102,
+            0.000001097, 0.00000115, 0.000001855, 0.000004, 0.000009877, 0.000015968, 0.000148728, 0.00553, 0.009118, 0.111, 0.5,
+            0.821, 1.353, 2.231, 3.679, 6.0655, 10.0]
+    uns = Map(orc, "type energyMap; grid unstruct; bins (%s);" % " ".join("%.9E" % x for x in grid))
+    assert [lin.map(E=e) for e in (7.5774, 9.3652, 3.9223, 6.5548, 1.7119, 20.0)] == [16, 19, 8, 14, 4, 0]
+    assert [log.map(E=e) for e in (0.0445008907555061, 1.79747463687278e-07, 1.64204055725811e-05, 2.34083673923110e-07,
+                                   5.98486350302033e-07, 20.0)] == [15, 1, 6, 1, 2, 0]
+    assert [uns.map(E=e) for e in (0.0761191517392624, 0.00217742635754091, 6.38548311340975e-08, 2.52734532533842,
+                                   2.59031729968032e-11, 20.0)] == [18, 16, 3, 23, 1, 0]
+    assert lin.map(mg=True, G=1) == 0 and log.map(mg=True, G=1) == 0 and uns.map(mg=True, G=1) == 0
+    assert (lin.bins(), log.bins(), uns.bins()) == (20, 20, 25)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_space_map_known_answers(orc, axis):
+    # spaceMap_test.f90: testStructuredGrid, testUnstructuredGrid, testBins
+    s = Map(orc, "type spaceMap; axis %s; grid lin; min -10.0; max 10.0; N 20;" % "xyz"[axis])
+    u = Map(orc, "type spaceMap; axis %s; grid unstruct; bins (-10.0 -8.0 -6.0 -4.0 -2.0 0.0 2.0 4.0 6.0 8.0 10.0);" % "xyz"[axis])
+
+    def at(x):
+        r = [0.0, 0.0, 0.0]; r[axis] = x
+        return r
+    assert [s.map(r=at(x)) for x in (0.5, -10.1)] == [11, 0]
+    assert [u.map(r=at(x)) for x in (0.5, -10.1)] == [6, 0]
+    assert (s.bins(), u.bins()) == (20, 10)
+
+
+def test_material_map_known_answers(orc):
+    # materialMap_test.f90: materials mat1..mat5, map over (mat2 mat3 mat5), with and without the undefined bin
+    mats = {"mat%d" % i: i for i in range(1, 6)}
+    a = Map(orc, "type materialMap; materials (mat2 mat3 mat5);", mats)
+    b = Map(orc, "type materialMap; materials (mat2 mat3 mat5); undefBin true;", mats)
+    assert [a.map(mat=i) for i in range(1, 6)] == [0, 1, 2, 0, 3]
+    assert [b.map(mat=i) for i in range(1, 6)] == [4, 1, 2, 4, 3]
+    assert (a.bins(), b.bins()) == (3, 4)
+
+
+def test_multi_map_known_answers(orc):
+    # Tallies/TallyMaps/Tests/multiMap_test.f90: testBinAndDimension, testMapping
+    m = Map(orc, """type multiMap; maps (map1 map2 map3);
+                    map1 {type spaceMap; axis x; grid unstruct; bins (0.0 1.0 2.0); }
+                    map2 {type spaceMap; axis y; grid unstruct; bins (0.0 2.0 4.0 6.0); }
+                    map3 {type spaceMap; axis z; grid unstruct; bins (0.0 3.0 6.0); }""")
+    assert m.bins() == 12
+    assert m.map(r=[0.1, 0.1, 0.1]) == 1 and m.map(r=[1.1, 5.1, 5.1]) == 12 and m.map(r=[1.1, 3.1, 2.1]) == 4
+    assert m.map(r=[-1.1, 5.1, 5.1]) == 0 and m.map(r=[1.1, 50.1, 5.1]) == 0 and m.map(r=[1.1, 5.1, -5.1]) == 0
+
+
+# --------------------------------------------------------------------------- collisionClerk / trackClerk
+MATS7 = {"m%d" % i: i for i in range(1, 8)}
+MAP7 = "map { type materialMap; materials (m1 m2 m3 m4 m5 m6 m7); }"          # stands in for testMap (bin = matIdx, maxIdx 7)
+
+
+def clerk_sequence(orc, text, kind, events, xs=0.3, tracking=0.3):
+    mat = np.array([e[0] for e in events], np.int32); w = np.array([e[1] for e in events], float); aux = np.array([e[2] for e in events], float)
+    out = np.zeros(64)
+    ml = " ".join("%s %d" % kv for kv in MATS7.items())
+    n = orc.orc_clerk_sequence(text.encode(), ml.encode(), xs, tracking, kind, len(events), ol.ip(mat), ol.dp(w), ol.dp(aux), ol.dp(out), 64)
+    assert n >= 0, ol.err(orc)
+    return out[:n]
+
+
+@pytest.mark.parametrize("virtual_handling", [False, True])
+def test_collision_clerk_known_answers(orc, virtual_handling):
+    # collisionClerk_test.f90 testScoring (:92-157, handleVirtual 0: the virtual collision of weight 1000.3 is ignored) and
+    # testScoringVirtual (:160-245, default handling: a virtual collision scores w / tracking XS): cases 1 and 3 (no filter);
+    # constant cross sections 0.3, weights 0.7 (material 1) and 1.3 (material 6)
+    s1, s2 = 0.7 / 0.3, 1.3 / 0.3
+    if virtual_handling:
+        head, ev = "type collisionClerk;", [(1, 0.7, 1), (6, 1.3, 0)]
+    else:
+        head, ev = "type collisionClerk; handleVirtual 0;", [(1, 0.7, 0), (6, 1.3, 0), (6, 1000.3, 1)]
+    flux = " response (flux); flux { type fluxResponse; }"
+    r = clerk_sequence(orc, head + flux, 0, ev)
+    assert len(r) == 1 and r[0] == pytest.approx(s1 + s2, abs=1e-9)                       # case 1: single bin
+    r = clerk_sequence(orc, head + flux + MAP7, 0, ev)
+    ref = np.zeros(7); ref[0] = s1; ref[5] = s2
+    np.testing.assert_allclose(r, ref, atol=1e-9)                                          # case 3: map, no filter
+    # cases 5 / 7 with the second response: the reference's testResponse (constant 1.3) is replaced by the total macroscopic
+    # cross section of the constant database (0.3); bins are response-fastest as in the reference (results(1), (2), (11), (12))
+    two = " response (flux tot); flux { type fluxResponse; } tot { type macroResponse; MT -1; }"
+    r = clerk_sequence(orc, head + two + MAP7, 0, ev)
+    ref = np.zeros(14); ref[0] = s1; ref[1] = s1 * 0.3; ref[10] = s2; ref[11] = s2 * 0.3
+    np.testing.assert_allclose(r, ref, atol=1e-9)
+
+
+def test_track_clerk_known_answers(orc):
+    # trackClerk_test.f90 testScoring: path length 0.3 at weights 0.7 (material 1) and 1.3 (material 6): score = w * L, cases 1 and 3
+    s1, s2 = 0.7 * 0.3, 1.3 * 0.3
+    ev = [(1, 0.7, 0.3), (6, 1.3, 0.3)]
+    flux = "type trackClerk; response (flux); flux { type fluxResponse; }"
+    r = clerk_sequence(orc, flux, 1, ev)
+    assert len(r) == 1 and r[0] == pytest.approx(s1 + s2, abs=1e-9)
+    r = clerk_sequence(orc, flux + MAP7, 1, ev)
+    ref = np.zeros(7); ref[0] = s1; ref[5] = s2
+    np.testing.assert_allclose(r, ref, atol=1e-9)
+
+
+# --------------------------------------------------------------------------- grid_class
+def grid(orc, kind, mini=0.0, maxi=0.0, N=0, bins=(), keys=()):
+    b = np.ascontiguousarray(bins, float) if len(bins) else np.zeros(1)
+    k = np.ascontiguousarray(keys, float) if len(keys) else np.zeros(1)
+    idx = np.zeros(max(1, len(keys)), np.int32); bounds = np.zeros(256)
+    n = orc.orc_grid(kind, mini, maxi, N, ol.dp(b), len(bins), len(keys), ol.dp(k), ol.ip(idx), ol.dp(bounds), 256)
+    assert n > 0, ol.err(orc)
+    return idx[:len(keys)].tolist(), bounds[:n]
+
+
+def test_grid_known_answers(orc):
+    # SharedModules/Tests/grid_test.f90: lin(-10.71, 10.71, 17), log(1e-11, 20, 70), the 9-point unstructured grid; valueOutsideArray = -1
+    FP = 50 * np.finfo(float).eps
+    OUT = -1
+    idx, b = grid(orc, 0, -10.71, 10.71, 17, keys=[-10.71, 3.13245, -8.96, -20.0, 10.72])
+    assert idx == [1, 11, 2, OUT, OUT] and len(b) == 18
+    for i, v in ((1, -10.71), (4, -6.93), (7, -3.15), (14, 5.67), (18, 10.71)):
+        assert b[i - 1] == pytest.approx(v, rel=FP)
+    idx, b = grid(orc, 1, 1.0e-11, 20.0, 70, keys=[1.0e-11, 6.7e-4, 1.0, 9.0e-12, 21.0])
+    assert idx == [1, 45, 63, OUT, OUT] and len(b) == 71
+    for i, v in ((1, 1.0e-11), (35, 9.435957972757912e-6), (70, 13.344459739056777), (71, 20.0)):
+        assert b[i - 1] == pytest.approx(v, rel=FP)
+    idx, b = grid(orc, 2, bins=[1.00e-11, 5.80e-08, 1.40e-07, 2.80e-07, 6.25e-07, 4.00e-06, 0.005530, 0.821000, 10.0],
+                  keys=[1.0e-11, 6.7e-4, 1.0, 9.0e-12, 21.0])
+    assert idx == [1, 6, 8, OUT, OUT] and len(b) == 9
