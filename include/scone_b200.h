@@ -136,12 +136,15 @@ typedef struct sb_map1d {
  * (keffAnalogClerk_class.f90:40-60,132-176), keffImplicitClerk = 5 bins { IMP_PROD, IMP_ABS, SCATTER_PROD, ANA_LEAK, K_EFF }
  * (keffImplicitClerk_class.f90:60-75,292-312): the first bins pass through closeCycle (normalised), the k bin is accumulated as is */
 enum { SB_CLERK_COLLISION = 0, SB_CLERK_KEFF_ANALOG = 1, SB_CLERK_KEFF_IMPLICIT = 2,
-       SB_CLERK_TRACK = 3 /* trackClerk (trackClerk_class.f90:185-232): maps on the pre-path state, score = response * w * path length; surface tracking only */ };
+       SB_CLERK_TRACK = 3 /* trackClerk (trackClerk_class.f90:185-232): maps on the pre-path state, score = response * w * path length; surface tracking only */,
+       SB_CLERK_SHANNON = 4 /* shannonEntropyClerk (shannonEntropyClerk_class.f90:117-190): maps only; N + 1 + cycles bins { weight, N bin weights, entropy of
+                               cycle 1..cycles }: the fission bank of every cycle end is binned by weight, -sum p log2 p is accumulated in the cycle's own bin */ };
 typedef struct sb_clerk {
   int32_t n_maps; sb_map1d maps[SB_MAX_MAPS];   /* multiMap order; 0 maps = single bin        */
   int32_t n_resp; int32_t resp_mt[SB_MAX_RESP]; /* 0 = fluxResponse, else SCONE macro MT (-1..) */
   int32_t handle_virtual;
   int32_t kind;                                 /* SB_CLERK_*; maps and responses are ignored for the k-eff clerks */
+  int32_t cycles;                               /* shannonEntropyClerk: number of cycles that are scored */
 } sb_clerk;
 
 enum { SB_TRACK_DT = 0, SB_TRACK_ST = 1, SB_TRACK_HT = 2 };

@@ -476,6 +476,25 @@ int orc_clerk_sequence(const char* clerkText, const char* matList, double xsAll,
   return (int)t.mem.N;
   ORC_CATCH(-1)
 }
+// shannonEntropyClerk_test.f90 testSimpleUseCase: cycles of end-of-cycle populations { matIdx, x, wgt }; out[c] = entropy of cycle c
+int orc_shannon_sequence(const char* clerkText, const char* matList, int nCycles, const int* counts, const int* matIdx, const double* x,
+                         const double* w, double* out) {
+  ORC_TRY
+  std::map<std::string, int> mats;
+  { std::istringstream is(matList ? matList : ""); std::string nm; int i; while (is >> nm >> i) mats[nm] = i; }
+  TallyAdmin t;
+  t.init(Dict::fromString(std::string("testClerk { ") + clerkText + " }"), mats);
+  int k = 0;
+  for (int c = 0; c < nCycles; ++c) {
+    Dungeon pop; pop.init(counts[c] + 1);
+    for (int i = 0; i < counts[c]; ++i, ++k) { ParticleState s; s.wgt = w[k]; s.matIdx = matIdx[k]; s.r[0] = x[k]; pop.detain(s); }
+    t.reportCycleEnd(pop);
+  }
+  const Clerk& cl = t.clerks.at(0);
+  for (int c = 0; c < std::min(nCycles, cl.maxCycles); ++c) { double m, sd; t.mem.getResult(m, sd, cl.addr + cl.map->bins() + 1 + c, 1); out[c] = m; }
+  return (int)t.mem.N;
+  ORC_CATCH(-1)
+}
 // keffAnalogClerk_test.f90 test1CycleBatch: cycles of { start population weight, end population weight, k_eff of the end dungeon }; closeCycle norm 0.8
 int orc_keff_analog_sequence(int n, const double* w_start, const double* w_end, const double* k_norm, double norm, double* k, double* std_) {
   ORC_TRY

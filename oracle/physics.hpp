@@ -263,6 +263,7 @@ struct ScoreMemory {
       bin[i] = s;
     }
   }
+  void resetBin(long idx) { if (idx > 0 && idx <= N) bin[idx - 1] = 0.0; }
   double getScore(long idx) const { if (idx <= 0 || idx > N) return 0.0; return bin[idx - 1]; }
   void closeCycle(double normFactor) {                              // :309-342
     cycles += 1;
@@ -479,7 +480,8 @@ struct Response {
 };
 
 struct Clerk {
-  enum Kind { COLLISION, KEFF_ANALOG, KEFF_IMPLICIT, TRACK } kind = COLLISION;
+  enum Kind { COLLISION, KEFF_ANALOG, KEFF_IMPLICIT, TRACK, SHANNON } kind = COLLISION;
+  int maxCycles = 0, currentCycle = 0;                                // shannonEntropyClerk
   std::string name;
   long addr = 1;
   // collisionClerk
@@ -487,6 +489,7 @@ struct Clerk {
   long size() const {
     if (kind == KEFF_ANALOG) return 3;
     if (kind == KEFF_IMPLICIT) return 5;
+    if (kind == SHANNON) return map->bins() + 1 + maxCycles;          // shannonEntropyClerk_class.f90:106-111
     long S = (long)response.size();
     if (map) S *= map->bins();
     return S;
@@ -518,6 +521,11 @@ struct TallyAdmin {
         for (auto& rn : cd.getWordArray("response")) { Response r; r.init(cd.getDict(rn)); c.response.push_back(r); }
       } else if (t == "keffAnalogClerk") c.kind = Clerk::KEFF_ANALOG;
       else if (t == "keffImplicitClerk") { c.kind = Clerk::KEFF_IMPLICIT; c.handleVirtual = cd.getBool("handleVirtual", true); }
+      else if (t == "shannonEntropyClerk") {                           // shannonEntropyClerk_class.f90:75-92
+        c.kind = Clerk::SHANNON;
+        c.map = newTallyMap(cd.getDict("map"), mats);
+        c.maxCycles = cd.getInt("cycles");
+      }
       else throw FatalError("new_tallyClerk", "Unsupported clerk in oracle: " + t);
       clerks.push_back(std::move(c));
     }
@@ -592,7 +600,28 @@ struct TallyAdmin {
   void reportCycleEnd(const Dungeon& end) {                         // tallyAdmin_class.f90:735-794
     if (atch) atch->reportCycleEnd(end);
     for (auto& c : clerks) if (c.kind == Clerk::KEFF_ANALOG) mem.score(end.popWeight(), c.addr + 1);
+    for (auto& c : clerks) if (c.kind == Clerk::SHANNON) {            // shannonEntropyClerk_class.f90:117-144 reportCycleEnd
+      c.currentCycle += 1;
+      if (c.currentCycle > c.maxCycles) continue;
+      mem.score(end.popWeight(), c.addr);
+      for (int i = 0; i < end.pop; ++i) {
+        int idx = c.map->map(end.prisoners[i]);
+        if (idx == 0) continue;
+        mem.score(end.prisoners[i].wgt, c.addr + idx);
+      }
+    }
     mem.reduceBins();
+    for (auto& c : clerks) if (c.kind == Clerk::SHANNON && c.currentCycle <= c.maxCycles) {   // closeCycle :149-190
+      const int N = c.map->bins();
+      double totWgt = mem.getScore(c.addr), val = 0.0;
+      const double one_log2 = 1.0 / mlog(2.0);
+      for (int i = 1; i <= N; ++i) {
+        double prob = mem.getScore(c.addr + i) / totWgt;
+        if (prob > 0.0 && prob < 1.0) val = val - prob * mlog(prob) * one_log2;
+      }
+      mem.accumulate(val, c.addr + N + c.currentCycle);
+      for (int i = 0; i <= N; ++i) mem.resetBin(c.addr + i);
+    }
     for (auto& c : clerks) {
       if (c.kind == Clerk::KEFF_ANALOG && mem.lastCycle()) {        // keffAnalogClerk_class.f90:156-176
         double k_norm = end.k_eff;

@@ -436,6 +436,55 @@ __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfir
 }
 
 // ------------------------------------------------------------------------------------------------
+// shannonEntropyClerk (Tallies/TallyClerks/shannonEntropyClerk_class.f90): reportCycleEnd bins the weights of the cycle's fission
+// bank (before normSize_Repr) over the clerk's map; closeCycle turns them into -sum p log2 p, accumulates it in the bin of the
+// current cycle and resets the weight bins.  Bank sites carry no material (particleState%matIdx stays -1): a materialMap sends
+// them to its default bin, as in the reference.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_shannon_score(const Model M, const char* blob, int phase, int clerkIdx, Bank sites, const CycleDev* cd, int cap, int isCE, double* bins) {
+  __shared__ double sTot[32];
+  const DClerk& c = ((const DClerk*)(blob + M.oClerk[phase]))[clerkIdx];
+  const int n = min(cd->nSites, cap);
+  double tot = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double r[3] = {sites.rx[i], sites.ry[i], sites.rz[i]};
+    const double w = sites.w[i];
+    tot += w;
+    const int bin = isCE ? sbc::clerkBinCE(c, blob, r, -1, sites.E[i]) : clerkBin(c, blob, r, -1);
+    if (bin > 0) atomicAdd(&bins[c.addr - 1 + bin], w);
+  }
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+  if ((threadIdx.x & 31) == 0) sTot[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sTot[k];
+    if (t != 0.0) atomicAdd(&bins[c.addr - 1], t);
+  }
+}
+__global__ void __launch_bounds__(256) k_shannon_close(int addr, int nBins, int cycle, double* bins, double* csum, double* csum2) {
+  __shared__ double sVal[8];
+  const double totWgt = bins[addr - 1];
+  const double one_log2 = 1.0 / sbm::log(2.0);
+  double val = 0.0;
+  for (int i = threadIdx.x; i < nBins; i += blockDim.x) {
+    const double prob = bins[addr + i] / totWgt;
+    if (prob > 0.0 && prob < 1.0) val = val - prob * sbm::log(prob) * one_log2;
+  }
+  for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+  if ((threadIdx.x & 31) == 0) sVal[threadIdx.x >> 5] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int k = 0; k < 8; ++k) v += sVal[k];
+    const int cc = addr - 1 + nBins + cycle;                  // 0-based position of getMemAddress() + N + currentCycle
+    csum[cc] = csum[cc] + v; csum2[cc] = csum2[cc] + v * v;   // scoreMemory%accumulate
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= nBins; i += blockDim.x) bins[addr - 1 + i] = 0.0;      // resetBin
+}
+
+// ------------------------------------------------------------------------------------------------
 // Ranks of one node exchanging through peer memory (NVLink / NVSwitch; CUDA IPC between the processes), no host in the loop.
 // What SCONE moves over MPI per cycle is tiny: 6 score sums + the bank size of every rank (scoreMemory%reduceBins,
 // particleDungeon_class.f90:464,516-518,593) and the sites that loadBalancing hands to the neighbours (:607-698).  Every rank owns
@@ -805,6 +854,8 @@ struct sb_engine {
   // peer-memory exchange between the ranks of a node (sb_peer_*)
   int peerRanks = 0, peerRank = 0, peerCap = 0; char* peerRegion = nullptr; PeerPtrs peerPtrs{}; void* peerOpened[PEER_MAX] = {};
   PeerPlan* dPlan = nullptr; PeerPlan* hPlan = nullptr; double* dKsumTot = nullptr; unsigned long long peerSeq = 0; double peerTimeoutS = 20.0;
+  struct ShannonRec { int clerk, addr, nBins, maxCycles, cycle; };
+  std::vector<ShannonRec> shannon[2];     // shannonEntropyClerk records of each phase; cycle = reportCycleEnd calls so far
   bool broodValid = false;       // the current bank came out of a cycle (its sites have parents); false for source / uploaded banks
   double* dFileSrc = nullptr; long long nFileSrc = 0; bool fileSrcMG = false;     // fileSource rows (printToFile records)
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
@@ -1121,7 +1172,7 @@ int sb_load_mg_data(sb_engine* h, const sb_mg_flat* d) {
 
 int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, int normClerk, double normVal) {
   if (phase < 0 || phase > 1) { h->err = "sb_define_tallies: phase must be 0 or 1"; return -1; }
-  h->clerks[phase].clear(); h->mapBounds[phase].clear(); h->mapMat[phase].clear();
+  h->clerks[phase].clear(); h->mapBounds[phase].clear(); h->mapMat[phase].clear(); h->shannon[phase].clear();
   h->mapBounds[phase].resize((size_t)std::max(1, n) * SB_MAX_MAPS); h->mapMat[phase].resize((size_t)std::max(1, n) * SB_MAX_MAPS);
   int memLoc = 1;
   h->normAddr[phase] = 0; h->normVal[phase] = normVal;
@@ -1138,10 +1189,12 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
       h->clerks[phase].push_back(d);
       continue;
     }
-    if (s.kind != SB_CLERK_COLLISION && s.kind != SB_CLERK_TRACK) { h->err = "sb_define_tallies: unknown clerk kind"; return -1; }
-    if (s.n_maps < 0 || s.n_maps > SB_MAX_MAPS || s.n_resp < 1 || s.n_resp > SB_MAX_RESP) { h->err = "sb_define_tallies: invalid clerk"; return -1; }
+    if (s.kind != SB_CLERK_COLLISION && s.kind != SB_CLERK_TRACK && s.kind != SB_CLERK_SHANNON) { h->err = "sb_define_tallies: unknown clerk kind"; return -1; }
+    const bool shannon = s.kind == SB_CLERK_SHANNON;
+    if (s.n_maps < 0 || s.n_maps > SB_MAX_MAPS || (!shannon && (s.n_resp < 1 || s.n_resp > SB_MAX_RESP))) { h->err = "sb_define_tallies: invalid clerk"; return -1; }
+    if (shannon && (s.n_maps < 1 || s.cycles < 0)) { h->err = "sb_define_tallies: shannonEntropyClerk needs a map and a number of cycles"; return -1; }
     DClerk d; memset(&d, 0, sizeof(d));
-    d.addr = memLoc; d.nMaps = s.n_maps; d.nResp = s.n_resp; d.handleVirtual = s.handle_virtual; d.kind = s.kind;
+    d.addr = memLoc; d.nMaps = s.n_maps; d.nResp = shannon ? 0 : s.n_resp; d.handleVirtual = s.handle_virtual; d.kind = s.kind; d.padk = shannon ? s.cycles : 0;
     int mul = 1;
     for (int m = 0; m < s.n_maps; ++m) {
       const sb_map1d& mp = s.maps[m];
@@ -1158,9 +1211,10 @@ int sb_define_tallies(sb_engine* h, int phase, const sb_clerk* clerks, int n, in
       }
       mul *= mp.n_bins;
     }
-    for (int i = 0; i < s.n_resp; ++i) d.respMT[i] = s.resp_mt[i];
+    for (int i = 0; i < d.nResp; ++i) d.respMT[i] = s.resp_mt[i];
     if (normClerk == c + 1) h->normAddr[phase] = memLoc;
-    memLoc += s.n_resp * mul;
+    if (shannon) { h->shannon[phase].push_back(sb_engine::ShannonRec{(int)h->clerks[phase].size(), memLoc, mul, s.cycles, 0}); memLoc += mul + 1 + s.cycles; }
+    else memLoc += s.n_resp * mul;
     h->clerks[phase].push_back(d);
   }
   h->nBins[phase] = memLoc - 1;
@@ -1462,6 +1516,14 @@ static int cycleCloseEnqueue(sb_engine* h, const double* dKsum) {
   cudaStream_t st = h->stream;
   k_close_cycle_head<<<1, 32, 0, st>>>(dKsum, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase],
                                        h->userKeff[phase], h->dCsum[phase], h->dCsum2[phase]);
+  for (auto& sr : h->shannon[phase]) {                       // reportCycleEnd + closeCycle of the entropy clerks, on the un-normalised bank
+    sr.cycle += 1;
+    if (sr.cycle > sr.maxCycles) continue;
+    Bank& sorted = h->bank[(h->cur + 2) % 3];
+    k_shannon_score<<<gridFor(h, h->cap / 4 + 1, 256), 256, 0, st>>>(h->M, h->dBlob, phase, sr.clerk, sorted, h->dCd, h->cap, h->ceMode ? 1 : 0, h->dBins[phase]);
+    k_shannon_close<<<1, 256, 0, st>>>(sr.addr, sr.nBins, sr.cycle, h->dBins[phase], h->dCsum[phase], h->dCsum2[phase]);
+    h->launches += 2;
+  }
   int nb = std::max(1, h->nBins[phase]);
   k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
   h->launches += 2;

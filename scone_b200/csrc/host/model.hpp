@@ -511,6 +511,20 @@ inline TallyDefs buildTallies(const Dict& d, const MatMap& mats, int nMat) {
       T.clerks.push_back(c); T.names.push_back(n);
       continue;
     }
+    if (t == "shannonEntropyClerk") {                               // shannonEntropyClerk_class.f90:75-92: one map, `cycles`
+      sb_clerk c{};
+      c.kind = SB_CLERK_SHANNON; c.handle_virtual = 1;
+      const Dict& md = cd.getDict("map");
+      if (md.getWord("type") == "multiMap") for (auto& mn : md.getWordArray("maps")) detail::addMap1D(T, c, md.getDict(mn), mats, nMat);
+      else detail::addMap1D(T, c, md, mats, nMat);
+      c.cycles = cd.getInt("cycles");
+      if (c.cycles < 0) throw FatalError("init (shannonEntropyClerk)", "-ve number of cycles");
+      long bins = 1; for (int i = 0; i < c.n_maps; ++i) bins *= c.maps[i].n_bins;
+      T.addr.push_back(memLoc); T.width.push_back(1);
+      memLoc += bins + 1 + c.cycles;
+      T.clerks.push_back(c); T.names.push_back(n);
+      continue;
+    }
     if (t != "collisionClerk" && t != "trackClerk") throw FatalError("new_tallyClerk", "tallyClerk type not supported by the device tallies: " + t);
     if (cd.isPresent("filter")) throw FatalError("init (" + t + ")", "tally filters are not supported by the device tallies");
     sb_clerk c{};

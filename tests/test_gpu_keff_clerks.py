@@ -110,3 +110,41 @@ def test_track_clerk_path_length_estimator(orc, deck, pop, lo, hi, tracking):
         pp.close(); orc.orc_eigen_free(e)
     finally:
         orc.orc_set_math_mode(0)
+
+
+ENTROPY = ("%s { entropy { type shannonEntropyClerk; cycles %d; map { type multiMap; maps (mx my); "
+           "mx { type spaceMap; axis x; grid lin; min %g; max %g; N 8; } my { type spaceMap; axis y; grid lin; min %g; max %g; N 6; } } } "
+           "fiss { type collisionClerk; response (fiss); fiss { type macroResponse; MT -6; } } }")
+
+
+@pytest.mark.parametrize("deck,pop,lo,hi", [(DECK["c5g7"], 8000, -32.13, 32.13), (DECK["ce_pin"], 3000, -0.63, 0.63)])
+def test_shannon_entropy_clerk_eigen(orc, deck, pop, lo, hi):
+    """shannonEntropyClerk (7 of the reference's input files): the weights of every cycle's fission bank, taken before normSize_Repr,
+    binned over a 2-D space map; entropy per cycle in its own bin; cycles beyond `cycles` are not scored (3 active cycles, 2 scored)."""
+    ov = "pop %d; inactive 3; active 3; seed 77; %s %s" % (pop, ENTROPY % ("inactiveTally", 3, lo, hi, lo, hi), ENTROPY % ("activeTally", 2, lo, hi, lo, hi))
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(deck.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(deck, ov, device=0)
+        orc.orc_eigen_init_source(e); pp.generateInitialState()
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(6):
+            pp.cycle(cyc >= 3)
+            k_o = orc.orc_eigen_cycle(e, 1 if cyc >= 3 else 0, k_o)
+        for phase, cycles in ((0, 3), (1, 2)):
+            n = orc.orc_eigen_tally_size(e, phase)
+            assert n == 48 + 1 + cycles + 1
+            cs, cs2, nb = pp.tally(bool(phase))
+            ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+            orc.orc_eigen_tally(e, phase, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+            assert len(cs) == n
+            np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-14)
+            np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-14)
+            ent = cs[49:49 + cycles]
+            assert (cs[:49] == 0).all()                              # the weight bins are reset every cycle
+            assert (ent > 0.5).all() and (ent < np.log2(48) + 1e-9).all()
+            assert cs[-1] > 0                                        # the collision clerk behind the entropy clerk keeps its address
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)

@@ -219,3 +219,20 @@ def test_grid_known_answers(orc):
     idx, b = grid(orc, 2, bins=[1.00e-11, 5.80e-08, 1.40e-07, 2.80e-07, 6.25e-07, 4.00e-06, 0.005530, 0.821000, 10.0],
                   keys=[1.0e-11, 6.7e-4, 1.0, 9.0e-12, 21.0])
     assert idx == [1, 6, 8, OUT, OUT] and len(b) == 9
+
+
+def test_shannon_entropy_clerk_known_answers(orc):
+    # shannonEntropyClerk_test.f90 testSimpleUseCase: 2 bins, 2 cycles; sites of equal weight in both bins -> 1 bit, both in one bin -> 0;
+    # memory = N + 1 + cycles bins (testMap is stood in by a materialMap over two materials)
+    text = "type shannonEntropyClerk; cycles 2; map { type materialMap; materials (m1 m2); }"
+    counts = np.array([2, 2], np.int32); mat = np.array([2, 1, 1, 1], np.int32); w = np.ones(4); x = np.zeros(4); out = np.zeros(2)
+    n = orc.orc_shannon_sequence(text.encode(), b"m1 1 m2 2", 2, ol.ip(counts), ol.ip(mat), ol.dp(x), ol.dp(w), ol.dp(out))
+    assert n == 2 + 1 + 2, ol.err(orc)
+    assert out[0] == pytest.approx(1.0, abs=1e-7) and out[1] == pytest.approx(0.0, abs=1e-7)
+    # unequal weights over a space map, and a third cycle beyond `cycles` that must not be scored
+    text = "type shannonEntropyClerk; cycles 2; map { type spaceMap; axis x; grid lin; min 0.0; max 4.0; N 4; }"
+    counts = np.array([3, 4, 2], np.int32); x = np.array([0.5, 1.5, 1.6, 0.1, 1.1, 2.1, 3.1, 0.5, 9.0]); w = np.array([1.0, 2.0, 1.0, 1, 1, 1, 1, 1, 1.0])
+    mat = np.zeros(9, np.int32); out = np.zeros(3)
+    assert orc.orc_shannon_sequence(text.encode(), b"", 3, ol.ip(counts), ol.ip(mat), ol.dp(x), ol.dp(w), ol.dp(out)) == 4 + 1 + 2
+    p = np.array([0.25, 0.75])
+    assert out[0] == pytest.approx(-(p * np.log2(p)).sum(), abs=1e-12) and out[1] == pytest.approx(2.0, abs=1e-12)
