@@ -45,7 +45,8 @@ typedef struct sb_engine sb_engine;
  *   par[6] = surface tolerance (surface_inter.f90 surf_tol)                                  */
 enum { SB_SURF_XPLANE = 1, SB_SURF_YPLANE = 2, SB_SURF_ZPLANE = 3, SB_SURF_PLANE = 4, SB_SURF_SPHERE = 5,
        SB_SURF_XCYL = 6, SB_SURF_YCYL = 7, SB_SURF_ZCYL = 8, SB_SURF_BOX = 9,
-       SB_SURF_XSQCYL = 10, SB_SURF_YSQCYL = 11, SB_SURF_ZSQCYL = 12 };
+       SB_SURF_XSQCYL = 10, SB_SURF_YSQCYL = 11, SB_SURF_ZSQCYL = 12,
+       SB_SURF_XTCYL = 13, SB_SURF_YTCYL = 14, SB_SURF_ZTCYL = 15 /* truncCylinder: par = origin[3], radius, radius^2, axial halfwidth, tolerance; BC { a_min, a_max } */ };
 #define SB_SURF_NPAR 8
 
 /* ---- universes: Geometry/Universes/ ------------------------------------------------------

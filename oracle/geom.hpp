@@ -302,6 +302,92 @@ struct BoxLike : Surface {
 };
 
 // Geometry/Surfaces/surfaceFactory_func.f90 + per-class init
+// CompositeSurfaces/truncCylinder_class.f90: finite cylinder along x, y or z; F(r) = max[ (rho^2 - R^2) / (2R), |r_ax - o_ax| - a ];
+// BCs on the two axial faces only { a_min, a_max }, the radial face is always vacuum
+struct TruncCylinder : Surface {
+  int axis = 2, p0 = 0, p1 = 1;
+  double o[3] = {0, 0, 0}, a = 0, r = 0;
+  int BC[2] = {VACUUM_BC, VACUUM_BC};
+  std::string myType() const override { return axis == 0 ? "xTruncCylinder" : axis == 1 ? "yTruncCylinder" : "zTruncCylinder"; }
+  double evaluate(const Vec3& p) const override {                   // :204-219
+    double d0 = p[p0] - o[p0], d1 = p[p1] - o[p1];
+    double c = ((d0 * d0 + d1 * d1) - r * r) / r * 0.5;
+    return std::max(c, std::fabs(p[axis] - o[axis]) - a);
+  }
+  double distance(const Vec3& p, const Vec3& u) const override {    // :231-309
+    const double FP_MISS_TOL = 1.0 + 10.0 * std::numeric_limits<double>::epsilon();
+    double d0 = p[p0] - o[p0], d1 = p[p1] - o[p1];
+    double c1 = (d0 * d0 + d1 * d1) - r * r;
+    double k = d0 * u[p0] + d1 * u[p1];
+    double aa = 1.0 - u[axis] * u[axis];
+    double delta = k * k - aa * c1;
+    double far, near;
+    if (delta <= 0.0 || aa == 0.0) { far = INF; near = std::copysign(INF, c1); }
+    else {
+      far = (-k + std::sqrt(delta)) / aa;
+      near = (-k - std::sqrt(delta)) / aa;
+      if (far < near) std::swap(far, near);
+    }
+    double rb = p[axis] - o[axis], tn, tf;
+    if (u[axis] != 0.0) { tn = (-a - rb) / u[axis]; tf = (a - rb) / u[axis]; }
+    else { tn = std::copysign(INF, -a - rb); tf = std::copysign(INF, a - rb); }
+    if (tf < tn) std::swap(tf, tn);
+    far = std::min(far, tf); near = std::max(near, tn);
+    double c = std::max(c1 / r * 0.5, std::fabs(rb) - a), d;
+    if (far <= near * FP_MISS_TOL) d = INF;
+    else if (std::fabs(c) < tol) d = (std::fabs(far) >= std::fabs(near)) ? far : near;
+    else d = (near <= 0.0) ? far : near;
+    if (d <= 0.0 || d > INF) d = INF;
+    return d;
+  }
+  bool going(const Vec3& p, const Vec3& u) const override {          // :320-359
+    double rp0 = p[p0] - o[p0], rp1 = p[p1] - o[p1];
+    double c1 = ((rp0 * rp0 + rp1 * rp1) - r * r) / r * 0.5;
+    double rv = p[axis] - o[axis];
+    double c2 = std::fabs(rv) - a, proj, c;
+    if (c1 >= 2.0 * r * c2) { proj = u[p0] * rp0 + u[p1] * rp1; c = c1; }
+    else { proj = u[axis] * rv; c = c2; }
+    bool hs = proj > 0.0;
+    if (proj == 0.0) hs = c >= 0.0;
+    return hs;
+  }
+  void boundingBox(double b[6]) const override {
+    b[axis] = o[axis] - a; b[axis + 3] = o[axis] + a;
+    b[p0] = o[p0] - r; b[p1] = o[p1] - r; b[p0 + 3] = o[p0] + r; b[p1 + 3] = o[p1] + r;
+  }
+  void setBC(const std::vector<int>& bc) override {                 // :432-460
+    if (bc.size() < 2) throw FatalError("setBC (truncCylinder)", "Wrong size of BC string. Must be at least 2");
+    for (int i = 0; i < 2; ++i) {
+      if (bc[i] != VACUUM_BC && bc[i] != REFLECTIVE_BC && bc[i] != PERIODIC_BC) throw FatalError("setBC (truncCylinder)", "Unrecognised BC");
+      BC[i] = bc[i];
+    }
+  }
+  void explicitBC(Vec3& p, Vec3& u) const override {                // :468-503
+    double r0 = p[axis] - o[axis];
+    if (std::fabs(r0) <= a - tol) return;
+    int bc = (r0 < 0.0) ? BC[0] : BC[1];
+    if (bc == REFLECTIVE_BC) u[axis] = -u[axis];
+    else if (bc == PERIODIC_BC) p[axis] = p[axis] - 2.0 * std::copysign(a, r0);
+  }
+  void transformBC(Vec3& p, Vec3& u) const override {               // :511-562
+    double a_bar = a - tol;
+    int Ri = (int)std::ceil(std::fabs(p[axis] - o[axis]) / a_bar) / 2;
+    for (int t = 1; t <= Ri; ++t) {
+      double r0 = p[axis] - o[axis];
+      int bc = (r0 < 0.0) ? BC[0] : BC[1];
+      if (bc == REFLECTIVE_BC) {
+        double a0 = std::copysign(a, r0) + o[axis];
+        double d = p[axis] - a0;
+        p[axis] = p[axis] - 2.0 * d;
+        u[axis] = -u[axis];
+      } else if (bc == PERIODIC_BC) {
+        double d = std::copysign(a, r0);
+        p[axis] = p[axis] - 2.0 * d;
+      }
+    }
+  }
+};
+
 inline std::unique_ptr<Surface> newSurface(const Dict& d) {
   std::string type = d.getWord("type");
   int id = d.getInt("id");
@@ -361,6 +447,20 @@ inline std::unique_ptr<Surface> newSurface(const Dict& d) {
       s->o[i] = o[s->ax[i]]; s->hw[i] = h[s->ax[i]];
       if (s->hw[i] < 0.0) throw FatalError("box init", "halfwidth cannot have -ve values.");
     }
+    return s;
+  }
+  if (type == "xTruncCylinder" || type == "yTruncCylinder" || type == "zTruncCylinder") {    // truncCylinder_class.f90:108-163
+    auto s = std::make_unique<TruncCylinder>();
+    s->id = id;
+    auto o = d.getRealArray("origin");
+    if (o.size() != 3) throw FatalError("init (truncCylinder)", "origin must have size 3");
+    for (int i = 0; i < 3; ++i) s->o[i] = o[i];
+    s->r = d.getReal("radius");
+    if (s->r <= 0.0) throw FatalError("init (truncCylinder)", "Radius must be +ve");
+    s->a = d.getReal("halfwidth");
+    if (s->a <= 0.0) throw FatalError("init (truncCylinder)", "Halfwidth must be +ve");
+    s->axis = type[0] - 'x';
+    s->p0 = (s->axis == 0) ? 1 : 0; s->p1 = (s->axis == 2) ? 1 : 2;
     return s;
   }
   throw FatalError("new_surface", "Unrecognised / unsupported type of a surface: " + type);

@@ -1146,6 +1146,7 @@ int sb_load_geometry(sb_engine* h, const sb_geom_flat* g) {
     int t = g->surf_type[g->border_idx - 1]; const double* p = g->surf_par + (size_t)(g->border_idx - 1) * SB_SURF_NPAR;
     double lo[3] = {-INF, -INF, -INF}, hi[3] = {INF, INF, INF};
     if (t == SB_SURF_BOX) for (int a = 0; a < 3; ++a) { lo[a] = p[a] - p[3 + a]; hi[a] = p[a] + p[3 + a]; }
+    else if (t >= SB_SURF_XTCYL) { int ax = t - SB_SURF_XTCYL; for (int a = 0; a < 3; ++a) { double hw = (a == ax) ? p[5] : p[3]; lo[a] = p[a] - hw; hi[a] = p[a] + hw; } }
     else if (t >= SB_SURF_XSQCYL) { int ax = t - SB_SURF_XSQCYL; for (int a = 0; a < 3; ++a) if (a != ax) { lo[a] = p[a] - p[3 + a]; hi[a] = p[a] + p[3 + a]; } }
     else if (t == SB_SURF_SPHERE) for (int a = 0; a < 3; ++a) { lo[a] = p[a] - p[3]; hi[a] = p[a] + p[3]; }
     else if (t >= SB_SURF_XCYL && t <= SB_SURF_ZCYL) { int ax = t - SB_SURF_XCYL; for (int a = 0; a < 3; ++a) if (a != ax) { lo[a] = p[a] - p[3]; hi[a] = p[a] + p[3]; } }

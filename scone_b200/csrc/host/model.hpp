@@ -156,6 +156,12 @@ inline FlatGeometry buildGeometry(const Dict& d, const MatMap& mats) {
         if (active && hw[a] < 0.0) throw FatalError("init (box)", "halfwidth cannot have -ve values.");
         p[a] = o[a]; p[3 + a] = hw[a];
       }
+    } else if (type == "xTruncCylinder" || type == "yTruncCylinder" || type == "zTruncCylinder") {      // truncCylinder_class.f90:108-163
+      t = SB_SURF_XTCYL + (type[0] - 'x');
+      auto o = vec3("origin"); double r = s.getReal("radius"), a = s.getReal("halfwidth");
+      if (r <= 0.0) throw FatalError("init (truncCylinder)", "Radius must be +ve");
+      if (a <= 0.0) throw FatalError("init (truncCylinder)", "Halfwidth must be +ve");
+      p[0] = o[0]; p[1] = o[1]; p[2] = o[2]; p[3] = r; p[4] = r * r; p[5] = a;
     } else throw FatalError("new_surface", "Unrecognised type of a surface: " + type);
     g.surfType.push_back(t); g.surfId.push_back(id);
     g.surfPar.insert(g.surfPar.end(), p, p + SB_SURF_NPAR);
@@ -292,7 +298,11 @@ inline FlatGeometry buildGeometry(const Dict& d, const MatMap& mats) {
   {
     auto BC = d.getIntArray("boundary");
     int bt = g.surfType[g.borderIdx - 1];
-    if (bt >= SB_SURF_BOX) {
+    if (bt >= SB_SURF_XTCYL) {                                       // truncCylinder%setBC: { a_min, a_max }, the radial face is vacuum
+      if (BC.size() < 2) throw FatalError("setBC", "Wrong size of BC string. Must be at least 2");
+      for (int i = 0; i < 2; ++i) { if (BC[i] < 0 || BC[i] > 2) throw FatalError("setBC", "Unrecognised BC"); g.bc[i] = BC[i]; }
+      for (int i = 2; i < 6; ++i) g.bc[i] = 0;
+    } else if (bt >= SB_SURF_BOX) {
       if (BC.size() < 6) throw FatalError("setBC", "Wrong size of BC string. Must be at least 6");
       for (int i = 0; i < 6; ++i) { if (BC[i] < 0 || BC[i] > 2) throw FatalError("setBC", "Unrecognised BC"); g.bc[i] = BC[i]; }
       for (int a = 0; a < 3; ++a) if ((g.bc[2 * a] == 2) != (g.bc[2 * a + 1] == 2)) throw FatalError("setBC", "Periodic BC need to be applied to oposite surfaces");

@@ -9,6 +9,7 @@ DECK = {
     "inf": os.path.join(ROOT, "decks", "urr", "inf"),
     "slab": os.path.join(ROOT, "decks", "urr", "slab"),
     "ce_pin": os.path.join(ROOT, "decks", "ce", "pincell"),
+    "can": os.path.join(ROOT, "decks", "mg", "can"),
 }
 
 

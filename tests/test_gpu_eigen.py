@@ -35,7 +35,9 @@ HT_HALF = " transportOperator { type transportOperatorHT; cutoff 0.5; cache 0; }
     ("inf", 4000, 3, 3, ""), ("slab", 4000, 3, 3, ""), ("c5g7", 20000, 3, 3, ""), ("c5g7_3d", 10000, 2, 2, ""),
     # surface tracking (transportOperatorST) and hybrid tracking (transportOperatorHT): coordList, distance cache, crossings, explicit BCs
     ("c5g7", 8000, 2, 2, ST), ("c5g7", 8000, 2, 2, HT), ("c5g7", 6000, 2, 1, ST_NOCACHE), ("c5g7", 6000, 2, 1, HT_HALF),
-    ("slab", 4000, 2, 2, ST), ("inf", 4000, 2, 2, ST), ("c5g7_3d", 5000, 2, 1, HT), ("c5g7_3d", 4000, 1, 1, ST)])
+    ("slab", 4000, 2, 2, ST), ("inf", 4000, 2, 2, ST), ("c5g7_3d", 5000, 2, 1, HT), ("c5g7_3d", 4000, 1, 1, ST),
+    # truncated cylinders as cell surfaces and as the boundary (reflective bottom, vacuum top): decks/mg/can
+    ("can", 6000, 2, 2, ""), ("can", 6000, 2, 2, ST_NOCACHE), ("can", 6000, 2, 2, " transportOperator { type transportOperatorDT; }"), ("can", 5000, 2, 1, HT_HALF)])
 def test_cycles_bit_exact_against_oracle(orc, deck, pop, ninact, nact, tracking):
     ov = "pop %d; inactive %d; active %d; seed 12345;%s" % (pop, ninact, nact, tracking)
     orc.orc_set_math_mode(1)

@@ -52,7 +52,7 @@ def test_deterministic_math_bit_exact(orc):
 
 @pytest.mark.parametrize("name,src,lo,hi", [
     ("test_lat", TEST_LAT, -1.5, 1.5), ("test_cyl", TEST_CYL, -5.5, 5.5),
-    ("c5g7", DECK["c5g7"], -33.0, 33.0), ("c5g7_3d", DECK["c5g7_3d"], -33.0, 70.0)])
+    ("c5g7", DECK["c5g7"], -33.0, 33.0), ("c5g7_3d", DECK["c5g7_3d"], -33.0, 70.0), ("can", DECK["can"], -7.5, 7.5)])
 def test_place_and_teleport_bit_exact(orc, name, src, lo, hi):
     import os
     text = open(src).read() if os.path.exists(src) else src

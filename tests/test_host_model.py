@@ -12,7 +12,7 @@ from tests.fixtures import TEST_CYL, TEST_LAT
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DECKS = [os.path.join(ROOT, "decks", "c5g7", "c5g7_2d"), os.path.join(ROOT, "decks", "c5g7", "c5g7_3d_rodded"),
-         os.path.join(ROOT, "decks", "urr", "inf"), os.path.join(ROOT, "decks", "urr", "slab")]
+         os.path.join(ROOT, "decks", "urr", "inf"), os.path.join(ROOT, "decks", "urr", "slab"), os.path.join(ROOT, "decks", "mg", "can")]
 
 
 @pytest.mark.parametrize("src", [TEST_LAT, TEST_CYL] + DECKS)

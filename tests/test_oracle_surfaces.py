@@ -241,3 +241,64 @@ def test_square_cylinder_regression_case(orc):
     s = Surf(orc, "type zSquareCylinder; id 7; origin (0.0 0.0 0.0); halfwidth (8.0 1.26 0.0);")
     assert not s.halfspace([-7.63, 1.26, 0.0], [0.0, -1.0, 0.0])
     s.close()
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_trunc_cylinder(orc, axis):
+    # truncCylinder_test.f90:66-78 (origin: axis 2, p1 1, p2 2; halfwidth 1.5; radius 2), testBC, testHalfspace, testDistance
+    ax = axis
+    p1, p2 = [(1, 2), (0, 2), (0, 1)][axis]
+    origin = [2.0, 2.0, 2.0]; origin[p1] = 1.0; origin[p2] = 2.0
+    s = Surf(orc, "type %sTruncCylinder; id 75; origin (%s); halfwidth 1.5; radius 2.0;" % ("xyz"[axis], " ".join(map(str, origin))))
+
+    def v(a, b, c):
+        out = np.zeros(3); out[ax] = a; out[p1] = b; out[p2] = c
+        return out
+
+    # BCs: { a_min, a_max }
+    r, u = s.bc(0, v(0.5, 0, 2.3), v(-1, 0, 0), [0, 1])                     # vacuum face
+    np.testing.assert_allclose(r, v(0.5, 0, 2.3), atol=1e-7); np.testing.assert_allclose(u, v(-1, 0, 0), atol=1e-7)
+    r, u = s.bc(0, v(3.5, 0, 2.3), v(1, 0, 0), [0, 1])                      # reflective face
+    np.testing.assert_allclose(r, v(3.5, 0, 2.3), atol=1e-7); np.testing.assert_allclose(u, v(-1, 0, 0), atol=1e-7)
+    r, u = s.bc(1, v(30.0, 0, 2.3), v(1, 0, 0), [0, 1])                     # transformBC
+    np.testing.assert_allclose(r, v(-23.0, 0, 2.3), atol=1e-7); np.testing.assert_allclose(u, v(-1, 0, 0), atol=1e-7)
+    r, u = s.bc(0, v(3.5, 0, 2.3), v(1, 0, 0), [2, 2])                      # periodic
+    np.testing.assert_allclose(r, v(0.5, 0, 2.3), atol=1e-7); np.testing.assert_allclose(u, v(1, 0, 0), atol=1e-7)
+    r, u = s.bc(1, v(12.0, 0, 2.3), v(1, 0, 0), [2, 2])
+    np.testing.assert_allclose(r, v(3.0, 0, 2.3), atol=1e-7); np.testing.assert_allclose(u, v(1, 0, 0), atol=1e-7)
+
+    u = v(0, 1, 0)
+    assert s.halfspace(v(5.0, 3.0, 4.0), u) and s.halfspace(v(1.3, 1.0, 5.0), u) and s.halfspace(v(1.3, -2.0, 3.3), u)
+    assert not s.halfspace(v(3.3, 1.1, 2.2), u) and not s.halfspace(v(2.1, -0.7, 2.1), u)
+    u = unit(v(1, 1, 0))
+    assert not s.halfspace(v(3.3, -1.0, 2.0), u) and s.halfspace(v(3.3, -1.0, 2.0), -u)               # on the cylinder face
+    assert not s.halfspace(v(3.3, -1.0 - 0.5 * SURF_TOL, 2.0), u)
+    assert s.halfspace(v(3.3, -1.0 - 1.001 * SURF_TOL, 2.0), u)
+    u = v(1, 0, 0)                                                                                     # parallel to the face
+    assert s.halfspace(v(3.3, -1.0 - 0.5 * SURF_TOL, 2.0), u) and not s.halfspace(v(3.3, -1.0 + 0.5 * SURF_TOL, 2.0), u)
+    u = unit(v(-1, 0, 1))
+    assert not s.halfspace(v(3.5, 1.3, 1.8), u) and s.halfspace(v(3.5, 1.3, 1.8), -u)                 # on the axial face
+    u = unit(v(-1, 1, 0))
+    assert not s.halfspace(v(3.5 + 0.5 * SURF_TOL, 1.3, 1.8), u) and s.halfspace(v(3.5 + 1.001 * SURF_TOL, 1.3, 1.8), u)
+    u = unit(v(0, -1, 1))
+    assert s.halfspace(v(3.5 + 0.5 * SURF_TOL, 1.3, 1.8), u) and not s.halfspace(v(3.5 - 0.5 * SURF_TOL, 1.3, 1.8), u)
+
+    r = v(5.0, 1.0, 2.0)                                                                               # outside, beyond the axial face
+    assert s.distance(r, v(-1, 0, 0)) == pytest.approx(1.5, rel=1e-7)
+    assert s.distance(r, unit(v(-1, -1, 0))) == pytest.approx(1.5 * SQRT2, rel=1e-7)
+    assert s.distance(r, unit(v(-1, -2, -2))) == INF and s.distance(r, unit(v(0, -2, -2))) == INF and s.distance(r, unit(v(1, -1, -1))) == INF
+    r = v(1.5, -2.0, 2.0)                                                                              # outside, beside the cylinder face
+    assert s.distance(r, v(0, 1, 0)) == pytest.approx(1.0, rel=1e-7)
+    assert s.distance(r, unit(v(1, 1, 0))) == pytest.approx(SQRT2, rel=1e-7)
+    uu = v(0, 1.5, np.sqrt(7.0) * 0.5); ref = np.sqrt((uu * uu).sum())
+    assert s.distance(r, uu / ref) == pytest.approx(ref, rel=1e-7)
+    assert s.distance(r, unit(v(1, 1, 2))) == INF and s.distance(r, v(1, 0, 0)) == INF and s.distance(r, unit(v(1, -1, 0))) == INF
+    eps = 0.5 * SURF_TOL                                                                               # in the surface tolerance
+    assert s.distance(v(3.5 + eps, 1.3, 1.8), v(-1, 0, 0)) == pytest.approx(3.0, rel=1e-7)
+    assert s.distance(v(3.5 - eps, 1.3, 1.8), v(1, 0, 0)) == INF
+    assert s.distance(v(3.3, -1.0 - eps, 2.0), v(0, 1, 0)) == pytest.approx(4.0, rel=1e-7)
+    assert s.distance(v(3.3, -1.0 + eps, 2.0), v(0, -1, 0)) == INF
+    r = v(3.0, 0.0, 2.0); u = unit(v(-1, -1, 0))                                                       # inside
+    assert s.distance(r, u) == pytest.approx(SQRT2, rel=1e-7) and s.distance(r, -u) == pytest.approx(0.5 * SQRT2, rel=1e-7)
+    assert s.distance(r, v(0, -1, 0)) == pytest.approx(1.0, rel=1e-7) and s.distance(r, v(-1, 0, 0)) == pytest.approx(2.5, rel=1e-7)
+    s.close()
