@@ -8,7 +8,8 @@ import scone_b200  # noqa: E402
 
 pop = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 extra = sys.argv[2] if len(sys.argv) > 2 else ""
-pp = scone_b200.EigenPhysicsPackage(os.path.join(ROOT, "decks/ce/pincell"), "pop %d; inactive 2; active 3; seed 1; %s" % (pop, extra), device=0)
+deck = sys.argv[3] if len(sys.argv) > 3 else "decks/ce/pincell"
+pp = scone_b200.EigenPhysicsPackage(os.path.join(ROOT, deck), "pop %d; inactive 2; active 3; seed 1; %s" % (pop, extra), device=0)
 pp.generateInitialState()
 pp.cycles(False, 2)
 res = pp.cycles(True, 3)
