@@ -566,6 +566,7 @@ inline TallyDefs buildTallies(const Dict& d, const MatMap& mats, int nMat) {
     T.clerks.push_back(c); T.names.push_back(n);
   }
   T.size = memLoc - 1;
+  if (d.getInt("batchSize", 1) != 1) throw FatalError("init (tallyAdmin)", "batchSize other than 1 is not supported by the device tallies");
   // fix up pointers into the stores (stable because of reserve)
   size_t ib = 0, im = 0;
   for (auto& c : T.clerks) for (int i = 0; i < c.n_maps; ++i) {

@@ -74,6 +74,10 @@ struct eigenPhysicsPackage {
       rankOffset = totalPop / nRanks * rank + std::max(0, totalPop % nRanks + rank - nRanks);
       if (isFixed) { N_cycles = dict.getInt("cycles"); bufferSize = dict.getInt("buffer", 50); N_inactive = 0; N_active = N_cycles; }
       else { N_inactive = dict.getInt("inactive"); N_active = dict.getInt("active"); }
+      // options of the reference packages that change the physics and are not on the device: refuse them rather than ignore them
+      if (!dict.getBool("reproducible", true)) return fail("reproducible 0 (normSize without the reproducible resampling) is not supported: the device bank is always resampled by normSize_Repr");
+      for (const char* key : {"temperature", "density", "uniformFissionSites"})
+        if (dict.isPresent(key)) return fail(std::string("superimposed field `") + key + "` is not supported by the device engine");
       outputFile = dict.getWord("outputFile", "./output");
       printSource = dict.getInt("printSource", 0);
       if (printSource < 0 || printSource > 2) return fail("printSource must be 0 (No printing), 1 (ASCII) or 2 (BINARY)");

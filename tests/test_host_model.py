@@ -113,3 +113,17 @@ def test_geometry_structure_errors(orc):
             scone_b200.GeometryHandle(text, device=-1)
         with pytest.raises(RuntimeError, match=msg):
             ol.Geom(orc, text)
+
+
+@pytest.mark.parametrize("ov,msg", [
+    ("reproducible 0;", "reproducible 0"),
+    ("uniformFissionSites { type uniFissSitesField; }", "uniformFissionSites"),
+    ("temperature { type cartesianField; }", "temperature"),
+    ("activeTally { batchSize 5; fiss { type collisionClerk; response (f); f { type fluxResponse; } } }", "batchSize"),
+    ("activeTally { c { type collisionClerk; response (f); f { type fluxResponse; } filter { type energyFilter; Emin 0.0; Emax 1.0; } } }", "filters"),
+    ("activeTally { c { type mgXsClerk; } }", "not supported"),
+    ("printSource 5;", "printSource must be")])
+def test_unsupported_options_are_refused_not_ignored(ov, msg):
+    """Options of the reference that would change the results and have no device implementation stop the run with a message."""
+    with pytest.raises(scone_b200.EngineError, match=msg):
+        scone_b200.EigenPhysicsPackage(DECKS[0], "seed 1; " + ov, device=-1)
