@@ -893,6 +893,8 @@ struct EigenPP {
     }
     if (!srcErr.empty()) throw FatalError("generate (source)", srcErr);
     pRNG.stride(pop);
+    cycleInPhase[1] += 1;                                            // fixedSourcePhysicsPackage_class.f90:191-194
+    if (printSource != 0) dungeonA.printToFile(outputFile + "_source" + std::to_string(cycleInPhase[1]), printSource == 2);
     tally.reportCycleStart(*thisCycle);
     long seg = 0, coll = 0;
 #pragma omp parallel reduction(+ : seg, coll)

@@ -81,7 +81,8 @@ struct eigenPhysicsPackage {
       outputFile = dict.getWord("outputFile", "./output");
       printSource = dict.getInt("printSource", 0);
       if (printSource < 0 || printSource > 2) return fail("printSource must be 0 (No printing), 1 (ASCII) or 2 (BINARY)");
-      if (printSource != 0 && isFixed) return fail("printSource is a keyword of the eigenvalue package");
+      if (isFixed) for (const char* key : {"commonBufferSize", "varianceReduction"})
+        if (dict.isPresent(key)) return fail(std::string("`") + key + "` of fixedSourcePhysicsPackage is not supported by the device engine");
       std::string nucData = dict.getWord("XSdata"), energy = dict.getWord("dataType");
       if (energy != "mg" && energy != "ce") return fail("dataType must be 'mg' or 'ce'");
       isCE = (energy == "ce");
@@ -159,7 +160,7 @@ struct eigenPhysicsPackage {
   // particleDungeon%printToFile (particleDungeon_class.f90:1077-1112) for the bank the cycle has just normalised: r, dir, E, real(G),
   // real(broodID), wgt per site; stream binary (.bin) or one text row per site (.txt, 17 significant digits: reads back exactly)
   // deferred = the caller still has to balance the banks of the ranks (loadBalancing is part of normSize_Repr): it prints afterwards
-  int printBank(int active, bool deferred = false) {
+  int printBank(int active, bool deferred = false, bool fixedBatch = false) {
     if (!deferred || nRanks == 1) cycleInPhase[active ? 1 : 0] += 1;      // the `i` of the cycles loop restarts with each phase
     if (printSource == 0 || (deferred && nRanks > 1)) return 0;
     if (downloadBank()) return -1;
@@ -167,7 +168,9 @@ struct eigenPhysicsPackage {
     if (sb_bank_brood(eng, (int)hBrood.size(), hBrood.data())) return engFail();
     const bool bin = (printSource == 2);
     const int i = cycleInPhase[active ? 1 : 0];
-    const std::string name = outputFile + "_source" + std::to_string(i) + "_rank" + std::to_string(rank) + (bin ? ".bin" : ".txt");
+    // eigenvalue: <outputFile>_source<i>_rank<r> (eigenPhysicsPackage_class.f90:279); fixed source: <outputFile>_source<i>, the batch the
+    // source has just generated (fixedSourcePhysicsPackage_class.f90:191-194)
+    const std::string name = outputFile + "_source" + std::to_string(i) + (fixedBatch ? std::string() : "_rank" + std::to_string(rank)) + (bin ? ".bin" : ".txt");
     FILE* f = fopen(name.c_str(), bin ? "wb" : "w");
     if (!f) return fail("printToFile: cannot open " + name);
     std::vector<double> rows(10 * (size_t)hN);
@@ -219,6 +222,7 @@ struct eigenPhysicsPackage {
     if (nRanks > 1) return fail("fixed-source batches of several ranks: run one package per rank with its own share of pop");
     if (isFileSrc ? sb_source_file(eng, pop, pRNG, 0) : sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
     stride(totalPop);
+    if (printBank(1, false, true)) return -1;
     if (sb_run_cycle(eng, pRNG, 0, 1.0, 1, &last)) return engFail();
     stride(totalPop);
     nSegActive += last.n_segments; nHist += last.n_start;

@@ -193,3 +193,28 @@ def test_eigen_dump_feeds_a_file_source(orc, tmp_path):
         fp.close(); orc.orc_eigen_free(e)
     finally:
         orc.orc_set_math_mode(0)
+
+
+@pytest.mark.parametrize("deck,ce", [(MG, False), (CE, True)])
+def test_fixed_source_batches_are_dumped_byte_identical(orc, tmp_path, deck, ce):
+    """fixedSourcePhysicsPackage prints the batch its source has just generated: <outputFile>_source<i> (no rank suffix,
+    fixedSourcePhysicsPackage_class.f90:191-194); broodID of source particles is 0."""
+    orc.orc_set_math_mode(1)
+    try:
+        go, oo = str(tmp_path / "gpu"), str(tmp_path / "orc")
+        ov = "pop 1500; cycles 2; seed 3; printSource 2; "
+        e = orc.orc_eigen_load(deck.encode(), (ov + "outputFile %s;" % oo).encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.FixedSourcePhysicsPackage(deck, ov + "outputFile %s;" % go, device=0)
+        for _ in range(2):
+            assert orc.orc_fixed_cycle(e) == 0, ol.err(orc)
+            pp.fixed_cycle()
+        for i in (1, 2):
+            g = open("%s_source%d.bin" % (go, i), "rb").read(); o = open("%s_source%d.bin" % (oo, i), "rb").read()
+            assert len(g) == 1500 * 80 and g == o
+        rows = np.frombuffer(g, dtype=np.float64).reshape(1500, 10)
+        assert (rows[:, 8] == 0).all() and (rows[:, 9] == 1.0).all()
+        assert ((rows[:, 6] > 0).all() and (rows[:, 7] == 0).all()) if ce else ((rows[:, 6] == 0).all() and (rows[:, 7] >= 1).all())
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
