@@ -168,7 +168,7 @@ typedef struct sb_cycle_result {
   int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
-       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10, SB_ERR_PEER_TIMEOUT = 11, SB_ERR_BALANCE = 12,
+       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10, SB_ERR_PEER_TIMEOUT = 11, SB_ERR_BALANCE = 12, SB_ERR_MAT_SOURCE = 13,
        SB_ERR_CE_ENERGY = 8 /* energy outside the bounds of the CE data */, SB_ERR_CE_DATA = 9 /* failed search / rejection loop in the reaction data */ };
 
 /* ---- life cycle -------------------------------------------------------------------------- */
@@ -223,6 +223,11 @@ int sb_source_point(sb_engine* h, int n, uint64_t rng_state, int history_offset,
  * (r, dir, E, G, broodID, wgt; particleDungeon_class.f90:1077-1112), kept on the device by sb_set_file_source.
  * sb_source_file = fileSource%sampleParticle for n particles (:151-196): row int(rand * n_rows) + 1, position checked
  * against OUTSIDE / undefined regions, weight and E (or G) from the row.                                                      */
+/* materialSource (ParticleObjects/Source/materialSource_class.f90:136-210): uniform points of the box [bottom, top] by rejection on the
+ * material at the point (at most 200 attempts of 4 random numbers each), isotropic direction, weight 1, E or G as given.                */
+typedef struct sb_material_source { int32_t mat_idx, is_mg, G, pad; double E, bottom[3], top[3]; } sb_material_source;
+int sb_source_material(sb_engine* h, int n, uint64_t rng_state, int history_offset, const sb_material_source* s);
+int sb_geometry_bounds(sb_engine* h, double* bounds6);      /* geometry%bounds(): AABB of the boundary surface, { min[3], max[3] } */
 int sb_set_file_source(sb_engine* h, int64_t n_rows, const double* rows, int is_mg);
 int sb_source_file(sb_engine* h, int n, uint64_t rng_state, int history_offset);
 

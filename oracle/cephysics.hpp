@@ -256,6 +256,7 @@ struct CeEigenPP : EigenPP {
     if (fixedSource) {
       activeTally.init(dict.getDict("tally"), mats);
       inactiveTally.init(Dict::fromString(""), mats);
+      sourceMats = mats;
       initSource(dict.getDict("source"), 0);
       return;
     }

@@ -725,6 +725,8 @@ struct EigenPP {
   struct PointSource { Vec3 r, dir; bool isotropic = true, isMG = true; double E = 0.0; int G = 1; std::vector<double> probG; } psrc;
   // fileSource (ParticleObjects/Source/fileSource_class.f90): rows of a printToFile dump
   struct FileSource { bool on = false, isMG = false; long N = 0; std::vector<double> rows; } fsrc;
+  // materialSource (ParticleObjects/Source/materialSource_class.f90)
+  struct MaterialSource { bool on = false, isMG = false; int matIdx = 0, G = 1; double E = 1.0E-6; Vec3 bottom, top; } msrc;
   // printSource / outputFile (eigenPhysicsPackage_class.f90:278-281,463,501-504)
   int printSource = 0; std::string outputFile = "./output"; int cycleInPhase[2] = {0, 0};
   // statistics the reference does not keep (for the segments/s metric)
@@ -778,9 +780,53 @@ struct EigenPP {
     if (fsrc.isMG) { p.G = (int)row[7]; p.isMG = true; } else { p.E = row[6]; p.isMG = false; }
     return p;
   }
-  ParticleState sampleSource(RNG& rand) const { return fsrc.on ? sampleFile(rand) : samplePoint(rand); }
+  // materialSource%init (:75-134) and %sampleParticle (:136-210)
+  void initMaterialSource(const Dict& d, bool dataIsMG, const std::map<std::string, int>& mats) {
+    std::string energy = d.getWord("data", "ce");
+    if (energy != "ce" && energy != "mg") throw FatalError("init (materialSource)", "Invalid source data type specified: must be ce or mg");
+    msrc.isMG = (energy == "mg");
+    if (msrc.isMG != dataIsMG) throw FatalError("init (materialSource)", "source data type does not match the nuclear database");
+    msrc.E = d.getReal("E", 1.0E-6); msrc.G = d.getInt("G", 1);
+    auto it = mats.find(d.getWord("mat"));
+    if (it == mats.end()) throw FatalError("init (materialSource)", "Source material " + d.getWord("mat") + " was not found in the material definitions");
+    msrc.matIdx = it->second;
+    if (d.isPresent("boundingBox")) {
+      auto b = d.getRealArray("boundingBox");
+      if (b.size() != 6) throw FatalError("init (materialSource)", "Bounding box must have 6 entries");
+      for (int k = 0; k < 3; ++k) { msrc.bottom[k] = b[k]; msrc.top[k] = b[3 + k]; }
+    } else {
+      double b[6]; geom.bounds(b);
+      for (int k = 0; k < 3; ++k) { msrc.bottom[k] = b[k]; msrc.top[k] = b[3 + k]; }
+    }
+    msrc.on = true;
+  }
+  ParticleState sampleMaterial(RNG& rand) const {
+    for (int i = 1; i <= 200; ++i) {
+      double r3[3] = {0, 0, 0};
+      r3[0] = rand.get(); r3[1] = rand.get(); r3[2] = rand.get();
+      Vec3 r;
+      for (int k = 0; k < 3; ++k) r[k] = (msrc.top[k] - msrc.bottom[k]) * r3[k] + msrc.bottom[k];
+      (void)rand.get();                                              // time
+      int m, uid; geom.whatIsAt(m, uid, r);
+      if (m == OUTSIDE_MAT) continue;
+      if (m == VOID_MAT || m == UNDEF_MAT || m == OVERLAP_MAT) throw FatalError("sampleParticle (materialSource)", "Nuclear data did not return neutron material.");
+      if (m != msrc.matIdx) continue;
+      ParticleState p;
+      p.r = r; p.wgt = 1.0; p.time = 0.0;
+      double mu = 2.0 * rand.get() - 1.0;
+      double phi = TWO_PI * rand.get();
+      Vec3 ex; ex[0] = 1.0;
+      p.dir = rotateVector(ex, mu, phi);
+      if (msrc.isMG) { p.G = msrc.G; p.isMG = true; } else { p.E = msrc.E; p.isMG = false; }
+      return p;
+    }
+    throw FatalError("sampleParticle (materialSource)", "Infinite loop in sampling source. Please check that defined volume contains source material.");
+  }
+  ParticleState sampleSource(RNG& rand) const { return fsrc.on ? sampleFile(rand) : msrc.on ? sampleMaterial(rand) : samplePoint(rand); }
+  std::map<std::string, int> sourceMats;                             // material names, set by init() before initSource
   void initSource(const Dict& d, int nG) {
     if (d.getWord("type") == "fileSource") initFileSource(d, nG > 0);
+    else if (d.getWord("type") == "materialSource") initMaterialSource(d, nG > 0, sourceMats);
     else initPointSource(d, nG);
   }
   // pointSource%init (ParticleObjects/Source/pointSource_class.f90:60-140)
@@ -861,6 +907,7 @@ struct EigenPP {
     if (fixedSource) {
       activeTally.init(dict.getDict("tally"), mats);
       inactiveTally.init(Dict::fromString(""), mats);
+      sourceMats = mats;
       initSource(dict.getDict("source"), db.nG);
       return;
     }

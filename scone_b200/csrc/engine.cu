@@ -732,6 +732,34 @@ __global__ void k_source_point(Bank out, int n, uint64_t rng0, int offset, doubl
   }
 }
 
+// materialSource%sampleParticle (ParticleObjects/Source/materialSource_class.f90:136-210)
+__global__ void k_source_material(const Model M, const char* blob, Bank out, int n, uint64_t rng0, int offset, sb_material_source S, CycleDev* cd) {
+  const Tables T = bind(M, blob);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint64_t rng = rng_skip(rng0, RNG_STRIDE * (int64_t)(offset + i + 1));
+    bool ok = false;
+    for (int att = 1; att <= 200 && !ok; ++att) {
+      double r3[3]; r3[0] = rng_get(rng); r3[1] = rng_get(rng); r3[2] = rng_get(rng);
+      double r[3], u[3] = {1.0, 0.0, 0.0};
+      for (int k = 0; k < 3; ++k) r[k] = (S.top[k] - S.bottom[k]) * r3[k] + S.bottom[k];
+      (void)rng_get(rng);                                       // time = tLow + rand * (tHigh - tLow): drawn in every attempt
+      int mat, uid;
+      geomPlace(M, T, r, u, mat, uid);
+      if (mat == SB_OUTSIDE_MAT) continue;
+      if (mat >= SB_OVERLAP_MAT) { atomicMax(&cd->error, mat == SB_VOID_MAT ? SB_ERR_MAT_SOURCE : (mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT)); break; }
+      if (mat != S.mat_idx) continue;
+      double mu = 2.0 * rng_get(rng) - 1.0;
+      double phi = TWO_PI * rng_get(rng);
+      double d[3] = {1.0, 0.0, 0.0};
+      rotateVector(d, mu, phi);
+      out.rx[i] = r[0]; out.ry[i] = r[1]; out.rz[i] = r[2];
+      out.ux[i] = d[0]; out.uy[i] = d[1]; out.uz[i] = d[2];
+      out.w[i] = 1.0; out.G[i] = S.is_mg ? S.G : 0; out.E[i] = S.is_mg ? 0.0 : S.E; out.brood[i] = 0; out.seq[i] = 0;
+      ok = true;
+    }
+    if (!ok) atomicMax(&cd->error, SB_ERR_MAT_SOURCE);
+  }
+}
 // fileSource%sampleParticle (ParticleObjects/Source/fileSource_class.f90:151-196)
 __global__ void k_source_file(const Model M, const char* blob, Bank out, int n, uint64_t rng0, int offset, const double* rows, long long nRows, int isMG,
                               CycleDev* cd) {
@@ -1295,6 +1323,7 @@ static int checkDeviceError(sb_engine* h, int code) {
     case SB_ERR_OVERLAP_MAT: msg = "Particle is in overlapping cells"; break;
     case SB_ERR_SAMPLING: msg = "Sampling failed (scatter XS / chi normalisation or random number above 1)"; break;
     case SB_ERR_NEST: msg = "Failed to find material cell (nesting exceeded)"; break;
+    case SB_ERR_MAT_SOURCE: msg = "materialSource: Infinite loop in sampling source. Please check that defined volume contains source material."; break;
     case SB_ERR_PEER_TIMEOUT: msg = "peer exchange: a rank of the node did not post its cycle data in time"; break;
     case SB_ERR_BALANCE: msg = "loadBalancing: nearest-neighbour exchange cannot restore the shares of this distribution"; break;
     case SB_ERR_FILE_SOURCE: msg = "fileSource: neutron sampled from file source is outside of geometry or in undefined region"; break;
@@ -1349,6 +1378,24 @@ int sb_source_point(sb_engine* h, int n, uint64_t rng_state, int history_offset,
   CUDA_OK(cudaGetLastError());
   h->nCur = n; h->broodValid = false;
   return 0;
+}
+int sb_geometry_bounds(sb_engine* h, double* b) { for (int i = 0; i < 6; ++i) b[i] = h->bounds[i]; return 0; }
+int sb_source_material(sb_engine* h, int n, uint64_t rng_state, int history_offset, const sb_material_source* s) {
+  if (!s || n < 1) { h->err = "sb_source_material: invalid arguments"; return -1; }
+  if (h->ceMode == (s->is_mg != 0)) { h->err = "sb_source_material: the source data type (ce / mg) does not match the loaded nuclear data"; return -1; }
+  if (s->mat_idx < 1 || s->mat_idx > h->nMat) { h->err = "sb_source_material: source material was not found in the material definitions"; return -1; }
+  if (s->is_mg && (s->G < 1 || s->G > h->nG)) { h->err = "sb_source_material: source group outside the group structure"; return -1; }
+  if (buildBlob(h)) return -1;
+  if (ensureCapacity(h, std::max(n, h->opt.max_pop))) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemsetAsync(h->dCd, 0, sizeof(CycleDev), h->stream));
+  k_source_material<<<gridFor(h, n, 128), 128, 0, h->stream>>>(h->M, h->dBlob, h->bank[h->cur], n, rng_state, history_offset, *s, h->dCd);
+  h->launches++;
+  CUDA_OK(cudaMemcpyAsync(h->hCd, h->dCd, sizeof(CycleDev), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  h->nCur = n; h->broodValid = false;
+  return checkDeviceError(h, h->hCd->error);
 }
 int sb_set_file_source(sb_engine* h, int64_t n_rows, const double* rows, int is_mg) {
   if (n_rows < 1 || !rows) { h->err = "sb_set_file_source: the source file holds no particles"; return -1; }

@@ -34,6 +34,7 @@ struct eigenPhysicsPackage {
   bool isFixed = false; int N_cycles = 0, bufferSize = 50; sb_point_source psrc{}; std::vector<double> probG;
   // fileSource (ParticleObjects/Source/fileSource_class.f90): the rows of a printToFile dump
   bool isFileSrc = false, fileSrcMG = false; std::vector<double> fileRows;
+  bool isMatSrc = false, matSrcBox = false; sb_material_source msrc{};
   // printSource / outputFile (eigenPhysicsPackage_class.f90:278-281,463,501-504)
   int printSource = 0; std::string outputFile = "./output"; int cycleInPhase[2] = {0, 0}, lastActive = 0; std::vector<int32_t> hBrood;
   sb_engine* eng = nullptr;
@@ -112,7 +113,8 @@ struct eigenPhysicsPackage {
         tallies[0] = sb::buildTallies(sb::Dict::fromString(""), mats, data.nMat);
         tallies[1] = sb::buildTallies(dict.getDict("tally"), mats, data.nMat);
         const sb::Dict& sd = dict.getDict("source");
-        if (int rc = (sd.getWord("type") == "fileSource") ? initFileSource(sd) : initPointSource(sd)) return rc;
+        const std::string st = sd.getWord("type");
+        if (int rc = (st == "fileSource") ? initFileSource(sd) : (st == "materialSource") ? initMaterialSource(sd, mats) : initPointSource(sd)) return rc;
       } else {
         tallies[0] = sb::buildTallies(dict.getDict("inactiveTally"), mats, data.nMat);
         tallies[1] = sb::buildTallies(dict.getDict("activeTally"), mats, data.nMat);
@@ -128,11 +130,40 @@ struct eigenPhysicsPackage {
         if (sb_define_tallies(eng, ph, tallies[ph].clerks.data(), (int)tallies[ph].clerks.size(), tallies[ph].normClerk, tallies[ph].normVal)) return engFail();
       if (sb_set_options(eng, &opt)) return engFail();
       if (isFixed && sb_set_fixed_source(eng, 1, bufferSize)) return engFail();
+      if (isMatSrc && !matSrcBox) {                                   // bounds = self % geom % bounds()
+        double b[6]; if (sb_geometry_bounds(eng, b)) return engFail();
+        for (int k = 0; k < 3; ++k) { msrc.bottom[k] = b[k]; msrc.top[k] = b[3 + k]; }
+      }
       if (isFileSrc && sb_set_file_source(eng, (int64_t)(fileRows.size() / 10), fileRows.data(), fileSrcMG ? 1 : 0)) return engFail();
     } catch (const std::exception& e) { return fail(e.what()); }
     return 0;
   }
 
+  // materialSource%init (materialSource_class.f90:75-134); boundingTime only moves the particle's time, which the engine does not carry
+  int initMaterialSource(const sb::Dict& d, const sb::MatMap& mats) {
+    std::string energy = d.getWord("data", "ce");
+    if (energy != "ce" && energy != "mg") return fail("init (materialSource): Invalid source data type specified: must be ce or mg");
+    msrc.is_mg = (energy == "mg") ? 1 : 0;
+    if ((msrc.is_mg != 0) == isCE) return fail("init (materialSource): the source data type does not match dataType");
+    msrc.E = d.getReal("E", 1.0E-6); msrc.G = d.getInt("G", 1);
+    const std::string name = d.getWord("mat");
+    auto it = mats.find(name);
+    if (it == mats.end()) return fail("init (materialSource): Source material " + name + " was not found in the material definitions");
+    msrc.mat_idx = it->second;
+    if (d.isPresent("boundingBox")) {
+      auto b = d.getRealArray("boundingBox");
+      if (b.size() != 6) return fail("init (materialSource): Bounding box must have 6 entries");
+      for (int k = 0; k < 3; ++k) { msrc.bottom[k] = b[k]; msrc.top[k] = b[3 + k]; }
+      matSrcBox = true;
+    }
+    if (d.isPresent("boundingTime")) {
+      auto t = d.getRealArray("boundingTime");
+      if (t.size() != 2) return fail("init (materialSource): Bounding time must have 2 entries");
+      if (t[1] < t[0]) return fail("init (materialSource): tHigh is less than tLow");
+    }
+    isMatSrc = true;
+    return 0;
+  }
   // fileSource%init (fileSource_class.f90:46-144): all rows are kept, broodID (column 9) is ignored by the sampling
   int initFileSource(const sb::Dict& d) {
     std::string energy = d.getWord("data", "ce");
@@ -220,7 +251,7 @@ struct eigenPhysicsPackage {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (!isFixed) return fail("not a fixedSourcePhysicsPackage deck");
     if (nRanks > 1) return fail("fixed-source batches of several ranks: run one package per rank with its own share of pop");
-    if (isFileSrc ? sb_source_file(eng, pop, pRNG, 0) : sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
+    if (isFileSrc ? sb_source_file(eng, pop, pRNG, 0) : isMatSrc ? sb_source_material(eng, pop, pRNG, 0, &msrc) : sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
     stride(totalPop);
     if (printBank(1, false, true)) return -1;
     if (sb_run_cycle(eng, pRNG, 0, 1.0, 1, &last)) return engFail();

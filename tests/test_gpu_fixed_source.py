@@ -21,7 +21,11 @@ CE = os.path.join(ROOT, "decks", "fixed", "ce_sphere")
     (MG, "pop 4000; cycles 2; seed 6; transportOperator { type transportOperatorST; } source { type pointSource; r (0.1 0.2 0.3); G 2; dir (0.0 1.0 1.0); }"),
     (MG, "pop 4000; cycles 2; seed 7; transportOperator { type transportOperatorHT; cutoff 0.7; } source { type pointSource; r (-1.0 0.0 0.5); probG (0.5 0.2 0.1 0.1 0.05 0.03 0.02); }"),
     (CE, "pop 6000; cycles 3; seed 8;"),
-    (CE, "pop 4000; cycles 2; seed 9; transportOperator { type transportOperatorDT; } source { type pointSource; r (1.0 1.0 0.0); E 2.0; }")])
+    (CE, "pop 4000; cycles 2; seed 9; transportOperator { type transportOperatorDT; } source { type pointSource; r (1.0 1.0 0.0); E 2.0; }"),
+    # materialSource (materialSource_class.f90): uniform in the fuel by rejection over the geometry's bounding box / a given box
+    (MG, "pop 5000; cycles 2; seed 10; source { type materialSource; mat UO2; data mg; G 3; }"),
+    (MG, "pop 4000; cycles 2; seed 11; source { type materialSource; mat water; data mg; G 1; boundingBox (-5.0 -5.0 -5.0 5.0 5.0 0.0); }"),
+    (CE, "pop 4000; cycles 2; seed 12; source { type materialSource; mat fuel; E 1.5; }")])
 def test_fixed_source_batches_against_oracle(orc, deck, ov):
     orc.orc_set_math_mode(1)
     try:
@@ -57,5 +61,13 @@ def test_secondary_buffer_overflow_is_the_reference_error():
     """A buffer of one entry cannot hold the sites of a fission with nu > 2: 'Run out of space for particles'."""
     pp = scone_b200.FixedSourcePhysicsPackage(MG, "pop 20000; cycles 1; seed 5; buffer 1;", device=0)
     with pytest.raises(scone_b200.EngineError, match="Run out of space for particles"):
+        pp.fixed_cycle()
+    pp.close()
+
+
+def test_material_source_without_its_material_in_the_box_is_the_reference_error():
+    ov = "pop 100; cycles 1; seed 1; source { type materialSource; mat UO2; data mg; G 1; boundingBox (4.0 4.0 4.0 4.9 4.9 4.9); }"
+    pp = scone_b200.FixedSourcePhysicsPackage(MG, ov, device=0)
+    with pytest.raises(scone_b200.EngineError, match="Infinite loop in sampling source"):
         pp.fixed_cycle()
     pp.close()
