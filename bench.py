@@ -100,8 +100,10 @@ def oracle_rate(deck, pop, n_inactive, seconds, threads, tracking=None):
     dt = time.perf_counter() - t0
     seg1, c1, h1 = C.c_long(), C.c_long(), C.c_long()
     orc.orc_eigen_stats(e, C.byref(seg1), C.byref(c1), C.byref(h1))
+    kc, ks = C.c_double(), C.c_double()
+    orc.orc_eigen_keff(e, 1, C.byref(kc), C.byref(ks))
     orc.orc_eigen_free(e)
-    return dict(nps=pop * n / dt, sps=(seg1.value - seg0.value) / dt, cycles=n, seconds=dt, k=k)
+    return dict(nps=pop * n / dt, sps=(seg1.value - seg0.value) / dt, cycles=n, seconds=dt, k=k, k_cum=kc.value, k_std=ks.value)
 
 
 def ce_nuclides_and_material(n_nuc=20):
@@ -197,13 +199,15 @@ def run_reference(args, rank, world):
     s1, c1, h1 = C.c_long(), C.c_long(), C.c_long()
     orc.orc_eigen_stats(e, C.byref(s1), C.byref(c1), C.byref(h1))
     val = pop * args.steps / dt
+    kc, ks = C.c_double(), C.c_double()
+    orc.orc_eigen_keff(e, 1, C.byref(kc), C.byref(ks))
     line = {
         "impl": "reference", "metric": "active-cycle neutrons/s", "value": val, "unit": "neutrons/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck == "ce_pin" else "DT"),
                    "note": "CPU reference arm: one step = one active cycle of pop histories on the host cores"},
-        "segments_per_s": (s1.value - s0.value) / dt, "keff": k,
+        "segments_per_s": (s1.value - s0.value) / dt, "keff": kc.value, "keff_std": ks.value,
         "cpu_baseline": {"value": val, "unit": "neutrons/s", "cores": threads, "kind": "port",
                          "sample": "%d active cycles of %d histories (oracle: C++/OpenMP restatement of SCONE's history loop; "
                                    "SCONE itself is Fortran and no Fortran compiler exists in the image)" % (args.steps, pop)},
@@ -370,7 +374,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = oracle_rate(DECKS[args.deck], pop, 3, args.cpu_seconds, threads, args.tracking)
+            comb = (r["k_std"] ** 2 + k_std ** 2) ** 0.5
             cpu = {"value": r["nps"], "unit": "neutrons/s", "cores": threads, "kind": "port", "segments_per_s": r["sps"],
+                   "keff": r["k_cum"], "keff_std": r["k_std"],
+                   "keff_delta_in_combined_sigma": (k_dev - r["k_cum"]) / comb if comb > 0 else None,
                    "sample": "%d active cycles of %d histories in %.1f s (oracle: C++/OpenMP restatement of SCONE's history loop; "
                              "SCONE is Fortran and cannot be compiled in this image)" % (r["cycles"], pop, r["seconds"])}
         line = {

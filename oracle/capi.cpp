@@ -403,6 +403,10 @@ int orc_eigen_info(void* ev, int* pop, int* nInactive, int* nActive, int* nG, in
 uint64_t orc_eigen_rng_state(void* ev) { return ((EigenPP*)ev)->pRNG.seed; }
 void orc_eigen_set_rng_state(void* ev, uint64_t s) { ((EigenPP*)ev)->pRNG.seed = s; }
 double orc_eigen_keff0(void* ev) { return ((EigenPP*)ev)->keff_0; }
+// cumulative k-eff of the active (which = 1) or inactive (0) attachment clerk: mean and standard deviation of the mean
+int orc_eigen_keff(void* ev, int which, double* k, double* std_) {
+  auto* e = (EigenPP*)ev; return (which ? e->activeAtch : e->inactiveAtch).getKeff(*k, *std_) ? 0 : -1;
+}
 int orc_eigen_init_source(void* ev) { ORC_TRY ((EigenPP*)ev)->generateInitialState(); return 0; ORC_CATCH(-1) }
 // one cycle; k_in is the k used for site generation; returns k_new (NaN on error)
 double orc_eigen_cycle(void* ev, int active, double k_in) {

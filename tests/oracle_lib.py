@@ -103,7 +103,7 @@ def load():
         "orc_eigen_info": (i32, [vp] + [c_ip] * 6),
         "orc_eigen_rng_state": (u64, [vp]),
         "orc_eigen_set_rng_state": (None, [vp, u64]),
-        "orc_eigen_keff0": (dbl, [vp]),
+        "orc_eigen_keff0": (dbl, [vp]), "orc_eigen_keff": (i32, [vp, i32, c_dp, c_dp]),
         "orc_eigen_init_source": (i32, [vp]),
         "orc_eigen_cycle": (dbl, [vp, i32, dbl]),
         "orc_eigen_run": (i32, [vp]),
