@@ -20,6 +20,24 @@ comm = D.TorchComm(device=torch.device("cuda", dev))
 pp = scone_b200.EigenPhysicsPackage(deck, ov, device=dev, rank=rank, n_ranks=ws)
 if len(sys.argv) > 11 and sys.argv[11] == "peer":          # exchange through peer memory instead of the process group
     assert D.enable_peer(pp, comm), "peer memory could not be attached: " + comm.peer_error
+if len(sys.argv) > 11 and sys.argv[11] == "peer_absent":    # rank 1 never runs its cycle: rank 0 must come back with the time-out error
+    assert D.enable_peer(pp, comm), "peer memory could not be attached: " + comm.peer_error
+    pp.generateInitialState()
+    if rank == 0:
+        pp.L.sb_peer_set_timeout(pp.engine, 0.5)
+        try:
+            pp.cycle(False, comm=comm)
+            print("no error raised")
+        except scone_b200.EngineError as ex:
+            print("raised:", ex)
+            if "did not post its cycle data in time" in str(ex):
+                print("ok", rank)
+    else:
+        print("ok", rank)
+    dist.barrier()
+    pp.close()
+    dist.destroy_process_group()
+    sys.exit(0)
 pp.generateInitialState()
 ks, segs = [], []
 for c in range(ninact + nact):

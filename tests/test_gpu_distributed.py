@@ -116,3 +116,9 @@ def test_peer_memory_exchange_reproduces_single_rank_histories(tmp_path, deck, p
         assert sum(int(f["seg"][c]) for f in fin) == res.n_segments
     assert len({int(f["rng"][0]) for f in fin}) == ws          # every rank keeps its own stream offset
     pp.close()
+
+
+def test_peer_exchange_times_out_when_a_rank_does_not_show_up(tmp_path):
+    """A rank that never posts its cycle data must not hang the others: the waiting kernels give up after the time-out and the call
+    returns the error (the spin is bounded on the device, nothing is left running)."""
+    run_ranks(2, "gloo", DECK["c5g7"], "pop 4000; inactive 1; active 1; seed 1;", 1, 1, tmp_path, extra=("peer_absent",))
