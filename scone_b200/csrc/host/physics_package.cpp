@@ -112,6 +112,7 @@ struct eigenPhysicsPackage {
       if (isFixed) {
         tallies[0] = sb::buildTallies(sb::Dict::fromString(""), mats, data.nMat);
         tallies[1] = sb::buildTallies(dict.getDict("tally"), mats, data.nMat);
+        for (auto& c : tallies[1].clerks) if (c.kind == SB_CLERK_SHANNON) return fail("shannonEntropyClerk in a fixed-source tally is not supported by the device tallies");
         const sb::Dict& sd = dict.getDict("source");
         const std::string st = sd.getWord("type");
         if (int rc = (st == "fileSource") ? initFileSource(sd) : (st == "materialSource") ? initMaterialSource(sd, mats) : initPointSource(sd)) return rc;
