@@ -9,7 +9,12 @@ for deck, ov, fixed in ((R + "/decks/ce/pincell", "pop 1500; inactive 1; active 
                         (R + "/decks/c5g7/c5g7_2d", "pop 3000; inactive 1; active 1; seed 3; transportOperator { type transportOperatorST; }", False),
                         (R + "/decks/c5g7/c5g7_2d", "pop 3000; inactive 1; active 1; seed 3;", False),
                         (R + "/decks/fixed/ce_sphere", "pop 2000; cycles 2; seed 3;", True),
-                        (R + "/decks/fixed/mg_sphere", "pop 2000; cycles 2; seed 3;", True)):
+                        (R + "/decks/fixed/mg_sphere", "pop 2000; cycles 2; seed 3;", True),
+                        (R + "/decks/fixed/mg_sphere", "pop 2000; cycles 2; seed 3; source { type materialSource; mat UO2; data mg; G 2; }", True),
+                        (R + "/decks/mg/can", "pop 3000; inactive 1; active 1; seed 3;", False),
+                        (R + "/decks/mg/can", "pop 3000; inactive 1; active 1; seed 3; transportOperator { type transportOperatorDT; }", False),
+                        (R + "/decks/c5g7/c5g7_2d", "pop 3000; inactive 1; active 1; seed 3; printSource 2; outputFile /tmp/san_dump; "
+                         "activeTally { e { type shannonEntropyClerk; cycles 1; map { type spaceMap; axis x; grid lin; min -32.13; max 32.13; N 10; } } }", False)):
     for cfg in (("", "events") if "ce/" in deck and not fixed else ("",)):
         if cfg: os.environ["SB_CE_KERNEL"] = cfg
         else: os.environ.pop("SB_CE_KERNEL", None)
