@@ -480,6 +480,17 @@ int orc_clerk_sequence(const char* clerkText, const char* matList, double xsAll,
   return (int)t.mem.N;
   ORC_CATCH(-1)
 }
+// tally responses over the constant-XS database (TallyResponses/Tests/macroResponse_test.f90, fluxResponse_test.f90):
+// xs = { total, elastic, inelastic, capture, fission, nuFission, kappaXS }
+double orc_response_value(const char* respText, const double* xs) {
+  ORC_TRY
+  ConstXsView v; v.x.total = xs[0]; v.x.elasticScatter = xs[1]; v.x.inelasticScatter = xs[2]; v.x.capture = xs[3]; v.x.fission = xs[4];
+  v.x.nuFission = xs[5]; v.x.kappaXS = xs[6];
+  Response r; r.init(Dict::fromString(respText));
+  Particle p; p.coords.matIdx = 1; p.w = 1.0;
+  return r.get(v, p);
+  ORC_CATCH(std::nan(""))
+}
 // shannonEntropyClerk_test.f90 testSimpleUseCase: cycles of end-of-cycle populations { matIdx, x, wgt }; out[c] = entropy of cycle c
 int orc_shannon_sequence(const char* clerkText, const char* matList, int nCycles, const int* counts, const int* matIdx, const double* x,
                          const double* w, double* out) {

@@ -136,6 +136,7 @@ def load():
         "orc_ace_card_info": (i32, [C.c_char_p, c_dp, c_ip, C.c_char_p]), "orc_ce_nuclide_elastic_isotropic": (i32, [vp]),
         "orc_heap_queue": (dbl, [i32, i32, c_dp, i32, c_ip]),
         "orc_shannon_sequence": (i32, [C.c_char_p, C.c_char_p, i32, c_ip, c_ip, c_dp, c_dp, c_dp]),
+        "orc_response_value": (dbl, [C.c_char_p, c_dp]),
         "orc_map_new": (vp, [C.c_char_p, C.c_char_p]), "orc_map_free": (None, [vp]), "orc_map_bins": (i32, [vp]),
         "orc_map_map": (i32, [vp, c_dp, dbl, i32, i32, i32]), "orc_fixed_cycle": (i32, [vp]), "orc_eigen_is_fixed": (i32, [vp]),
         "orc_tabpdf_sample": (dbl, [i32, c_dp, c_dp, c_dp, i32, dbl]),

@@ -148,3 +148,45 @@ def test_shannon_entropy_clerk_eigen(orc, deck, pop, lo, hi):
         pp.close(); orc.orc_eigen_free(e)
     finally:
         orc.orc_set_math_mode(0)
+
+
+ALL_RESP = ("%s { a { type collisionClerk; response (r1 r2 r22 r4 r6 r7 r80 r21); %s } "
+            "b { type collisionClerk; map { type materialMap; materials (%s); undefBin yes; } response (fl r3 r20 r8 r9 m18 m101); fl { type fluxResponse; } %s } }")
+
+
+@pytest.mark.parametrize("deck,pop,mats,extra", [
+    (DECK["c5g7"], 5000, "UO2 water", ""), (DECK["c5g7"], 4000, "UO2 water", " transportOperator { type transportOperatorST; }"),
+    (DECK["ce_pin"], 2500, "fuel water", ""), (DECK["ce_pin"], 2500, "fuel water", " transportOperator { type transportOperatorDT; }")])
+def test_every_macro_response_against_oracle(orc, deck, pop, mats, extra):
+    """macroResponse over the whole table of neutronMacroXSs%get (neutronXsPackages_class.f90:143-190): total, capture, elastic, non-elastic,
+    inelastic, all scattering, fission, nu-fission, kappa-fission, prompt / delayed nu-fission, absorption, and ENDF MT numbers (18, 101)."""
+    def defs(mts, pre="r"):
+        return " ".join("%s%d { type macroResponse; MT %d; }" % (pre, abs(m), m) for m in mts)
+    t1 = defs([-1, -2, -22, -4, -6, -7, -80, -21])
+    t2 = defs([-3, -20, -8, -9]) + " " + defs([18, 101], "m")
+    ov = "pop %d; inactive 1; active 3; seed 5; inactiveTally { } %s%s" % (pop, ALL_RESP % ("activeTally", t1, mats, t2), extra)
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(deck.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(deck, ov, device=0)
+        orc.orc_eigen_init_source(e); pp.generateInitialState()
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(4):
+            pp.cycle(cyc >= 1)
+            k_o = orc.orc_eigen_cycle(e, 1 if cyc >= 1 else 0, k_o)
+        n = orc.orc_eigen_tally_size(e, 1)
+        assert n == 8 + 3 * 7
+        cs, cs2, nb = pp.tally(True)
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+        a = cs[:8]
+        assert (a[[0, 1, 2, 4, 5, 6, 7]] > 0).all()
+        assert a[7] == pytest.approx(a[1] + a[4], rel=1e-9)            # absorption = capture + fission
+        assert sum(cs[8 + 7 * b + 5] for b in range(3)) == pytest.approx(a[4], rel=1e-9)      # MT 18 over the material bins = fission
+        assert sum(cs[8 + 7 * b + 6] for b in range(3)) == pytest.approx(a[1], rel=1e-9)      # MT 101 = capture
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)

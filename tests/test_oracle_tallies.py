@@ -236,3 +236,14 @@ def test_shannon_entropy_clerk_known_answers(orc):
     assert orc.orc_shannon_sequence(text.encode(), b"", 3, ol.ip(counts), ol.ip(mat), ol.dp(x), ol.dp(w), ol.dp(out)) == 4 + 1 + 2
     p = np.array([0.25, 0.75])
     assert out[0] == pytest.approx(-(p * np.log2(p)).sum(), abs=1e-12) and out[1] == pytest.approx(2.0, abs=1e-12)
+
+
+def test_response_known_answers(orc):
+    # TallyResponses/Tests/macroResponse_test.f90:29,62-68 (database: total 6, elastic 3, inelastic 0, capture 2, fission 1, nuFission 1.5,
+    # kappa 9): total 6, disappearance (capture) 2, fission 1, nuFission 1.5, absorbtion 3, kappa-fission 9; fluxResponse_test.f90: 1
+    xs = np.array([6.0, 3.0, 0.0, 2.0, 1.0, 1.5, 9.0])
+    for mt, ref in ((-1, 6.0), (-2, 2.0), (-6, 1.0), (-7, 1.5), (-21, 3.0), (-80, 9.0)):
+        assert orc.orc_response_value(("type macroResponse; MT %d;" % mt).encode(), ol.dp(xs)) == pytest.approx(ref, abs=1e-9)
+    for mt, ref in ((1, 6.0), (101, 2.0), (18, 1.0), (27, 3.0), (301, 9.0)):           # ENDF MT numbers are translated to the macroscopic ones
+        assert orc.orc_response_value(("type macroResponse; MT %d;" % mt).encode(), ol.dp(xs)) == pytest.approx(ref, abs=1e-9)
+    assert orc.orc_response_value(b"type fluxResponse;", ol.dp(xs)) == 1.0
