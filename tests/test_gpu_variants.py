@@ -1,0 +1,86 @@
+"""Deck features that the benchmark decks do not touch, driven through whole cycles on the GPU against the oracle (bit-identical banks,
+tallies to rounding): rotated and translated universes, a cell universe with the overlap check inside a lattice with an offset map,
+unstructured space / energy grids, a linear energy grid, material maps with the undefined bin."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scone_b200
+from tests import oracle_lib as ol
+from tests.gpu_util import DECK
+from tests.test_gpu_ce_transport import oracle_bank as oracle_bank_ce
+from tests.test_gpu_eigen import oracle_bank as oracle_bank_mg
+
+pytestmark = pytest.mark.gpu
+
+GEOM = """geometry {
+  type geometryStd;
+  boundary (1 1 1 1 1 1);
+  graph { type %s; }
+  surfaces {
+    bound { id 1; type box; origin (0.0 0.0 0.0); halfwidth (4.0 4.0 5.0); }
+    ball  { id 2; type sphere; origin (0.3 -0.2 0.4); radius 1.1; }
+    slab  { id 3; type plane; coeffs (1.0 1.0 0.5 0.7); }
+  }
+  cells {
+    in   { id 1; type simpleCell; surfaces (-2);   filltype mat; material %s; }
+    low  { id 2; type simpleCell; surfaces (2 -3); filltype mat; material %s; }
+    high { id 3; type simpleCell; surfaces (2 3);  filltype uni; universe 31; }
+  }
+  universes {
+    root  { id 1; type rootUniverse; border 1; fill u<10>; }
+    lat   { id 10; type latUniverse; origin (0.0 0.0 0.0); shape (2 2 2); pitch (4.0 4.0 5.0); padMat %s;
+            map (31 32 32 31 32 31 31 32); offsetMap (1 0 1 1 1 1 0 1); }
+    tilt  { id 31; type pinUniverse; origin (0.4 0.0 0.0); rotation (20.0 30.0 10.0); radii (0.9 1.4 0.0); fills (%s %s %s); }
+    cells { id 32; type cellUniverse; origin (0.1 0.2 -0.3); rotation (0.0 45.0 0.0); checkOverlap 1; cells (1 2 3); }
+  }
+}"""
+SPACE = "mz { type spaceMap; axis z; grid unstruct; bins (-5.0 -2.0 -0.5 0.1 0.9 3.3 5.0); }"
+
+
+def run(orc, deck, ov, ncyc, bank_fn, n_bins):
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(deck.encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.EigenPhysicsPackage(deck, ov, device=0)
+        assert orc.orc_eigen_init_source(e) == 0, ol.err(orc)
+        pp.generateInitialState()
+        k_o = orc.orc_eigen_keff0(e)
+        for cyc in range(ncyc):
+            pp.cycle(cyc >= 1)
+            k_o = orc.orc_eigen_cycle(e, 1 if cyc >= 1 else 0, k_o)
+            assert not np.isnan(k_o), ol.err(orc)
+            for a, b in zip(pp.bank(), bank_fn(orc, e)):
+                assert np.array_equal(a, b), "bank differs after cycle %d" % cyc
+        n = orc.orc_eigen_tally_size(e, 1)
+        assert n == n_bins
+        cs, cs2, nb = pp.tally(True)
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+        assert np.count_nonzero(cs) > n_bins // 3
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
+
+
+@pytest.mark.parametrize("graph,tracking", [("shrunk", "transportOperatorDT"), ("extended", "transportOperatorST"), ("shrunk", "transportOperatorHT")])
+def test_mg_rotated_universes_and_unstructured_maps(orc, graph, tracking):
+    geom = GEOM % (graph, "UO2", "water", "water", "mox87", "GT", "water")
+    tally = ("activeTally { f { type collisionClerk; map { type multiMap; maps (mz mm); %s "
+             "mm { type materialMap; materials (UO2 mox87); undefBin yes; } } response (fl fi); fl { type fluxResponse; } fi { type macroResponse; MT -6; } } }" % SPACE)
+    ov = "pop 5000; inactive 1; active 2; seed 9; inactiveTally { } transportOperator { type %s; } %s %s" % (tracking, geom, tally)
+    run(orc, DECK["c5g7"], ov, 3, oracle_bank_mg, 6 * 3 * 2)
+
+
+@pytest.mark.parametrize("tracking", ["transportOperatorDT", "transportOperatorST"])
+def test_ce_rotated_universes_and_energy_grids(orc, tracking):
+    geom = GEOM % ("shrunk", "fuel", "water", "water", "fuel", "water", "water")
+    tally = ("activeTally { f { type collisionClerk; map { type multiMap; maps (eu mz); "
+             "eu { type energyMap; grid unstruct; bins (1.0E-11 1.0E-7 6.25E-7 1.0E-4 0.1 1.0 20.0); } %s } response (fl); fl { type fluxResponse; } } "
+             "g { type collisionClerk; map { type energyMap; grid lin; min 0.0; max 10.0; N 25; } response (fl ab); fl { type fluxResponse; } ab { type macroResponse; MT -21; } } }" % SPACE)
+    ov = "pop 2500; inactive 1; active 2; seed 10; inactiveTally { } transportOperator { type %s; } %s %s" % (tracking, geom, tally)
+    run(orc, DECK["ce_pin"], ov, 3, oracle_bank_ce, 6 * 6 + 25 * 2)
