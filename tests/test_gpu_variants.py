@@ -84,3 +84,43 @@ def test_ce_rotated_universes_and_energy_grids(orc, tracking):
              "g { type collisionClerk; map { type energyMap; grid lin; min 0.0; max 10.0; N 25; } response (fl ab); fl { type fluxResponse; } ab { type macroResponse; MT -21; } } }" % SPACE)
     ov = "pop 2500; inactive 1; active 2; seed 10; inactiveTally { } transportOperator { type %s; } %s %s" % (tracking, geom, tally)
     run(orc, DECK["ce_pin"], ov, 3, oracle_bank_ce, 6 * 6 + 25 * 2)
+
+
+GEOM_PERIODIC = """geometry {
+  type geometryStd;
+  boundary (%s);
+  graph { type shrunk; }
+  surfaces {
+    bound { id 1; type %s; origin (0.0 0.0 0.0); halfwidth (%s); }
+    cx { id 2; type xCylinder; origin (0.0 0.5 -0.5); radius 0.8; }
+    cy { id 3; type yCylinder; origin (-1.0 0.0 1.0); radius 0.6; }
+    px { id 4; type xPlane; x0 0.9; }
+    sq { id 5; type xSquareCylinder; origin (0.0 -1.2 -1.2); halfwidth (0.0 0.5 0.4); }
+  }
+  cells {
+    a { id 1; type simpleCell; surfaces (-2 -4);    filltype mat; material UO2; }
+    b { id 2; type simpleCell; surfaces (-3 2);     filltype mat; material mox43; }
+    c { id 3; type simpleCell; surfaces (-5 2 3);   filltype mat; material GT; }
+    d { id 4; type simpleCell; surfaces (2 3 5);    filltype mat; material water; }
+    e { id 5; type simpleCell; surfaces (-2 4 3);   filltype mat; material water; }
+  }
+  universes {
+    root { id 1; type rootUniverse; border 1; fill u<2>; }
+    main { id 2; type cellUniverse; cells (1 2 3 4 5); }
+  }
+}"""
+
+
+@pytest.mark.parametrize("border,hw,bc,tracking", [
+    ("box", "2.0 2.5 2.2", "2 2 1 1 2 2", "transportOperatorDT"),              # periodic in x and z, reflective in y
+    ("box", "2.0 2.5 2.2", "2 2 0 1 2 2", "transportOperatorST"),              # one vacuum face
+    ("ySquareCylinder", "2.0 0.0 2.2", "2 2 0 0 1 1", "transportOperatorST"),  # infinite in y: periodic x, reflective z
+    ("zSquareCylinder", "2.0 2.5 0.0", "1 1 2 2 0 0", "transportOperatorHT")])
+def test_mg_axis_cylinders_planes_and_periodic_boundaries(orc, border, hw, bc, tracking):
+    geom = GEOM_PERIODIC % (bc, border, hw)
+    tally = "activeTally { f { type collisionClerk; map { type spaceMap; axis x; grid lin; min -2.0; max 2.0; N 8; } response (fl); fl { type fluxResponse; } } }"
+    ov = "pop 4000; inactive 1; active 2; seed 4; inactiveTally { } transportOperator { type %s; cache %d; } %s %s" % (
+        tracking, 0 if tracking == "transportOperatorHT" else 1, geom, tally)
+    if tracking == "transportOperatorDT":
+        ov = ov.replace("cache 1; ", "")
+    run(orc, DECK["c5g7"], ov, 3, oracle_bank_mg, 8)
