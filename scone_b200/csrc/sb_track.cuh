@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
         else {
           invSigmaTrack = 1.0 / sigmaTrack;
           dist = -sbm::log(rngGet(rng)) * invSigmaTrack;
-          sigmaT = mgRow(M, T, m, G)[XS_TOTAL] + 0.0;
+          sigmaT = (m == SB_VOID_MAT) ? 0.0 : mgRow(M, T, m, G)[XS_TOTAL] + 0.0;      // getTotalMatXS of a void region is 0
         }
         int event;
         const double rPre[3] = {c.r[0][0], c.r[0][1], c.r[0][2]};      // p%savePrePath (transportOperatorST_class.f90:107)

@@ -124,3 +124,46 @@ def test_mg_axis_cylinders_planes_and_periodic_boundaries(orc, border, hw, bc, t
     if tracking == "transportOperatorDT":
         ov = ov.replace("cache 1; ", "")
     run(orc, DECK["c5g7"], ov, 3, oracle_bank_mg, 8)
+
+
+GEOM_VOID = """geometry {
+  type geometryStd;
+  boundary (1 1 1 1 0 0);
+  graph { type shrunk; }
+  surfaces {
+    bound { id 1; type box; origin (0.0 0.0 0.0); halfwidth (3.0 3.0 4.0); }
+    gapIn  { id 2; type zCylinder; origin (0.0 0.0 0.0); radius 1.0; }
+    gapOut { id 3; type zCylinder; origin (0.0 0.0 0.0); radius 1.4; }
+  }
+  cells {
+    fuel { id 1; type simpleCell; surfaces (-2);   filltype mat; material %s; }
+    gap  { id 2; type simpleCell; surfaces (2 -3); filltype mat; material void; }
+    mod  { id 3; type simpleCell; surfaces (3);    filltype mat; material %s; }
+  }
+  universes {
+    root { id 1; type rootUniverse; border 1; fill u<2>; }
+    main { id 2; type cellUniverse; cells (1 2 3); }
+  }
+}"""
+ND_MG = """nuclearData { handles { mg { type baseMgNeutronDatabase; PN P0; avgDist 2.5; } }
+  materials { UO2 { temp 300; xsFile ./xs/UO2.xs; composition { } } water { temp 300; xsFile ./xs/moder.xs; composition { } } } }"""
+ND_CE = """nuclearData { handles { ce { type aceNeutronDatabase; aceLibrary ../../tests/golden/ace/aceLib; ures 0; majorant 1; avgDist 3.0; } }
+  materials { fuel  { temp 293; composition { 92233.03 1.5E-4; 52126.03 2.2E-2; 91231.03 5.0E-5; 91232.03 2.0E-6; } }
+              water { temp 293; composition { 1001.03 6.67E-2; 52126.03 1.0E-3; } } } }"""
+FLUX = "activeTally { f { type collisionClerk; map { type spaceMap; axis z; grid lin; min -4.0; max 4.0; N 8; } response (fl); fl { type fluxResponse; } } }"
+
+
+@pytest.mark.parametrize("tracking", ["transportOperatorDT", "transportOperatorST", "transportOperatorHT"])
+def test_mg_void_gap_and_minimum_collision_distance(orc, tracking):
+    """A void gap (no collisions, flux still scored at virtual collisions) and `avgDist` of the database (collisionXS = 1 / avgDist as the
+    floor of the tracking cross section, baseMgNeutronDatabase_class.f90:95-133), vacuum top and bottom."""
+    ov = "pop 4000; inactive 1; active 2; seed 6; inactiveTally { } transportOperator { type %s; } %s %s %s" % (
+        tracking, GEOM_VOID % ("UO2", "water"), ND_MG, FLUX)
+    run(orc, DECK["c5g7"], ov, 3, oracle_bank_mg, 8)
+
+
+@pytest.mark.parametrize("tracking", ["transportOperatorDT", "transportOperatorST", "transportOperatorHT"])
+def test_ce_void_gap_and_minimum_collision_distance(orc, tracking):
+    ov = "pop 2500; inactive 1; active 2; seed 7; inactiveTally { } transportOperator { type %s; } %s %s %s" % (
+        tracking, GEOM_VOID % ("fuel", "water"), ND_CE, FLUX)
+    run(orc, DECK["ce_pin"], ov, 3, oracle_bank_ce, 8)
