@@ -167,3 +167,16 @@ def test_ce_void_gap_and_minimum_collision_distance(orc, tracking):
     ov = "pop 2500; inactive 1; active 2; seed 7; inactiveTally { } transportOperator { type %s; } %s %s %s" % (
         tracking, GEOM_VOID % ("fuel", "water"), ND_CE, FLUX)
     run(orc, DECK["ce_pin"], ov, 3, oracle_bank_ce, 8)
+
+
+@pytest.mark.parametrize("deck,pop,tracking,bank_fn", [
+    ("c5g7", 5000, "transportOperatorDT", oracle_bank_mg), ("c5g7", 4000, "transportOperatorHT", oracle_bank_mg), ("c5g7", 4000, "transportOperatorST", oracle_bank_mg),
+    ("ce_pin", 2500, "transportOperatorDT", oracle_bank_ce), ("ce_pin", 2500, "transportOperatorHT", oracle_bank_ce)])
+def test_collision_clerk_without_virtual_collisions(orc, deck, pop, tracking, bank_fn):
+    """handleVirtual 0 (collisionClerk_class.f90:204-231): virtual collisions are skipped and the flux is w / Sigma_t of the material, next to a
+    clerk with the default handling in the same tally; track clerk alongside (scores only on surface-tracking segments)."""
+    tally = ("activeTally { real { type collisionClerk; handleVirtual 0; response (fl ab); fl { type fluxResponse; } ab { type macroResponse; MT -21; } } "
+             "all { type collisionClerk; response (fl ab); fl { type fluxResponse; } ab { type macroResponse; MT -21; } } "
+             "path { type trackClerk; response (fl ab); fl { type fluxResponse; } ab { type macroResponse; MT -21; } } }")
+    ov = "pop %d; inactive 1; active 3; seed 8; inactiveTally { } transportOperator { type %s; } %s" % (pop, tracking, tally)
+    run(orc, DECK[deck], ov, 4, bank_fn, 6)
