@@ -168,7 +168,7 @@ typedef struct sb_cycle_result {
   int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
-       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10, SB_ERR_PEER_TIMEOUT = 11, SB_ERR_BALANCE = 12, SB_ERR_MAT_SOURCE = 13,
+       SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10, SB_ERR_PEER_TIMEOUT = 11, SB_ERR_BALANCE = 12, SB_ERR_MAT_SOURCE = 13, SB_ERR_MAT_SOURCE_VOID = 14,
        SB_ERR_CE_ENERGY = 8 /* energy outside the bounds of the CE data */, SB_ERR_CE_DATA = 9 /* failed search / rejection loop in the reaction data */ };
 
 /* ---- life cycle -------------------------------------------------------------------------- */

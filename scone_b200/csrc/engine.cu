@@ -746,7 +746,7 @@ __global__ void k_source_material(const Model M, const char* blob, Bank out, int
       int mat, uid;
       geomPlace(M, T, r, u, mat, uid);
       if (mat == SB_OUTSIDE_MAT) continue;
-      if (mat >= SB_OVERLAP_MAT) { atomicMax(&cd->error, mat == SB_VOID_MAT ? SB_ERR_MAT_SOURCE : (mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT)); break; }
+      if (mat >= SB_OVERLAP_MAT) { atomicMax(&cd->error, mat == SB_VOID_MAT ? SB_ERR_MAT_SOURCE_VOID : (mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT)); ok = true; break; }
       if (mat != S.mat_idx) continue;
       double mu = 2.0 * rng_get(rng) - 1.0;
       double phi = TWO_PI * rng_get(rng);
@@ -1323,6 +1323,7 @@ static int checkDeviceError(sb_engine* h, int code) {
     case SB_ERR_OVERLAP_MAT: msg = "Particle is in overlapping cells"; break;
     case SB_ERR_SAMPLING: msg = "Sampling failed (scatter XS / chi normalisation or random number above 1)"; break;
     case SB_ERR_NEST: msg = "Failed to find material cell (nesting exceeded)"; break;
+    case SB_ERR_MAT_SOURCE_VOID: msg = "materialSource: Nuclear data did not return neutron material (a sampled point lies in a void region)."; break;
     case SB_ERR_MAT_SOURCE: msg = "materialSource: Infinite loop in sampling source. Please check that defined volume contains source material."; break;
     case SB_ERR_PEER_TIMEOUT: msg = "peer exchange: a rank of the node did not post its cycle data in time"; break;
     case SB_ERR_BALANCE: msg = "loadBalancing: nearest-neighbour exchange cannot restore the shares of this distribution"; break;

@@ -180,3 +180,55 @@ def test_collision_clerk_without_virtual_collisions(orc, deck, pop, tracking, ba
              "path { type trackClerk; response (fl ab); fl { type fluxResponse; } ab { type macroResponse; MT -21; } } }")
     ov = "pop %d; inactive 1; active 3; seed 8; inactiveTally { } transportOperator { type %s; } %s" % (pop, tracking, tally)
     run(orc, DECK[deck], ov, 4, bank_fn, 6)
+
+
+@pytest.mark.parametrize("deck,nd,mats,src,tracking", [
+    ("c5g7", ND_MG, ("UO2", "water"), "source { type pointSource; r (0.2 0.1 0.0); G 1; }", "transportOperatorST"),
+    ("c5g7", ND_MG, ("UO2", "water"), "source { type materialSource; mat water; data mg; G 2; boundingBox (1.5 1.5 -3.9 2.9 2.9 3.9); }", "transportOperatorHT"),
+    ("c5g7", ND_MG, ("UO2", "water"), "source { type pointSource; r (1.2 0.0 0.0); G 7; }", "transportOperatorDT"),      # born in the void gap
+    ("ce_pin", ND_CE, ("fuel", "water"), "source { type pointSource; r (0.0 0.0 1.0); E 14.1; }", "transportOperatorST"),
+    ("ce_pin", ND_CE, ("fuel", "water"), "source { type materialSource; mat fuel; E 2.0; boundingBox (-0.7 -0.7 -3.9 0.7 0.7 3.9); }", "transportOperatorDT")])
+def test_fixed_source_with_void_gap(orc, deck, nd, mats, src, tracking):
+    """Fixed-source batches (secondaries from the private buffer) in the geometry with a void gap, vacuum ends and a minimum collision
+    distance: segment and collision counts equal to the oracle's, tallies to rounding."""
+    ov = ("type fixedSourcePhysicsPackage; pop 3000; cycles 2; seed 13; buffer 60; transportOperator { type %s; } %s %s %s "
+          "tally { f { type collisionClerk; map { type spaceMap; axis z; grid lin; min -4.0; max 4.0; N 8; } response (fl); fl { type fluxResponse; } } "
+          "p { type trackClerk; response (fl); fl { type fluxResponse; } } }" % (tracking, GEOM_VOID % mats, nd, src))
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(DECK[deck].encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.FixedSourcePhysicsPackage(DECK[deck], ov, device=0)
+        segs = colls = 0
+        for _ in range(2):
+            assert orc.orc_fixed_cycle(e) == 0, ol.err(orc)
+            res = pp.fixed_cycle()
+            segs += res.n_segments; colls += res.n_collisions
+            assert pp.rng_state == orc.orc_eigen_rng_state(e)
+        seg, coll, hist = C.c_long(), C.c_long(), C.c_long()
+        orc.orc_eigen_stats(e, C.byref(seg), C.byref(coll), C.byref(hist))
+        assert segs == seg.value and colls == coll.value
+        n = orc.orc_eigen_tally_size(e, 1)
+        cs, cs2, nb = pp.tally(True)
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(cs2, ocs2, rtol=1e-10, atol=1e-300)
+        assert cs[:8].sum() > 0
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
+
+
+def test_material_source_point_in_void_is_the_reference_error(orc):
+    """materialSource asks the database for the material at every sampled point; a void region has none (materialSource_class.f90:176-177)."""
+    ov = ("type fixedSourcePhysicsPackage; pop 500; cycles 1; seed 13; transportOperator { type transportOperatorDT; } %s %s "
+          "source { type materialSource; mat water; data mg; G 2; } tally { }" % (GEOM_VOID % ("UO2", "water"), ND_MG))
+    e = orc.orc_eigen_load(DECK["c5g7"].encode(), ov.encode())
+    assert e, ol.err(orc)
+    assert orc.orc_fixed_cycle(e) != 0 and "did not return neutron material" in ol.err(orc)
+    orc.orc_eigen_free(e)
+    pp = scone_b200.FixedSourcePhysicsPackage(DECK["c5g7"], ov, device=0)
+    with pytest.raises(scone_b200.EngineError, match="did not return neutron material"):
+        pp.fixed_cycle()
+    pp.close()
