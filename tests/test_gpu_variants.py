@@ -232,3 +232,38 @@ def test_material_source_point_in_void_is_the_reference_error(orc):
     with pytest.raises(scone_b200.EngineError, match="did not return neutron material"):
         pp.fixed_cycle()
     pp.close()
+
+
+@pytest.mark.parametrize("src,tracking", [
+    ("r (0.5 0.0 -1.0); dir (1.0 0.0 0.0); G 1;", "transportOperatorST"),        # along the axis of the x truncated cylinder
+    ("r (3.5 0.0 -1.0); dir (0.0 0.0 1.0); G 3;", "transportOperatorST"),        # born ON the rod surface, moving parallel to it
+    ("r (3.5 0.0 -1.0); dir (-1.0 0.0 0.0); G 3;", "transportOperatorHT"),
+    ("r (0.5 0.0 3.0); dir (0.0 1.0 0.0); G 2;", "transportOperatorST"),         # born ON the top face of the rod
+    ("r (0.5 0.0 -5.999999999999); G 7;", "transportOperatorDT")])               # a hair above the reflective bottom
+def test_fixed_source_on_surfaces_and_along_axes(orc, src, tracking):
+    """Source particles that start exactly on surfaces or fly along coordinate axes (zero direction components, parallel-to-surface
+    branches of `going`, the tolerance branches of `distance`): decks/mg/can as a fixed-source problem."""
+    ov = ("type fixedSourcePhysicsPackage; pop 3000; cycles 2; seed 21; transportOperator { type %s; } source { type pointSource; %s } "
+          "tally { f { type collisionClerk; map { type spaceMap; axis z; grid lin; min -6.0; max 6.0; N 6; } response (fl); fl { type fluxResponse; } } }" % (tracking, src))
+    orc.orc_set_math_mode(1)
+    try:
+        e = orc.orc_eigen_load(DECK["can"].encode(), ov.encode())
+        assert e, ol.err(orc)
+        pp = scone_b200.FixedSourcePhysicsPackage(DECK["can"], ov, device=0)
+        segs = colls = 0
+        for _ in range(2):
+            assert orc.orc_fixed_cycle(e) == 0, ol.err(orc)
+            res = pp.fixed_cycle()
+            segs += res.n_segments; colls += res.n_collisions
+        seg, coll, hist = C.c_long(), C.c_long(), C.c_long()
+        orc.orc_eigen_stats(e, C.byref(seg), C.byref(coll), C.byref(hist))
+        assert segs == seg.value and colls == coll.value
+        n = orc.orc_eigen_tally_size(e, 1)
+        cs, cs2, nb = pp.tally(True)
+        ocs = np.zeros(n); ocs2 = np.zeros(n); b = C.c_int()
+        orc.orc_eigen_tally(e, 1, ol.dp(ocs), ol.dp(ocs2), C.byref(b))
+        np.testing.assert_allclose(cs, ocs, rtol=1e-10, atol=1e-300)
+        assert cs.sum() > 0
+        pp.close(); orc.orc_eigen_free(e)
+    finally:
+        orc.orc_set_math_mode(0)
