@@ -122,3 +122,36 @@ def test_peer_exchange_times_out_when_a_rank_does_not_show_up(tmp_path):
     """A rank that never posts its cycle data must not hang the others: the waiting kernels give up after the time-out and the call
     returns the error (the spin is bounded on the device, nothing is left running)."""
     run_ranks(2, "gloo", DECK["c5g7"], "pop 4000; inactive 1; active 1; seed 1;", 1, 1, tmp_path, extra=("peer_absent",))
+
+
+@pytest.mark.parametrize("extra", [(), ("peer",)])
+def test_ranked_surface_tracking_with_entropy_clerk(tmp_path, extra):
+    """Several ranks with surface tracking, a Shannon-entropy clerk and a very subcritical system (decks/mg/can, k = 0.18: every cycle the
+    bank is multiplied up with copies by normSize_Repr, so most sites change rank in the balancing): same banks as one rank, over the
+    process group and over peer memory."""
+    pop, ws, ninact, nact = 6002, 3, 2, 2
+    tal = ("%s { ent { type shannonEntropyClerk; cycles 2; map { type spaceMap; axis z; grid lin; min -6.0; max 6.0; N 6; } } "
+           "fl { type collisionClerk; response (f); f { type fluxResponse; } } }")
+    ov = "pop %d; inactive %d; active %d; seed 77; transportOperator { type transportOperatorST; cache 1; } %s %s" % (
+        pop, ninact, nact, tal % "inactiveTally", tal % "activeTally")
+    run_ranks(ws, "gloo", DECK["can"], ov, ninact, nact, tmp_path, extra=extra)
+    pp = scone_b200.EigenPhysicsPackage(DECK["can"], ov, device=0)
+    pp.generateInitialState()
+    fin = [np.load(os.path.join(tmp_path, "final_r%d.npz" % r)) for r in range(ws)]
+    for c in range(ninact + nact):
+        res = pp.cycle(c >= ninact)
+        parts = [np.load(os.path.join(tmp_path, "bank_c%d_r%d.npz" % (c, r))) for r in range(ws)]
+        assert [len(p["w"]) for p in parts] == [scone_b200.distributed.workshare(pop, ws, r)[0] for r in range(ws)]
+        for key, ref in zip(("r", "d", "w", "G"), pp.bank()):
+            assert np.array_equal(np.concatenate([p[key] for p in parts]), ref), "bank differs after cycle %d (%s)" % (c, key)
+        for f in fin:
+            assert f["k"][c] == pytest.approx(pp.k, rel=1e-12)
+        assert sum(int(f["seg"][c]) for f in fin) == res.n_segments
+    cs, cs2, nb = pp.tally(True)
+    tot = sum(f["cs"] for f in fin)
+    assert tot[-1] == pytest.approx(cs[-1], rel=1e-10)                  # the flux clerk is additive over ranks
+    ent_single = cs[7:9]
+    assert (ent_single > 0).all()
+    for f in fin:                                                       # every rank scores the entropy of ITS share of the bank (no mpiSync)
+        assert (f["cs"][7:9] > 0).all() and (f["cs"][:7] == 0).all()
+    pp.close()
