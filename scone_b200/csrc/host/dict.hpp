@@ -162,7 +162,9 @@ class Dict {
     long long v = std::strtoll(t.c_str(), &end, 10);
     return v >= INT32_MIN && v <= INT32_MAX;
   }
-  // ^[-+]?[0-9]*[.][0-9]*([eEdD][-+]?[0-9]+)?$ with at least one digit in the mantissa
+  // What a Fortran formatted READ with an ES edit descriptor accepts (dictParser_func.f90:781, tried after the I20 read failed):
+  // [sign] digits [. digits] | [sign] . digits, then optionally an exponent: a letter e E d D with an optional sign, or a bare sign,
+  // followed by digits ("1E-11", "1.0d3", "2.5+3").  Integers that do not fit 32 bits fail the integer read and are reals too.
   static bool isReal(const std::string& t) {
     size_t i = 0, n = t.size();
     if (i < n && (t[i] == '-' || t[i] == '+')) ++i;
@@ -172,11 +174,11 @@ class Dict {
       else if (t[i] == '.' && !dot) dot = true;
       else break;
     }
-    if (!dot || nd == 0) return false;
+    if (nd == 0) return false;
     if (i == n) return true;
-    if (t[i] != 'e' && t[i] != 'E' && t[i] != 'd' && t[i] != 'D') return false;
-    ++i;
-    if (i < n && (t[i] == '-' || t[i] == '+')) ++i;
+    if (t[i] == 'e' || t[i] == 'E' || t[i] == 'd' || t[i] == 'D') { ++i; if (i < n && (t[i] == '-' || t[i] == '+')) ++i; }
+    else if (t[i] == '-' || t[i] == '+') ++i;
+    else return false;
     if (i >= n) return false;
     for (; i < n; ++i) if (t[i] < '0' || t[i] > '9') return false;
     return true;
@@ -185,7 +187,9 @@ class Dict {
   static double toReal(const std::string& t) {
     std::string s = t;
     for (auto& c : s) if (c == 'd' || c == 'D') c = 'e';
-    return std::strtod(s.c_str(), nullptr);   // correctly rounded, as list-directed READ
+    for (size_t i = 1; i < s.size(); ++i)                                   // exponent given by a bare sign: 2.5+3
+      if ((s[i] == '+' || s[i] == '-') && ((s[i - 1] >= '0' && s[i - 1] <= '9') || s[i - 1] == '.')) { s.insert(i, "e"); break; }
+    return std::strtod(s.c_str(), nullptr);   // correctly rounded, as the formatted READ
   }
 
  private:

@@ -17,6 +17,7 @@
 #include "../../../include/scone_b200.h"
 #include "../sb_rng.h"
 #include "model.hpp"
+#include <sstream>
 #include "ce_model.hpp"
 #include "../sb_cekin.cuh"
 
@@ -485,6 +486,34 @@ int sbh_ce_card_process(void* pv, int nuc, int* gridSize, int* rows, int* nMT, d
 int sbh_ce_info(void* pv, int* nNuc, int* nMat) { auto* p = (eigenPhysicsPackage*)pv; *nNuc = (int)p->ceData.cards.size(); *nMat = p->ceData.nMat; return 0; }
 int sbh_eigen_cycle_peer(void* pv, int active, double* k, int32_t* finalSizes, sb_cycle_result* res) {
   auto* p = (eigenPhysicsPackage*)pv; int rc = p->cyclePeer(active, finalSizes, *k); if (res) *res = p->last; return rc;
+}
+// input dictionaries (DataStructures/dictParser_func.f90, dictionary_class.f90): value at `path` ("key" or "sub/key") of a dictionary given
+// as text or as a file, as text: kind 'i' int, 'r' real (%.17g), 'w' word, 'I' / 'R' / 'W' arrays (space separated), 'k' keys of the
+// (sub)dictionary at path ("" = top).  Returns the length, -1 on error (message in sbh_last_error(NULL)).
+int sbh_dict_get(const char* text, int isPath, const char* path, char kind, char* out, int cap) {
+  try {
+    sb::Dict top = isPath ? sb::Dict::fromFile(text) : sb::Dict::fromString(text);
+    const sb::Dict* d = &top;
+    std::string p = path ? path : "", key;
+    for (;;) {
+      size_t k = p.find('/');
+      if (k == std::string::npos) { key = p; break; }
+      d = &d->getDict(p.substr(0, k)); p = p.substr(k + 1);
+    }
+    std::ostringstream os; os.precision(17);
+    if (kind == 'i') os << d->getInt(key);
+    else if (kind == 'r') os << d->getReal(key);
+    else if (kind == 'w') os << d->getWord(key);
+    else if (kind == 'I') { bool f = true; for (int v : d->getIntArray(key)) { os << (f ? "" : " ") << v; f = false; } }
+    else if (kind == 'R') { bool f = true; for (double v : d->getRealArray(key)) { os << (f ? "" : " ") << v; f = false; } }
+    else if (kind == 'W') { bool f = true; for (auto& v : d->getWordArray(key)) { os << (f ? "" : " ") << v; f = false; } }
+    else if (kind == 'k') { const sb::Dict& q = key.empty() ? *d : d->getDict(key); bool f = true; for (auto& v : q.keys("all")) { os << (f ? "" : " ") << v; f = false; } }
+    else throw sb::FatalError("sbh_dict_get", "unknown kind");
+    std::string r = os.str();
+    if ((int)r.size() + 1 > cap) throw sb::FatalError("sbh_dict_get", "buffer too small");
+    memcpy(out, r.c_str(), r.size() + 1);
+    return (int)r.size();
+  } catch (const std::exception& e) { g_sbhErr = e.what(); return -1; }
 }
 // several ranks: the source dump of this rank after the caller has balanced the banks
 int sbh_eigen_print_source(void* pv, int active) { return ((eigenPhysicsPackage*)pv)->printBank(active); }

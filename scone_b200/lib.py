@@ -82,6 +82,7 @@ def load_library():
         "sb_bank_brood": (i32, [vp, i32, ip]), "sb_set_file_source": (i32, [vp, i64, dp, i32]), "sb_source_file": (i32, [vp, i32, u64, i32]),
         "sbh_eigen_print_source": (i32, [vp, i32]), "sbh_eigen_print_source_mode": (i32, [vp]),
         "sb_source_material": (i32, [vp, i32, u64, i32, vp]), "sb_geometry_bounds": (i32, [vp, dp]),
+        "sbh_dict_get": (i32, [C.c_char_p, i32, C.c_char_p, C.c_char, C.c_char_p, i32]),
         "sb_peer_create": (i32, [vp, i32, i32, i32, vp]), "sb_bank_capacity": (i32, [vp]), "sb_peer_attach": (i32, [vp, vp, ip]), "sb_peer_capacity": (i32, [vp]),
         "sb_peer_set_timeout": (i32, [vp, dbl]),
         "sb_run_cycle_ranked_peer": (i32, [vp, u64, i32, dbl, i32, i32, u64, ip, C.POINTER(CycleResult)]),
