@@ -27,11 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DECKS = {"c5g7": "decks/c5g7/c5g7_2d", "c5g7_3d": "decks/c5g7/c5g7_3d_rodded", "inf": "decks/urr/inf", "slab": "decks/urr/slab",
-         "ce_pin": "decks/ce/pincell", "ce_asm": "decks/ce/assembly17"}
+         "ce_pin": "decks/ce/pincell", "ce_asm": "decks/ce/assembly17", "can": "decks/mg/can"}
 WORKLOAD = {"c5g7": "C5G7 MOX 2D 7-group eigenvalue, delta tracking (InputFiles/Benchmarks/Multigroup/C5G7 as decks/c5g7/c5g7_2d)",
             "c5g7_3d": "C5G7 3D rodded-A 7-group eigenvalue with 34x34x9 flux+fission mesh, delta tracking",
             "inf": "SCONE_Inf URRa-2-1-IN 2-group infinite medium", "slab": "SCONE_Slab URRa-2-1-SL 2-group slab (P1)",
             "ce_asm": "synthetic continuous-energy 17x17 assembly, 20 nuclides per fuel material (5 bundled ACE nuclides + 15 energy-shifted clones), delta tracking, k-eff only (BASELINE configs[4] at a single-GPU population)",
+            "can": "7-group finite can bounded by truncated cylinders (reflective bottom, vacuum top), surface tracking, strongly subcritical",
             "ce_pin": "continuous-energy U-233 / H-1 pin cell from the reference's bundled ACE nuclides (BASELINE configs[2] stand-in), 300-bin energy x material flux tally"}
 ALG_BYTES_PER_SEGMENT = 124      # particle SoA read+write per flight segment
 ALG_BYTES_PER_SCORE = 16         # f64 read-modify-write per tally score
@@ -205,7 +206,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "active-cycle neutrons/s", "value": val, "unit": "neutrons/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck == "ce_pin" else "DT"),
+        "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck in ("ce_pin", "can") else "DT"),
                    "note": "CPU reference arm: one step = one active cycle of pop histories on the host cores"},
         "segments_per_s": (s1.value - s0.value) / dt, "keff": kc.value, "keff_std": ks.value,
         "cpu_baseline": {"value": val, "unit": "neutrons/s", "cores": threads, "kind": "port",
@@ -385,7 +386,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD[args.deck], "deck": DECKS[args.deck], "pop_per_cycle_per_gpu": pop, "pop_per_cycle_total": total_pop,
-                       "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck == "ce_pin" else "DT"), "inactive_cycles_before": args.inactive,
+                       "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck in ("ce_pin", "can") else "DT"), "inactive_cycles_before": args.inactive,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
                        "parallelism": "bank sharded by history index over %d GPU(s)%s" % (
                            world, exchange)},

@@ -4,7 +4,7 @@ import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); c=d.get('cpu_baseline',{})
-        print(json.dumps({'deck':'$1','pop':$2,'tracking':d['config']['tracking'],'neutrons_per_s':d['value'],'ms_per_cycle':d['ms_per_step'],'segments_per_s':d['segments_per_s'],'e2e':d['e2e']['value'],'keff':d['keff'],'cpu_neutrons_per_s':c.get('value'),'cpu_cores':c.get('cores'),'cpu_pop':c.get('sample')}))
+        print(json.dumps({'deck':'$1','pop':$2,'tracking':d['config']['tracking'],'neutrons_per_s':d['value'],'ms_per_cycle':d['ms_per_step'],'segments_per_s':d['segments_per_s'],'e2e':d['e2e']['value'],'keff':d['keff'],'keff_std':d['keff_std'],'cpu_keff':c.get('keff'),'keff_delta_sigma':c.get('keff_delta_in_combined_sigma'),'cpu_neutrons_per_s':c.get('value'),'cpu_cores':c.get('cores'),'cpu_pop':c.get('sample')}))
     else: print(l.rstrip())
 "; }
 run c5g7 100000 20 8
@@ -13,3 +13,4 @@ run slab 1000000 10 5
 run ce_pin 1000000 5 3
 run c5g7_3d 1250000 6 4
 run ce_asm 1250000 4 3
+run can 200000 10 5
