@@ -188,6 +188,8 @@ struct Dungeon {
 
   // :431-602, single rank (nRanks = 1; MPI collectives degenerate to identities)
   void normSize_Repr(int totPop, RNG& rand) {
+    // an empty fission bank: the reference divides by the number of sites (:478-481); the restatement stops with a message instead
+    if (pop <= 0) throw FatalError("normSize_Repr", "the fission bank is empty");
     int maxBroodID = 0;
     for (int i = 0; i < pop; ++i) maxBroodID = std::max(maxBroodID, prisoners[i].broodID);
     sortByBroodID(maxBroodID);
@@ -694,12 +696,19 @@ struct FissionSource {
   }
   void generate(Dungeon& dungeon, int n, const RNG& rand) const {
     dungeon.setSize(n);
+    std::string srcErr;                                              // an exception may not leave the parallel region
 #pragma omp parallel for schedule(static)
     for (int i = 1; i <= n; ++i) {
+      if (!srcErr.empty()) continue;
       RNG pRand = rand;
       pRand.stride(i);
-      dungeon.prisoners[i - 1] = sampleParticle(pRand);
+      try { dungeon.prisoners[i - 1] = sampleParticle(pRand); }
+      catch (const std::exception& ex) {
+#pragma omp critical
+        srcErr = ex.what();
+      }
     }
+    if (!srcErr.empty()) throw FatalError("generate (source)", srcErr);
   }
 };
 
@@ -1141,8 +1150,17 @@ struct EigenPP {
     tally.reportCycleStart(*thisCycle);
     int nParticles = thisCycle->pop;
     long seg = 0, coll = 0;
+    std::string histErr;                                             // fatalError inside a history: stop after the loop (an exception may not leave the parallel region)
 #pragma omp parallel for schedule(dynamic) reduction(+ : seg, coll)
-    for (int n = 1; n <= nParticles; ++n) history(n, k_new, tally, seg, coll);
+    for (int n = 1; n <= nParticles; ++n) {
+      if (!histErr.empty()) continue;
+      try { history(n, k_new, tally, seg, coll); }
+      catch (const std::exception& ex) {
+#pragma omp critical
+        histErr = std::string(ex.what()) + " [history " + std::to_string(n) + "]";
+      }
+    }
+    if (!histErr.empty()) throw FatalError("cycles", histErr);
     nSegments += seg; nCollisions += coll; nHistories += nParticles;
     thisCycle->pop = 0;                                             // cleanPop
     pRNG.stride(pop + 1);
