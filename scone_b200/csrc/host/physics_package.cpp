@@ -36,6 +36,7 @@ struct eigenPhysicsPackage {
   // fileSource (ParticleObjects/Source/fileSource_class.f90): the rows of a printToFile dump
   bool isFileSrc = false, fileSrcMG = false; std::vector<double> fileRows;
   bool isMatSrc = false, matSrcBox = false; sb_material_source msrc{};
+  bool fixedStarted = false;
   // printSource / outputFile (eigenPhysicsPackage_class.f90:278-281,463,501-504)
   int printSource = 0; std::string outputFile = "./output"; int cycleInPhase[2] = {0, 0}, lastActive = 0; std::vector<int32_t> hBrood;
   sb_engine* eng = nullptr;
@@ -252,7 +253,9 @@ struct eigenPhysicsPackage {
   int fixedCycle() {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (!isFixed) return fail("not a fixedSourcePhysicsPackage deck");
-    if (nRanks > 1) return fail("fixed-source batches of several ranks: run one package per rank with its own share of pop");
+    // several ranks (fixedSourcePhysicsPackage_class.f90:131,347): every rank owns getWorkshare(totalPop) source particles of each batch and
+    // starts from the package RNG strided by getOffset(totalPop); no exchange during the run, tally%collectDistributed at the end
+    if (!fixedStarted) { pRNG = sbd::rng_skip(pRNG, sbd::RNG_STRIDE * (int64_t)rankOffset); fixedStarted = true; }
     if (isFileSrc ? sb_source_file(eng, pop, pRNG, 0) : isMatSrc ? sb_source_material(eng, pop, pRNG, 0, &msrc) : sb_source_point(eng, pop, pRNG, 0, &psrc)) return engFail();
     stride(totalPop);
     if (printBank(1, false, true)) return -1;

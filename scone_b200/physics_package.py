@@ -80,8 +80,8 @@ class GeometryHandle(_Base):
 class FixedSourcePhysicsPackage:
     """fixedSourcePhysicsPackage on the B200 engine: the same handle as EigenPhysicsPackage, created from a deck of that type."""
 
-    def __new__(cls, deck, overrides="", device=0):
-        pp = EigenPhysicsPackage(deck, overrides, device)
+    def __new__(cls, deck, overrides="", device=0, rank=0, n_ranks=1):
+        pp = EigenPhysicsPackage(deck, overrides, device, rank=rank, n_ranks=n_ranks)
         if not pp.is_fixed_source:
             pp.close()
             raise EngineError("%s is not a fixedSourcePhysicsPackage deck" % deck)

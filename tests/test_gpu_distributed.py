@@ -155,3 +155,27 @@ def test_ranked_surface_tracking_with_entropy_clerk(tmp_path, extra):
     for f in fin:                                                       # every rank scores the entropy of ITS share of the bank (no mpiSync)
         assert (f["cs"][7:9] > 0).all() and (f["cs"][:7] == 0).all()
     pp.close()
+
+
+@pytest.mark.parametrize("deck,ws", [("mg_sphere", 2), ("ce_sphere", 3)])
+def test_ranked_fixed_source_is_the_single_rank_run_split(tmp_path, deck, ws):
+    """Fixed-source batches over several ranks (fixedSourcePhysicsPackage_class.f90:131,347): the ranks' histories together are the
+    histories of the single-rank run (same random streams), so segment counts add up exactly and un-normalised tallies to rounding."""
+    path = os.path.join(ROOT, "decks", "fixed", deck)
+    ov = "pop 4001; cycles 3; seed 17; tally { f { type collisionClerk; map { type spaceMap; axis x; grid lin; min -5.0; max 5.0; N 10; } response (fl); fl { type fluxResponse; } } }"
+    port = str(_free_port())
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "fixed_dist_worker.py"), ROOT, port, str(r), str(ws), path, ov, str(tmp_path)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(ws)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and ("ok %d" % r) in o, o[-3000:]
+    fin = [np.load(os.path.join(tmp_path, "fixed_r%d.npz" % r)) for r in range(ws)]
+    assert [int(f["pop"]) for f in fin] == [scone_b200.distributed.workshare(4001, ws, r)[0] for r in range(ws)]
+    pp = scone_b200.FixedSourcePhysicsPackage(path, ov, device=0)
+    segs = sum(pp.fixed_cycle().n_segments for _ in range(3))
+    cs, cs2, nb = pp.tally(True)
+    assert sum(int(f["seg"]) for f in fin) == segs
+    np.testing.assert_allclose(sum(f["cs"] for f in fin), cs, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(fin[0]["ccs"], cs, rtol=1e-10, atol=1e-300)          # collectDistributed: the master holds the sums
+    assert int(fin[0]["cnb"]) == ws * nb
+    pp.close()
