@@ -77,6 +77,14 @@ class CeDatabase:
             out["majorant"] = j
         return out
 
+    def lookup_into(self, E, mat, total):
+        """Host arrays in, PREALLOCATED host array out (e.g. page-locked numpy views of pinned torch tensors): Sigma_t per particle."""
+        if not (E.flags.c_contiguous and mat.flags.c_contiguous and total.flags.c_contiguous) or E.dtype != np.float64 or mat.dtype != np.int32 or total.dtype != np.float64:
+            raise ValueError("lookup_into: contiguous float64 / int32 / float64 arrays of equal length are required")
+        if self.L.sb_ce_lookup(self.eng, len(E), _dp(E), _ip(mat), _dp(total), None, None) != 0:
+            raise EngineError(self._err())
+        return total
+
     def lookup_device(self, dE, dMat, dTotal=0, dMacro=0, dMajorant=0, n=None):
         """Device pointers (ints, e.g. torch tensor .data_ptr()); returns the CUDA-event time of the kernel in ms."""
         if self.L.sb_ce_lookup_device(self.eng, n, dE, dMat, dTotal or None, dMacro or None, dMajorant or None) != 0:
