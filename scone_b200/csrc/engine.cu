@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(256) k_shannon_close(int addr, int nBins, int 
 // flags - no rank ever reads remote memory.  Slots are double-buffered by cycle parity: the all-to-all of the sums is a barrier,
 // so a rank is never more than one cycle ahead of another and a slot is rewritten only after its reader has consumed it.
 // ------------------------------------------------------------------------------------------------
+constexpr int CE_PIPE = 8;            // chunks in flight of the host-buffer CE lookup
 constexpr int PEER_MAX = 64;
 struct PeerBox {
   double data[2][PEER_MAX][8];                   // [parity][source rank]: 6 score sums, bank size, 0
@@ -884,6 +885,7 @@ struct sb_engine {
   PeerPlan* dPlan = nullptr; PeerPlan* hPlan = nullptr; double* dKsumTot = nullptr; unsigned long long peerSeq = 0; double peerTimeoutS = 20.0;
   struct ShannonRec { int clerk, addr, nBins, maxCycles, cycle; };
   std::vector<ShannonRec> shannon[2];     // shannonEntropyClerk records of each phase; cycle = reportCycleEnd calls so far
+  cudaStream_t ceStreamIn = nullptr, ceStreamOut = nullptr; cudaEvent_t ceEvIn[CE_PIPE] = {}, ceEvK[CE_PIPE] = {};      // sb_ce_lookup pipeline
   bool broodValid = false;       // the current bank came out of a cycle (its sites have parents); false for source / uploaded banks
   double* dFileSrc = nullptr; long long nFileSrc = 0; bool fileSrcMG = false;     // fileSource rows (printToFile records)
   bool ceMode = false; sbc::CeModelDev ceModel{}; std::vector<sbk::CardOut> ceCards; std::vector<void*> ceAllocs;
@@ -1142,6 +1144,7 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
   cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG); cudaFree(h->dFileSrc);
+  if (h->ceStreamIn) { cudaStreamDestroy(h->ceStreamIn); cudaStreamDestroy(h->ceStreamOut); for (int i = 0; i < CE_PIPE; ++i) { cudaEventDestroy(h->ceEvIn[i]); cudaEventDestroy(h->ceEvK[i]); } }
   for (int r = 0; r < PEER_MAX; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerOpened[r]);
   cudaFree(h->peerRegion); cudaFree(h->dPlan); cudaFreeHost(h->hPlan); cudaFree(h->dKsumTot);
   for (void* p : h->ceAllocs) cudaFree(p);
@@ -2044,19 +2047,48 @@ int sb_ce_last_kernel_ms(sb_engine* h, double* ms) { *ms = h->ceLastMs; return 0
 int sb_ce_lookup(sb_engine* h, int64_t n, const double* E, const int32_t* mat, double* total, double* macro, double* majorant) {
   CUDA_OK(cudaSetDevice(h->device));
   if (n <= 0) return 0;
+  if (!h->ce.loaded) { h->err = "continuous-energy data has not been loaded (sb_load_ce_data)"; return -1; }
+  if ((total || macro) && !mat) { h->err = "sb_ce_lookup: material indices are required for total / macro"; return -1; }
   // staging: E | mat | total | macro | majorant
   size_t need = sizeof(double) * (size_t)n * (1 + 1 + 1 + 8 + 1);
   if (ensureStage(h, need)) return -1;
   double* dE = h->dStage; int* dMat = (int*)(dE + n); double* dT = dE + 2 * n; double* dM = dE + 3 * n; double* dJ = dE + 11 * n;
-  cudaStream_t st = h->stream;
-  CUDA_OK(cudaMemcpyAsync(dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  if (mat) CUDA_OK(cudaMemcpyAsync(dMat, mat, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-  if ((total || macro) && !mat) { h->err = "sb_ce_lookup: material indices are required for total / macro"; return -1; }
-  if (ceLaunch(h, n, dE, dMat, total ? dT : nullptr, macro ? dM : nullptr, majorant ? dJ : nullptr, nullptr, 0)) return -1;
-  if (total) CUDA_OK(cudaMemcpyAsync(total, dT, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  if (macro) CUDA_OK(cudaMemcpyAsync(macro, dM, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
-  if (majorant) CUDA_OK(cudaMemcpyAsync(majorant, dJ, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (!h->dCeErr) { CUDA_OK(cudaMalloc(&h->dCeErr, sizeof(int))); CUDA_OK(cudaEventCreate(&h->evC0)); CUDA_OK(cudaEventCreate(&h->evC1)); }
+  // Three-stage pipeline over chunks: host->device copies, lookups and device->host copies run on their own streams (both copy
+  // engines busy, PCIe in both directions at once); with page-locked host arrays the call is bounded by the slower direction.
+  if (!h->ceStreamIn) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->ceStreamIn, cudaStreamNonBlocking)); CUDA_OK(cudaStreamCreateWithFlags(&h->ceStreamOut, cudaStreamNonBlocking));
+    for (int i = 0; i < CE_PIPE; ++i) { CUDA_OK(cudaEventCreateWithFlags(&h->ceEvIn[i], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&h->ceEvK[i], cudaEventDisableTiming)); }
+  }
+  cudaStream_t st = h->stream, sIn = h->ceStreamIn, sOut = h->ceStreamOut;
+  CUDA_OK(cudaMemsetAsync(h->dCeErr, 0, sizeof(int), st));
+  CUDA_OK(cudaEventRecord(h->ceEvK[0], st));
+  CUDA_OK(cudaStreamWaitEvent(sIn, h->ceEvK[0], 0));                 // the staging buffer may still be in use by earlier work of the main stream
+  const int64_t chunk = std::max<int64_t>(1 << 18, (n + CE_PIPE - 1) / CE_PIPE);
+  int c = 0;
+  for (int64_t o = 0; o < n; o += chunk, ++c) {
+    const int64_t m = std::min(chunk, n - o);
+    CUDA_OK(cudaMemcpyAsync(dE + o, E + o, sizeof(double) * m, cudaMemcpyHostToDevice, sIn));
+    if (mat) CUDA_OK(cudaMemcpyAsync(dMat + o, mat + o, sizeof(int) * m, cudaMemcpyHostToDevice, sIn));
+    CUDA_OK(cudaEventRecord(h->ceEvIn[c], sIn));
+    CUDA_OK(cudaStreamWaitEvent(st, h->ceEvIn[c], 0));
+    int blocks = (int)std::min<long long>((m + 255) / 256, (long long)h->numSM * 8);
+    sbce::k_ce_lookup<<<blocks, 256, 0, st>>>(h->ce.dev, m, dE + o, mat ? dMat + o : nullptr, total ? dT + o : nullptr, macro ? dM + 8 * o : nullptr,
+                                              majorant ? dJ + o : nullptr, nullptr, 0, h->dCeErr);
+    h->launches++;
+    CUDA_OK(cudaEventRecord(h->ceEvK[c], st));
+    CUDA_OK(cudaStreamWaitEvent(sOut, h->ceEvK[c], 0));
+    if (total) CUDA_OK(cudaMemcpyAsync(total + o, dT + o, sizeof(double) * m, cudaMemcpyDeviceToHost, sOut));
+    if (macro) CUDA_OK(cudaMemcpyAsync(macro + 8 * o, dM + 8 * o, sizeof(double) * 8 * m, cudaMemcpyDeviceToHost, sOut));
+    if (majorant) CUDA_OK(cudaMemcpyAsync(majorant + o, dJ + o, sizeof(double) * m, cudaMemcpyDeviceToHost, sOut));
+  }
+  int e = 0;
+  CUDA_OK(cudaMemcpyAsync(&e, h->dCeErr, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaStreamSynchronize(sOut));
+  CUDA_OK(cudaGetLastError());
+  if (e == 1) { h->err = "Failed to find energy in the nuclide energy grids (energy outside the bounds of the data)"; return -1; }
+  if (e == 2) { h->err = "Invalid material index in continuous-energy lookup"; return -1; }
   return 0;
 }
 int sb_ce_nuclide_index(sb_engine* h, int nuc_idx, int64_t n, const double* E, int32_t* idx) {
