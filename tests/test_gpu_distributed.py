@@ -179,3 +179,23 @@ def test_ranked_fixed_source_is_the_single_rank_run_split(tmp_path, deck, ws):
     np.testing.assert_allclose(fin[0]["ccs"], cs, rtol=1e-10, atol=1e-300)          # collectDistributed: the master holds the sums
     assert int(fin[0]["cnb"]) == ws * nb
     pp.close()
+
+
+@pytest.mark.parametrize("deck,pop,ws,extra", [
+    ("can", 402, 4, ()), ("can", 402, 4, ("peer",)),        # k = 0.18: strongly fluctuating per-rank fission banks (2 x share is the capacity, as in the reference)
+    ("c5g7", 130, 4, ()), ("c5g7", 130, 4, ("peer",))])
+def test_ranked_runs_with_tiny_shares(tmp_path, deck, pop, ws, extra):
+    """A few histories per rank: fission banks of single ranks can be empty, the resampling multiplies sites up with copies and nearly every
+    site changes rank in the balancing; both exchanges must reproduce the single-rank banks."""
+    ninact, nact = 2, 1
+    ov = "pop %d; inactive %d; active %d; seed 55; inactiveTally { } activeTally { }" % (pop, ninact, nact)
+    run_ranks(ws, "gloo", DECK[deck], ov, ninact, nact, tmp_path, extra=extra)
+    pp = scone_b200.EigenPhysicsPackage(DECK[deck], ov, device=0)
+    pp.generateInitialState()
+    for c in range(ninact + nact):
+        pp.cycle(c >= ninact)
+        parts = [np.load(os.path.join(tmp_path, "bank_c%d_r%d.npz" % (c, r))) for r in range(ws)]
+        assert [len(p["w"]) for p in parts] == [scone_b200.distributed.workshare(pop, ws, r)[0] for r in range(ws)]
+        for key, ref in zip(("r", "d", "w", "G"), pp.bank()):
+            assert np.array_equal(np.concatenate([p[key] for p in parts]), ref), "bank differs after cycle %d (%s)" % (c, key)
+    pp.close()
