@@ -286,7 +286,7 @@ size_t sb_site_buffer_bytes(int k);
  *   sb_run_cycle_ranked_peer  = sb_cycle_begin + reduction + sb_cycle_end_resample_ranked + loadBalancing with ONE host
  *                   synchronisation; final_sizes[n_ranks] = every rank's bank size afterwards.  All ranks must call it for the
  *                   same cycles; a rank that does not show up within the timeout (default 20 s) gives SB_ERR_PEER_TIMEOUT.     */
-int sb_bank_capacity(sb_engine* h);
+int sb_bank_capacity(sb_engine* h);          /* sites the banks of this engine hold: 2 * max_pop, the dungeons of eigenPhysicsPackage_class.f90:355-356 */
 int sb_peer_create(sb_engine* h, int n_ranks, int rank, int stage_cap, void* ipc_handle_64_bytes);
 int sb_peer_attach(sb_engine* h, const void* ipc_handles, const int32_t* caps);
 int sb_peer_capacity(sb_engine* h);
