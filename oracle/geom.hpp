@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../scone_b200/csrc/host/dict.hpp"   // input grammar only (no arithmetic)
+#include "../scone_b200/csrc/host/named_grids.hpp"   // input data only (the named energy-group structures)
 
 namespace orc {
 

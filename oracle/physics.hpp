@@ -369,7 +369,12 @@ struct EnergyMap : TallyMap {                                       // Maps1D/en
     std::string g = d.getWord("grid");
     if (g == "lin" || g == "log") { N = d.getInt("N"); grid.initEqual(d.getReal("min"), d.getReal("max"), N, g); }
     else if (g == "unstruct") { auto b = d.getRealArray("bins"); std::sort(b.begin(), b.end()); grid.initUnstruct(b); N = (int)b.size() - 1; }
-    else throw FatalError("init (energyMap)", "'grid' keyword must be: lin, log, unstruct (predef unsupported in oracle)");
+    else if (g == "predef") {                                       // build_predef (energyMap_class.f90:137-177): named grid, thermal to fast
+      auto b = sb::namedEnergyGrid(d.getWord("name"));
+      if (b.empty()) throw FatalError("build_predef (energyMap)", "Grid " + d.getWord("name") + " is undefined!");
+      grid.initUnstruct(b); N = (int)b.size() - 1;
+    }
+    else throw FatalError("init (energyMap)", "'grid' keyword must be: lin, log, unstruct or predef");
   }
   int bins() const override { return N; }
   int map(const ParticleState& s) const override {

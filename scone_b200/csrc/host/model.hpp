@@ -19,6 +19,7 @@
 
 #include "../../../include/scone_b200.h"
 #include "dict.hpp"
+#include "named_grids.hpp"
 
 namespace sb {
 
@@ -473,8 +474,12 @@ inline void addMap1D(TallyDefs& T, sb_clerk& c, const Dict& d, const MatMap& mat
     if (t == "spaceMap") { std::string ax = d.getWord("axis"); if (ax == "x") m.axis = 0; else if (ax == "y") m.axis = 1; else if (ax == "z") m.axis = 2; else throw FatalError("init (spaceMap)", "Unrecognised axis: " + ax); }
     std::string g = d.getWord("grid");
     if (g == "lin" || (g == "log" && t == "energyMap")) { m.grid = (g == "lin") ? SB_GRID_LIN : SB_GRID_LOG; m.n_bins = d.getInt("N"); gridEqual(g, d.getReal("min"), d.getReal("max"), m.n_bins, m.first, m.step); }
-    else if (g == "unstruct") {
-      auto b = d.getRealArray("bins");
+    else if (g == "unstruct" || (g == "predef" && t == "energyMap")) {
+      std::vector<double> b;
+      if (g == "predef") {                                          // energyMap%build_predef (energyMap_class.f90:137-177)
+        b = namedEnergyGrid(d.getWord("name"));
+        if (b.empty()) throw FatalError("build_predef (energyMap)", "Grid " + d.getWord("name") + " is undefined!");
+      } else b = d.getRealArray("bins");
       if (t == "energyMap") std::sort(b.begin(), b.end());
       if (b.size() < 2) throw FatalError("init_unstruct", "Empty array or array of size 1 was provided");
       for (size_t i = 1; i < b.size(); ++i) if (b[i] < b[i - 1]) throw FatalError("init_unstruct", "Provided grid is not sorted");

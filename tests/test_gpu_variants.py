@@ -267,3 +267,14 @@ def test_fixed_source_on_surfaces_and_along_axes(orc, src, tracking):
         pp.close(); orc.orc_eigen_free(e)
     finally:
         orc.orc_set_math_mode(0)
+
+
+def test_ce_predefined_energy_grids(orc):
+    """energyMap with `grid predef` (energyMap_class.f90:137-177): the named group structures, thermal to fast, in a multi-map with space."""
+    tally = ("activeTally { w { type collisionClerk; map { type energyMap; grid predef; name wims69; } response (fl); fl { type fluxResponse; } } "
+             "v { type collisionClerk; map { type multiMap; maps (e z); e { type energyMap; grid predef; name casmo7; } %s } response (fl ab); "
+             "fl { type fluxResponse; } ab { type macroResponse; MT -21; } } }" % SPACE.replace("mz {", "z {"))
+    ov = "pop 2500; inactive 1; active 2; seed 14; inactiveTally { } %s" % tally
+    run(orc, DECK["ce_pin"], ov, 3, oracle_bank_ce, 69 + 7 * 6 * 2)
+    with pytest.raises(scone_b200.EngineError, match="is undefined"):
+        scone_b200.EigenPhysicsPackage(DECK["ce_pin"], "seed 1; activeTally { w { type collisionClerk; map { type energyMap; grid predef; name nogrid; } response (fl); fl { type fluxResponse; } } }", device=-1)

@@ -105,8 +105,13 @@ def test_energy_map_known_answers(orc):
                                    5.98486350302033e-07, 20.0)] == [15, 1, 6, 1, 2, 0]
     assert [uns.map(E=e) for e in (0.0761191517392624, 0.00217742635754091, 6.38548311340975e-08, 2.52734532533842,
                                    2.59031729968032e-11, 20.0)] == [18, 16, 3, 23, 1, 0]
-    assert lin.map(mg=True, G=1) == 0 and log.map(mg=True, G=1) == 0 and uns.map(mg=True, G=1) == 0
-    assert (lin.bins(), log.bins(), uns.bins()) == (20, 20, 25)
+    pre = Map(orc, "type energyMap; grid predef; name casmo23;")           # testPredefGrid
+    assert [pre.map(E=e) for e in (0.0445008907555061, 1.79747463687278e-07, 1.64204055725811e-05, 2.34083673923110e-07,
+                                   5.98486350302033e-07, 20.0)] == [16, 4, 13, 4, 6, 0]
+    assert lin.map(mg=True, G=1) == 0 and log.map(mg=True, G=1) == 0 and uns.map(mg=True, G=1) == 0 and pre.map(mg=True, G=1) == 0
+    assert (lin.bins(), log.bins(), uns.bins(), pre.bins()) == (20, 20, 25, 23)
+    for name, n in (("wims69", 69), ("wims172", 172), ("casmo40", 40), ("casmo12", 12), ("casmo7", 7), ("ecco33", 33), ("vitaminj", 175)):
+        assert Map(orc, "type energyMap; grid predef; name %s;" % name).bins() == n
 
 
 @pytest.mark.parametrize("axis", [0, 1, 2])
