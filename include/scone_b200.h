@@ -336,6 +336,10 @@ int sb_geom_query(sb_engine* h, int64_t n, double* r, double* dir, const double*
 int sb_mg_query(sb_engine* h, int64_t n, const int32_t* mat, const int32_t* G, double* total, double* majorant);
 int sb_rng_query(int64_t n, const uint64_t* state, const int64_t* skip, uint64_t* out_state, double* out_real);
 int sb_math_query(int64_t n, const double* x, double* log_x, double* sin_x, double* cos_x);
+/* self-check of the engine's in-line division / square root (the sequences nvcc expands `/` and sqrt into, without
+   their per-operation range branch) against the plain operators on n generated operand pairs with binary exponents in
+   [-exp_span, exp_span]: *mismatches = results that differ in any bit (must be 0). */
+int sb_fastmath_check(int64_t n, uint64_t seed, int exp_span, int64_t* mismatches);
 
 #ifdef __cplusplus
 }

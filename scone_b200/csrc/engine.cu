@@ -814,6 +814,46 @@ __global__ void k_math_query(long long n, const double* x, double* lg, double* s
     double s, c; sbm::sincos(x[i], &s, &c); sn[i] = s; cs[i] = c;
   }
 }
+// the merged-range division / square root of sb_device.cuh against the plain operators, on generated operands:
+// a = 2^ea * (1 + fraction), b likewise, exponents within the fast range; counts results that differ in any bit
+__global__ void k_fastmath_check(long long n, unsigned long long seed, int expSpan, unsigned long long* bad) {
+  unsigned long long nb = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint64_t s = rng_skip(seed, 3 * i + 1);
+    double fa = rng_get(s), fb = rng_get(s), fe = rng_get(s);
+    int ea = (int)(fe * (2 * expSpan + 1)) - expSpan, eb = (int)((fe * 7919.0 - floor(fe * 7919.0)) * (2 * expSpan + 1)) - expSpan;
+    double a = ldexp(1.0 + fa, ea), b = ldexp(1.0 + fb, eb);
+    if (i & 1) a = -a;
+    if (i % 5 == 0) b = 1.0 - fb * fb;                      // the operands rotateVector sees: 1 - mu^2, sums of squares near one
+    if (i % 7 == 0) a = fa * fb;
+    if (fastRange(a) && fastRange(b)) {
+      double y = rcpRefined(b);
+      if (__double_as_longlong(divBy(a, b, y)) != __double_as_longlong(a / b)) ++nb;
+      if (b > 0.0 && __double_as_longlong(sqrtFast(b)) != __double_as_longlong(sqrt(b))) ++nb;
+    }
+  }
+  if (nb) atomicAdd(bad, nb);
+}
+
+// fissionMG%sampleOut + rotateVector for the sites the delta-tracking history kernel left unfinished (sb_hist.cuh):
+// slot = {r, parent direction, weight, G = material, E = bits of the stream state in front of the site's numbers}.
+// fissionMG_class.f90:183-206 (mu, phi, then the chi walk), neutronMGstd_class.f90:131-199
+__global__ void k_finish_sites(const Model M, const char* blob, Bank b, CycleDev* cd, int cap) {
+  const Tables T = bind(M, blob);
+  const int n = min(cd->nSites, cap);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    uint64_t rng = (uint64_t)__double_as_longlong(b.E[s]);
+    const int mat = b.G[s];
+    double mu, phi;
+    int Gout = mgFissionSample(M, T, mat, mu, phi, rng);
+    if (Gout == 0) { atomicMax(&cd->error, SB_ERR_SAMPLING); Gout = 1; }
+    double d[3] = {b.ux[s], b.uy[s], b.uz[s]};
+    rotateVector(d, mu, phi);
+    b.ux[s] = d[0]; b.uy[s] = d[1]; b.uz[s] = d[2];
+    b.G[s] = Gout; b.E[s] = 0.0;
+  }
+}
+
 __global__ void k_cycle_begin(CycleDev* cd, int* nCur, int n) {
   cd->nStart = n; cd->nSites = 0; cd->nextHistory = 0; cd->error = 0;
   cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; cd->nNew = 0;
@@ -871,6 +911,8 @@ struct sb_engine {
   int* dRankCounts = nullptr; int* hRankCounts = nullptr;
   double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
+  int maxSegMin = 256, loneMode = 1, cellCache = 1;
+  long long* dProfRounds = nullptr;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
   double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
@@ -920,6 +962,7 @@ static int ensureCapacity(sb_engine* h, int maxPop) {
   CUDA_OK(cudaMalloc(&h->dHProd, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHAbs, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&h->dHLeak, sizeof(double) * cap)); CUDA_OK(cudaMalloc(&h->dHScat, sizeof(double) * cap));
   CUDA_OK(cudaMalloc(&h->dRn, sizeof(unsigned long long) * cap));
+  CUDA_OK(cudaDeviceSynchronize());            // allocBank's null-stream memsets land before the engine stream uses the banks
   h->cap = cap; h->cur = 0; h->nCur = 0;
   return 0;
 }
@@ -998,7 +1041,7 @@ static int buildBlob(sb_engine* h) {
       U.type = sbh::HU_COLD;
       if (t == SB_UNI_LAT) {
         U.type = sbh::HU_LAT;
-        for (int i = 0; i < 3; ++i) { U.pitch[i] = dp[12 + i]; U.corner[i] = dp[15 + i]; U.abar[i] = dp[18 + i]; U.inv[i] = 1.0 / dp[12 + i]; U.hp[i] = 0.5 * dp[12 + i]; }
+        for (int i = 0; i < 3; ++i) { U.ph[i].x = dp[12 + i]; U.ci[i].x = dp[15 + i]; U.ab[i] = dp[18 + i]; U.ci[i].y = 1.0 / dp[12 + i]; U.ph[i].y = 0.5 * dp[12 + i]; }
         U.n0 = ip[2]; U.n1 = ip[3]; U.n2 = ip[4]; U.outID = ip[5]; U.aux = ip[7];
         if (ip[6] == 1) U.flags |= sbh::HF_OFFALL; else if (ip[6] == 2) U.flags |= sbh::HF_OFFMAP;
         if (ip[4] == 1 && dp[14] >= 2.0 * INF && dp[17] == -INF) U.flags |= sbh::HF_LAT2D;
@@ -1009,14 +1052,20 @@ static int buildBlob(sb_engine* h) {
         if (h->gi_surfType[sidx] == SB_SURF_BOX) {
           const double* p = &h->gd_surfPar[(size_t)sidx * SB_SURF_NPAR];
           U.type = sbh::HU_ROOTBOX;
-          for (int i = 0; i < 3; ++i) { U.corner[i] = p[i]; U.pitch[i] = p[3 + i]; }
-          U.abar[0] = p[6];
+          for (int i = 0; i < 3; ++i) { U.ci[i].x = p[i]; U.ph[i].x = p[3 + i]; }
+          U.ab[0] = p[6];
         }
       }
     }
     L.oUni = put(hb, unis); L.oGraph = put(hb, graph); L.oAuxD = put(hb, h->gd_auxD); L.oAuxI = put(hb, h->gi_auxI);
     L.oXs = put(hb, h->xs); L.oP0 = put(hb, h->P0); L.oProd = put(hb, h->prod); L.oP1 = h->isP1 ? put(hb, h->P1) : L.oP0;
-    L.oChi = put(hb, h->chi); L.oFissile = put(hb, h->fissile);
+    {
+      std::vector<int> first((size_t)h->nMat * h->nG, h->nG);
+      for (size_t row = 0; row < first.size(); ++row)
+        for (int g = 0; g < h->nG; ++g) if (h->P0[row * h->nG + g] != 0.0) { first[row] = g; break; }
+      L.oP0First = put(hb, first);
+    }
+    L.oFissile = put(hb, h->fissile);
     std::vector<double> majT(h->nG), majInv(h->nG);
     for (int g = 0; g < h->nG; ++g) { majT[g] = std::fmax(h->majorant[g] + 0.0, h->collisionXS); majInv[g] = 1.0 / majT[g]; }   // getTrackingXS(MAJORANT_XS)
     L.oMajT = put(hb, majT); L.oMajInv = put(hb, majInv);
@@ -1065,9 +1114,17 @@ static int buildBlob(sb_engine* h) {
     CUDA_OK(cudaMemcpy(h->dHot, hb.data(), hb.size(), cudaMemcpyHostToDevice));
     // shared-memory staging when two CTAs per SM fit beside each other (227 KB per SM on sm_100)
     h->useSmem = (L.bytes <= 72 * 1024) ? 1 : 0;
-    if (h->useSmem) {
-      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
-      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+    {
+      const int hotB = h->useSmem ? L.bytes : 0;
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbh::histScratchBytes(256)));
+      if (getenv("SB_DEBUG_OCC")) {
+        int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbh::k_histories<true, 2>, 256, hotB + sbh::histScratchBytes(256));
+        fprintf(stderr, "k_histories<true,2>: %d CTAs per SM with %d bytes of dynamic shared memory\n", nb, hotB + sbh::histScratchBytes(256));
+      }
     }
   }
   for (int ph = 0; ph < 2; ++ph) {
@@ -1079,6 +1136,9 @@ static int buildBlob(sb_engine* h) {
     CUDA_OK(cudaMemset(h->dCsum[ph], 0, sizeof(double) * nb)); CUDA_OK(cudaMemset(h->dCsum2[ph], 0, sizeof(double) * nb));
     h->batchN[ph] = 0;
   }
+  // the uploads and memsets above ran on the legacy null stream from pageable memory; the engine's stream is
+  // non-blocking and does not order itself after them, so make them complete before any kernel can be enqueued
+  CUDA_OK(cudaDeviceSynchronize());
   h->blobDirty = false;
   return 0;
 }
@@ -1115,7 +1175,7 @@ int sb_create(sb_engine** out, int device) {
   cudaMallocHost(&h->hCd, sizeof(CycleDev));
   cudaMalloc(&h->dPartial, sizeof(RedOut) * RED_BLOCKS);
   {                                        // LCG jump table for per-history seeding: maps for stride*i*1024^level
-    std::vector<ulonglong2> tab(3 * 1024);
+    std::vector<ulonglong2> tab(3 * 1024 + 32);
     for (int lvl = 0; lvl < 3; ++lvl)
       for (int i = 0; i < 1024; ++i) {
         int64_t k = RNG_STRIDE * ((int64_t)i << (10 * lvl));
@@ -1123,6 +1183,10 @@ int sb_create(sb_engine** out, int device) {
         uint64_t g = (rng_skip(1ULL, k) - c) & RNG_MASK;     // f^k(1) - C_k = G_k
         tab[lvl * 1024 + i] = make_ulonglong2(g, c);
       }
+    for (int j = 0; j < 32; ++j) {                            // j + 1 consecutive draws as one map (draw window of sb_hist.cuh)
+      uint64_t c = rng_skip(0ULL, j + 1);
+      tab[3 * 1024 + j] = make_ulonglong2((rng_skip(1ULL, j + 1) - c) & RNG_MASK, c);
+    }
     cudaMalloc(&h->dSeedTab, sizeof(ulonglong2) * tab.size());
     cudaMemcpy(h->dSeedTab, tab.data(), sizeof(ulonglong2) * tab.size(), cudaMemcpyHostToDevice);
   }
@@ -1130,7 +1194,11 @@ int sb_create(sb_engine** out, int device) {
   cudaMalloc(&h->dNcur, sizeof(int)); cudaMalloc(&h->dKsum, 8 * sizeof(double)); cudaMalloc(&h->dNd, sizeof(NormDev));
   if (const char* e = getenv("SB_REFILL_MIN")) h->refillMin = std::max(1, atoi(e));     // tuning knobs (measurement only)
   if (const char* e = getenv("SB_BLOCKS_PER_SM")) h->opt.blocks_per_sm = atoi(e);
+  if (const char* e = getenv("SB_MAXSEG_MIN")) h->maxSegMin = atoi(e);
+  if (const char* e = getenv("SB_LONE_MODE")) h->loneMode = atoi(e);
+  if (const char* e = getenv("SB_CELL_CACHE")) h->cellCache = atoi(e);
   cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
+  if (cudaDeviceSynchronize() != cudaSuccess) { g_globalErr = "scone_b200: device initialisation failed"; delete h; return -1; }   // null-stream uploads above
   *out = h;
   return 0;
 }
@@ -1412,6 +1480,7 @@ int sb_set_file_source(sb_engine* h, int64_t n_rows, const double* rows, int is_
   cudaFree(h->dFileSrc); h->dFileSrc = nullptr;
   CUDA_OK(cudaMalloc(&h->dFileSrc, sizeof(double) * 10 * (size_t)n_rows));
   CUDA_OK(cudaMemcpy(h->dFileSrc, rows, sizeof(double) * 10 * (size_t)n_rows, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaDeviceSynchronize());
   h->nFileSrc = n_rows; h->fileSrcMG = is_mg != 0;
   return 0;
 }
@@ -1470,9 +1539,13 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   for (int i = 0; i < h->userKeff[phase].n; ++i) if (h->userKeff[phase].kind[i] == SB_CLERK_KEFF_IMPLICIT) impScores = 1;
   a.impScores = impScores;
   a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
-  a.refillMin = h->refillMin;
-  const int threads = 256;
+#ifdef SB_PROFILE_ROUNDS
+  { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * 40 * 8 * 1024); } cudaMemsetAsync(dProf, 0, 8 * 40 * 8 * 1024, st); a.prof = dProf; h->dProfRounds = dProf; }
+#endif
+  a.refillMin = h->refillMin; a.maxSegMin = h->maxSegMin; a.loneMode = h->loneMode; a.cellCache = h->cellCache;
+  int threads = 256;
   const int bps = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 2;
+  if (const char* e = getenv("SB_HIST_THREADS")) threads = atoi(e);
   int blocks = h->numSM * bps;
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
@@ -1540,9 +1613,16 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     if (cfg && !strcmp(cfg, "async")) sbt::k_histories_track<128, 4, false><<<std::min(h->numSM * 4, (n + 127) / 128), 128, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
     else sbt::k_histories_track<512, 1, true><<<std::min(h->numSM, (n + 511) / 512), 512, h->trackSmem ? h->M.blobBytes : 0, st>>>(t);
   } else
-  if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, threads, h->hot.bytes, st>>>(a);
-  else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, threads, h->hot.bytes, st>>>(a);
-  else sbh::k_histories<false, 2><<<blocks, threads, 0, st>>>(a);
+  {
+    const int hotB = h->useSmem ? h->hot.bytes : 0;
+    if (h->useSmem && bps == 1 && threads == 384) sbh::k_histories<true, 1, 384><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
+    else if (h->useSmem && bps == 1) sbh::k_histories<true, 1><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
+    else if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
+    else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
+    else sbh::k_histories<false, 2><<<blocks, 256, sbh::histScratchBytes(256), st>>>(a);
+    k_finish_sites<<<gridFor(h, n, 128), 128, 0, st>>>(h->M, h->dBlob, raw, h->dCd, h->cap);     // the sites' directions and groups
+    h->launches++;
+  }
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK1, st));
   h->launches++;
 
@@ -1932,6 +2012,7 @@ int sb_load_ce_data(sb_engine* h, const sb_ce_flat* d) {
   CUDA_OK(cudaSetDevice(h->device));
   h->err.clear();
   if (sbce::ceBuild(h->ce, d, h->err)) return -1;
+  CUDA_OK(cudaDeviceSynchronize());                       // ceBuild uploads on the null stream
   sbce::k_ce_majorant<<<std::max(1, std::min((h->ce.dev.nUnion + 127) / 128, h->numSM * 8)), 128, 0, h->stream>>>(h->ce.dev, (double*)h->ce.dev.uMaj);
   h->launches++;
   CUDA_OK(cudaMemcpyAsync(h->ce.uMaj.data(), h->ce.dev.uMaj, sizeof(double) * h->ce.uMaj.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -1965,6 +2046,7 @@ int sb_load_ce_model(sb_engine* h, const sb_ce_model* m) {
   std::vector<int> active(m->active_mats, m->active_mats + std::max(0, m->n_active));
   if (active.empty()) { h->err = "sb_load_ce_model: no active material"; return -1; }
   if (sbce::ceBuild(h->ce, &f, h->err, &active)) return -1;
+  CUDA_OK(cudaDeviceSynchronize());                       // ceBuild uploads on the null stream; the engine stream does not wait for it
   sbce::k_ce_majorant<<<std::max(1, std::min((h->ce.dev.nUnion + 127) / 128, h->numSM * 8)), 128, 0, h->stream>>>(h->ce.dev, (double*)h->ce.dev.uMaj);
   h->launches++;
   CUDA_OK(cudaMemcpyAsync(h->ce.uMaj.data(), h->ce.dev.uMaj, sizeof(double) * h->ce.uMaj.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -1974,6 +2056,7 @@ int sb_load_ce_model(sb_engine* h, const sb_ce_model* m) {
   D.xs = h->ce.dev;
   D.tape = ceModelUpload(h, tape); D.nuc = ceModelUpload(h, recs); D.mt = ceModelUpload(h, mts);
   if (!D.tape || !D.nuc || !D.mt) return -1;
+  CUDA_OK(cudaDeviceSynchronize());
   D.minE = m->min_energy; D.maxE = m->max_energy; D.threshE = m->thresh_energy; D.threshA = m->thresh_mass; D.sourceE = m->source_energy;
   D.eLo = h->ce.dev.eMin; D.eHi = h->ce.dev.eMax;
   if (!(D.minE >= 0.0) || !(D.maxE >= 0.0) || D.minE >= D.maxE || D.threshE < 0 || D.threshA < 0) { h->err = "sb_load_ce_model: invalid neutronCEstd settings (minEnergy / maxEnergy / thresholds)"; return -1; }
@@ -2163,6 +2246,22 @@ int sb_math_query(int64_t n, const double* x, double* lg, double* sn, double* cs
   cudaMemcpy(lg, dl, 8 * n, cudaMemcpyDeviceToHost); cudaMemcpy(sn, dsn, 8 * n, cudaMemcpyDeviceToHost); cudaMemcpy(cs, dcs, 8 * n, cudaMemcpyDeviceToHost);
   cudaFree(dx); cudaFree(dl); cudaFree(dsn); cudaFree(dcs);
   if (e != cudaSuccess) { g_globalErr = cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
+#ifdef SB_PROFILE_ROUNDS
+int sb_profile_rounds(sb_engine* h, long long* out) { cudaStreamSynchronize(h->stream); return cudaMemcpy(out, h->dProfRounds, 8 * 40 * 8 * 1024, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
+#endif
+int sb_fastmath_check(int64_t n, uint64_t seed, int exp_span, int64_t* mismatches) {
+  unsigned long long* d = nullptr;
+  if (n < 1 || exp_span < 0 || exp_span > 500 || !mismatches) { g_globalErr = "sb_fastmath_check: invalid arguments"; return -1; }
+  if (cudaMalloc(&d, 8) != cudaSuccess) { g_globalErr = "sb_fastmath_check: no CUDA device / allocation failed"; return -1; }
+  cudaMemset(d, 0, 8);
+  k_fastmath_check<<<1184, 256>>>(n, seed & RNG_MASK, exp_span, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long hbad = 0; cudaMemcpy(&hbad, d, 8, cudaMemcpyDeviceToHost); cudaFree(d);
+  if (e != cudaSuccess) { g_globalErr = cudaGetErrorString(e); return -1; }
+  *mismatches = (int64_t)hbad;
   return 0;
 }
 

@@ -28,18 +28,20 @@ using namespace sbd;
 enum { HU_ROOTBOX = 1, HU_PIN = 2, HU_LAT = 3, HU_COLD = 4 };
 enum { HF_ROT = 1, HF_GLOBAL = 2, HF_LAT2D = 4, HF_OFFALL = 8, HF_OFFMAP = 16, HF_ORG0 = 32 };
 
-// one universe, 192 bytes.  ROOTBOX: corner = box origin, pitch = halfwidth, abar[0] = surface tolerance
+// one universe, 192 bytes, laid out for 16-byte shared-memory loads.  Per axis a: ci[a] = {corner, 1/pitch},
+// ph[a] = {pitch, pitch/2}, ab[a] = a_bar.  ROOTBOX: ci[a].x = box origin, ph[a].x = halfwidth, ab[0] = surface tolerance
 struct __align__(16) HUni {
   int type, flags, n0, n1, n2, outID, aux, pad;
-  double org[3];
-  double pitch[3], corner[3], abar[3], inv[3], hp[3];
-  double pad2[2];
+  double org[3], pad0;
+  double2 ci[3];
+  double2 ph[3];
+  double ab[3], pad1;
 };
 static_assert(sizeof(HUni) == 192, "HUni layout");
 
 struct HotLayout {
   int bytes;
-  int oUni, oGraph, oAuxD, oAuxI, oXs, oP0, oProd, oP1, oChi, oFissile, oMajT, oMajInv;
+  int oUni, oGraph, oAuxD, oAuxI, oXs, oP0, oProd, oP1, oP0First, oFissile, oMajT, oMajInv;
   int oClerk[2], nClerk[2];
   int oScoreMask[2];                     // per phase: [nMat*nG + 1] bytes, 1 if any clerk can score a non-zero in (mat, G); last = void
   int nG, nMat, isP1, rootIdx, borderS, borderIsBox;
@@ -73,18 +75,33 @@ struct HistArgs {
   double* bins; int phase; int impScores;      // impScores: keffImplicitClerk scores wanted (active phase, or a user clerk)
   uint64_t rng0; int histOffset; double k_eff;
   CycleDev* cd; int refillMin;
+  int maxSegMin;                         // histories longer than this report their length (cd->maxSeg)
+  long long* prof;                       // SB_PROFILE_ROUNDS builds: per-warp round timings
+  int cellCache;                         // 1: placement resumes below the lattice cell of the previous site when the new one is safely inside it
+  int loneMode;                          // 1: a history left alone in its warp gets its random numbers from the warp's draw window
 };
 
 // ------------------------------------------------------------------------------------------------
 // RNG: same stream as sb_rng.h; the int64 -> double conversion is done with two exact magic-number
 // subtractions (hi*2^32 + lo rounded once = round-to-nearest of the 63-bit integer, as I2F does)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rngGet(uint64_t& s) {
-  s = (RNG_G * s + 1ULL) & RNG_MASK;
+__device__ __forceinline__ double rngReal(uint64_t s) {
   // the same with every term scaled by 2^-63 (exact): (2^21 + hi*2^-31) - (2^21 + 2^-11) + (2^-11 + lo*2^-63)
   double hi = __hiloint2double(0x41400000, (int)(s >> 32));
   double lo = __hiloint2double(0x3f400000, (int)(s & 0xffffffffu));
   return (hi - 2097152.00048828125) + lo;                                // exact difference; the sum rounds once = RN(s) * 2^-63
+}
+__device__ __forceinline__ double rngGet(uint64_t& s) {
+  s = (RNG_G * s + 1ULL) & RNG_MASK;
+  return rngReal(s);
+}
+// state after K draws as ONE affine map of the current state (K compile-time): the draws of an event whose order is
+// fixed are then independent of one another instead of a chain of multiplications
+__host__ __device__ constexpr uint64_t rngJumpA(int k) { uint64_t a = 1; for (int i = 0; i < k; ++i) a = (a * RNG_G) & RNG_MASK; return a; }
+__host__ __device__ constexpr uint64_t rngJumpC(int k) { uint64_t c = 0; for (int i = 0; i < k; ++i) c = (c * RNG_G + 1ULL) & RNG_MASK; return c; }
+template <int K> __device__ __forceinline__ uint64_t rngJump(uint64_t s) {
+  constexpr uint64_t A = rngJumpA(K), C = rngJumpC(K);
+  return (A * s + C) & RNG_MASK;
 }
 __device__ __forceinline__ uint64_t rngSeed(const ulonglong2* tab, uint64_t s, unsigned n) {
 #pragma unroll
@@ -104,15 +121,14 @@ __device__ __noinline__ int coldFindCell(const char* blob, int ui, double r0, do
   const Tables T = bind(M, blob);
   return uniFindCellCold(T, ui, r0, r1, r2, u0, u1, u2);
 }
-// universe%enter rotation (universe_inter.f90:400-424)
-__device__ __noinline__ void coldRotate(const char* blob, int ui, double* r, double* u) {
+// a rotated universe on the way down (universe_inter.f90:400-424): the whole placement is redone by the generic search
+// over the model blob, which carries the rotated direction from level to level; returns the material (nesting overflow: -1)
+__device__ __noinline__ int coldPlace(const char* blob, double r0, double r1, double r2, double u0, double u1, double u2) {
   const Model& M = blobModel(blob);
-  const double* m = (const double*)(blob + M.oUniDpar) + ui * SB_UNI_NDPAR + 3;
-  double a[3] = {r[0], r[1], r[2]}, b[3] = {u[0], u[1], u[2]};
-  for (int i = 0; i < 3; ++i) {
-    r[i] = m[3 * i] * a[0] + m[3 * i + 1] * a[1] + m[3 * i + 2] * a[2];
-    u[i] = m[3 * i] * b[0] + m[3 * i + 1] * b[1] + m[3 * i + 2] * b[2];
-  }
+  const Tables T = bind(M, blob);
+  const double r[3] = {r0, r1, r2}, u[3] = {u0, u1, u2};
+  int mat, uid;
+  return geomPlace(M, T, r, u, mat, uid) ? mat : -1;
 }
 // geometryStd%teleport, boundary part: transformBC of the border surface
 __device__ __noinline__ void coldTransformBC(const char* blob, double* r, double* u) {
@@ -136,6 +152,42 @@ __device__ __forceinline__ double floorDiv(double d, double pitch, double inv) {
   double frac = t - f;
   if (!(fabs(t) < 1.0e6) || frac < 1.0e-7 || frac > 1.0 - 1.0e-7) f = floor(d / pitch);
   return f;
+}
+// true if floor(d * inv) may differ from floor(d / pitch): the product is within 1e-7 of an integer, huge or NaN
+__device__ __forceinline__ bool floorUnsafe(double t, double fl) {
+  return !(fabs((t - fl) - 0.5) < 0.5 - 1.0e-7) || !(fabs(t) < 1.0e6);
+}
+
+// ------------------------------------------------------------------------------------------------
+// draw window of a history that is alone in its warp (the tail of every cycle: a few long histories, one per warp).
+// The 31 idle lanes compute the NEXT 32 numbers of the history's stream at once - state, uniform, -log, sin / cos of
+// the azimuth 2 pi xi, sin of the polar angle of mu = 2 xi - 1 - and the history picks what the reference's draw order
+// asks for: the random-number arithmetic, the logarithm and the trigonometry leave the history's dependent chain.
+// Every value is what the inline code computes from the same state, so histories do not change.
+// ------------------------------------------------------------------------------------------------
+constexpr int WIN = 32;
+constexpr int WIN_ROUND = 12;              // draws a round may take from the window before the generic fallback: flight 2 + channel 3 + one site 3 + scattering 3 (+1)
+struct DrawWin {
+  unsigned long long st[WIN];
+  double xi[WIN], nlog[WIN], sn[WIN], cs[WIN], A[WIN];
+};
+
+// ------------------------------------------------------------------------------------------------
+// cell cache of the placement. A history that scatters in a moderator collides again a fraction of a pitch away: most
+// tentative collision sites lie in the lattice cell of the previous one. Under a root box, up to two nested 2-D lattices
+// (no rotation, no origin shift) the search is then known in advance: the lane keeps, from its last full search, the
+// offsets (cellOffset of each lattice level), the universe filling the innermost lattice cell and a SAFE BOX in root
+// coordinates - the intersection of the root box and of the lattice cells found, shrunk by GC_MARGIN, far more than the
+// surface tolerances and the rounding of the index arithmetic. A point strictly inside the safe box gets the same lattice
+// indices from latUniverse%findCell at every level (no face adjustment can trigger), so its local coordinates are the
+// same two subtractions r - offset_A - offset_B the full search makes, and the search resumes at the cached universe.
+// Anything else (near a face, another cell, 3-D lattices, rotated / shifted universes) takes the full search.
+// ------------------------------------------------------------------------------------------------
+constexpr double GC_MARGIN = 1.0e-8;
+
+// dynamic shared memory of k_histories beside the hot blob, per thread count
+__host__ __device__ constexpr int histScratchBytes(int threads) {
+  return (int)sizeof(DrawWin) * (threads / 32) + threads * (3 * 16 + 2 * 16 + 16 + 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -168,9 +220,16 @@ __device__ __forceinline__ void stageHot(char* smem, const char* gsrc, int bytes
   }
 }
 
-template <bool SMEM, int BPS>
-__global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
+template <bool SMEM, int BPS, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
+  // dynamic shared memory: [hot blob (SMEM)] [draw windows] [cell caches] [scatter scores]
+  char* const sx = g_hotSmem + (SMEM ? a.L.bytes : 0);
+  DrawWin* const s_win = (DrawWin*)sx;                                          // one per warp
+  double2 (* const s_gcB)[THREADS] = (double2 (*)[THREADS])(sx + sizeof(DrawWin) * (THREADS / 32));   // cell cache: safe box {lo, hi} per axis
+  double2 (* const s_gcO)[THREADS] = s_gcB + 3;                                 // offsets of the outer (A) and inner (B) lattice level, {x, y}
+  int4* const s_gcI = (int4*)(s_gcO + 2);                                       // universe to resume at, its rootID, its level
+  double* const s_scat = (double*)(s_gcI + THREADS);                            // keffImplicitClerk%reportOutColl score of the history (non-zero only with multiplicities)
   const char* hb;
   if (SMEM) { stageHot(g_hotSmem, a.hot, a.L.bytes, &s_bar); hb = g_hotSmem; }
   else hb = a.hot;
@@ -182,7 +241,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
   const double* const P0 = (const double*)(hb + a.L.oP0);
   const double* const prodT = (const double*)(hb + a.L.oProd);
   const double* const P1 = (const double*)(hb + a.L.oP1);
-  const double* const chiT = (const double*)(hb + a.L.oChi);
+  const int* const p0First = (const int*)(hb + a.L.oP0First);           // per (material, group in): first non-zero term of the P0 row
   const int* const fissileT = (const int*)(hb + a.L.oFissile);
   const double* const majT = (const double*)(hb + a.L.oMajT);
   const double* const majInvT = (const double*)(hb + a.L.oMajInv);
@@ -193,121 +252,223 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
   const bool active = a.impScores != 0;
 
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned ltMask = (1u << lane) - 1u;
+#define lane ((int)(threadIdx.x & 31))
+#define ltMask ((1u << lane) - 1u)
+  DrawWin& W = s_win[threadIdx.x >> 5];
 
   bool alive = false, exhausted = false;
   int hi = -1, G = 1, mat = 0, nSite = 0, hSeg = 0;
+  int winPos = 99;                                 // < WIN only while this lane's draws come from the window
   double r0 = 0.0, r1 = 0.0, r2 = 0.0, u0 = 1.0, u1 = 0.0, u2 = 0.0;
-  double w = 0.0, w0 = 0.0, flux = 0.0, majInv = 1.0;
+  double w = 0.0, w0 = 0.0, majInv = 1.0;
   uint64_t rng = 0;
-  double sProd = 0.0, sAbs = 0.0, sScat = 0.0, sLeak = 0.0;     // sLeak: leaked weight of the history (with its secondaries in a fixed-source run)
+  double sProd = 0.0, sAbs = 0.0;                  // implicit k-eff scores of the history
+  bool leaked = false;                             // (a delta-tracking history of an eigenvalue cycle leaks at most once: its weight at that point)
   unsigned nSeg = 0, nColl = 0, nScore = 0;        // per lane, over all its histories
 
+  // leave the window for the rest of the round (code that draws through rng_get directly)
+  auto leaveWindow = [&]() {
+    if (winPos <= WIN) { if (winPos > 0) rng = W.st[winPos - 1]; winPos = WIN + 1; }
+  };
+  // fission sites: the stream position is needed as a state; the window is left (its next rebuild starts behind the sites)
+  auto leaveWindowKeep = leaveWindow;
+
+#ifdef SB_PROFILE_ROUNDS
+  long long prT[6] = {0, 0, 0, 0, 0, 0}; int prN[6] = {0, 0, 0, 0, 0, 0}; long long prT0 = clock64(); const long long prStart = prT0; int prB = -1;
+  long long prR[6][4]; for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) prR[i][j] = 0;
+  long long prS = 0;
+#define PR_MARK(j) { long long t = clock64(); prR[prB][j] += t - prS; prS = t; }
+#else
+#define PR_MARK(j)
+#endif
   for (;;) {
     // ---------------- refill dead lanes (warp-level compaction of the bank) ----------------------------
-    {
-      unsigned need = __ballot_sync(FULL, !alive);
-      if (need != 0u && !exhausted) {
-        int cnt = __popc(need);
-        if (cnt >= a.refillMin || need == FULL) {
-          int b = 0;
-          if (lane == 0) b = atomicAdd(&a.cd->nextHistory, cnt);
-          b = __shfl_sync(FULL, b, 0);
-          if (b + cnt >= a.n) exhausted = true;
-          int my = b + __popc(need & ltMask);
-          if (!alive && my < a.n) {
-            hi = my;
-            r0 = a.in.rx[hi]; r1 = a.in.ry[hi]; r2 = a.in.rz[hi];
-            u0 = a.in.ux[hi]; u1 = a.in.uy[hi]; u2 = a.in.uz[hi];
-            w = a.in.w[hi]; w0 = w; G = a.in.G[hi];
-            rng = rngSeed(a.seedTab, a.rng0, (unsigned)(a.histOffset + hi + 1));
-            // geom%placeCoord of the source site is not needed by delta tracking: the first thing the
-            // flight does is teleport + placeCoord (transportOperatorDT_class.f90:57-75)
-            majInv = majInvT[G - 1]; flux = w / majT[G - 1];
-            nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; sScat = 0.0; sLeak = 0.0;
-            alive = true;
-            need &= ~(1u << lane);
-          }
-          need = __ballot_sync(FULL, !alive);
+    unsigned need = __ballot_sync(FULL, !alive);
+#ifdef SB_PROFILE_ROUNDS
+    { long long t = clock64(); if (prB >= 0) { prT[prB] += t - prT0; prN[prB]++; } prT0 = t; }
+#endif
+    if (need != 0u && !exhausted) {
+      int cnt = __popc(need);
+      if (cnt >= a.refillMin || need == FULL) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(&a.cd->nextHistory, cnt);
+        b = __shfl_sync(FULL, b, 0);
+        if (b + cnt >= a.n) exhausted = true;
+        int my = b + __popc(need & ltMask);
+        if (!alive && my < a.n) {
+          hi = my;
+          r0 = a.in.rx[hi]; r1 = a.in.ry[hi]; r2 = a.in.rz[hi];
+          u0 = a.in.ux[hi]; u1 = a.in.uy[hi]; u2 = a.in.uz[hi];
+          w = a.in.w[hi]; w0 = w; G = a.in.G[hi];
+          rng = rngSeed(a.seedTab, a.rng0, (unsigned)(a.histOffset + hi + 1));
+          // geom%placeCoord of the source site is not needed by delta tracking: the first thing the
+          // flight does is teleport + placeCoord (transportOperatorDT_class.f90:57-75)
+          majInv = majInvT[G - 1];
+          nSite = 0; hSeg = 0; sProd = 0.0; sAbs = 0.0; leaked = false; s_scat[threadIdx.x] = 0.0;
+          s_gcB[0][threadIdx.x] = make_double2(INF, -INF);           // no cached cell yet
+          alive = true;
         }
+        need = __ballot_sync(FULL, !alive);
       }
-      if (need == FULL && exhausted) break;
+    }
+    if (need == FULL && exhausted) break;
+
+    // ---------------- a history alone in its warp: (re)build its draw window with all 32 lanes ---------
+    if (exhausted && a.loneMode && __popc(~need) == 1) {
+      const int owner = __ffs(~need) - 1;
+      if (__shfl_sync(FULL, winPos, owner) > WIN - WIN_ROUND) {
+        const uint64_t sb = __shfl_sync(FULL, rng, owner);
+        const ulonglong2 j = __ldg(a.seedTab + 3 * 1024 + lane);         // affine map of lane + 1 draws
+        const uint64_t st = (j.x * sb + j.y) & RNG_MASK;
+        const double xi = rngReal(st);
+        double sn, cs;
+        sbm::sincos(TWO_PI * xi, &sn, &cs);
+        W.st[lane] = st; W.xi[lane] = xi; W.nlog[lane] = -sbm::log(xi); W.sn[lane] = sn; W.cs[lane] = cs;
+        W.A[lane] = sinPolar(2.0 * xi - 1.0);
+        __syncwarp();
+        if (lane == owner) winPos = 0;
+      }
     }
 
+#ifdef SB_PROFILE_ROUNDS
+    { int na = __popc(~need); int wp = __shfl_sync(FULL, winPos, na ? __ffs(~need) - 1 : 0); prB = na == 1 ? (wp <= WIN ? 0 : 1) : na <= 4 ? 2 : na <= 16 ? 3 : na < 32 ? 4 : 5; }
+#endif
+#ifdef SB_PROFILE_ROUNDS
+    prS = clock64();
+#endif
     // ---------------- event: tentative flight = move + cell search + virtual/real decision -------------
     bool realColl = false, died = false;
-    double leak = 0.0;
     if (alive) {
       {
-        double distance = -sbm::log(rngGet(rng)) * majInv;
+        double nlog;
+        if (winPos < WIN - 1) { nlog = W.nlog[winPos]; winPos += 1; }
+        else {
+          leaveWindow();
+          rng = rngJump<1>(rng);
+          nlog = -sbm::log(rngReal(rng));
+        }
+        const double distance = nlog * majInv;
         r0 = r0 + distance * u0; r1 = r1 + distance * u1; r2 = r2 + distance * u2;
-        ++nSeg; ++hSeg;
+        ++hSeg;
       }
-      int uid = 0;
 #pragma unroll 1
       for (int pass = 0;; ++pass) {
         // ---- placeCoord + diveToMat ----
-        double p0 = r0, p1 = r1, p2 = r2, v0 = u0, v1 = u1, v2 = u2;
-        int ui = a.L.rootIdx - 1, rootID = 1;
-        mat = SB_UNDEF_MAT; uid = -3;
+        double p0 = r0, p1 = r1, p2 = r2;
+        double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+        int ui = a.L.rootIdx - 1, rootID = 1, lvl0 = 1;
+        // cacheable prefix of this search: 0 nothing yet, 1 root box passed, 2 / 3 one / two lattice levels passed, -1 closed
+        int gcN = a.cellCache ? 0 : -1, gcA = 0, gcB = 0; double ga0 = 0.0, ga1 = 0.0;   // gcA / gcB: the lattices passed; (ga0, ga1): cellOffset of the first when a second follows
+        {
+          const double2 b0 = s_gcB[0][threadIdx.x], b1 = s_gcB[1][threadIdx.x], b2 = s_gcB[2][threadIdx.x];
+          if (r0 > b0.x && r0 < b0.y && r1 > b1.x && r1 < b1.y && r2 > b2.x && r2 < b2.y) {      // inside the safe box of the cached cell
+            const double2 oa = s_gcO[0][threadIdx.x], ob = s_gcO[1][threadIdx.x]; const int4 gi = s_gcI[threadIdx.x];
+            p0 = r0 - oa.x; p1 = r1 - oa.y; o0 = ob.x; o1 = ob.y;
+            ui = gi.x; rootID = gi.y; lvl0 = gi.z; gcN = -1;
+          }
+        }
+        mat = SB_UNDEF_MAT;
 #pragma unroll 1
         for (int lvl = 1; lvl <= MAX_NEST; ++lvl) {
+          if (lvl < lvl0) continue;                               // a lane that resumes below joins the others at its level
           const HUni& U = uni[ui];
-          const int type = U.type, flags = U.flags;
-          if (flags & HF_ROT) {
-            double tr[3] = {p0, p1, p2}, tu[3] = {v0, v1, v2};
-            coldRotate(a.blob, ui, tr, tu);
-            p0 = tr[0]; p1 = tr[1]; p2 = tr[2]; v0 = tu[0]; v1 = tu[1]; v2 = tu[2];
+          const int4 h0 = *(const int4*)&U.type;                  // type, flags, n0, n1
+          const int type = h0.x, flags = h0.y;
+          if (gcN > 0 && !(type == HU_LAT && gcN < 3 && (flags & (HF_LAT2D | HF_ORG0 | HF_ROT | HF_GLOBAL)) == (HF_LAT2D | HF_ORG0))) {
+            // the cacheable prefix ends above this universe: remember where to resume and the safe box
+            // (o0, o1) is still the cellOffset of the last lattice passed
+            if (gcN > 1) {
+              const HUni& R = uni[a.L.rootIdx - 1]; const HUni& LA = uni[gcA];
+              const double ax = (gcN == 3) ? ga0 : o0, ay = (gcN == 3) ? ga1 : o1;              // centre of the cell of lattice A, root coordinates
+              double l0 = fmax(R.ci[0].x - R.ph[0].x, ax - LA.ph[0].y), h0x = fmin(R.ci[0].x + R.ph[0].x, ax + LA.ph[0].y);
+              double l1 = fmax(R.ci[1].x - R.ph[1].x, ay - LA.ph[1].y), h1x = fmin(R.ci[1].x + R.ph[1].x, ay + LA.ph[1].y);
+              if (gcN == 3) {
+                const HUni& LB = uni[gcB]; const double bx = ga0 + o0, by = ga1 + o1;           // centre of the cell of lattice B
+                l0 = fmax(l0, bx - LB.ph[0].y); h0x = fmin(h0x, bx + LB.ph[0].y); l1 = fmax(l1, by - LB.ph[1].y); h1x = fmin(h1x, by + LB.ph[1].y);
+              }
+              s_gcB[0][threadIdx.x] = make_double2(l0 + GC_MARGIN, h0x - GC_MARGIN); s_gcB[1][threadIdx.x] = make_double2(l1 + GC_MARGIN, h1x - GC_MARGIN);
+              s_gcB[2][threadIdx.x] = make_double2(fmax(R.ci[2].x - R.ph[2].x, -999.0) + GC_MARGIN, fmin(R.ci[2].x + R.ph[2].x, 999.0) - GC_MARGIN);   // |z| < 1000: the 2-D lattices
+              s_gcO[0][threadIdx.x] = (gcN == 3) ? make_double2(ga0, ga1) : make_double2(0.0, 0.0);
+              s_gcO[1][threadIdx.x] = make_double2(o0, o1);
+              s_gcI[threadIdx.x] = make_int4(ui, rootID, lvl, 0);
+            }
+            gcN = -1;
+          }
+          if (gcN == 2) { ga0 = o0; ga1 = o1; }                   // a second lattice follows the first: keep the first's cellOffset
+          if (lvl > 1) {                                          // local coordinates of the universe below the cell just found
+            if (flags & HF_GLOBAL) { p0 = r0; p1 = r1; p2 = r2; }
+            else { p0 = p0 - o0; p1 = p1 - o1; p2 = p2 - o2; }
+          }
+          if (flags & HF_ROT) {                                   // rare: hand the whole placement to the generic search
+            mat = coldPlace(a.blob, r0, r1, r2, u0, u1, u2);
+            if (mat == -1) { atomicMax(&a.cd->error, SB_ERR_NEST); mat = SB_UNDEF_MAT; }
+            break;
           }
           if (!(flags & HF_ORG0)) { p0 = p0 - U.org[0]; p1 = p1 - U.org[1]; p2 = p2 - U.org[2]; }
           int localID;
-          double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+          o0 = 0.0; o1 = 0.0; o2 = 0.0;
           if (type == HU_LAT) {                                   // latUniverse_class.f90:270-310
-            double f0 = floorDiv(p0 - U.corner[0], U.pitch[0], U.inv[0]) + 1.0;
-            double f1 = floorDiv(p1 - U.corner[1], U.pitch[1], U.inv[1]) + 1.0;
-            double rb0 = p0 - U.corner[0] - f0 * U.pitch[0] + U.hp[0];
-            double rb1 = p1 - U.corner[1] - f1 * U.pitch[1] + U.hp[1];
-            if (fabs(rb0) > U.abar[0] && rb0 * v0 > 0.0) f0 += (v0 < 0.0) ? -1.0 : 1.0;
-            if (fabs(rb1) > U.abar[1] && rb1 * v1 > 0.0) f1 += (v1 < 0.0) ? -1.0 : 1.0;
+            const double2 c0 = U.ci[0], c1 = U.ci[1], q0 = U.ph[0], q1 = U.ph[1];
+            const double d0 = p0 - c0.x, d1 = p1 - c1.x;
+            const double t0 = d0 * c0.y, t1 = d1 * c1.y;
+            double f0 = floor(t0), f1 = floor(t1);
+            if (floorUnsafe(t0, f0) || floorUnsafe(t1, f1)) { f0 = floor(d0 / q0.x); f1 = floor(d1 / q1.x); }
+            f0 = f0 + 1.0; f1 = f1 + 1.0;
+            const double rb0 = d0 - f0 * q0.x + q0.y;
+            const double rb1 = d1 - f1 * q1.x + q1.y;
+            if (fabs(rb0) > U.ab[0] || fabs(rb1) > U.ab[1]) {     // within the surface tolerance of a cell face: the direction decides
+              if (fabs(rb0) > U.ab[0] && rb0 * u0 > 0.0) f0 += (u0 < 0.0) ? -1.0 : 1.0;
+              if (fabs(rb1) > U.ab[1] && rb1 * u1 > 0.0) f1 += (u1 < 0.0) ? -1.0 : 1.0;
+            }
+            const int4 h1 = *(const int4*)&U.n2;                  // n2, outID, aux, pad
             double f2 = 1.0;
             const bool flat = (flags & HF_LAT2D) && fabs(p2) < 1000.0;
             if (!flat) {
-              f2 = floor((p2 - U.corner[2]) / U.pitch[2]) + 1.0;
-              double rb2 = p2 - U.corner[2] - f2 * U.pitch[2] + U.hp[2];
-              if (fabs(rb2) > U.abar[2] && rb2 * v2 > 0.0) f2 += (v2 < 0.0) ? -1.0 : 1.0;
+              const double2 c2 = U.ci[2], q2 = U.ph[2];
+              f2 = floor((p2 - c2.x) / q2.x) + 1.0;
+              double rb2 = p2 - c2.x - f2 * q2.x + q2.y;
+              if (fabs(rb2) > U.ab[2] && rb2 * u2 > 0.0) f2 += (u2 < 0.0) ? -1.0 : 1.0;
             }
-            int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
-            if (i0 <= 0 || i0 > U.n0 || i1 <= 0 || i1 > U.n1 || i2 <= 0 || i2 > U.n2) localID = U.outID;
+            const int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
+            bool doOff = false;
+            if ((unsigned)(i0 - 1) >= (unsigned)h0.z || (unsigned)(i1 - 1) >= (unsigned)h0.w || (unsigned)(i2 - 1) >= (unsigned)h1.x) localID = h1.y;
             else {
-              localID = i0 + U.n0 * (i1 - 1 + U.n1 * (i2 - 1));
-              bool doOff = (flags & HF_OFFALL) || ((flags & HF_OFFMAP) && auxI[U.aux + localID - 1] == 1);
+              localID = i0 + h0.z * (i1 - 1 + h0.w * (i2 - 1));
+              doOff = (flags & HF_OFFALL) || ((flags & HF_OFFMAP) && auxI[h1.z + localID - 1] == 1);
               if (doOff) {                                        // cellOffset (latUniverse_class.f90:381-401)
-                o0 = (f0 - 0.5) * U.pitch[0] + U.corner[0];
-                o1 = (f1 - 0.5) * U.pitch[1] + U.corner[1];
-                if (!flat) o2 = (f2 - 0.5) * U.pitch[2] + U.corner[2];
+                o0 = (f0 - 0.5) * q0.x + c0.x;
+                o1 = (f1 - 0.5) * q1.x + c1.x;
+                if (!flat) o2 = (f2 - 0.5) * U.ph[2].x + U.ci[2].x;
               }
+            }
+            if (gcN > 0) {                                        // cell cache: this lattice cell in root coordinates
+              if (flat && doOff) {                                // (the cellOffset is the centre of the cell)
+                if (gcN == 1) gcA = ui; else { gcB = ui; }
+                ++gcN;
+              } else gcN = -1;
             }
           } else if (type == HU_PIN) {                            // pinUniverse_class.f90:150-172
             double rs = p0 * p0 + p1 * p1;
-            double mul = (p0 * v0 + p1 * v1 >= 0.0) ? -1.0 : 1.0;
-            const int N = U.n0; const double* r_sq = auxD + U.aux; const double* tol = r_sq + N;
+            double mul = (p0 * u0 + p1 * u1 >= 0.0) ? -1.0 : 1.0;
+            const int N = h0.z; const double* r_sq = auxD + U.aux; const double* tol = r_sq + N;
 #pragma unroll 1
             for (localID = 1; localID <= N; ++localID) if (rs < r_sq[localID - 1] + mul * tol[localID - 1]) break;
           } else {
             localID = 0;
             if (type == HU_ROOTBOX) {                             // box evaluate + halfspace (box_class.f90:134-146)
-              double c = fmax(fmax(fabs(p0 - U.corner[0]) - U.pitch[0], fabs(p1 - U.corner[1]) - U.pitch[1]), fabs(p2 - U.corner[2]) - U.pitch[2]);
-              if (fabs(c) >= U.abar[0]) localID = (c > 0.0) ? 2 : 1;
+              double c = fmax(fmax(fabs(p0 - U.ci[0].x) - U.ph[0].x, fabs(p1 - U.ci[1].x) - U.ph[1].x), fabs(p2 - U.ci[2].x) - U.ph[2].x);
+              if (fabs(c) >= U.ab[0]) localID = (c > 0.0) ? 2 : 1;
+              if (gcN == 0 && lvl == 1 && localID == 1 && (flags & (HF_ORG0 | HF_ROT)) == HF_ORG0) {
+                gcN = 1;                                          // cell cache: the search passed a plain root box
+              }
             }
-            if (localID == 0) localID = coldFindCell(a.blob, ui, p0, p1, p2, v0, v1, v2);
+            if (gcN == 0) gcN = -1;
+            if (localID == 0) localID = coldFindCell(a.blob, ui, p0, p1, p2, u0, u1, u2);
           }
-          int2 f = graph[rootID + localID - 2];
-          if (f.x >= 0) { mat = f.x; uid = f.y; break; }
+          const int2 f = graph[rootID + localID - 2];
+          if (f.x >= 0) { mat = f.x; break; }
           if (lvl == MAX_NEST) { atomicMax(&a.cd->error, SB_ERR_NEST); break; }
           ui = -f.x - 1; rootID = f.y;
-          if (uni[ui].flags & HF_GLOBAL) { p0 = r0; p1 = r1; p2 = r2; }
-          else { p0 = p0 - o0; p1 = p1 - o1; p2 = p2 - o2; }
         }
         // ---- geometryStd%teleport: outside -> transformBC, place again (once) ----
         if (mat != SB_OUTSIDE_MAT || pass == 1 || !a.L.borderIsBox) break;
@@ -315,8 +476,8 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
         coldTransformBC(a.blob, tr, tu);
         r0 = tr[0]; r1 = tr[1]; r2 = tr[2]; u0 = tu[0]; u1 = tu[1]; u2 = tu[2];
       }
-      (void)uid;
-      if (mat == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }                     // LEAK_FATE
+      __syncwarp(__activemask()); PR_MARK(0)
+      if (mat == SB_OUTSIDE_MAT) { leaked = true; died = true; }                          // LEAK_FATE
       else if (mat >= SB_OVERLAP_MAT && mat != SB_VOID_MAT) {
         atomicMax(&a.cd->error, mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true;
       } else {
@@ -326,11 +487,15 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
         bool virt = true;
         if (!isVoid) {
           double sigmaT = x[XS_TOTAL] + 0.0;
-          if (rngGet(rng) < sigmaT * majInv) { realColl = true; virt = false; }
+          double xiAcc;                                                        // the acceptance test draws (not in void)
+          if (winPos < WIN) { xiAcc = W.xi[winPos]; winPos += 1; } else { leaveWindow(); rng = rngJump<1>(rng); xiAcc = rngReal(rng); }
+          if (xiAcc < sigmaT * majInv) { realColl = true; virt = false; }
         }
         // ---- tallyAdmin%reportInColl: collisionClerks, then keffImplicitClerk (active cycles) ----
         // (skipped when no clerk of this phase can score a non-zero value in this material and group)
         const int nC = scoreMask[isVoid ? a.L.nMat * nG : (mat - 1) * nG + (G - 1)] ? nClerk : 0;
+        // flux score w / Sigma_maj; majInv = 1 / Sigma_maj is that quotient for a particle of weight one
+        const double flux = (nC || active) ? ((w == 1.0) ? majInv : w / majT[G - 1]) : 0.0;
 #pragma unroll 1
         for (int c = 0; c < nC; ++c) {
           const DClerk& k = clerks[c];
@@ -380,12 +545,20 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
       }
     }
 
+    __syncwarp(); PR_MARK(1)
     // ---------------- event: collision, part 1 (channel + number of fission sites) --------------------
     int MT = 0, nNew = 0;
     if (realColl) {
       const double* x = xsT + ((mat - 1) * nG + (G - 1)) * 6;
-      (void)rngGet(rng);                                  // alpha-absorption test always draws (probAlpha = 0)
-      double rr = rngGet(rng);
+      const bool fissile = fissileT[mat - 1] != 0;
+      double rr, rand1 = 0.0;                             // the alpha-absorption test always draws first (probAlpha = 0)
+      if (winPos <= WIN - 3) { rr = W.xi[winPos + 1]; rand1 = W.xi[winPos + 2]; winPos += fissile ? 3 : 2; }
+      else {
+        leaveWindow();
+        const uint64_t s2 = rngJump<2>(rng), s3 = rngJump<3>(rng);
+        rr = rngReal(s2); rand1 = rngReal(s3);
+        rng = fissile ? s3 : s2;
+      }
       {                                                   // neutronMacroXSs%invert (neutronXsPackages_class.f90:211-250)
         int C = 1;
         double xs = x[XS_TOTAL] * rr - 0.0;
@@ -397,8 +570,7 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
         MT = C;                                           // 1 elastic, 2 inelastic, 3 capture, 4 fission
       }
       ++nColl;
-      if (fissileT[mat - 1] != 0) {                       // neutronMGstd implicit (:131-199)
-        double rand1 = rngGet(rng);
+      if (fissile) {                                      // neutronMGstd implicit (:131-199)
         nNew = (int)(fabs((w * x[XS_NUFISSION]) / (w0 * x[XS_TOTAL] * a.k_eff)) + rand1);
         if (nNew < 0) nNew = 0;
       }
@@ -421,61 +593,104 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
       }
     }
 
+    PR_MARK(2)
     // ---------------- collision, part 2: fission sites, then the scattered neutron --------------------
-    // one loop, one rotateVector: iterations 0..nNew-1 emit sites (fissionMG%sampleOut: mu, phi, then chi),
-    // the last iteration is the scattering itself (multiScatterMG%sampleOut: G_out, then mu, phi)
+    // The sites are written UNFINISHED: position, the parent's direction, the material, and the state of the history's
+    // stream in front of the site's three numbers. fissionMG%sampleOut (mu, phi, chi walk) and rotateVector are applied
+    // to all sites of the cycle at once by k_finish_sites, with the same arithmetic on the same numbers - they do not
+    // feed back into the history, so they leave its dependent chain (and the chains of the other lanes of the warp).
     if (realColl) {
-      const double wSite = fsign(w0, w);
-      const int nIter = nNew + (MT == 2 ? 1 : 0);
-      const int row = (mat - 1) * nG + (G - 1);
+      if (nNew > 0) {
+        const double wSite = fsign(w0, w);
+        leaveWindowKeep();                                // rng = the stream position in front of the sites
 #pragma unroll 1
-      for (int i = 0; i < nIter; ++i) {
-        const bool isScat = (i == nNew);
-        const double* cdf = isScat ? P0 + row * nG : chiT + (mat - 1) * nG;
-        double mu = 0.0, phi = 0.0, rem;
-        if (isScat) rem = rngGet(rng) * xsT[row * 6 + XS_IESCATTER];
-        else { mu = 2.0 * rngGet(rng) - 1.0; phi = TWO_PI * rngGet(rng); rem = rngGet(rng); }
+        for (int i = 0; i < nNew; ++i) {
+          if (slot >= 0) {
+            const int s = slot + i;
+            a.out.rx[s] = r0; a.out.ry[s] = r1; a.out.rz[s] = r2;
+            a.out.ux[s] = u0; a.out.uy[s] = u1; a.out.uz[s] = u2;
+            a.out.w[s] = wSite; a.out.G[s] = mat; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
+            a.out.E[s] = __longlong_as_double((long long)rng);
+          }
+          rng = rngJump<3>(rng);
+        }
+        nSite += nNew;
+      }
+      if (MT == 2) {                                        // multiScatterMG%sampleOut: G_out, then mu, phi
+        const int row = (mat - 1) * nG + (G - 1);
+        const double* cdf = P0 + row * nG;
+        double mu, A, sn, cs, rem;
+        const bool legendre = a.L.isP1 != 0;
+        if (winPos <= WIN - 3 && !legendre) {              // three numbers in the order of the reaction, all from the window
+          rem = W.xi[winPos]; mu = 2.0 * W.xi[winPos + 1] - 1.0; A = W.A[winPos + 1]; sn = W.sn[winPos + 2]; cs = W.cs[winPos + 2];
+          winPos += 3;
+        } else if (!legendre) {
+          leaveWindow();
+          const uint64_t s1 = rngJump<1>(rng), s2 = rngJump<2>(rng), s3 = rngJump<3>(rng);
+          rng = s3;
+          rem = rngReal(s1);
+          mu = 2.0 * rngReal(s2) - 1.0;
+          sbm::sincos(TWO_PI * rngReal(s3), &sn, &cs);
+          A = sinPolar(mu);
+        } else { leaveWindow(); rem = rngGet(rng); mu = 0.0; A = 0.0; sn = 0.0; cs = 1.0; }
+        rem = rem * xsT[row * 6 + XS_IESCATTER];
         int Gout = 0;
 #pragma unroll 1
-        for (int g = 1; g <= nG; ++g) { rem = rem - cdf[g - 1]; if (rem < 0.0) { Gout = g; break; } }
+        for (int g0 = p0First[row]; g0 < nG && Gout == 0; g0 += 4) {   // rem = rem - cdf(g) in the reference's order, four terms per trip;
+          // leading zero terms are skipped (x - 0 = x) and a zero term past nG leaves a non-negative remainder non-negative
+          const double c0 = cdf[g0], c1 = (g0 + 1 < nG) ? cdf[g0 + 1] : 0.0, c2 = (g0 + 2 < nG) ? cdf[g0 + 2] : 0.0, c3 = (g0 + 3 < nG) ? cdf[g0 + 3] : 0.0;
+          const double e1 = rem - c0, e2 = e1 - c1, e3 = e2 - c2, e4 = e3 - c3;
+          if (e1 < 0.0) Gout = g0 + 1;
+          else if (e2 < 0.0) Gout = g0 + 2;
+          else if (e3 < 0.0) Gout = g0 + 3;
+          else if (e4 < 0.0) Gout = g0 + 4;
+          rem = e4;
+        }
         if (Gout == 0) { atomicMax(&a.cd->error, SB_ERR_SAMPLING); Gout = G; }
-        if (isScat) {
-          if (a.L.isP1) mu = sampleLegendreP1(P1[row * nG + (Gout - 1)], rng);
-          else mu = 2.0 * rngGet(rng) - 1.0;
-          phi = TWO_PI * rngGet(rng);
+        if (legendre) {
+          mu = sampleLegendreP1(P1[row * nG + (Gout - 1)], rng);
+          sbm::sincos(TWO_PI * rngGet(rng), &sn, &cs);
+          A = sinPolar(mu);
         }
         double d[3] = {u0, u1, u2};
-        rotateVector(d, mu, phi);
-        if (isScat) {                                       // neutronMGstd inelastic (:221-252)
+        rotateVectorSC(d, mu, sn, cs, A);
+        {                                                   // neutronMGstd inelastic (:221-252)
           double w_mul = prodT[row * nG + (Gout - 1)];
           double wPre = w;
-          G = Gout;
-          majInv = majInvT[G - 1];
-          w = w * w_mul;
-          flux = w / majT[G - 1];
+          if (Gout != G || w_mul != 1.0) {
+            G = Gout;
+            majInv = majInvT[G - 1];
+            w = w * w_mul;
+          }
           u0 = d[0]; u1 = d[1]; u2 = d[2];
           double sc = fmax(w - wPre, 0.0);                   // keffImplicitClerk%reportOutColl
-          if (sc > 0.0) sScat += sc;
-        } else if (slot >= 0) {
-          int s = slot + i;
-          a.out.rx[s] = r0; a.out.ry[s] = r1; a.out.rz[s] = r2;
-          a.out.ux[s] = d[0]; a.out.uy[s] = d[1]; a.out.uz[s] = d[2];
-          a.out.w[s] = wSite; a.out.G[s] = Gout; a.out.brood[s] = hi; a.out.seq[s] = nSite + i;
+          if (sc > 0.0) s_scat[threadIdx.x] += sc;
         }
       }
-      nSite += nNew;
       if (MT == 3 || MT == 4) died = true;                   // capture / fission: history ends (ABS_FATE)
       // MT == 1 (elastic) cannot be selected for MG data (elasticScatter = 0): "Do nothing"
     }
+    __syncwarp(); PR_MARK(3)
+    if (winPos <= WIN && winPos > 0) rng = W.st[winPos - 1];  // the stream position after this round's draws from the window
 
     if (died) {
       a.nsites[hi] = nSite;
-      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = sLeak; a.hScat[hi] = sScat;
-      if (hSeg > 256) atomicMax(&a.cd->maxSeg, hSeg);
-      alive = false;
+      a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = leaked ? 0.0 + w : 0.0; a.hScat[hi] = s_scat[threadIdx.x];
+      nSeg += hSeg;
+      if (hSeg > a.maxSegMin) atomicMax(&a.cd->maxSeg, hSeg);
+      alive = false; winPos = 99;
     }
   }
 
+#ifdef SB_PROFILE_ROUNDS
+  if (lane == 0 && a.prof) {
+    long long* o = a.prof + 16 * (long long)(blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5));
+    for (int i = 0; i < 6; ++i) { o[i] = prT[i]; o[6 + i] = prN[i]; }
+    o[12] = clock64() - prStart;
+    long long* q = a.prof + 16 * 8 * 1024 + 24 * (long long)(blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5));
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) q[4 * i + j] = prR[i][j];
+  }
+#endif
   // ---------------- per-warp event counters (integers: order-independent) -----------------------------
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -487,4 +702,6 @@ __global__ void __launch_bounds__(256, BPS) k_histories(const HistArgs a) {
   }
 }
 
+#undef lane
+#undef ltMask
 }  // namespace sbh

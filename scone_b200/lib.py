@@ -11,7 +11,8 @@ class EngineError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libscone_b200.so")
+    # SB_LIBRARY: an instrumented build of the same library (profiles/round_profile.py); never a different implementation
+    return os.environ.get("SB_LIBRARY") or os.path.join(_HERE, "libscone_b200.so")
 
 
 class CycleResult(C.Structure):
@@ -63,6 +64,7 @@ def load_library():
         "sb_ce_nuclide_index": (i32, [vp, i32, i64, dp, ip]), "sb_ce_last_kernel_ms": (i32, [vp, dp]),
         "sb_rng_query": (i32, [i64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), dp]),
         "sb_math_query": (i32, [i64, dp, dp, dp, dp]),
+        "sb_fastmath_check": (i32, [i64, C.c_uint64, i32, C.POINTER(i64)]),
         # host driver (scone_b200/csrc/host/physics_package.cpp)
         "sbh_last_error": (C.c_char_p, [vp]),
         "sbh_eigen_create": (vp, [C.c_char_p, C.c_char_p, i32, i32, i32]), "sbh_eigen_destroy": (None, [vp]),

@@ -50,6 +50,16 @@ def test_deterministic_math_bit_exact(orc):
     np.testing.assert_allclose(lg[x > 0], np.log(x[x > 0]), rtol=3e-16)
 
 
+def test_fast_div_sqrt_exact():
+    """rotateVector's divisions and square roots are nvcc's own expansions of `/` and sqrt with ONE range test for
+    the group (sb_device.cuh: rcpRefined / divBy / sqrtFast): every result must be the IEEE one, bit for bit."""
+    L = scone_b200.load_library()
+    for seed, span in ((1, 3), (2, 60), (3, 500)):
+        bad = C.c_int64(-1)
+        assert L.sb_fastmath_check(200_000_000, seed, span, C.byref(bad)) == 0
+        assert bad.value == 0
+
+
 @pytest.mark.parametrize("name,src,lo,hi", [
     ("test_lat", TEST_LAT, -1.5, 1.5), ("test_cyl", TEST_CYL, -5.5, 5.5),
     ("c5g7", DECK["c5g7"], -33.0, 33.0), ("c5g7_3d", DECK["c5g7_3d"], -33.0, 70.0), ("can", DECK["can"], -7.5, 7.5)])
