@@ -1,4 +1,7 @@
-"""Round timings of the history kernel per number of histories alive in the warp (needs a library built with -DSB_PROFILE_ROUNDS)."""
+"""Where a long history's round goes (needs a library built with -DSB_PROFILE_ROUNDS: build.sh -DSB_PROFILE_ROUNDS -o ../libscone_b200_prof.so,
+run with SB_LIBRARY=.../libscone_b200_prof.so). Per lane the kernel accumulates clock64() differences per region of the rounds in which
+the lane's history was alone in its warp (with / without the draw window) or shared it with 1 - 3 others; this prints the lane that had
+the most rounds alone (the cycle's longest history) and the sum over all lanes."""
 import os, sys
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 import numpy as np, ctypes as C
@@ -9,16 +12,18 @@ pp = scone_b200.EigenPhysicsPackage(os.path.join(ROOT, "decks/c5g7/c5g7_2d"), "p
 pp.generateInitialState(); pp.cycles(False, 3)
 L, eng = pp.L, pp.engine
 L.sb_profile_rounds.argtypes = [C.c_void_p, C.c_void_p]
-names = ["lone(window)", "lone(no window)", "2-4 alive", "5-16", "17-31", "32"]
-for cyc in range(3):
+regions = ["refill+window", "draw+move", "placement", "XS+accept+scoring", "channel", "site slots", "scatter draw+group", "rotate+update+end"]
+kinds = ["alone, window", "alone, no window", "with 1-3 others"]
+for cyc in range(2):
     res = pp.cycle(True)
-    raw = np.zeros(8 * 1024 * 40, np.int64)
+    raw = np.zeros(27 * 148 * 384, np.int64)
     assert L.sb_profile_rounds(eng, raw.ctypes.data) == 0
-    buf = raw[:8 * 1024 * 16].reshape(8 * 1024, 16); reg = raw[8 * 1024 * 16:].reshape(8 * 1024, 6, 4)
-    tot = buf[:, 12]; w = int(np.argmax(tot))
-    print("cycle %d: longest history %d flights; slowest warp %d ran %.3f ms (at 1.965 GHz)" % (cyc, res.max_history_segments, w, tot[w] / 1.965e6))
-    for i, nm in enumerate(names):
-        T, N = buf[w, i], buf[w, 6 + i]
-        Ta, Na = buf[:, i].sum(), buf[:, 6 + i].sum()
-        print("   %-16s slowest warp: %5d rounds, %7.0f cycles/round (%.3f ms) | all warps: %8d rounds, %7.0f cycles/round | slowest warp per round: flight+geometry %5.0f, scoring %5.0f, channel+slots %5.0f, sites+scattering %5.0f" % (
-            nm, N, T / max(N, 1), T / 1.965e6, Na, Ta / max(Na, 1), *(reg[w, i] / max(N, 1))))
+    d = raw.reshape(-1, 27)
+    ln = int(np.argmax(d[:, 24] + d[:, 25]))
+    print("cycle %d: longest history %d flights" % (cyc, res.max_history_segments))
+    for k, nm in enumerate(kinds):
+        n1, nA = d[ln, 24 + k], d[:, 24 + k].sum()
+        if nA == 0: continue
+        print("  %-18s lane of the longest history: %4d rounds, %6.0f cycles/round | all lanes: %8d rounds, %6.0f cycles/round" % (
+            nm, n1, d[ln, 8 * k:8 * k + 8].sum() / max(n1, 1), nA, d[:, 8 * k:8 * k + 8].sum() / nA))
+        print("       " + ", ".join("%s %.0f (%.0f)" % (r, d[ln, 8 * k + j] / max(n1, 1), d[:, 8 * k + j].sum() / nA) for j, r in enumerate(regions)))

@@ -911,7 +911,7 @@ struct sb_engine {
   int* dRankCounts = nullptr; int* hRankCounts = nullptr;
   double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
-  int maxSegMin = 256, loneMode = 1, cellCache = 1;
+  int maxSegMin = 256, loneMode = 1, cellCache = 48;
   long long* dProfRounds = nullptr;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -1196,7 +1196,7 @@ int sb_create(sb_engine** out, int device) {
   if (const char* e = getenv("SB_BLOCKS_PER_SM")) h->opt.blocks_per_sm = atoi(e);
   if (const char* e = getenv("SB_MAXSEG_MIN")) h->maxSegMin = atoi(e);
   if (const char* e = getenv("SB_LONE_MODE")) h->loneMode = atoi(e);
-  if (const char* e = getenv("SB_CELL_CACHE")) h->cellCache = atoi(e);
+  if (const char* e = getenv("SB_CELL_CACHE")) h->cellCache = atoi(e) < 0 ? 0x7fffffff : atoi(e);
   cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
   if (cudaDeviceSynchronize() != cudaSuccess) { g_globalErr = "scone_b200: device initialisation failed"; delete h; return -1; }   // null-stream uploads above
   *out = h;
@@ -1540,12 +1540,15 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   a.impScores = impScores;
   a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
 #ifdef SB_PROFILE_ROUNDS
-  { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * 40 * 8 * 1024); } cudaMemsetAsync(dProf, 0, 8 * 40 * 8 * 1024, st); a.prof = dProf; h->dProfRounds = dProf; }
+  { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * 27 * 148 * 384); } cudaMemsetAsync(dProf, 0, 8 * 27 * 148 * 384, st); a.prof = dProf; h->dProfRounds = dProf; }
 #endif
   a.refillMin = h->refillMin; a.maxSegMin = h->maxSegMin; a.loneMode = h->loneMode; a.cellCache = h->cellCache;
-  int threads = 256;
-  const int bps = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 2;
+  // one CTA of 12 warps per SM (168 registers per thread, no spills) unless told otherwise: at the populations of an
+  // eigenvalue cycle the kernel's time is the chain of its longest history, not the number of resident warps
+  int threads = 384;
+  const int bps = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 1;
   if (const char* e = getenv("SB_HIST_THREADS")) threads = atoi(e);
+  if (bps != 1 || !h->useSmem) threads = 256;
   int blocks = h->numSM * bps;
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
@@ -2250,7 +2253,7 @@ int sb_math_query(int64_t n, const double* x, double* lg, double* sn, double* cs
 }
 
 #ifdef SB_PROFILE_ROUNDS
-int sb_profile_rounds(sb_engine* h, long long* out) { cudaStreamSynchronize(h->stream); return cudaMemcpy(out, h->dProfRounds, 8 * 40 * 8 * 1024, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
+int sb_profile_rounds(sb_engine* h, long long* out) { cudaStreamSynchronize(h->stream); return cudaMemcpy(out, h->dProfRounds, 8 * 27 * 148 * 384, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
 #endif
 int sb_fastmath_check(int64_t n, uint64_t seed, int exp_span, int64_t* mismatches) {
   unsigned long long* d = nullptr;

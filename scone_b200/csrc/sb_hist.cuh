@@ -77,7 +77,8 @@ struct HistArgs {
   CycleDev* cd; int refillMin;
   int maxSegMin;                         // histories longer than this report their length (cd->maxSeg)
   long long* prof;                       // SB_PROFILE_ROUNDS builds: per-warp round timings
-  int cellCache;                         // 1: placement resumes below the lattice cell of the previous site when the new one is safely inside it
+  int cellCache;                         // placement resumes below the lattice cell of the previous site when the new one is safely inside it,
+                                         // for histories older than this many flights (a huge value switches the cache off)
   int loneMode;                          // 1: a history left alone in its warp gets its random numbers from the warp's draw window
 };
 
@@ -165,7 +166,7 @@ __device__ __forceinline__ bool floorUnsafe(double t, double fl) {
 // asks for: the random-number arithmetic, the logarithm and the trigonometry leave the history's dependent chain.
 // Every value is what the inline code computes from the same state, so histories do not change.
 // ------------------------------------------------------------------------------------------------
-constexpr int WIN = 32;
+constexpr int WIN = 64;                    // two numbers per lane
 constexpr int WIN_ROUND = 12;              // draws a round may take from the window before the generic fallback: flight 2 + channel 3 + one site 3 + scattering 3 (+1)
 struct DrawWin {
   unsigned long long st[WIN];
@@ -255,6 +256,8 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
 #define lane ((int)(threadIdx.x & 31))
 #define ltMask ((1u << lane) - 1u)
   DrawWin& W = s_win[threadIdx.x >> 5];
+  uint64_t jA, jC;                                 // the affine map of lane + 1 draws (draw window)
+  { const ulonglong2 j = __ldg(a.seedTab + 3 * 1024 + lane); jA = j.x; jC = j.y; }
 
   bool alive = false, exhausted = false;
   int hi = -1, G = 1, mat = 0, nSite = 0, hSeg = 0;
@@ -274,19 +277,18 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
   auto leaveWindowKeep = leaveWindow;
 
 #ifdef SB_PROFILE_ROUNDS
-  long long prT[6] = {0, 0, 0, 0, 0, 0}; int prN[6] = {0, 0, 0, 0, 0, 0}; long long prT0 = clock64(); const long long prStart = prT0; int prB = -1;
-  long long prR[6][4]; for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) prR[i][j] = 0;
-  long long prS = 0;
-#define PR_MARK(j) { long long t = clock64(); prR[prB][j] += t - prS; prS = t; }
+  // per LANE: cycles per region of the rounds in which the lane's history was alone in the warp with its window [0..7],
+  // alone without [8..15], with 1 - 3 others [16..23]; rounds of each kind [24..26]
+  long long prR[27]; for (int i = 0; i < 27; ++i) prR[i] = 0;
+  long long prS = clock64(); int prB = -1;
+#define PR_MARK(j) { long long t = clock64(); if (alive && prB >= 0) prR[8 * prB + (j)] += t - prS; prS = t; }
 #else
 #define PR_MARK(j)
 #endif
   for (;;) {
+    PR_MARK(7)
     // ---------------- refill dead lanes (warp-level compaction of the bank) ----------------------------
     unsigned need = __ballot_sync(FULL, !alive);
-#ifdef SB_PROFILE_ROUNDS
-    { long long t = clock64(); if (prB >= 0) { prT[prB] += t - prT0; prN[prB]++; } prT0 = t; }
-#endif
     if (need != 0u && !exhausted) {
       int cnt = __popc(need);
       if (cnt >= a.refillMin || need == FULL) {
@@ -318,24 +320,25 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
       const int owner = __ffs(~need) - 1;
       if (__shfl_sync(FULL, winPos, owner) > WIN - WIN_ROUND) {
         const uint64_t sb = __shfl_sync(FULL, rng, owner);
-        const ulonglong2 j = __ldg(a.seedTab + 3 * 1024 + lane);         // affine map of lane + 1 draws
-        const uint64_t st = (j.x * sb + j.y) & RNG_MASK;
-        const double xi = rngReal(st);
-        double sn, cs;
-        sbm::sincos(TWO_PI * xi, &sn, &cs);
-        W.st[lane] = st; W.xi[lane] = xi; W.nlog[lane] = -sbm::log(xi); W.sn[lane] = sn; W.cs[lane] = cs;
-        W.A[lane] = sinPolar(2.0 * xi - 1.0);
+        uint64_t st = (jA * sb + jC) & RNG_MASK;                           // lane + 1 draws ahead, then 32 more
+#pragma unroll
+        for (int k = 0; k < WIN / 32; ++k) {
+          const int e = lane + 32 * k;
+          const double xi = rngReal(st);
+          double sn, cs;
+          sbm::sincos(TWO_PI * xi, &sn, &cs);
+          W.st[e] = st; W.xi[e] = xi; W.nlog[e] = -sbm::log(xi); W.sn[e] = sn; W.cs[e] = cs;
+          W.A[e] = sinPolar(2.0 * xi - 1.0);
+          st = rngJump<32>(st);
+        }
         __syncwarp();
         if (lane == owner) winPos = 0;
       }
     }
-
 #ifdef SB_PROFILE_ROUNDS
-    { int na = __popc(~need); int wp = __shfl_sync(FULL, winPos, na ? __ffs(~need) - 1 : 0); prB = na == 1 ? (wp <= WIN ? 0 : 1) : na <= 4 ? 2 : na <= 16 ? 3 : na < 32 ? 4 : 5; }
+    { const int na = __popc(~need); prB = (na == 1) ? (winPos <= WIN ? 0 : 1) : (na <= 4 ? 2 : -1); if (alive && prB >= 0) prR[24 + prB] += 1; }
 #endif
-#ifdef SB_PROFILE_ROUNDS
-    prS = clock64();
-#endif
+    PR_MARK(0)
     // ---------------- event: tentative flight = move + cell search + virtual/real decision -------------
     bool realColl = false, died = false;
     if (alive) {
@@ -351,6 +354,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
         r0 = r0 + distance * u0; r1 = r1 + distance * u1; r2 = r2 + distance * u2;
         ++hSeg;
       }
+      PR_MARK(1)
 #pragma unroll 1
       for (int pass = 0;; ++pass) {
         // ---- placeCoord + diveToMat ----
@@ -358,8 +362,9 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
         double o0 = 0.0, o1 = 0.0, o2 = 0.0;
         int ui = a.L.rootIdx - 1, rootID = 1, lvl0 = 1;
         // cacheable prefix of this search: 0 nothing yet, 1 root box passed, 2 / 3 one / two lattice levels passed, -1 closed
-        int gcN = a.cellCache ? 0 : -1, gcA = 0, gcB = 0; double ga0 = 0.0, ga1 = 0.0;   // gcA / gcB: the lattices passed; (ga0, ga1): cellOffset of the first when a second follows
-        {
+        // (young histories are fast neutrons with long flights: the cache only starts after a.cellCache flights)
+        int gcN = (hSeg > a.cellCache) ? 0 : -1, gcA = 0, gcB = 0; double ga0 = 0.0, ga1 = 0.0;   // gcA / gcB: the lattices passed; (ga0, ga1): cellOffset of the first when a second follows
+        if (gcN == 0) {
           const double2 b0 = s_gcB[0][threadIdx.x], b1 = s_gcB[1][threadIdx.x], b2 = s_gcB[2][threadIdx.x];
           if (r0 > b0.x && r0 < b0.y && r1 > b1.x && r1 < b1.y && r2 > b2.x && r2 < b2.y) {      // inside the safe box of the cached cell
             const double2 oa = s_gcO[0][threadIdx.x], ob = s_gcO[1][threadIdx.x]; const int4 gi = s_gcI[threadIdx.x];
@@ -476,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
         coldTransformBC(a.blob, tr, tu);
         r0 = tr[0]; r1 = tr[1]; r2 = tr[2]; u0 = tu[0]; u1 = tu[1]; u2 = tu[2];
       }
-      __syncwarp(__activemask()); PR_MARK(0)
+      PR_MARK(2)
       if (mat == SB_OUTSIDE_MAT) { leaked = true; died = true; }                          // LEAK_FATE
       else if (mat >= SB_OVERLAP_MAT && mat != SB_VOID_MAT) {
         atomicMax(&a.cd->error, mat == SB_UNDEF_MAT ? SB_ERR_UNDEF_MAT : SB_ERR_OVERLAP_MAT); died = true;
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
       }
     }
 
-    __syncwarp(); PR_MARK(1)
+    PR_MARK(3)
     // ---------------- event: collision, part 1 (channel + number of fission sites) --------------------
     int MT = 0, nNew = 0;
     if (realColl) {
@@ -576,6 +581,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
       }
     }
 
+    PR_MARK(4)
     // ---------------- warp-aggregated allocation of fission-bank slots --------------------------------
     int slot = -1;
     {
@@ -593,7 +599,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
       }
     }
 
-    PR_MARK(2)
+    PR_MARK(5)
     // ---------------- collision, part 2: fission sites, then the scattered neutron --------------------
     // The sites are written UNFINISHED: position, the parent's direction, the material, and the state of the history's
     // stream in front of the site's three numbers. fissionMG%sampleOut (mu, phi, chi walk) and rotateVector are applied
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
           sbm::sincos(TWO_PI * rngGet(rng), &sn, &cs);
           A = sinPolar(mu);
         }
+        PR_MARK(6)
         double d[3] = {u0, u1, u2};
         rotateVectorSC(d, mu, sn, cs, A);
         {                                                   // neutronMGstd inelastic (:221-252)
@@ -670,7 +677,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
       if (MT == 3 || MT == 4) died = true;                   // capture / fission: history ends (ABS_FATE)
       // MT == 1 (elastic) cannot be selected for MG data (elasticScatter = 0): "Do nothing"
     }
-    __syncwarp(); PR_MARK(3)
+    PR_MARK(7)
     if (winPos <= WIN && winPos > 0) rng = W.st[winPos - 1];  // the stream position after this round's draws from the window
 
     if (died) {
@@ -683,13 +690,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
   }
 
 #ifdef SB_PROFILE_ROUNDS
-  if (lane == 0 && a.prof) {
-    long long* o = a.prof + 16 * (long long)(blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5));
-    for (int i = 0; i < 6; ++i) { o[i] = prT[i]; o[6 + i] = prN[i]; }
-    o[12] = clock64() - prStart;
-    long long* q = a.prof + 16 * 8 * 1024 + 24 * (long long)(blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5));
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) q[4 * i + j] = prR[i][j];
-  }
+  if (a.prof) { long long* o = a.prof + 27 * ((long long)blockIdx.x * THREADS + threadIdx.x); for (int i = 0; i < 27; ++i) o[i] = prR[i]; }
 #endif
   // ---------------- per-warp event counters (integers: order-independent) -----------------------------
 #pragma unroll
