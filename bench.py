@@ -318,6 +318,8 @@ def main():
     launches = pp.launch_count() - launches0 - (args.steps if flush else 0) * 0
     msk, nl, segp, scp = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
     L.sb_profile_read(eng, C.byref(msk), C.byref(nl), C.byref(segp), C.byref(scp))
+    ms_wait, ms_tail = C.c_double(), C.c_double()
+    L.sb_profile_peer_stages(eng, C.byref(ms_wait), C.byref(ms_tail))
     L.sb_profile_enable(eng, 0)
     ms_max = maxreduce(ms_total)
     value = total_pop * args.steps / (ms_max * 1e-3)
@@ -404,6 +406,9 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "clocks": sampler.summary(),
         }
+        if world > 1:
+            line["stage_ms_rank0"] = {"histories": msk.value / max(1, nl.value), "waiting_for_every_rank_sums": ms_wait.value / args.steps,
+                                      "close_resample_balance": ms_tail.value / args.steps}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if large is not None:

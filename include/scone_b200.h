@@ -308,6 +308,10 @@ int sb_timer_begin(sb_engine* h);
 int sb_timer_end(sb_engine* h, double* ms);
 int sb_profile_enable(sb_engine* h, int on);
 int sb_profile_read(sb_engine* h, double* ms_histories, int64_t* n_launches, int64_t* n_segments, int64_t* n_scores);
+/* ranked cycles over peer memory, while profiling is enabled: accumulated device time [ms] between the end of the brood
+   ordering and the arrival of every rank's sums (waiting for the slowest rank), and of the cycle close + normSize_Repr +
+   load balancing that follow */
+int sb_profile_peer_stages(sb_engine* h, double* ms_wait, double* ms_tail);
 int sb_flush_l2(sb_engine* h, size_t bytes);
 /* page-locked host memory for the banks the caller keeps (so that uploads/downloads are true async DMA) */
 void* sb_pinned_alloc(size_t bytes);

@@ -915,6 +915,7 @@ struct sb_engine {
   long long* dProfRounds = nullptr;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
+  cudaEvent_t evP1 = nullptr, evP2 = nullptr; double msPeerWait = 0.0, msPeerTail = 0.0; bool peerStagesOpen = false;
   double msHistories = 0.0; long long nHistLaunches = 0; long long segProfiled = 0, scoreProfiled = 0;
   double* dStage = nullptr; size_t stageBytes = 0;
   // continuous-energy transport model (sb_load_ce_model)
@@ -1197,6 +1198,7 @@ int sb_create(sb_engine** out, int device) {
   if (const char* e = getenv("SB_MAXSEG_MIN")) h->maxSegMin = atoi(e);
   if (const char* e = getenv("SB_LONE_MODE")) h->loneMode = atoi(e);
   if (const char* e = getenv("SB_CELL_CACHE")) h->cellCache = atoi(e) < 0 ? 0x7fffffff : atoi(e);
+  cudaEventCreate(&h->evP1); cudaEventCreate(&h->evP2);
   cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
   if (cudaDeviceSynchronize() != cudaSuccess) { g_globalErr = "scone_b200: device initialisation failed"; delete h; return -1; }   // null-stream uploads above
   *out = h;
@@ -1675,6 +1677,11 @@ static int cycleFinish(sb_engine* h, sb_cycle_result* res) {
   if (h->profiling) {
     float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, h->evK0, h->evK1));
     h->msHistories += ms; h->nHistLaunches++; h->segProfiled += (long long)c.nSeg; h->scoreProfiled += (long long)c.nScore;
+    if (h->peerStagesOpen) {
+      CUDA_OK(cudaEventElapsedTime(&ms, h->evK1, h->evP1)); h->msPeerWait += ms;
+      CUDA_OK(cudaEventElapsedTime(&ms, h->evP1, h->evP2)); h->msPeerTail += ms;
+      h->peerStagesOpen = false;
+    }
   }
   if (res) {
     res->n_start = c.nStart; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
@@ -1880,6 +1887,7 @@ int sb_run_cycle_ranked_peer(sb_engine* h, uint64_t rng_state, int history_offse
   const unsigned long long seq = ++h->peerSeq, tmo = (unsigned long long)(h->peerTimeoutS * 1.0e9);
   const int par = (int)(seq & 1ULL), nr = h->peerRanks;
   k_peer_post_wait<<<1, PEER_MAX, 0, st>>>(h->peerPtrs, nr, h->peerRank, seq, h->dKsum, h->dKsumTot, h->dPlan, h->dCd, h->cap, tmo);
+  if (h->profiling) CUDA_OK(cudaEventRecord(h->evP1, st));
   if (cycleCloseEnqueue(h, h->dKsumTot)) return -1;
   {  // normSize_Repr with the global sizes taken from the plan on the device (resampleEnqueue with host-known sizes otherwise)
     Bank& sorted = h->bank[(h->cur + 2) % 3]; Bank& dst = h->bank[(h->cur + 1) % 3];
@@ -1910,6 +1918,7 @@ int sb_run_cycle_ranked_peer(sb_engine* h, uint64_t rng_state, int history_offse
     k_peer_splice<<<gl, 256, 0, st>>>(h->peerPtrs, h->dPlan, dst, sorted, h->peerCap, par, h->dCd);
     h->launches += 20;
   }
+  if (h->profiling) { CUDA_OK(cudaEventRecord(h->evP2, st)); h->peerStagesOpen = true; }
   CUDA_OK(cudaMemcpyAsync(h->hPlan, h->dPlan, sizeof(PeerPlan), cudaMemcpyDeviceToHost, st));
   if (cycleFinish(h, res)) return -1;                      // the one synchronisation
   if (h->hCd->nSites <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
@@ -1971,10 +1980,11 @@ int sb_tally_last_bins(sb_engine* h, int phase, double* bins) {
 }
 
 // ---- measurement -----------------------------------------------------------------------------------
-int sb_profile_enable(sb_engine* h, int on) { h->profiling = on != 0; h->msHistories = 0.0; h->nHistLaunches = 0; h->segProfiled = 0; h->scoreProfiled = 0; return 0; }
+int sb_profile_enable(sb_engine* h, int on) { h->profiling = on != 0; h->msPeerWait = 0.0; h->msPeerTail = 0.0; h->msHistories = 0.0; h->nHistLaunches = 0; h->segProfiled = 0; h->scoreProfiled = 0; return 0; }
 int sb_profile_read(sb_engine* h, double* ms_histories, int64_t* n_launches, int64_t* n_segments, int64_t* n_scores) {
   *ms_histories = h->msHistories; *n_launches = h->nHistLaunches; *n_segments = h->segProfiled; *n_scores = h->scoreProfiled; return 0;
 }
+int sb_profile_peer_stages(sb_engine* h, double* ms_wait, double* ms_tail) { *ms_wait = h->msPeerWait; *ms_tail = h->msPeerTail; return 0; }
 int sb_timer_begin(sb_engine* h) { CUDA_OK(cudaSetDevice(h->device)); CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaEventRecord(h->evT0, h->stream)); return 0; }
 int sb_timer_end(sb_engine* h, double* ms) {
   CUDA_OK(cudaSetDevice(h->device));

@@ -188,7 +188,7 @@ constexpr double GC_MARGIN = 1.0e-8;
 
 // dynamic shared memory of k_histories beside the hot blob, per thread count
 __host__ __device__ constexpr int histScratchBytes(int threads) {
-  return (int)sizeof(DrawWin) * (threads / 32) + threads * (3 * 16 + 2 * 16 + 16 + 8);
+  return (int)sizeof(DrawWin) * (threads / 32) + threads * (3 * 16 + 3 * 16 + 16 + 16 + 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,9 +228,10 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
   char* const sx = g_hotSmem + (SMEM ? a.L.bytes : 0);
   DrawWin* const s_win = (DrawWin*)sx;                                          // one per warp
   double2 (* const s_gcB)[THREADS] = (double2 (*)[THREADS])(sx + sizeof(DrawWin) * (THREADS / 32));   // cell cache: safe box {lo, hi} per axis
-  double2 (* const s_gcO)[THREADS] = s_gcB + 3;                                 // offsets of the outer (A) and inner (B) lattice level, {x, y}
-  int4* const s_gcI = (int4*)(s_gcO + 2);                                       // universe to resume at, its rootID, its level
-  double* const s_scat = (double*)(s_gcI + THREADS);                            // keffImplicitClerk%reportOutColl score of the history (non-zero only with multiplicities)
+  double2 (* const s_gcO)[THREADS] = s_gcB + 3;                                 // offsets of the outer (A) and inner (B) lattice level, {x, y}; origin of the cached universe
+  int4* const s_gcI = (int4*)(s_gcO + 3);                                       // universe to resume at, its rootID, its level
+  int4* const s_gcP = s_gcI + THREADS;                                          // if that universe is a plain pin: position of its radii, their number, has-origin flag (else -1)
+  double* const s_scat = (double*)(s_gcP + THREADS);                            // keffImplicitClerk%reportOutColl score of the history (non-zero only with multiplicities)
   const char* hb;
   if (SMEM) { stageHot(g_hotSmem, a.hot, a.L.bytes, &s_bar); hb = g_hotSmem; }
   else hb = a.hot;
@@ -360,21 +361,35 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
         // ---- placeCoord + diveToMat ----
         double p0 = r0, p1 = r1, p2 = r2;
         double o0 = 0.0, o1 = 0.0, o2 = 0.0;
-        int ui = a.L.rootIdx - 1, rootID = 1, lvl0 = 1;
+        int ui = a.L.rootIdx - 1, rootID = 1, lvl0 = 1, pinMat = -1;
         // cacheable prefix of this search: 0 nothing yet, 1 root box passed, 2 / 3 one / two lattice levels passed, -1 closed
         // (young histories are fast neutrons with long flights: the cache only starts after a.cellCache flights)
         int gcN = (hSeg > a.cellCache) ? 0 : -1, gcA = 0, gcB = 0; double ga0 = 0.0, ga1 = 0.0;   // gcA / gcB: the lattices passed; (ga0, ga1): cellOffset of the first when a second follows
         if (gcN == 0) {
           const double2 b0 = s_gcB[0][threadIdx.x], b1 = s_gcB[1][threadIdx.x], b2 = s_gcB[2][threadIdx.x];
           if (r0 > b0.x && r0 < b0.y && r1 > b1.x && r1 < b1.y && r2 > b2.x && r2 < b2.y) {      // inside the safe box of the cached cell
-            const double2 oa = s_gcO[0][threadIdx.x], ob = s_gcO[1][threadIdx.x]; const int4 gi = s_gcI[threadIdx.x];
+            const double2 oa = s_gcO[0][threadIdx.x], ob = s_gcO[1][threadIdx.x], og = s_gcO[2][threadIdx.x];
+            const int4 gi = s_gcI[threadIdx.x], gp = s_gcP[threadIdx.x];
             p0 = r0 - oa.x; p1 = r1 - oa.y; o0 = ob.x; o1 = ob.y;
             ui = gi.x; rootID = gi.y; lvl0 = gi.z; gcN = -1;
+            if (gp.x >= 0) {                                      // the cached universe is a plain pin: pinUniverse%findCell right here
+              double q0 = p0 - o0, q1 = p1 - o1;
+              if (gp.z) { q0 = q0 - og.x; q1 = q1 - og.y; }       // universe%enter: its origin
+              const double rs = q0 * q0 + q1 * q1;
+              const double mul = (q0 * u0 + q1 * u1 >= 0.0) ? -1.0 : 1.0;
+              const int N = gp.y; const double* r_sq = auxD + gp.x; const double* tol = r_sq + N;
+              int localID;
+#pragma unroll 1
+              for (localID = 1; localID <= N; ++localID) if (rs < r_sq[localID - 1] + mul * tol[localID - 1]) break;
+              const int2 f = graph[rootID + localID - 2];
+              if (f.x >= 0) pinMat = f.x;                          // (a universe in a pin ring: the level loop below goes on from the cached universe)
+            }
           }
         }
         mat = SB_UNDEF_MAT;
+        if (pinMat >= 0) { mat = pinMat; break; }
 #pragma unroll 1
-        for (int lvl = 1; lvl <= MAX_NEST; ++lvl) {
+        for (int lvl = (winPos <= WIN) ? lvl0 : 1; lvl <= MAX_NEST; ++lvl) {      // (a history alone in its warp starts where it resumes)
           if (lvl < lvl0) continue;                               // a lane that resumes below joins the others at its level
           const HUni& U = uni[ui];
           const int4 h0 = *(const int4*)&U.type;                  // type, flags, n0, n1
@@ -396,6 +411,9 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
               s_gcO[0][threadIdx.x] = (gcN == 3) ? make_double2(ga0, ga1) : make_double2(0.0, 0.0);
               s_gcO[1][threadIdx.x] = make_double2(o0, o1);
               s_gcI[threadIdx.x] = make_int4(ui, rootID, lvl, 0);
+              const bool plainPin = type == HU_PIN && !(flags & (HF_ROT | HF_GLOBAL));
+              s_gcP[threadIdx.x] = make_int4(plainPin ? U.aux : -1, h0.z, (flags & HF_ORG0) ? 0 : 1, 0);
+              s_gcO[2][threadIdx.x] = make_double2(U.org[0], U.org[1]);
             }
             gcN = -1;
           }
