@@ -911,7 +911,7 @@ struct sb_engine {
   int* dRankCounts = nullptr; int* hRankCounts = nullptr;
   double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
-  int maxSegMin = 256, loneMode = 1, cellCache = 48;
+  int maxSegMin = 256, loneMode = 1, cellCache = 48; unsigned laneMask = 0xffffffffu;
   long long* dProfRounds = nullptr;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -1110,6 +1110,14 @@ static int buildBlob(sb_engine* h) {
     L.bytes = (int)hb.size();
     L.nG = h->nG; L.nMat = h->nMat; L.isP1 = h->isP1; L.rootIdx = h->g.root_idx; L.borderS = h->g.border_idx - 1;
     L.borderIsBox = h->gi_surfType[h->g.border_idx - 1] >= SB_SURF_BOX ? 1 : 0;
+    {                                                   // the border is the box the root universe record holds: boundary transformations inline
+      const int ri = h->g.root_idx - 1; const int* rip = &h->gi_uniIpar[(size_t)ri * SB_UNI_NIPAR];
+      if (unis[ri].type == sbh::HU_ROOTBOX && rip[2] == h->g.border_idx && h->gi_surfType[h->g.border_idx - 1] == SB_SURF_BOX) {
+        L.borderIsBox = 2;
+        for (int i = 0; i < 6; ++i) L.bc[i] = h->g.bc[i];
+        L.borderTol = h->gd_surfPar[(size_t)(h->g.border_idx - 1) * SB_SURF_NPAR + 6];
+      }
+    }
     cudaFree(h->dHot);
     CUDA_OK(cudaMalloc(&h->dHot, hb.size()));
     CUDA_OK(cudaMemcpy(h->dHot, hb.data(), hb.size(), cudaMemcpyHostToDevice));
@@ -1121,6 +1129,8 @@ static int buildBlob(sb_engine* h) {
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 448>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(448)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(512)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbh::histScratchBytes(256)));
       if (getenv("SB_DEBUG_OCC")) {
         int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbh::k_histories<true, 2>, 256, hotB + sbh::histScratchBytes(256));
@@ -1197,6 +1207,7 @@ int sb_create(sb_engine** out, int device) {
   if (const char* e = getenv("SB_BLOCKS_PER_SM")) h->opt.blocks_per_sm = atoi(e);
   if (const char* e = getenv("SB_MAXSEG_MIN")) h->maxSegMin = atoi(e);
   if (const char* e = getenv("SB_LONE_MODE")) h->loneMode = atoi(e);
+  if (const char* e = getenv("SB_LANES")) { int k = atoi(e); h->laneMask = (k >= 32 || k < 1) ? 0xffffffffu : ((1u << k) - 1u); }
   if (const char* e = getenv("SB_CELL_CACHE")) h->cellCache = atoi(e) < 0 ? 0x7fffffff : atoi(e);
   cudaEventCreate(&h->evP1); cudaEventCreate(&h->evP2);
   cudaEventCreate(&h->evK0); cudaEventCreate(&h->evK1); cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
@@ -1544,13 +1555,13 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
 #ifdef SB_PROFILE_ROUNDS
   { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * 27 * 148 * 384); } cudaMemsetAsync(dProf, 0, 8 * 27 * 148 * 384, st); a.prof = dProf; h->dProfRounds = dProf; }
 #endif
-  a.refillMin = h->refillMin; a.maxSegMin = h->maxSegMin; a.loneMode = h->loneMode; a.cellCache = h->cellCache;
+  a.refillMin = h->refillMin; a.maxSegMin = h->maxSegMin; a.loneMode = h->loneMode; a.cellCache = h->cellCache; a.laneMask = h->laneMask;
   // one CTA of 12 warps per SM (168 registers per thread, no spills) unless told otherwise: at the populations of an
   // eigenvalue cycle the kernel's time is the chain of its longest history, not the number of resident warps
   int threads = 384;
   const int bps = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 1;
   if (const char* e = getenv("SB_HIST_THREADS")) threads = atoi(e);
-  if (bps != 1 || !h->useSmem) threads = 256;
+  if (bps != 1 || !h->useSmem || (threads != 384 && threads != 448 && threads != 512)) threads = 256;
   int blocks = h->numSM * bps;
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
@@ -1621,6 +1632,8 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   {
     const int hotB = h->useSmem ? h->hot.bytes : 0;
     if (h->useSmem && bps == 1 && threads == 384) sbh::k_histories<true, 1, 384><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
+    else if (h->useSmem && bps == 1 && threads == 448) sbh::k_histories<true, 1, 448><<<blocks, 448, hotB + sbh::histScratchBytes(448), st>>>(a);
+    else if (h->useSmem && bps == 1 && threads == 512) sbh::k_histories<true, 1, 512><<<blocks, 512, hotB + sbh::histScratchBytes(512), st>>>(a);
     else if (h->useSmem && bps == 1) sbh::k_histories<true, 1><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);

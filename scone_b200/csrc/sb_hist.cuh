@@ -44,7 +44,8 @@ struct HotLayout {
   int oUni, oGraph, oAuxD, oAuxI, oXs, oP0, oProd, oP1, oP0First, oFissile, oMajT, oMajInv;
   int oClerk[2], nClerk[2];
   int oScoreMask[2];                     // per phase: [nMat*nG + 1] bytes, 1 if any clerk can score a non-zero in (mat, G); last = void
-  int nG, nMat, isP1, rootIdx, borderS, borderIsBox;
+  int nG, nMat, isP1, rootIdx, borderS, borderIsBox;      // borderIsBox: 1 box-like border (transformBC applies), 2 it is the root universe's box (hot record)
+  int bc[6]; double borderTol;           // boundary conditions and SURF_TOL of that box
 };
 
 struct Bank {            // particleDungeon as structure of arrays
@@ -75,6 +76,7 @@ struct HistArgs {
   double* bins; int phase; int impScores;      // impScores: keffImplicitClerk scores wanted (active phase, or a user clerk)
   uint64_t rng0; int histOffset; double k_eff;
   CycleDev* cd; int refillMin;
+  unsigned laneMask;                     // lanes of a warp that take histories from the bank (all: 0xffffffff)
   int maxSegMin;                         // histories longer than this report their length (cd->maxSeg)
   long long* prof;                       // SB_PROFILE_ROUNDS builds: per-warp round timings
   int cellCache;                         // placement resumes below the lattice cell of the previous site when the new one is safely inside it,
@@ -290,15 +292,16 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
     PR_MARK(7)
     // ---------------- refill dead lanes (warp-level compaction of the bank) ----------------------------
     unsigned need = __ballot_sync(FULL, !alive);
-    if (need != 0u && !exhausted) {
-      int cnt = __popc(need);
+    if ((need & a.laneMask) != 0u && !exhausted) {
+      const unsigned take = need & a.laneMask;             // lanes that may be refilled
+      int cnt = __popc(take);
       if (cnt >= a.refillMin || need == FULL) {
         int b = 0;
         if (lane == 0) b = atomicAdd(&a.cd->nextHistory, cnt);
         b = __shfl_sync(FULL, b, 0);
         if (b + cnt >= a.n) exhausted = true;
-        int my = b + __popc(need & ltMask);
-        if (!alive && my < a.n) {
+        int my = b + __popc(take & ltMask);
+        if (!alive && ((take >> lane) & 1u) && my < a.n) {
           hi = my;
           r0 = a.in.rx[hi]; r1 = a.in.ry[hi]; r2 = a.in.rz[hi];
           u0 = a.in.ux[hi]; u1 = a.in.uy[hi]; u2 = a.in.uz[hi];
@@ -322,16 +325,26 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
       if (__shfl_sync(FULL, winPos, owner) > WIN - WIN_ROUND) {
         const uint64_t sb = __shfl_sync(FULL, rng, owner);
         uint64_t st = (jA * sb + jC) & RNG_MASK;                           // lane + 1 draws ahead, then 32 more
+        // both entries of the lane in one straight line (sb_math.h: log_main / sincos_main, the same values without
+        // branches), so that the two logarithms, sines / cosines and square roots overlap; the special arguments after
+        bool rare[WIN / 32];
 #pragma unroll
         for (int k = 0; k < WIN / 32; ++k) {
           const int e = lane + 32 * k;
           const double xi = rngReal(st);
           double sn, cs;
-          sbm::sincos(TWO_PI * xi, &sn, &cs);
-          W.st[e] = st; W.xi[e] = xi; W.nlog[e] = -sbm::log(xi); W.sn[e] = sn; W.cs[e] = cs;
-          W.A[e] = sinPolar(2.0 * xi - 1.0);
+          sbm::sincos_main(TWO_PI * xi, &sn, &cs);
+          const double mu = 2.0 * xi - 1.0, a2 = fmax(0.0, 1.0 - mu * mu);
+          bool rl;
+          const double lg = sbm::log_main(xi, &rl);
+          rare[k] = rl || !fastRange(a2);
+          W.st[e] = st; W.xi[e] = xi; W.nlog[e] = -lg; W.sn[e] = sn; W.cs[e] = cs;
+          W.A[e] = sqrtFast(a2);
           st = rngJump<32>(st);
         }
+#pragma unroll
+        for (int k = 0; k < WIN / 32; ++k)
+          if (rare[k]) { const int e = lane + 32 * k; const double xi = W.xi[e]; W.nlog[e] = -sbm::log(xi); W.A[e] = sinPolar(2.0 * xi - 1.0); }
         __syncwarp();
         if (lane == owner) winPos = 0;
       }
@@ -495,9 +508,31 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const HistArgs a) {
         }
         // ---- geometryStd%teleport: outside -> transformBC, place again (once) ----
         if (mat != SB_OUTSIDE_MAT || pass == 1 || !a.L.borderIsBox) break;
-        double tr[3] = {r0, r1, r2}, tu[3] = {u0, u1, u2};
-        coldTransformBC(a.blob, tr, tu);
-        r0 = tr[0]; r1 = tr[1]; r2 = tr[2]; u0 = tu[0]; u1 = tu[1]; u2 = tu[2];
+        if (a.L.borderIsBox == 2) {
+          // the border is the root universe's box (box_class.f90:432-487 transformBC): an axis on which the point is within
+          // a_bar = halfwidth (1 - SURF_TOL) of the origin makes no reflection - |d| / a_bar <= 1 exactly when |d| <= a_bar - so
+          // the quotient is only formed for the axes that are outside
+          const HUni& R = uni[a.L.rootIdx - 1];
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            double& rc = (ax == 0) ? r0 : ((ax == 1) ? r1 : r2); double& uc = (ax == 0) ? u0 : ((ax == 1) ? u1 : u2);
+            const double org = R.ci[ax].x, hw = R.ph[ax].x;
+            const double a_bar = hw * (1.0 - a.L.borderTol);
+            if (fabs(rc - org) <= a_bar) continue;
+            const int Ri = (int)ceil(fabs(rc - org) / a_bar) / 2;
+#pragma unroll 1
+            for (int t = 1; t <= Ri; ++t) {
+              const double d0 = rc - org;
+              const int b = (d0 < 0.0) ? a.L.bc[2 * ax] : a.L.bc[2 * ax + 1];
+              if (b == 1) { const double a0 = fsign(hw, d0) + org; const double d = rc - a0; rc = rc - 2.0 * d; uc = -uc; }
+              else if (b == 2) { const double d = fsign(hw, d0); rc = rc - 2.0 * d; }
+            }
+          }
+        } else {
+          double tr[3] = {r0, r1, r2}, tu[3] = {u0, u1, u2};
+          coldTransformBC(a.blob, tr, tu);
+          r0 = tr[0]; r1 = tr[1]; r2 = tr[2]; u0 = tu[0]; u1 = tu[1]; u2 = tu[2];
+        }
       }
       PR_MARK(2)
       if (mat == SB_OUTSIDE_MAT) { leaked = true; died = true; }                          // LEAK_FATE
