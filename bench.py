@@ -34,8 +34,19 @@ WORKLOAD = {"c5g7": "C5G7 MOX 2D 7-group eigenvalue, delta tracking (InputFiles/
             "ce_asm": "synthetic continuous-energy 17x17 assembly, 20 nuclides per fuel material (5 bundled ACE nuclides + 15 energy-shifted clones), delta tracking, k-eff only (BASELINE configs[4] at a single-GPU population)",
             "can": "7-group finite can bounded by truncated cylinders (reflective bottom, vacuum top), surface tracking, strongly subcritical",
             "ce_pin": "continuous-energy U-233 / H-1 pin cell from the reference's bundled ACE nuclides (BASELINE configs[2] stand-in), 300-bin energy x material flux tally"}
-ALG_BYTES_PER_SEGMENT = 124      # particle SoA read+write per flight segment
+ALG_BYTES_PER_SEGMENT = 124      # particle SoA read+write per flight segment (multigroup)
 ALG_BYTES_PER_SCORE = 16         # f64 read-modify-write per tally score
+# continuous energy, SURVEY.md section 8(d) / DESIGN.md section 4: a flight segment moves the particle record (132 B with E) and one
+# total-cross-section lookup of 36 B per nuclide of the material + 20 B; a real collision walks the nuclides again (36 B each) and
+# reads one micro set (148 B)
+CE_BYTES_PER_SEGMENT = 132 + 20
+CE_BYTES_PER_NUCLIDE_TERM = 36
+CE_BYTES_PER_COLLISION = 148
+DATA = {"c5g7": "NEA C5G7 benchmark 7-group constants re-authored from the published specification (decks/c5g7); uniform initial source",
+        "c5g7_3d": "NEA C5G7 benchmark 7-group constants, 3-D rodded configuration A authored from the published specification; uniform initial source",
+        "inf": "analytic benchmark constants URRa-2-1-IN (Sood et al.) as in the reference's InputFiles/SCONE_Inf", "slab": "analytic benchmark constants URRa-2-1-SL (Sood et al.) as in the reference's InputFiles/SCONE_Slab",
+        "ce_pin": "the reference's bundled JEF-3.1.1 ACE nuclides (data/ace); authored pin-cell deck", "can": "NEA C5G7 7-group constants in an authored finite geometry",
+        "ce_asm": "synthetic: the reference's bundled ACE nuclides plus seeded energy-shifted clones (decks/ce/synth); authored 17x17 deck"}
 
 
 def measured_peak():
@@ -212,7 +223,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "active-cycle neutrons/s", "value": val, "unit": "neutrons/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": DATA[args.deck],
         "config": {"workload": WORKLOAD[args.deck], "deck": deck, "pop_per_cycle": pop, "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck in ("ce_pin", "can") else "DT"),
                    "note": "CPU reference arm: one step = one active cycle of pop histories on the host cores"},
         "segments_per_s": (s1.value - s0.value) / dt, "keff": kc.value, "keff_std": ks.value,
@@ -303,7 +314,7 @@ def main():
     L.sb_profile_enable(eng, 1)
     launches0 = pp.launch_count()
     barrier()
-    ms_total = 0.0; seg = 0; scores = 0; nsites = 0
+    ms_total = 0.0; seg = 0; scores = 0; nsites = 0; coll = 0; xs_terms = 0
     ms = C.c_double()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -312,7 +323,7 @@ def main():
         L.sb_timer_begin(eng)
         res = pp.cycle(True, comm=comm)
         L.sb_timer_end(eng, C.byref(ms))
-        ms_total += ms.value; seg += res.n_segments; scores += res.n_scores; nsites += res.n_sites
+        ms_total += ms.value; seg += res.n_segments; scores += res.n_scores; nsites += res.n_sites; coll += res.n_collisions; xs_terms += res.n_xs_terms
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = pp.launch_count() - launches0 - (args.steps if flush else 0) * 0
@@ -341,7 +352,13 @@ def main():
 
     # ---- roofline of the dominant kernel (k_histories) -----------------------------------------------------
     peak, peak_src = measured_peak()
-    alg_bytes = (ALG_BYTES_PER_SEGMENT * segp.value + ALG_BYTES_PER_SCORE * scp.value) / max(1, nl.value)
+    is_ce = args.deck.startswith("ce_")
+    if is_ce:          # mean nuclides per lookup from the engine's counter; the collision walks the same material again
+        nbar = xs_terms / max(1, seg)
+        alg_bytes = (CE_BYTES_PER_SEGMENT * seg + CE_BYTES_PER_NUCLIDE_TERM * xs_terms + (CE_BYTES_PER_COLLISION + CE_BYTES_PER_NUCLIDE_TERM * nbar) * coll
+                     + ALG_BYTES_PER_SCORE * scores) / max(1, args.steps)
+    else:
+        alg_bytes = (ALG_BYTES_PER_SEGMENT * segp.value + ALG_BYTES_PER_SCORE * scp.value) / max(1, nl.value)
     k_ms = msk.value / max(1, nl.value)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
@@ -353,6 +370,12 @@ def main():
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,
+                "algorithmic_bytes": ("per segment 132 + 20 B + 36 B per nuclide term of the total cross section (%.2f terms per segment counted by the engine); per real collision 148 B + the nuclide walk again; 16 B per score"
+                                      % (xs_terms / max(1, seg))) if is_ce else "124 B per flight segment + 16 B per tally score",
+                # what actually bounds the kernel at this population: the dependent chain of the cycle's longest history
+                "latency": {"longest_history_flights": max_seg, "kernel_us_per_flight_of_the_longest_history": (1e3 * k_ms / max_seg) if max_seg > 256 else None,
+                            "mean_flights_per_history": seg / max(1, pop * args.steps),
+                            "note": "the kernel ends when the longest history of the cycle ends: its flights x the latency of one flight + collision round of a history that runs alone in its warp (profiles/README.md, round 2)"},
                 "note": ("lane-resident histories in CTA-lockstep phases: bound by instruction fetch, barrier wait and memory latency at 16-32 warps per SM, not by HBM (DESIGN.md section 4, profiles/README.md)"
                          if kname != "k_histories" else "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)")}
 
@@ -393,13 +416,13 @@ def main():
         line = {
             "metric": "active-cycle neutrons/s", "value": value, "unit": "neutrons/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": DATA[args.deck],
             "config": {"workload": WORKLOAD[args.deck], "deck": DECKS[args.deck], "pop_per_cycle_per_gpu": pop, "pop_per_cycle_total": total_pop,
                        "tracking": args.tracking or "as the deck (%s)" % ("ST, cache" if args.deck in ("ce_pin", "can") else "DT"), "inactive_cycles_before": args.inactive,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush else "not flushed (steady-state cycles)",
                        "parallelism": "bank sharded by history index over %d GPU(s)%s" % (
                            world, exchange)},
-            "longest_history_segments": max_seg,
+            "longest_history_segments": max_seg, "virtual_per_real_collision": (seg - coll) / max(1, coll),
             "segments_per_s": seg_all / (ms_max * 1e-3), "segments_per_history": seg / max(1, pop * args.steps),
             "keff": k_dev, "keff_std": k_std, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_val, "unit": "neutrons/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,

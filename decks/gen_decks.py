@@ -413,7 +413,7 @@ nuclearData {
 
 # ---------------------------------------------------------------------------------------
 # Continuous-energy decks (authored from the nuclides bundled with the reference; the cards travel as the binary fixtures
-# tests/golden/ace/*.acebin, see tests/golden/make_ace_fixtures.py)
+# data/ace/*.acebin, see tests/golden/make_ace_fixtures.py)
 CE_BASE = [("1001", "1001JEF311"), ("92233", "92233JEF311"), ("52126", "52126JEF311"), ("91231", "91231JEF311"), ("91232", "91232JEF311")]
 
 
@@ -424,14 +424,14 @@ def synth_ace_cards(outdir):
     import struct
     import numpy as np
     here = os.path.dirname(os.path.abspath(__file__))
-    src = os.path.join(here, "..", "tests", "golden", "ace")
+    src = os.path.join(here, "..", "data", "ace")
     dst = os.path.join(outdir, "ce", "synth")
     os.makedirs(dst, exist_ok=True)
     rng = np.random.default_rng(20261017)
     lib = ["! synthetic ACE library: the five bundled cards + 15 energy-shifted clones (decks/gen_decks.py)"]
     for za, fn in CE_BASE:
         raw = open(os.path.join(src, fn + ".acebin"), "rb").read()
-        lib.append("%s.03c; 1; ../../../tests/golden/ace/%s.acebin;" % (za, fn))
+        lib.append("%s.03c; 1; ../../../data/ace/%s.acebin;" % (za, fn))
         head = raw[:8 + 16 + 16]
         nxs = np.frombuffer(raw, np.int32, 16, 40).copy(); jxs = np.frombuffer(raw, np.int32, 32, 104).copy()
         n = struct.unpack_from("<q", raw, 232)[0]
@@ -613,7 +613,7 @@ geometry {
 }
 
 nuclearData {
-  handles { ce { type aceNeutronDatabase; aceLibrary ../../tests/golden/ace/aceLib; ures 0; majorant 1; } }
+  handles { ce { type aceNeutronDatabase; aceLibrary ../../data/ace/aceLib; ures 0; majorant 1; } }
   materials {
     fuel  { temp 293; composition { 92233.03 1.0E-3; 52126.03 2.2E-2; 91231.03 5.0E-5; 91232.03 2.0E-6; } }
     water { temp 293; composition { 1001.03 6.67E-2; 52126.03 1.0E-3; } }

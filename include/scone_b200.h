@@ -166,6 +166,7 @@ typedef struct sb_cycle_result {
   int64_t n_segments, n_collisions, n_scores;   /* flights, real collisions, tally scores (f64 accumulations) */
   int32_t error;              /* device-side fatal condition (SB_ERR_*), 0 if none             */
   int32_t max_history_segments; /* flights of the longest history (>= 256; the cycle's critical path)  */
+  int64_t n_xs_terms;         /* continuous energy: nuclide terms summed by the total-cross-section lookups of the flights */
 } sb_cycle_result;
 enum { SB_ERR_BANK_OVERFLOW = 1, SB_ERR_UNDEF_MAT = 2, SB_ERR_OVERLAP_MAT = 3, SB_ERR_SAMPLING = 4,
        SB_ERR_NEST = 5, SB_ERR_SOURCE = 6, SB_ERR_NORM = 7, SB_ERR_FILE_SOURCE = 10, SB_ERR_PEER_TIMEOUT = 11, SB_ERR_BALANCE = 12, SB_ERR_MAT_SOURCE = 13, SB_ERR_MAT_SOURCE_VOID = 14,

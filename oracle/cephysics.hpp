@@ -26,7 +26,7 @@ namespace orc {
 
 constexpr double kBoltzmannMeV = 1.380649e-23 / 1.60218e-13;          // universalVariables.f90: kBoltzmann / joulesPerMeV
 
-// binary form of an ACE card (tests/golden/ace/*.acebin, written by tests/golden/make_ace_fixtures.py): the GPU box has no
+// binary form of an ACE card (data/ace/*.acebin, written by tests/golden/make_ace_fixtures.py): the GPU box has no
 // /root/reference, so the card arrays travel as a fixture.  Layout: "SBACE1\0\0", ZAID[16], AW, TZ, NXS[16] i32, JXS[32] i32, n i64, XSS[n]
 inline void readAceBin(orc_ce::AceCard& ace, const std::string& path) {
   std::ifstream f(path, std::ios::binary);

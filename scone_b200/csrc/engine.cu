@@ -857,7 +857,7 @@ __global__ void k_finish_sites(const Model M, const char* blob, Bank b, CycleDev
 __global__ void k_cycle_begin(CycleDev* cd, int* nCur, int n) {
   cd->nStart = n; cd->nSites = 0; cd->nextHistory = 0; cd->error = 0;
   cd->selBin = -1; cd->selRank = 0; cd->nCand = 0; cd->nNew = 0;
-  cd->nSeg = 0ULL; cd->nColl = 0ULL; cd->nScore = 0ULL; cd->maxSeg = 256;
+  cd->nSeg = 0ULL; cd->nColl = 0ULL; cd->nScore = 0ULL; cd->nXsTerms = 0ULL; cd->maxSeg = 256;
   *nCur = n;
 }
 // particleState arrays cross the boundary as r(3,n), dir(3,n) (Fortran order); banks are SoA on the device
@@ -1700,7 +1700,7 @@ static int cycleFinish(sb_engine* h, sb_cycle_result* res) {
     res->n_start = c.nStart; res->n_sites = c.nSites; res->start_wgt = c.startWgt; res->end_wgt = c.endWgt;
     res->imp_prod = c.impProd; res->imp_abs = c.impAbs; res->scatter_prod = c.scatProd; res->ana_leak = c.anaLeak;
     res->k_analog = c.kAnalog; res->k_implicit = c.kImplicit; res->k_cum = c.kCum; res->k_cum_std = c.kCumStd;
-    res->n_segments = (int64_t)c.nSeg; res->n_collisions = (int64_t)c.nColl; res->n_scores = (int64_t)c.nScore; res->error = c.error; res->max_history_segments = c.maxSeg;
+    res->n_segments = (int64_t)c.nSeg; res->n_collisions = (int64_t)c.nColl; res->n_scores = (int64_t)c.nScore; res->error = c.error; res->max_history_segments = c.maxSeg; res->n_xs_terms = (int64_t)c.nXsTerms;
   }
   h->sortedReady = true; h->phaseOpen = -1;
   h->kCumLast = c.kCum;

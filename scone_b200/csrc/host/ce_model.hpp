@@ -52,7 +52,7 @@ inline AceCardData readAceText(const std::string& path, int lineNum) {
   }
   return c;
 }
-// the same card as a binary fixture (tests/golden/ace/*.acebin): "SBACE1\0\0", ZAID[16], AW, TZ, NXS[16] i32, JXS[32] i32, n i64, XSS[n] f64
+// the same card as a binary fixture (data/ace/*.acebin): "SBACE1\0\0", ZAID[16], AW, TZ, NXS[16] i32, JXS[32] i32, n i64, XSS[n] f64
 inline AceCardData readAceBinary(const std::string& path) {
   std::ifstream f(path, std::ios::binary);
   if (!f) throw FatalError("readFromFile (aceCard)", "Cannot open ACE file: " + path);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
   const double collisionXS = M.collisionXS;
-  unsigned nSeg = 0, nColl = 0, nScore = 0;
+  unsigned nSeg = 0, nColl = 0, nScore = 0, nTerms = 0;
   constexpr int NPASS = (SLOTS + THREADS - 1) / THREADS;
 
   for (;;) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
           else if (a.tracking == SB_TRACK_ST) mode = 2;
           else {
             double majorant_inv = 1.0 / majXS;
-            double sigmaT = (s.c.mat == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, s.c.mat) + 0.0;
+            double sigmaT = (s.c.mat == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, s.c.mat, nTerms) + 0.0;
             double ratio = sigmaT * majorant_inv;
             mode = (ratio > (1.0 - a.htCutoff)) ? 1 : 2;
           }
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
             bool virt = true;
             double sigTot = 0.0;
             if (m != SB_VOID_MAT) {
-              sigTot = ceMatTotal(X, u, E, m);
+              sigTot = ceMatTotal(X, u, E, m, nTerms);
               if (rngGet(rng) < (sigTot + 0.0) * majorant_inv) { realColl = true; virt = false; }
             }
             S.sigTot[g] = sigTot;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
         } else {
           const double tol = 1.0E-12;
           int m = s.c.mat;
-          const double sigTot = (m == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, m);
+          const double sigTot = (m == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, m, nTerms);
           S.sigTot[g] = sigTot;
           double sigmaTrack = (m == SB_VOID_MAT) ? collisionXS : fmax(sigTot + 0.0, collisionXS);
           S.trackXS[g] = sigmaTrack;
@@ -463,10 +463,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     nSeg += __shfl_down_sync(FULL, nSeg, d); nColl += __shfl_down_sync(FULL, nColl, d); nScore += __shfl_down_sync(FULL, nScore, d);
+    nTerms += __shfl_down_sync(FULL, nTerms, d);
   }
   if (lane == 0) {
     atomicAdd(&a.cd->nSeg, (unsigned long long)nSeg); atomicAdd(&a.cd->nColl, (unsigned long long)nColl);
-    atomicAdd(&a.cd->nScore, (unsigned long long)nScore);
+    atomicAdd(&a.cd->nScore, (unsigned long long)nScore); atomicAdd(&a.cd->nXsTerms, (unsigned long long)nTerms);
   }
 }
 

@@ -162,8 +162,9 @@ __device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, con
 }
 
 // sbce::matTotal with the loop kept rolled (code size; the lookup kernel keeps the unrolled one)
-__device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e, int m) {
+__device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e, int m, unsigned& terms) {
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
+  terms += (unsigned)(k1 - k0);
   const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
   double tot = 0.0;
 #pragma unroll NUC_UNROLL
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
   double E = 1.0, w = 0.0, w0 = 0.0, trackXS = 1.0, majXS = 1.0, sigTot = 0.0;
   uint64_t rng = 0;
   double sProd = 0.0, sAbs = 0.0, sScat = 0.0, sLeak = 0.0;     // sLeak: leaked weight of the history (with its secondaries in a fixed-source run)
-  unsigned nSeg = 0, nColl = 0, nScore = 0;
+  unsigned nSeg = 0, nColl = 0, nScore = 0, nTerms = 0;
   c.nesting = 1; c.mat = SB_UNDEF_MAT; c.uid = -3;
 
   for (;;) {
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
         else if (a.tracking == SB_TRACK_ST) mode = 2;
         else {                                              // transportOperatorHT_class.f90:49-81
           double majorant_inv = 1.0 / majXS;
-          double sigmaT = (c.mat == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, c.mat) + 0.0;
+          double sigmaT = (c.mat == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, c.mat, nTerms) + 0.0;
           double ratio = sigmaT * majorant_inv;
           mode = (ratio > (1.0 - a.htCutoff)) ? 1 : 2;
         }
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
           bool virt = true;
           sigTot = 0.0;
           if (c.mat != SB_VOID_MAT) {
-            sigTot = ceMatTotal(X, u, E, c.mat);
+            sigTot = ceMatTotal(X, u, E, c.mat, nTerms);
             if (rngGet(rng) < (sigTot + 0.0) * majorant_inv) { realColl = true; virt = false; }
           }
           scoreVirt = virt;
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
       } else {                                              // surfaceTracking, one segment
         const double tol = 1.0E-12;
         int m = c.mat;
-        sigTot = (m == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, m);
+        sigTot = (m == SB_VOID_MAT) ? 0.0 : ceMatTotal(X, u, E, m, nTerms);
         double sigmaTrack = (m == SB_VOID_MAT) ? collisionXS : fmax(sigTot + 0.0, collisionXS);
         trackXS = sigmaTrack;
         double dist, invSigmaTrack, sigmaT;
@@ -623,10 +624,11 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     nSeg += __shfl_down_sync(FULL, nSeg, d); nColl += __shfl_down_sync(FULL, nColl, d); nScore += __shfl_down_sync(FULL, nScore, d);
+    nTerms += __shfl_down_sync(FULL, nTerms, d);
   }
   if (lane == 0) {
     atomicAdd(&a.cd->nSeg, (unsigned long long)nSeg); atomicAdd(&a.cd->nColl, (unsigned long long)nColl);
-    atomicAdd(&a.cd->nScore, (unsigned long long)nScore);
+    atomicAdd(&a.cd->nScore, (unsigned long long)nScore); atomicAdd(&a.cd->nXsTerms, (unsigned long long)nTerms);
   }
 }
 

@@ -62,6 +62,7 @@ struct CycleDev {        // small device-resident record of the running cycle
   double thrReal;
   double startWgt, endWgt, impProd, impAbs, scatProd, anaLeak, kAnalog, kImplicit, normFactor;
   unsigned long long nSeg, nColl, nScore;
+  unsigned long long nXsTerms;           // continuous energy: nuclide terms of the flights' total-cross-section lookups
   // cumulative k of the attachment clerks: [phase] CSUM, CSUM2, batches
   double kCsum[2], kCsum2[2]; int kBatches[2];
   double kCum, kCumStd;

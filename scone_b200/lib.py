@@ -21,7 +21,7 @@ class CycleResult(C.Structure):
                 ("start_wgt", C.c_double), ("end_wgt", C.c_double),
                 ("imp_prod", C.c_double), ("imp_abs", C.c_double), ("scatter_prod", C.c_double), ("ana_leak", C.c_double),
                 ("k_analog", C.c_double), ("k_implicit", C.c_double), ("k_cum", C.c_double), ("k_cum_std", C.c_double),
-                ("n_segments", C.c_int64), ("n_collisions", C.c_int64), ("n_scores", C.c_int64), ("error", C.c_int32), ("max_history_segments", C.c_int32)]
+                ("n_segments", C.c_int64), ("n_collisions", C.c_int64), ("n_scores", C.c_int64), ("error", C.c_int32), ("max_history_segments", C.c_int32), ("n_xs_terms", C.c_int64)]
 
 
 def load_library():

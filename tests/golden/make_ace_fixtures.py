@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Writes tests/golden/ace/*.acebin + tests/golden/ace/aceLib from the reference's bundled ACE files
+"""Writes data/ace/*.acebin + data/ace/aceLib from the reference's bundled ACE files
 (run where /root/reference exists; the GPU box has no /root/reference, so the card arrays travel as fixtures).
 
 An .acebin file is the ACE card itself (ZAID, AW, TZ, NXS(16), JXS(32), XSS(:) as aceCard holds them after readFromFile,
@@ -38,7 +38,7 @@ def read_card(path, line):
 
 
 def main():
-    out = os.path.join(ROOT, "tests", "golden", "ace")
+    out = os.path.join(ROOT, "data", "ace")
     os.makedirs(out, exist_ok=True)
     lib = ["! ACE library of the fixtures (aceLibrary_mod.f90 format: NAME; LINE; PATH;) - paths relative to this file"]
     for name, fn, line in FILES:

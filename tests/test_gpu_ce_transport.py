@@ -133,7 +133,7 @@ def test_ce_nuclides_on_engine_match_oracle(orc):
     """What sb_load_ce_model built (energy grids, main data, MT order) is what the oracle builds from the same cards."""
     pp = scone_b200.EigenPhysicsPackage(DECK, "pop 100;", device=0)
     L = pp.L
-    ace = os.path.join(ROOT, "tests", "golden", "ace")
+    ace = os.path.join(ROOT, "data", "ace")
     for i, name in enumerate(["92233JEF311", "52126JEF311", "91231JEF311", "91232JEF311", "1001JEF311"], start=1):
         gs, rows, nmt = C.c_int32(), C.c_int32(), C.c_int32()
         assert L.sb_ce_nuclide_info(pp.engine, i, C.byref(gs), C.byref(rows), C.byref(nmt)) == 0

@@ -28,7 +28,7 @@ def composition(rng, need_fissile):
 @pytest.mark.parametrize("seed", list(range(12)))
 def test_random_ce_compositions(orc, seed):
     rng = np.random.default_rng(2000 + seed)
-    nd = ("nuclearData { handles { ce { type aceNeutronDatabase; aceLibrary ../../tests/golden/ace/aceLib; ures 0; majorant 1; %s} } materials { "
+    nd = ("nuclearData { handles { ce { type aceNeutronDatabase; aceLibrary ../../data/ace/aceLib; ures 0; majorant 1; %s} } materials { "
           "fuel { temp %d; composition { %s } } water { temp %d; composition { %s } } } }" % (
               "avgDist 5.0; " if rng.random() < 0.4 else "", int(rng.integers(250, 900)), composition(rng, True), int(rng.integers(250, 900)), composition(rng, False)))
     co = "collisionOperator { neutronCE { type neutronCEstd; energyThreshold %.1f; massThreshold %.2f; minEnergy %.3E; maxEnergy %.1f; } }" % (

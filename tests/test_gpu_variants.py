@@ -147,7 +147,7 @@ GEOM_VOID = """geometry {
 }"""
 ND_MG = """nuclearData { handles { mg { type baseMgNeutronDatabase; PN P0; avgDist 2.5; } }
   materials { UO2 { temp 300; xsFile ./xs/UO2.xs; composition { } } water { temp 300; xsFile ./xs/moder.xs; composition { } } } }"""
-ND_CE = """nuclearData { handles { ce { type aceNeutronDatabase; aceLibrary ../../tests/golden/ace/aceLib; ures 0; majorant 1; avgDist 3.0; } }
+ND_CE = """nuclearData { handles { ce { type aceNeutronDatabase; aceLibrary ../../data/ace/aceLib; ures 0; majorant 1; avgDist 3.0; } }
   materials { fuel  { temp 293; composition { 92233.03 1.5E-4; 52126.03 2.2E-2; 91231.03 5.0E-5; 91232.03 2.0E-6; } }
               water { temp 293; composition { 1001.03 6.67E-2; 52126.03 1.0E-3; } } } }"""
 FLUX = "activeTally { f { type collisionClerk; map { type spaceMap; axis z; grid lin; min -4.0; max 4.0; N 8; } response (fl); fl { type fluxResponse; } } }"

@@ -10,7 +10,7 @@ from tests import oracle_lib as ol
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/IntegrationTestFiles/"
-ACE = os.path.join(ROOT, "tests", "golden", "ace")
+ACE = os.path.join(ROOT, "data", "ace")
 have_ref = os.path.exists(REF + "1001JEF311.ace")
 DECK = os.path.join(ROOT, "decks", "ce", "pincell")
 FILES = [("1001JEF311", 1779), ("92233JEF311", 1), ("52126JEF311", 1), ("91231JEF311", 1), ("91232JEF311", 1)]
@@ -53,7 +53,7 @@ def test_endf_table_known_answers(orc):
 
 @pytest.mark.skipif(not have_ref, reason="reference ACE files are not on this box")
 def test_ace_fixtures_are_the_reference_cards(orc):
-    """tests/golden/ace/*.acebin hold exactly what the reference's text cards hold (nuclide built from either is identical)."""
+    """data/ace/*.acebin hold exactly what the reference's text cards hold (nuclide built from either is identical)."""
     for name, line in FILES:
         a = orc.orc_ce_nuclide_from_ace((REF + name + ".ace").encode(), line)
         b = orc.orc_ce_nuclide_from_acebin(os.path.join(ACE, name + ".acebin").encode())
