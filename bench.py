@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--pop", type=int, default=100000, help="histories per cycle PER GPU (weak scaling)")
     ap.add_argument("--inactive", type=int, default=10, help="untimed inactive cycles before the active phase")
     ap.add_argument("--tracking", default=None, choices=["DT", "ST", "HT"], help="transportOperator; default: what the deck says (delta tracking for the MG decks as BASELINE configs[0] names it, surface tracking with cache for the CE pin cell)")
+    ap.add_argument("--no-rank-parity", action="store_true", help="N > 1: skip the check that the ranks reproduce the single-rank k-eff")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: per-cycle exchange between the ranks through peer memory (engine kernels storing into the other GPUs' HBM over NVLink) or through NCCL collectives")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -350,6 +351,32 @@ def main():
     e2e_val = total_pop * args.steps / t_e2e
     sampler.stop_flag = True; sampler.join(timeout=2)
 
+    # ---- N > 1: the ranks together against ONE rank on the same histories (hardware check of the exchange) ----
+    rank_parity = None
+    if world > 1 and not args.no_rank_parity:
+        ovp = "pop %d; inactive 3; active 2; seed 20261017;%s" % (20000 * world, tracking_override(args.tracking))
+        comm2 = scone_b200.distributed.TorchComm(device=torch.device("cuda", local))
+        ppr = scone_b200.EigenPhysicsPackage(deck, ovp, device=local, rank=rank, n_ranks=world)
+        if args.exchange == "peer":
+            scone_b200.distributed.enable_peer(ppr, comm2)
+        ppr.generateInitialState()
+        ks = []
+        for c in range(5):
+            ppr.cycle(c >= 3, comm=comm2); ks.append(ppr.k)
+        ppr.close()
+        if rank == 0:
+            pp1 = scone_b200.EigenPhysicsPackage(deck, ovp, device=local)
+            pp1.generateInitialState()
+            ks1 = []
+            for c in range(5):
+                pp1.cycle(c >= 3); ks1.append(pp1.k)
+            pp1.close()
+            diff = max(abs(a - b) / abs(b) for a, b in zip(ks, ks1))
+            rank_parity = {"cycles": 5, "histories_per_cycle": 20000 * world, "ranks": world, "k_of_the_ranks": ks[-1], "k_of_one_rank": ks1[-1],
+                           "max_rel_k_difference": diff, "bound": 1e-12, "ok": bool(diff <= 1e-12)}
+            if diff > 1e-12:
+                print("bench.py: the %d ranks and the single rank disagree on k-eff: %r vs %r" % (world, ks, ks1), file=sys.stderr)
+
     # ---- roofline of the dominant kernel (k_histories) -----------------------------------------------------
     peak, peak_src = measured_peak()
     is_ce = args.deck.startswith("ce_")
@@ -429,6 +456,8 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "clocks": sampler.summary(),
         }
+        if rank_parity is not None:
+            line["rank_parity"] = rank_parity
         if world > 1:
             line["stage_ms_rank0"] = {"histories": msk.value / max(1, nl.value), "waiting_for_every_rank_sums": ms_wait.value / args.steps,
                                       "close_resample_balance": ms_tail.value / args.steps}

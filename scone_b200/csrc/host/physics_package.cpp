@@ -26,6 +26,7 @@ namespace {
 struct eigenPhysicsPackage {
   // settings
   int pop = 0, totalPop = 0, N_inactive = 0, N_active = 0;
+  sb_options opt{};
   double keff_0 = 1.0;
   uint64_t pRNG = 0, masterRNG = 0;      // masterRNG: the pRNG of rank 0 (normSize_Repr draws from the master's stream)
   int rank = 0, nRanks = 1;
@@ -104,7 +105,7 @@ struct eigenPhysicsPackage {
         data = sb::buildMgData(nd, nucData, dirName(deckPath), geom.activeMats());
         if (!co.isPresent("neutronMG") || co.getDict("neutronMG").getWord("type") != "neutronMGstd") return fail("collisionOperator: neutronMGstd is required");
       }
-      sb_options opt{}; opt.max_pop = pop; opt.ht_cutoff = 0.9; opt.st_cache = 1;
+      opt = sb_options{}; opt.max_pop = pop; opt.ht_cutoff = 0.9; opt.st_cache = 1;
       const sb::Dict& to = dict.getDict("transportOperator");
       std::string tt = to.getWord("type");
       if (tt == "transportOperatorDT") opt.tracking = SB_TRACK_DT;
@@ -406,6 +407,47 @@ void sbh_eigen_destroy(void* pv) {
   sb_pinned_free(p->hr); sb_pinned_free(p->hdir); sb_pinned_free(p->hw); sb_pinned_free(p->hG); sb_pinned_free(p->hE);
   if (p->eng) sb_destroy(p->eng);
   delete p;
+}
+// The flat model of a multigroup eigenvalue deck - exactly the arrays that cross the C ABI (sb_geom_flat, sb_mg_flat, the sb_clerk
+// lists of both phases, sb_options) plus the package scalars a driver needs (pop, pRNG, keff_0) - written to a little-endian file:
+// "SBFLAT1\0", then a sequence of blocks { int64 count, count items }. tests/c_driver/run_cycle.c reads it and drives the engine
+// through sb_* alone; tests/golden/make_flat_model.py writes the committed fixture with it (no device needed).
+int sbh_model_dump(void* pv, const char* path) {
+  auto* p = (eigenPhysicsPackage*)pv;
+  if (p->isCE) { p->err = "sbh_model_dump: multigroup decks only"; return -1; }
+  FILE* f = fopen(path, "wb");
+  if (!f) { p->err = std::string("sbh_model_dump: cannot open ") + path; return -1; }
+  auto blk = [&](const void* d, int64_t n, size_t sz) { fwrite(&n, 8, 1, f); if (n > 0) fwrite(d, sz, (size_t)n, f); };
+  auto i32 = [&](int32_t v) { blk(&v, 1, 4); };
+  auto f64 = [&](double v) { blk(&v, 1, 8); };
+  fwrite("SBFLAT1\0", 1, 8, f);
+  const sb_geom_flat g = p->geom.view();
+  i32(g.n_surf); blk(g.surf_type, g.n_surf, 4); blk(g.surf_par, (int64_t)g.n_surf * SB_SURF_NPAR, 8);
+  i32(g.n_cell); blk(g.cell_off, g.n_cell + 1, 4); blk(g.cell_surf, g.n_cell > 0 ? g.cell_off[g.n_cell] : 0, 4);
+  i32(g.n_uni); blk(g.uni_type, g.n_uni, 4); blk(g.uni_ipar, (int64_t)g.n_uni * SB_UNI_NIPAR, 4); blk(g.uni_dpar, (int64_t)g.n_uni * SB_UNI_NDPAR, 8);
+  i32(g.n_aux_d); blk(g.aux_d, g.n_aux_d, 8); i32(g.n_aux_i); blk(g.aux_i, g.n_aux_i, 4);
+  i32(g.n_graph); blk(g.graph_idx, g.n_graph, 4); blk(g.graph_id, g.n_graph, 4);
+  i32(g.root_idx); i32(g.border_idx); blk(g.bc, 6, 4);
+  const sb_mg_flat d = p->data.view();
+  const int64_t nm = d.n_mat, ng = d.n_g;
+  i32(d.n_mat); i32(d.n_g); blk(d.data, nm * ng * 6, 8); blk(d.P0, nm * ng * ng, 8); blk(d.prod, nm * ng * ng, 8);
+  blk(d.P1, d.P1 ? nm * ng * ng : 0, 8); blk(d.chi, nm * ng, 8); blk(d.fissile, nm, 4); blk(d.majorant, ng, 8); f64(d.collision_xs);
+  for (int ph = 0; ph < 2; ++ph) {
+    const auto& T = p->tallies[ph];
+    i32((int32_t)T.clerks.size()); i32(T.normClerk); f64(T.normVal);
+    for (const sb_clerk& c : T.clerks) {
+      i32(c.n_maps); i32(c.n_resp); blk(c.resp_mt, SB_MAX_RESP, 4); i32(c.handle_virtual); i32(c.kind); i32(c.cycles);
+      for (int m = 0; m < c.n_maps; ++m) {
+        const sb_map1d& q = c.maps[m];
+        i32(q.type); i32(q.axis); i32(q.grid); i32(q.n_bins); f64(q.first); f64(q.step); i32(q.default_bin);
+        blk(q.bounds, q.bounds ? q.n_bins + 1 : 0, 8); blk(q.mat_bin, q.mat_bin ? nm : 0, 4);
+      }
+    }
+  }
+  i32(p->opt.tracking); f64(p->opt.ht_cutoff); i32(p->opt.st_cache); i32(p->opt.max_pop);
+  i32(p->pop); blk(&p->pRNG, 1, 8); f64(p->keff_0);
+  fclose(f);
+  return 0;
 }
 sb_engine* sbh_engine(void* pv) { return ((eigenPhysicsPackage*)pv)->eng; }
 int sbh_eigen_info(void* pv, int* pop, int* nInactive, int* nActive, int* nG, int* nMat, int* nGraph, int* uniqueCells) {

@@ -69,7 +69,7 @@ def load_library():
         # host driver (scone_b200/csrc/host/physics_package.cpp)
         "sbh_last_error": (C.c_char_p, [vp]),
         "sbh_eigen_create": (vp, [C.c_char_p, C.c_char_p, i32, i32, i32]), "sbh_eigen_destroy": (None, [vp]),
-        "sbh_engine": (vp, [vp]),
+        "sbh_engine": (vp, [vp]), "sbh_model_dump": (i32, [vp, C.c_char_p]),
         "sbh_eigen_info": (i32, [vp] + [ip] * 7),
         "sbh_eigen_total_pop": (i32, [vp]), "sbh_eigen_rng_state": (u64, [vp]), "sbh_eigen_set_rng_state": (None, [vp, u64]), "sbh_eigen_keff0": (dbl, [vp]),
         "sbh_eigen_generate_initial_state": (i32, [vp]),
