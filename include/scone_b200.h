@@ -249,6 +249,15 @@ int sb_resample(sb_engine* h, int tot_pop, uint64_t rng_state);
 int sb_run_cycle_resample(sb_engine* h, uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop,
                           uint64_t rng_state_resample, sb_cycle_result* res);
 
+/* The same for a caller that keeps its dungeons in host memory (what bench.py's `e2e` figure times): upload of the bank (n sites:
+ * r, dir [n][3], w, and G - or E for continuous energy, G then NULL), the cycle, normSize_Repr, and the read-back of the normalised
+ * bank (tot_pop sites) and of the cycle's BIN column (bins_out, may be NULL; sb_tally_size doubles), enqueued together and
+ * synchronised ONCE. Output arrays may be the input arrays.                                                        */
+int sb_run_cycle_resample_host(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G, const double* E,
+                               uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop, uint64_t rng_state_resample,
+                               int* n_out, double* r_out, double* dir_out, double* w_out, int32_t* G_out, double* E_out, double* bins_out,
+                               sb_cycle_result* res);
+
 /* ---- the cycle split for several ranks (one engine = one GPU = one rank) ---------------------
  * Ranks own contiguous shares of the bank (getWorkshare/getOffset, SharedModules/mpi_func.f90:133-159) and
  * exchange once per cycle what SCONE exchanges over MPI; the transport between ranks (NCCL, CUDA-aware MPI,
@@ -334,6 +343,11 @@ int sb_ce_lookup_device(sb_engine* h, int64_t n, const double* dE, const int32_t
 int sb_ce_nuclide_index(sb_engine* h, int nuc_idx, int64_t n, const double* E, int32_t* idx);
 /* CUDA-event time of the last sb_ce_lookup_device launch, in ms */
 int sb_ce_last_kernel_ms(sb_engine* h, double* ms);
+/* device memory of the loaded CE tables: raw_bytes = the nuclide grids and mainData as the reference holds them; index_bytes = what
+ * the engine adds to find and interpolate them (pair records of the total cross section, the per-nuclide hashed index, the
+ * unionised grid and majorant, and - only while it is small, SB_CE_IDXTAB_MAX_MB, default 256 - the [union interval][nuclide]
+ * index table; has_union_table tells whether that one was built). */
+int sb_ce_memory(sb_engine* h, int64_t* raw_bytes, int64_t* index_bytes, int32_t* has_union_table);
 
 /* ---- batch queries used by the parity tests (same device functions as the cycle kernel) ---- */
 /* placeCoord / whatIsAt for n points; if dist != NULL teleport by dist[i] first (geometryStd teleport) */

@@ -100,6 +100,13 @@ class CeDatabase:
             raise EngineError(self._err())
         return idx
 
+    def memory(self):
+        """(bytes of the nuclide tables as the reference holds them, bytes of the lookup structures on top, union index table built?)"""
+        raw, idx, tab = C.c_int64(), C.c_int64(), C.c_int32()
+        if self.L.sb_ce_memory(self.eng, C.byref(raw), C.byref(idx), C.byref(tab)) != 0:
+            raise EngineError(self._err())
+        return raw.value, idx.value, bool(tab.value)
+
     def launch_count(self):
         return int(self.L.sb_launch_count(self.eng))
 
@@ -107,6 +114,28 @@ class CeDatabase:
         if self.eng:
             self.L.sb_destroy(self.eng)
             self.eng = None
+
+
+def refine_nuclide(grid, data, factor):
+    """A nuclide with `factor` times as many grid intervals: factor - 1 points inserted in every interval, log-spaced in energy,
+    cross sections interpolated linearly as the lookup does (the shape of the grid - resonance clusters, sparse tails - is kept)."""
+    g = np.asarray(grid, np.float64); d = np.asarray(data, np.float64)
+    if factor <= 1:
+        return g.copy(), d.copy()
+    t = np.arange(factor)[None, :] / factor
+    lo, hi = g[:-1, None], g[1:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = np.where(lo > 0, lo * (hi / np.where(lo > 0, lo, 1.0)) ** t, lo + (hi - lo) * t)
+    e[:, 0] = g[:-1]
+    f = ((e - lo) / np.where(hi > lo, hi - lo, 1.0))[:, :, None]
+    x = d[1:, None, :] * f + (1.0 - f) * d[:-1, None, :]
+    gg = np.concatenate([e.reshape(-1), g[-1:]]); dd = np.concatenate([x.reshape(-1, d.shape[1]), d[-1:]])
+    # a zero-width interval of the original grid (a discontinuity: the same energy twice) stays one pair of points
+    keep = np.ones(len(gg), bool)
+    zero = np.repeat(g[1:] == g[:-1], factor)
+    inner = np.tile(np.arange(factor) > 0, len(g) - 1)
+    keep[:-1] = ~(zero & inner)
+    return np.ascontiguousarray(gg[keep]), np.ascontiguousarray(dd[keep])
 
 
 def synthetic_nuclides(base, n_total, seed=2026):
@@ -123,3 +152,19 @@ def synthetic_nuclides(base, n_total, seed=2026):
             g[1:-1] = np.sort(gi)
         out.append((g, np.asarray(d, np.float64)))
     return out
+
+
+def large_library(n_nuclides=300, per_material=20, seed=11):
+    """A library that does not fit in the GPU's L2: the reference's five bundled nuclides refined to 2e4 - 6e4 grid points
+    (refine_nuclide) and cloned with seeded energy shifts to n_nuclides; materials of per_material nuclides that together use
+    every nuclide once.  Returns (nuclides, materials) for CeDatabase."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "ce_nuclides.npz"))
+    factors = {"1001": 64, "92233": 16, "52126": 16, "91231": 32, "91232": 96}
+    base = [refine_nuclide(g["grid_" + n], g["data_" + n], f) for n, f in factors.items()]
+    nuclides = synthetic_nuclides(base, n_nuclides, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    order = rng.permutation(n_nuclides)
+    materials = [[(int(k) + 1, float(rng.uniform(1e-5, 5e-2))) for k in order[i:i + per_material]] for i in range(0, n_nuclides, per_material)]
+    return nuclides, materials

@@ -1793,6 +1793,56 @@ int sb_run_cycle_resample(sb_engine* h, uint64_t rng_state, int history_offset, 
   return resampleFinish(h, nullptr, false);
 }
 
+// The whole cycle of a caller that keeps its dungeons in (page-locked) host memory, with ONE host synchronisation: upload of this
+// cycle's bank, transport, cycle close, normSize_Repr, and the read-back of the normalised bank and of the cycle's BIN column are
+// all enqueued on the engine's stream; the sizes of the copies do not depend on anything the device computes (single rank:
+// normSize_Repr returns exactly tot_pop sites). Host arrays must stay untouched until the call returns; they need not be
+// page-locked (the copies are then staged by the driver), the timing figures of bench.py use page-locked ones.
+// E_or_null: continuous-energy banks carry E (G is then not read / written).
+int sb_run_cycle_resample_host(sb_engine* h, int n, const double* r, const double* dir, const double* w, const int32_t* G, const double* E,
+                               uint64_t rng_state, int history_offset, double k_eff, int phase, int tot_pop, uint64_t rng_state_resample,
+                               int* n_out, double* r_out, double* dir_out, double* w_out, int32_t* G_out, double* E_out, double* bins_out,
+                               sb_cycle_result* res) {
+  if (n < 1 || !r || !dir || !w || (!G && !E)) { h->err = "sb_run_cycle_resample_host: invalid bank arguments"; return -1; }
+  if (ensureCapacity(h, std::max(std::max(n, tot_pop), h->opt.max_pop))) return -1;
+  if (2 * tot_pop > h->cap) { h->err = "sb_resample: target population exceeds the bank capacity"; return -1; }
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ensureStage(h, sizeof(double) * 6 * (size_t)h->cap)) return -1;
+  cudaStream_t st = h->stream;
+  {
+    Bank& b = h->bank[h->cur];
+    CUDA_OK(cudaMemcpyAsync(h->dStage, r, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->dStage + 3 * (size_t)h->cap, dir, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (E) { CUDA_OK(cudaMemcpyAsync(b.E, E, sizeof(double) * n, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemsetAsync(b.G, 0, sizeof(int) * n, st)); }
+    else CUDA_OK(cudaMemcpyAsync(b.G, G, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    k_bank_unpack<<<gridFor(h, n, 256), 256, 0, st>>>(h->dStage, h->dStage + 3 * (size_t)h->cap, b, n);
+    h->launches++;
+    h->nCur = n; h->broodValid = false;
+  }
+  if (cycleTransport(h, rng_state, history_offset, k_eff, phase)) return -1;
+  if (cycleCloseEnqueue(h, h->dKsum)) return -1;
+  if (resampleEnqueue(h, tot_pop, rng_state_resample, -1, 0, 1, -1)) return -1;
+  {                                                                   // the normalised bank (tot_pop sites) and the BIN column of the cycle
+    Bank& nb = h->bank[(h->cur + 1) % 3];
+    const int m = tot_pop;
+    k_bank_pack<<<gridFor(h, m, 256), 256, 0, st>>>(nb, h->dStage, h->dStage + 3 * (size_t)h->cap, m);
+    h->launches++;
+    CUDA_OK(cudaMemcpyAsync(r_out, h->dStage, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(dir_out, h->dStage + 3 * (size_t)h->cap, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(w_out, nb.w, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    if (E_out) CUDA_OK(cudaMemcpyAsync(E_out, nb.E, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    else if (G_out) CUDA_OK(cudaMemcpyAsync(G_out, nb.G, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+    if (bins_out && h->nBins[phase] > 0) CUDA_OK(cudaMemcpyAsync(bins_out, h->dLast[phase], sizeof(double) * h->nBins[phase], cudaMemcpyDeviceToHost, st));
+  }
+  if (cycleFinish(h, res)) return -1;                      // the one synchronisation
+  if (h->hCd->nSites <= 0) { h->err = "sb_resample: the fission bank is empty"; return -1; }
+  if (resampleFinish(h, nullptr, false)) return -1;
+  if (h->nCur != tot_pop) { h->err = "sb_run_cycle_resample_host: normSize_Repr did not return the target population"; return -1; }
+  if (n_out) *n_out = h->nCur;
+  return 0;
+}
+
 int sb_resample(sb_engine* h, int totPop, uint64_t rng_state) {
   if (2 * totPop > h->cap) { h->err = "sb_resample: target population exceeds the bank capacity"; return -1; }
   return resampleImpl(h, totPop, rng_state, -1, 0, 1, nullptr);
@@ -2022,7 +2072,10 @@ static int ceLaunch(sb_engine* h, int64_t n, const double* dE, const int* dMat, 
   int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 8);
   if (blocks < 1) blocks = 1;
   CUDA_OK(cudaEventRecord(h->evC0, h->stream));
-  sbce::k_ce_lookup<<<blocks, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, dM, dJ, dIdx, probeNuc, h->dCeErr);
+  if (!h->ce.dev.idxTab && dT && !dM && !dJ && !dIdx)       // total cross sections of a library without the union table: the lean kernel
+    sbce::k_ce_total_hashed<<<(int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 6), 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, h->dCeErr);
+  else
+    sbce::k_ce_lookup<<<blocks, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, dM, dJ, dIdx, probeNuc, h->dCeErr);
   CUDA_OK(cudaEventRecord(h->evC1, h->stream));
   h->launches++;
   int e = 0;
@@ -2153,6 +2206,11 @@ int sb_ce_lookup_device(sb_engine* h, int64_t n, const double* dE, const int32_t
   return ceLaunch(h, n, dE, dMat, dTotal, dMacro, dMajorant, nullptr, 0);
 }
 int sb_ce_last_kernel_ms(sb_engine* h, double* ms) { *ms = h->ceLastMs; return 0; }
+int sb_ce_memory(sb_engine* h, int64_t* raw_bytes, int64_t* index_bytes, int32_t* has_union_table) {
+  if (!h->ce.loaded) { h->err = "continuous-energy data has not been loaded (sb_load_ce_data)"; return -1; }
+  *raw_bytes = h->ce.rawBytes; *index_bytes = h->ce.indexBytes; *has_union_table = h->ce.dev.idxTab ? 1 : 0;
+  return 0;
+}
 int sb_ce_lookup(sb_engine* h, int64_t n, const double* E, const int32_t* mat, double* total, double* macro, double* majorant) {
   CUDA_OK(cudaSetDevice(h->device));
   if (n <= 0) return 0;

@@ -27,6 +27,7 @@ struct eigenPhysicsPackage {
   // settings
   int pop = 0, totalPop = 0, N_inactive = 0, N_active = 0;
   sb_options opt{};
+  double* hBinsP = nullptr; size_t hBinsCap = 0;          // page-locked copy of the cycle's BIN column (host-buffer cycles)
   double keff_0 = 1.0;
   uint64_t pRNG = 0, masterRNG = 0;      // masterRNG: the pRNG of rank 0 (normSize_Repr draws from the master's stream)
   int rank = 0, nRanks = 1;
@@ -349,16 +350,16 @@ struct eigenPhysicsPackage {
   int cycleHostBuffers(int active, double& k_new) {
     if (!eng) return fail("no engine: this handle was created without a device");
     if (hN == 0) { if (downloadBank()) return -1; }
-    if (isCE ? sb_bank_upload_ce(eng, hN, hr, hdir, hw, hE) : sb_bank_upload(eng, hN, hr, hdir, hw, hG)) return engFail();
     const uint64_t rng0 = pRNG;
     stride(totalPop + 1);
-    if (sb_run_cycle_resample(eng, rng0, 0, k_new, active, pop, pRNG, &last)) return engFail();
+    int64_t nb = sb_tally_size(eng, active);
+    if ((int64_t)hBinsCap < std::max<int64_t>(1, nb)) { sb_pinned_free(hBinsP); hBinsCap = (size_t)std::max<int64_t>(1, nb); hBinsP = (double*)sb_pinned_alloc(sizeof(double) * hBinsCap); if (!hBinsP) return fail("pinned host allocation failed"); }
+    // upload, cycle, normSize_Repr, read-back of the bank and of the BIN column: one call, one synchronisation
+    if (sb_run_cycle_resample_host(eng, hN, hr, hdir, hw, isCE ? nullptr : hG, isCE ? hE : nullptr, rng0, 0, k_new, active, pop, pRNG,
+                                   &hN, hr, hdir, hw, isCE ? nullptr : hG, isCE ? hE : nullptr, nb > 0 ? hBinsP : nullptr, &last)) return engFail();
     stride(1);
     if (printBank(active)) return -1;
-    if (downloadBank()) return -1;
-    int64_t nb = sb_tally_size(eng, active);
-    hBins.resize((size_t)std::max<int64_t>(1, nb));
-    if (nb > 0 && sb_tally_last_bins(eng, active, hBins.data())) return engFail();
+    hBins.assign(hBinsP, hBinsP + (size_t)std::max<int64_t>(1, nb));
     k_new = last.k_cum; keff_0 = k_new; cycleK.push_back(k_new);
     (active ? nSegActive : nSegInactive) += last.n_segments;
     nHist += last.n_start;
@@ -404,7 +405,7 @@ void* sbh_eigen_create(const char* deckPath, const char* overrides, int device, 
 }
 void sbh_eigen_destroy(void* pv) {
   auto* p = (eigenPhysicsPackage*)pv; if (!p) return;
-  sb_pinned_free(p->hr); sb_pinned_free(p->hdir); sb_pinned_free(p->hw); sb_pinned_free(p->hG); sb_pinned_free(p->hE);
+  sb_pinned_free(p->hBinsP); sb_pinned_free(p->hr); sb_pinned_free(p->hdir); sb_pinned_free(p->hw); sb_pinned_free(p->hG); sb_pinned_free(p->hE);
   if (p->eng) sb_destroy(p->eng);
   delete p;
 }

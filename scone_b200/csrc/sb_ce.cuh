@@ -32,10 +32,10 @@
 
 namespace sbce {
 
-constexpr int HASH_MBITS = 9;                     // mantissa bits in the bucket key
+constexpr int HASH_MBITS_MIN = 9, HASH_MBITS_MAX = 22;      // mantissa bits in the bucket key of the union grid: about one point per bucket
 
 struct CeDev {                                    // device pointers + sizes, passed by value
-  int nNuc, nMat, nUnion, nBuckets;
+  int nNuc, nMat, nUnion, nBuckets, uShift;
   long long keyMin;
   const double* grid; const double* data; const long long* gridOff; const long long* dataOff; const int* rows; const int* gridSize;
   const int* matOff; const int* matNuc; const double* matDens;
@@ -43,23 +43,29 @@ struct CeDev {                                    // device pointers + sizes, pa
   const double* pairTot; const long long* pairOff;      // per nuclide and grid interval: { E_low, E_top, total_low, total_top }, 32-byte aligned
   const int* activeMat; int nActive;                    // materials the majorant covers (nuclearDatabase%activate: those present in the geometry)
   double eMin, eMax;
+  // per-nuclide hashed index (always built; the only index when idxTab == nullptr, i.e. for libraries whose
+  // [union interval][nuclide] table would not fit): nuclide n keys its grid on the IEEE bits of E shifted by nbShift[n]
+  // (about one grid point per bucket), nbStart[nbOff[n] + b] = number of its grid points whose key is below bucket b
+  const int* nbStart; const long long* nbOff; const int* nbShift; const long long* nbKeyMin; const int* nbCount;
+  const struct NucMeta* nbMeta;                         // the same per nuclide in one 32-byte record (one load per nuclide and lookup)
 };
+struct __align__(32) NucMeta { long long keyMin, nbOff, pairOff; int shift, last; };      // last = index of the last pair record (N - 2)
 
-__host__ __device__ inline long long hashKey(double E) {
+__host__ __device__ inline long long hashKey(double E, int shift) {
   long long b;
 #if defined(__CUDA_ARCH__)
   b = __double_as_longlong(E);
 #else
   memcpy(&b, &E, 8);
 #endif
-  return b >> (52 - HASH_MBITS);
+  return b >> shift;
 }
 
 // number of union points <= E (1 .. nUnion); 0 if E is outside [eMin, eMax].  Row (count - 1) of idxTab holds the
 // nuclide indices; min(count, nUnion - 1) is the floor index on the union grid itself (binarySearch returns N-1 at the top edge)
 __device__ __forceinline__ int unionSearch(const CeDev& c, double E) {
   if (!(E >= c.eMin) || !(E <= c.eMax)) return 0;
-  long long b = hashKey(E) - c.keyMin;
+  long long b = hashKey(E, c.uShift) - c.keyMin;
   b = b < 0 ? 0 : (b >= c.nBuckets ? c.nBuckets - 1 : b);
   int u = __ldg(c.bucketStart + b);
   const int hi = __ldg(c.bucketStart + b + 1);
@@ -71,20 +77,85 @@ __device__ __forceinline__ int unionSearch(const CeDev& c, double E) {
 __device__ __forceinline__ void ldPair(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+// nuclide%search without the union table: the bucket of e in the nuclide's own hashed index, then a short walk.
+// lo = number of grid points whose key is below the key of e (all of them are < e); the points sharing e's bucket may lie on
+// either side of it. Returns what binarySearch(eGrid, e) returns (genericProcedures.f90:132-166): the number of points <= e,
+// at most N - 1.
+__device__ __forceinline__ void nucBucket(const CeDev& c, int nuc0, double e, int& lo, int& hi) {
+  long long b = (__double_as_longlong(e) >> __ldg(c.nbShift + nuc0)) - __ldg(c.nbKeyMin + nuc0);
+  const int nB = __ldg(c.nbCount + nuc0);
+  b = b < 0 ? 0 : (b >= nB ? nB - 1 : b);
+  const int* q = c.nbStart + __ldg(c.nbOff + nuc0) + b;
+  lo = __ldg(q); hi = __ldg(q + 1);
+}
+__device__ __forceinline__ int nucSearch(const CeDev& c, int nuc0, double e) {
+  int p, hi; nucBucket(c, nuc0, e, p, hi);
+  const double* g = c.grid + __ldg(c.gridOff + nuc0);
+  while (p < hi && __ldg(g + p) <= e) ++p;
+  const int N = __ldg(c.gridSize + nuc0);
+  return p < 1 ? 1 : (p > N - 1 ? N - 1 : p);
+}
+// the index of nuclide nuc0 for an energy in union interval u: from the union table when the library has one
+__device__ __forceinline__ int nucIndex(const CeDev& c, int u, double e, int nuc0) {
+  if (c.idxTab) return __ldg(c.idxTab + (size_t)(u - 1) * c.nNuc + nuc0);
+  return nucSearch(c, nuc0, e);
+}
+// the same search walking the 32-byte pair records of the total cross section (the record found is the one the interpolation
+// needs: no separate read of the grid): record i covers [grid(i+1), grid(i+2)) in 1-based grid terms
+__device__ __forceinline__ void nucPairSearch(const CeDev& c, int nuc0, double e, double& E_low, double& E_top, double& s_low, double& s_top) {
+  int lo, hi; nucBucket(c, nuc0, e, lo, hi);
+  const int last = __ldg(c.gridSize + nuc0) - 2;                 // last record
+  int i = lo - 1; i = i < 0 ? 0 : (i > last ? last : i);
+  const double* rec = c.pairTot + 4 * __ldg(c.pairOff + nuc0);
+  ldPair(rec + 4 * (size_t)i, E_low, E_top, s_low, s_top);
+  while (i < last && e >= E_top) { ++i; ldPair(rec + 4 * (size_t)i, E_low, E_top, s_low, s_top); }
+}
 // Sigma_t(material m, E) with E in union interval u: updateTotalMatXS (aceNeutronDatabase_class.f90:509-571)
 __device__ __forceinline__ double matTotal(const CeDev& c, int u, double e, int m) {
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
-  const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
   double tot = 0.0;
   for (int k = k0; k < k1; ++k) {
     const int nuc = __ldg(c.matNuc + k) - 1;
-    const int idx = __ldg(row + nuc);                          // what binarySearch(eGrid, E) returns for this nuclide
     double E_low, E_top, s_low, s_top;
-    ldPair(c.pairTot + 4 * (__ldg(c.pairOff + nuc) + (idx - 1)), E_low, E_top, s_low, s_top);
+    if (c.idxTab) {
+      const int idx = __ldg(c.idxTab + (size_t)(u - 1) * c.nNuc + nuc);    // what binarySearch(eGrid, E) returns for this nuclide
+      ldPair(c.pairTot + 4 * (__ldg(c.pairOff + nuc) + (idx - 1)), E_low, E_top, s_low, s_top);
+    } else nucPairSearch(c, nuc, e, E_low, E_top, s_low, s_top);
     const double f = (e - E_low) / (E_top - E_low);            // nuclide%search
     tot = tot + __ldg(c.matDens + k) * (s_top * f + (1.0 - f) * s_low);      // nuclide%totalXS
   }
   return tot * 1.0;
+}
+// Sigma_t for a library without the union table, as a kernel of its own (few registers: many lookups in flight per SM, which is
+// what a chain of two dependent random memory accesses per nuclide needs): per nuclide one 32-byte record of the hashed index
+// (L1 resident), the bucket entry, then the pair records from that point on. The terms are added in material order (matTotal).
+__global__ void __launch_bounds__(256, 6) k_ce_total_hashed(const CeDev c, long long n, const double* __restrict__ E, const int* __restrict__ mat,
+                                                            double* __restrict__ total, int* __restrict__ err) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const double e = E[t];
+    if (!(e >= c.eMin) || !(e <= c.eMax)) { atomicMax(err, 1); continue; }             // "Failed to find energy"
+    const int m = mat[t];
+    if (m < 1 || m > c.nMat) { atomicMax(err, 2); continue; }
+    const long long eb = __double_as_longlong(e);
+    const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
+    double tot = 0.0;
+#pragma unroll 2
+    for (int k = k0; k < k1; ++k) {
+      const int4* q = (const int4*)(c.nbMeta + (__ldg(c.matNuc + k) - 1));
+      const int4 a = __ldg(q), b = __ldg(q + 1);                                        // { keyMin, nbOff | pairOff, shift, last }
+      const long long keyMin = ((long long)(unsigned)a.x) | ((long long)a.y << 32), nbOff = ((long long)(unsigned)a.z) | ((long long)a.w << 32);
+      const long long pairOff = ((long long)(unsigned)b.x) | ((long long)b.y << 32);
+      int i = __ldg(c.nbStart + nbOff + ((eb >> b.z) - keyMin)) - 1;                    // inside the key range: eMin / eMax lie inside every grid
+      i = i < 0 ? 0 : (i > b.w ? b.w : i);
+      const double* rec = c.pairTot + 4 * pairOff;
+      double E_low, E_top, s_low, s_top;
+      ldPair(rec + 4 * (size_t)i, E_low, E_top, s_low, s_top);
+      while (i < b.w && e >= E_top) { ++i; ldPair(rec + 4 * (size_t)i, E_low, E_top, s_low, s_top); }
+      const double f = (e - E_low) / (E_top - E_low);                                   // nuclide%search
+      tot = tot + __ldg(c.matDens + k) * (s_top * f + (1.0 - f) * s_low);               // nuclide%totalXS
+    }
+    total[t] = tot * 1.0;
+  }
 }
 // initMajorant (:1545-1617): majorant(i) = max over materials of Sigma_t(E_i), nudged up by 1e-6
 __global__ void k_ce_majorant(const CeDev c, double* uMaj) {
@@ -103,7 +174,8 @@ __global__ void __launch_bounds__(256) k_ce_lookup(const CeDev c, long long n, c
                                                    int* __restrict__ probeIdx, int probeNuc, int* __restrict__ err) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double e = E[i];
-    const int u = unionSearch(c, e);
+    // the union interval is needed by the majorant and by the [union interval][nuclide] table; without either only the bounds
+    const int u = (maj || c.idxTab) ? unionSearch(c, e) : ((e >= c.eMin && e <= c.eMax) ? 1 : 0);
     if (u == 0) { atomicMax(err, 1); continue; }               // "Failed to find energy"
     if (maj) {                                                 // updateMajorantXS
       const int uu = u > c.nUnion - 1 ? c.nUnion - 1 : u;
@@ -111,19 +183,18 @@ __global__ void __launch_bounds__(256) k_ce_lookup(const CeDev c, long long n, c
       const double f = (e - E_low) / (E_top - E_low);
       maj[i] = __ldg(c.uMaj + uu) * f + (1.0 - f) * __ldg(c.uMaj + uu - 1);
     }
-    if (probeIdx) probeIdx[i] = __ldg(c.idxTab + (size_t)(u - 1) * c.nNuc + (probeNuc - 1));
+    if (probeIdx) probeIdx[i] = nucIndex(c, u, e, probeNuc - 1);
     if (!total && !macro) continue;
     const int m = mat[i];
     if (m < 1 || m > c.nMat) { atomicMax(err, 2); continue; }
     if (!macro) { total[i] = matTotal(c, u, e, m); continue; }
     const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
-    const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
     double tot = 0.0;
     double xs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = k0; k < k1; ++k) {
       const int nuc = __ldg(c.matNuc + k) - 1;
       const double dens = __ldg(c.matDens + k);
-      const int idx = __ldg(row + nuc);                        // what binarySearch(eGrid, E) returns for this nuclide
+      const int idx = nucIndex(c, u, e, nuc);                  // what binarySearch(eGrid, E) returns for this nuclide
       const double* g = c.grid + __ldg(c.gridOff + nuc) + (idx - 1);
       const double E_low = __ldg(g), E_top = __ldg(g + 1);
       const double f = (e - E_low) / (E_top - E_low);          // nuclide%search
@@ -165,6 +236,7 @@ struct CeHost {
   std::vector<void*> allocs;
   std::vector<double> uGrid, uMaj;
   int nNuc = 0, nMat = 0;
+  long long rawBytes = 0, indexBytes = 0;           // the nuclide tables as the reference holds them / everything this file adds to look them up
   long long algBytesTotal(int nNucInMat) const { return 36LL * nNucInMat + 20; }
 };
 
@@ -216,13 +288,32 @@ static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err, const std::
   if (nU < 2) { err = "sb_load_ce_data: unionised grid has fewer than 2 points"; return -1; }
   // idxTab[j][n] = min(N_n - 1, #{ i : grid_n(i) <= U_j }) : the value of binarySearch for any E in [U_j, U_{j+1})
   // (last row: E == U_last exactly)
-  std::vector<int> idxTab((size_t)nU * nNuc, 1);
-  for (int n = 0; n < nNuc; ++n) {
-    const double* g = &grid[gridOff[n]]; int N = gsize[n], p = 0;
-    for (int j = 0; j < nU; ++j) {
-      while (p < N && g[p] <= u[j]) ++p;
-      idxTab[(size_t)j * nNuc + n] = std::max(1, std::min(N - 1, p));
+  // - only while it stays small: it grows with (union points) x (nuclides); a real library (hundreds of nuclides, 1e6 union
+  // points) is served by the per-nuclide hashed index below, whose size is proportional to the data itself
+  size_t idxTabMax = (size_t)256 << 20;
+  if (const char* e = getenv("SB_CE_IDXTAB_MAX_MB")) idxTabMax = (size_t)atoll(e) << 20;
+  const bool haveTab = (size_t)nU * nNuc * sizeof(int) <= idxTabMax;
+  std::vector<int> idxTab(haveTab ? (size_t)nU * nNuc : 0, 1);
+  if (haveTab)
+    for (int n = 0; n < nNuc; ++n) {
+      const double* g = &grid[gridOff[n]]; int N = gsize[n], p = 0;
+      for (int j = 0; j < nU; ++j) {
+        while (p < N && g[p] <= u[j]) ++p;
+        idxTab[(size_t)j * nNuc + n] = std::max(1, std::min(N - 1, p));
+      }
     }
+  // per-nuclide hashed index: the smallest number of mantissa bits that gives at least one bucket per grid point
+  std::vector<int> nbShift(nNuc), nbCount(nNuc), nbStart; std::vector<long long> nbOff(nNuc), nbKeyMin(nNuc);
+  auto bitsOf = [](double x) { long long b; memcpy(&b, &x, 8); return b; };
+  for (int n = 0; n < nNuc; ++n) {
+    const double* g = &grid[gridOff[n]]; const int N = gsize[n];
+    int shift = 52;
+    for (; shift > 52 - 20; --shift) if ((bitsOf(g[N - 1]) >> shift) - (bitsOf(g[0] > 0.0 ? g[0] : 1.0e-300) >> shift) + 1 >= (long long)N) break;
+    const long long k0 = bitsOf(g[0] > 0.0 ? g[0] : 1.0e-300) >> shift, k1 = bitsOf(g[N - 1]) >> shift;
+    const int nBk = (int)(k1 - k0 + 1);
+    nbShift[n] = shift; nbKeyMin[n] = k0; nbCount[n] = nBk; nbOff[n] = (long long)nbStart.size();
+    int p = 0;
+    for (int b = 0; b <= nBk; ++b) { while (p < N && (bitsOf(g[p]) >> shift) - k0 < b) ++p; nbStart.push_back(p); }
   }
   // pair table of the total cross section: one 32-byte record per nuclide grid interval
   std::vector<long long> pairOff(nNuc); long long po = 0;
@@ -235,19 +326,27 @@ static int ceBuild(CeHost& H, const sb_ce_flat* f, std::string& err, const std::
       q[2] = data[dataOff[n] + (size_t)i * rows[n]]; q[3] = data[dataOff[n] + (size_t)(i + 1) * rows[n]];
     }
   // hash buckets on the IEEE bits
-  const long long keyMin = hashKey(u.front()), keyMax = hashKey(u.back());
+  int uShift = 52 - HASH_MBITS_MIN;
+  while (uShift > 52 - HASH_MBITS_MAX && hashKey(u.back(), uShift) - hashKey(u.front(), uShift) + 1 < (long long)nU) --uShift;
+  const long long keyMin = hashKey(u.front(), uShift), keyMax = hashKey(u.back(), uShift);
   const int nB = (int)(keyMax - keyMin + 1);
   std::vector<int> bucketStart(nB + 1, 0);
-  { int p = 0; for (int b = 0; b <= nB; ++b) { while (p < nU && hashKey(u[p]) - keyMin < b) ++p; bucketStart[b] = p; } }
+  { int p = 0; for (int b = 0; b <= nB; ++b) { while (p < nU && hashKey(u[p], uShift) - keyMin < b) ++p; bucketStart[b] = p; } }
   CeDev& d = H.dev;
-  d.nNuc = nNuc; d.nMat = nMat; d.nUnion = nU; d.nBuckets = nB; d.keyMin = keyMin; d.eMin = u.front(); d.eMax = u.back();
+  d.nNuc = nNuc; d.nMat = nMat; d.nUnion = nU; d.nBuckets = nB; d.uShift = uShift; d.keyMin = keyMin; d.eMin = u.front(); d.eMax = u.back();
   H.uGrid = u; H.uMaj.assign(nU, 0.0);
   d.grid = ceUpload(H, grid, err); d.data = ceUpload(H, data, err); d.gridOff = ceUpload(H, gridOff, err); d.dataOff = ceUpload(H, dataOff, err);
   d.rows = ceUpload(H, rows, err); d.gridSize = ceUpload(H, gsize, err);
   d.matOff = ceUpload(H, matOff, err); d.matNuc = ceUpload(H, matNuc, err); d.matDens = ceUpload(H, matDens, err);
   d.pairTot = ceUpload(H, pairTot, err); d.pairOff = ceUpload(H, pairOff, err);
   d.activeMat = ceUpload(H, active, err); d.nActive = (int)active.size();
-  d.uGrid = ceUpload(H, u, err); d.uMaj = ceUpload(H, H.uMaj, err); d.idxTab = ceUpload(H, idxTab, err); d.bucketStart = ceUpload(H, bucketStart, err);
+  d.uGrid = ceUpload(H, u, err); d.uMaj = ceUpload(H, H.uMaj, err); d.idxTab = haveTab ? ceUpload(H, idxTab, err) : nullptr; d.bucketStart = ceUpload(H, bucketStart, err);
+  std::vector<NucMeta> meta(nNuc);
+  for (int n = 0; n < nNuc; ++n) { meta[n].keyMin = nbKeyMin[n]; meta[n].nbOff = nbOff[n]; meta[n].pairOff = pairOff[n]; meta[n].shift = nbShift[n]; meta[n].last = gsize[n] - 2; }
+  d.nbMeta = ceUpload(H, meta, err);
+  d.nbStart = ceUpload(H, nbStart, err); d.nbOff = ceUpload(H, nbOff, err); d.nbShift = ceUpload(H, nbShift, err); d.nbKeyMin = ceUpload(H, nbKeyMin, err); d.nbCount = ceUpload(H, nbCount, err);
+  H.rawBytes = (long long)(grid.size() + data.size()) * 8;
+  H.indexBytes = (long long)(pairTot.size() * 8 + nbStart.size() * 4 + idxTab.size() * 4 + bucketStart.size() * 4 + (u.size() * 2) * 8);
   if (!err.empty()) return -1;
   H.nNuc = nNuc; H.nMat = nMat; H.loaded = true;
   return 0;

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_events_ce(const CeEventArgs ea) 
 #pragma unroll 1
           for (int k = k0; k < k1; ++k) {
             const int nn = __ldg(X.matNuc + k) - 1;
-            const int idx = __ldg(X.idxTab + (size_t)(u - 1) * X.nNuc + nn);
+            const int idx = sbce::nucIndex(X, u, E, nn);
             double E_low, E_top, s_low, s_top;
             sbce::ldPair(X.pairTot + 4 * (__ldg(X.pairOff + nn) + (idx - 1)), E_low, E_top, s_low, s_top);
             const double f = (E - E_low) / (E_top - E_low);

@@ -59,7 +59,7 @@ struct CeCtx { Model M; Tables T; CeModelDev ce; double* bins; int phase, needMa
 struct NucPoint { int idx; double f; const double* d; int rows; };
 __device__ __forceinline__ NucPoint nucPoint(const sbce::CeDev& c, int u, double e, int nuc0) {      // nuclide%search through the index table
   NucPoint p;
-  p.idx = __ldg(c.idxTab + (size_t)(u - 1) * c.nNuc + nuc0);
+  p.idx = sbce::nucIndex(c, u, e, nuc0);
   const double* g = c.grid + __ldg(c.gridOff + nuc0) + (p.idx - 1);
   const double E_low = __ldg(g), E_top = __ldg(g + 1);
   p.f = (e - E_low) / (E_top - E_low);
@@ -165,12 +165,11 @@ __device__ __noinline__ void scoreInCollCE(const CeCtx& a, const char* base, con
 __device__ __noinline__ double ceMatTotal(const sbce::CeDev& c, int u, double e, int m, unsigned& terms) {
   const int k0 = __ldg(c.matOff + m - 1), k1 = __ldg(c.matOff + m);
   terms += (unsigned)(k1 - k0);
-  const int* row = c.idxTab + (size_t)(u - 1) * c.nNuc;
   double tot = 0.0;
 #pragma unroll NUC_UNROLL
   for (int k = k0; k < k1; ++k) {
     const int nuc = __ldg(c.matNuc + k) - 1;
-    const int idx = __ldg(row + nuc);
+    const int idx = sbce::nucIndex(c, u, e, nuc);
     double E_low, E_top, s_low, s_top;
     sbce::ldPair(c.pairTot + 4 * (__ldg(c.pairOff + nuc) + (idx - 1)), E_low, E_top, s_low, s_top);
     const double f = (e - E_low) / (E_top - E_low);
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_ce(const CeArgs a) {
 #pragma unroll NUC_UNROLL
       for (int k = k0; k < k1; ++k) {
         const int nn = __ldg(X.matNuc + k) - 1;
-        const int idx = __ldg(X.idxTab + (size_t)(u - 1) * X.nNuc + nn);
+        const int idx = sbce::nucIndex(X, u, E, nn);
         double E_low, E_top, s_low, s_top;
         sbce::ldPair(X.pairTot + 4 * (__ldg(X.pairOff + nn) + (idx - 1)), E_low, E_top, s_low, s_top);
         const double f = (E - E_low) / (E_top - E_low);

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import scone_b200
-from scone_b200.ce import CeDatabase, synthetic_nuclides
+from scone_b200.ce import CeDatabase, large_library, synthetic_nuclides
 from tests import ce_util
 from tests import oracle_lib as ol
 
@@ -17,8 +17,10 @@ def edge_energies(nuclides):
     return np.concatenate([pts, np.nextafter(pts[1:], 0.0), np.nextafter(pts[:-1], 100.0)])
 
 
-@pytest.mark.parametrize("case", ["bundled", "synthetic20"])
-def test_lookup_bit_exact(orc, case):
+@pytest.mark.parametrize("case", ["bundled", "synthetic20", "synthetic20_hashed"])
+def test_lookup_bit_exact(orc, case, monkeypatch):
+    if case.endswith("_hashed"):                         # no [union interval][nuclide] table: the per-nuclide hashed index alone
+        monkeypatch.setenv("SB_CE_IDXTAB_MAX_MB", "0")
     if case == "bundled":
         nuclides, materials = ce_util.base_nuclides(), ce_util.MATERIALS_5
     else:
@@ -27,6 +29,7 @@ def test_lookup_bit_exact(orc, case):
         materials = [[(k + 1, float(rng.uniform(1e-5, 5e-2))) for k in range(20)], [(1, 6.6e-2), (3, 3.3e-2)], [(k + 1, float(rng.uniform(1e-5, 5e-2))) for k in range(0, 20, 2)]]
     db, nU = ce_util.oracle_db(orc, nuclides, materials)
     eng = CeDatabase(nuclides, materials, device=0)
+    assert eng.memory()[2] == (not case.endswith("_hashed"))
     # unionised grid and majorant
     ug, um = eng.union()
     og = np.zeros(nU); om = np.zeros(nU); orc.orc_ce_db_union(db, ol.dp(og), ol.dp(om))
@@ -68,4 +71,67 @@ def test_full_size_lookup_properties():
     b = eng.lookup(E, np.full(len(E), 2, np.int32), total=True)
     np.testing.assert_allclose(b["total"], 2.0 * a["total"], rtol=1e-13)
     assert np.mean(b["total"] > a["majorant"] * (1 + 1e-12)) < 1e-3          # violations only next to grid discontinuities
+    eng.close()
+
+
+def test_hashed_library_bit_exact(orc, monkeypatch):
+    """The lookup structures of a library whose union table is not built (per-nuclide hashed index alone), on 60 nuclides of
+    3.6e3 - 5.9e4 grid points: indices, Sigma_t and the macroscopic set against the oracle's binary searches, bit for bit."""
+    monkeypatch.setenv("SB_CE_IDXTAB_MAX_MB", "0")
+    nuclides, materials = large_library(60)
+    db, nU = ce_util.oracle_db(orc, nuclides, materials)
+    eng = CeDatabase(nuclides, materials, device=0)
+    assert not eng.memory()[2]
+    E = np.concatenate([ce_util.log_uniform(400000, 1e-11, 19.9, 17), edge_energies(nuclides[:3]), [1e-11]])
+    for n in (1, 2, 7, 33, 59, 60):
+        oi = np.zeros(len(E), np.int32); orc.orc_ce_db_index_n(db, n, len(E), ol.dp(E), ol.ip(oi))
+        assert np.array_equal(eng.nuclide_index(n, E), oi), "grid index of nuclide %d differs" % n
+    rng = np.random.default_rng(9)
+    mat = rng.integers(1, len(materials) + 1, len(E)).astype(np.int32)
+    got = eng.lookup(E, mat, total=True, macro=True, majorant=True)
+    tot = np.zeros(len(E)); mac = np.zeros((len(E), 8)); maj = np.zeros(len(E))
+    assert orc.orc_ce_db_total_n(db, len(E), ol.dp(E), ol.ip(mat), ol.dp(tot)) == 0
+    assert orc.orc_ce_db_macro_n(db, len(E), ol.dp(E), ol.ip(mat), ol.dp(mac)) == 0
+    assert orc.orc_ce_db_majorant_n(db, len(E), ol.dp(E), ol.dp(maj)) == 0
+    # (equal_nan: an energy exactly on a repeated grid point at the top of a nuclide's grid interpolates 0 / 0 on both sides)
+    assert np.array_equal(got["total"], tot, equal_nan=True) and np.array_equal(got["macro"], mac, equal_nan=True) and np.array_equal(got["majorant"], maj, equal_nan=True)
+    assert np.array_equal(eng.lookup(E, mat, total=True)["total"], tot, equal_nan=True)          # the total-only kernel of the hashed index
+    eng.close(); orc.orc_ce_db_free(db)
+
+
+def test_large_library_full_size():
+    """A library that does not fit in L2: 300 nuclides, 15 materials of 20 nuclides, > 1 GB on the device, no union table.
+    The checker at this size is a numpy restatement of the reference's search and interpolation (the C++ oracle needs minutes to
+    build its majorant for 9.4e6 union points): idx = number of grid points <= E, at most N - 1 (binarySearch,
+    genericProcedures.f90:132-166); f = (E - E(idx)) / (E(idx+1) - E(idx)); sigma = hi * f + (1 - f) * lo
+    (aceNeutronNuclide_class.f90:342-453); Sigma_t = sum over the nuclides in material order of dens * sigma
+    (aceNeutronDatabase_class.f90:509-571).  Bit for bit; sorted and unsorted batches agree; memory stays below twice the tables."""
+    nuclides, materials = large_library(300)
+    eng = CeDatabase(nuclides, materials, device=0)
+    raw, idx, tab = eng.memory()
+    assert not tab and raw > 500e6 and idx <= 1.0 * raw
+    E = np.concatenate([ce_util.log_uniform(200000, 1e-11, 19.9, 23), edge_energies(nuclides[:2]), [1e-11]])
+    rng = np.random.default_rng(4)
+    mat = rng.integers(1, len(materials) + 1, len(E)).astype(np.int32)
+
+    def search(g, e):
+        return np.clip(np.searchsorted(g, e, side="right"), 1, len(g) - 1)
+
+    for n in (1, 2, 150, 300):
+        assert np.array_equal(eng.nuclide_index(n, E), search(nuclides[n - 1][0], E)), "grid index of nuclide %d differs" % n
+    want = np.zeros(len(E))
+    for mi, m in enumerate(materials):
+        sel = np.nonzero(mat == mi + 1)[0]
+        e = E[sel]; acc = np.zeros(len(sel))
+        for nuc, dens in m:
+            g, d = nuclides[nuc - 1]
+            i = search(g, e)
+            with np.errstate(all="ignore"):
+                f = (e - g[i - 1]) / (g[i] - g[i - 1])
+                acc = acc + dens * (d[i, 0] * f + (1.0 - f) * d[i - 1, 0])
+        want[sel] = acc * 1.0
+    got = eng.lookup(E, mat, total=True)["total"]
+    assert np.array_equal(got, want, equal_nan=True) and np.isnan(want).sum() < 10
+    o = np.argsort(E, kind="stable")
+    assert np.array_equal(eng.lookup(E[o], mat[o], total=True)["total"], want[o], equal_nan=True)
     eng.close()
