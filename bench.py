@@ -143,11 +143,11 @@ def ce_lookup_bench(device, n_lookups, cpu_seconds, with_cpu):
     rng = np.random.default_rng(3)
     E_h = np.exp(rng.uniform(np.log(1e-11), np.log(19.0), n_lookups))
 
-    def timed(eng, E, mat, tot):
+    def timed(eng, E, mat, tot, sort=False):
         ms = []
         for it in range(8):
             flush.zero_(); torch.cuda.synchronize()
-            ms.append(eng.lookup_device(E.data_ptr(), mat.data_ptr(), tot.data_ptr(), 0, 0, n=n_lookups))
+            ms.append(eng.lookup_device(E.data_ptr(), mat.data_ptr(), tot.data_ptr(), 0, 0, n=n_lookups, sort=sort))
         return sum(ms[3:]) / len(ms[3:])
 
     # ---- the library that does not fit in L2 --------------------------------------------------------------------------
@@ -158,9 +158,9 @@ def ce_lookup_bench(device, n_lookups, cpu_seconds, with_cpu):
     E = torch.from_numpy(E_h).to(flush.device); mat = torch.from_numpy(m_h).to(flush.device)
     tot = torch.zeros(n_lookups, dtype=torch.float64, device=flush.device)
     k_ms = timed(eng, E, mat, tot)
-    Es, order = torch.sort(E); ms_ = mat[order].contiguous(); tots = torch.zeros_like(tot)
-    k_ms_sorted = timed(eng, Es, ms_, tots)
-    assert torch.equal(tots, tot[order]), "sorted lookups differ from unsorted ones"
+    tots = torch.zeros_like(tot)
+    k_ms_sorted = timed(eng, E, mat, tots, sort=True)          # the engine bins the lookups by (material, energy) itself: sort + lookup timed
+    assert torch.equal(tots.nan_to_num(1e300), tot.nan_to_num(1e300)), "binned lookups differ from unsorted ones"
     alg = (36 * 20 + 20) * n_lookups                                 # 36 B per nuclide + 20 B per lookup
     E_p = torch.from_numpy(E_h).pin_memory(); m_p = torch.from_numpy(m_h).pin_memory(); t_p = torch.zeros(n_lookups, dtype=torch.float64).pin_memory()
     eng.lookup_into(E_p.numpy(), m_p.numpy(), t_p.numpy())
@@ -175,13 +175,16 @@ def ce_lookup_bench(device, n_lookups, cpu_seconds, with_cpu):
            "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg,
            "lookups_per_s": n_lookups / (k_ms * 1e-3), "e2e_lookups_per_s_host_buffers": n_lookups / t_e2e, "e2e_bytes_per_lookup": {"h2d": 12, "d2h": 8},
            "memory": {"nuclide_tables_bytes": raw, "lookup_structures_bytes": idx, "ratio_to_nuclide_tables": (raw + idx) / raw},
-           "sorted_by_energy": {"kernel_ms_per_launch": k_ms_sorted, "achieved": alg / (k_ms_sorted * 1e-3) / 1e9, "frac": alg / (k_ms_sorted * 1e-3) / 1e9 / peak,
-                                "lookups_per_s": n_lookups / (k_ms_sorted * 1e-3), "note": "the same kernel on the same lookups in energy order: neighbouring lanes share sectors, the gathers coalesce"},
+           "binned_by_material_and_energy": {"ms_per_call": k_ms_sorted, "achieved": alg / (k_ms_sorted * 1e-3) / 1e9, "frac": alg / (k_ms_sorted * 1e-3) / 1e9 / peak,
+                                "lookups_per_s": n_lookups / (k_ms_sorted * 1e-3), "traffic": None,
+                                "note": "sb_ce_lookup_sorted_device on the same unsorted batch: counting sort of the lookups by (material, energy bin) on the device + the same lookup "
+                                        "kernel in that order (both inside the timed region); neighbouring lanes gather from the same sectors, results bit-identical"},
            "l2": "flushed before every timed launch (256 MiB memset)",
            "parity": "grid indices and cross sections bit-identical to the CPU restatement's binary searches (tests/test_gpu_ce.py::test_large_library_bit_exact)"}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         out["traffic"] = tr.get("k_ce_lookup_large_dram_bytes_per_launch")
+        out["binned_by_material_and_energy"]["traffic"] = tr.get("k_ce_lookup_large_binned_dram_bytes_per_call")
     except Exception:
         pass
     if with_cpu:
@@ -200,7 +203,7 @@ def ce_lookup_bench(device, n_lookups, cpu_seconds, with_cpu):
         assert np.array_equal(oc, tot[:m].cpu().numpy()), "CE lookup differs from the oracle"
         orc.orc_ce_db_free(db)
     eng.close()
-    del E, mat, tot, Es, ms_, tots
+    del E, mat, tot, tots
 
     # ---- the 20-nuclide library of round 1: tables resident in L2 -----------------------------------------------------
     nuclides, material = ce_nuclides_and_material(20)

@@ -341,6 +341,11 @@ int sb_ce_union(sb_engine* h, double* grid, double* majorant);
 int sb_ce_lookup(sb_engine* h, int64_t n, const double* E, const int32_t* mat, double* total, double* macro, double* majorant);
 int sb_ce_lookup_device(sb_engine* h, int64_t n, const double* dE, const int32_t* dMat, double* dTotal, double* dMacro, double* dMajorant);
 int sb_ce_nuclide_index(sb_engine* h, int nuc_idx, int64_t n, const double* E, int32_t* idx);
+/* the same with the lookups binned by (material, energy) first - the north star's "sorting by material and energy": a counting
+ * sort of the lookup numbers on the device (histogram, scan, scatter), then the same lookup kernel with lane j working on the j-th
+ * lookup of that order, so that the lanes of a warp gather from the same sectors.  Results land in the caller's order and are
+ * bit-identical to sb_ce_lookup_device's.  sb_ce_last_kernel_ms then covers sort + lookup.                               */
+int sb_ce_lookup_sorted_device(sb_engine* h, int64_t n, const double* dE, const int32_t* dMat, double* dTotal, double* dMacro, double* dMajorant);
 /* CUDA-event time of the last sb_ce_lookup_device launch, in ms */
 int sb_ce_last_kernel_ms(sb_engine* h, double* ms);
 /* device memory of the loaded CE tables: raw_bytes = the nuclide grids and mainData as the reference holds them; index_bytes = what

@@ -16,14 +16,15 @@ print("library: %d nuclides, %.0f MB of nuclide tables, %.0f MB of lookup struct
 rng = np.random.default_rng(3)
 E = torch.from_numpy(np.exp(rng.uniform(np.log(1e-11), np.log(19.0), n))).cuda()
 mat = torch.from_numpy(rng.integers(1, len(materials) + 1, n).astype(np.int32)).cuda()
-if len(sys.argv) > 3 and sys.argv[3] == "sorted":
+mode = sys.argv[3] if len(sys.argv) > 3 else ""
+if mode == "sorted":                     # pre-sorted by the caller (energy order)
     E, order = torch.sort(E); mat = mat[order]
 tot = torch.zeros(n, dtype=torch.float64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ms = []
 for it in range(6):
     flush.zero_(); torch.cuda.synchronize()
-    ms.append(db.lookup_device(E.data_ptr(), mat.data_ptr(), tot.data_ptr(), 0, 0, n=n))
+    ms.append(db.lookup_device(E.data_ptr(), mat.data_ptr(), tot.data_ptr(), 0, 0, n=n, sort=(mode == "engine-sort")))
 k = sum(ms[2:]) / len(ms[2:])
 alg = (36 * 20 + 20) * n
 print("%d lookups: %.3f ms, %.3g lookups/s, algorithmic %.0f GB/s" % (n, k, n / (k * 1e-3), alg / (k * 1e-3) / 1e9))

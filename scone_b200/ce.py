@@ -85,9 +85,11 @@ class CeDatabase:
             raise EngineError(self._err())
         return total
 
-    def lookup_device(self, dE, dMat, dTotal=0, dMacro=0, dMajorant=0, n=None):
-        """Device pointers (ints, e.g. torch tensor .data_ptr()); returns the CUDA-event time of the kernel in ms."""
-        if self.L.sb_ce_lookup_device(self.eng, n, dE, dMat, dTotal or None, dMacro or None, dMajorant or None) != 0:
+    def lookup_device(self, dE, dMat, dTotal=0, dMacro=0, dMajorant=0, n=None, sort=False):
+        """Device pointers (ints, e.g. torch tensor .data_ptr()); returns the CUDA-event time of the kernel(s) in ms.
+        sort=True: the engine bins the lookups by (material, energy) first (sb_ce_lookup_sorted_device)."""
+        f = self.L.sb_ce_lookup_sorted_device if sort else self.L.sb_ce_lookup_device
+        if f(self.eng, n, dE, dMat, dTotal or None, dMacro or None, dMajorant or None) != 0:
             raise EngineError(self._err())
         ms = C.c_double()
         self.L.sb_ce_last_kernel_ms(self.eng, C.byref(ms))

@@ -912,6 +912,7 @@ struct sb_engine {
   double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
   int maxSegMin = 256, loneMode = 1, cellCache = 48; unsigned laneMask = 0xffffffffu;
+  int *dCePerm = nullptr, *dCeHist = nullptr, *dCeCursor = nullptr, *dCeTile = nullptr, *dCeNbin = nullptr; size_t cePermCap = 0, ceBinCap = 0;   // sorted CE lookups
   long long* dProfRounds = nullptr;
   // measurement
   bool profiling = false; cudaEvent_t evK0 = nullptr, evK1 = nullptr, evT0 = nullptr, evT1 = nullptr;
@@ -1224,6 +1225,7 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dHProd); cudaFree(h->dHAbs); cudaFree(h->dHLeak); cudaFree(h->dHScat); cudaFree(h->dRn);
   cudaFree(h->dCand); cudaFree(h->dHist); cudaFree(h->dPartial); cudaFree(h->dHot); cudaFree(h->dSeedTab); cudaFree(h->dKsum); cudaFree(h->dNd); cudaFree(h->dRnGlobal); cudaFree(h->dRankCounts); cudaFreeHost(h->hRankCounts); cudaFree(h->dCd); cudaFree(h->dNcur); cudaFreeHost(h->hCd); cudaFree(h->dBlob);
   for (int ph = 0; ph < 2; ++ph) { cudaFree(h->dBins[ph]); cudaFree(h->dLast[ph]); cudaFree(h->dCsum[ph]); cudaFree(h->dCsum2[ph]); }
+  cudaFree(h->dCePerm); cudaFree(h->dCeHist); cudaFree(h->dCeCursor); cudaFree(h->dCeTile); cudaFree(h->dCeNbin);
   cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG); cudaFree(h->dFileSrc);
   if (h->ceStreamIn) { cudaStreamDestroy(h->ceStreamIn); cudaStreamDestroy(h->ceStreamOut); for (int i = 0; i < CE_PIPE; ++i) { cudaEventDestroy(h->ceEvIn[i]); cudaEventDestroy(h->ceEvK[i]); } }
   for (int r = 0; r < PEER_MAX; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerOpened[r]);
@@ -2065,17 +2067,42 @@ int sb_flush_l2(sb_engine* h, size_t bytes) {
 }
 
 // ---- continuous-energy lookup ----------------------------------------------------------------------
-static int ceLaunch(sb_engine* h, int64_t n, const double* dE, const int* dMat, double* dT, double* dM, double* dJ, int* dIdx, int probeNuc) {
+static int ceLaunch(sb_engine* h, int64_t n, const double* dE, const int* dMat, double* dT, double* dM, double* dJ, int* dIdx, int probeNuc, bool sorted = false) {
   if (!h->ce.loaded) { h->err = "continuous-energy data has not been loaded (sb_load_ce_data)"; return -1; }
   if (!h->dCeErr) { CUDA_OK(cudaMalloc(&h->dCeErr, sizeof(int))); CUDA_OK(cudaEventCreate(&h->evC0)); CUDA_OK(cudaEventCreate(&h->evC1)); }
   CUDA_OK(cudaMemsetAsync(h->dCeErr, 0, sizeof(int), h->stream));
   int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 8);
   if (blocks < 1) blocks = 1;
   CUDA_OK(cudaEventRecord(h->evC0, h->stream));
+  const int* perm = nullptr;
+  if (sorted && n > 1) {                                     // bin the lookups by (material, energy): counting sort on the engine's stream
+    if (n > 0x7fffffffLL) { h->err = "sb_ce_lookup_sorted_device: at most 2^31 - 1 lookups per call"; return -1; }
+    long long kLo, kHi; { double a = h->ce.dev.eMin, b = h->ce.dev.eMax; memcpy(&kLo, &a, 8); memcpy(&kHi, &b, 8); }
+    kLo >>= (52 - sbce::SORT_MBITS); kHi >>= (52 - sbce::SORT_MBITS);
+    const int nEb = (int)(kHi - kLo + 1), nBin = nEb * h->ce.dev.nMat;
+    if ((size_t)n > h->cePermCap) { cudaFree(h->dCePerm); h->dCePerm = nullptr; CUDA_OK(cudaMalloc(&h->dCePerm, sizeof(int) * (size_t)n)); h->cePermCap = (size_t)n; }
+    if ((size_t)nBin + 1 > h->ceBinCap) {
+      cudaFree(h->dCeHist); cudaFree(h->dCeCursor); cudaFree(h->dCeTile); cudaFree(h->dCeNbin); h->dCeHist = h->dCeCursor = h->dCeTile = h->dCeNbin = nullptr;
+      h->ceBinCap = (size_t)nBin + 1;
+      CUDA_OK(cudaMalloc(&h->dCeHist, sizeof(int) * h->ceBinCap)); CUDA_OK(cudaMalloc(&h->dCeCursor, sizeof(int) * h->ceBinCap));
+      CUDA_OK(cudaMalloc(&h->dCeTile, sizeof(int) * (h->ceBinCap / SCAN_TILE + 2))); CUDA_OK(cudaMalloc(&h->dCeNbin, sizeof(int)));
+    }
+    CUDA_OK(cudaMemsetAsync(h->dCeHist, 0, sizeof(int) * (size_t)nBin, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->dCeNbin, &nBin, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const int gs = (int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 8);
+    sbce::k_ce_sort_hist<<<gs, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, nEb, kLo, h->dCeHist);
+    const int tiles = (nBin + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<tiles, SCAN_BLOCK, 0, h->stream>>>(h->dCeHist, h->dCeNbin, h->dCeTile);
+    k_scan_tiles<<<1, 1024, 0, h->stream>>>(h->dCeTile, h->dCeNbin, nullptr);
+    k_scan_apply<<<tiles, SCAN_BLOCK, 0, h->stream>>>(h->dCeHist, h->dCeNbin, h->dCeTile, h->dCeCursor);
+    sbce::k_ce_sort_scatter<<<gs, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, nEb, kLo, h->dCeCursor, h->dCePerm);
+    h->launches += 5;
+    perm = h->dCePerm;
+  }
   if (!h->ce.dev.idxTab && dT && !dM && !dJ && !dIdx)       // total cross sections of a library without the union table: the lean kernel
-    sbce::k_ce_total_hashed<<<(int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 6), 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, h->dCeErr);
+    sbce::k_ce_total_hashed<<<(int)std::min<long long>((n + 255) / 256, (long long)h->numSM * 6), 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, h->dCeErr, perm);
   else
-    sbce::k_ce_lookup<<<blocks, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, dM, dJ, dIdx, probeNuc, h->dCeErr);
+    sbce::k_ce_lookup<<<blocks, 256, 0, h->stream>>>(h->ce.dev, n, dE, dMat, dT, dM, dJ, dIdx, probeNuc, h->dCeErr, perm);
   CUDA_OK(cudaEventRecord(h->evC1, h->stream));
   h->launches++;
   int e = 0;
@@ -2205,6 +2232,11 @@ int sb_ce_lookup_device(sb_engine* h, int64_t n, const double* dE, const int32_t
   CUDA_OK(cudaSetDevice(h->device));
   return ceLaunch(h, n, dE, dMat, dTotal, dMacro, dMajorant, nullptr, 0);
 }
+int sb_ce_lookup_sorted_device(sb_engine* h, int64_t n, const double* dE, const int32_t* dMat, double* dTotal, double* dMacro, double* dMajorant) {
+  CUDA_OK(cudaSetDevice(h->device));
+  if (!dMat) { h->err = "sb_ce_lookup_sorted_device: material indices are required"; return -1; }
+  return ceLaunch(h, n, dE, dMat, dTotal, dMacro, dMajorant, nullptr, 0, true);
+}
 int sb_ce_last_kernel_ms(sb_engine* h, double* ms) { *ms = h->ceLastMs; return 0; }
 int sb_ce_memory(sb_engine* h, int64_t* raw_bytes, int64_t* index_bytes, int32_t* has_union_table) {
   if (!h->ce.loaded) { h->err = "continuous-energy data has not been loaded (sb_load_ce_data)"; return -1; }
@@ -2240,8 +2272,11 @@ int sb_ce_lookup(sb_engine* h, int64_t n, const double* E, const int32_t* mat, d
     CUDA_OK(cudaEventRecord(h->ceEvIn[c], sIn));
     CUDA_OK(cudaStreamWaitEvent(st, h->ceEvIn[c], 0));
     int blocks = (int)std::min<long long>((m + 255) / 256, (long long)h->numSM * 8);
-    sbce::k_ce_lookup<<<blocks, 256, 0, st>>>(h->ce.dev, m, dE + o, mat ? dMat + o : nullptr, total ? dT + o : nullptr, macro ? dM + 8 * o : nullptr,
-                                              majorant ? dJ + o : nullptr, nullptr, 0, h->dCeErr);
+    if (!h->ce.dev.idxTab && total && !macro && !majorant && mat)
+      sbce::k_ce_total_hashed<<<(int)std::min<long long>((m + 255) / 256, (long long)h->numSM * 6), 256, 0, st>>>(h->ce.dev, m, dE + o, dMat + o, dT + o, h->dCeErr, nullptr);
+    else
+      sbce::k_ce_lookup<<<blocks, 256, 0, st>>>(h->ce.dev, m, dE + o, mat ? dMat + o : nullptr, total ? dT + o : nullptr, macro ? dM + 8 * o : nullptr,
+                                                majorant ? dJ + o : nullptr, nullptr, 0, h->dCeErr, nullptr);
     h->launches++;
     CUDA_OK(cudaEventRecord(h->ceEvK[c], st));
     CUDA_OK(cudaStreamWaitEvent(sOut, h->ceEvK[c], 0));

@@ -129,9 +129,11 @@ __device__ __forceinline__ double matTotal(const CeDev& c, int u, double e, int 
 // Sigma_t for a library without the union table, as a kernel of its own (few registers: many lookups in flight per SM, which is
 // what a chain of two dependent random memory accesses per nuclide needs): per nuclide one 32-byte record of the hashed index
 // (L1 resident), the bucket entry, then the pair records from that point on. The terms are added in material order (matTotal).
+// perm: lane j of the launch handles lookup perm[j] (the lookups binned by material and energy, k_ce_sort_*); nullptr: lookup j
 __global__ void __launch_bounds__(256, 6) k_ce_total_hashed(const CeDev c, long long n, const double* __restrict__ E, const int* __restrict__ mat,
-                                                            double* __restrict__ total, int* __restrict__ err) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+                                                            double* __restrict__ total, int* __restrict__ err, const int* __restrict__ perm) {
+  for (long long tj = blockIdx.x * (long long)blockDim.x + threadIdx.x; tj < n; tj += (long long)gridDim.x * blockDim.x) {
+    const long long t = perm ? perm[tj] : tj;
     const double e = E[t];
     if (!(e >= c.eMin) || !(e <= c.eMax)) { atomicMax(err, 1); continue; }             // "Failed to find energy"
     const int m = mat[t];
@@ -157,6 +159,25 @@ __global__ void __launch_bounds__(256, 6) k_ce_total_hashed(const CeDev c, long 
     total[t] = tot * 1.0;
   }
 }
+// The lookups of a batch binned by (material, energy): bin = (mat - 1) * nEb + (IEEE key of E with 10 mantissa bits) - so that the
+// lanes of a warp ask for the same nuclides at neighbouring energies and their gathers fall into the same sectors.  A counting
+// sort: histogram, exclusive scan (the engine's scan kernels), scatter of the lookup numbers (order inside a bin is arbitrary; every
+// lookup is computed exactly as in an unsorted launch, only the lane that computes it changes).
+constexpr int SORT_MBITS = 10;
+__device__ __forceinline__ int sortBin(const CeDev& c, double e, int m, int nEb, long long keyLo) {
+  long long b = (__double_as_longlong(e) >> (52 - SORT_MBITS)) - keyLo;
+  b = b < 0 ? 0 : (b >= nEb ? nEb - 1 : b);
+  const int mm = (m < 1 || m > c.nMat) ? 1 : m;
+  return (mm - 1) * nEb + (int)b;
+}
+__global__ void k_ce_sort_hist(const CeDev c, long long n, const double* __restrict__ E, const int* __restrict__ mat, int nEb, long long keyLo, int* __restrict__ hist) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(hist + sortBin(c, E[i], mat ? mat[i] : 1, nEb, keyLo), 1);
+}
+__global__ void k_ce_sort_scatter(const CeDev c, long long n, const double* __restrict__ E, const int* __restrict__ mat, int nEb, long long keyLo, int* __restrict__ cursor, int* __restrict__ perm) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    perm[atomicAdd(cursor + sortBin(c, E[i], mat ? mat[i] : 1, nEb, keyLo), 1)] = (int)i;
+}
 // initMajorant (:1545-1617): majorant(i) = max over materials of Sigma_t(E_i), nudged up by 1e-6
 __global__ void k_ce_majorant(const CeDev c, double* uMaj) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.nUnion; j += gridDim.x * blockDim.x) {
@@ -171,8 +192,9 @@ __global__ void k_ce_majorant(const CeDev c, double* uMaj) {
 // total / macro set (8 values) / majorant / per-nuclide index of nuclide `probeNuc`, whichever output pointers are given
 __global__ void __launch_bounds__(256) k_ce_lookup(const CeDev c, long long n, const double* __restrict__ E, const int* __restrict__ mat,
                                                    double* __restrict__ total, double* __restrict__ macro, double* __restrict__ maj,
-                                                   int* __restrict__ probeIdx, int probeNuc, int* __restrict__ err) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+                                                   int* __restrict__ probeIdx, int probeNuc, int* __restrict__ err, const int* __restrict__ perm) {
+  for (long long ij = blockIdx.x * (long long)blockDim.x + threadIdx.x; ij < n; ij += (long long)gridDim.x * blockDim.x) {
+    const long long i = perm ? perm[ij] : ij;
     const double e = E[i];
     // the union interval is needed by the majorant and by the [union interval][nuclide] table; without either only the bounds
     const int u = (maj || c.idxTab) ? unionSearch(c, e) : ((e >= c.eMin && e <= c.eMax) ? 1 : 0);

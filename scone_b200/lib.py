@@ -62,7 +62,7 @@ def load_library():
         "sb_profile_peer_stages": (i32, [vp, dp, dp]),
         "sb_flush_l2": (i32, [vp, C.c_size_t]), "sb_pinned_alloc": (vp, [C.c_size_t]), "sb_pinned_free": (None, [vp]),
         "sb_load_ce_data": (i32, [vp, vp]), "sb_ce_union_size": (i32, [vp]), "sb_ce_union": (i32, [vp, dp, dp]),
-        "sb_ce_lookup": (i32, [vp, i64, dp, ip, dp, dp, dp]), "sb_ce_lookup_device": (i32, [vp, i64, vp, vp, vp, vp, vp]),
+        "sb_ce_lookup": (i32, [vp, i64, dp, ip, dp, dp, dp]), "sb_ce_lookup_device": (i32, [vp, i64, vp, vp, vp, vp, vp]), "sb_ce_lookup_sorted_device": (i32, [vp, i64, vp, vp, vp, vp, vp]),
         "sb_ce_nuclide_index": (i32, [vp, i32, i64, dp, ip]), "sb_ce_last_kernel_ms": (i32, [vp, dp]),
         "sb_ce_memory": (i32, [vp, C.POINTER(i64), C.POINTER(i64), ip]),
         "sb_rng_query": (i32, [i64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), dp]),

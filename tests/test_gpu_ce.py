@@ -134,4 +134,9 @@ def test_large_library_full_size():
     assert np.array_equal(got, want, equal_nan=True) and np.isnan(want).sum() < 10
     o = np.argsort(E, kind="stable")
     assert np.array_equal(eng.lookup(E[o], mat[o], total=True)["total"], want[o], equal_nan=True)
+    # the engine's own binning by (material, energy): same numbers, in the caller's order
+    import torch
+    dE = torch.from_numpy(E).cuda(); dm = torch.from_numpy(mat).cuda(); dt = torch.zeros(len(E), dtype=torch.float64, device="cuda")
+    eng.lookup_device(dE.data_ptr(), dm.data_ptr(), dt.data_ptr(), 0, 0, n=len(E), sort=True)
+    assert np.array_equal(dt.cpu().numpy(), want, equal_nan=True)
     eng.close()
