@@ -193,19 +193,23 @@ __global__ void k_sum_partials(const RedOut* partial, double* ksum, const CycleD
 struct UserKeff { int n; int kind[4]; int addr[4]; };
 // tallyAdmin%reportCycleEnd (tallyAdmin_class.f90:735-794) for the attachment clerks + normalisation factor
 //   keffAnalogClerk%closeCycle (keffAnalogClerk_class.f90:156-176), keffImplicitClerk%closeCycle (:292-312)
-__global__ void k_close_cycle_head(const double* ksum, CycleDev* cd, int phase, double kNorm,
+// ksum: the score sums the attachment clerks close with (reduced over the ranks in a ranked run: that tally is mpiSync in the
+// reference, eigenPhysicsPackage_class.f90:605-640); ksumLocal: this rank's own sums, which is what the k-eff clerks of the
+// deck's own tally blocks hold (those are not synchronised per cycle; collectDistributed sums them once at the end)
+__global__ void k_close_cycle_head(const double* ksum, const double* ksumLocal, CycleDev* cd, int phase, double kNorm,
                                    double* bins, int normAddr, double normVal, UserKeff uk, double* csum, double* csum2) {
   if (threadIdx.x != 0) return;
   const double prod = ksum[0], abs_ = ksum[1], leak = ksum[2], scat = ksum[3], wgt = ksum[4], endW = ksum[5];
   for (int i = 0; i < uk.n; ++i) {                          // user clerks: scores into BIN (closed with the other bins), k accumulated directly
     const int a0 = uk.addr[i] - 1;
+    const double lprod = ksumLocal[0], labs = ksumLocal[1], lleak = ksumLocal[2], lscat = ksumLocal[3], lwgt = ksumLocal[4], lend = ksumLocal[5];
     if (uk.kind[i] == SB_CLERK_KEFF_ANALOG) {               // keffAnalogClerk_class.f90:132-176
-      bins[a0] = wgt; bins[a0 + 1] = endW;
-      const double k = endW / wgt * kNorm;
+      bins[a0] = lwgt; bins[a0 + 1] = lend;
+      const double k = lend / lwgt * kNorm;
       csum[a0 + 2] = csum[a0 + 2] + k; csum2[a0 + 2] = csum2[a0 + 2] + k * k;
     } else {                                                // keffImplicitClerk_class.f90:180-312
-      bins[a0] = prod; bins[a0 + 1] = abs_; bins[a0 + 2] = scat; bins[a0 + 3] = leak;
-      const double k = prod / (abs_ + leak - scat);
+      bins[a0] = lprod; bins[a0 + 1] = labs; bins[a0 + 2] = lscat; bins[a0 + 3] = lleak;
+      const double k = lprod / (labs + lleak - lscat);
       csum[a0 + 4] = csum[a0 + 4] + k; csum2[a0 + 4] = csum2[a0 + 4] + k * k;
     }
   }
@@ -926,6 +930,7 @@ struct sb_engine {
   bool fixedSource = false; int stkCap = 50; double* dStkD = nullptr; int* dStkG = nullptr; size_t stkLanes = 0; int stkAllocCap = 0;
   // peer-memory exchange between the ranks of a node (sb_peer_*)
   int peerRanks = 0, peerRank = 0, peerCap = 0; char* peerRegion = nullptr; PeerPtrs peerPtrs{}; void* peerOpened[PEER_MAX] = {};
+  double* dKsumRed = nullptr;          // score sums reduced over the ranks by the caller (sb_cycle_end_resample_ranked)
   PeerPlan* dPlan = nullptr; PeerPlan* hPlan = nullptr; double* dKsumTot = nullptr; unsigned long long peerSeq = 0; double peerTimeoutS = 20.0;
   struct ShannonRec { int clerk, addr, nBins, maxCycles, cycle; };
   std::vector<ShannonRec> shannon[2];     // shannonEntropyClerk records of each phase; cycle = reportCycleEnd calls so far
@@ -1229,7 +1234,7 @@ void sb_destroy(sb_engine* h) {
   cudaFree(h->dStage); sbce::ceFree(h->ce); cudaFree(h->dCeErr); cudaFree(h->dCeSlots); cudaFree(h->dStkD); cudaFree(h->dStkG); cudaFree(h->dFileSrc);
   if (h->ceStreamIn) { cudaStreamDestroy(h->ceStreamIn); cudaStreamDestroy(h->ceStreamOut); for (int i = 0; i < CE_PIPE; ++i) { cudaEventDestroy(h->ceEvIn[i]); cudaEventDestroy(h->ceEvK[i]); } }
   for (int r = 0; r < PEER_MAX; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerOpened[r]);
-  cudaFree(h->peerRegion); cudaFree(h->dPlan); cudaFreeHost(h->hPlan); cudaFree(h->dKsumTot);
+  cudaFree(h->peerRegion); cudaFree(h->dPlan); cudaFreeHost(h->hPlan); cudaFree(h->dKsumTot); cudaFree(h->dKsumRed);
   for (void* p : h->ceAllocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1666,7 +1671,7 @@ static int cycleCloseEnqueue(sb_engine* h, const double* dKsum) {
   if (phase < 0) { h->err = "sb_cycle_end: no cycle is open"; return -1; }
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  k_close_cycle_head<<<1, 32, 0, st>>>(dKsum, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase],
+  k_close_cycle_head<<<1, 32, 0, st>>>(dKsum, h->dKsum, h->dCd, phase, h->kNormNext, h->dBins[phase], h->normAddr[phase], h->normVal[phase],
                                        h->userKeff[phase], h->dCsum[phase], h->dCsum2[phase]);
   for (auto& sr : h->shannon[phase]) {                       // reportCycleEnd + closeCycle of the entropy clerks, on the un-normalised bank
     sr.cycle += 1;
@@ -1871,8 +1876,9 @@ int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_
   if (tot > 2000000000LL || tot <= 0) { h->err = "sb_cycle_end_resample_ranked: invalid total number of sites"; return -1; }
   if (!h->dRankCounts) { CUDA_OK(cudaMalloc(&h->dRankCounts, 64 * sizeof(int))); CUDA_OK(cudaMallocHost(&h->hRankCounts, 64 * sizeof(int))); }
   cudaStream_t st = h->stream;
-  CUDA_OK(cudaMemcpyAsync(h->dKsum, host_sums, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (cycleCloseEnqueue(h, h->dKsum)) return -1;
+  if (!h->dKsumRed) CUDA_OK(cudaMalloc(&h->dKsumRed, 8 * sizeof(double)));
+  CUDA_OK(cudaMemcpyAsync(h->dKsumRed, host_sums, 6 * sizeof(double), cudaMemcpyHostToDevice, st));     // (the rank's own sums stay in dKsum: user k-eff clerks)
+  if (cycleCloseEnqueue(h, h->dKsumRed)) return -1;
   if (resampleEnqueue(h, tot_pop, master_rng_state, (int)tot, (int)off, 0, pop_sizes[rank])) return -1;
   CUDA_OK(cudaMemsetAsync(h->dRankCounts, 0, 64 * sizeof(int), st));
   k_norm_rank_counts<<<gridFor(h, tot, 256), 256, 0, st>>>(h->dRnGlobal, h->dCd, h->dNd, ro, h->dRankCounts);

@@ -28,7 +28,7 @@ using namespace sbd;
 enum { HU_ROOTBOX = 1, HU_PIN = 2, HU_LAT = 3, HU_COLD = 4 };
 enum { HF_ROT = 1, HF_GLOBAL = 2, HF_LAT2D = 4, HF_OFFALL = 8, HF_OFFMAP = 16, HF_ORG0 = 32 };
 
-// one universe, 192 bytes, laid out for 16-byte shared-memory loads.  Per axis a: ci[a] = {corner, 1/pitch},
+// one universe, 208 bytes, laid out for 16-byte shared-memory loads.  Per axis a: ci[a] = {corner, 1/pitch},
 // ph[a] = {pitch, pitch/2}, ab[a] = a_bar.  ROOTBOX: ci[a].x = box origin, ph[a].x = halfwidth, ab[0] = surface tolerance
 struct __align__(16) HUni {
   int type, flags, n0, n1, n2, outID, aux, pad;
@@ -36,8 +36,9 @@ struct __align__(16) HUni {
   double2 ci[3];
   double2 ph[3];
   double ab[3], pad1;
+  double pad2[2];                      // 208 bytes = 52 words: consecutive universes start 20 banks apart (192 bytes would put every second one on the same banks)
 };
-static_assert(sizeof(HUni) == 192, "HUni layout");
+static_assert(sizeof(HUni) == 208, "HUni layout");
 
 struct HotLayout {
   int bytes;

@@ -67,6 +67,30 @@ def test_ranked_run_reproduces_single_rank_histories(tmp_path, deck, pop, ws):
     pp.close()
 
 
+@pytest.mark.parametrize("exchange", ["gloo", "peer"])
+def test_ranked_user_keff_clerks_hold_the_ranks_own_scores(tmp_path, exchange):
+    """A keffImplicitClerk named in the deck's own activeTally is not synchronised per cycle in the reference (only the
+    attachment tally is mpiSync): every rank accumulates ITS scores and collectDistributed adds the ranks up at the end.
+    The four score bins of the ranks must then add up to the single-rank run's; with the rank-global sums in them the total
+    would come out n_ranks times too large."""
+    pop, ws, ninact, nact = 12000, 2, 2, 3
+    ov = ("pop %d; inactive %d; active %d; seed 777; activeTally { kimp { type keffImplicitClerk; } "
+          "fis { type collisionClerk; response (f); f { type macroResponse; MT -6; } } }" % (pop, ninact, nact))
+    run_ranks(ws, "gloo", DECK["c5g7"], ov, ninact, nact, tmp_path, extra=(("peer",) if exchange == "peer" else ()))
+    pp = scone_b200.EigenPhysicsPackage(DECK["c5g7"], ov, device=0)
+    pp.generateInitialState()
+    for c in range(ninact + nact):
+        pp.cycle(c >= ninact)
+    cs, cs2, nb = pp.tally(True)
+    fin = [np.load(os.path.join(tmp_path, "final_r%d.npz" % r)) for r in range(ws)]
+    tot = sum(f["cs"] for f in fin)
+    np.testing.assert_allclose(tot[:4], cs[:4], rtol=1e-11)            # IMP_PROD, IMP_ABS, SCATTER_PROD, ANA_LEAK: additive over ranks
+    np.testing.assert_allclose(tot[5:], cs[5:], rtol=1e-10, atol=1e-300)   # the collision clerk behind it
+    for f in fin:                                                       # each rank's own k estimate is a k-eff, not a multiple of one
+        assert 0.5 < f["cs"][4] / nb < 2.0
+    pp.close()
+
+
 def test_ranked_source_dumps_concatenate_to_the_single_rank_dump(tmp_path):
     """printSource with several ranks: every rank writes <outputFile>_source<i>_rank<r> AFTER the load balancing
     (eigenPhysicsPackage_class.f90:275-281); the rank files in rank order hold the sites of the single-rank dump.  broodID is the
