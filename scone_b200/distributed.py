@@ -212,6 +212,12 @@ def cycle(pp, active, comm):
 def load_balance(pp, comm, sizes):
     """particleDungeon%loadBalancing on the device banks."""
     L, eng = pp.L, pp.engine
+    # every rank works out the plan of EVERY rank from the same sizes, so that a distribution nearest-neighbour transfers cannot
+    # fix (a rank would have to pass on sites it has not received yet) is refused by all ranks together, before anyone waits in
+    # a receive; the peer-memory path does the same on the device (k_peer_plan, SB_ERR_BALANCE)
+    for r in range(comm.size):
+        if r != comm.rank:
+            balance_plan(pp.total_pop, comm.size, r, sizes)
     send_up, recv_up, send_down, recv_down = balance_plan(pp.total_pop, comm.size, comm.rank, sizes)
     if not (send_up or recv_up or send_down or recv_down):
         return

@@ -28,6 +28,25 @@ def test_workshare_matches_mpi_func():
     assert [D.workshare(10, 4, r) for r in range(4)] == [(2, 0), (2, 2), (3, 4), (3, 7)]
 
 
+def test_unbalanceable_distribution_is_seen_by_every_rank():
+    """sizes (0, 0, 12) over three ranks: rank 1 would have to pass on sites it has not received yet; nearest-neighbour transfers
+    cannot do that. load_balance works out the plan of every rank on every rank, so all of them refuse before anyone waits."""
+    import pytest
+    from scone_b200.lib import EngineError
+    sizes = [0, 0, 12]
+    failing = []
+    for r in range(3):
+        try:
+            D.balance_plan(12, 3, r, sizes)
+        except EngineError:
+            failing.append(r)
+    assert failing == [2] or failing                         # at least one rank's plan is impossible ...
+    for me in range(3):                                      # ... and the loop every rank runs in load_balance finds it whoever `me` is
+        with pytest.raises(EngineError):
+            for r in range(3):
+                D.balance_plan(12, 3, r, sizes)
+
+
 def test_balance_plan_restores_target_offsets():
     rng = np.random.default_rng(5)
     for ws in (2, 3, 4, 8):
