@@ -32,6 +32,19 @@
 using namespace sbd;
 using sbh::Bank; using sbh::CycleDev; using sbh::HistArgs; using sbh::HotLayout; using sbh::HUni;
 
+// Programmatic dependent launch for the chain of small kernels that closes a cycle (brood ordering, reductions, cycle close,
+// normSize_Repr, the peer exchange): each of them starts with PDL_ENTER - let the next kernel of the stream be scheduled now, then
+// wait until everything before this kernel has completed and is visible - so the launch latency and the prologue of kernel i + 1
+// overlap the execution of kernel i; the data dependencies are the same as with plain stream order.
+#define PDL_ENTER() do { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+template <typename... P, typename... A>
+static inline void pdlLaunch(void (*k)(P...), int grid, int block, cudaStream_t st, A&&... a) {
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at{}; at.id = cudaLaunchAttributeProgrammaticStreamSerialization; at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, P(a)...);
+}
+
 #define CUDA_OK(call)                                                                         \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
@@ -67,6 +80,7 @@ __device__ __forceinline__ int blockExclusiveScan(int v, int* sWarp, int& blockT
 
 // nPtr: device pointer to the element count (so no host sync is needed); nMax bounds the grid
 __global__ void k_scan_reduce(const int* in, const int* nPtr, int* tileSums) {
+  PDL_ENTER();
   __shared__ int sWarp[33];
   int n = *nPtr;
   int tile = blockIdx.x;
@@ -79,6 +93,7 @@ __global__ void k_scan_reduce(const int* in, const int* nPtr, int* tileSums) {
   if (threadIdx.x == 0) tileSums[tile] = tot;
 }
 __global__ void __launch_bounds__(1024) k_scan_tiles(int* tileSums, const int* nPtr, int* totalOut) {
+  PDL_ENTER();
   __shared__ int sWarp[33];
   __shared__ int carry;
   int n = *nPtr;
@@ -98,6 +113,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(int* tileSums, const int* n
   if (threadIdx.x == 0 && totalOut) *totalOut = carry;
 }
 __global__ void k_scan_apply(const int* in, const int* nPtr, const int* tileSums, int* out) {
+  PDL_ENTER();
   __shared__ int sWarp[33];
   int n = *nPtr;
   int tile = blockIdx.x;
@@ -117,6 +133,7 @@ __global__ void k_scan_apply(const int* in, const int* nPtr, const int* tileSums
 // (brood, seq) is offset[brood] + seq.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_sort_sites(Bank src, Bank dst, const int* offsets, const CycleDev* cd, int cap) {
+  PDL_ENTER();
   int n = min(cd->nSites, cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     int b = src.brood[s];
@@ -144,6 +161,7 @@ __device__ __forceinline__ double warpSum(double v) {
 // the same blocks also sum the weights of the (sorted) next-cycle bank: popWeight for keffAnalogClerk%reportCycleEnd
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(int n, const double* hProd, const double* hAbs, const double* hLeak, const double* hScat,
                                                              const double* wIn, const double* wSites, const CycleDev* cd, int cap, RedOut* partial) {
+  PDL_ENTER();
   __shared__ double sd[6][RED_THREADS / 32];
   // contiguous slice per block, strided by thread inside the slice: fixed order for fixed n
   double v[6] = {0, 0, 0, 0, 0, 0};
@@ -174,6 +192,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_hist(int n, const double
 // (the bins of keffImplicitClerk / keffAnalogClerk that are reduced across ranks every cycle: mpiSync = 1,
 //  eigenPhysicsPackage_class.f90:605-640, scoreMemory_class.f90:404-431)
 __global__ void k_sum_partials(const RedOut* partial, double* ksum, const CycleDev* cd, int cap) {
+  PDL_ENTER();
   const int lane = threadIdx.x;
   double v[6] = {0, 0, 0, 0, 0, 0};
   for (int i = lane; i < RED_BLOCKS; i += 32) {
@@ -198,6 +217,7 @@ struct UserKeff { int n; int kind[4]; int addr[4]; };
 // deck's own tally blocks hold (those are not synchronised per cycle; collectDistributed sums them once at the end)
 __global__ void k_close_cycle_head(const double* ksum, const double* ksumLocal, CycleDev* cd, int phase, double kNorm,
                                    double* bins, int normAddr, double normVal, UserKeff uk, double* csum, double* csum2) {
+  PDL_ENTER();
   if (threadIdx.x != 0) return;
   const double prod = ksum[0], abs_ = ksum[1], leak = ksum[2], scat = ksum[3], wgt = ksum[4], endW = ksum[5];
   for (int i = 0; i < uk.n; ++i) {                          // user clerks: scores into BIN (closed with the other bins), k accumulated directly
@@ -236,6 +256,7 @@ __global__ void k_close_cycle_head(const double* ksum, const double* ksumLocal, 
 }
 // scoreMemory%closeCycle (scoreMemory_class.f90:309-342)
 __global__ void k_close_cycle_bins(double* bins, double* lastBins, double* csum, double* csum2, int nBins, const CycleDev* cd) {
+  PDL_ENTER();
   double nf = cd->normFactor;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nBins; i += gridDim.x * blockDim.x) {
     double b = bins[i];
@@ -256,6 +277,7 @@ __global__ void k_close_cycle_bins(double* bins, double* lastBins, double* csum,
 // ------------------------------------------------------------------------------------------------
 struct NormDev { int nGlobal, offLocal, nLocal, totPop, check, pad; };
 __global__ void k_norm_setup(NormDev* nd, const CycleDev* cd, int cap, int totPop, int nGlobal, int offLocal, int check) {
+  PDL_ENTER();
   int nLocal = min(cd->nSites, cap);
   nd->nLocal = nLocal; nd->totPop = totPop; nd->check = check;
   nd->nGlobal = (nGlobal < 0) ? nLocal : nGlobal;
@@ -264,6 +286,7 @@ __global__ void k_norm_setup(NormDev* nd, const CycleDev* cd, int cap, int totPo
 constexpr int RN_CHUNK = 16;
 // rn_j = j-th number of the LCG stream started at `state0` (j = 1..n), stored as the integer state
 __global__ void k_rn_generate(unsigned long long* rn, const NormDev* nd, uint64_t state0) {
+  PDL_ENTER();
   int n = nd->nGlobal;
   int nChunks = (n + RN_CHUNK - 1) / RN_CHUNK;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nChunks; c += gridDim.x * blockDim.x) {
@@ -276,6 +299,7 @@ constexpr int SEL_BITS = 16;
 constexpr int SEL_BINS = 1 << SEL_BITS;
 constexpr int SEL_CAND_CAP = 1 << 18;
 __global__ void k_sel_hist(const unsigned long long* rn, const NormDev* nd, int* hist) {
+  PDL_ENTER();
   int n = nd->nGlobal;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
     atomicAdd(&hist[(int)(rn[j] >> (63 - SEL_BITS))], 1);
@@ -283,6 +307,7 @@ __global__ void k_sel_hist(const unsigned long long* rn, const NormDev* nd, int*
 // heapSize-th smallest (1-based rank k): find the 16-bit bin holding it.
 // 1024 threads: each sums its 64 consecutive bins, one block scan, the owner of the rank walks its bins
 __global__ void __launch_bounds__(1024) k_sel_find_bin(const int* hist, CycleDev* cd, const NormDev* nd) {
+  PDL_ENTER();
   __shared__ int sWarp[33];
   int totSites = nd->nGlobal;
   int excess = totSites - nd->totPop;
@@ -306,6 +331,7 @@ __global__ void __launch_bounds__(1024) k_sel_find_bin(const int* hist, CycleDev
   }
 }
 __global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, const NormDev* nd, unsigned long long* cand) {
+  PDL_ENTER();
   int n = nd->nGlobal;
   int bin = cd->selBin;
   if (bin < 0) return;
@@ -319,6 +345,7 @@ __global__ void k_sel_collect(const unsigned long long* rn, CycleDev* cd, const 
 }
 // threshold = selRank-th smallest of the candidates (states are distinct within the LCG period)
 __global__ void __launch_bounds__(1024) k_sel_threshold(const unsigned long long* cand, CycleDev* cd) {
+  PDL_ENTER();
   int m = cd->nCand;
   if (cd->selBin < 0) { if (threadIdx.x == 0) { cd->thrState = 0; cd->thrReal = 1.0; } return; }
   if (m > SEL_CAND_CAP) { if (threadIdx.x == 0) atomicMax(&cd->error, SB_ERR_NORM); return; }
@@ -332,6 +359,7 @@ __global__ void __launch_bounds__(1024) k_sel_threshold(const unsigned long long
 }
 // keep (excess > 0: rn > threshold) or duplicate (excess < 0: rn <= threshold) flags of the local slice
 __global__ void k_norm_flags(const unsigned long long* rn, const CycleDev* cd, const NormDev* nd, int* flag) {
+  PDL_ENTER();
   int n = nd->nLocal;
   int excess = nd->nGlobal - nd->totPop;
   int nDup = (excess < 0) ? (int)(((long long)(-excess)) % nd->nGlobal) : 0;
@@ -351,6 +379,7 @@ __global__ void k_norm_flags(const unsigned long long* rn, const CycleDev* cd, c
 // sortByBroodID of the reference produces (:571-574): per brood, copies first, duplicates after.
 __global__ void k_norm_scatter(Bank src, Bank dst, const int* flag, const int* offs, const int* hOff, const int* hCnt,
                                const NormDev* nd, int dstCap, CycleDev* cdw) {
+  PDL_ENTER();
   int n = nd->nLocal;
   int excess = nd->nGlobal - nd->totPop;
   int nCopies = (excess < 0) ? (-excess) / nd->nGlobal : 0;
@@ -377,6 +406,7 @@ __global__ void k_norm_scatter(Bank src, Bank dst, const int* flag, const int* o
   }
 }
 __global__ void k_norm_count(const int* flag, const int* offs, const NormDev* nd, CycleDev* cdw) {
+  PDL_ENTER();
   int n = nd->nLocal;
   if (n <= 0) { cdw->nNew = 0; return; }
   int excess = nd->nGlobal - nd->totPop;
@@ -391,6 +421,7 @@ __global__ void k_norm_count(const int* flag, const int* offs, const NormDev* nd
 // every rank can then compute every rank's new bank size itself (replaces the mpi_allgather of :593)
 struct RankOffs { int n; int off[65]; };
 __global__ void k_norm_rank_counts(const unsigned long long* rn, const CycleDev* cd, const NormDev* nd, const RankOffs ro, int* counts) {
+  PDL_ENTER();
   __shared__ int sc[64];
   if (threadIdx.x < 64) sc[threadIdx.x] = 0;
   __syncthreads();
@@ -446,6 +477,7 @@ __global__ void k_bank_copy_range(Bank src, int first, int k, Bank dst, int dfir
 // them to its default bin, as in the reference.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_shannon_score(const Model M, const char* blob, int phase, int clerkIdx, Bank sites, const CycleDev* cd, int cap, int isCE, double* bins) {
+  PDL_ENTER();
   __shared__ double sTot[32];
   const DClerk& c = ((const DClerk*)(blob + M.oClerk[phase]))[clerkIdx];
   const int n = min(cd->nSites, cap);
@@ -467,6 +499,7 @@ __global__ void k_shannon_score(const Model M, const char* blob, int phase, int 
   }
 }
 __global__ void __launch_bounds__(256) k_shannon_close(int addr, int nBins, int cycle, double* bins, double* csum, double* csum2) {
+  PDL_ENTER();
   __shared__ double sVal[8];
   const double totWgt = bins[addr - 1];
   const double one_log2 = 1.0 / sbm::log(2.0);
@@ -528,6 +561,7 @@ __device__ __forceinline__ bool spinUntil(const unsigned long long* flag, unsign
 // all-to-all of { 6 sums, bank size } + the barrier it implies; sums added in rank order (same bits on every rank)
 __global__ void k_peer_post_wait(PeerPtrs P, int nRanks, int rank, unsigned long long seq, const double* own, double* total, PeerPlan* plan,
                                  CycleDev* cd, int cap, unsigned long long timeoutNs) {
+  PDL_ENTER();
   __shared__ int sOk[PEER_MAX];
   const int par = (int)(seq & 1ULL), t = threadIdx.x;
   if (t < nRanks) {
@@ -560,10 +594,12 @@ __global__ void k_peer_post_wait(PeerPtrs P, int nRanks, int rank, unsigned long
   }
 }
 __global__ void k_norm_setup_plan(NormDev* nd, const CycleDev* cd, int cap, int totPop, const PeerPlan* plan) {
+  PDL_ENTER();
   nd->nLocal = min(cd->nSites, cap); nd->totPop = totPop; nd->check = 0;
   nd->nGlobal = plan->nGlobal; nd->offLocal = plan->offLocal;
 }
 __global__ void k_norm_rank_counts_plan(const unsigned long long* rn, const CycleDev* cd, const NormDev* nd, const PeerPlan* plan, int* counts) {
+  PDL_ENTER();
   __shared__ int sc[PEER_MAX]; __shared__ int so[PEER_MAX + 1];
   const int nr = plan->n;
   if (threadIdx.x < PEER_MAX) sc[threadIdx.x] = 0;
@@ -586,6 +622,7 @@ __global__ void k_norm_rank_counts_plan(const unsigned long long* rn, const Cycl
 }
 // every rank's size after normSize_Repr (what the mpi_allgather of :593 returns) and this rank's part of loadBalancing (:607-698)
 __global__ void k_peer_plan(PeerPlan* plan, const int* counts, const NormDev* nd, CycleDev* cd, int cap, int stageCap) {
+  PDL_ENTER();
   const int nr = plan->n, rank = plan->rank, totPop = nd->totPop;
   const long long tot = nd->nGlobal, excess = tot - totPop, nCopies = excess < 0 ? (-excess) / tot : 0;
   long long off1 = 0, off2 = 0, sum = 0;
@@ -637,6 +674,7 @@ __device__ __forceinline__ double* peerStage(const PeerPtrs& P, int r, int par, 
 }
 // the sites this rank gives away go straight into the neighbours' stage buffers (stores over NVLink)
 __global__ void k_peer_push(PeerPtrs P, const PeerPlan* plan, Bank src, int cap, int par) {
+  PDL_ENTER();
   const int rank = plan->rank, nLocal = plan->newSizes[rank];
   const int up = plan->sendUp, down = plan->sendDown;
   double* bufUp = up > 0 ? peerStage(P, rank + 1, par, 0, cap) : nullptr;          // arrives "from below" at rank + 1
@@ -647,12 +685,14 @@ __global__ void k_peer_push(PeerPtrs P, const PeerPlan* plan, Bank src, int cap,
   }
 }
 __global__ void k_peer_flag_sites(PeerPtrs P, const PeerPlan* plan, unsigned long long seq) {
+  PDL_ENTER();
   const int rank = plan->rank, par = (int)(seq & 1ULL);
   __threadfence_system();
   if (threadIdx.x == 0 && plan->sendUp > 0) stReleaseSys(&P.box[rank + 1]->flagSites[par][0], seq);
   if (threadIdx.x == 1 && plan->sendDown > 0) stReleaseSys(&P.box[rank - 1]->flagSites[par][1], seq);
 }
 __global__ void k_peer_wait_sites(PeerPtrs P, const PeerPlan* plan, unsigned long long seq, CycleDev* cd, unsigned long long timeoutNs) {
+  PDL_ENTER();
   const int rank = plan->rank, par = (int)(seq & 1ULL);
   bool ok = true;
   if (threadIdx.x == 0 && plan->recvDown > 0) ok = spinUntil(&P.box[rank]->flagSites[par][0], seq, timeoutNs);
@@ -661,6 +701,7 @@ __global__ void k_peer_wait_sites(PeerPtrs P, const PeerPlan* plan, unsigned lon
 }
 // the bank after loadBalancing: [received from below] + kept middle + [received from above]
 __global__ void k_peer_splice(PeerPtrs P, const PeerPlan* plan, Bank src, Bank dst, int cap, int par, const CycleDev* cd) {
+  PDL_ENTER();
   const int rank = plan->rank;
   const bool bad = cd->error != 0;
   const int addF = bad ? 0 : plan->recvDown, addB = bad ? 0 : plan->recvUp, dropF = plan->sendDown, dropB = plan->sendUp;
@@ -843,6 +884,7 @@ __global__ void k_fastmath_check(long long n, unsigned long long seed, int expSp
 // slot = {r, parent direction, weight, G = material, E = bits of the stream state in front of the site's numbers}.
 // fissionMG_class.f90:183-206 (mu, phi, then the chi walk), neutronMGstd_class.f90:131-199
 __global__ void k_finish_sites(const Model M, const char* blob, Bank b, CycleDev* cd, int cap) {
+  PDL_ENTER();
   const Tables T = bind(M, blob);
   const int n = min(cd->nSites, cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -878,7 +920,7 @@ __global__ void k_bank_pack(Bank b, double* r, double* d, int n) {
     d[3 * (size_t)i] = b.ux[i]; d[3 * (size_t)i + 1] = b.uy[i]; d[3 * (size_t)i + 2] = b.uz[i];
   }
 }
-__global__ void k_zero_int(int* p, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0; }
+__global__ void k_zero_int(int* p, int n) { PDL_ENTER(); for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0; }
 
 // ================================================================================================
 // host side: engine handle + C ABI
@@ -1645,7 +1687,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     else if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else sbh::k_histories<false, 2><<<blocks, 256, sbh::histScratchBytes(256), st>>>(a);
-    k_finish_sites<<<gridFor(h, n, 128), 128, 0, st>>>(h->M, h->dBlob, raw, h->dCd, h->cap);     // the sites' directions and groups
+    pdlLaunch(k_finish_sites, gridFor(h, n, 128), 128, st, h->M, h->dBlob, raw, h->dCd, h->cap);     // the sites' directions and groups
     h->launches++;
   }
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK1, st));
@@ -1653,13 +1695,13 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
 
   // brood offsets = exclusive scan of per-history site counts ; stable brood order
   int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dNsites, h->dNcur, h->dTile);
-  k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, h->dNcur, nullptr);
-  k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dNsites, h->dNcur, h->dTile, h->dOffsets);
-  k_sort_sites<<<gridFor(h, 2LL * n, 256), 256, 0, st>>>(raw, sorted, h->dOffsets, h->dCd, h->cap);
+  pdlLaunch(k_scan_reduce, tiles, SCAN_BLOCK, st, h->dNsites, h->dNcur, h->dTile);
+  pdlLaunch(k_scan_tiles, 1, 1024, st, h->dTile, h->dNcur, nullptr);
+  pdlLaunch(k_scan_apply, tiles, SCAN_BLOCK, st, h->dNsites, h->dNcur, h->dTile, h->dOffsets);
+  pdlLaunch(k_sort_sites, gridFor(h, 2LL * n, 256), 256, st, raw, sorted, h->dOffsets, h->dCd, h->cap);
   // deterministic reductions of this rank's scores
-  k_reduce_hist<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, h->dHProd, h->dHAbs, h->dHLeak, h->dHScat, in.w, sorted.w, h->dCd, h->cap, h->dPartial);
-  k_sum_partials<<<1, 32, 0, st>>>(h->dPartial, h->dKsum, h->dCd, h->cap);
+  pdlLaunch(k_reduce_hist, RED_BLOCKS, RED_THREADS, st, n, h->dHProd, h->dHAbs, h->dHLeak, h->dHScat, in.w, sorted.w, h->dCd, h->cap, h->dPartial);
+  pdlLaunch(k_sum_partials, 1, 32, st, h->dPartial, h->dKsum, h->dCd, h->cap);
   h->launches += 6;
   h->phaseOpen = phase;
   return 0;
@@ -1677,12 +1719,12 @@ static int cycleCloseEnqueue(sb_engine* h, const double* dKsum) {
     sr.cycle += 1;
     if (sr.cycle > sr.maxCycles) continue;
     Bank& sorted = h->bank[(h->cur + 2) % 3];
-    k_shannon_score<<<gridFor(h, h->cap / 4 + 1, 256), 256, 0, st>>>(h->M, h->dBlob, phase, sr.clerk, sorted, h->dCd, h->cap, h->ceMode ? 1 : 0, h->dBins[phase]);
-    k_shannon_close<<<1, 256, 0, st>>>(sr.addr, sr.nBins, sr.cycle, h->dBins[phase], h->dCsum[phase], h->dCsum2[phase]);
+    pdlLaunch(k_shannon_score, gridFor(h, h->cap / 4 + 1, 256), 256, st, h->M, h->dBlob, phase, sr.clerk, sorted, h->dCd, h->cap, h->ceMode ? 1 : 0, h->dBins[phase]);
+    pdlLaunch(k_shannon_close, 1, 256, st, sr.addr, sr.nBins, sr.cycle, h->dBins[phase], h->dCsum[phase], h->dCsum2[phase]);
     h->launches += 2;
   }
   int nb = std::max(1, h->nBins[phase]);
-  k_close_cycle_bins<<<gridFor(h, nb, 256), 256, 0, st>>>(h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
+  pdlLaunch(k_close_cycle_bins, gridFor(h, nb, 256), 256, st, h->dBins[phase], h->dLast[phase], h->dCsum[phase], h->dCsum2[phase], h->nBins[phase], h->dCd);
   h->launches += 2;
   h->batchN[phase] += 1;
   return 0;
@@ -1750,21 +1792,21 @@ static int resampleEnqueue(sb_engine* h, int totPop, uint64_t rng_state, int nGl
     if ((size_t)nG > h->rnGlobalCap) { cudaFree(h->dRnGlobal); h->rnGlobalCap = (size_t)nG + nG / 4 + 1024; CUDA_OK(cudaMalloc(&h->dRnGlobal, sizeof(unsigned long long) * h->rnGlobalCap)); }
     rn = h->dRnGlobal;
   }
-  k_norm_setup<<<1, 1, 0, st>>>(h->dNd, h->dCd, h->cap, totPop, nGlobal, offLocal, check);
+  pdlLaunch(k_norm_setup, 1, 1, st, h->dNd, h->dCd, h->cap, totPop, nGlobal, offLocal, check);
   int g = gridFor(h, nG, 256), gl = gridFor(h, std::max(1, nSites), 256);
-  k_rn_generate<<<gridFor(h, (nG + RN_CHUNK - 1) / RN_CHUNK, 128), 128, 0, st>>>(rn, h->dNd, rng_state);
-  k_zero_int<<<gridFor(h, SEL_BINS, 256), 256, 0, st>>>(h->dHist, SEL_BINS);
-  k_sel_hist<<<g, 256, 0, st>>>(rn, h->dNd, h->dHist);
-  k_sel_find_bin<<<1, 1024, 0, st>>>(h->dHist, h->dCd, h->dNd);
-  k_sel_collect<<<g, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dCand);
-  k_sel_threshold<<<1, 1024, 0, st>>>(h->dCand, h->dCd);
-  k_norm_flags<<<gl, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dFlag);
+  pdlLaunch(k_rn_generate, gridFor(h, (nG + RN_CHUNK - 1) / RN_CHUNK, 128), 128, st, rn, h->dNd, rng_state);
+  pdlLaunch(k_zero_int, gridFor(h, SEL_BINS, 256), 256, st, h->dHist, SEL_BINS);
+  pdlLaunch(k_sel_hist, g, 256, st, rn, h->dNd, h->dHist);
+  pdlLaunch(k_sel_find_bin, 1, 1024, st, h->dHist, h->dCd, h->dNd);
+  pdlLaunch(k_sel_collect, g, 256, st, rn, h->dCd, h->dNd, h->dCand);
+  pdlLaunch(k_sel_threshold, 1, 1024, st, h->dCand, h->dCd);
+  pdlLaunch(k_norm_flags, gl, 256, st, rn, h->dCd, h->dNd, h->dFlag);
   int tiles = (std::max(1, nSites) + SCAN_TILE - 1) / SCAN_TILE;
-  k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile);
-  k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, &h->dNd->nLocal, nullptr);
-  k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile, h->dFlagOff);
-  k_norm_scatter<<<gl, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
-  k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dNd, h->dCd);
+  pdlLaunch(k_scan_reduce, tiles, SCAN_BLOCK, st, h->dFlag, &h->dNd->nLocal, h->dTile);
+  pdlLaunch(k_scan_tiles, 1, 1024, st, h->dTile, &h->dNd->nLocal, nullptr);
+  pdlLaunch(k_scan_apply, tiles, SCAN_BLOCK, st, h->dFlag, &h->dNd->nLocal, h->dTile, h->dFlagOff);
+  pdlLaunch(k_norm_scatter, gl, 256, st, sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
+  pdlLaunch(k_norm_count, 1, 1, st, h->dFlag, h->dFlagOff, h->dNd, h->dCd);
   h->launches += 13;
   return 0;
 }
@@ -1881,7 +1923,7 @@ int sb_cycle_end_resample_ranked(sb_engine* h, const double* host_sums, int tot_
   if (cycleCloseEnqueue(h, h->dKsumRed)) return -1;
   if (resampleEnqueue(h, tot_pop, master_rng_state, (int)tot, (int)off, 0, pop_sizes[rank])) return -1;
   CUDA_OK(cudaMemsetAsync(h->dRankCounts, 0, 64 * sizeof(int), st));
-  k_norm_rank_counts<<<gridFor(h, tot, 256), 256, 0, st>>>(h->dRnGlobal, h->dCd, h->dNd, ro, h->dRankCounts);
+  pdlLaunch(k_norm_rank_counts, gridFor(h, tot, 256), 256, st, h->dRnGlobal, h->dCd, h->dNd, ro, h->dRankCounts);
   h->launches++;
   CUDA_OK(cudaMemcpyAsync(h->hRankCounts, h->dRankCounts, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (cycleFinish(h, res)) return -1;
@@ -1957,36 +1999,36 @@ int sb_run_cycle_ranked_peer(sb_engine* h, uint64_t rng_state, int history_offse
   cudaStream_t st = h->stream;
   const unsigned long long seq = ++h->peerSeq, tmo = (unsigned long long)(h->peerTimeoutS * 1.0e9);
   const int par = (int)(seq & 1ULL), nr = h->peerRanks;
-  k_peer_post_wait<<<1, PEER_MAX, 0, st>>>(h->peerPtrs, nr, h->peerRank, seq, h->dKsum, h->dKsumTot, h->dPlan, h->dCd, h->cap, tmo);
+  pdlLaunch(k_peer_post_wait, 1, PEER_MAX, st, h->peerPtrs, nr, h->peerRank, seq, h->dKsum, h->dKsumTot, h->dPlan, h->dCd, h->cap, tmo);
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evP1, st));
   if (cycleCloseEnqueue(h, h->dKsumTot)) return -1;
   {  // normSize_Repr with the global sizes taken from the plan on the device (resampleEnqueue with host-known sizes otherwise)
     Bank& sorted = h->bank[(h->cur + 2) % 3]; Bank& dst = h->bank[(h->cur + 1) % 3];
     const long long nGmax = (long long)nr * h->peerCap; const int nSites = h->cap;
     unsigned long long* rn = h->dRnGlobal;
-    k_norm_setup_plan<<<1, 1, 0, st>>>(h->dNd, h->dCd, h->cap, tot_pop, h->dPlan);
+    pdlLaunch(k_norm_setup_plan, 1, 1, st, h->dNd, h->dCd, h->cap, tot_pop, h->dPlan);
     int g = gridFor(h, nGmax, 256), gl = gridFor(h, nSites, 256);
-    k_rn_generate<<<gridFor(h, (nGmax + RN_CHUNK - 1) / RN_CHUNK, 128), 128, 0, st>>>(rn, h->dNd, master_rng_resample);
-    k_zero_int<<<gridFor(h, SEL_BINS, 256), 256, 0, st>>>(h->dHist, SEL_BINS);
-    k_sel_hist<<<g, 256, 0, st>>>(rn, h->dNd, h->dHist);
-    k_sel_find_bin<<<1, 1024, 0, st>>>(h->dHist, h->dCd, h->dNd);
-    k_sel_collect<<<g, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dCand);
-    k_sel_threshold<<<1, 1024, 0, st>>>(h->dCand, h->dCd);
-    k_norm_flags<<<gl, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dFlag);
+    pdlLaunch(k_rn_generate, gridFor(h, (nGmax + RN_CHUNK - 1) / RN_CHUNK, 128), 128, st, rn, h->dNd, master_rng_resample);
+    pdlLaunch(k_zero_int, gridFor(h, SEL_BINS, 256), 256, st, h->dHist, SEL_BINS);
+    pdlLaunch(k_sel_hist, g, 256, st, rn, h->dNd, h->dHist);
+    pdlLaunch(k_sel_find_bin, 1, 1024, st, h->dHist, h->dCd, h->dNd);
+    pdlLaunch(k_sel_collect, g, 256, st, rn, h->dCd, h->dNd, h->dCand);
+    pdlLaunch(k_sel_threshold, 1, 1024, st, h->dCand, h->dCd);
+    pdlLaunch(k_norm_flags, gl, 256, st, rn, h->dCd, h->dNd, h->dFlag);
     int tiles = (nSites + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile);
-    k_scan_tiles<<<1, 1024, 0, st>>>(h->dTile, &h->dNd->nLocal, nullptr);
-    k_scan_apply<<<tiles, SCAN_BLOCK, 0, st>>>(h->dFlag, &h->dNd->nLocal, h->dTile, h->dFlagOff);
-    k_norm_scatter<<<gl, 256, 0, st>>>(sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
-    k_norm_count<<<1, 1, 0, st>>>(h->dFlag, h->dFlagOff, h->dNd, h->dCd);
+    pdlLaunch(k_scan_reduce, tiles, SCAN_BLOCK, st, h->dFlag, &h->dNd->nLocal, h->dTile);
+    pdlLaunch(k_scan_tiles, 1, 1024, st, h->dTile, &h->dNd->nLocal, nullptr);
+    pdlLaunch(k_scan_apply, tiles, SCAN_BLOCK, st, h->dFlag, &h->dNd->nLocal, h->dTile, h->dFlagOff);
+    pdlLaunch(k_norm_scatter, gl, 256, st, sorted, dst, h->dFlag, h->dFlagOff, h->dOffsets, h->dNsites, h->dNd, h->cap, h->dCd);
+    pdlLaunch(k_norm_count, 1, 1, st, h->dFlag, h->dFlagOff, h->dNd, h->dCd);
     CUDA_OK(cudaMemsetAsync(h->dRankCounts, 0, 64 * sizeof(int), st));
-    k_norm_rank_counts_plan<<<g, 256, 0, st>>>(rn, h->dCd, h->dNd, h->dPlan, h->dRankCounts);
-    k_peer_plan<<<1, 1, 0, st>>>(h->dPlan, h->dRankCounts, h->dNd, h->dCd, h->cap, h->peerCap);
+    pdlLaunch(k_norm_rank_counts_plan, g, 256, st, rn, h->dCd, h->dNd, h->dPlan, h->dRankCounts);
+    pdlLaunch(k_peer_plan, 1, 1, st, h->dPlan, h->dRankCounts, h->dNd, h->dCd, h->cap, h->peerCap);
     // loadBalancing: push to the neighbours, flag, wait for what they push, rebuild
-    k_peer_push<<<gridFor(h, h->cap / 8 + 1, 256), 256, 0, st>>>(h->peerPtrs, h->dPlan, dst, h->peerCap, par);
-    k_peer_flag_sites<<<1, 32, 0, st>>>(h->peerPtrs, h->dPlan, seq);
-    k_peer_wait_sites<<<1, 32, 0, st>>>(h->peerPtrs, h->dPlan, seq, h->dCd, tmo);
-    k_peer_splice<<<gl, 256, 0, st>>>(h->peerPtrs, h->dPlan, dst, sorted, h->peerCap, par, h->dCd);
+    pdlLaunch(k_peer_push, gridFor(h, h->cap / 8 + 1, 256), 256, st, h->peerPtrs, h->dPlan, dst, h->peerCap, par);
+    pdlLaunch(k_peer_flag_sites, 1, 32, st, h->peerPtrs, h->dPlan, seq);
+    pdlLaunch(k_peer_wait_sites, 1, 32, st, h->peerPtrs, h->dPlan, seq, h->dCd, tmo);
+    pdlLaunch(k_peer_splice, gl, 256, st, h->peerPtrs, h->dPlan, dst, sorted, h->peerCap, par, h->dCd);
     h->launches += 20;
   }
   if (h->profiling) { CUDA_OK(cudaEventRecord(h->evP2, st)); h->peerStagesOpen = true; }
