@@ -96,6 +96,42 @@ def test_host_buffer_cycle_equals_device_resident_cycle():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("deck,pop,extra", [("c5g7", 3000, ""), ("c5g7", 40000, ""), ("inf", 2000, ""), ("c5g7_3d", 3000, ""), ("can", 3000, " transportOperator { type transportOperatorDT; }")])
+def test_history_kernel_options_follow_the_same_histories(deck, pop, extra):
+    """The delta-tracking kernel runs a history that is alone in its warp from a draw window built by the idle lanes, resumes the
+    geometry search from a cell cache, and limits the lanes that refill (sb_hist.cuh). None of these may change a history: with each
+    of them switched off (SB_LONE_MODE=0, SB_CELL_CACHE=-1, SB_LANES=8; read when the engine is created) the banks are bit-identical
+    after every cycle, k-eff is equal and tally sums agree to summation-order rounding. Small populations put most of a cycle into
+    the lone-history path."""
+    import os
+    knobs = ("SB_LONE_MODE", "SB_CELL_CACHE", "SB_LANES")
+    ov = "pop %d; inactive 2; active 3; seed 4242;%s" % (pop, extra)
+    runs = []
+    for env in ({}, {"SB_LONE_MODE": "0"}, {"SB_CELL_CACHE": "-1"}, {"SB_LANES": "8", "SB_LONE_MODE": "1"}):
+        old = {k: os.environ.get(k) for k in knobs}
+        os.environ.update(env)
+        try:
+            pp = scone_b200.EigenPhysicsPackage(DECK[deck], ov, device=0)
+        finally:
+            for k, v in old.items():
+                if v is None: os.environ.pop(k, None)
+                else: os.environ[k] = v
+        pp.generateInitialState()
+        banks, ks = [], []
+        for cyc in range(5):
+            res = pp.cycle(cyc >= 2)
+            banks.append([x.copy() for x in pp.bank()]); ks.append((pp.k, res.n_segments, res.n_collisions))
+        cs, cs2, nb = pp.tally(True)
+        runs.append((banks, ks, cs.copy()))
+        pp.close()
+    for banks, ks, cs in runs[1:]:
+        assert ks == runs[0][1]
+        for b0, b1 in zip(runs[0][0], banks):
+            for x, y in zip(b0, b1):
+                assert np.array_equal(x, y)
+        np.testing.assert_allclose(cs, runs[0][2], rtol=1e-11, atol=1e-300)
+
+
 def test_k_inf_analytic():
     """InputFiles/SCONE_Inf: k-inf of the 2-group URR set is 1.631452 (eigenvalue of the 2x2 balance)."""
     pp = scone_b200.EigenPhysicsPackage(DECK["inf"], "pop 100000; inactive 20; active 60; seed 99;", device=0)
