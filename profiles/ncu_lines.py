@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Executed warp instructions and stall samples of an ncu report per CUDA source line, in source order, summed over the kernel results of
-the report (SASS page joined with nvdisasm line info of the library).  usage: ncu_lines.py <report.ncu-rep> <library.so> <kernel-substring> [file-filter]"""
+the report (SASS page joined with nvdisasm line info of the library).  usage: ncu_lines.py <report.ncu-rep> <library.so> <kernel-substring> [file-filter]
+NCU_LINES_DEPTH=k attributes an inlined instruction to the k-th frame from the outside (0: the line of the kernel body, the default)."""
 import collections, csv, glob, os, re, subprocess, sys, tempfile
 rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 flt = sys.argv[4] if len(sys.argv) > 4 else ""
@@ -9,21 +10,24 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, std
 amap = {}
 for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
     txt = subprocess.run(["nvdisasm", "--print-line-info-inline", cubin], capture_output=True, text=True).stdout
-    on, cur = False, None
+    on, frames, fresh = False, [], True
     for ln in txt.split("\n"):
         m = re.match(r"^\.text\.(\S+):", ln)
         if m:
             on = kern in m.group(1); continue
         if not on: continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            # with inlining the outermost "inlined at" site is the line of the kernel body
-            chain = re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))
-            inner = (os.path.basename(m.group(1)), int(m.group(2)))
-            outer = (os.path.basename(chain[-1][0]), int(chain[-1][1])) if chain else inner
-            cur = (outer, inner); continue
+            # one "File" line per inline frame, innermost first; a new group starts after an instruction
+            if fresh: frames = []; fresh = False
+            frames.append((os.path.basename(m.group(1)), int(m.group(2)))); continue
         m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", ln)
-        if m: amap[int(m.group(1), 16)] = cur
+        if m:
+            fresh = True
+            if frames:
+                depth = int(os.environ.get("NCU_LINES_DEPTH", "0"))
+                outer = frames[max(0, len(frames) - 1 - depth)]
+                amap[int(m.group(1), 16)] = (outer, frames[0])
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.split("\n")))
 agg = collections.defaultdict(lambda: [0, 0]); hdr = None; base = None; nres = 0

@@ -45,6 +45,14 @@ static inline void pdlLaunch(void (*k)(P...), int grid, int block, cudaStream_t 
   cudaLaunchKernelEx(&cfg, k, P(a)...);
 }
 
+template <typename... P, typename... A>
+static inline void pdlLaunchSmem(void (*k)(P...), int grid, int block, size_t smem, cudaStream_t st, A&&... a) {
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at{}; at.id = cudaLaunchAttributeProgrammaticStreamSerialization; at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, P(a)...);
+}
+
 #define CUDA_OK(call)                                                                         \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
@@ -957,7 +965,8 @@ struct sb_engine {
   int* dRankCounts = nullptr; int* hRankCounts = nullptr;
   double* dKsum = nullptr; NormDev* dNd = nullptr; unsigned long long* dRnGlobal = nullptr; size_t rnGlobalCap = 0;
   int refillMin = 1;
-  int maxSegMin = 256, loneMode = 1, cellCache = 48; unsigned laneMask = 0xffffffffu;
+  int maxSegMin = 256, loneMode = 1, cellCache = 48, assist = -1; unsigned laneMask = 0xffffffffu;
+  sbh::LoneRec* dLoneQ = nullptr; int* dLoneCtl = nullptr; int* dLoneReady = nullptr; int loneCap = 0, loneTag = 0;      // queue between k_histories and k_lone; { count, next, done }
   int *dCePerm = nullptr, *dCeHist = nullptr, *dCeCursor = nullptr, *dCeTile = nullptr, *dCeNbin = nullptr; size_t cePermCap = 0, ceBinCap = 0;   // sorted CE lookups
   long long* dProfRounds = nullptr;
   // measurement
@@ -1177,6 +1186,7 @@ static int buildBlob(sb_engine* h) {
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
+      if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(sbh::k_lone<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::loneScratchBytes(128)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 448>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(448)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(512)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbh::histScratchBytes(256)));
@@ -1255,6 +1265,7 @@ int sb_create(sb_engine** out, int device) {
   if (const char* e = getenv("SB_BLOCKS_PER_SM")) h->opt.blocks_per_sm = atoi(e);
   if (const char* e = getenv("SB_MAXSEG_MIN")) h->maxSegMin = atoi(e);
   if (const char* e = getenv("SB_LONE_MODE")) h->loneMode = atoi(e);
+  if (const char* e = getenv("SB_ASSIST")) h->assist = atoi(e);
   if (const char* e = getenv("SB_LANES")) { int k = atoi(e); h->laneMask = (k >= 32 || k < 1) ? 0xffffffffu : ((1u << k) - 1u); }
   if (const char* e = getenv("SB_CELL_CACHE")) h->cellCache = atoi(e) < 0 ? 0x7fffffff : atoi(e);
   cudaEventCreate(&h->evP1); cudaEventCreate(&h->evP2);
@@ -1588,6 +1599,12 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   Bank& in = h->bank[h->cur]; Bank& raw = h->bank[(h->cur + 1) % 3]; Bank& sorted = h->bank[(h->cur + 2) % 3];
 
   // reset the running-cycle record (the cumulative k sums stay)
+  if (!h->dLoneCtl) {                                          // one queue slot per lane that can be resident (12 warps on every SM)
+    h->loneCap = h->numSM * 512;
+    CUDA_OK(cudaMalloc(&h->dLoneQ, sizeof(sbh::LoneRec) * (size_t)h->loneCap)); CUDA_OK(cudaMalloc(&h->dLoneCtl, 4 * sizeof(int)));
+    CUDA_OK(cudaMalloc(&h->dLoneReady, sizeof(int) * (size_t)h->loneCap)); CUDA_OK(cudaMemsetAsync(h->dLoneReady, 0, sizeof(int) * (size_t)h->loneCap, st));
+  }
+  CUDA_OK(cudaMemsetAsync(h->dLoneCtl, 0, 4 * sizeof(int), st));
   k_cycle_begin<<<1, 1, 0, st>>>(h->dCd, h->dNcur, n);
   h->launches++;
 
@@ -1602,9 +1619,19 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   a.impScores = impScores;
   a.rng0 = rng_state; a.histOffset = history_offset; a.k_eff = k_eff; a.cd = h->dCd;
 #ifdef SB_PROFILE_ROUNDS
-  { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * 27 * 148 * 384); } cudaMemsetAsync(dProf, 0, 8 * 27 * 148 * 384, st); a.prof = dProf; h->dProfRounds = dProf; }
+  { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * (36 * 148 * 384 + 12 * 148 * 16)); } cudaMemsetAsync(dProf, 0, 8 * (36 * 148 * 384 + 12 * 148 * 16), st); a.prof = dProf; h->dProfRounds = dProf; }
 #endif
   a.refillMin = h->refillMin; a.maxSegMin = h->maxSegMin; a.loneMode = h->loneMode; a.cellCache = h->cellCache; a.laneMask = h->laneMask;
+  // the last histories of every warp go on in k_lone (speculative batches; what they restate is multiScatterMG with P0 scattering).
+  // A warp hands its histories over when it is down to T of them: as many as k_lone's warps (8 per SM) can take at once, counted over
+  // the warps that will run (measured, profiles/README.md: T = 1 at 1e5 histories, 2 at 2e4, 8 at 2e3 per GPU)
+  {
+    const int warpsA = std::min(h->numSM * 12, (n + 31) / 32);
+    int T = h->assist >= 0 ? h->assist : std::max(1, std::min(8, (int)(1.1 * 8 * h->numSM / std::max(1, warpsA))));
+    a.assist = (T > 0 && h->loneMode && !h->hot.isP1 && h->useSmem) ? std::min(T, 32) : 0;
+  }
+  a.loneQ = h->dLoneQ; a.loneCount = h->dLoneCtl; a.loneNext = h->dLoneCtl + 1; a.loneCap = h->loneCap;
+  a.loneReady = h->dLoneReady; a.loneDone = h->dLoneCtl + 2; a.loneTag = ++h->loneTag;
   // one CTA of 12 warps per SM (168 registers per thread, no spills) unless told otherwise: at the populations of an
   // eigenvalue cycle the kernel's time is the chain of its longest history, not the number of resident warps
   int threads = 384;
@@ -1614,6 +1641,7 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   int blocks = h->numSM * bps;
   int needBlocks = (n + threads - 1) / threads;
   if (needBlocks < blocks) blocks = needBlocks;
+  a.loneWarps = blocks * (threads / 32);
   if (h->profiling) CUDA_OK(cudaEventRecord(h->evK0, st));
   bool useTrack = h->opt.tracking != SB_TRACK_DT || h->fixedSource;      // the DT-only kernel has no secondary buffer
   // (trackClerks score along surface-tracking segments only: under delta tracking the reference makes no path reports either)
@@ -1687,6 +1715,10 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     else if (h->useSmem && bps >= 3) sbh::k_histories<true, 3><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else sbh::k_histories<false, 2><<<blocks, 256, sbh::histScratchBytes(256), st>>>(a);
+    if (a.assist > 0) {                                            // the last histories of every warp, one warp each
+      pdlLaunchSmem(sbh::k_lone<128>, h->numSM * 2, 128, (size_t)(hotB + sbh::loneScratchBytes(128)), st, a);
+      h->launches++;
+    }
     pdlLaunch(k_finish_sites, gridFor(h, n, 128), 128, st, h->M, h->dBlob, raw, h->dCd, h->cap);     // the sites' directions and groups
     h->launches++;
   }
@@ -2417,7 +2449,7 @@ int sb_math_query(int64_t n, const double* x, double* lg, double* sn, double* cs
 }
 
 #ifdef SB_PROFILE_ROUNDS
-int sb_profile_rounds(sb_engine* h, long long* out) { cudaStreamSynchronize(h->stream); return cudaMemcpy(out, h->dProfRounds, 8 * 27 * 148 * 384, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
+int sb_profile_rounds(sb_engine* h, long long* out) { cudaStreamSynchronize(h->stream); return cudaMemcpy(out, h->dProfRounds, 8 * (36 * 148 * 384 + 12 * 148 * 16), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
 #endif
 int sb_fastmath_check(int64_t n, uint64_t seed, int exp_span, int64_t* mismatches) {
   unsigned long long* d = nullptr;

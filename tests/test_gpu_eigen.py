@@ -99,15 +99,16 @@ def test_host_buffer_cycle_equals_device_resident_cycle():
 @pytest.mark.parametrize("deck,pop,extra", [("c5g7", 3000, ""), ("c5g7", 40000, ""), ("inf", 2000, ""), ("c5g7_3d", 3000, ""), ("can", 3000, " transportOperator { type transportOperatorDT; }")])
 def test_history_kernel_options_follow_the_same_histories(deck, pop, extra):
     """The delta-tracking kernel runs a history that is alone in its warp from a draw window built by the idle lanes, resumes the
-    geometry search from a cell cache, and limits the lanes that refill (sb_hist.cuh). None of these may change a history: with each
-    of them switched off (SB_LONE_MODE=0, SB_CELL_CACHE=-1, SB_LANES=8; read when the engine is created) the banks are bit-identical
+    geometry search from a cell cache, limits the lanes that refill, and hands the last histories of every warp to a second kernel that
+    runs them ahead in speculative batches (sb_hist.cuh). None of these may change a history: with each of them switched off or
+    changed (SB_LONE_MODE=0, SB_CELL_CACHE=-1, SB_LANES=8, SB_ASSIST=0 / 3 / 32; read when the engine is created) the banks are bit-identical
     after every cycle, k-eff is equal and tally sums agree to summation-order rounding. Small populations put most of a cycle into
     the lone-history path."""
     import os
-    knobs = ("SB_LONE_MODE", "SB_CELL_CACHE", "SB_LANES")
+    knobs = ("SB_LONE_MODE", "SB_CELL_CACHE", "SB_LANES", "SB_ASSIST")
     ov = "pop %d; inactive 2; active 3; seed 4242;%s" % (pop, extra)
     runs = []
-    for env in ({}, {"SB_LONE_MODE": "0"}, {"SB_CELL_CACHE": "-1"}, {"SB_LANES": "8", "SB_LONE_MODE": "1"}):
+    for env in ({}, {"SB_ASSIST": "0"}, {"SB_ASSIST": "3"}, {"SB_ASSIST": "32"}, {"SB_LONE_MODE": "0"}, {"SB_CELL_CACHE": "-1"}, {"SB_LANES": "8", "SB_LONE_MODE": "1"}):
         old = {k: os.environ.get(k) for k in knobs}
         os.environ.update(env)
         try:
