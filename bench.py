@@ -417,10 +417,10 @@ def main():
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(("k_histories_ce" if args.deck.startswith("ce_") else "k_histories") + "_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(("k_histories_ce" if args.deck.startswith("ce_") else "k_histories") + "_dram_bytes_per_launch")     # (k_histories: with k_lone)
     except Exception:
         pass
-    kname = "k_histories_ce" if args.deck.startswith("ce_") else ("k_histories" if args.tracking in (None, "DT") else "k_histories_track")
+    kname = "k_histories_ce" if args.deck.startswith("ce_") else ("k_histories + k_lone" if args.tracking in (None, "DT") else "k_histories_track")
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (msk.value / ms_total) if ms_total > 0 else None,
@@ -431,7 +431,7 @@ def main():
                             "mean_flights_per_history": seg / max(1, pop * args.steps),
                             "note": "the kernel ends when the longest history of the cycle ends: its flights x the latency of one flight + collision round of a history that runs alone in its warp (profiles/README.md, round 2)"},
                 "note": ("lane-resident histories in CTA-lockstep phases: bound by instruction fetch, barrier wait and memory latency at 16-32 warps per SM, not by HBM (DESIGN.md section 4, profiles/README.md)"
-                         if kname != "k_histories" else "register-resident histories: the kernel is latency/FP64-issue bound, not HBM bound (see DESIGN.md)")}
+                         if not kname.startswith("k_histories +") else "register-resident histories (k_histories) and the last histories of every warp one per warp (k_lone, running beside it): latency bound, not HBM bound; kernel_ms_per_launch is from the first launch of k_histories to the end of k_lone and k_finish_sites (DESIGN.md section 4)")}
 
     # ---- extras (N = 1 only): the same deck at a GPU-sized population, and the CE XS-lookup kernel ----------------
     large = None; ce = None

@@ -21,6 +21,7 @@
 //     reference arithmetic gives ijk = 1, r_bar = 0 and offset 0 exactly.
 #pragma once
 #include "sb_device.cuh"
+#include <type_traits>
 
 namespace sbh {
 using namespace sbd;
@@ -513,6 +514,57 @@ __device__ __forceinline__ void scoreColl(const HistArgs& a, const HotCtx& H, co
 //           boundary, void, fission sites).
 // Lane `owner` has the history; the other lanes use the same variables as scratch for the points they check.
 // ------------------------------------------------------------------------------------------------
+// the next WIN numbers of a history's stream behind state sb, WIN / 32 per lane, with everything the loops take from them: state, uniform,
+// -log, sin / cos of the azimuth 2 pi xi, sin of the polar angle of mu = 2 xi - 1. All entries of the lane in one straight line (sb_math.h:
+// log_main / sincos_main, the same values without branches) so that the logarithms, sines / cosines and square roots overlap; the special
+// arguments after. Out of line: the loops that use the window stay compact (instruction caches).
+template <int WIN>
+__device__ __noinline__ void buildDrawWindow(DrawWinT<WIN>* Wp, const uint64_t sb, const JumpTab* jt) {
+  DrawWinT<WIN>& W = *Wp;
+  const int lane_ = (int)(threadIdx.x & 31);
+  const ulonglong2 jm = jt->j[lane_];
+  uint64_t st = (jm.x * sb + jm.y) & RNG_MASK;                             // lane + 1 draws ahead, then 32 more
+  bool rare[WIN / 32];
+#pragma unroll
+  for (int k = 0; k < WIN / 32; ++k) {
+    const int e = lane_ + 32 * k;
+    const double xi = rngReal(st);
+    double sn, cs;
+    sbm::sincos_main(TWO_PI * xi, &sn, &cs);
+    const double mu = 2.0 * xi - 1.0, a2 = fmax(0.0, 1.0 - mu * mu);
+    bool rl;
+    const double lg = sbm::log_main(xi, &rl);
+    rare[k] = rl || !fastRange(a2);
+    W.st[e] = st; W.xi[e] = xi; W.nlog[e] = -lg; W.sn[e] = sn; W.cs[e] = cs;
+    W.A[e] = sqrtFast(a2);
+    st = rngJump<32>(st);
+  }
+#pragma unroll
+  for (int k = 0; k < WIN / 32; ++k)
+    if (rare[k]) { const int e = lane_ + 32 * k; const double xi = W.xi[e]; W.nlog[e] = -sbm::log(xi); W.A[e] = sinPolar(2.0 * xi - 1.0); }
+  __syncwarp();
+}
+
+// rotateVector for the loop of k_lone: the fast paths of rotateVectorSC (sb_device.cuh) in one straight block - the same operations
+// in the same order - and rotateVectorSC itself, out of line, for arguments outside them (so that the loop stays compact)
+__device__ __noinline__ double divCold(double a, double b) { return a / b; }
+__device__ __noinline__ void rotateVectorCold(double d[3], double mu, double sinPol, double cosPol, double A) { rotateVectorSC(d, mu, sinPol, cosPol, A); }
+__device__ __forceinline__ void rotateVectorHot(double& u0, double& u1, double& u2, const double mu, const double sinPol, const double cosPol, const double A) {
+  const double b2 = fmax(0.0, 1.0 - u2 * u2);
+  const double B = sqrtFast(b2), yB = rcpRefined(B);
+  const double t0 = A * (u0 * u2 * cosPol - u1 * sinPol), t1 = A * (u1 * u2 * cosPol + u0 * sinPol);
+  const double q0 = divBy(t0, B, yB), q1 = divBy(t1, B, yB);
+  const double n0 = mu * u0 + q0, n1 = mu * u1 + q1, n2 = mu * u2 - A * B * cosPol;
+  const double nn = n0 * n0 + n1 * n1 + n2 * n2;
+  const double nrm = sqrtFast(nn), yN = rcpRefined(nrm);
+  if (fastRange(b2) && B > 1E-8 && fastRange(t0) && fastRange(t1) && fastRange(nn) && fastRange(n0) && fastRange(n1) && fastRange(n2)) {
+    u0 = divBy(n0, nrm, yN); u1 = divBy(n1, nrm, yN); u2 = divBy(n2, nrm, yN);
+  } else {
+    double d[3] = {u0, u1, u2};
+    rotateVectorCold(d, mu, sinPol, cosPol, A);
+    u0 = d[0]; u1 = d[1]; u2 = d[2];
+  }
+}
 struct __align__(16) LoneRec {             // a history handed from k_histories to k_lone
   double r0, r1, r2, u0, u1, u2, w, w0, sProd, sAbs, sScat;
   unsigned long long rng;
@@ -548,28 +600,7 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
   for (;;) {
     // ---- the draw window: the next WIN numbers of the history's stream, four per lane ----
     if (__shfl_sync(FULL, winPos, owner) > WIN - 32) {
-      const uint64_t sb = __shfl_sync(FULL, rng, owner);
-      const ulonglong2 jm = jt->j[lane];
-      uint64_t st = (jm.x * sb + jm.y) & RNG_MASK;
-      bool rare[WIN / 32];
-#pragma unroll
-      for (int k = 0; k < WIN / 32; ++k) {
-        const int e = lane + 32 * k;
-        const double xi = rngReal(st);
-        double sn, cs;
-        sbm::sincos_main(TWO_PI * xi, &sn, &cs);
-        const double mu = 2.0 * xi - 1.0, a2 = fmax(0.0, 1.0 - mu * mu);
-        bool rl;
-        const double lg = sbm::log_main(xi, &rl);
-        rare[k] = rl || !fastRange(a2);
-        W.st[e] = st; W.xi[e] = xi; W.nlog[e] = -lg; W.sn[e] = sn; W.cs[e] = cs;
-        W.A[e] = sqrtFast(a2);
-        st = rngJump<32>(st);
-      }
-#pragma unroll
-      for (int k = 0; k < WIN / 32; ++k)
-        if (rare[k]) { const int e = lane + 32 * k; const double xi = W.xi[e]; W.nlog[e] = -sbm::log(xi); W.A[e] = sinPolar(2.0 * xi - 1.0); }
-      __syncwarp();
+      buildDrawWindow<WIN>(&W, __shfl_sync(FULL, rng, owner), jt);
       if (lane == owner) winPos = 0;
     }
     PL_MARK(1)
@@ -579,8 +610,9 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
     const int mat0 = __shfl_sync(FULL, mat, owner);
     const int hSeg0 = __shfl_sync(FULL, hSeg, owner);
     int nR = 0;
-    if (lane == owner) {
-      const bool seq = mode == 2;
+    // two copies of the rounds, one per mode: the one that runs ahead is compact enough for the instruction cache of its scheduler
+    auto rounds = [&](auto seqTag) {
+      constexpr bool seq = decltype(seqTag)::value;
       int p = winPos, nC = 0, m = mat0, sameRun = 0;               // sameRun: rounds in a row in one material
       double sScat = H.scat[threadIdx.x];
       bool ended = false, recorded = false;                        // ended: absorbed, leaked or lost; recorded: rec[nR] holds the history in front of round nR
@@ -628,7 +660,7 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
         }
         if (seq) scoreColl(a, H, false, !real, true, r0, r1, r2, mat, G, w, majInv, sProd, sAbs, nScore);                        // clerks and implicit k-eff scores
         else if (active) {                                         // keffImplicitClerk%reportInColl, as in scoreColl
-          const double flux = (w == 1.0) ? majInv : w / majT[G - 1];
+          const double flux = (w == 1.0) ? majInv : divCold(w, majT[G - 1]);
           const double nuf = fissile ? x[XS_NUFISSION] : 0.0, fis = fissile ? x[XS_FISSION] : 0.0;
           sProd += nuf * flux;
           sAbs += (x[XS_CAPTURE] + fis) * flux;
@@ -678,12 +710,10 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
             rem = e4;
           }
           if (Gout == 0) { fl |= SR_SAMPLING; Gout = G; if (seq) atomicMax(&a.cd->error, SB_ERR_SAMPLING); }
-          double d[3] = {u0, u1, u2};
-          rotateVectorSC(d, mu, sn, cs, A);
+          rotateVectorHot(u0, u1, u2, mu, sn, cs, A);
           const double w_mul = prodT[row * nG + (Gout - 1)];
           const double wPre = w;
           if (Gout != G || w_mul != 1.0) { G = Gout; majInv = majInvT[G - 1]; w = w * w_mul; }
-          u0 = d[0]; u1 = d[1]; u2 = d[2];
           const double sc = fmax(w - wPre, 0.0);
           if (sc > 0.0) sScat += sc;
           p = p3 + 3;
@@ -707,7 +737,8 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
         R.b0 = r0; R.b1 = r1; R.b2 = r2; R.u0 = u0; R.u1 = u1; R.u2 = u2; R.w = w;
         R.sProd = sProd; R.sAbs = sAbs; R.sScat = sScat; R.G = G; R.p = p; R.nColl = nC; R.flags = 0;
       }
-    }
+    };
+    if (lane == owner) { if (mode == 2) rounds(std::true_type{}); else rounds(std::false_type{}); }
     nR = __shfl_sync(FULL, nR, owner);
     __syncwarp();
 #ifdef SB_PROFILE_ROUNDS
@@ -938,30 +969,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
     if (exhausted && a.loneMode && __popc(~need) == 1) {
       const int owner = __ffs(~need) - 1;
       if (__shfl_sync(FULL, winPos, owner) > WIN - WIN_ROUND) {
-        const uint64_t sb = __shfl_sync(FULL, rng, owner);
-        const ulonglong2 jm = s_jump->j[lane];
-        uint64_t st = (jm.x * sb + jm.y) & RNG_MASK;                       // lane + 1 draws ahead, then 32 more
-        // both entries of the lane in one straight line (sb_math.h: log_main / sincos_main, the same values without
-        // branches), so that the two logarithms, sines / cosines and square roots overlap; the special arguments after
-        bool rare[WIN / 32];
-#pragma unroll
-        for (int k = 0; k < WIN / 32; ++k) {
-          const int e = lane + 32 * k;
-          const double xi = rngReal(st);
-          double sn, cs;
-          sbm::sincos_main(TWO_PI * xi, &sn, &cs);
-          const double mu = 2.0 * xi - 1.0, a2 = fmax(0.0, 1.0 - mu * mu);
-          bool rl;
-          const double lg = sbm::log_main(xi, &rl);
-          rare[k] = rl || !fastRange(a2);
-          W.st[e] = st; W.xi[e] = xi; W.nlog[e] = -lg; W.sn[e] = sn; W.cs[e] = cs;
-          W.A[e] = sqrtFast(a2);
-          st = rngJump<32>(st);
-        }
-#pragma unroll
-        for (int k = 0; k < WIN / 32; ++k)
-          if (rare[k]) { const int e = lane + 32 * k; const double xi = W.xi[e]; W.nlog[e] = -sbm::log(xi); W.A[e] = sinPolar(2.0 * xi - 1.0); }
-        __syncwarp();
+        buildDrawWindow<WIN>(&W, __shfl_sync(FULL, rng, owner), s_jump);
         if (lane == owner) winPos = 0;
       }
     }
@@ -1114,7 +1122,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
         }
         PR_MARK(6)
         double d[3] = {u0, u1, u2};
-        rotateVectorSC(d, mu, sn, cs, A);
+        rotateVectorHot(d[0], d[1], d[2], mu, sn, cs, A);
         {                                                   // neutronMGstd inelastic (:221-252)
           double w_mul = prodT[row * nG + (Gout - 1)];
           double wPre = w;
