@@ -1186,6 +1186,7 @@ static int buildBlob(sb_engine* h) {
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
       if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(sbh::k_lone<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::loneScratchBytes(128)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 448>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(448)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(512)));
@@ -1708,7 +1709,8 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   } else
   {
     const int hotB = h->useSmem ? h->hot.bytes : 0;
-    if (h->useSmem && bps == 1 && threads == 384) sbh::k_histories<true, 1, 384><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
+    if (h->useSmem && bps == 1 && threads == 384 && a.assist > 0) sbh::k_histories<true, 1, 384, false><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
+    else if (h->useSmem && bps == 1 && threads == 384) sbh::k_histories<true, 1, 384><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
     else if (h->useSmem && bps == 1 && threads == 448) sbh::k_histories<true, 1, 448><<<blocks, 448, hotB + sbh::histScratchBytes(448), st>>>(a);
     else if (h->useSmem && bps == 1 && threads == 512) sbh::k_histories<true, 1, 512><<<blocks, 512, hotB + sbh::histScratchBytes(512), st>>>(a);
     else if (h->useSmem && bps == 1) sbh::k_histories<true, 1><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);

@@ -548,6 +548,9 @@ __device__ __noinline__ void buildDrawWindow(DrawWinT<WIN>* Wp, const uint64_t s
 // rotateVector for the loop of k_lone: the fast paths of rotateVectorSC (sb_device.cuh) in one straight block - the same operations
 // in the same order - and rotateVectorSC itself, out of line, for arguments outside them (so that the loop stays compact)
 __device__ __noinline__ double divCold(double a, double b) { return a / b; }
+__device__ __noinline__ double logCold(double x) { return sbm::log(x); }
+// -log(xi) as the draw windows compute it: the branch-free main path, the special arguments out of line (the same values as sbm::log)
+__device__ __forceinline__ double negLogHot(const double xi) { bool rl; const double lg = sbm::log_main(xi, &rl); return rl ? -logCold(xi) : -lg; }
 __device__ __noinline__ void rotateVectorCold(double d[3], double mu, double sinPol, double cosPol, double A) { rotateVectorSC(d, mu, sinPol, cosPol, A); }
 __device__ __forceinline__ void rotateVectorHot(double& u0, double& u1, double& u2, const double mu, const double sinPol, const double cosPol, const double A) {
   const double b2 = fmax(0.0, 1.0 - u2 * u2);
@@ -840,7 +843,9 @@ __device__ __forceinline__ void stageHot(char* smem, const char* gsrc, int bytes
   }
 }
 
-template <bool SMEM, int BPS, int THREADS = 256>
+// LW: the loop has the draw window of a history that is alone in its warp. The launches that hand their last histories to k_lone
+// (HistArgs::assist > 0) never have such a history and run the copy without it (fewer tests per draw, a smaller loop).
+template <bool SMEM, int BPS, int THREADS = 256, bool LW = true>
 __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constant__ HistArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
   constexpr int NW = THREADS / 32;
@@ -896,12 +901,12 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
 
   // leave the window for the rest of the round (code that draws through rng_get directly)
   auto leaveWindow = [&]() {
-    if (winPos <= WIN) { if (winPos > 0) rng = W.st[winPos - 1]; winPos = WIN + 1; }
+    if (LW && winPos <= WIN) { if (winPos > 0) rng = W.st[winPos - 1]; winPos = WIN + 1; }
   };
   // fission sites: the stream position is needed as a state; the window is left (its next rebuild starts behind the sites)
   auto leaveWindowKeep = leaveWindow;
 
-  auto place = [&]() -> bool { return placePoint(a, H, winPos <= WIN, hSeg, r0, r1, r2, u0, u1, u2, mat); };
+  auto place = [&]() -> bool { return placePoint(a, H, LW && winPos <= WIN, hSeg, r0, r1, r2, u0, u1, u2, mat); };
   auto score = [&](const bool isVoid, const bool virt, const bool keff) { scoreColl(a, H, isVoid, virt, keff, r0, r1, r2, mat, G, w, majInv, sProd, sAbs, nScore); };
 
 #ifdef SB_PROFILE_ROUNDS
@@ -966,7 +971,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
     }
 
     // ---------------- a history alone in its warp: (re)build its draw window with all 32 lanes ---------
-    if (exhausted && a.loneMode && __popc(~need) == 1) {
+    if (LW && exhausted && a.loneMode && __popc(~need) == 1) {
       const int owner = __ffs(~need) - 1;
       if (__shfl_sync(FULL, winPos, owner) > WIN - WIN_ROUND) {
         buildDrawWindow<WIN>(&W, __shfl_sync(FULL, rng, owner), s_jump);
@@ -982,11 +987,11 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
     if (alive) {
       {
         double nlog;
-        if (winPos < WIN - 1) { nlog = W.nlog[winPos]; winPos += 1; }
+        if (LW && winPos < WIN - 1) { nlog = W.nlog[winPos]; winPos += 1; }
         else {
           leaveWindow();
           rng = rngJump<1>(rng);
-          nlog = -sbm::log(rngReal(rng));
+          nlog = negLogHot(rngReal(rng));
         }
         const double distance = nlog * majInv;
         r0 = r0 + distance * u0; r1 = r1 + distance * u1; r2 = r2 + distance * u2;
@@ -1005,7 +1010,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
           const double* x = xsT + ((mat - 1) * nG + (G - 1)) * 6;
           double sigmaT = x[XS_TOTAL] + 0.0;
           double xiAcc;                                                        // the acceptance test draws (not in void)
-          if (winPos < WIN) { xiAcc = W.xi[winPos]; winPos += 1; } else { leaveWindow(); rng = rngJump<1>(rng); xiAcc = rngReal(rng); }
+          if (LW && winPos < WIN) { xiAcc = W.xi[winPos]; winPos += 1; } else { leaveWindow(); rng = rngJump<1>(rng); xiAcc = rngReal(rng); }
           if (xiAcc < sigmaT * majInv) { realColl = true; virt = false; }
         }
         score(isVoid, virt, true);
@@ -1019,7 +1024,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
       const double* x = xsT + ((mat - 1) * nG + (G - 1)) * 6;
       const bool fissile = fissileT[mat - 1] != 0;
       double rr, rand1 = 0.0;                             // the alpha-absorption test always draws first (probAlpha = 0)
-      if (winPos <= WIN - 3) { rr = W.xi[winPos + 1]; rand1 = W.xi[winPos + 2]; winPos += fissile ? 3 : 2; }
+      if (LW && winPos <= WIN - 3) { rr = W.xi[winPos + 1]; rand1 = W.xi[winPos + 2]; winPos += fissile ? 3 : 2; }
       else {
         leaveWindow();
         const uint64_t s2 = rngJump<2>(rng), s3 = rngJump<3>(rng);
@@ -1088,8 +1093,8 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
         const int row = (mat - 1) * nG + (G - 1);
         const double* cdf = P0 + row * nG;
         double mu, A, sn, cs, rem;
-        const bool legendre = a.L.isP1 != 0;
-        if (winPos <= WIN - 3 && !legendre) {              // three numbers in the order of the reaction, all from the window
+        const bool legendre = LW && a.L.isP1 != 0;          // (launches without LW are P0: HistArgs::assist)
+        if (LW && winPos <= WIN - 3 && !legendre) {              // three numbers in the order of the reaction, all from the window
           rem = W.xi[winPos]; mu = 2.0 * W.xi[winPos + 1] - 1.0; A = W.A[winPos + 1]; sn = W.sn[winPos + 2]; cs = W.cs[winPos + 2];
           winPos += 3;
         } else if (!legendre) {
@@ -1098,7 +1103,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
           rng = s3;
           rem = rngReal(s1);
           mu = 2.0 * rngReal(s2) - 1.0;
-          sbm::sincos(TWO_PI * rngReal(s3), &sn, &cs);
+          sbm::sincos_main(TWO_PI * rngReal(s3), &sn, &cs);       // (as the draw windows: the same values for 0 <= x < 2 pi)
           A = sinPolar(mu);
         } else { leaveWindow(); rem = rngGet(rng); mu = 0.0; A = 0.0; sn = 0.0; cs = 1.0; }
         rem = rem * xsT[row * 6 + XS_IESCATTER];
@@ -1140,7 +1145,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
       // MT == 1 (elastic) cannot be selected for MG data (elasticScatter = 0): "Do nothing"
     }
     PR_MARK(7)
-    if (winPos <= WIN && winPos > 0) rng = W.st[winPos - 1];  // the stream position after this round's draws from the window
+    if (LW && winPos <= WIN && winPos > 0) rng = W.st[winPos - 1];  // the stream position after this round's draws from the window
     if (died) {
       a.nsites[hi] = nSite;
       a.hProd[hi] = sProd; a.hAbs[hi] = sAbs; a.hLeak[hi] = leaked ? 0.0 + w : 0.0; a.hScat[hi] = s_scat[threadIdx.x];
