@@ -143,8 +143,8 @@ namespace sbk {
 // rng: the lane's LCG state, advanced through sbh::rngGet.  log / sincos / the table functions are kept out of line: one
 // copy each in the kernel (instruction-cache footprint, see sb_track.cuh)
 #define SBK_RNG(rng) sbh::rngGet(rng)
-__device__ __noinline__ double kLog(double x) { return sbm::log(x); }
-__device__ __noinline__ void kSinCos(double x, double* s, double* c) { sbm::sincos(x, s, c); }
+__device__ __noinline__ double kLog(double x) { return -sbd::negLogHot(x); }
+__device__ __noinline__ void kSinCos(double x, double* s, double* c) { sbd::sincosHot(x, s, c); }
 __device__ __noinline__ double tapeTableAtNI(const Tape& T, int pos, double x, int* err, int* next) { return tapeTableAt(T, pos, x, err, next); }
 __device__ __noinline__ double tapeNuNI(const Tape& T, int pos, double E, int* err) { return tapeNu(T, pos, E, err); }
 

@@ -545,29 +545,6 @@ __device__ __noinline__ void buildDrawWindow(DrawWinT<WIN>* Wp, const uint64_t s
   __syncwarp();
 }
 
-// rotateVector for the loop of k_lone: the fast paths of rotateVectorSC (sb_device.cuh) in one straight block - the same operations
-// in the same order - and rotateVectorSC itself, out of line, for arguments outside them (so that the loop stays compact)
-__device__ __noinline__ double divCold(double a, double b) { return a / b; }
-__device__ __noinline__ double logCold(double x) { return sbm::log(x); }
-// -log(xi) as the draw windows compute it: the branch-free main path, the special arguments out of line (the same values as sbm::log)
-__device__ __forceinline__ double negLogHot(const double xi) { bool rl; const double lg = sbm::log_main(xi, &rl); return rl ? -logCold(xi) : -lg; }
-__device__ __noinline__ void rotateVectorCold(double d[3], double mu, double sinPol, double cosPol, double A) { rotateVectorSC(d, mu, sinPol, cosPol, A); }
-__device__ __forceinline__ void rotateVectorHot(double& u0, double& u1, double& u2, const double mu, const double sinPol, const double cosPol, const double A) {
-  const double b2 = fmax(0.0, 1.0 - u2 * u2);
-  const double B = sqrtFast(b2), yB = rcpRefined(B);
-  const double t0 = A * (u0 * u2 * cosPol - u1 * sinPol), t1 = A * (u1 * u2 * cosPol + u0 * sinPol);
-  const double q0 = divBy(t0, B, yB), q1 = divBy(t1, B, yB);
-  const double n0 = mu * u0 + q0, n1 = mu * u1 + q1, n2 = mu * u2 - A * B * cosPol;
-  const double nn = n0 * n0 + n1 * n1 + n2 * n2;
-  const double nrm = sqrtFast(nn), yN = rcpRefined(nrm);
-  if (fastRange(b2) && B > 1E-8 && fastRange(t0) && fastRange(t1) && fastRange(nn) && fastRange(n0) && fastRange(n1) && fastRange(n2)) {
-    u0 = divBy(n0, nrm, yN); u1 = divBy(n1, nrm, yN); u2 = divBy(n2, nrm, yN);
-  } else {
-    double d[3] = {u0, u1, u2};
-    rotateVectorCold(d, mu, sinPol, cosPol, A);
-    u0 = d[0]; u1 = d[1]; u2 = d[2];
-  }
-}
 struct __align__(16) LoneRec {             // a history handed from k_histories to k_lone
   double r0, r1, r2, u0, u1, u2, w, w0, sProd, sAbs, sScat;
   unsigned long long rng;

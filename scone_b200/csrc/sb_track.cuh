@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
       if (mode == 1) {                                      // deltaTracking, one tentative flight
         trackXS = mgMajorant(M, T, G);
         double majorant_inv = 1.0 / trackXS;
-        double distance = -sbm::log(rngGet(rng)) * majorant_inv;
+        double distance = negLogHot(rngGet(rng)) * majorant_inv;
         geomTeleportCoords(M, T, c, distance);
         ++nSeg; ++hSeg;
         if (c.mat == SB_OUTSIDE_MAT) { leak = w; sLeak = sLeak + w; died = true; }
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories_track(const TrackArg
         if (sigmaTrack < tol) { dist = INF; invSigmaTrack = INF; sigmaT = 0.0; }
         else {
           invSigmaTrack = 1.0 / sigmaTrack;
-          dist = -sbm::log(rngGet(rng)) * invSigmaTrack;
+          dist = negLogHot(rngGet(rng)) * invSigmaTrack;
           sigmaT = (m == SB_VOID_MAT) ? 0.0 : mgRow(M, T, m, G)[XS_TOTAL] + 0.0;      // getTotalMatXS of a void region is 0
         }
         int event;
