@@ -178,6 +178,40 @@ def test_full_size_c5g7_invariants_and_statistics(orc):
     orc.orc_eigen_free(e); pp.close()
 
 
+@pytest.mark.parametrize("deck,pop,ninact,nact,opop,oact,kref,ktol", [
+    ("inf", 1000000, 5, 10, 20000, 40, 1.631452, 0.003),           # BASELINE configs[1]; k-inf analytic (Sood URRa-2-1-IN)
+    ("c5g7_3d", 1250000, 40, 8, 20000, 40, None, None),            # BASELINE configs[3], the share of one of eight GPUs (40 inactive cycles: the 3-D core converges slowly from a flat source)
+    ("ce_pin", 1000000, 4, 4, 8000, 25, None, None)])              # BASELINE configs[2] stand-in (bundled nuclides), surface tracking
+def test_full_size_configs_agree_with_the_libm_oracle(orc, deck, pop, ninact, nact, opop, oact, kref, ktol):
+    """The other BASELINE configurations at the population one GPU runs: k-eff of the engine within 3 combined standard deviations of the
+    oracle in libm mode (the reference's own arithmetic; smaller population, independent seed), the bank normalised to the population,
+    every site inside the geometry with a unit direction."""
+    ov = "pop %d; inactive %d; active %d; seed 2027;" % (pop, ninact, nact)
+    pp = scone_b200.EigenPhysicsPackage(DECK[deck], ov, device=0)
+    pp.generateInitialState()
+    pp.cycles(False, ninact)
+    for _ in range(nact):
+        res = pp.cycle(True)
+        assert res.n_start == pop and 0.3 * pop < res.n_sites < 3 * pop
+    bank = pp.bank()
+    r, d, w = bank[0], bank[1], bank[2]
+    assert len(w) == pop and np.all(w == 1.0)
+    np.testing.assert_allclose((d * d).sum(1), 1.0, rtol=1e-12)
+    k_gpu, s_gpu = pp.k, res.k_cum_std
+    e = orc.orc_eigen_load(DECK[deck].encode(), ("pop %d; inactive %d; active %d; seed 4243;" % (opop, max(ninact, 10), oact)).encode())
+    assert e, ol.err(orc)
+    assert orc.orc_eigen_run(e) == 0, ol.err(orc)
+    cs = np.zeros(5); cs2 = np.zeros(5); b = C.c_int()
+    orc.orc_eigen_tally(e, 3, ol.dp(cs), ol.dp(cs2), C.byref(b))
+    n = b.value
+    k_o = cs[4] / n
+    s_o = np.sqrt(max(cs2[4] / n / (n - 1) - k_o * k_o / (n - 1), 0.0))
+    assert abs(k_gpu - k_o) < 3.0 * np.sqrt(s_gpu ** 2 + s_o ** 2), (k_gpu, s_gpu, k_o, s_o)
+    if kref is not None:
+        assert abs(k_gpu - kref) < ktol
+    orc.orc_eigen_free(e); pp.close()
+
+
 def test_libm_oracle_against_engine_bank_overlap(orc):
     """How far the engine is from the reference's OWN arithmetic. The bit-exact tests above compare with the oracle in its
     "sbmath" mode (one shared log / sin / cos). Here the oracle calls glibc like SCONE does: a result that differs in the
