@@ -1186,8 +1186,10 @@ static int buildBlob(sb_engine* h) {
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(256)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
-      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
-      if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(sbh::k_lone<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::loneScratchBytes(128)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
+      CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 384, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(384)));
+      if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(sbh::k_lone<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::loneScratchBytes(128)));
+      if (h->useSmem) CUDA_OK(cudaFuncSetAttribute(sbh::k_lone<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::loneScratchBytes(128)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 448>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(448)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<true, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, hotB + sbh::histScratchBytes(512)));
       CUDA_OK(cudaFuncSetAttribute(sbh::k_histories<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbh::histScratchBytes(256)));
@@ -1623,13 +1625,13 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   { static long long* dProf = nullptr; if (!dProf) { cudaMalloc(&dProf, 8 * (36 * 148 * 384 + 12 * 148 * 16)); } cudaMemsetAsync(dProf, 0, 8 * (36 * 148 * 384 + 12 * 148 * 16), st); a.prof = dProf; h->dProfRounds = dProf; }
 #endif
   a.refillMin = h->refillMin; a.maxSegMin = h->maxSegMin; a.loneMode = h->loneMode; a.cellCache = h->cellCache; a.laneMask = h->laneMask;
-  // the last histories of every warp go on in k_lone (speculative batches; what they restate is multiScatterMG with P0 scattering).
+  // the last histories of every warp go on in k_lone (speculative batches; multiScatterMG and multiScatterP1MG).
   // A warp hands its histories over when it is down to T of them: as many as k_lone's warps (8 per SM) can take at once, counted over
   // the warps that will run (measured, profiles/README.md: T = 1 at 1e5 histories, 2 at 2e4, 8 at 2e3 per GPU)
   {
     const int warpsA = std::min(h->numSM * 12, (n + 31) / 32);
     int T = h->assist >= 0 ? h->assist : std::max(1, std::min(8, (int)(1.1 * 8 * h->numSM / std::max(1, warpsA))));
-    a.assist = (T > 0 && h->loneMode && !h->hot.isP1 && h->useSmem) ? std::min(T, 32) : 0;
+    a.assist = (T > 0 && h->loneMode && h->useSmem) ? std::min(T, 32) : 0;
   }
   a.loneQ = h->dLoneQ; a.loneCount = h->dLoneCtl; a.loneNext = h->dLoneCtl + 1; a.loneCap = h->loneCap;
   a.loneReady = h->dLoneReady; a.loneDone = h->dLoneCtl + 2; a.loneTag = ++h->loneTag;
@@ -1709,7 +1711,8 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
   } else
   {
     const int hotB = h->useSmem ? h->hot.bytes : 0;
-    if (h->useSmem && bps == 1 && threads == 384 && a.assist > 0) sbh::k_histories<true, 1, 384, false><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
+    if (h->useSmem && bps == 1 && threads == 384 && a.assist > 0 && !h->hot.isP1) sbh::k_histories<true, 1, 384, false, false><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
+    else if (h->useSmem && bps == 1 && threads == 384 && a.assist > 0) sbh::k_histories<true, 1, 384, false, true><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
     else if (h->useSmem && bps == 1 && threads == 384) sbh::k_histories<true, 1, 384><<<blocks, 384, hotB + sbh::histScratchBytes(384), st>>>(a);
     else if (h->useSmem && bps == 1 && threads == 448) sbh::k_histories<true, 1, 448><<<blocks, 448, hotB + sbh::histScratchBytes(448), st>>>(a);
     else if (h->useSmem && bps == 1 && threads == 512) sbh::k_histories<true, 1, 512><<<blocks, 512, hotB + sbh::histScratchBytes(512), st>>>(a);
@@ -1718,7 +1721,8 @@ static int cycleTransport(sb_engine* h, uint64_t rng_state, int history_offset, 
     else if (h->useSmem) sbh::k_histories<true, 2><<<blocks, 256, hotB + sbh::histScratchBytes(256), st>>>(a);
     else sbh::k_histories<false, 2><<<blocks, 256, sbh::histScratchBytes(256), st>>>(a);
     if (a.assist > 0) {                                            // the last histories of every warp, one warp each
-      pdlLaunchSmem(sbh::k_lone<128>, h->numSM * 2, 128, (size_t)(hotB + sbh::loneScratchBytes(128)), st, a);
+      if (h->hot.isP1) pdlLaunchSmem(sbh::k_lone<128, true>, h->numSM * 2, 128, (size_t)(hotB + sbh::loneScratchBytes(128)), st, a);
+      else pdlLaunchSmem(sbh::k_lone<128, false>, h->numSM * 2, 128, (size_t)(hotB + sbh::loneScratchBytes(128)), st, a);
       h->launches++;
     }
     pdlLaunch(k_finish_sites, gridFor(h, n, 128), 128, st, h->M, h->dBlob, raw, h->dCd, h->cap);     // the sites' directions and groups

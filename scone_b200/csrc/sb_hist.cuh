@@ -551,7 +551,7 @@ struct __align__(16) LoneRec {             // a history handed from k_histories 
   int G, mat, hi, nSite, hSeg, leaked, pad0, pad1;
 };
 static_assert(sizeof(LoneRec) == 128, "LoneRec layout");
-template <int WIN>
+template <int WIN, bool LEG>
 __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, DrawWinT<WIN>& W, SpecRec* const rec, const JumpTab* const jt,
                                             const LoneRec& in, const int owner, unsigned& nSeg, unsigned& nColl, unsigned& nScore, long long* prL) {
   const unsigned FULL = 0xffffffffu;
@@ -565,7 +565,7 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
   const double* const xsT = H.xsT; const double* const P0 = H.P0; const double* const prodT = H.prodT;
   const double* const majT = H.majT; const double* const majInvT = H.majInvT;
   const int* const p0First = H.p0First; const int* const fissileT = H.fissileT;
-  const int nG = H.nG; const bool active = H.active;
+  const int nG = H.nG; const bool active = H.active; constexpr bool legendre = LEG;    // (P1 data run the copy with multiScatterP1MG)
   double r0 = in.r0, r1 = in.r1, r2 = in.r2, u0 = in.u0, u1 = in.u1, u2 = in.u2, w = in.w, sProd = in.sProd, sAbs = in.sAbs;
   const double w0 = in.w0;
   uint64_t rng = in.rng;
@@ -598,7 +598,7 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
       bool ended = false, recorded = false;                        // ended: absorbed, leaked or lost; recorded: rec[nR] holds the history in front of round nR
       uint64_t sd = 0;                                             // the stream where it has left the window (many fission sites)
 #pragma unroll 1
-      for (int k = 0; k < K && !ended && p + 8 <= WIN; ++k) {      // a round in the window: flight 1, acceptance 1, channel 3, scattering 3
+      for (int k = 0; k < K && !ended && p + 9 <= WIN; ++k) {      // a round in the window: flight 1, acceptance 1, channel 3, scattering 3 (P1: 4)
         SpecRec& R = rec[k];
         if (!seq) {
           R.b0 = r0; R.b1 = r1; R.b2 = r2; R.u0 = u0; R.u1 = u1; R.u2 = u2; R.w = w;
@@ -669,8 +669,12 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
           p3 += 3 * nNew;
         }
         if (C == 2) {                                              // multiScatterMG%sampleOut, rotateVector, neutronMGstd inelastic
-          double rem, mu, A, sn, cs;
-          if (p3 + 3 <= WIN) { rem = W.xi[p3]; mu = 2.0 * W.xi[p3 + 1] - 1.0; A = W.A[p3 + 1]; sn = W.sn[p3 + 2]; cs = W.cs[p3 + 2]; }
+          double rem, mu = 0.0, A = 0.0, sn = 0.0, cs = 1.0;
+          const bool inWin = p3 + (legendre ? 4 : 3) <= WIN;       // the numbers of the scattering are in the window
+          int used = 3;
+          if (legendre) {                                          // multiScatterP1MG: G_out first, then mu from the P1 coefficient, then phi
+            if (inWin) rem = W.xi[p3]; else rem = rngGet(sd);
+          } else if (inWin) { rem = W.xi[p3]; mu = 2.0 * W.xi[p3 + 1] - 1.0; A = W.A[p3 + 1]; sn = W.sn[p3 + 2]; cs = W.cs[p3 + 2]; }
           else {                                                   // (many sites) the three numbers straight from the stream
             const uint64_t s1 = rngJump<1>(sd), s2 = rngJump<2>(sd), s3 = rngJump<3>(sd);
             rem = rngReal(s1); mu = 2.0 * rngReal(s2) - 1.0; sbm::sincos(TWO_PI * rngReal(s3), &sn, &cs); A = sinPolar(mu);
@@ -690,13 +694,36 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
             rem = e4;
           }
           if (Gout == 0) { fl |= SR_SAMPLING; Gout = G; if (seq) atomicMax(&a.cd->error, SB_ERR_SAMPLING); }
+          if (legendre) {                                          // sampleLegendre_P1 (legendrePoly_func.f90:35-93) on the window's numbers
+            const double P1v = H.P1[row * nG + (Gout - 1)];
+            if (inWin) {
+              const double P1_loc = fabs(P1v);
+              double threshold; int Low, Top;                      // 1 UNIFORM, 2 LIN, 3 DELTA
+              if (P1_loc < 1.0) { threshold = P1_loc; Top = 2; Low = 1; }
+              else { threshold = 0.5 * (P1_loc - 1.0); Top = 3; Low = 2; }
+              int q = p3 + 1;
+              const int exec = (W.xi[q] < threshold) ? Top : Low; ++q;
+              double xx;
+              if (exec == 1) { xx = 2.0 * W.xi[q] - 1.0; ++q; }
+              else if (exec == 2) { xx = 2.0 * sqrt(W.xi[q]) - 1.0; ++q; }
+              else xx = 1.0;
+              if (P1v < 0.0) xx = -xx;
+              mu = xx; sn = W.sn[q]; cs = W.cs[q]; ++q;
+              used = q - p3;
+            } else {
+              mu = sampleLegendreP1(P1v, sd);
+              sincosHot(TWO_PI * rngGet(sd), &sn, &cs);
+            }
+            A = sinPolar(mu);
+          }
+          if (!inWin) used = WIN + 1 - p3;                         // (the stream has left the window: p > WIN below)
           rotateVectorHot(u0, u1, u2, mu, sn, cs, A);
           const double w_mul = prodT[row * nG + (Gout - 1)];
           const double wPre = w;
           if (Gout != G || w_mul != 1.0) { G = Gout; majInv = majInvT[G - 1]; w = w * w_mul; }
           const double sc = fmax(w - wPre, 0.0);
           if (sc > 0.0) sScat += sc;
-          p = p3 + 3;
+          p = p3 + used;
         } else {
           p = p3;
           if (C == 3 || C == 4) { fl |= SR_DIED; ended = true; }  // capture / fission: the history ends (ABS_FATE)
@@ -822,7 +849,8 @@ __device__ __forceinline__ void stageHot(char* smem, const char* gsrc, int bytes
 
 // LW: the loop has the draw window of a history that is alone in its warp. The launches that hand their last histories to k_lone
 // (HistArgs::assist > 0) never have such a history and run the copy without it (fewer tests per draw, a smaller loop).
-template <bool SMEM, int BPS, int THREADS = 256, bool LW = true>
+// LEG: the loop has multiScatterP1MG; P0 data run the copy without it (k_lone<THREADS, LEG> likewise).
+template <bool SMEM, int BPS, int THREADS = 256, bool LW = true, bool LEG = true>
 __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constant__ HistArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
   constexpr int NW = THREADS / 32;
@@ -1070,7 +1098,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
         const int row = (mat - 1) * nG + (G - 1);
         const double* cdf = P0 + row * nG;
         double mu, A, sn, cs, rem;
-        const bool legendre = LW && a.L.isP1 != 0;          // (launches without LW are P0: HistArgs::assist)
+        const bool legendre = LEG && a.L.isP1 != 0;         // (LEG = false: a copy of the loop for P0 data without the P1 code)
         if (LW && winPos <= WIN - 3 && !legendre) {              // three numbers in the order of the reaction, all from the window
           rem = W.xi[winPos]; mu = 2.0 * W.xi[winPos + 1] - 1.0; A = W.A[winPos + 1]; sn = W.sn[winPos + 2]; cs = W.cs[winPos + 2];
           winPos += 3;
@@ -1152,7 +1180,7 @@ __global__ void __launch_bounds__(THREADS, BPS) k_histories(const __grid_constan
 // k_lone: the histories k_histories handed over, one warp each (loneHistory). Launched behind k_histories on the same stream
 // with programmatic dependent launch: the tables are staged while the last warps of k_histories finish.
 // ------------------------------------------------------------------------------------------------
-template <int THREADS>
+template <int THREADS, bool LEG>
 __global__ void __launch_bounds__(THREADS, 2) k_lone(const __grid_constant__ HistArgs a) {
   __shared__ __align__(8) uint64_t s_bar;
   constexpr int NW = THREADS / 32;
@@ -1196,7 +1224,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_lone(const __grid_constant__ His
 #pragma unroll
       for (int i = 0; i < (int)(sizeof(LoneRec) / 16); ++i) dst[i] = __ldcg(src + i);
     }
-    loneHistory<WIN_BIG>(a, H, s_win[threadIdx.x >> 5], s_rec + (threadIdx.x >> 5) * (SPEC_MAX + 1), s_jump, in, 0, nSeg, nColl, nScore, prL);
+    loneHistory<WIN_BIG, LEG>(a, H, s_win[threadIdx.x >> 5], s_rec + (threadIdx.x >> 5) * (SPEC_MAX + 1), s_jump, in, 0, nSeg, nColl, nScore, prL);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {

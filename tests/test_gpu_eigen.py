@@ -96,7 +96,7 @@ def test_host_buffer_cycle_equals_device_resident_cycle():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("deck,pop,extra", [("c5g7", 3000, ""), ("c5g7", 40000, ""), ("inf", 2000, ""), ("c5g7_3d", 3000, ""), ("can", 3000, " transportOperator { type transportOperatorDT; }")])
+@pytest.mark.parametrize("deck,pop,extra", [("c5g7", 3000, ""), ("c5g7", 40000, ""), ("inf", 2000, ""), ("slab", 3000, ""), ("c5g7_3d", 3000, ""), ("can", 3000, " transportOperator { type transportOperatorDT; }")])
 def test_history_kernel_options_follow_the_same_histories(deck, pop, extra):
     """The delta-tracking kernel runs a history that is alone in its warp from a draw window built by the idle lanes, resumes the
     geometry search from a cell cache, limits the lanes that refill, and hands the last histories of every warp to a second kernel that
