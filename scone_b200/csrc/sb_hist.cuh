@@ -576,7 +576,6 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
   int winPos = WIN + 1;                                      // (the window is built behind rng)
   int specK = 2;                                             // rounds run ahead at once (> 0) or geometry searches in their place (0)
   if (lane == owner) H.scat[threadIdx.x] = in.sScat;
-  {
   for (;;) {
     // ---- the draw window: the next WIN numbers of the history's stream, four per lane ----
     if (__shfl_sync(FULL, winPos, owner) > WIN - 32) {
@@ -793,7 +792,6 @@ __device__ __forceinline__ void loneHistory(const HistArgs& a, const HotCtx& H, 
 #endif
     }
     if (!__shfl_sync(FULL, (int)alive, owner)) break;
-  }
   }
   if (lane == owner) {                                       // the scores of the history
     a.nsites[hi] = nSite;
